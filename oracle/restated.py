@@ -1,0 +1,513 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of FlowConductor's element-wise bijection hot path.
+
+This file is the parity ORACLE for the sm_100a kernels in `flowconductor_b200/csrc`.  It is never
+imported by the product package; only `tests/`, `__graft_entry__.smoke()` and the CPU-baseline /
+`--impl reference` legs of `bench.py` may use it.
+
+It restates, in plain CPU PyTorch (dtype-generic: fp32 to mirror the reference, fp64 as ground
+truth, autograd-capable for gradient checks), the algorithms of the reference files listed in
+SURVEY.md §8(a).  Every function cites the reference file:line it follows (paths relative to
+/root/reference).  The operation ORDER of the reference is kept on purpose (theta from knot
+differences, log(num) - 2 log(den), root = 2c / (-b - sqrt(disc)), softmax -> cumsum -> rescale ->
+forced end knots -> re-derived widths), because fp32 parity depends on it.
+
+Parity is PINNED: `tests/test_oracle_golden.py` checks this file against golden vectors produced
+by the unmodified reference (`oracle/make_golden.py`, run in the build container where
+/root/reference is importable) and, when the reference tree is present, against the live reference.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+DEFAULT_MIN_BIN_WIDTH = 1e-3  # flowcon/transforms/splines/rational_quadratic.py:8
+DEFAULT_MIN_BIN_HEIGHT = 1e-3  # :9
+DEFAULT_MIN_DERIVATIVE = 1e-3  # :10
+
+
+class InputOutsideDomain(Exception):
+    """flowcon/transforms/base.py:16-19."""
+
+
+# --------------------------------------------------------------------------------------------
+# a3 / a4 helpers
+# --------------------------------------------------------------------------------------------
+def bin_index(knots, x, eps=1e-6):
+    """flowcon/utils/torchutils.py:147-149 (`searchsorted`): bump the LAST knot by eps, then count
+    knots <= x and subtract one.  The reference bumps in place; the bumped knot is never gathered,
+    so a copy is equivalent."""
+    bumped = knots.clone()
+    bumped[..., -1] += eps
+    return torch.sum(x[..., None] >= bumped, dim=-1) - 1
+
+
+def sum_except_batch(x, num_batch_dims=1):
+    """flowcon/utils/torchutils.py:25-30."""
+    dims = list(range(num_batch_dims, x.dim()))
+    return torch.sum(x, dim=dims) if dims else x
+
+
+# --------------------------------------------------------------------------------------------
+# a2: rational_quadratic_spline  (flowcon/transforms/splines/rational_quadratic.py:66-181)
+# --------------------------------------------------------------------------------------------
+def _knots(unnormalized, lo, hi, min_size):
+    """:91-98 (widths) and :106-113 (heights): softmax, floor, cumsum, pad, rescale, force the two
+    end knots, re-derive the bin sizes from knot differences."""
+    num_bins = unnormalized.shape[-1]
+    sizes = F.softmax(unnormalized, dim=-1)
+    sizes = min_size + (1 - min_size * num_bins) * sizes
+    cum = torch.cumsum(sizes, dim=-1)
+    cum = F.pad(cum, pad=(1, 0), mode="constant", value=0.0)
+    cum = (hi - lo) * cum + lo
+    cum[..., 0] = lo
+    cum[..., -1] = hi
+    sizes = cum[..., 1:] - cum[..., :-1]
+    return cum, sizes
+
+
+def rational_quadratic_spline(
+    inputs,
+    unnormalized_widths,
+    unnormalized_heights,
+    unnormalized_derivatives,
+    inverse=False,
+    left=0.0,
+    right=1.0,
+    bottom=0.0,
+    top=1.0,
+    min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+    min_bin_height=DEFAULT_MIN_BIN_HEIGHT,
+    min_derivative=DEFAULT_MIN_DERIVATIVE,
+    enable_identity_init=False,
+    check_domain=True,
+):
+    """Monotone rational-quadratic spline on [left,right] -> [bottom,top]; returns (outputs,
+    per-element logabsdet).  rational_quadratic.py:66-181."""
+    if check_domain and inputs.numel() > 0:
+        if torch.min(inputs) < left or torch.max(inputs) > right:  # :81-82
+            raise InputOutsideDomain()
+    num_bins = unnormalized_widths.shape[-1]
+    if min_bin_width * num_bins > 1.0:  # :86-89
+        raise ValueError("Minimal bin width too large for the number of bins")
+    if min_bin_height * num_bins > 1.0:
+        raise ValueError("Minimal bin height too large for the number of bins")
+
+    cumwidths, widths = _knots(unnormalized_widths, left, right, min_bin_width)
+    beta = math.log(2) / (1 - min_derivative) if enable_identity_init else 1  # :100-103
+    derivatives = min_derivative + F.softplus(unnormalized_derivatives, beta=beta)  # :104
+    cumheights, heights = _knots(unnormalized_heights, bottom, top, min_bin_height)
+
+    k = bin_index(cumheights if inverse else cumwidths, inputs)[..., None]  # :115-118
+
+    def pick(t):
+        return t.gather(-1, k)[..., 0]
+
+    cw, w = pick(cumwidths), pick(widths)  # :120-121
+    ch = pick(cumheights)  # :123
+    delta = pick(heights / widths)  # :124-125
+    d0 = pick(derivatives)  # :127
+    d1 = pick(derivatives[..., 1:])  # :128
+    h = pick(heights)  # :130
+
+    if inverse:  # :132-160
+        u = inputs - ch
+        s = d0 + d1 - 2 * delta
+        a = u * s + h * (delta - d0)
+        b = h * d0 - u * s
+        c = -delta * u
+        discriminant = b.pow(2) - 4 * a * c
+        assert (discriminant >= 0).all()  # :142
+        root = (2 * c) / (-b - torch.sqrt(discriminant))
+        outputs = root * w + cw
+        t1mt = root * (1 - root)
+        denominator = delta + s * t1mt
+        numerator = delta.pow(2) * (d1 * root.pow(2) + 2 * delta * t1mt + d0 * (1 - root).pow(2))
+        logabsdet = torch.log(numerator) - 2 * torch.log(denominator)
+        return outputs, -logabsdet
+    theta = (inputs - cw) / w  # :162
+    t1mt = theta * (1 - theta)
+    numerator = h * (delta * theta.pow(2) + d0 * t1mt)
+    denominator = delta + (d0 + d1 - 2 * delta) * t1mt
+    outputs = ch + numerator / denominator
+    dnum = delta.pow(2) * (d1 * theta.pow(2) + 2 * delta * t1mt + d0 * (1 - theta).pow(2))
+    logabsdet = torch.log(dnum) - 2 * torch.log(denominator)
+    return outputs, logabsdet
+
+
+# --------------------------------------------------------------------------------------------
+# a1: unconstrained_rational_quadratic_spline  (rational_quadratic.py:13-63)
+# --------------------------------------------------------------------------------------------
+def unconstrained_rational_quadratic_spline(
+    inputs,
+    unnormalized_widths,
+    unnormalized_heights,
+    unnormalized_derivatives,
+    inverse=False,
+    tails="linear",
+    tail_bound=1.0,
+    min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+    min_bin_height=DEFAULT_MIN_BIN_HEIGHT,
+    min_derivative=DEFAULT_MIN_DERIVATIVE,
+    enable_identity_init=False,
+):
+    """Linear-tail wrapper.  The reference gathers the inside elements with a boolean mask, calls
+    the spline on them and scatters back (:43-61); per element that is the same as evaluating the
+    spline everywhere on a clamped copy and selecting, which is what is done here (no data-dependent
+    shapes, identical arithmetic on every inside element)."""
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))  # :41
+    inside = (inputs >= -tail_bound) & (inputs <= tail_bound)  # :26, both ends inclusive
+    derivs = F.pad(unnormalized_derivatives, pad=(1, 1))  # :33
+    constant = math.log(math.exp(1 - min_derivative) - 1)  # :34
+    derivs[..., 0] = constant
+    derivs[..., -1] = constant
+    safe = torch.where(inside, inputs, torch.zeros_like(inputs))
+    y_in, lad_in = rational_quadratic_spline(
+        safe,
+        unnormalized_widths,
+        unnormalized_heights,
+        derivs,
+        inverse=inverse,
+        left=-tail_bound,
+        right=tail_bound,
+        bottom=-tail_bound,
+        top=tail_bound,
+        min_bin_width=min_bin_width,
+        min_bin_height=min_bin_height,
+        min_derivative=min_derivative,
+        enable_identity_init=enable_identity_init,
+        check_domain=False,
+    )
+    outputs = torch.where(inside, y_in, inputs)  # :38
+    logabsdet = torch.where(inside, lad_in, torch.zeros_like(lad_in))  # :39
+    return outputs, logabsdet
+
+
+def split_rq_params(params, num_bins, wh_divisor=None):
+    """flowcon/transforms/coupling.py:549-556 / autoregressive.py:585-591: per feature
+    [w_0..w_{K-1} ; h_0..h_{K-1} ; d...]; widths and heights divided by sqrt(hidden) iff the
+    conditioner exposes `.hidden_features` (ResidualNet yes, transforms.made.MADE no)."""
+    uw = params[..., :num_bins]
+    uh = params[..., num_bins : 2 * num_bins]
+    ud = params[..., 2 * num_bins :]
+    if wh_divisor is not None:
+        uw = uw / wh_divisor
+        uh = uh / wh_divisor
+    return uw, uh, ud
+
+
+def rq_elementwise(inputs, params, num_bins, tails, tail_bound, inverse, wh_divisor, identity_init,
+                   min_bin_width=DEFAULT_MIN_BIN_WIDTH, min_bin_height=DEFAULT_MIN_BIN_HEIGHT,
+                   min_derivative=DEFAULT_MIN_DERIVATIVE, constrained_bound=None):
+    """Shared body of coupling.py:549-582 (`_piecewise_cdf`), autoregressive.py:578-615 and
+    conditional.py:700-741: view params [B, D_t, P], slice, optional scaling, dispatch on tails.
+    `constrained_bound`: None -> [0,1] (coupling, tails=None); 1.2 -> [-1.2,1.2] (AR/conditional)."""
+    b, d = inputs.shape
+    params = params.reshape(b, d, -1)
+    uw, uh, ud = split_rq_params(params, num_bins, wh_divisor)
+    kw = dict(inverse=inverse, min_bin_width=min_bin_width, min_bin_height=min_bin_height,
+              min_derivative=min_derivative, enable_identity_init=identity_init)
+    if tails is None:
+        if constrained_bound is not None:
+            c = constrained_bound
+            kw.update(left=-c, right=c, bottom=-c, top=c)
+        y, lad = rational_quadratic_spline(inputs, uw, uh, ud, **kw)
+    else:
+        y, lad = unconstrained_rational_quadratic_spline(inputs, uw, uh, ud, tails=tails,
+                                                         tail_bound=tail_bound, **kw)
+    return y, sum_except_batch(lad)  # coupling.py:293
+
+
+# --------------------------------------------------------------------------------------------
+# a7 / a9: affine element-wise transforms
+# --------------------------------------------------------------------------------------------
+def affine_scale(unconstrained, activation):
+    """'sigmoid2': coupling.py:224 default; 'softplus_clamp3': coupling.py:225 general;
+    'softplus_eps': autoregressive.py:102 (MAF, epsilon 1e-3 from :91)."""
+    if activation == "sigmoid2":
+        return torch.sigmoid(unconstrained + 2) + 1e-3
+    if activation == "softplus_clamp3":
+        return (F.softplus(unconstrained) + 1e-3).clamp(0, 3)
+    if activation == "softplus_eps":
+        return F.softplus(unconstrained) + 1e-3
+    raise ValueError(activation)
+
+
+def affine_elementwise(inputs, params, layout, activation, inverse):
+    """coupling.py:234-252 (layout 'blocked': params[:, :D_t] = shift, params[:, D_t:] = raw scale)
+    and autoregressive.py:97-129 (layout 'interleaved': view [B,D,2], [...,0] raw scale, [...,1]
+    shift)."""
+    b, d = inputs.shape
+    if layout == "blocked":
+        shift, raw = params[:, :d], params[:, d:]
+    elif layout == "interleaved":
+        p = params.reshape(b, d, 2)
+        raw, shift = p[..., 0], p[..., 1]
+    else:
+        raise ValueError(layout)
+    scale = affine_scale(raw, activation)
+    log_scale = torch.log(scale)
+    if inverse:
+        return (inputs - shift) / scale, -sum_except_batch(log_scale)
+    return inputs * scale + shift, sum_except_batch(log_scale)
+
+
+# --------------------------------------------------------------------------------------------
+# a11 / a12: sum of sigmoids + extended softplus
+# --------------------------------------------------------------------------------------------
+SOS_SCALE_MIN = 0.1  # flowcon/transforms/adaptive_sigmoids.py:22
+SOS_SCALE_MAX = 10.0  # :23
+SOS_SHIFT_MAX = 10  # :24
+SOS_EPS = 1e-6  # :69
+
+
+def sos_forward_elementwise(inputs, raw_params, n_sigmoids):
+    """adaptive_sigmoids.py:111-142 with raw params [B, D, 3n+1] split as :92, and
+    ExtendedSoftplus flowcon/transforms/nonlinearities.py:519-552.  Returns (outputs [B,D],
+    per-element log-derivative [B,D])."""
+    n = n_sigmoids
+    shift_raw, logscale_raw, softmax_raw, esp_raw = torch.split(raw_params, [n, n, n, 1], dim=-1)
+    # get_params :132-142  (log_scale_postact == 0 -> exp() == 1, :67)
+    weights = F.softmax(softmax_raw, dim=-1) + SOS_EPS
+    weights = weights / weights.sum(-1).unsqueeze(-1)
+    weights = math.exp(0.0) * weights
+    scale = torch.sigmoid(logscale_raw) * (SOS_SCALE_MAX - SOS_SCALE_MIN) + SOS_SCALE_MIN
+    shift = torch.tanh(shift_raw) * SOS_SHIFT_MAX
+    # sum_of_sigmoids :120-130
+    pre = scale * (inputs.unsqueeze(-1) - shift)
+    sig = weights * torch.sigmoid(pre)
+    log_jac = torch.log(weights) + torch.log(scale) + (pre - 2 * F.softplus(pre))  # :108-109
+    y_sig = sig.sum(-1) / weights.sum(-1)
+    logj_sig = torch.logsumexp(log_jac, -1)
+    # ExtendedSoftplus.forward nonlinearities.py:543-552
+    s = F.softplus(esp_raw.reshape(inputs.shape)) + 1e-1  # get_shift :519-520
+    y_esp = F.softplus(inputs - s) + (-F.softplus(-(inputs + s)))
+    logj_esp = torch.logaddexp(-torch.logaddexp(s, inputs) + inputs, -F.softplus(s + inputs))
+    return y_sig + y_esp, torch.logaddexp(logj_sig, logj_esp)  # :114-116
+
+
+def sos_forward(inputs, params, n_sigmoids, offset=0.0):
+    """SumOfSigmoids.forward + wrapper offset (autoregressive.py:309 subtracts 0.5; conditional.py
+    :774-780 does not).  Returns (outputs, logabsdet[B])."""
+    b, d = inputs.shape
+    y, logj = sos_forward_elementwise(inputs, params.reshape(b, d, 3 * n_sigmoids + 1), n_sigmoids)
+    return y + offset, logj.sum(-1)
+
+
+def sos_inverse(z, params, n_sigmoids, offset=0.0, num_iterations=50, lim=120.0, ratio_multiplier=1.5,
+                atol=1e-7):
+    """MonotonicTransform.inverse -> newton_inverse -> bisection_inverse,
+    flowcon/transforms/no_analytic_inv/base.py:23-83,100-103, with SoS settings
+    (adaptive_sigmoids.py:26,57: 50 iterations, lim 120).  `offset` as in sos_forward: the wrapper
+    adds 0.5 to the inputs before inverting (autoregressive.py:313)."""
+    b, d = z.shape
+    raw = params.reshape(b, d, 3 * n_sigmoids + 1)
+    z = z - offset
+
+    def fwd(x):
+        return sos_forward_elementwise(x, raw, n_sigmoids)
+
+    def diffs(z_max, z_min):  # calc_diffs :85-92
+        dmax = z - z_max
+        imax = torch.argmax(dmax)
+        dmin = z - z_min
+        imin = torch.argmin(dmin)
+        return imax, imin, dmax.flatten()[imax], dmin.flatten()[imin]
+
+    with torch.no_grad():
+        x_max = torch.ones_like(z) * lim
+        x_min = -torch.ones_like(z) * lim
+        z_max, _ = fwd(x_max)
+        z_min, _ = fwd(x_min)
+        imax, imin, maxdiff, mindiff = diffs(z_max, z_min)
+        while maxdiff > 0:  # :48-52
+            ratio = (maxdiff + z_max.flatten()[imax]) / z_max.flatten()[imax]
+            x_max = x_max * ratio_multiplier * ratio
+            z_max, _ = fwd(x_max)
+            imax, imin, maxdiff, mindiff = diffs(z_max, z_min)
+        x_max = x_max + 1
+        while mindiff < 0:  # :55-59
+            ratio = (mindiff + z_min.flatten()[imin]) / z_min.flatten()[imin]
+            x_min = x_min * ratio_multiplier * ratio
+            z_min, _ = fwd(x_min)
+            imax, imin, maxdiff, mindiff = diffs(z_max, z_min)
+        x_min = x_min - 1
+        i = 0
+        x_mid = (x_max + x_min) / 2
+        while i < num_iterations and (x_mid - z).abs().max() > atol:  # :67 (guard compares x to z: quirk)
+            x_mid = (x_max + x_min) / 2
+            z_mid, _ = fwd(x_mid)
+            go_left = (z_mid > z).to(z.dtype)
+            go_right = (z_mid < z).to(z.dtype)
+            equal = 1 - (go_left + go_right)
+            x_max = go_left * x_mid + go_right * x_max + equal * x_mid
+            x_min = go_right * x_mid + go_left * x_min + equal * x_mid
+            i += 1
+        x = (x_max + x_min) / 2
+    # two Newton steps, derivative through autograd, df + 1e-7  (:27-33)
+    with torch.enable_grad():
+        guess = x.detach().requires_grad_(True)
+        for _ in range(2):
+            f = fwd(guess)[0] - z
+            df = torch.autograd.grad(f, [guess], grad_outputs=torch.ones_like(f), create_graph=True)[0]
+            guess = guess - f / (df + 1e-7)
+    _, logj = fwd(guess)
+    return guess, -logj.sum(-1)
+
+
+# --------------------------------------------------------------------------------------------
+# a15: conditioner networks evaluated from a state_dict (keys as in the reference modules)
+# --------------------------------------------------------------------------------------------
+def residual_net(state, prefix, inputs, context=None, num_blocks=2):
+    """flowcon/nn/nets/resnet.py:55-100 (ResidualNet) with ResidualBlock :9-52, relu activation,
+    no dropout / batch norm (the configurations on the path)."""
+    def lin(name, t):
+        return F.linear(t, state[prefix + name + ".weight"], state[prefix + name + ".bias"])
+
+    temps = lin("initial_layer", inputs if context is None else torch.cat((inputs, context), dim=1))
+    for i in range(num_blocks):
+        blk = "blocks.{}.".format(i)
+        t = F.relu(temps)
+        t = lin(blk + "linear_layers.0", t)
+        t = F.relu(t)
+        t = lin(blk + "linear_layers.1", t)
+        if context is not None:
+            t = F.glu(torch.cat((t, lin(blk + "context_layer", context)), dim=1), dim=1)
+        temps = temps + t
+    return lin("final_layer", temps)
+
+
+def made_net(state, prefix, inputs, context=None, num_blocks=2):
+    """flowcon/transforms/made.py:274-283 (MADE.forward, residual blocks :190-202) with
+    MaskedLinear.forward :71-72 = F.linear(x, weight * mask, bias)."""
+    def mlin(name, t):
+        return F.linear(t, state[prefix + name + ".weight"] * state[prefix + name + ".mask"],
+                        state[prefix + name + ".bias"])
+
+    def lin(name, t):
+        return F.linear(t, state[prefix + name + ".weight"], state[prefix + name + ".bias"])
+
+    temps = mlin("initial_layer", inputs)
+    if context is not None:
+        temps = temps + F.relu(lin("context_layer", context))
+    for i in range(num_blocks):
+        blk = "blocks.{}.".format(i)
+        t = F.relu(temps)
+        t = mlin(blk + "linear_layers.0", t)
+        if context is not None:
+            t = t + lin(blk + "context_layer", context)
+        t = F.relu(t)
+        t = mlin(blk + "linear_layers.1", t)
+        temps = temps + t
+    return mlin("final_layer", temps)
+
+
+# --------------------------------------------------------------------------------------------
+# a5-a10, a14, a16: layers, composition, base density — driven by a plain-data layer spec
+# --------------------------------------------------------------------------------------------
+def _coupling(state, spec, inputs, context, inverse, elementwise):
+    """CouplingTransform.forward/inverse, flowcon/transforms/coupling.py:73-130 (no unconditional
+    transform on the path)."""
+    p = spec["prefix"]
+    idf = state[p + "identity_features"]
+    trf = state[p + "transform_features"]
+    identity = inputs[:, idf]
+    transform = inputs[:, trf]
+    params = residual_net(state, p + "transform_net.", identity, context, spec.get("num_blocks", 2))
+    transform, lad = elementwise(transform, params)
+    outputs = torch.empty_like(inputs)
+    outputs[:, idf] = identity
+    outputs[:, trf] = transform
+    return outputs, lad
+
+
+def _autoregressive(state, spec, inputs, context, inverse, elementwise):
+    """AutoregressiveTransform.forward/inverse, autoregressive.py:39-53 (inverse = D passes)."""
+    p = spec["prefix"] + "autoregressive_net."
+    nb = spec.get("num_blocks", 2)
+    if not inverse:
+        return elementwise(inputs, made_net(state, p, inputs, context, nb))
+    outputs = torch.zeros_like(inputs)
+    lad = None
+    for _ in range(inputs.shape[1]):
+        outputs, lad = elementwise(inputs, made_net(state, p, outputs, context, nb))
+    return outputs, lad
+
+
+def apply_layer(state, spec, inputs, context=None, inverse=False):
+    """One bijection layer in the direction asked; returns (outputs, logabsdet[B])."""
+    kind = spec["kind"]
+    p = spec["prefix"]
+    if kind == "permutation":  # flowcon/transforms/permutations.py:27-46
+        perm = state[p + "_permutation"]
+        if inverse:
+            perm = torch.argsort(perm)
+        return torch.index_select(inputs, 1, perm), inputs.new_zeros(inputs.shape[0])
+    if kind in ("prq_coupling", "maf_prq", "cond_prq"):
+        hidden = spec["hidden_features"]
+        # 1/sqrt(H) scaling only where the conditioner exposes .hidden_features (coupling.py:554,
+        # conditional.py:711); transforms.made.MADE does not (autoregressive.py:589)
+        divisor = None if kind == "maf_prq" else math.sqrt(hidden)
+        ident = kind != "prq_coupling"  # autoregressive.py:611, conditional.py:733
+        bound = None if kind == "prq_coupling" else 1.2  # autoregressive.py:595, conditional.py:717
+
+        def ew(x, params):
+            return rq_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0),
+                                  inverse, divisor, ident, constrained_bound=bound)
+    elif kind == "affine_coupling":
+        def ew(x, params):
+            return affine_elementwise(x, params, "blocked", spec.get("scale_activation", "sigmoid2"), inverse)
+    elif kind == "maf_affine":
+        def ew(x, params):
+            return affine_elementwise(x, params, "interleaved", "softplus_eps", inverse)
+    elif kind in ("maf_sos", "cond_sos"):
+        off = -0.5 if kind == "maf_sos" else 0.0  # autoregressive.py:309,313
+
+        def ew(x, params):
+            if inverse:
+                return sos_inverse(x, params, spec["n_sigmoids"], offset=off)
+            return sos_forward(x, params, spec["n_sigmoids"], offset=off)
+    else:
+        raise ValueError(kind)
+
+    if kind.endswith("_coupling"):
+        return _coupling(state, spec, inputs, context, inverse, ew)
+    if kind.startswith("maf_"):
+        return _autoregressive(state, spec, inputs, context, inverse, ew)
+    # ConditionalTransform.forward/inverse, flowcon/transforms/conditional.py:74-86
+    if context is None:
+        raise TypeError("Conditional transforms require a context.")
+    params = residual_net(state, p + "conditional_net.", context, None, spec.get("num_blocks", 2))
+    return ew(inputs, params)
+
+
+def composite(state, specs, inputs, context=None, inverse=False):
+    """CompositeTransform._cascade, flowcon/transforms/base.py:44-60 (inverse walks the layers in
+    reverse order)."""
+    total = inputs.new_zeros(inputs.shape[0])
+    outputs = inputs
+    for spec in (reversed(specs) if inverse else specs):
+        outputs, lad = apply_layer(state, spec, outputs, context, inverse)
+        total = total + lad
+    return outputs, total
+
+
+def standard_normal_log_prob(inputs):
+    """StandardNormal._log_prob, flowcon/distributions/normal.py:23-33 (log_z is a 0-dim fp64
+    buffer; subtracting it does not promote an fp32 result)."""
+    d = inputs.shape[1]
+    log_z = torch.tensor(0.5 * d * math.log(2 * math.pi), dtype=torch.float64)
+    return -0.5 * sum_except_batch(inputs ** 2) - log_z.to(inputs.dtype)
+
+
+def flow_log_prob(state, specs, inputs, context=None):
+    """Flow._log_prob, flowcon/flows/base.py:41-48."""
+    noise, lad = composite(state, specs, inputs, context, inverse=False)
+    return standard_normal_log_prob(noise) + lad
+
+
+def flow_sample_from_noise(state, specs, noise, context=None):
+    """Flow._sample, flowcon/flows/base.py:50-74, with the base-distribution draw factored out so
+    the same noise can be fed to both implementations."""
+    samples, _ = composite(state, specs, noise, context, inverse=True)
+    return samples
