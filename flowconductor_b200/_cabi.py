@@ -1,0 +1,159 @@
+"""ctypes binding of libflowcon_b200.so (see include/flowcon_b200.h).
+
+Plain pointers and sizes only: tensors are passed as `data_ptr()`, the stream as the raw cudaStream_t of
+torch's current stream.  There is NO fallback: if the library has not been built, or a tensor is not a
+CUDA fp32 tensor, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflowcon_b200.so")
+
+FC_OK = 0
+ERRORS = {-1: "invalid argument", -2: "unsupported configuration", -3: "CUDA launch error"}
+STATUS_INPUT_OUTSIDE_DOMAIN = 1
+STATUS_NEGATIVE_DISCRIMINANT = 2
+TAILS_NONE, TAILS_LINEAR = 0, 1
+AFFINE_BLOCKED, AFFINE_INTERLEAVED = 0, 1
+SCALE_SIGMOID2, SCALE_SOFTPLUS_CLAMP3, SCALE_SOFTPLUS_EPS = 0, 1, 2
+
+EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
+           "fc_sos_backward", "fc_stdnormal_log_prob", "fc_version", "fc_built_for_sm"]
+
+
+class RqsConfig(ctypes.Structure):
+    """struct fc_rqs_config"""
+    _fields_ = [("num_bins", ctypes.c_int32), ("tails", ctypes.c_int32), ("identity_init", ctypes.c_int32),
+                ("inverse", ctypes.c_int32), ("left", ctypes.c_float), ("right", ctypes.c_float),
+                ("bottom", ctypes.c_float), ("top", ctypes.c_float), ("min_bin_width", ctypes.c_float),
+                ("min_bin_height", ctypes.c_float), ("min_derivative", ctypes.c_float), ("wh_scale", ctypes.c_float)]
+
+
+class Cols(ctypes.Structure):
+    """struct fc_cols"""
+    _fields_ = [("idx", ctypes.c_void_p), ("n", ctypes.c_int32)]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the library once; raise loudly when it is missing (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                "libflowcon_b200.so not found at {}. Build it with `python -m flowconductor_b200.build` "
+                "(needs nvcc; targets sm_100a). flowconductor_b200 has no CPU or eager fallback.".format(LIB_PATH))
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+        L.fc_rqs_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, Cols, Cols,
+                                   ctypes.POINTER(RqsConfig), vp, vp]
+        L.fc_rqs_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols,
+                                      ctypes.POINTER(RqsConfig), vp]
+        L.fc_affine_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, Cols, Cols, i32, i32, i32, vp]
+        L.fc_affine_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols, i32,
+                                         i32, i32, vp]
+        L.fc_sos_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, i32, f32, i32, i32, f32, vp]
+        L.fc_sos_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, i32, vp]
+        L.fc_stdnormal_log_prob.argtypes = [vp, i64, vp, vp, i64, i32, vp]
+        L.fc_version.restype = ctypes.c_char_p
+        for name in EXPORTS:
+            if name not in ("fc_version",):
+                getattr(L, name).restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != FC_OK:
+        raise RuntimeError("{} failed: {} ({})".format(what, ERRORS.get(rc, "unknown error"), rc))
+
+
+def require_cuda_f32(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "{} must be a CUDA tensor: flowconductor_b200 runs only on the GPU (no CPU fallback)".format(name))
+    if t.dtype != torch.float32:
+        raise RuntimeError("{} must be float32 (got {})".format(name, t.dtype))
+    return t
+
+
+def rows(t):
+    """(pointer, row stride in elements) of a 2-D tensor whose last dim is dense."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t, t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def cols(t):
+    if t is None or t.numel() == 0:
+        return Cols(None, 0)
+    assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous()
+    return Cols(t.data_ptr(), t.numel())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# launch accounting: every C-ABI kernel launch goes through `launch(...)`
+# ------------------------------------------------------------------------------------------------
+class LaunchStats:
+    """Counts kernel launches and, when `timing` is on, brackets each one with CUDA events recorded on the
+    launching stream (bench.py uses this for `gpu_launches` and the per-kernel roofline)."""
+
+    def __init__(self):
+        self.counts = {}
+        self.timing = False
+        self.events = {}
+
+    def reset(self):
+        self.counts = {}
+        self.events = {}
+
+    def total(self):
+        return sum(self.counts.values())
+
+    def elapsed_ms(self, name):
+        """(number of timed launches, their summed device time in ms); call after a synchronize."""
+        pairs = self.events.get(name, [])
+        return len(pairs), sum(a.elapsed_time(b) for a, b in pairs)
+
+
+STATS = LaunchStats()
+
+
+class launch:
+    __slots__ = ("name", "device", "start")
+
+    def __init__(self, name, device):
+        self.name = name
+        self.device = device
+
+    def __enter__(self):
+        STATS.counts[self.name] = STATS.counts.get(self.name, 0) + 1
+        self.start = None
+        if STATS.timing:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(torch.cuda.current_stream(self.device))
+            STATS.events.setdefault(self.name, []).append((self.start, end))
+        return False

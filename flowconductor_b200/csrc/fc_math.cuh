@@ -1,0 +1,662 @@
+// fc_math.cuh — per-element arithmetic of the bijections, shared by every kernel in this directory.
+//
+// All functions are __host__ __device__ so that the exact statements the GPU executes can also be
+// compiled with g++ into a test-only shim (tests/hostmath) and checked against the oracle on a box
+// without a GPU.  The product never calls the host instantiation.
+//
+// Arithmetic follows the reference's operation order where fp32 parity depends on it (citations are
+// file:line under /root/reference):
+//   knots:   softmax -> min + (1-min*K)*p -> running sum -> (hi-lo)*cum + lo -> forced end knots ->
+//            bin sizes from knot differences          splines/rational_quadratic.py:91-98,106-113
+//   bin:     largest i with knot_i <= x  (== count(knots <= x) - 1 for sorted knots, last knot + 1e-6)
+//                                                      utils/torchutils.py:147-149
+//   forward: rational_quadratic.py:162-181     inverse: rational_quadratic.py:132-160
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/flowcon_b200.h"
+
+#if defined(__CUDACC__)
+#define FC_HD __host__ __device__ __forceinline__
+#else
+#define FC_HD inline
+#endif
+
+// Un-contracted fp32 primitives for the knot pipeline: eager PyTorch rounds after every op, and the bin
+// an input lands in depends on the knot bits.  (The closed forms below may use FMA: more accurate.)
+#if defined(__CUDA_ARCH__)
+#define FC_MUL(a, b) __fmul_rn((a), (b))
+#define FC_ADD(a, b) __fadd_rn((a), (b))
+#define FC_SUB(a, b) __fsub_rn((a), (b))
+#else
+#define FC_MUL(a, b) ((a) * (b))  // host shim is built with -ffp-contract=off
+#define FC_ADD(a, b) ((a) + (b))
+#define FC_SUB(a, b) ((a) - (b))
+#endif
+
+#define FC_MAX_BINS_GENERIC 64  // runtime-K instantiation keeps its arrays in local memory up to this
+
+namespace fc {
+
+// Device-side copy of fc_rqs_config plus host-precomputed constants.
+struct RqsParams {
+  int K, tails, identity_init, inverse;
+  float left, right, bottom, top;
+  float min_w, min_h, min_d, wh_scale;
+  float beta, inv_beta;  // softplus beta (rational_quadratic.py:100-103)
+  float pad_deriv;       // derivative at the two padded boundary knots, linear tails (:33-36 then :104)
+  float coef_w, coef_h;  // 1 - min*K (:92, :107)
+  int P;                 // params per feature
+};
+
+FC_HD float softplus_beta(float x, float beta, float inv_beta) {
+  // torch.nn.functional.softplus(x, beta, threshold=20)
+  const float bx = x * beta;
+  return bx > 20.f ? x : log1pf(expf(bx)) * inv_beta;
+}
+
+FC_HD float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+FC_HD float softplus1(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// derivative of softplus_beta w.r.t. x
+FC_HD float softplus_beta_grad(float x, float beta) {
+  const float bx = x * beta;
+  return bx > 20.f ? 1.f : sigmoidf_(bx);
+}
+
+// Host side: validate an fc_rqs_config and derive the constants the kernels use.
+inline int make_rqs_params(const fc_rqs_config* cfg, RqsParams& c) {
+  if (!cfg) return FC_ERR_INVALID_ARGUMENT;
+  if (cfg->num_bins < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (cfg->num_bins > FC_MAX_BINS_GENERIC) return FC_ERR_UNSUPPORTED;
+  if (cfg->tails != FC_TAILS_NONE && cfg->tails != FC_TAILS_LINEAR) return FC_ERR_INVALID_ARGUMENT;
+  // rational_quadratic.py:86-89 raises ValueError for these
+  if (cfg->min_bin_width * cfg->num_bins > 1.0f || cfg->min_bin_height * cfg->num_bins > 1.0f)
+    return FC_ERR_INVALID_ARGUMENT;
+  c.K = cfg->num_bins;
+  c.tails = cfg->tails;
+  c.identity_init = cfg->identity_init;
+  c.inverse = cfg->inverse;
+  c.left = cfg->left;
+  c.right = cfg->right;
+  c.bottom = cfg->bottom;
+  c.top = cfg->top;
+  c.min_w = cfg->min_bin_width;
+  c.min_h = cfg->min_bin_height;
+  c.min_d = cfg->min_derivative;
+  c.wh_scale = cfg->wh_scale;
+  const double beta = cfg->identity_init ? log(2.0) / (1.0 - (double)cfg->min_derivative) : 1.0;
+  c.beta = (float)beta;
+  c.inv_beta = (float)(1.0 / beta);
+  // rational_quadratic.py:34: constant = log(exp(1 - min_derivative) - 1), stored into an fp32 tensor
+  const float pad_raw = (float)log(exp(1.0 - (double)cfg->min_derivative) - 1.0);
+  c.pad_deriv = c.min_d + softplus_beta(pad_raw, c.beta, c.inv_beta);
+  // (1 - min * K) is evaluated in Python doubles in the reference, then multiplies an fp32 tensor
+  c.coef_w = (float)(1.0 - (double)cfg->min_bin_width * cfg->num_bins);
+  c.coef_h = (float)(1.0 - (double)cfg->min_bin_height * cfg->num_bins);
+  c.P = cfg->tails == FC_TAILS_LINEAR ? 3 * c.K - 1 : 3 * c.K + 1;
+  return FC_OK;
+}
+
+// derivative value at knot j (0..K).  `pd` points at the raw derivative block of this feature.
+FC_HD float knot_derivative(const RqsParams& c, int K, const float* pd, int j) {
+  float raw;
+  if (c.tails == FC_TAILS_LINEAR) {
+    if (j == 0 || j == K) return c.pad_deriv;
+    raw = pd[j - 1];
+  } else {
+    raw = pd[j];
+  }
+  return c.min_d + softplus_beta(raw, c.beta, c.inv_beta);
+}
+
+// softmax numerators e[i] = exp(scale*u[i] - max) and 1/sum.
+template <int KC>
+FC_HD float softmax_numerators(const float* u, int K, float scale, float* e) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < (KC ? KC : K); ++i) {
+    e[i] = u[i] * scale;
+    m = fmaxf(m, e[i]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < (KC ? KC : K); ++i) {
+    e[i] = expf(e[i] - m);
+    s += e[i];
+  }
+  return 1.f / s;
+}
+
+// Walk the knots built from softmax numerators e[] (see file header).  If `search`, find the bin of x:
+// k = largest i with knot_i <= x; otherwise use the given k.  Returns knot_k (lo_k) and knot_{k+1} (hi_k).
+template <int KC, bool kSearch>
+FC_HD void knot_scan(const float* e, float inv_sum, int K, float lo, float hi, float min_size, float coef,
+                     float x, int& k, float& lo_k, float& hi_k) {
+  const float span = hi - lo;
+  float cum = 0.f, prev = lo;
+  if (kSearch) k = 0;
+  lo_k = lo;
+  hi_k = hi;
+#pragma unroll
+  for (int i = 0; i < (KC ? KC : K); ++i) {
+    const float size = FC_ADD(min_size, FC_MUL(coef, FC_MUL(e[i], inv_sum)));
+    cum = FC_ADD(cum, size);
+    const float next = (i == K - 1) ? hi : FC_ADD(FC_MUL(span, cum), lo);
+    const bool take = kSearch ? (x >= prev) : (i == k);
+    if (take) {
+      if (kSearch) k = i;
+      lo_k = prev;
+      hi_k = next;
+    }
+    prev = next;
+  }
+}
+
+// Everything the closed forms need about the selected bin.
+struct RqsBin {
+  int k;
+  float cw, w;   // left width knot, bin width
+  float ch, h;   // bottom height knot, bin height
+  float delta, d0, d1;
+};
+
+// Shared front half of forward / inverse / backward: inside test, softmax, knots, bin, derivatives.
+// ew / eh receive the softmax numerators (needed again by the backward); inv_w / inv_h their 1/sum.
+template <int KC>
+FC_HD void rqs_locate(const RqsParams& c, int K, float x, const float* p, RqsBin& bin, float* ew, float* eh,
+                      float& inv_w, float& inv_h) {
+  inv_w = softmax_numerators<KC>(p, K, c.wh_scale, ew);
+  inv_h = softmax_numerators<KC>(p + K, K, c.wh_scale, eh);
+  float a, b;
+  if (!c.inverse) {
+    knot_scan<KC, true>(ew, inv_w, K, c.left, c.right, c.min_w, c.coef_w, x, bin.k, a, b);
+    bin.cw = a;
+    bin.w = FC_SUB(b, a);
+    knot_scan<KC, false>(eh, inv_h, K, c.bottom, c.top, c.min_h, c.coef_h, x, bin.k, a, b);
+    bin.ch = a;
+    bin.h = FC_SUB(b, a);
+  } else {
+    knot_scan<KC, true>(eh, inv_h, K, c.bottom, c.top, c.min_h, c.coef_h, x, bin.k, a, b);
+    bin.ch = a;
+    bin.h = FC_SUB(b, a);
+    knot_scan<KC, false>(ew, inv_w, K, c.left, c.right, c.min_w, c.coef_w, x, bin.k, a, b);
+    bin.cw = a;
+    bin.w = FC_SUB(b, a);
+  }
+  bin.delta = bin.h / bin.w;
+  const float* pd = p + 2 * K;
+  bin.d0 = knot_derivative(c, K, pd, bin.k);
+  bin.d1 = knot_derivative(c, K, pd, bin.k + 1);
+}
+
+// Domain handling shared by all entry points.  Returns true if the element takes the spline branch;
+// `xs` is the value fed to the spline (clamped into the domain when the reference would have raised).
+FC_HD bool rqs_domain(const RqsParams& c, float x, float& xs, unsigned& status) {
+  const float lo = c.inverse ? c.bottom : c.left;
+  const float hi = c.inverse ? c.top : c.right;
+  if (c.tails == FC_TAILS_LINEAR) {
+    const bool inside = (x >= lo) && (x <= hi);  // rational_quadratic.py:26 (both ends inclusive)
+    xs = inside ? x : 0.f;
+    return inside;
+  }
+  xs = x;
+  if (!(x >= lo && x <= hi)) {  // rational_quadratic.py:81-82 raises InputOutsideDomain
+    status |= FC_STATUS_INPUT_OUTSIDE_DOMAIN;
+    xs = fminf(fmaxf(x, lo), hi);
+    if (!(xs == xs)) xs = lo;
+  }
+  return true;
+}
+
+// Inverse closed form: root theta of the quadratic (rational_quadratic.py:132-146).
+FC_HD float rqs_inverse_root(const RqsBin& b, float x, unsigned& status) {
+  const float u = x - b.ch;
+  const float s = b.d0 + b.d1 - 2.f * b.delta;
+  const float qa = u * s + b.h * (b.delta - b.d0);
+  const float qb = b.h * b.d0 - u * s;
+  const float qc = -b.delta * u;
+  float disc = qb * qb - 4.f * qa * qc;
+  if (!(disc >= 0.f)) {
+    status |= FC_STATUS_NEGATIVE_DISCRIMINANT;
+    disc = 0.f;
+  }
+  return (2.f * qc) / (-qb - sqrtf(disc));
+}
+
+// log|dy/dx| of the forward spline at theta (rational_quadratic.py:148-158 / :173-179).
+FC_HD float rqs_logdet_at(const RqsBin& b, float theta, float& denominator) {
+  const float t1mt = theta * (1.f - theta);
+  denominator = b.delta + (b.d0 + b.d1 - 2.f * b.delta) * t1mt;
+  const float omt = 1.f - theta;
+  const float dnum = (b.delta * b.delta) * (b.d1 * (theta * theta) + 2.f * b.delta * t1mt + b.d0 * (omt * omt));
+  return logf(dnum) - 2.f * logf(denominator);
+}
+
+// One element, forward or inverse (c.inverse).  p -> this feature's P raw parameters.
+template <int KC>
+FC_HD void rqs_eval(const RqsParams& c, float x, const float* p, float& y, float& lad, unsigned& status) {
+  const int K = KC ? KC : c.K;
+  float xs;
+  if (!rqs_domain(c, x, xs, status)) {
+    y = x;  // rational_quadratic.py:38-39 linear tails: identity, zero log-det
+    lad = 0.f;
+    return;
+  }
+  float ew[KC ? KC : FC_MAX_BINS_GENERIC], eh[KC ? KC : FC_MAX_BINS_GENERIC];
+  float inv_w, inv_h;
+  RqsBin b;
+  rqs_locate<KC>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
+  float den;
+  if (c.inverse) {
+    const float root = rqs_inverse_root(b, xs, status);
+    y = root * b.w + b.cw;
+    lad = -rqs_logdet_at(b, root, den);
+  } else {
+    const float theta = (xs - b.cw) / b.w;
+    const float t1mt = theta * (1.f - theta);
+    const float num = b.h * (b.delta * (theta * theta) + b.d0 * t1mt);
+    lad = rqs_logdet_at(b, theta, den);
+    y = b.ch + num / den;
+  }
+}
+
+// Backward of rqs_eval for one element.  Upstream: gy = dL/dy, gl = dL/d(lad).  Writes dL/dx and the P
+// parameter gradients to gp[0..P-1] (zeros where the reference's autograd gives zero).  SURVEY.md App. B.
+//
+// Forward direction.  With a,b the width knots of the bin, cc,ee the height knots:
+//   W=b-a, H=ee-cc, theta=(x-a)/W, delta=H/W, s=d0+d1-2delta, t=theta(1-theta),
+//   N=H(delta theta^2 + d0 t), D=delta+s t, y=cc+N/D, Q=d1 theta^2+2 delta t+d0(1-theta)^2,
+//   lad=2 log delta + log Q - 2 log D.
+// Inverse direction: out=g^{-1}(x), lad=-ladf(out); implicit differentiation through the same adjoint
+//   with  gy' = -dL/dx  (dL/dx = (gy - gl * d ladf/d out)/g'(out)),  gl' = -gl.
+template <int KC>
+FC_HD void rqs_backward_elem(const RqsParams& c, float x, const float* p, float gy, float gl, float& gx,
+                             float* gp) {
+  const int K = KC ? KC : c.K;
+  const int P = c.P;
+  float xs;
+  unsigned status = 0;
+  if (!rqs_domain(c, x, xs, status)) {
+    gx = gy;
+    for (int i = 0; i < P; ++i) gp[i] = 0.f;
+    return;
+  }
+  float ew[KC ? KC : FC_MAX_BINS_GENERIC], eh[KC ? KC : FC_MAX_BINS_GENERIC];
+  float inv_w, inv_h;
+  RqsBin b;
+  rqs_locate<KC>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
+
+  const float W = b.w, H = b.h, delta = b.delta, d0 = b.d0, d1 = b.d1;
+  const float s = d0 + d1 - 2.f * delta;
+  float theta;
+  if (c.inverse) {
+    theta = rqs_inverse_root(b, xs, status);
+  } else {
+    theta = (xs - b.cw) / W;
+  }
+  const float omt = 1.f - theta;
+  const float t = theta * omt;
+  const float M = delta * theta * theta + d0 * t;
+  const float N = H * M;
+  const float D = delta + s * t;
+  const float Q = d1 * theta * theta + 2.f * delta * t + d0 * omt * omt;
+  const float invD = 1.f / D, invQ = 1.f / Q, invW = 1.f / W;
+
+  float gyf = gy, glf = gl;  // upstream of the FORWARD map evaluated at theta
+  float gx_inverse = 0.f;
+  if (c.inverse) {
+    // d ladf / d theta, and g'(out) = delta^2 Q / D^2
+    const float dQ = 2.f * d1 * theta - 2.f * d0 * omt;
+    const float dt = 1.f - 2.f * theta;
+    const float dlad_dtheta = invQ * (dQ + 2.f * delta * dt) - 2.f * invD * s * dt;
+    const float gprime = delta * delta * Q * invD * invD;
+    glf = -gl;
+    gx_inverse = (gy + glf * dlad_dtheta * invW) / gprime;
+    gyf = -gx_inverse;
+  }
+  // adjoints
+  const float Nb = gyf * invD;
+  float Db = -gyf * N * invD * invD - 2.f * glf * invD;
+  const float Qb = glf * invQ;
+  float deltab = 2.f * glf / delta + Qb * 2.f * t + Db;
+  float tb = Qb * 2.f * delta + Db * s;
+  float d0b = Qb * omt * omt;
+  float d1b = Qb * theta * theta;
+  float thetab = Qb * (2.f * d1 * theta - 2.f * d0 * omt);
+  const float sb = Db * t;
+  float Hb = Nb * M;
+  const float Mb = Nb * H;
+  deltab += Mb * theta * theta;
+  thetab += Mb * 2.f * delta * theta;
+  d0b += Mb * t + sb;
+  tb += Mb * d0;
+  d1b += sb;
+  deltab -= 2.f * sb;
+  thetab += tb * (1.f - 2.f * theta);
+  Hb += deltab * invW;
+  float Wb = -deltab * delta * invW;
+  const float xb = thetab * invW;   // d/dx of theta=(x-a)/W
+  float ab = -xb;                    // knot a (left width knot)
+  Wb -= thetab * theta * invW;
+  const float bb = Wb;               // knot b = a + W
+  ab -= Wb;
+  const float eb = Hb;               // top height knot
+  const float cb = gyf - Hb;         // bottom height knot (y = cc + ...)
+  gx = c.inverse ? gx_inverse : xb;
+
+  const int k = b.k;
+  // ---- widths: knot_m = left + span * sum_{i<m} w_i for interior m; w_i = min + coef * softmax_i
+  {
+    const float span = c.right - c.left;
+    const float GA = (k >= 1) ? ab * span * c.coef_w : 0.f;
+    const float GB = (k + 1 <= K - 1) ? bb * span * c.coef_w : 0.f;
+    float dot = 0.f;  // sum_j p_j * pbar_j
+#pragma unroll
+    for (int i = 0; i < (KC ? KC : K); ++i) {
+      const float pi = ew[i] * inv_w;
+      const float pb = (i < k ? GA : 0.f) + (i <= k ? GB : 0.f);
+      dot += pi * pb;
+    }
+#pragma unroll
+    for (int i = 0; i < (KC ? KC : K); ++i) {
+      const float pi = ew[i] * inv_w;
+      const float pb = (i < k ? GA : 0.f) + (i <= k ? GB : 0.f);
+      gp[i] = c.wh_scale * pi * (pb - dot);
+    }
+  }
+  // ---- heights
+  {
+    const float span = c.top - c.bottom;
+    const float GA = (k >= 1) ? cb * span * c.coef_h : 0.f;
+    const float GB = (k + 1 <= K - 1) ? eb * span * c.coef_h : 0.f;
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < (KC ? KC : K); ++i) {
+      const float pi = eh[i] * inv_h;
+      const float pb = (i < k ? GA : 0.f) + (i <= k ? GB : 0.f);
+      dot += pi * pb;
+    }
+#pragma unroll
+    for (int i = 0; i < (KC ? KC : K); ++i) {
+      const float pi = eh[i] * inv_h;
+      const float pb = (i < k ? GA : 0.f) + (i <= k ? GB : 0.f);
+      gp[K + i] = c.wh_scale * pi * (pb - dot);
+    }
+  }
+  // ---- derivatives: only the two knots of the bin, through softplus' = sigmoid(beta * raw)
+  {
+    // (gp may alias p — the kernels overwrite the staged tile in place — so read before writing)
+    const float* pd = p + 2 * K;
+    float* gd = gp + 2 * K;
+    const int nd = P - 2 * K;
+    const int off = (c.tails == FC_TAILS_LINEAR) ? -1 : 0;  // knot j <-> raw index j + off
+    const int j0 = k + off, j1 = k + 1 + off;
+    const bool has0 = j0 >= 0 && j0 < nd, has1 = j1 >= 0 && j1 < nd;
+    const float g0 = has0 ? d0b * softplus_beta_grad(pd[j0], c.beta) : 0.f;
+    const float g1 = has1 ? d1b * softplus_beta_grad(pd[j1], c.beta) : 0.f;
+    for (int i = 0; i < nd; ++i) gd[i] = 0.f;
+    if (has0) gd[j0] = g0;
+    if (has1) gd[j1] = g1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// affine (coupling.py:224-252, autoregressive.py:97-129)
+// ------------------------------------------------------------------------------------------------
+FC_HD float affine_scale(float u, int activation) {
+  if (activation == FC_SCALE_SIGMOID2) return sigmoidf_(u + 2.f) + 1e-3f;
+  const float sp = softplus1(u) + 1e-3f;
+  if (activation == FC_SCALE_SOFTPLUS_CLAMP3) return fminf(fmaxf(sp, 0.f), 3.f);
+  return sp;
+}
+
+// d scale / d u
+FC_HD float affine_scale_grad(float u, int activation) {
+  if (activation == FC_SCALE_SIGMOID2) {
+    const float sg = sigmoidf_(u + 2.f);
+    return sg * (1.f - sg);
+  }
+  const float g = u > 20.f ? 1.f : sigmoidf_(u);
+  if (activation == FC_SCALE_SOFTPLUS_CLAMP3) {
+    const float sp = softplus1(u) + 1e-3f;
+    return (sp > 3.f || sp < 0.f) ? 0.f : g;  // torch.clamp backward: gradient passes where min <= x <= max
+  }
+  return g;
+}
+
+FC_HD void affine_eval(float x, float raw_scale, float shift, int activation, int inverse, float& y, float& lad) {
+  const float scale = affine_scale(raw_scale, activation);
+  const float ls = logf(scale);
+  if (inverse) {
+    y = (x - shift) / scale;
+    lad = -ls;
+  } else {
+    y = x * scale + shift;
+    lad = ls;
+  }
+}
+
+FC_HD void affine_backward_elem(float x, float raw_scale, float shift, int activation, int inverse, float gy,
+                                float gl, float& gx, float& g_raw, float& g_shift) {
+  const float scale = affine_scale(raw_scale, activation);
+  const float ds = affine_scale_grad(raw_scale, activation);
+  if (inverse) {
+    const float inv = 1.f / scale;
+    gx = gy * inv;
+    g_shift = -gy * inv;
+    const float y = (x - shift) * inv;
+    g_raw = (-gy * y * inv - gl * inv) * ds;
+  } else {
+    gx = gy * scale;
+    g_shift = gy;
+    g_raw = (gy * x + gl / scale) * ds;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum of sigmoids + extended softplus (adaptive_sigmoids.py:111-142, nonlinearities.py:519-552)
+// ------------------------------------------------------------------------------------------------
+#define FC_SOS_MAX_SIGMOIDS 64
+
+FC_HD float logaddexpf_(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + log1pf(expf(-fabsf(a - b)));
+}
+
+// Forward for one element.  raw -> [shift_raw(n) | log_scale_raw(n) | softmax_raw(n) | esp_raw].
+// Returns y (without wrapper offset) and the per-element log-derivative.
+FC_HD void sos_eval(float x, const float* raw, int n, float& y, float& logj) {
+  // softmax weights + eps, renormalised (adaptive_sigmoids.py:133-135)
+  const float* sm = raw + 2 * n;
+  float m = -INFINITY;
+  for (int j = 0; j < n; ++j) m = fmaxf(m, sm[j]);
+  float se = 0.f;
+  for (int j = 0; j < n; ++j) se += expf(sm[j] - m);
+  const float inv_se = 1.f / se;
+  float wsum = 0.f;
+  for (int j = 0; j < n; ++j) wsum += expf(sm[j] - m) * inv_se + 1e-6f;
+  const float inv_wsum = 1.f / wsum;
+
+  float ysum = 0.f, wtot = 0.f, jac = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;  // :137-138
+    const float sh = tanhf(raw[j]) * 10.f;                          // :140
+    const float pre = a * (x - sh);
+    const float E = expf(-fabsf(pre));
+    const float r = 1.f / (1.f + E);
+    const float sig = pre >= 0.f ? r : E * r;          // sigmoid(pre)
+    const float dsig = E * r * r;                      // sigmoid'(pre) = sig (1 - sig)
+    ysum += w * sig;
+    wtot += w;
+    jac += w * a * dsig;
+  }
+  const float y_sig = ysum / wtot;  // :127
+  // extended softplus
+  const float s = softplus1(raw[3 * n]) + 0.1f;  // nonlinearities.py:519-520
+  const float y_esp = softplus1(x - s) - softplus1(-(x + s));
+  const float lj_esp = logaddexpf_(x - logaddexpf_(s, x), -softplus1(s + x));
+  y = y_sig + y_esp;
+  float lj_sig;
+  if (jac > 1e-30f) {
+    lj_sig = logf(jac);
+  } else {
+    // every sigmoid is saturated: redo the reduction in the log domain (logsumexp, :130)
+    float acc = 0.f;
+    float mx = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+      const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+      const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
+      const float pre = a * (x - tanhf(raw[j]) * 10.f);
+      const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
+      mx = fmaxf(mx, term);
+    }
+    for (int j = 0; j < n; ++j) {
+      const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+      const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
+      const float pre = a * (x - tanhf(raw[j]) * 10.f);
+      const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
+      acc += expf(term - mx);
+    }
+    lj_sig = mx + logf(acc);
+  }
+  logj = logaddexpf_(lj_sig, lj_esp);  // :116
+}
+
+// sigmoid(x), 1 - sigmoid(x) and sigmoid'(x) without cancellation for saturated arguments.
+FC_HD void sigmoid_parts(float x, float& sig, float& omsig, float& dsig) {
+  const float E = expf(-fabsf(x));
+  const float r = 1.f / (1.f + E);
+  const float big = r, small = E * r;
+  sig = x >= 0.f ? big : small;
+  omsig = x >= 0.f ? small : big;
+  dsig = E * r * r;
+}
+
+// 1 - tanh(x)^2 = 4 e^{-2|x|} / (1 + e^{-2|x|})^2
+FC_HD float sech2f_(float x) {
+  const float E = expf(-2.f * fabsf(x));
+  const float r = 1.f / (1.f + E);
+  return 4.f * E * r * r;
+}
+
+// Backward for one element: upstream gy (on y) and gl (on the per-element log-derivative).
+// Linear-domain derivation: J = J_sig + J_esp, logj = log J with
+//   J_sig = sum_j w_j a_j sig'_j   (the reference's logsumexp, adaptive_sigmoids.py:124-130, exponentiated)
+//   y_sig = sum_j w_j sig_j / sum_j w_j.
+FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float gl, float& gx, float* graw) {
+  const float* sm = raw + 2 * n;
+  float m = -INFINITY;
+  for (int j = 0; j < n; ++j) m = fmaxf(m, sm[j]);
+  float se = 0.f;
+  for (int j = 0; j < n; ++j) se += expf(sm[j] - m);
+  const float inv_se = 1.f / se;
+  const float wsum = 1.f + 1e-6f * (float)n;  // sum_j (softmax_j + eps)
+  const float inv_wsum = 1.f / wsum;
+
+  // pass 1: totals
+  float ysum = 0.f, jac = 0.f, djac_dx = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+    const float a = sigmoidf_(raw[n + j]) * 9.9f + 0.1f;
+    const float sh = tanhf(raw[j]) * 10.f;
+    float sig, omsig, ds;
+    sigmoid_parts(a * (x - sh), sig, omsig, ds);
+    ysum += w * sig;
+    jac += w * a * ds;
+    djac_dx += w * a * a * ds * (omsig - sig);
+  }
+  // extended softplus pieces
+  const float er = raw[3 * n];
+  const float s = softplus1(er) + 0.1f;
+  const float ds_der = er > 20.f ? 1.f : sigmoidf_(er);
+  float sp, omsp, dsp, sn, omsn, dsn;
+  sigmoid_parts(x - s, sp, omsp, dsp);       // d softplus(x-s)/dx and its derivative
+  sigmoid_parts(-(x + s), sn, omsn, dsn);    // d (-softplus(-(x+s)))/dx
+  const float j_esp = sp + sn;
+  const float dj_esp_dx = dsp - dsn;
+  const float dy_esp_ds = -sp + sn;
+  const float dj_esp_ds = -dsp - dsn;
+  const float J = fmaxf(jac + j_esp, 1e-37f);  // total derivative
+  const float gJ = gl / J;
+  gx = gy * (jac + j_esp) + gJ * (djac_dx + dj_esp_dx);
+  graw[3 * n] = (gy * dy_esp_ds + gJ * dj_esp_ds) * ds_der;
+
+  // pass 2: per-sigmoid parameter gradients
+  // softmax path: w_j = (p_j + eps)/wsum ; dL/dw_j = gy * (sig_j - ysum) + gJ * a_j ds_j
+  float dot = 0.f;  // sum_j p_j * dL/dp_j
+  for (int j = 0; j < n; ++j) {
+    const float pj = expf(sm[j] - m) * inv_se;
+    const float a = sigmoidf_(raw[n + j]) * 9.9f + 0.1f;
+    float sig, omsig, ds;
+    sigmoid_parts(a * (x - tanhf(raw[j]) * 10.f), sig, omsig, ds);
+    const float gw = gy * (sig - ysum) + gJ * a * ds;
+    dot += pj * gw * inv_wsum;
+  }
+  for (int j = 0; j < n; ++j) {
+    const float pj = expf(sm[j] - m) * inv_se;
+    const float w = (pj + 1e-6f) * inv_wsum;
+    float lsg, omlsg, dlsg;
+    sigmoid_parts(raw[n + j], lsg, omlsg, dlsg);
+    const float a = lsg * 9.9f + 0.1f;
+    const float th = tanhf(raw[j]);
+    const float sh = th * 10.f;
+    float sig, omsig, ds;
+    sigmoid_parts(a * (x - sh), sig, omsig, ds);
+    const float dds = ds * (omsig - sig);
+    const float gw = gy * (sig - ysum) + gJ * a * ds;
+    // pre = a (x - sh):  d/d pre of [gy w sig + gJ w a ds] = gy w ds + gJ w a dds
+    const float gpre = gy * w * ds + gJ * w * a * dds;
+    const float ga = gpre * (x - sh) + gJ * w * ds;
+    const float gsh = -gpre * a;
+    // (graw may alias raw: all reads of slot j / n+j / 2n+j of this iteration are done)
+    graw[2 * n + j] = pj * (gw * inv_wsum - dot);
+    graw[n + j] = ga * 9.9f * dlsg;
+    graw[j] = gsh * 10.f * sech2f_(raw[j] * 1.f);
+  }
+}
+
+// Numerical inverse for one element: find x with sos(x) = z.  Bracket [-lim, lim] grown until it
+// contains the root (no_analytic_inv/base.py:48-60, per element instead of batch-global), `iters`
+// bisection steps (:67-79), then two Newton steps with the analytic derivative and the reference's
+// +1e-7 damping (:30-33).
+FC_HD void sos_invert(float z, const float* raw, int n, int iters, float lim, float& x, float& logj) {
+  float hi = lim, lo = -lim, y, lj;
+  for (int g = 0; g < 64; ++g) {
+    sos_eval(hi, raw, n, y, lj);
+    if (!(z > y)) break;
+    hi *= 1.5f;
+  }
+  hi += 1.f;
+  for (int g = 0; g < 64; ++g) {
+    sos_eval(lo, raw, n, y, lj);
+    if (!(z < y)) break;
+    lo *= 1.5f;
+  }
+  lo -= 1.f;
+  for (int i = 0; i < iters; ++i) {
+    const float mid = 0.5f * (hi + lo);
+    if (mid == hi || mid == lo) break;  // fp32 resolution reached
+    sos_eval(mid, raw, n, y, lj);
+    if (y > z) {
+      hi = mid;
+    } else if (y < z) {
+      lo = mid;
+    } else {
+      hi = mid;
+      lo = mid;
+    }
+  }
+  x = 0.5f * (hi + lo);
+  for (int i = 0; i < 2; ++i) {
+    sos_eval(x, raw, n, y, lj);
+    x = x - (y - z) / (expf(lj) + 1e-7f);
+  }
+  sos_eval(x, raw, n, y, logj);
+}
+
+}  // namespace fc

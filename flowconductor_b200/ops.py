@@ -1,0 +1,303 @@
+"""torch custom ops (`torch.ops.flowcon_b200.*`) over the C-ABI kernels, with autograd.
+
+Each op is one kernel launch on torch's current CUDA stream.  Layer ops take the FULL-width input
+[B, D] plus int32 column lists, so the coupling split / scatter of the reference
+(flowcon/transforms/coupling.py:82-83,96-98) happens inside the kernel; autoregressive / conditional
+layers pass no column lists.  Backward ops recompute the forward intermediates from (x, params)
+ — nothing else is saved.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+
+
+def _cfg(num_bins, tails, inverse, identity_init, left, right, bottom, top, min_w, min_h, min_d, wh_scale):
+    return _cabi.RqsConfig(int(num_bins), int(tails), int(identity_init), int(inverse), left, right, bottom, top,
+                           min_w, min_h, min_d, wh_scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# RQ-spline layer
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("flowcon_b200::rqs_layer", mutates_args=())
+def rqs_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: Optional[Tensor], num_bins: int,
+              tails: int, inverse: bool, identity_init: bool, left: float, right: float, bottom: float, top: float,
+              min_bin_width: float, min_bin_height: float, min_derivative: float,
+              wh_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    _cabi.require_cuda_f32(x, "inputs")
+    _cabi.require_cuda_f32(params, "transform params")
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    y = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
+    lad = torch.empty((B,), dtype=x.dtype, device=x.device)
+    status = torch.zeros((1,), dtype=torch.int32, device=x.device)
+    cfg = _cfg(num_bins, tails, inverse, identity_init, left, right, bottom, top, min_bin_width, min_bin_height,
+               min_derivative, wh_scale)
+    p_per = 3 * num_bins - 1 if tails == _cabi.TAILS_LINEAR else 3 * num_bins + 1
+    if params.shape[1] != d_t * p_per:
+        raise ValueError("transform params have {} columns, expected {} x {}".format(params.shape[1], d_t, p_per))
+    with torch.cuda.device(x.device), _cabi.launch("fc_rqs_apply", x.device):
+        rc = L.fc_rqs_apply(xp, xs, pp, ps, y.data_ptr(), y.shape[1], lad.data_ptr(), 0, B, d_t, _cabi.cols(tcols),
+                            _cabi.cols(ccols), ctypes.byref(cfg), status.data_ptr(), _cabi.stream_ptr(x.device))
+    if rc == -1 and (min_bin_width * num_bins > 1.0 or min_bin_height * num_bins > 1.0):
+        # flowcon/transforms/splines/rational_quadratic.py:86-89
+        raise ValueError("Minimal bin width/height too large for the number of bins")
+    _cabi.check(rc, "fc_rqs_apply")
+    return y, lad, status
+
+
+@rqs_layer.register_fake
+def _(x, params, tcols, ccols, num_bins, tails, inverse, identity_init, left, right, bottom, top, min_bin_width,
+      min_bin_height, min_derivative, wh_scale):
+    return torch.empty_like(x), x.new_empty((x.shape[0],)), x.new_empty((1,), dtype=torch.int32)
+
+
+@torch.library.custom_op("flowcon_b200::rqs_layer_backward", mutates_args=())
+def rqs_layer_backward(x: Tensor, params: Tensor, grad_y: Tensor, grad_lad: Optional[Tensor],
+                       tcols: Optional[Tensor], ccols: Optional[Tensor], num_bins: int, tails: int, inverse: bool,
+                       identity_init: bool, left: float, right: float, bottom: float, top: float,
+                       min_bin_width: float, min_bin_height: float, min_derivative: float,
+                       wh_scale: float) -> Tuple[Tensor, Tensor]:
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    grad_y, gyp, gys = _cabi.rows(_cabi.require_cuda_f32(grad_y, "grad outputs"))
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    gx = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
+    gp = torch.empty((B, params.shape[1]), dtype=x.dtype, device=x.device)
+    if tcols is not None and (tcols.numel() + (ccols.numel() if ccols is not None else 0)) < x.shape[1]:
+        gx.zero_()
+    glp = None
+    if grad_lad is not None:
+        grad_lad = grad_lad.contiguous()
+        glp = grad_lad.data_ptr()
+    cfg = _cfg(num_bins, tails, inverse, identity_init, left, right, bottom, top, min_bin_width, min_bin_height,
+               min_derivative, wh_scale)
+    with torch.cuda.device(x.device), _cabi.launch("fc_rqs_backward", x.device):
+        rc = L.fc_rqs_backward(xp, xs, pp, ps, gyp, gys, glp, gx.data_ptr(), gx.shape[1], gp.data_ptr(), gp.shape[1],
+                               B, d_t, _cabi.cols(tcols), _cabi.cols(ccols), ctypes.byref(cfg),
+                               _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_rqs_backward")
+    return gx, gp
+
+
+@rqs_layer_backward.register_fake
+def _(x, params, grad_y, grad_lad, tcols, ccols, *args):
+    return torch.empty_like(x), torch.empty_like(params)
+
+
+def _rqs_setup(ctx, inputs, output):
+    x, params, tcols, ccols = inputs[:4]
+    ctx.save_for_backward(x, params, tcols, ccols)
+    ctx.hyper = inputs[4:]
+
+
+def _rqs_backward(ctx, gy, gl, gstatus):
+    x, params, tcols, ccols = ctx.saved_tensors
+    if gy is None:
+        gy = torch.zeros_like(x)
+    gx, gp = rqs_layer_backward(x, params, gy, gl, tcols, ccols, *ctx.hyper)
+    return (gx, gp) + (None,) * (2 + len(ctx.hyper))
+
+
+rqs_layer.register_autograd(_rqs_backward, setup_context=_rqs_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# affine layer
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("flowcon_b200::affine_layer", mutates_args=())
+def affine_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: Optional[Tensor], layout: int,
+                 activation: int, inverse: bool) -> Tuple[Tensor, Tensor]:
+    _cabi.require_cuda_f32(x, "inputs")
+    _cabi.require_cuda_f32(params, "transform params")
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    if params.shape[1] != 2 * d_t:
+        raise ValueError("affine params have {} columns, expected {}".format(params.shape[1], 2 * d_t))
+    y = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
+    lad = torch.empty((B,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device), _cabi.launch("fc_affine_apply", x.device):
+        rc = L.fc_affine_apply(xp, xs, pp, ps, y.data_ptr(), y.shape[1], lad.data_ptr(), 0, B, d_t,
+                               _cabi.cols(tcols), _cabi.cols(ccols), layout, activation, int(inverse),
+                               _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_affine_apply")
+    return y, lad
+
+
+@affine_layer.register_fake
+def _(x, params, tcols, ccols, layout, activation, inverse):
+    return torch.empty_like(x), x.new_empty((x.shape[0],))
+
+
+@torch.library.custom_op("flowcon_b200::affine_layer_backward", mutates_args=())
+def affine_layer_backward(x: Tensor, params: Tensor, grad_y: Tensor, grad_lad: Optional[Tensor],
+                          tcols: Optional[Tensor], ccols: Optional[Tensor], layout: int, activation: int,
+                          inverse: bool) -> Tuple[Tensor, Tensor]:
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    grad_y, gyp, gys = _cabi.rows(_cabi.require_cuda_f32(grad_y, "grad outputs"))
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    gx = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
+    gp = torch.empty((B, params.shape[1]), dtype=x.dtype, device=x.device)
+    if tcols is not None and (tcols.numel() + (ccols.numel() if ccols is not None else 0)) < x.shape[1]:
+        gx.zero_()
+    glp = None
+    if grad_lad is not None:
+        grad_lad = grad_lad.contiguous()
+        glp = grad_lad.data_ptr()
+    with torch.cuda.device(x.device), _cabi.launch("fc_affine_backward", x.device):
+        rc = L.fc_affine_backward(xp, xs, pp, ps, gyp, gys, glp, gx.data_ptr(), gx.shape[1], gp.data_ptr(),
+                                  gp.shape[1], B, d_t, _cabi.cols(tcols), _cabi.cols(ccols), layout, activation,
+                                  int(inverse), _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_affine_backward")
+    return gx, gp
+
+
+@affine_layer_backward.register_fake
+def _(x, params, grad_y, grad_lad, tcols, ccols, layout, activation, inverse):
+    return torch.empty_like(x), torch.empty_like(params)
+
+
+def _affine_setup(ctx, inputs, output):
+    x, params, tcols, ccols = inputs[:4]
+    ctx.save_for_backward(x, params, tcols, ccols)
+    ctx.hyper = inputs[4:]
+
+
+def _affine_backward(ctx, gy, gl):
+    x, params, tcols, ccols = ctx.saved_tensors
+    if gy is None:
+        gy = torch.zeros_like(x)
+    gx, gp = affine_layer_backward(x, params, gy, gl, tcols, ccols, *ctx.hyper)
+    return (gx, gp) + (None,) * (2 + len(ctx.hyper))
+
+
+affine_layer.register_autograd(_affine_backward, setup_context=_affine_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# sum-of-sigmoids layer
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("flowcon_b200::sos_layer", mutates_args=())
+def sos_layer(x: Tensor, params: Tensor, n_sigmoids: int, offset: float, inverse: bool, bisection_iterations: int,
+              lim: float) -> Tuple[Tensor, Tensor]:
+    _cabi.require_cuda_f32(x, "inputs")
+    _cabi.require_cuda_f32(params, "transform params")
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    B, D = x.shape
+    if params.shape[1] != D * (3 * n_sigmoids + 1):
+        raise ValueError("sum-of-sigmoids params have {} columns, expected {}".format(
+            params.shape[1], D * (3 * n_sigmoids + 1)))
+    y = torch.empty((B, D), dtype=x.dtype, device=x.device)
+    lad = torch.empty((B,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device), _cabi.launch("fc_sos_apply", x.device):
+        rc = L.fc_sos_apply(xp, xs, pp, ps, y.data_ptr(), D, lad.data_ptr(), 0, B, D, n_sigmoids, offset,
+                            int(inverse), bisection_iterations, lim, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_sos_apply")
+    return y, lad
+
+
+@sos_layer.register_fake
+def _(x, params, n_sigmoids, offset, inverse, bisection_iterations, lim):
+    return torch.empty_like(x), x.new_empty((x.shape[0],))
+
+
+@torch.library.custom_op("flowcon_b200::sos_layer_backward", mutates_args=())
+def sos_layer_backward(x: Tensor, params: Tensor, grad_y: Tensor, grad_lad: Optional[Tensor],
+                       n_sigmoids: int) -> Tuple[Tensor, Tensor]:
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    grad_y, gyp, gys = _cabi.rows(_cabi.require_cuda_f32(grad_y, "grad outputs"))
+    B, D = x.shape
+    gx = torch.empty((B, D), dtype=x.dtype, device=x.device)
+    gp = torch.empty((B, params.shape[1]), dtype=x.dtype, device=x.device)
+    glp = None
+    if grad_lad is not None:
+        grad_lad = grad_lad.contiguous()
+        glp = grad_lad.data_ptr()
+    with torch.cuda.device(x.device), _cabi.launch("fc_sos_backward", x.device):
+        rc = L.fc_sos_backward(xp, xs, pp, ps, gyp, gys, glp, gx.data_ptr(), D, gp.data_ptr(), gp.shape[1], B, D,
+                               n_sigmoids, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_sos_backward")
+    return gx, gp
+
+
+@sos_layer_backward.register_fake
+def _(x, params, grad_y, grad_lad, n_sigmoids):
+    return torch.empty_like(x), torch.empty_like(params)
+
+
+def _sos_setup(ctx, inputs, output):
+    x, params, n_sigmoids, offset, inverse = inputs[:5]
+    ctx.save_for_backward(x, params)
+    ctx.n_sigmoids = n_sigmoids
+    ctx.inverse = inverse
+
+
+def _sos_backward(ctx, gy, gl):
+    if ctx.inverse:
+        raise NotImplementedError("gradients through the numerical sum-of-sigmoids inverse are not implemented")
+    x, params = ctx.saved_tensors
+    if gy is None:
+        gy = torch.zeros_like(x)
+    gx, gp = sos_layer_backward(x, params, gy, gl, ctx.n_sigmoids)
+    return gx, gp, None, None, None, None, None
+
+
+sos_layer.register_autograd(_sos_backward, setup_context=_sos_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# standard-normal tail
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("flowcon_b200::stdnormal_log_prob", mutates_args=())
+def stdnormal_log_prob(z: Tensor, logabsdet: Optional[Tensor]) -> Tensor:
+    _cabi.require_cuda_f32(z, "noise")
+    L = _cabi.lib()
+    z, zp, zs = _cabi.rows(z)
+    B, D = z.shape
+    out = torch.empty((B,), dtype=z.dtype, device=z.device)
+    ladp = None
+    if logabsdet is not None:
+        logabsdet = _cabi.require_cuda_f32(logabsdet, "logabsdet").contiguous()
+        ladp = logabsdet.data_ptr()
+    with torch.cuda.device(z.device), _cabi.launch("fc_stdnormal_log_prob", z.device):
+        rc = L.fc_stdnormal_log_prob(zp, zs, ladp, out.data_ptr(), B, D, _cabi.stream_ptr(z.device))
+    _cabi.check(rc, "fc_stdnormal_log_prob")
+    return out
+
+
+@stdnormal_log_prob.register_fake
+def _(z, logabsdet):
+    return z.new_empty((z.shape[0],))
+
+
+def _sn_setup(ctx, inputs, output):
+    z, lad = inputs
+    ctx.save_for_backward(z)
+    ctx.has_lad = lad is not None
+
+
+def _sn_backward(ctx, g):
+    (z,) = ctx.saved_tensors
+    return -z * g[:, None], (g if ctx.has_lad else None)
+
+
+stdnormal_log_prob.register_autograd(_sn_backward, setup_context=_sn_setup)

@@ -1,0 +1,130 @@
+"""Masked autoregressive layers on the hot path, API of
+flowcon/transforms/autoregressive/autoregressive.py (AutoregressiveTransform :25-62,
+MaskedAffineAutoregressiveTransform :65-129, MaskedSumOfSigmoidsTransform :266-318,
+MaskedPiecewiseRationalQuadraticAutoregressiveTransform :529-621).  Sub-module name `autoregressive_net`
+(a MADE) is kept so reference state_dicts load.
+"""
+import numpy as np
+import torch
+from torch.nn import functional as F
+
+from .. import _cabi, ops
+from . import made as made_module
+from . import splines
+from .base import Transform
+
+
+class AutoregressiveTransform(Transform):
+    """Forward: one conditioner pass + one element-wise kernel.  Inverse: D passes, each re-running the
+    conditioner on the partially inverted outputs (autoregressive.py:44-53) — D x the forward cost."""
+
+    def __init__(self, autoregressive_net):
+        super().__init__()
+        self.autoregressive_net = autoregressive_net
+
+    def forward(self, inputs, context=None):
+        params = self.autoregressive_net(inputs, context)
+        return self._elementwise_forward(inputs, params)
+
+    def inverse(self, inputs, context=None):
+        outputs = torch.zeros_like(inputs)
+        logabsdet = None
+        for _ in range(int(np.prod(inputs.shape[1:]))):
+            params = self.autoregressive_net(outputs, context)
+            outputs, logabsdet = self._elementwise_inverse(inputs, params)
+        return outputs, logabsdet
+
+    def _output_dim_multiplier(self):
+        raise NotImplementedError()
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        raise NotImplementedError()
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        raise NotImplementedError()
+
+
+def _made(layer, features, hidden_features, context_features, num_blocks, use_residual_blocks, random_mask,
+          activation, dropout_probability, use_batch_norm):
+    return made_module.MADE(features=features, hidden_features=hidden_features, context_features=context_features,
+                            num_blocks=num_blocks, output_multiplier=layer._output_dim_multiplier(),
+                            use_residual_blocks=use_residual_blocks, random_mask=random_mask, activation=activation,
+                            dropout_probability=dropout_probability, use_batch_norm=use_batch_norm)
+
+
+class MaskedAffineAutoregressiveTransform(AutoregressiveTransform):
+    """MAF layer: params viewed [B, D, 2] = (raw scale, shift) pairs; scale = softplus(raw) + 1e-3."""
+
+    def __init__(self, features, hidden_features, context_features=None, num_blocks=2, use_residual_blocks=True,
+                 random_mask=False, activation=F.relu, dropout_probability=0.0, use_batch_norm=False):
+        self.features = features
+        self._epsilon = 1e-3
+        super().__init__(_made(self, features, hidden_features, context_features, num_blocks, use_residual_blocks,
+                               random_mask, activation, dropout_probability, use_batch_norm))
+
+    def _output_dim_multiplier(self):
+        return 2
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return ops.affine_layer(inputs, autoregressive_params, None, None, _cabi.AFFINE_INTERLEAVED,
+                                _cabi.SCALE_SOFTPLUS_EPS, False)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return ops.affine_layer(inputs, autoregressive_params, None, None, _cabi.AFFINE_INTERLEAVED,
+                                _cabi.SCALE_SOFTPLUS_EPS, True)
+
+
+class MaskedSumOfSigmoidsTransform(AutoregressiveTransform):
+    """Autoregressive sum-of-sigmoids layer; forward output is shifted by -0.5 (autoregressive.py:309,313)."""
+
+    def __init__(self, features, hidden_features, n_sigmoids=30, context_features=None, num_blocks=2,
+                 use_residual_blocks=True, random_mask=False, activation=F.relu, dropout_probability=0.0,
+                 use_batch_norm=False):
+        self.features = features
+        self.n_sigmoids = n_sigmoids
+        super().__init__(_made(self, features, hidden_features, context_features, num_blocks, use_residual_blocks,
+                               random_mask, activation, dropout_probability, use_batch_norm))
+
+    def _output_dim_multiplier(self):
+        return 3 * self.n_sigmoids + 1
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return ops.sos_layer(inputs, autoregressive_params, self.n_sigmoids, -0.5, False, 50, 120.0)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return ops.sos_layer(inputs, autoregressive_params, self.n_sigmoids, -0.5, True, 50, 120.0)
+
+
+class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTransform):
+    """MAF-RQS layer.  Identity-init softplus (beta = ln2/(1-min_derivative)) is always on (autoregressive.py
+    :611); tails=None means the box [-1.2, 1.2]^2 (:595); no 1/sqrt(H) pre-scale because MADE exposes no
+    `hidden_features` (:589)."""
+
+    def __init__(self, features, hidden_features, context_features=None, num_bins=10, tails=None, tail_bound=1.0,
+                 num_blocks=2, use_residual_blocks=True, random_mask=False, activation=F.relu,
+                 dropout_probability=0.0, use_batch_norm=False, min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT, min_derivative=splines.DEFAULT_MIN_DERIVATIVE):
+        self.num_bins = num_bins
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.min_derivative = min_derivative
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self._spline = splines.RationalQuadraticSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height,
+                                                         min_derivative, identity_init=True,
+                                                         constrained_box=(-1.2, 1.2))
+        super().__init__(_made(self, features, hidden_features, context_features, num_blocks, use_residual_blocks,
+                               random_mask, activation, dropout_probability, use_batch_norm))
+
+    def _output_dim_multiplier(self):
+        return self._spline.params_per_feature()
+
+    def _elementwise(self, inputs, autoregressive_params, inverse=False):
+        hidden = getattr(self.autoregressive_net, "hidden_features", None)
+        return self._spline.apply(inputs, autoregressive_params, None, None, inverse, hidden)
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return self._elementwise(inputs, autoregressive_params)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return self._elementwise(inputs, autoregressive_params, inverse=True)

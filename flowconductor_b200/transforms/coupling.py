@@ -1,0 +1,152 @@
+"""Coupling layers on the hot path, API of flowcon/transforms/coupling.py (CouplingTransform :20-142,
+AffineCouplingTransform :212-252, AdditiveCouplingTransform :255-269, PiecewiseRationalQuadraticCouplingTransform
+:502-582).  Same constructor arguments, same buffers (`identity_features`, `transform_features`) and sub-module
+names (`transform_net`), so reference state_dicts load.
+
+What changed: the conditioner output goes straight into ONE kernel that evaluates the bijection on the
+transform columns, copies the identity columns, and reduces the per-sample log-det — the reference's
+gather / scatter / mask-dispatch / 40-op pointwise chain (coupling.py:82-98, rational_quadratic.py) is gone.
+"""
+import warnings
+
+import torch
+
+from .. import _cabi, ops
+from . import splines
+from .base import Transform
+
+
+class CouplingTransform(Transform):
+    def __init__(self, mask, transform_net_create_fn, unconditional_transform=None):
+        mask = torch.as_tensor(mask)
+        if mask.dim() != 1:
+            raise ValueError("Mask must be a 1-dim tensor.")
+        if mask.numel() <= 0:
+            raise ValueError("Mask can't be empty.")
+        if unconditional_transform is not None:
+            raise NotImplementedError("unconditional_transform on the identity features is outside the "
+                                      "B200 hot path (SURVEY.md §8f n3)")
+        super().__init__()
+        self.features = len(mask)
+        index = torch.arange(self.features)
+        self.register_buffer("identity_features", index.masked_select(mask <= 0))
+        self.register_buffer("transform_features", index.masked_select(mask > 0))
+        # int32 copies for the kernels; non-persistent so the state_dict equals the reference's
+        self.register_buffer("_ccols", self.identity_features.to(torch.int32), persistent=False)
+        self.register_buffer("_tcols", self.transform_features.to(torch.int32), persistent=False)
+        assert self.num_identity_features + self.num_transform_features == self.features
+        self.transform_net = transform_net_create_fn(
+            self.num_identity_features, self.num_transform_features * self._transform_dim_multiplier())
+        self.unconditional_transform = None
+
+    @property
+    def num_identity_features(self):
+        return len(self.identity_features)
+
+    @property
+    def num_transform_features(self):
+        return len(self.transform_features)
+
+    def _check(self, inputs):
+        if inputs.dim() == 4:
+            raise NotImplementedError("4-D (image) inputs are outside the B200 hot path")
+        if inputs.dim() != 2:
+            raise ValueError("Inputs must be a 2D or a 4D tensor.")
+        if inputs.shape[1] != self.features:
+            raise ValueError("Expected features = {}, got {}.".format(self.features, inputs.shape[1]))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._ccols = self.identity_features.to(torch.int32)
+        self._tcols = self.transform_features.to(torch.int32)
+
+    def forward(self, inputs, context=None):
+        self._check(inputs)
+        params = self.transform_net(inputs[:, self.identity_features], context)
+        return self._coupling_layer(inputs, params, inverse=False)
+
+    def inverse(self, inputs, context=None):
+        self._check(inputs)
+        params = self.transform_net(inputs[:, self.identity_features], context)
+        return self._coupling_layer(inputs, params, inverse=True)
+
+    def _transform_dim_multiplier(self):
+        raise NotImplementedError()
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        """(full-width inputs, conditioner output) -> (full-width outputs, logabsdet[B]), one kernel."""
+        raise NotImplementedError()
+
+
+class AffineCouplingTransform(CouplingTransform):
+    """Scale-and-shift coupling (Real NVP).  `scale_activation` must be one of the two predefined activations
+    of the reference (coupling.py:224-225); they are selected by identity and evaluated inside the kernel."""
+
+    DEFAULT_SCALE_ACTIVATION = "sigmoid(x + 2) + 1e-3"
+    GENERAL_SCALE_ACTIVATION = "clamp(softplus(x) + 1e-3, 0, 3)"
+
+    def __init__(self, mask, transform_net_create_fn, unconditional_transform=None,
+                 scale_activation=DEFAULT_SCALE_ACTIVATION):
+        if scale_activation == self.DEFAULT_SCALE_ACTIVATION:
+            self._activation_code = _cabi.SCALE_SIGMOID2
+        elif scale_activation == self.GENERAL_SCALE_ACTIVATION:
+            self._activation_code = _cabi.SCALE_SOFTPLUS_CLAMP3
+        else:
+            raise NotImplementedError("scale_activation must be AffineCouplingTransform.DEFAULT_SCALE_ACTIVATION "
+                                      "or GENERAL_SCALE_ACTIVATION (arbitrary callables cannot run in the kernel)")
+        self.scale_activation = scale_activation
+        super().__init__(mask, transform_net_create_fn, unconditional_transform)
+
+    def _transform_dim_multiplier(self):
+        return 2
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        return ops.affine_layer(inputs, transform_params, self._tcols, self._ccols, _cabi.AFFINE_BLOCKED,
+                                self._activation_code, bool(inverse))
+
+
+class AdditiveCouplingTransform(AffineCouplingTransform):
+    """Shift-only coupling (NICE, coupling.py:255-269): zero log-det, no kernel needed beyond an indexed add."""
+
+    def _transform_dim_multiplier(self):
+        return 1
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        outputs = inputs.clone()
+        cols = self.transform_features
+        outputs[:, cols] = inputs[:, cols] - transform_params if inverse else inputs[:, cols] + transform_params
+        return outputs, inputs.new_zeros(inputs.shape[0])
+
+
+class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
+    def __init__(self, mask, transform_net_create_fn, num_bins=10, tails=None, tail_bound=1.0,
+                 apply_unconditional_transform=False, img_shape=None,
+                 min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH, min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT,
+                 min_derivative=splines.DEFAULT_MIN_DERIVATIVE):
+        if apply_unconditional_transform:
+            raise NotImplementedError("apply_unconditional_transform is outside the B200 hot path "
+                                      "(SURVEY.md §8f n3)")
+        self.num_bins = num_bins
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.min_derivative = min_derivative
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self._spline = splines.RationalQuadraticSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height,
+                                                         min_derivative, identity_init=False,
+                                                         constrained_box=(0.0, 1.0))
+        super().__init__(mask, transform_net_create_fn, unconditional_transform=None)
+
+    def _transform_dim_multiplier(self):
+        return self._spline.params_per_feature()
+
+    def _scaling_width(self):
+        # coupling.py:554-563: widths and heights are divided by sqrt(hidden) when the net exposes it
+        for attr in ("hidden_features", "hidden_channels"):
+            if hasattr(self.transform_net, attr):
+                return getattr(self.transform_net, attr)
+        warnings.warn("Inputs to the softmax are not scaled down: initialization might be bad.")
+        return None
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        return self._spline.apply(inputs, transform_params, self._tcols, self._ccols, inverse, self._scaling_width())

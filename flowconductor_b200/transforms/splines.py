@@ -1,0 +1,106 @@
+"""Function-level seam: `rational_quadratic_spline` / `unconstrained_rational_quadratic_spline` with the
+signatures of flowcon/transforms/splines/rational_quadratic.py:13-25,66-80, backed by the CUDA kernels.
+
+Inputs of any shape [...]; raw parameters [..., K], [..., K], [..., K-1 | K+1]; returns
+(outputs [...], per-element logabsdet [...]).  These are what `flowconductor_b200.patch_reference()`
+installs into the reference's modules.  The layer classes do NOT go through here: they hand the
+conditioner's [B, D_t*P] output to the kernel directly (no concatenation, column split fused).
+"""
+import math
+
+import torch
+
+from .. import _cabi, ops
+from .base import InputOutsideDomain
+
+DEFAULT_MIN_BIN_WIDTH = 1e-3
+DEFAULT_MIN_BIN_HEIGHT = 1e-3
+DEFAULT_MIN_DERIVATIVE = 1e-3
+
+# when True, every spline call checks the device status word (one host sync, like the reference's own
+# checks at rational_quadratic.py:81-82,142) even with linear tails
+STRICT = False
+
+
+def check_status(status, tails):
+    """Turn the device status word into the reference's exceptions."""
+    if tails == _cabi.TAILS_NONE or STRICT:
+        code = int(status.item())
+        if code & _cabi.STATUS_INPUT_OUTSIDE_DOMAIN:
+            raise InputOutsideDomain()
+        if code & _cabi.STATUS_NEGATIVE_DISCRIMINANT:
+            raise AssertionError("negative discriminant in the rational-quadratic inverse")
+
+
+def _elementwise(inputs, unnormalized_widths, unnormalized_heights, unnormalized_derivatives, inverse, tails, left,
+                 right, bottom, top, min_bin_width, min_bin_height, min_derivative, enable_identity_init):
+    num_bins = unnormalized_widths.shape[-1]
+    if min_bin_width * num_bins > 1.0:
+        raise ValueError("Minimal bin width too large for the number of bins")
+    if min_bin_height * num_bins > 1.0:
+        raise ValueError("Minimal bin height too large for the number of bins")
+    shape = inputs.shape
+    params = torch.cat((unnormalized_widths, unnormalized_heights, unnormalized_derivatives), dim=-1)
+    params = params.reshape(-1, params.shape[-1])
+    # every element is its own row (D_t = 1), so the kernel's per-row log-det IS the per-element one
+    y, lad, status = ops.rqs_layer(inputs.reshape(-1, 1), params, None, None, num_bins, tails, bool(inverse),
+                                   bool(enable_identity_init), float(left), float(right), float(bottom), float(top),
+                                   float(min_bin_width), float(min_bin_height), float(min_derivative), 1.0)
+    check_status(status, tails)
+    return y.reshape(shape), lad.reshape(shape)
+
+
+def rational_quadratic_spline(inputs, unnormalized_widths, unnormalized_heights, unnormalized_derivatives,
+                              inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0,
+                              min_bin_width=DEFAULT_MIN_BIN_WIDTH, min_bin_height=DEFAULT_MIN_BIN_HEIGHT,
+                              min_derivative=DEFAULT_MIN_DERIVATIVE, enable_identity_init=False):
+    return _elementwise(inputs, unnormalized_widths, unnormalized_heights, unnormalized_derivatives, inverse,
+                        _cabi.TAILS_NONE, left, right, bottom, top, min_bin_width, min_bin_height, min_derivative,
+                        enable_identity_init)
+
+
+def unconstrained_rational_quadratic_spline(inputs, unnormalized_widths, unnormalized_heights,
+                                            unnormalized_derivatives, inverse=False, tails="linear", tail_bound=1.0,
+                                            min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+                                            min_bin_height=DEFAULT_MIN_BIN_HEIGHT,
+                                            min_derivative=DEFAULT_MIN_DERIVATIVE, enable_identity_init=False):
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    return _elementwise(inputs, unnormalized_widths, unnormalized_heights, unnormalized_derivatives, inverse,
+                        _cabi.TAILS_LINEAR, -tail_bound, tail_bound, -tail_bound, tail_bound, min_bin_width,
+                        min_bin_height, min_derivative, enable_identity_init)
+
+
+class RationalQuadraticSettings:
+    """The spline hyper-parameters a layer class carries, and the one call that applies them to a
+    conditioner output.  `constrained_bound` is the box used when tails is None: 1.0 -> [0,1] for couplings
+    (coupling.py:566-567), 1.2 -> [-1.2,1.2] for autoregressive / conditional layers (autoregressive.py:595)."""
+
+    def __init__(self, num_bins, tails, tail_bound, min_bin_width, min_bin_height, min_derivative,
+                 identity_init, constrained_box):
+        if tails not in (None, "linear"):
+            raise ValueError(tails)
+        self.num_bins = num_bins
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.min_derivative = min_derivative
+        self.identity_init = identity_init
+        self.constrained_box = constrained_box
+
+    def params_per_feature(self):
+        return self.num_bins * 3 - 1 if self.tails == "linear" else self.num_bins * 3 + 1
+
+    def apply(self, inputs, params, tcols, ccols, inverse, hidden_for_scaling):
+        if self.tails == "linear":
+            tails, lo, hi = _cabi.TAILS_LINEAR, -self.tail_bound, self.tail_bound
+        else:
+            tails, (lo, hi) = _cabi.TAILS_NONE, self.constrained_box
+        wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
+        y, lad, status = ops.rqs_layer(inputs, params, tcols, ccols, self.num_bins, tails, bool(inverse),
+                                       bool(self.identity_init), float(lo), float(hi), float(lo), float(hi),
+                                       float(self.min_bin_width), float(self.min_bin_height),
+                                       float(self.min_derivative), float(wh_scale))
+        check_status(status, tails)
+        return y, lad

@@ -1,0 +1,140 @@
+/*
+ * flowcon_b200.h — C ABI of libflowcon_b200.so: sm_100a kernels for FlowConductor's element-wise
+ * bijection hot path (rational-quadratic splines, affine, sum-of-sigmoids) with the per-sample
+ * log|det J| reduction, coupling column split/scatter and the final-conditioner GEMM fused in.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; fp32 unless stated; row-major.
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, stateless and
+ *    re-entrant.  Return value: 0, or a negative FC_ERR_* code (never throws, never syncs).
+ *  - matrices are described by (base, row_stride in ELEMENTS, optional int32 column list).  A NULL
+ *    column list means columns 0..D_t-1.  This is how the coupling split / scatter of the reference
+ *    (flowcon/transforms/coupling.py:82-83,96-98) is folded into the kernels.
+ *  - `params` is the conditioner output [B, D_t * P] exactly as the reference lays it out
+ *    (feature-major; coupling.py:289, autoregressive.py:581-583): P consecutive floats per feature.
+ *  - domain violations that the reference reports by raising after a host sync
+ *    (InputOutsideDomain rational_quadratic.py:81-82, discriminant assert :142) are OR-ed into the
+ *    caller's `status` word (FC_STATUS_*); pass NULL to ignore.
+ *
+ * The reference is pure Python: there is no existing FFI.  Each entry point below names the
+ * reference function (file:line under /root/reference) it replaces; INTEGRATION.md shows the ctypes
+ * binding and the monkey-patch a maintainer would add on the reference side.
+ */
+#ifndef FLOWCON_B200_H
+#define FLOWCON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FC_OK 0
+#define FC_ERR_INVALID_ARGUMENT (-1)
+#define FC_ERR_UNSUPPORTED (-2)
+#define FC_ERR_CUDA (-3)
+
+#define FC_STATUS_INPUT_OUTSIDE_DOMAIN 1 /* rational_quadratic.py:81-82 */
+#define FC_STATUS_NEGATIVE_DISCRIMINANT 2 /* rational_quadratic.py:142 */
+#define FC_STATUS_NONFINITE 4
+
+#define FC_TAILS_NONE 0   /* constrained spline on [left,right] -> [bottom,top] */
+#define FC_TAILS_LINEAR 1 /* identity outside [-tail_bound, tail_bound]; P = 3K-1 */
+
+/* Spline hyper-parameters: arguments of rational_quadratic_spline /
+ * unconstrained_rational_quadratic_spline (flowcon/transforms/splines/rational_quadratic.py:13-25,66-80). */
+typedef struct fc_rqs_config {
+  int32_t num_bins;      /* K; P = 3K-1 (linear tails) or 3K+1 (none) */
+  int32_t tails;         /* FC_TAILS_* */
+  int32_t identity_init; /* enable_identity_init: softplus beta = ln2 / (1 - min_derivative) */
+  int32_t inverse;       /* 0 forward, 1 inverse */
+  float left, right, bottom, top; /* linear tails: -tail_bound, tail_bound, -tail_bound, tail_bound */
+  float min_bin_width, min_bin_height, min_derivative;
+  float wh_scale; /* raw widths/heights are multiplied by this: 1/sqrt(hidden_features) where the
+                     reference divides in place (coupling.py:554-556, conditional.py:711-713), else 1 */
+} fc_rqs_config;
+
+/* A [B, *] fp32 matrix seen through an optional column list. */
+typedef struct fc_cols {
+  const int32_t* idx; /* device int32[n], or NULL for 0..n-1 */
+  int32_t n;
+} fc_cols;
+
+/*
+ * RQ-spline layer, forward or inverse (cfg->inverse):   replaces
+ *   unconstrained_rational_quadratic_spline / rational_quadratic_spline (rational_quadratic.py:13-181),
+ *   searchsorted (utils/torchutils.py:147-149), sum_except_batch (utils/torchutils.py:25-30) and the
+ *   column split/scatter of CouplingTransform.forward/inverse (coupling.py:82-83,96-98).
+ * For r < B, j < D_t:  y[r, tcols[j]] = spline(x[r, tcols[j]]; params[r, j*P .. j*P+P-1])
+ *                      y[r, ccols[i]] = x[r, ccols[i]]            (identity columns; ccols.n may be 0)
+ *                      logabsdet[r]   = (accumulate ? logabsdet[r] : 0) + sum_j log|dy/dx|
+ */
+int fc_rqs_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                 float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,
+                 int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, const fc_rqs_config* cfg,
+                 int32_t* status, void* stream);
+
+/*
+ * Backward of fc_rqs_apply (the reference differentiates its op chain with autograd).
+ * grad_params is written densely ([B, D_t*P], zero where the reference's gradient is zero).
+ *   grad_x[r, tcols[j]] = grad_y[r, tcols[j]] * dy/dx + grad_logabsdet[r] * d lad/dx
+ *   grad_x[r, ccols[i]] = grad_y[r, ccols[i]]
+ */
+int fc_rqs_backward(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                    const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet,
+                    float* grad_x, int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride,
+                    int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, const fc_rqs_config* cfg,
+                    void* stream);
+
+/* Affine element-wise transforms. */
+#define FC_AFFINE_BLOCKED 0     /* params[r] = [shift(D_t) | raw_scale(D_t)]      coupling.py:234-238 */
+#define FC_AFFINE_INTERLEAVED 1 /* params[r] = [raw_scale_0, shift_0, raw_scale_1, ...] autoregressive.py:124-129 */
+#define FC_SCALE_SIGMOID2 0       /* sigmoid(u + 2) + 1e-3                 coupling.py:224 */
+#define FC_SCALE_SOFTPLUS_CLAMP3 1 /* clamp(softplus(u) + 1e-3, 0, 3)       coupling.py:225 */
+#define FC_SCALE_SOFTPLUS_EPS 2    /* softplus(u) + 1e-3                    autoregressive.py:102 */
+
+/* replaces AffineCouplingTransform._coupling_transform_forward/_inverse (coupling.py:240-252) and
+ * MaskedAffineAutoregressiveTransform._elementwise_forward/_inverse (autoregressive.py:97-117). */
+int fc_affine_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                    float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,
+                    int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t layout, int32_t activation,
+                    int32_t inverse, void* stream);
+
+int fc_affine_backward(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                       const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet,
+                       float* grad_x, int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride,
+                       int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t layout, int32_t activation,
+                       int32_t inverse, void* stream);
+
+/*
+ * Sum-of-sigmoids + extended softplus (adaptive_sigmoids.py:111-142, nonlinearities.py:519-552).
+ * params[r, j*(3n+1) ..] = [shift_raw(n) | log_scale_raw(n) | softmax_raw(n) | esp_shift_raw].
+ * `offset` is added to the forward output / subtracted from the inverse input
+ * (MaskedSumOfSigmoidsTransform uses -0.5, autoregressive.py:309,313; the conditional wrapper 0).
+ * inverse != 0: per-element bracketed bisection (`bisection_iterations`, initial bracket +-`lim`,
+ * replaces MonotonicTransform.bisection_inverse no_analytic_inv/base.py:36-83) followed by two Newton
+ * steps with the analytic derivative (replaces newton_inverse :23-34); logabsdet is negated.
+ */
+int fc_sos_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                 float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,
+                 int64_t B, int32_t D, int32_t n_sigmoids, float offset, int32_t inverse,
+                 int32_t bisection_iterations, float lim, void* stream);
+
+int fc_sos_backward(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                    const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet,
+                    float* grad_x, int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride,
+                    int64_t B, int32_t D, int32_t n_sigmoids, void* stream);
+
+/* Base density tail: out[r] = -0.5 * sum_j z[r,j]^2 - 0.5*D*ln(2*pi) + logabsdet[r]
+ * (StandardNormal._log_prob distributions/normal.py:23-33 + flows/base.py:48). logabsdet may be NULL. */
+int fc_stdnormal_log_prob(const float* z, int64_t z_row_stride, const float* logabsdet, float* out,
+                          int64_t B, int32_t D, void* stream);
+
+/* Library / build info (also used by the loader test). */
+const char* fc_version(void);
+int fc_built_for_sm(void); /* 100 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWCON_B200_H */

@@ -1,0 +1,74 @@
+// TEST INFRASTRUCTURE ONLY — compiles flowconductor_b200/csrc/fc_math.cuh (the per-element arithmetic
+// the CUDA kernels execute) with g++ so that tests can check those exact statements against the oracle
+// on a machine without a GPU.  Never loaded by the product package.
+#include "../../flowconductor_b200/csrc/fc_math.cuh"
+
+using namespace fc;
+
+template <int KC>
+static void rqs_apply_t(const RqsParams& c, const float* x, const float* params, float* y, float* lad, long n,
+                        unsigned* status) {
+  for (long i = 0; i < n; ++i) rqs_eval<KC>(c, x[i], params + i * c.P, y[i], lad[i], *status);
+}
+
+template <int KC>
+static void rqs_backward_t(const RqsParams& c, const float* x, const float* params, const float* gy, const float* gl,
+                           float* gx, float* gp, long n) {
+  for (long i = 0; i < n; ++i) rqs_backward_elem<KC>(c, x[i], params + i * c.P, gy[i], gl[i], gx[i], gp + i * c.P);
+}
+
+extern "C" {
+
+// element-wise: x[n], params[n, P] -> y[n], lad[n] (per element, not reduced)
+int hm_rqs_apply(const float* x, const float* params, float* y, float* lad, long n, const fc_rqs_config* cfg,
+                 int use_generic, unsigned* status) {
+  RqsParams c;
+  int rc = make_rqs_params(cfg, c);
+  if (rc) return rc;
+  *status = 0;
+  if (!use_generic && c.K == 8) rqs_apply_t<8>(c, x, params, y, lad, n, status);
+  else if (!use_generic && c.K == 16) rqs_apply_t<16>(c, x, params, y, lad, n, status);
+  else if (!use_generic && c.K == 5) rqs_apply_t<5>(c, x, params, y, lad, n, status);
+  else rqs_apply_t<0>(c, x, params, y, lad, n, status);
+  return 0;
+}
+
+int hm_rqs_backward(const float* x, const float* params, const float* gy, const float* gl, float* gx, float* gp,
+                    long n, const fc_rqs_config* cfg, int use_generic) {
+  RqsParams c;
+  int rc = make_rqs_params(cfg, c);
+  if (rc) return rc;
+  if (!use_generic && c.K == 8) rqs_backward_t<8>(c, x, params, gy, gl, gx, gp, n);
+  else if (!use_generic && c.K == 16) rqs_backward_t<16>(c, x, params, gy, gl, gx, gp, n);
+  else if (!use_generic && c.K == 5) rqs_backward_t<5>(c, x, params, gy, gl, gx, gp, n);
+  else rqs_backward_t<0>(c, x, params, gy, gl, gx, gp, n);
+  return 0;
+}
+
+void hm_affine_apply(const float* x, const float* raw, const float* shift, float* y, float* lad, long n, int activation,
+                     int inverse) {
+  for (long i = 0; i < n; ++i) affine_eval(x[i], raw[i], shift[i], activation, inverse, y[i], lad[i]);
+}
+
+void hm_affine_backward(const float* x, const float* raw, const float* shift, const float* gy, const float* gl,
+                        float* gx, float* graw, float* gshift, long n, int activation, int inverse) {
+  for (long i = 0; i < n; ++i)
+    affine_backward_elem(x[i], raw[i], shift[i], activation, inverse, gy[i], gl[i], gx[i], graw[i], gshift[i]);
+}
+
+void hm_sos_apply(const float* x, const float* params, float* y, float* logj, long n, int n_sigmoids) {
+  for (long i = 0; i < n; ++i) sos_eval(x[i], params + i * (3 * n_sigmoids + 1), n_sigmoids, y[i], logj[i]);
+}
+
+void hm_sos_backward(const float* x, const float* params, const float* gy, const float* gl, float* gx, float* gp,
+                     long n, int n_sigmoids) {
+  const int P = 3 * n_sigmoids + 1;
+  for (long i = 0; i < n; ++i) sos_backward_elem(x[i], params + i * P, n_sigmoids, gy[i], gl[i], gx[i], gp + i * P);
+}
+
+void hm_sos_invert(const float* z, const float* params, float* x, float* logj, long n, int n_sigmoids, int iters,
+                   float lim) {
+  for (long i = 0; i < n; ++i)
+    sos_invert(z[i], params + i * (3 * n_sigmoids + 1), n_sigmoids, iters, lim, x[i], logj[i]);
+}
+}

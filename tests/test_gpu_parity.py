@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through torch.ops.flowcon_b200 -> C ABI) against
+  (1) golden vectors from the unmodified reference (fp32 + fp64),
+  (2) the oracle restatement on fresh seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes (forward o inverse = id, logabsdet
+      antisymmetry, identity-init known answer, outside-tail identity).
+
+Tolerances (north_star): outputs and logabsdet within 1e-5 relative in fp32, gradients within 1e-4, judged
+with the three-way rule of tests/helpers.assert_parity (the reference's own fp32 noise floor is ~1e-5).
+"""
+import math
+
+import pytest
+import torch
+
+from flowconductor_b200 import _cabi, ops, transforms, workloads
+from flowconductor_b200.transforms import splines
+from oracle import restated
+from tests.helpers import assert_parity, golden_state, load_golden
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def fn_gold():
+    return load_golden("functions")
+
+
+def _spline_call(gold, name, dev, requires_grad=False):
+    k, lin, tb, inv, ident = gold[name + "/meta"].tolist()
+    k = int(k)
+    x = gold[name + "/x"].to(dev).requires_grad_(requires_grad)
+    p = gold[name + "/params"].to(dev).requires_grad_(requires_grad)
+    uw, uh, ud = p[..., :k], p[..., k:2 * k], p[..., 2 * k:]
+    kw = dict(inverse=bool(inv), enable_identity_init=bool(ident))
+    if lin:
+        y, lad = transforms.unconstrained_rational_quadratic_spline(x, uw, uh, ud, tails="linear", tail_bound=tb,
+                                                                    **kw)
+    else:
+        y, lad = transforms.rational_quadratic_spline(x, uw, uh, ud, **kw)
+    return x, p, y, lad, tb
+
+
+RQ_CASES = ["rq_fwd_lin_k8", "rq_inv_lin_k8", "rq_fwd_lin_k16_id", "rq_inv_lin_k16_id", "rq_fwd_none_k5",
+            "rq_inv_none_k5", "rq_fwd_lin_k10_b1", "rq_fwd_lin_k8_zero_id"]
+
+
+@pytest.mark.parametrize("name", RQ_CASES)
+def test_spline_functions_match_reference(fn_gold, dev, name):
+    _, _, y, lad, tb = _spline_call(fn_gold, name, dev)
+    assert_parity(y, fn_gold[name + "/y32"], fn_gold[name + "/y64"], OUT_TOL, max(tb, 1.0), name + " outputs")
+    assert_parity(lad, fn_gold[name + "/lad32"], fn_gold[name + "/lad64"], OUT_TOL, 1.0, name + " logabsdet")
+
+
+@pytest.mark.parametrize("name", ["rq_fwd_lin_k8", "rq_inv_lin_k8", "rq_fwd_lin_k16_id", "rq_fwd_none_k5"])
+def test_spline_gradients_match_reference(fn_gold, dev, name):
+    x, p, y, lad, _ = _spline_call(fn_gold, name, dev, requires_grad=True)
+    gy, gl = fn_gold[name + "/gy"].to(dev), fn_gold[name + "/gl"].to(dev)
+    gx, gp = torch.autograd.grad((y * gy).sum() + (lad * gl).sum(), [x, p])
+    s = max(1.0, fn_gold[name + "/gx64"].abs().median().item())
+    assert_parity(gx, fn_gold[name + "/gx32"], fn_gold[name + "/gx64"], GRAD_TOL, s, name + " grad x")
+    s = max(1e-2, fn_gold[name + "/gp64"].abs().mean().item())
+    assert_parity(gp, fn_gold[name + "/gp32"], fn_gold[name + "/gp64"], GRAD_TOL, s, name + " grad params")
+
+
+def test_bin_parity_through_outputs(fn_gold, dev):
+    """Bins identical except within 1e-6 (normalised units) of a knot: a wrong bin away from a knot would
+    move the output by O(bin width); near a knot the spline is C1 so outputs still agree."""
+    name = "rq_fwd_lin_k8"
+    _, _, y, _, _ = _spline_call(fn_gold, name, dev)
+    err = (y.cpu().double() - fn_gold[name + "/y64"]).abs()
+    assert err.max() < 1e-4
+
+
+def test_identity_init_known_answers(dev):
+    # tests/transforms/splines/rational_quadratic_test.py:33-62 (constrained, K+1 zero derivatives)
+    k, shape = 10, (2, 3, 4)
+    z = torch.zeros(*shape, k, device=dev)
+    zd = torch.zeros(*shape, k + 1, device=dev)
+    x = torch.rand(*shape, device=dev)
+    for inverse in (False, True):
+        y, lad = transforms.rational_quadratic_spline(x, z, z, zd, inverse=inverse, enable_identity_init=True)
+        assert (y - x).abs().max() <= 1e-6
+        assert lad.abs().max() <= 1e-6
+    # :116-146 all inputs in the tails -> identity, zero logabsdet
+    xt = torch.sign(torch.randn(*shape, device=dev)) * (1.0 + torch.rand(*shape, device=dev))
+    y, lad = transforms.unconstrained_rational_quadratic_spline(xt, z, z, zd[..., :k - 1], tail_bound=1.0,
+                                                                enable_identity_init=True)
+    assert torch.equal(y, xt) and torch.equal(lad, torch.zeros_like(lad))
+
+
+def test_domain_errors(dev):
+    # tests/transforms/nonlinearities_test.py:60-76
+    p = torch.zeros(1, 16, device=dev)
+    for bad in (-1.0, -0.1, 1.1, 2.0):
+        with pytest.raises(transforms.InputOutsideDomain):
+            transforms.rational_quadratic_spline(torch.tensor([bad], device=dev), p[:, :5], p[:, 5:10], p[:, 10:])
+    with pytest.raises(ValueError):
+        transforms.rational_quadratic_spline(torch.zeros(1, device=dev), p[:, :5], p[:, 5:10], p[:, 10:],
+                                             min_bin_width=0.3)
+    with pytest.raises(RuntimeError):
+        transforms.unconstrained_rational_quadratic_spline(torch.zeros(1, device=dev), p[:, :5], p[:, 5:10],
+                                                           p[:, 10:14], tails="cubic")
+
+
+@pytest.mark.parametrize("k,tb,ident", [(8, 3.0, False), (16, 3.0, True), (7, 2.0, False), (33, 5.0, True)])
+def test_spline_matches_oracle_on_fresh_inputs(dev, k, tb, ident):
+    """Fresh seeded inputs vs the oracle (fp32 and fp64), incl. an odd K and a K on the runtime-K path."""
+    g = torch.Generator().manual_seed(100 + k)
+    x = torch.randn(513, 11, generator=g) * tb * 0.6
+    p = torch.randn(513, 11, 3 * k - 1, generator=g) * 2
+    for inverse in (False, True):
+        args = lambda t: (t[..., :k], t[..., k:2 * k], t[..., 2 * k:])  # noqa: E731
+        kw = dict(inverse=inverse, tails="linear", tail_bound=tb, enable_identity_init=ident)
+        r32y, r32l = restated.unconstrained_rational_quadratic_spline(x, *args(p), **kw)
+        r64y, r64l = restated.unconstrained_rational_quadratic_spline(x.double(), *args(p.double()), **kw)
+        y, lad = transforms.unconstrained_rational_quadratic_spline(x.to(dev), *args(p.to(dev)), **kw)
+        assert_parity(y, r32y, r64y, OUT_TOL, tb, "oracle outputs K=%d inv=%s" % (k, inverse))
+        assert_parity(lad, r32l, r64l, OUT_TOL, 1.0, "oracle logabsdet K=%d inv=%s" % (k, inverse))
+
+
+def test_empty_and_ragged_batches(dev):
+    k = 8
+    for n in (0, 1, 7, 255, 257):
+        x = torch.randn(n, 5, device=dev)
+        p = torch.randn(n, 5 * 23, device=dev)
+        y, lad, _ = ops.rqs_layer(x, p, None, None, k, _cabi.TAILS_LINEAR, False, False, -3.0, 3.0, -3.0, 3.0, 1e-3,
+                                  1e-3, 1e-3, 1.0)
+        assert y.shape == (n, 5) and lad.shape == (n,)
+        if n:
+            ry, rl = restated.rq_elementwise(x.cpu(), p.cpu(), k, "linear", 3.0, False, None, False)
+            assert (y.cpu() - ry).abs().max() < 1e-4 and (lad.cpu() - rl).abs().max() < 1e-3
+
+
+def test_strided_inputs_and_column_lists(dev):
+    """Coupling-style call: full-width rows, int32 column lists, non-contiguous row stride."""
+    g = torch.Generator().manual_seed(5)
+    B, D, k = 300, 10, 8
+    big = torch.randn(B, D + 6, generator=g).to(dev)
+    x = big[:, 3:3 + D]  # row stride D+6, last dim dense
+    tc = torch.tensor([0, 3, 4, 8], dtype=torch.int32, device=dev)
+    cc = torch.tensor([1, 2, 5, 6, 7, 9], dtype=torch.int32, device=dev)
+    p = (torch.randn(B, 4 * 23, generator=g) * 2).to(dev)
+    y, lad, _ = ops.rqs_layer(x, p, tc, cc, k, _cabi.TAILS_LINEAR, False, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3,
+                              1e-3, 0.25)
+    xc = x.cpu()
+    ry, rl = restated.rq_elementwise(xc[:, tc.cpu().long()], p.cpu(), k, "linear", 3.0, False, 4.0, False)
+    assert torch.equal(y[:, cc.long()].cpu(), xc[:, cc.cpu().long()])
+    assert (y[:, tc.long()].cpu() - ry).abs().max() < 1e-4
+    assert (lad.cpu() - rl).abs().max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# affine / sum of sigmoids function level
+# ------------------------------------------------------------------------------------------------
+def test_affine_kernels(fn_gold, dev):
+    x = fn_gold["affine/x"].to(dev)
+    p = fn_gold["affine/params"].to(dev)
+    for act, name in ((_cabi.SCALE_SIGMOID2, "blocked_sigmoid2"), (_cabi.SCALE_SOFTPLUS_CLAMP3,
+                                                                    "blocked_softplus_clamp3")):
+        y, lad = ops.affine_layer(x, p, None, None, _cabi.AFFINE_BLOCKED, act, False)
+        assert_parity(y, fn_gold["affine/%s_fwd_y32" % name], fn_gold["affine/%s_fwd_y64" % name], OUT_TOL, 1.0, name)
+        assert_parity(lad, fn_gold["affine/%s_fwd_lad32" % name], fn_gold["affine/%s_fwd_lad64" % name], OUT_TOL, 1.0,
+                      name + " lad")
+        yi, ladi = ops.affine_layer(x, p, None, None, _cabi.AFFINE_BLOCKED, act, True)
+        assert_parity(yi, fn_gold["affine/%s_inv_y32" % name], fn_gold["affine/%s_inv_y64" % name], OUT_TOL, 1.0,
+                      name + " inverse")
+        assert torch.equal(ladi, -lad)
+    y, lad = ops.affine_layer(x, p, None, None, _cabi.AFFINE_INTERLEAVED, _cabi.SCALE_SOFTPLUS_EPS, False)
+    assert_parity(y, fn_gold["affine/interleaved_fwd_y32"], fn_gold["affine/interleaved_fwd_y64"], OUT_TOL, 1.0, "maf")
+    assert_parity(lad, fn_gold["affine/interleaved_fwd_lad32"], fn_gold["affine/interleaved_fwd_lad64"], OUT_TOL, 1.0,
+                  "maf lad")
+
+
+@pytest.mark.parametrize("name", ["sos_n10", "sos_n3_wide"])
+def test_sum_of_sigmoids_kernels(fn_gold, dev, name):
+    ns = int(fn_gold[name + "/meta"][0])
+    x = fn_gold[name + "/x"].to(dev).requires_grad_(True)
+    raw = fn_gold[name + "/params"].to(dev).requires_grad_(True)
+    n, d = x.shape
+    y, lad = ops.sos_layer(x, raw.reshape(n, -1), ns, 0.0, False, 50, 120.0)
+    floor = max(1.0, fn_gold[name + "/y64"].abs().median().item())
+    assert_parity(y, fn_gold[name + "/y32"], fn_gold[name + "/y64"], OUT_TOL, floor, name + " y")
+    assert_parity(lad, fn_gold[name + "/lad32"], fn_gold[name + "/lad64"], OUT_TOL, 1.0, name + " lad")
+    gy, gl = fn_gold[name + "/gy"].to(dev), fn_gold[name + "/gl"].to(dev)
+    gx, gp = torch.autograd.grad((y * gy).sum() + (lad * gl).sum(), [x, raw])
+    s = max(1e-2, fn_gold[name + "/gx64"].abs().mean().item())
+    assert_parity(gx, fn_gold[name + "/gx32"], fn_gold[name + "/gx64"], GRAD_TOL, s, name + " gx")
+    s = max(1e-2, fn_gold[name + "/gp64"].abs().mean().item())
+    assert_parity(gp, fn_gold[name + "/gp32"], fn_gold[name + "/gp64"], GRAD_TOL, s, name + " gp")
+    # numerical inverse: reference tests accept eps 1e-5 .. 1e-3 (adaptive_sigmoid_test.py:40-41,64-79)
+    with torch.no_grad():
+        xi, ladi = ops.sos_layer(fn_gold[name + "/y32"].to(dev), raw.reshape(n, -1), ns, 0.0, True, 50, 120.0)
+    ref = fn_gold[name + "/inv_x64"]
+    scale = ref.abs().clamp_min(1.0)
+    assert ((xi.cpu().double() - ref).abs() / scale).max() < 1e-3
+    assert (ladi.cpu().double() - fn_gold[name + "/inv_lad64"]).abs().max() < 5e-3
+
+
+def test_sum_of_sigmoids_large_inputs(dev):
+    # adaptive_sigmoid_test.py:64-79: inverse at |x| ~ 200 still consistent
+    t = transforms.SumOfSigmoids(features=3, n_sigmoids=5).to(dev)
+    x = torch.tensor([[200.0, -200.0, 150.0], [-180.0, 0.5, 199.0]], device=dev)
+    with torch.no_grad():
+        y, lad = t(x)
+        xi, ladi = t.inverse(y)
+    assert ((xi - x).abs() / x.abs().clamp_min(1)).max() < 1e-4
+    assert (lad + ladi).abs().max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# model level: the drop-in classes with the reference's weights
+# ------------------------------------------------------------------------------------------------
+MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
+          "maf_sos_small", "prq_coupling_notails_small"]
+
+
+def _load(name, dev):
+    gold = load_golden(name)
+    wl = workloads.get_workload(name)
+    flow = workloads.build_flow(wl)
+    flow.load_state_dict(golden_state(gold), strict=True)
+    return gold, wl, flow.to(dev)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_flow_matches_reference(dev, name):
+    gold, wl, flow = _load(name, dev)
+    x = gold["x"].to(dev)
+    ctx = gold["context"].to(dev) if "context" in gold else None
+    with torch.no_grad():
+        z, lad = flow._transform(x, context=ctx)
+        lp = flow.log_prob(x, context=ctx)
+        xi, ladi = flow._transform.inverse(gold["noise"].to(dev), context=ctx)
+    yfloor = max(1.0, gold["fwd_y64"].abs().median().item())
+    assert_parity(z, gold["fwd_y32"], gold["fwd_y64"], OUT_TOL, yfloor, name + " forward outputs")
+    assert_parity(lad, gold["fwd_lad32"], gold["fwd_lad64"], OUT_TOL, 1.0, name + " forward logabsdet")
+    assert_parity(lp, gold["log_prob32"], gold["log_prob64"], OUT_TOL, 1.0, name + " log_prob")
+    numerical = "sos" in name or name == "cfg4_small"
+    tol = 1e-3 if numerical else OUT_TOL  # numerical inverse: reference test eps (1e-5 .. 1e-3)
+    yfloor = max(1.0, gold["inv_y64"].abs().median().item())
+    assert_parity(xi, gold["inv_y32"], gold["inv_y64"], tol, yfloor, name + " inverse outputs")
+    assert_parity(ladi, gold["inv_lad32"], gold["inv_lad64"], 10 * tol if numerical else tol, 1.0,
+                  name + " inverse logabsdet")
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small",
+                                  "cond_prq_small"])
+def test_flow_parameter_gradients_match_reference(dev, name):
+    """loss = -log_prob(x).mean(); backward through our kernels vs the reference's autograd."""
+    gold, wl, flow = _load(name, dev)
+    x = gold["x"].to(dev)
+    ctx = gold["context"].to(dev) if "context" in gold else None
+    loss = -flow.log_prob(x, context=ctx).mean()
+    loss.backward()
+    assert_parity(loss, gold["loss32"], gold["loss64"], OUT_TOL, 1.0, name + " loss")
+    for pn, p in flow.named_parameters():
+        r32, r64 = gold["grad32/" + pn], gold["grad64/" + pn]
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        scale = max(1e-6, r64.abs().max().item())
+        assert_parity(g / scale, r32 / scale, r64 / scale, GRAD_TOL, 1.0, name + " grad " + pn)
+
+
+def test_sample_and_log_prob_consistency(dev):
+    # tests/flows/base_test.py:54-69: sample_and_log_prob == log_prob(sample)
+    _, _, flow = _load("cfg2_small", dev)
+    with torch.no_grad():
+        samples, lp = flow.sample_and_log_prob(64)
+        lp2 = flow.log_prob(samples)
+        assert flow.sample(10).shape == (10, 64)
+    assert samples.shape == (64, 64) and lp.shape == (64,)
+    assert ((lp - lp2).abs() / lp2.abs().clamp_min(1)).max() < 1e-4
+
+
+def test_patch_reference_functions(dev):
+    """The function-level seam with the reference's own calling convention (strided views of one
+    [B, D, 3K-1] tensor, coupling.py:550-552)."""
+    g = torch.Generator().manual_seed(3)
+    B, D, K = 64, 6, 8
+    x = (torch.randn(B, D, generator=g) * 2).to(dev)
+    tp = torch.randn(B, D, 3 * K - 1, generator=g).to(dev)
+    y, lad = splines.unconstrained_rational_quadratic_spline(x, tp[..., :K], tp[..., K:2 * K], tp[..., 2 * K:],
+                                                             tails="linear", tail_bound=3.0)
+    ry, rl = restated.unconstrained_rational_quadratic_spline(x.cpu(), tp.cpu()[..., :K], tp.cpu()[..., K:2 * K],
+                                                              tp.cpu()[..., 2 * K:], tails="linear", tail_bound=3.0)
+    assert (y.cpu() - ry).abs().max() < 1e-4 and (lad.cpu() - rl).abs().max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json sizes; the oracle is too slow here, so size-independent checks)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_cfg2_roundtrip_and_spot_check(dev):
+    wl = workloads.get_workload("cfg2")
+    flow = workloads.build_flow(wl)
+    state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl)
+    flow.load_state_dict(state)
+    flow = flow.to(dev)
+    B = wl["batch"]
+    x = torch.randn(B, 64, generator=torch.Generator(device=dev).manual_seed(1234), device=dev)
+    with torch.no_grad():
+        z, lad = flow._transform(x)
+        lp = flow.log_prob(x)
+        xr, ladr = flow._transform.inverse(z)
+    assert torch.isfinite(lp).all()
+    assert (xr - x).abs().max() < 2e-3            # encode -> decode round trip (reference eps 1e-3)
+    assert (lad + ladr).abs().max() < 2e-2        # logabsdet antisymmetry over 8 layers
+    # log_prob == base density of the noise + logabsdet
+    ref_lp = -0.5 * (z.double() ** 2).sum(1) - 0.5 * 64 * math.log(2 * math.pi) + lad.double()
+    assert (lp.double() - ref_lp).abs().max() < 1e-3
+    # oracle spot check on the first and last 512 rows of the SAME full-size launch
+    specs = workloads.oracle_specs(wl)
+    rows = torch.cat([torch.arange(512), torch.arange(B - 512, B)])
+    cpu_state = {k: v.cpu() for k, v in flow.state_dict().items()}
+    with torch.no_grad():
+        o32 = restated.flow_log_prob(cpu_state, specs, x[rows].cpu())
+        o64 = restated.flow_log_prob({k: (v.double() if v.is_floating_point() else v) for k, v in cpu_state.items()},
+                                     specs, x[rows].cpu().double())
+    assert_parity(lp[rows], o32, o64, OUT_TOL, 1.0, "cfg2 full-size log_prob rows")
+
+
+def test_full_size_cfg3_training_step_is_finite(dev):
+    wl = workloads.get_workload("cfg3")
+    flow = workloads.build_flow(wl).to(dev)
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-3, weight_decay=1e-5)
+    x = torch.randn(32768, 16, device=dev)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = -flow.log_prob(x).mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]

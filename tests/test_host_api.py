@@ -1,0 +1,134 @@
+"""CPU tests of the host side: API mirror, state_dict compatibility with the reference, C-ABI exports,
+and the 'no CPU fallback' contract."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import flowconductor_b200 as fcb
+from flowconductor_b200 import _cabi, transforms, workloads
+from flowconductor_b200.nn import nets
+from flowconductor_b200.utils import torchutils
+from tests.helpers import ROOT, golden_state, load_golden
+
+MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
+          "maf_sos_small", "prq_coupling_notails_small"]
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_reference_state_dict_loads_strictly(name):
+    """Golden state_dicts were saved from the unmodified reference: same keys, same shapes."""
+    gold = load_golden(name)
+    flow = workloads.build_flow(workloads.get_workload(name))
+    state = golden_state(gold)
+    assert set(flow.state_dict().keys()) == set(state.keys())
+    flow.load_state_dict(state, strict=True)
+    for k, v in flow.state_dict().items():
+        assert v.shape == state[k].shape, k
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "flowcon_b200.h")).read()
+    declared = set(re.findall(r"\b(fc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert os.path.exists(_cabi.LIB_PATH), "build the library first: python -m flowconductor_b200.build"
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), "libflowcon_b200.so does not export " + sym
+    assert set(_cabi.EXPORTS) <= declared
+    lib.fc_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.fc_version()
+    assert lib.fc_built_for_sm() == 100
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    lib = _cabi.lib()
+    cfg = _cabi.RqsConfig(8, 1, 0, 0, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0)
+    none = _cabi.Cols(None, 0)
+    # null pointers -> FC_ERR_INVALID_ARGUMENT before any CUDA call
+    assert lib.fc_rqs_apply(None, 0, None, 0, None, 0, None, 0, 4, 2, none, none, ctypes.byref(cfg), None, None) == -1
+    bad = _cabi.RqsConfig(2000, 1, 0, 0, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0)
+    assert lib.fc_rqs_apply(None, 0, None, 0, None, 0, None, 0, 4, 2, none, none, ctypes.byref(bad), None, None) < 0
+    assert lib.fc_sos_apply(None, 0, None, 0, None, 0, None, 0, 4, 2, 10, 0.0, 0, 50, 120.0, None) == -1
+    assert lib.fc_affine_apply(None, 0, None, 0, None, 0, None, 0, 4, 2, none, none, 0, 0, 0, None) == -1
+
+
+def test_cpu_tensors_fail_loudly():
+    """north_star: no CPU fallback.  A CPU tensor must raise, not silently take another path."""
+    flow = workloads.build_flow(workloads.get_workload("cfg2_small"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        flow.log_prob(torch.randn(4, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        transforms.unconstrained_rational_quadratic_spline(torch.zeros(3), torch.zeros(3, 4), torch.zeros(3, 4),
+                                                           torch.zeros(3, 3))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libflowcon_b200.so")
+    with pytest.raises(_cabi.LibraryMissing):
+        _cabi.lib()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "flowconductor_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+                assert "hostmath" not in src, os.path.join(dirpath, f)
+
+
+def test_masks_and_helpers():
+    assert torchutils.create_alternating_binary_mask(5, even=True).tolist() == [1, 0, 1, 0, 1]
+    assert torchutils.create_alternating_binary_mask(5, even=False).tolist() == [0, 1, 0, 1, 0]
+    assert torchutils.create_mid_split_binary_mask(5).tolist() == [1, 1, 1, 0, 0]
+    assert int(torchutils.create_random_binary_mask(7).sum()) == 4
+    assert torchutils.tile(torch.tensor([1, 2, 3]), 2).tolist() == [1, 1, 2, 2, 3, 3]
+    x = torch.arange(24.0).reshape(2, 3, 4)
+    assert torchutils.sum_except_batch(x).tolist() == x.reshape(2, -1).sum(1).tolist()  # torchutils_test.py:106-114
+    assert torchutils.repeat_rows(torch.tensor([[1], [2]]), 2).flatten().tolist() == [1, 1, 2, 2]
+    assert torchutils.merge_leading_dims(x, 2).shape == (6, 4)
+    assert torchutils.split_leading_dim(torch.zeros(6, 4), [2, 3]).shape == (2, 3, 4)
+
+
+def test_made_masks_are_autoregressive():
+    """tests/transforms/made_test.py:109-137: the product of all masks is strictly lower triangular
+    (output of feature d sees only features < d)."""
+    d, h, mult = 6, 16, 3
+    made = transforms.MADE(features=d, hidden_features=h, num_blocks=2, output_multiplier=mult)
+    total = made.initial_layer.mask
+    for block in made.blocks:
+        total = block.linear_layers[1].mask @ (block.linear_layers[0].mask @ total) + total
+    total = made.final_layer.mask @ total
+    total = (total > 0).reshape(d, mult, d)
+    for out_f in range(d):
+        for in_f in range(d):
+            if in_f >= out_f:
+                assert not total[out_f, :, in_f].any()
+    assert not hasattr(made, "hidden_features")  # autoregressive.py:589 relies on this
+
+
+def test_coupling_constructor_contract():
+    net = lambda i, o: nets.ResidualNet(i, o, hidden_features=8)  # noqa: E731
+    with pytest.raises(ValueError):
+        transforms.PiecewiseRationalQuadraticCouplingTransform(torch.zeros(2, 2), net)
+    with pytest.raises(ValueError):
+        transforms.PiecewiseRationalQuadraticCouplingTransform(torch.zeros(0), net)
+    t = transforms.PiecewiseRationalQuadraticCouplingTransform([1, 0, 1, 0], net, num_bins=8, tails="linear")
+    assert t.transform_features.tolist() == [0, 2] and t.identity_features.tolist() == [1, 3]
+    assert t.transform_net.final_layer.out_features == 2 * 23
+    t = transforms.PiecewiseRationalQuadraticCouplingTransform([1, 0, 1, 0], net, num_bins=8, tails=None)
+    assert t.transform_net.final_layer.out_features == 2 * 25
+    with pytest.raises(ValueError):
+        t.forward(torch.zeros(3, 5))
+    with pytest.raises(TypeError):
+        transforms.ConditionalSumOfSigmoidsTransform(4, 8, context_features=2).forward(torch.zeros(3, 4))
+    with pytest.raises(transforms.InverseNotAvailable):
+        transforms.Transform().inverse(torch.zeros(1, 1))
+
+
+def test_package_metadata():
+    assert fcb.__version__
