@@ -29,8 +29,8 @@ import torch  # noqa: E402
 METRIC = "flow_log_prob_samples_per_sec"
 UNIT = "samples/s"
 WORKLOAD = "cfg2"
-CPU_SAMPLE_ROWS = 16384       # cpu_baseline leg of the default run
-REF_STEP_ROWS = 8192          # --impl reference: rows per step (bounded so K+W steps end within minutes)
+CPU_SAMPLE_ROWS = 262144      # cpu_baseline leg of the default run (~10-30 s of host work)
+REF_STEP_ROWS = 65536         # --impl reference: rows per step (bounded so K+W steps end within minutes)
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 
 

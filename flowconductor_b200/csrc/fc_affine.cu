@@ -124,7 +124,9 @@ extern "C" int fc_affine_apply(const float* x, int64_t x_row_stride, const float
                                int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t layout,
                                int32_t activation, int32_t inverse, void* stream) {
   int rc = check_layer_args(x, params, y, B, D_t, tcols, ccols);
-  if (rc != FC_OK || !logabsdet) return FC_ERR_INVALID_ARGUMENT;
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!logabsdet) return FC_ERR_INVALID_ARGUMENT;
   if (layout != FC_AFFINE_BLOCKED && layout != FC_AFFINE_INTERLEAVED) return FC_ERR_INVALID_ARGUMENT;
   if (activation < FC_SCALE_SIGMOID2 || activation > FC_SCALE_SOFTPLUS_EPS) return FC_ERR_INVALID_ARGUMENT;
   if (B == 0) return FC_OK;
@@ -145,7 +147,9 @@ extern "C" int fc_affine_backward(const float* x, int64_t x_row_stride, const fl
                                   int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t layout,
                                   int32_t activation, int32_t inverse, void* stream) {
   int rc = check_layer_args(x, params, grad_x, B, D_t, tcols, ccols);
-  if (rc != FC_OK || !grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
   if (layout != FC_AFFINE_BLOCKED && layout != FC_AFFINE_INTERLEAVED) return FC_ERR_INVALID_ARGUMENT;
   if (activation < FC_SCALE_SIGMOID2 || activation > FC_SCALE_SOFTPLUS_EPS) return FC_ERR_INVALID_ARGUMENT;
   if (B == 0) return FC_OK;
@@ -163,8 +167,9 @@ extern "C" int fc_affine_backward(const float* x, int64_t x_row_stride, const fl
 
 extern "C" int fc_stdnormal_log_prob(const float* z, int64_t z_row_stride, const float* logabsdet, float* out,
                                      int64_t B, int32_t D, void* stream) {
-  if (!z || !out || B < 0 || D < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (B < 0 || D < 1) return FC_ERR_INVALID_ARGUMENT;
   if (B == 0) return FC_OK;
+  if (!z || !out) return FC_ERR_INVALID_ARGUMENT;
   const int seg = lane_map(D).seg;
   // distributions/normal.py:18-21: log_z = 0.5 * D * log(2 pi) (fp64 buffer, applied to an fp32 tensor)
   const float log_z = (float)(0.5 * (double)D * log(2.0 * 3.14159265358979323846));

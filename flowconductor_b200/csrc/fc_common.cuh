@@ -64,6 +64,11 @@ inline int tile_rows(int row_floats, const LaneMap& m, int64_t B) {
 
 __device__ __forceinline__ float seg_reduce_sum(float v, int seg) {
   // xor-shuffle sum over aligned segments of `seg` lanes (seg is a power of two <= 32)
+  if (seg == 32) {  // the common case (D_t >= 32), fully unrolled
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  }
   for (int off = seg >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }

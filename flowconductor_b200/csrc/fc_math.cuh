@@ -35,15 +35,75 @@
 #define FC_SUB(a, b) ((a) - (b))
 #endif
 
+// Fast primitives (DESIGN.md "arithmetic budget"): the layer kernels are instruction-issue bound with IEEE
+// division / full-range expf, so the hot path uses the SFU approximations where the error analysis allows:
+//   fc_exp2: ex2.approx (~1-2 ulp).  Used for softmax numerators 2^(t - max), t <= max: the absolute error of a
+//            softmax term is <= e^-|x| |x| 6e-8 <= 2.2e-8, below the fp32 rounding of the term itself.
+//   fc_rcp : rcp.approx + one Newton step (<= 1 ulp), a*fc_rcp(b) replaces a/b (<= 1.5 ulp vs 0.5 ulp).
+//   fc_sqrt: sqrt.approx (max rel. error 2^-23).
+// Host builds (test shim) use the libm equivalents.
+#if defined(__CUDA_ARCH__)
+#define FC_DEVICE_MATH 1
+#else
+#define FC_DEVICE_MATH 0
+#endif
+
+#define FC_LOG2E 1.4426950408889634f
+
 #define FC_MAX_BINS_GENERIC 64  // runtime-K instantiation keeps its arrays in local memory up to this
 
 namespace fc {
+
+FC_HD float fc_exp2(float x) {
+#if FC_DEVICE_MATH
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return exp2f(x);
+#endif
+}
+
+FC_HD float fc_rcp(float x) {
+#if FC_DEVICE_MATH
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+#else
+  return 1.f / x;
+#endif
+}
+
+FC_HD float fc_sqrt(float x) {
+#if FC_DEVICE_MATH
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return sqrtf(x);
+#endif
+}
+
+// a / b to <= 0.5 ulp + epsilon: approximate reciprocal, then one residual correction of the QUOTIENT.
+FC_HD float fc_div(float a, float b) {
+#if FC_DEVICE_MATH
+  const float r = fc_rcp(b);
+  const float q = a * r;
+  return fmaf(fmaf(-b, q, a), r, q);
+#else
+  return a / b;
+#endif
+}
+
+// exp(x) for the softplus argument (|x| <= 20): relative error <= |x| 6e-8 + ~2 ulp
+FC_HD float fc_exp(float x) { return fc_exp2(x * FC_LOG2E); }
 
 // Device-side copy of fc_rqs_config plus host-precomputed constants.
 struct RqsParams {
   int K, tails, identity_init, inverse;
   float left, right, bottom, top;
   float min_w, min_h, min_d, wh_scale;
+  float wh_scale_l2e;    // wh_scale * log2(e): the softmax is evaluated in base 2
   float beta, inv_beta;  // softplus beta (rational_quadratic.py:100-103)
   float pad_deriv;       // derivative at the two padded boundary knots, linear tails (:33-36 then :104)
   float coef_w, coef_h;  // 1 - min*K (:92, :107)
@@ -53,7 +113,7 @@ struct RqsParams {
 FC_HD float softplus_beta(float x, float beta, float inv_beta) {
   // torch.nn.functional.softplus(x, beta, threshold=20)
   const float bx = x * beta;
-  return bx > 20.f ? x : log1pf(expf(bx)) * inv_beta;
+  return bx > 20.f ? x : log1pf(fc_exp(bx)) * inv_beta;
 }
 
 FC_HD float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -87,6 +147,7 @@ inline int make_rqs_params(const fc_rqs_config* cfg, RqsParams& c) {
   c.min_h = cfg->min_bin_height;
   c.min_d = cfg->min_derivative;
   c.wh_scale = cfg->wh_scale;
+  c.wh_scale_l2e = (float)((double)cfg->wh_scale * 1.4426950408889634);
   const double beta = cfg->identity_init ? log(2.0) / (1.0 - (double)cfg->min_derivative) : 1.0;
   c.beta = (float)beta;
   c.inv_beta = (float)(1.0 / beta);
@@ -100,58 +161,84 @@ inline int make_rqs_params(const fc_rqs_config* cfg, RqsParams& c) {
   return FC_OK;
 }
 
-// derivative value at knot j (0..K).  `pd` points at the raw derivative block of this feature.
+// derivative value at knot j (0..K).  `pd` points at the raw derivative block of this feature.  Branch-free:
+// with linear tails the two boundary knots take the padded constant (rational_quadratic.py:33-36).
 FC_HD float knot_derivative(const RqsParams& c, int K, const float* pd, int j) {
-  float raw;
-  if (c.tails == FC_TAILS_LINEAR) {
-    if (j == 0 || j == K) return c.pad_deriv;
-    raw = pd[j - 1];
-  } else {
-    raw = pd[j];
-  }
-  return c.min_d + softplus_beta(raw, c.beta, c.inv_beta);
+  const bool lin = c.tails == FC_TAILS_LINEAR;
+  const bool padded = lin && (j == 0 || j == K);
+  const int idx = padded ? 0 : (lin ? j - 1 : j);
+  const float d = c.min_d + softplus_beta(pd[idx], c.beta, c.inv_beta);
+  return padded ? c.pad_deriv : d;
 }
 
-// softmax numerators e[i] = exp(scale*u[i] - max) and 1/sum.
+// softmax numerators e[i] = 2^(scale_l2e*u[i] - max) == exp(scale*u[i] - max'); returns their sum.
 template <int KC>
-FC_HD float softmax_numerators(const float* u, int K, float scale, float* e) {
+FC_HD float softmax_numerators(const float* u, int K, float scale_l2e, float* e) {
   float m = -INFINITY;
 #pragma unroll
   for (int i = 0; i < (KC ? KC : K); ++i) {
-    e[i] = u[i] * scale;
+    e[i] = u[i] * scale_l2e;
     m = fmaxf(m, e[i]);
   }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < (KC ? KC : K); ++i) {
-    e[i] = expf(e[i] - m);
+    e[i] = fc_exp2(e[i] - m);
     s += e[i];
   }
-  return 1.f / s;
+  return s;
 }
 
-// Walk the knots built from softmax numerators e[] (see file header).  If `search`, find the bin of x:
-// k = largest i with knot_i <= x; otherwise use the given k.  Returns knot_k (lo_k) and knot_{k+1} (hi_k).
-template <int KC, bool kSearch>
-FC_HD void knot_scan(const float* e, float inv_sum, int K, float lo, float hi, float min_size, float coef,
-                     float x, int& k, float& lo_k, float& hi_k) {
-  const float span = hi - lo;
-  float cum = 0.f, prev = lo;
-  if (kSearch) k = 0;
-  lo_k = lo;
-  hi_k = hi;
+// One running-sum step of the knot pipeline.  torch.cumsum on CPU accumulates fp32 inputs in double
+// (acc_type<float,false>), so for more than 8 bins a plain fp32 running sum is measurably worse than the
+// reference; Kahan compensation is used there.
+template <bool kCompensated>
+FC_HD void knot_accumulate(float size, float& cum, float& comp) {
+  if (kCompensated) {
+    const float yv = FC_SUB(size, comp);
+    const float t = FC_ADD(cum, yv);
+    comp = FC_SUB(FC_SUB(t, cum), yv);
+    cum = t;
+  } else {
+    cum = FC_ADD(cum, size);
+  }
+}
+
+// Walk the knots of BOTH axes in one pass.  The "search" axis (widths for the forward map, heights for the
+// inverse) locates the bin: k = largest i with knot_i <= x.  Knots are increasing, so the predicates
+// p_i = (x >= knot_i) are a run of trues followed by falses and "last true wins" selects bin k on both axes with
+// the same predicates.  size_i = min + (1 - min K) softmax_i is one FMA per bin (g = (1 - min K) / sum(e) is
+// computed to full precision by the caller: an error in g would move every knot coherently).
+// Outputs: k, [s_lo, s_hi] = knots k, k+1 of the search axis, [o_lo, o_hi] the same for the other axis.
+template <int KC>
+FC_HD void knot_scan2(const float* es, float gs, float lo_s, float hi_s, float min_s, const float* eo, float go,
+                      float lo_o, float hi_o, float min_o, int K, float x, int& k, float& s_lo, float& s_hi,
+                      float& o_lo, float& o_hi) {
+  constexpr bool kCompensated = (KC == 0 || KC > 8);
+  const float span_s = hi_s - lo_s, span_o = hi_o - lo_o;
+  float cum_s = 0.f, comp_s = 0.f, prev_s = lo_s;
+  float cum_o = 0.f, comp_o = 0.f, prev_o = lo_o;
+  k = 0;
+  s_lo = lo_s;
+  s_hi = hi_s;
+  o_lo = lo_o;
+  o_hi = hi_o;
 #pragma unroll
   for (int i = 0; i < (KC ? KC : K); ++i) {
-    const float size = FC_ADD(min_size, FC_MUL(coef, FC_MUL(e[i], inv_sum)));
-    cum = FC_ADD(cum, size);
-    const float next = (i == K - 1) ? hi : FC_ADD(FC_MUL(span, cum), lo);
-    const bool take = kSearch ? (x >= prev) : (i == k);
-    if (take) {
-      if (kSearch) k = i;
-      lo_k = prev;
-      hi_k = next;
+    knot_accumulate<kCompensated>(fmaf(es[i], gs, min_s), cum_s, comp_s);
+    knot_accumulate<kCompensated>(fmaf(eo[i], go, min_o), cum_o, comp_o);
+    const bool last = (i == K - 1);
+    const float next_s = last ? hi_s : fmaf(span_s, cum_s, lo_s);
+    const float next_o = last ? hi_o : fmaf(span_o, cum_o, lo_o);
+    if (x >= prev_s) {
+      k = i;
+      s_lo = prev_s;
+      s_hi = next_s;
+      o_lo = prev_o;
+      o_hi = next_o;
     }
-    prev = next;
+    prev_s = next_s;
+    prev_o = next_o;
   }
 }
 
@@ -160,6 +247,7 @@ struct RqsBin {
   int k;
   float cw, w;   // left width knot, bin width
   float ch, h;   // bottom height knot, bin height
+  float inv_w;   // 1 / w
   float delta, d0, d1;
 };
 
@@ -168,25 +256,27 @@ struct RqsBin {
 template <int KC>
 FC_HD void rqs_locate(const RqsParams& c, int K, float x, const float* p, RqsBin& bin, float* ew, float* eh,
                       float& inv_w, float& inv_h) {
-  inv_w = softmax_numerators<KC>(p, K, c.wh_scale, ew);
-  inv_h = softmax_numerators<KC>(p + K, K, c.wh_scale, eh);
-  float a, b;
+  const float sum_w = softmax_numerators<KC>(p, K, c.wh_scale_l2e, ew);
+  const float sum_h = softmax_numerators<KC>(p + K, K, c.wh_scale_l2e, eh);
+  inv_w = fc_rcp(sum_w);
+  inv_h = fc_rcp(sum_h);
+  const float gw = fc_div(c.coef_w, sum_w), gh = fc_div(c.coef_h, sum_h);
+  float a, b, a2, b2;
   if (!c.inverse) {
-    knot_scan<KC, true>(ew, inv_w, K, c.left, c.right, c.min_w, c.coef_w, x, bin.k, a, b);
+    knot_scan2<KC>(ew, gw, c.left, c.right, c.min_w, eh, gh, c.bottom, c.top, c.min_h, K, x, bin.k, a, b, a2, b2);
     bin.cw = a;
     bin.w = FC_SUB(b, a);
-    knot_scan<KC, false>(eh, inv_h, K, c.bottom, c.top, c.min_h, c.coef_h, x, bin.k, a, b);
-    bin.ch = a;
-    bin.h = FC_SUB(b, a);
+    bin.ch = a2;
+    bin.h = FC_SUB(b2, a2);
   } else {
-    knot_scan<KC, true>(eh, inv_h, K, c.bottom, c.top, c.min_h, c.coef_h, x, bin.k, a, b);
+    knot_scan2<KC>(eh, gh, c.bottom, c.top, c.min_h, ew, gw, c.left, c.right, c.min_w, K, x, bin.k, a, b, a2, b2);
     bin.ch = a;
     bin.h = FC_SUB(b, a);
-    knot_scan<KC, false>(ew, inv_w, K, c.left, c.right, c.min_w, c.coef_w, x, bin.k, a, b);
-    bin.cw = a;
-    bin.w = FC_SUB(b, a);
+    bin.cw = a2;
+    bin.w = FC_SUB(b2, a2);
   }
-  bin.delta = bin.h / bin.w;
+  bin.inv_w = fc_rcp(bin.w);
+  bin.delta = bin.h * bin.inv_w;
   const float* pd = p + 2 * K;
   bin.d0 = knot_derivative(c, K, pd, bin.k);
   bin.d1 = knot_derivative(c, K, pd, bin.k + 1);
@@ -223,44 +313,59 @@ FC_HD float rqs_inverse_root(const RqsBin& b, float x, unsigned& status) {
     status |= FC_STATUS_NEGATIVE_DISCRIMINANT;
     disc = 0.f;
   }
-  return (2.f * qc) / (-qb - sqrtf(disc));
+  return (2.f * qc) * fc_rcp(-qb - fc_sqrt(disc));
 }
 
-// log|dy/dx| of the forward spline at theta (rational_quadratic.py:148-158 / :173-179).
-FC_HD float rqs_logdet_at(const RqsBin& b, float theta, float& denominator) {
+// log(v) for the derivative value v of the spline (1e-4 .. 1e4): lg2.approx (absolute error 2^-22 for v in
+// (0.5, 2), relative 2^-22 elsewhere) times ln 2 — the same size as the fp32 rounding of the reference's
+// log(numerator) - 2 log(denominator) (rational_quadratic.py:158,179), at 2 instructions instead of ~45.
+FC_HD float fc_log_deriv(float v) {
+#if FC_DEVICE_MATH
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+  return y * 0.6931471805599453f;
+#else
+  return logf(v);
+#endif
+}
+
+// log|dy/dx| of the forward spline at theta (rational_quadratic.py:148-158 / :173-179); also returns
+// 1/denominator, which the forward output needs.
+FC_HD float rqs_logdet_at(const RqsBin& b, float theta, float& inv_den) {
   const float t1mt = theta * (1.f - theta);
-  denominator = b.delta + (b.d0 + b.d1 - 2.f * b.delta) * t1mt;
+  const float den = b.delta + (b.d0 + b.d1 - 2.f * b.delta) * t1mt;
   const float omt = 1.f - theta;
   const float dnum = (b.delta * b.delta) * (b.d1 * (theta * theta) + 2.f * b.delta * t1mt + b.d0 * (omt * omt));
-  return logf(dnum) - 2.f * logf(denominator);
+  inv_den = fc_rcp(den);
+  return fc_log_deriv(dnum * inv_den * inv_den);
 }
 
 // One element, forward or inverse (c.inverse).  p -> this feature's P raw parameters.
+// Branch-free over the tails: outside elements evaluate the spline on a clamped input and are then replaced
+// by the identity (rational_quadratic.py:38-39), so a warp never diverges on the inside test.
 template <int KC>
 FC_HD void rqs_eval(const RqsParams& c, float x, const float* p, float& y, float& lad, unsigned& status) {
   const int K = KC ? KC : c.K;
   float xs;
-  if (!rqs_domain(c, x, xs, status)) {
-    y = x;  // rational_quadratic.py:38-39 linear tails: identity, zero log-det
-    lad = 0.f;
-    return;
-  }
+  const bool inside = rqs_domain(c, x, xs, status);
   float ew[KC ? KC : FC_MAX_BINS_GENERIC], eh[KC ? KC : FC_MAX_BINS_GENERIC];
   float inv_w, inv_h;
   RqsBin b;
   rqs_locate<KC>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
-  float den;
+  float inv_den, ys, ls;
   if (c.inverse) {
     const float root = rqs_inverse_root(b, xs, status);
-    y = root * b.w + b.cw;
-    lad = -rqs_logdet_at(b, root, den);
+    ys = root * b.w + b.cw;
+    ls = -rqs_logdet_at(b, root, inv_den);
   } else {
-    const float theta = (xs - b.cw) / b.w;
+    const float theta = (xs - b.cw) * b.inv_w;
     const float t1mt = theta * (1.f - theta);
     const float num = b.h * (b.delta * (theta * theta) + b.d0 * t1mt);
-    lad = rqs_logdet_at(b, theta, den);
-    y = b.ch + num / den;
+    ls = rqs_logdet_at(b, theta, inv_den);
+    ys = b.ch + num * inv_den;
   }
+  y = inside ? ys : x;
+  lad = inside ? ls : 0.f;
 }
 
 // Backward of rqs_eval for one element.  Upstream: gy = dL/dy, gl = dL/d(lad).  Writes dL/dx and the P
@@ -295,7 +400,7 @@ FC_HD void rqs_backward_elem(const RqsParams& c, float x, const float* p, float 
   if (c.inverse) {
     theta = rqs_inverse_root(b, xs, status);
   } else {
-    theta = (xs - b.cw) / W;
+    theta = (xs - b.cw) * b.inv_w;
   }
   const float omt = 1.f - theta;
   const float t = theta * omt;
@@ -303,7 +408,7 @@ FC_HD void rqs_backward_elem(const RqsParams& c, float x, const float* p, float 
   const float N = H * M;
   const float D = delta + s * t;
   const float Q = d1 * theta * theta + 2.f * delta * t + d0 * omt * omt;
-  const float invD = 1.f / D, invQ = 1.f / Q, invW = 1.f / W;
+  const float invD = fc_rcp(D), invQ = fc_rcp(Q), invW = b.inv_w;
 
   float gyf = gy, glf = gl;  // upstream of the FORWARD map evaluated at theta
   float gx_inverse = 0.f;
@@ -314,14 +419,14 @@ FC_HD void rqs_backward_elem(const RqsParams& c, float x, const float* p, float 
     const float dlad_dtheta = invQ * (dQ + 2.f * delta * dt) - 2.f * invD * s * dt;
     const float gprime = delta * delta * Q * invD * invD;
     glf = -gl;
-    gx_inverse = (gy + glf * dlad_dtheta * invW) / gprime;
+    gx_inverse = (gy + glf * dlad_dtheta * invW) * fc_rcp(gprime);
     gyf = -gx_inverse;
   }
   // adjoints
   const float Nb = gyf * invD;
   float Db = -gyf * N * invD * invD - 2.f * glf * invD;
   const float Qb = glf * invQ;
-  float deltab = 2.f * glf / delta + Qb * 2.f * t + Db;
+  float deltab = 2.f * glf * fc_rcp(delta) + Qb * 2.f * t + Db;
   float tb = Qb * 2.f * delta + Db * s;
   float d0b = Qb * omt * omt;
   float d1b = Qb * theta * theta;

@@ -6,7 +6,7 @@
 // (transforms/coupling.py:82-83,96-98): ~151 ATen calls, 3 host syncs and ~158 KB of tensor traffic per
 // sample per layer become one launch that touches each byte once.  Kernel skeleton: fc_staged.cuh;
 // element math: fc_math.cuh.
-#include "fc_staged.cuh"
+#include "fc_pipeline.cuh"
 
 namespace fc {
 
@@ -45,7 +45,9 @@ extern "C" int fc_rqs_apply(const float* x, int64_t x_row_stride, const float* p
   int rc = make_rqs_params(cfg, c);
   if (rc != FC_OK) return rc;
   rc = check_layer_args(x, params, y, B, D_t, tcols, ccols);
-  if (rc != FC_OK || !logabsdet) return FC_ERR_INVALID_ARGUMENT;
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!logabsdet) return FC_ERR_INVALID_ARGUMENT;
   if (B == 0) return FC_OK;
   LayerArgs a;
   a.x = x; a.params = params; a.y = y; a.lad = logabsdet; a.status = status;
@@ -53,11 +55,13 @@ extern "C" int fc_rqs_apply(const float* x, int64_t x_row_stride, const float* p
   a.B = B; a.D_t = D_t; a.n_copy = ccols.n; a.tcols = tcols.idx; a.ccols = ccols.idx;
   a.accumulate = accumulate_logabsdet;
   const size_t smem = plan_tiles(a, c.P);
-#define CALL(KC)                                                        \
-  {                                                                     \
-    RqsOp<KC> op;                                                       \
-    op.c = c;                                                           \
-    return launch_apply(a, op, smem, (cudaStream_t)stream);             \
+#define CALL(KC)                                                                                   \
+  {                                                                                                \
+    RqsOp<KC> op;                                                                                  \
+    op.c = c;                                                                                      \
+    const int piped = try_launch_pipelined(a, op, c.P, (int)x_row_stride, (cudaStream_t)stream);   \
+    if (piped != 0) return piped < 0 ? piped : FC_OK;                                              \
+    return launch_apply(a, op, smem, (cudaStream_t)stream);                                        \
   }
   FC_DISPATCH_K(c.K, CALL)
 #undef CALL
@@ -72,7 +76,9 @@ extern "C" int fc_rqs_backward(const float* x, int64_t x_row_stride, const float
   int rc = make_rqs_params(cfg, c);
   if (rc != FC_OK) return rc;
   rc = check_layer_args(x, params, grad_x, B, D_t, tcols, ccols);
-  if (rc != FC_OK || !grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
   if (B == 0) return FC_OK;
   LayerBwdArgs a;
   a.x = x; a.params = params; a.gy = grad_y; a.gl = grad_logabsdet; a.gx = grad_x; a.gp = grad_params;

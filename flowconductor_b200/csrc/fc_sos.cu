@@ -6,7 +6,7 @@
 // reference builds an nn.Module per call and runs ~35 pointwise passes over [B, D, n] (forward) or ~55
 // full forward passes plus two autograd passes with host syncs (inverse).
 // Kernel skeleton: fc_staged.cuh; element math: fc_math.cuh.
-#include "fc_staged.cuh"
+#include "fc_pipeline.cuh"
 
 namespace fc {
 
@@ -45,7 +45,9 @@ extern "C" int fc_sos_apply(const float* x, int64_t x_row_stride, const float* p
                             float lim, void* stream) {
   fc_cols none = {nullptr, 0};
   int rc = check_layer_args(x, params, y, B, D, none, none);
-  if (rc != FC_OK || !logabsdet) return FC_ERR_INVALID_ARGUMENT;
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!logabsdet) return FC_ERR_INVALID_ARGUMENT;
   if (n_sigmoids < 1) return FC_ERR_INVALID_ARGUMENT;
   if (n_sigmoids > FC_SOS_MAX_SIGMOIDS) return FC_ERR_UNSUPPORTED;
   if (B == 0) return FC_OK;
@@ -57,6 +59,8 @@ extern "C" int fc_sos_apply(const float* x, int64_t x_row_stride, const float* p
   SosOp op;
   op.n = n_sigmoids; op.offset = offset; op.inverse = inverse; op.iters = bisection_iterations; op.lim = lim;
   const size_t smem = plan_tiles(a, 3 * n_sigmoids + 1);
+  const int piped = try_launch_pipelined(a, op, 3 * n_sigmoids + 1, (int)x_row_stride, (cudaStream_t)stream);
+  if (piped != 0) return piped < 0 ? piped : FC_OK;
   return launch_apply(a, op, smem, (cudaStream_t)stream);
 }
 
@@ -66,7 +70,9 @@ extern "C" int fc_sos_backward(const float* x, int64_t x_row_stride, const float
                                int32_t n_sigmoids, void* stream) {
   fc_cols none = {nullptr, 0};
   int rc = check_layer_args(x, params, grad_x, B, D, none, none);
-  if (rc != FC_OK || !grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
   if (n_sigmoids < 1) return FC_ERR_INVALID_ARGUMENT;
   if (n_sigmoids > FC_SOS_MAX_SIGMOIDS) return FC_ERR_UNSUPPORTED;
   if (B == 0) return FC_OK;

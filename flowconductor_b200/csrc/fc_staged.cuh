@@ -223,7 +223,8 @@ inline int launch_backward(const LayerBwdArgs& a, const Op& op, size_t smem, cud
 
 inline int check_layer_args(const void* x, const void* params, const void* out, int64_t B, int32_t D_t, fc_cols tcols,
                             fc_cols ccols) {
-  if (B < 0 || D_t < 1 || !x || !params || !out) return FC_ERR_INVALID_ARGUMENT;
+  if (B < 0 || D_t < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (B > 0 && (!x || !params || !out)) return FC_ERR_INVALID_ARGUMENT;  // empty batches carry null pointers
   if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
   if (ccols.n < 0 || (ccols.n > 0 && !ccols.idx)) return FC_ERR_INVALID_ARGUMENT;
   return FC_OK;

