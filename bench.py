@@ -294,7 +294,7 @@ def run_ours(args, wl):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "staged_apply_kernel<RqsOp<8>> (fc_rqs_apply)",
+            "roofline": {"bound": "hbm", "kernel": "pipelined_apply_kernel<RqsOp<8>, true> (fc_rqs_apply)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_sample * B,

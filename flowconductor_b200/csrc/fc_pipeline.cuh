@@ -60,15 +60,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-template <class Op>
+// kSimple: D_t == 32 (one feature per lane, one row per warp pass): the feature loop and the segment logic fold away.
+template <class Op, bool kSimple>
 __global__ void __launch_bounds__(512) pipelined_apply_kernel(const PipeArgs pa, const Op op) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LayerArgs& a = pa.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int seg = a.seg, rpw = 32 / seg;
+  const int seg = kSimple ? 32 : a.seg, rpw = 32 / seg;
   const int sub = lane / seg, j0 = lane % seg;
   const int P = op.P();
-  const int D = pa.D, D_t = a.D_t, S = pa.stages, R = pa.slot_rows;
+  const int D = pa.D, D_t = kSimple ? 32 : a.D_t, S = pa.stages, R = pa.slot_rows;
   const int row_floats = D_t * P;
   const int slot_floats = R * (row_floats + D);
   const int32_t* __restrict__ tcols = a.tcols;
@@ -134,7 +135,11 @@ __global__ void __launch_bounds__(512) pipelined_apply_kernel(const PipeArgs pa,
     for (int r = sub; r < rows + sub; r += rpw, xrow += xstep, prow += pstep) {  // uniform trip count
       const bool row_ok = r < rows;
       float lad_acc = 0.f;
-      if (row_ok) {
+      if (kSimple) {
+        float yv;
+        op.eval(xrow[col0], prow, yv, lad_acc, status);
+        xrow[col0] = yv;
+      } else if (row_ok) {
         const float* pj = prow;
         for (int j = j0; j < D_t; j += seg, pj += jstep) {
           const int col = (j == j0) ? col0 : (tcols ? __ldg(tcols + j) : j);
@@ -152,7 +157,11 @@ __global__ void __launch_bounds__(512) pipelined_apply_kernel(const PipeArgs pa,
       const int n4 = (rows * D) >> 2;
       const float4* s4 = reinterpret_cast<const float4*>(sx);
       float4* d4 = reinterpret_cast<float4*>(yout);
-      for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+      if (n4 == 32) {
+        d4[lane] = s4[lane];
+      } else {
+        for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+      }
     }
     __syncwarp();
     if (lane == 0 && fetch_row < B) {
@@ -187,20 +196,19 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
   const int64_t row_bytes = (row_floats + D) * 4;
   // slot: about 6 KB, at least one pass of the warp
   int slot_rows = lm.rows_per_warp;
-  const int target = env_int("FC_PIPE_SLOT_BYTES", 8192);
+  const int target = env_int("FC_PIPE_SLOT_BYTES", 4096);
   while ((int64_t)(slot_rows * 2) * row_bytes <= target) slot_rows *= 2;
   slot_rows = env_int("FC_PIPE_SLOT_ROWS", slot_rows);
   int stages = env_int("FC_PIPE_STAGES", 2);
   int warps = env_int("FC_PIPE_WARPS", 16);
-  int ctas_per_sm = env_int("FC_PIPE_CTAS", 1);
+  int ctas_per_sm = env_int("FC_PIPE_CTAS", 2);
   const int64_t slot_bytes = slot_rows * row_bytes;
   if (slot_bytes > 96 * 1024) return 0;  // rows too long for a per-warp ring
   auto smem_need = [&](int w, int s) { return (int64_t)w * s * (slot_bytes + 8) + 128; };
   const int64_t sm_budget = 224 * 1024;  // 228 KB per SM minus the per-CTA reservation
   while ((int64_t)ctas_per_sm * (smem_need(warps, stages) + 1024) > sm_budget) {
     if (stages > 2) --stages;
-    else if (warps > 4) --warps;
-    else if (ctas_per_sm > 1) --ctas_per_sm;
+    else if (ctas_per_sm > 1) --ctas_per_sm;  // keep 16 warps per CTA before giving up the second CTA
     else if (warps > 1) --warps;
     else return 0;
   }
@@ -218,8 +226,13 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
   const int64_t need = (pa.num_groups + warps - 1) / warps;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  if (prepare_kernel(pipelined_apply_kernel<Op>, smem) != FC_OK) return FC_ERR_CUDA;
-  pipelined_apply_kernel<Op><<<(int)grid, warps * 32, smem, st>>>(pa, op);
+  if (a.D_t == 32) {
+    if (prepare_kernel(pipelined_apply_kernel<Op, true>, smem) != FC_OK) return FC_ERR_CUDA;
+    pipelined_apply_kernel<Op, true><<<(int)grid, warps * 32, smem, st>>>(pa, op);
+  } else {
+    if (prepare_kernel(pipelined_apply_kernel<Op, false>, smem) != FC_OK) return FC_ERR_CUDA;
+    pipelined_apply_kernel<Op, false><<<(int)grid, warps * 32, smem, st>>>(pa, op);
+  }
   if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
   return 1;
 }
