@@ -21,7 +21,8 @@ AFFINE_BLOCKED, AFFINE_INTERLEAVED = 0, 1
 SCALE_SIGMOID2, SCALE_SOFTPLUS_CLAMP3, SCALE_SOFTPLUS_EPS = 0, 1, 2
 
 EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
-           "fc_sos_backward", "fc_stdnormal_log_prob", "fc_version", "fc_built_for_sm"]
+           "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
+           "fc_version", "fc_built_for_sm"]
 
 
 class RqsConfig(ctypes.Structure):
@@ -35,6 +36,12 @@ class RqsConfig(ctypes.Structure):
 class Cols(ctypes.Structure):
     """struct fc_cols"""
     _fields_ = [("idx", ctypes.c_void_p), ("n", ctypes.c_int32)]
+
+
+class LinearWeights(ctypes.Structure):
+    """struct fc_linear_weights"""
+    _fields_ = [("w", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("n_pad", ctypes.c_int32),
+                ("k_pad", ctypes.c_int32)]
 
 
 class LibraryMissing(RuntimeError):
@@ -64,6 +71,11 @@ def lib():
         L.fc_sos_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, i32, f32, i32, i32, f32, vp]
         L.fc_sos_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, i32, vp]
         L.fc_stdnormal_log_prob.argtypes = [vp, i64, vp, vp, i64, i32, vp]
+        L.fc_linear_pack.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp]
+        L.fc_linear_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, i32, i32, vp,
+                                      i64, vp]
+        L.fc_linear_rqs_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, vp, i64, vp,
+                                          i32, i32, Cols, Cols, ctypes.POINTER(RqsConfig), vp, vp]
         L.fc_version.restype = ctypes.c_char_p
         for name in EXPORTS:
             if name not in ("fc_version",):

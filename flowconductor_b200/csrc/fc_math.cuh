@@ -193,6 +193,20 @@ FC_HD float knot_derivative(const RqsParams& c, int K, const float* pd, int j) {
   return padded ? c.pad_deriv : d;
 }
 
+// Register-resident variant for the fused GEMM epilogue (linear tails only): `pd` is a register array, so the
+// raw derivative is picked with a select chain over compile-time indices instead of a dynamic index (which would
+// push the array to local memory).  Same arithmetic as knot_derivative.
+template <int KC>
+FC_HD float knot_derivative_regs(const RqsParams& c, const float* pd, int j) {
+  const bool padded = (j == 0 || j == KC);
+  const int idx = padded ? 0 : j - 1;
+  float raw = pd[0];
+#pragma unroll
+  for (int i = 1; i < KC - 1; ++i) raw = (i == idx) ? pd[i] : raw;
+  const float d = c.min_d + softplus_beta(raw, c.beta, c.inv_beta);
+  return padded ? c.pad_deriv : d;
+}
+
 // softmax numerators e[i] = 2^(scale_l2e*u[i] - max) == exp(scale*u[i] - max'); returns their sum.
 template <int KC>
 FC_HD float softmax_numerators(const float* u, int K, float scale_l2e, float* e) {
@@ -275,7 +289,7 @@ struct RqsBin {
 
 // Shared front half of forward / inverse / backward: inside test, softmax, knots, bin, derivatives.
 // ew / eh receive the softmax numerators (needed again by the backward); inv_w / inv_h their 1/sum.
-template <int KC>
+template <int KC, bool kRegs = false>
 FC_HD void rqs_locate(const RqsParams& c, int K, float x, const float* p, RqsBin& bin, float* ew, float* eh,
                       float& inv_w, float& inv_h) {
   const float sum_w = softmax_numerators<KC>(p, K, c.wh_scale_l2e, ew);
@@ -300,8 +314,13 @@ FC_HD void rqs_locate(const RqsParams& c, int K, float x, const float* p, RqsBin
   bin.inv_w = fc_rcp(bin.w);
   bin.delta = bin.h * bin.inv_w;
   const float* pd = p + 2 * K;
-  bin.d0 = knot_derivative(c, K, pd, bin.k);
-  bin.d1 = knot_derivative(c, K, pd, bin.k + 1);
+  if (kRegs && KC > 1) {
+    bin.d0 = knot_derivative_regs<(KC > 1 ? KC : 2)>(c, pd, bin.k);
+    bin.d1 = knot_derivative_regs<(KC > 1 ? KC : 2)>(c, pd, bin.k + 1);
+  } else {
+    bin.d0 = knot_derivative(c, K, pd, bin.k);
+    bin.d1 = knot_derivative(c, K, pd, bin.k + 1);
+  }
 }
 
 // Domain handling shared by all entry points.  Returns true if the element takes the spline branch;
@@ -365,7 +384,7 @@ FC_HD float rqs_logdet_at(const RqsBin& b, float theta, float& inv_den) {
 // One element, forward or inverse (c.inverse).  p -> this feature's P raw parameters.
 // Branch-free over the tails: outside elements evaluate the spline on a clamped input and are then replaced
 // by the identity (rational_quadratic.py:38-39), so a warp never diverges on the inside test.
-template <int KC>
+template <int KC, bool kRegs = false>
 FC_HD void rqs_eval(const RqsParams& c, float x, const float* p, float& y, float& lad, unsigned& status) {
   const int K = KC ? KC : c.K;
   float xs;
@@ -373,7 +392,7 @@ FC_HD void rqs_eval(const RqsParams& c, float x, const float* p, float& y, float
   float ew[KC ? KC : FC_MAX_BINS_GENERIC], eh[KC ? KC : FC_MAX_BINS_GENERIC];
   float inv_w, inv_h;
   RqsBin b;
-  rqs_locate<KC>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
+  rqs_locate<KC, kRegs>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
   float inv_den, ys, ls;
   if (c.inverse) {
     const float root = rqs_inverse_root(b, xs, status);

@@ -1,0 +1,148 @@
+"""Inference path of the conditioner networks on the tensor cores (csrc/fc_linear.cu).
+
+`ResidualNet` (flowcon/nn/nets/resnet.py:59-100) and `MADE` (flowcon/transforms/made.py:205-283) are chains of
+Linear / MaskedLinear layers with pre-activation residual blocks.  When no gradient is needed, every layer runs as
+one `fc_linear_apply` launch (3xTF32 tcgen05 GEMM, ReLU / bias / skip connection fused) and the final layer
+runs as `fc_linear_rqs_apply` (spline in the GEMM epilogue) where the bijection is a linear-tails
+rational-quadratic spline with 8 or 16 bins; otherwise the final layer's parameters are materialised by
+`fc_linear_apply` and handed to the stand-alone element-wise kernel.
+
+The packed weights are cached on the module and rebuilt when any parameter changes (data pointer or
+in-place version counter).  Training (autograd) keeps using the torch.nn modules and the custom ops of
+`flowconductor_b200.ops`: this path has no backward.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import _cabi, linear as fl
+
+ENABLED = True  # set False to force the unfused (torch.nn + element-wise kernel) path everywhere
+
+
+def _is_relu(act):
+    return act is F.relu or act is torch.relu or isinstance(act, nn.ReLU)
+
+
+def wants_grad(net, *tensors):
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in net.parameters())
+
+
+def supported_net(net, context):
+    """True if `net` is a ResidualNet / MADE configuration the kernels cover."""
+    from ..transforms import made as made_module
+    from .nets.resnet import ResidualNet
+
+    if not ENABLED or context is not None:
+        return False
+    if isinstance(net, ResidualNet):
+        if net.context_features is not None:
+            return False
+        blocks = net.blocks
+    elif isinstance(net, made_module.MADE):
+        if not net.use_residual_blocks or hasattr(net, "context_layer") or not _is_relu(net.activation):
+            return False
+        blocks = net.blocks
+    else:
+        return False
+    for blk in blocks:
+        if getattr(blk, "use_batch_norm", False) or not _is_relu(blk.activation):
+            return False
+        if blk.dropout.p > 0 and blk.training:
+            return False
+    if net.initial_layer.weight.shape[0] % 4 != 0:
+        return False
+    return True
+
+
+def usable(net, a, context, *other_inputs):
+    """Should this conditioner call take the tensor-core path?  `a` is the matrix the first layer multiplies."""
+    if not supported_net(net, context) or wants_grad(net, a, *other_inputs):
+        return False
+    if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0):
+        return False
+    # TMA operand constraints: 16-byte aligned base and row pitch
+    if a.stride(1) != 1 or a.stride(0) % 4 != 0 or a.data_ptr() % 16 != 0:
+        return False
+    return net.final_layer.weight.shape[0] % 4 == 0
+
+
+def _param_key(net):
+    return tuple((p.data_ptr(), p._version) for p in net.parameters())
+
+
+class _Plan:
+    __slots__ = ("key", "initial", "blocks", "final", "final_kind")
+
+
+def _pack_layer(layer, **kw):
+    mask = getattr(layer, "mask", None)
+    return fl.pack(layer.weight, layer.bias, mask=mask, **kw)
+
+
+def plan_for(net, col_map, k_in, final_kind, final_group=None):
+    """Packed layers of `net`, cached on the module.  col_map / k_in: scatter of the first layer's input columns
+    (coupling layers read the full-width inputs).  final_kind: ("store",) or ("rqs", K)."""
+    key = (_param_key(net), final_kind, k_in)
+    plan = getattr(net, "_fc_plan", None)
+    if plan is not None and plan.key == key:
+        return plan
+    plan = _Plan()
+    plan.key = key
+    plan.initial = _pack_layer(net.initial_layer, col_map=col_map, k_in=k_in)
+    plan.blocks = [(_pack_layer(b.linear_layers[0]), _pack_layer(b.linear_layers[1])) for b in net.blocks]
+    plan.final_kind = final_kind
+    fin = net.final_layer
+    if final_kind[0] == "rqs":
+        K = final_kind[1]
+        P = 3 * K - 1
+        d_t = fin.weight.shape[0] // P
+        rm = fl.grouped_row_map(d_t, P, fl.RQS_PPAD[K], fin.weight.device)
+        plan.final = _pack_layer(fin, row_map=rm, n_tile=fl.N_TILE_RQS)
+    else:
+        plan.final = _pack_layer(fin)
+    object.__setattr__(net, "_fc_plan", plan)
+    return plan
+
+
+def hidden(plan, a):
+    """Everything up to (not including) the final layer: ResidualNet.hidden / MADE.hidden."""
+    h = fl.linear(a, plan.initial)
+    for l0, l1 in plan.blocks:
+        t = fl.linear(h, l0, relu_in=True, relu_out=True)   # relu(W0 relu(h) + b0): only ever consumed through ReLU
+        h = fl.linear(t, l1, residual=h)                    # h + W1 t + b1
+    return h
+
+
+def params(net, a, col_map=None, k_in=None):
+    """Full conditioner output [B, out_features] (final layer materialised)."""
+    plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("store",))
+    return fl.linear(hidden(plan, a), plan.final)
+
+
+def rqs_fusable(spline, final_out_features, d_t):
+    return (ENABLED and spline.tails == "linear" and spline.num_bins in fl.RQS_PPAD
+            and final_out_features == d_t * (3 * spline.num_bins - 1))
+
+
+def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None):
+    """Conditioner + spline for one layer; returns (outputs, logabsdet)."""
+    d_t = tcols.numel() if tcols is not None else inputs.shape[1]
+    plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("rqs", spline.num_bins))
+    h = hidden(plan, a)
+    tb = float(spline.tail_bound)
+    wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
+    cfg = _cabi.RqsConfig(int(spline.num_bins), _cabi.TAILS_LINEAR, int(bool(spline.identity_init)), int(bool(inverse)),
+                          -tb, tb, -tb, tb, float(spline.min_bin_width), float(spline.min_bin_height),
+                          float(spline.min_derivative), wh_scale)
+    x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
+    y = torch.empty_like(x)
+    lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
+    fl.linear_rqs(h, plan.final, x, y, lad, False, d_t, tcols, ccols, cfg, None)
+    return y, lad

@@ -9,6 +9,7 @@ import torch
 from torch.nn import functional as F
 
 from .. import _cabi, ops
+from ..nn import tensorcore
 from . import made as made_module
 from . import splines
 from .base import Transform
@@ -23,16 +24,29 @@ class AutoregressiveTransform(Transform):
         self.autoregressive_net = autoregressive_net
 
     def forward(self, inputs, context=None):
+        if tensorcore.usable(self.autoregressive_net, inputs, context):
+            return self._tensorcore_layer(inputs, inputs, inverse=False)
         params = self.autoregressive_net(inputs, context)
         return self._elementwise_forward(inputs, params)
 
     def inverse(self, inputs, context=None):
         outputs = torch.zeros_like(inputs)
         logabsdet = None
+        fast = tensorcore.usable(self.autoregressive_net, outputs, context, inputs)
         for _ in range(int(np.prod(inputs.shape[1:]))):
-            params = self.autoregressive_net(outputs, context)
-            outputs, logabsdet = self._elementwise_inverse(inputs, params)
+            if fast:
+                outputs, logabsdet = self._tensorcore_layer(outputs, inputs, inverse=True)
+            else:
+                params = self.autoregressive_net(outputs, context)
+                outputs, logabsdet = self._elementwise_inverse(inputs, params)
         return outputs, logabsdet
+
+    def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
+        """MADE on the tensor cores (inference); `conditioner_inputs` feeds the MADE, `inputs` the bijection."""
+        params = tensorcore.params(self.autoregressive_net, conditioner_inputs)
+        if inverse:
+            return self._elementwise_inverse(inputs, params)
+        return self._elementwise_forward(inputs, params)
 
     def _output_dim_multiplier(self):
         raise NotImplementedError()
@@ -128,3 +142,10 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
 
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._elementwise(inputs, autoregressive_params, inverse=True)
+
+    def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
+        net = self.autoregressive_net
+        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1]):
+            return super()._tensorcore_layer(conditioner_inputs, inputs, inverse)
+        return tensorcore.rqs_layer(net, conditioner_inputs, inputs, self._spline, None, None, inverse,
+                                    getattr(net, "hidden_features", None))

@@ -7,6 +7,7 @@ import torch
 from torch.nn import functional as F
 
 from .. import ops
+from ..nn import tensorcore
 from ..nn.nets import ResidualNet
 from . import splines
 from .base import Transform
@@ -35,12 +36,23 @@ class ConditionalTransform(Transform):
     def forward(self, inputs, context=None):
         if context is None:
             raise TypeError("Conditional transforms require a context.")
+        if tensorcore.usable(self.conditional_net, context, None, inputs):
+            return self._tensorcore_layer(inputs, context, inverse=False)
         return self._forward_given_params(inputs, self.conditional_net(context))
 
     def inverse(self, inputs, context=None):
         if context is None:
             raise TypeError("Conditional transforms require a context.")
+        if tensorcore.usable(self.conditional_net, context, None, inputs):
+            return self._tensorcore_layer(inputs, context, inverse=True)
         return self._inverse_given_params(inputs, self.conditional_net(context))
+
+    def _tensorcore_layer(self, inputs, context, inverse):
+        """Hypernetwork on the tensor cores (inference): the context is the conditioner's only input."""
+        params = tensorcore.params(self.conditional_net, context)
+        if inverse:
+            return self._inverse_given_params(inputs, params)
+        return self._forward_given_params(inputs, params)
 
     def _output_dim_multiplier(self):
         raise NotImplementedError()
@@ -85,6 +97,13 @@ class ConditionalPiecewiseRationalQuadraticTransform(ConditionalTransform):
 
     def _inverse_given_params(self, inputs, autoregressive_params):
         return self._elementwise(inputs, autoregressive_params, inverse=True)
+
+    def _tensorcore_layer(self, inputs, context, inverse):
+        net = self.conditional_net
+        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1]):
+            return super()._tensorcore_layer(inputs, context, inverse)
+        return tensorcore.rqs_layer(net, context, inputs, self._spline, None, None, inverse,
+                                    getattr(net, "hidden_features", None))
 
 
 class ConditionalSumOfSigmoidsTransform(ConditionalTransform):

@@ -12,6 +12,7 @@ import warnings
 import torch
 
 from .. import _cabi, ops
+from ..nn import tensorcore
 from . import splines
 from .base import Transform
 
@@ -62,13 +63,23 @@ class CouplingTransform(Transform):
 
     def forward(self, inputs, context=None):
         self._check(inputs)
-        params = self.transform_net(inputs[:, self.identity_features], context)
-        return self._coupling_layer(inputs, params, inverse=False)
+        return self._run_layer(inputs, context, inverse=False)
 
     def inverse(self, inputs, context=None):
         self._check(inputs)
+        return self._run_layer(inputs, context, inverse=True)
+
+    def _run_layer(self, inputs, context, inverse):
+        if tensorcore.usable(self.transform_net, inputs, context):
+            # inference: conditioner on the tensor cores; its first layer reads the full-width inputs through a
+            # column-scattered weight, so the identity-column gather (coupling.py:82-86) disappears as well
+            return self._tensorcore_layer(inputs, inverse)
         params = self.transform_net(inputs[:, self.identity_features], context)
-        return self._coupling_layer(inputs, params, inverse=True)
+        return self._coupling_layer(inputs, params, inverse)
+
+    def _tensorcore_layer(self, inputs, inverse):
+        params = tensorcore.params(self.transform_net, inputs, col_map=self._ccols, k_in=self.features)
+        return self._coupling_layer(inputs, params, inverse)
 
     def _transform_dim_multiplier(self):
         raise NotImplementedError()
@@ -150,3 +161,11 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
 
     def _coupling_layer(self, inputs, transform_params, inverse):
         return self._spline.apply(inputs, transform_params, self._tcols, self._ccols, inverse, self._scaling_width())
+
+    def _tensorcore_layer(self, inputs, inverse):
+        net = self.transform_net
+        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], self.num_transform_features):
+            return super()._tensorcore_layer(inputs, inverse)
+        # final layer + spline in one kernel: the [B, D_t*P] parameter tensor never reaches HBM
+        return tensorcore.rqs_layer(net, inputs, inputs, self._spline, self._tcols, self._ccols, inverse,
+                                    self._scaling_width(), col_map=self._ccols, k_in=self.features)

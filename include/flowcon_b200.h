@@ -130,6 +130,53 @@ int fc_sos_backward(const float* x, int64_t x_row_stride, const float* params, i
 int fc_stdnormal_log_prob(const float* z, int64_t z_row_stride, const float* logabsdet, float* out,
                           int64_t B, int32_t D, void* stream);
 
+/*
+ * Conditioner dense layers on the tensor cores (tcgen05 / TMEM / TMA), fp32-faithful "3xTF32" arithmetic.
+ *
+ * fc_linear_weights is the packed form of one nn.Linear / MaskedLinear (flowcon/nn/nets/resnet.py:26-28,69-91,
+ * flowcon/transforms/made.py:15-72): two K-major [n_pad, k_pad] planes (tf32 "hi", then tf32 "lo" = W - hi) and a
+ * padded bias.  fc_linear_pack builds it:  packed row row_map[n] (default n), packed column col_map[k] (default
+ * k) <- W[n, k] * mask[n, k];  everything else is zero.  row_map is how the final layer's per-feature parameter
+ * groups are padded (P -> P_pad accumulator columns per feature: 24 for K = 8 bins, 48 for K = 16) and how the
+ * blocked affine layout is interleaved; col_map is how the coupling layer's identity-column gather
+ * (coupling.py:82-86) is folded into the first layer (the GEMM then reads the full-width inputs).
+ * k_pad must be a multiple of 32, n_pad a multiple of the kernel's N tile (256 for fc_linear_apply, 192 for
+ * fc_linear_rqs_apply).
+ */
+typedef struct fc_linear_weights {
+  const float* w;    /* device [2][n_pad][k_pad] */
+  const float* bias; /* device [n_pad] */
+  int32_t n_pad, k_pad;
+} fc_linear_weights;
+
+int fc_linear_pack(const float* W, int64_t w_row_stride, const float* mask, int64_t mask_row_stride,
+                   const float* bias, int32_t N, int32_t K, const int32_t* row_map, const int32_t* col_map,
+                   int32_t n_pad, int32_t k_pad, float* w_packed, float* bias_packed, void* stream);
+
+/*
+ * out[M, n_out] = act_out( act_in(A[M, K]) * W^T + bias (+ residual) ),  act = ReLU when the flag is set.
+ * Replaces F.linear in ResidualNet / ResidualBlock / MADE hidden layers (resnet.py:39-56,93-99,
+ * made.py:71-72,96-124,152-181): relu_in is the pre-activation of the residual blocks, `residual` their skip
+ * connection.  A, out, residual: 16-byte aligned, row strides multiples of 4 floats; n_out a multiple of 4.
+ */
+int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w, int32_t relu_in,
+                    float* out, int64_t ldo, int32_t n_out, int32_t relu_out, const float* residual, int64_t ldr,
+                    void* stream);
+
+/*
+ * Final conditioner layer with the rational-quadratic spline in the GEMM epilogue (SURVEY a15 + a1-a6):
+ *   params[r, :] = act_in(hidden[r, :H]) * W^T + bias      (never written to memory)
+ *   y[r, tcols[j]] = spline(x[r, tcols[j]]; params[r, j*P .. j*P+P-1]),   y[r, ccols[i]] = x[r, ccols[i]],
+ *   logabsdet[r] = (accumulate ? logabsdet[r] : 0) + sum_j log|dy/dx|
+ * i.e. final_layer (resnet.py:99 / made.py:266-272) + fc_rqs_apply in one kernel.  `w` must have been packed with
+ * row_map[j*P + i] = j*P_pad + i.  Supported: linear tails, num_bins 8 or 16 (else FC_ERR_UNSUPPORTED: run
+ * fc_linear_apply + fc_rqs_apply).  y may alias x.
+ */
+int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
+                        int32_t relu_in, const float* x, int64_t x_row_stride, float* y, int64_t y_row_stride,
+                        float* logabsdet, int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                        const fc_rqs_config* cfg, int32_t* status, void* stream);
+
 /* Library / build info (also used by the loader test). */
 const char* fc_version(void);
 int fc_built_for_sm(void); /* 100 */
