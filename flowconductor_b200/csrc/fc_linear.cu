@@ -15,13 +15,24 @@
 //   * activations: TMA lands the raw fp32 tile in shared memory, two converter warps rewrite it in place as a_hi
 //     (optionally after ReLU — the residual blocks are pre-activation, resnet.py:41-47) and write a_lo next to it.
 //
-// Kernel: persistent, one CTA per SM, 12 warps:
-//   warp 0      TMA producer   : per K-chunk one box of A (128 x BK) and the hi/lo boxes of W (BN x BK each)
-//   warp 1      UMMA issuer    : 3 x BK/8 tcgen05.mma (128 x BN x 8, kind::tf32) per K-chunk, commit -> barriers
-//   warps 2-3   converters     : raw A tile -> (a_hi, a_lo)
-//   warps 4-11  epilogue       : tcgen05.ld the accumulator (double-buffered in TMEM, so the epilogue of tile i
-//                                overlaps the MMAs of tile i+1), + bias, then either ReLU/residual/store or the
-//                                rational-quadratic spline of 8 (K=8) / 4 (K=16) features per 192-column tile.
+// Accumulation: the tensor core truncates (rounds toward zero) every time an MMA result is added to the fp32
+// accumulator in TMEM; over the K/8 = 32 dependent additions of a K = 256 dot product that is a systematic error
+// of ~1.5e-6 relative, 5x the rounding noise of an fp32 FMA chain.  The accumulator is therefore drained every
+// `chunk` pipeline stages (default 32 k-values = 4 UMMA k-steps): the MMA warp starts a fresh partial sum in the
+// other TMEM buffer while the epilogue warps add the finished partial into fp32 REGISTER accumulators with
+// round-to-nearest.  The partials are 8x smaller and 8x shorter, which brings the GEMM error down to that of the
+// fp32 cuBLAS GEMM the reference runs (measured on K = 256 Gaussian operands, scripts/check_linear.py: rms error
+// 1.8e-6 undrained, 4.6e-7 at 64, 2.5e-7 at 32; cuBLAS fp32 2.9e-7).
+//
+// Kernel: persistent, one CTA per SM, 16 warps (register budget re-balanced with setmaxnreg):
+//   warp 0      TMA producer   : per stage one box of A (128 x BK) and the hi/lo boxes of W (BN x BK each)
+//   warp 1      UMMA issuer    : 3 x BK/8 tcgen05.mma (128 x BN x 8, kind::tf32) per stage, commit -> barriers
+//   warp 2      TMEM allocator
+//   warps 4-7   converters     : raw A tile -> (a_hi, a_lo)
+//   warps 8-15  epilogue       : tcgen05.ld each partial accumulator (double-buffered in TMEM, so draining chunk i
+//                                overlaps the MMAs of chunk i+1) into registers, then + bias and either
+//                                ReLU/residual/store or the rational-quadratic spline of 8 (K=8) / 4 (K=16)
+//                                features per 192-column tile.
 #include "fc_common.cuh"
 #include "fc_tc.cuh"
 
@@ -29,14 +40,17 @@ namespace fc {
 
 using namespace tc;
 
-constexpr int kLinThreads = 384;
+constexpr int kLinThreads = 512;
 constexpr int kBM = 128;
-constexpr int kEpiWarp0 = 4;
-constexpr int kNumConv = 64;  // converter threads (warps 2-3)
+constexpr int kConvWarp0 = 4;
+constexpr int kEpiWarp0 = 8;
+constexpr int kNumConv = 128;  // converter threads (warps 4-7)
+constexpr int kRegsProducer = 40, kRegsConverter = 56, kRegsEpilogue = 208;  // 128*(40+56) + 256*208 == 65536
 
 struct LinArgs {
   int M;
-  int num_k_chunks;
+  int num_k_stages;  // pipeline stages (BK k-values each) per output tile
+  int chunk;         // stages per partial accumulator
   int num_m_tiles, num_n_tiles;
   int n_pad;         // rows of one weight plane (lo plane starts at row n_pad of the weight tensor map)
   int relu_in;       // ReLU applied to A while splitting
@@ -78,13 +92,42 @@ struct LinSmem {
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
 };
 
+template <int N>
+__device__ __forceinline__ void set_max_regs_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void set_max_regs_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// acc[0..N) (=|+=) N consecutive TMEM columns of this thread's lane.  16 columns per tcgen05.ld, software-pipelined:
+// the additions of group j run while the load of group j+1 is in flight.
+template <int N, bool kFirst>
+__device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
+  static_assert(N % 32 == 0, "column count per thread must be a multiple of 32");
+  if (kFirst) {
+#pragma unroll
+    for (int j = 0; j < N; j += 32) tmem_ld32(taddr + (uint32_t)j, reinterpret_cast<uint32_t*>(acc + j));
+    tmem_wait_ld();
+    return;
+  }
+  uint32_t v[2][16];
+  tmem_ld16(taddr, v[0]);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < N; j += 16) {
+    const int cur = (j >> 4) & 1;
+    if (j + 16 < N) tmem_ld16(taddr + (uint32_t)(j + 16), v[cur ^ 1]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[j + i] += __uint_as_float(v[cur][i]);
+    if (j + 16 < N) tmem_wait_ld();
+  }
+}
+
 // EPI: 0 = store (bias, optional residual / ReLU), 1 = rational-quadratic spline with KC bins.
 // RQS tile geometry: FEATS features of PPAD accumulator columns each (BN = FEATS * PPAD).
-// SPLIT: the two cross terms (a_lo*b_hi, a_hi*b_lo) accumulate in their own TMEM accumulator (columns BN..2BN) and are
-// added to the main one by the epilogue in fp32 round-to-nearest.  The tensor core truncates (rounds toward zero)
-// every time an MMA result is added to the accumulator; keeping the 2K/8 small-term additions out of the large
-// accumulator cuts the truncation error 3x.  Uses both accumulator buffers for one tile (no MMA/epilogue overlap).
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, bool SPLIT>
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD>
 __global__ void __launch_bounds__(kLinThreads, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const LinArgs la, const StoreEpi se, const RqsEpi re) {
@@ -106,7 +149,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 512;
-  constexpr int NACC = SPLIT ? 1 : 2;  // accumulator buffers in flight
+  static_assert(2 * BN <= 512, "two partial accumulators must fit in tensor memory");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -128,76 +171,85 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
 
-  const int nk = la.num_k_chunks;
+  const int nk = la.num_k_stages;
   const int n_tiles = la.num_n_tiles;
+  const int chunk = la.chunk;
+  const int n_chunks = (nk + chunk - 1) / chunk;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < n_tiles; ++nt) {
-          for (int kc = 0; kc < nk; ++kc) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            const uint32_t st = base + s * SM::STAGE_BYTES;
-            mbar_expect_tx(full_bar(s), SM::A_BYTES + 2 * SM::B_BYTES);
-            tma_load_2d(st, &tmA, kc * BK, mt * kBM, full_bar(s));
-            tma_load_2d(st + 2 * SM::A_BYTES, &tmB, kc * BK, nt * BN, full_bar(s));
-            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + nt * BN, full_bar(s));
-            if (++s == STAGES) {
-              s = 0;
-              ph ^= 1u;
+  if (warp < kConvWarp0) {
+    set_max_regs_dec<kRegsProducer>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
+          for (int nt = 0; nt < n_tiles; ++nt) {
+            for (int kc = 0; kc < nk; ++kc) {
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              const uint32_t st = base + s * SM::STAGE_BYTES;
+              mbar_expect_tx(full_bar(s), SM::A_BYTES + 2 * SM::B_BYTES);
+              tma_load_2d(st, &tmA, kc * BK, mt * kBM, full_bar(s));
+              tma_load_2d(st + 2 * SM::A_BYTES, &tmB, kc * BK, nt * BN, full_bar(s));
+              tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + nt * BN, full_bar(s));
+              if (++s == STAGES) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
-      int s = 0, acc = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < n_tiles; ++nt) {
-          mbar_wait(tempty_bar(acc), aph ^ 1u);
-          tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-          const uint32_t d2 = SPLIT ? tmem_base + (uint32_t)BN : d;  // accumulator of the cross terms
-          for (int kc = 0; kc < nk; ++kc) {
-            mbar_wait(full_bar(s), ph);
-            mbar_wait(conv_bar(s), ph);
-            tc_fence_after();
-            const uint32_t st = base + s * SM::STAGE_BYTES;
-            const uint64_t a_hi = make_smem_desc(st, BK * 4);
-            const uint64_t a_lo = make_smem_desc(st + SM::A_BYTES, BK * 4);
-            const uint64_t b_hi = make_smem_desc(st + 2 * SM::A_BYTES, BK * 4);
-            const uint64_t b_lo = make_smem_desc(st + 2 * SM::A_BYTES + SM::B_BYTES, BK * 4);
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- UMMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
+        int s = 0, acc = 0;
+        uint32_t ph = 0, aph = 0;
+        for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
+          for (int nt = 0; nt < n_tiles; ++nt) {
+            for (int k0 = 0; k0 < nk; k0 += chunk) {
+              const int k1 = k0 + chunk < nk ? k0 + chunk : nk;
+              mbar_wait(tempty_bar(acc), aph ^ 1u);
+              tc_fence_after();
+              const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+              for (int kc = k0; kc < k1; ++kc) {
+                mbar_wait(full_bar(s), ph);
+                mbar_wait(conv_bar(s), ph);
+                tc_fence_after();
+                const uint32_t st = base + s * SM::STAGE_BYTES;
+                const uint64_t a_hi = make_smem_desc(st, BK * 4);
+                const uint64_t a_lo = make_smem_desc(st + SM::A_BYTES, BK * 4);
+                const uint64_t b_hi = make_smem_desc(st + 2 * SM::A_BYTES, BK * 4);
+                const uint64_t b_lo = make_smem_desc(st + 2 * SM::A_BYTES + SM::B_BYTES, BK * 4);
 #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk) {
-              const uint64_t o = (uint64_t)(kk * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along K inside the swizzle span
-              umma_tf32_ss(d2, a_lo + o, b_hi + o, idesc, (kc | kk) ? 1u : 0u);
-              umma_tf32_ss(d2, a_hi + o, b_lo + o, idesc, 1u);
-              umma_tf32_ss(d, a_hi + o, b_hi + o, idesc, (SPLIT && !(kc | kk)) ? 0u : 1u);
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                  const uint64_t o = (uint64_t)(kk * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along K in the swizzle span
+                  // small terms first, so they are not absorbed by the large one before they have been summed
+                  umma_tf32_ss(d, a_lo + o, b_hi + o, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
+                  umma_tf32_ss(d, a_hi + o, b_lo + o, idesc, 1u);
+                  umma_tf32_ss(d, a_hi + o, b_hi + o, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));
+                if (++s == STAGES) {
+                  s = 0;
+                  ph ^= 1u;
+                }
+              }
+              umma_commit(tfull_bar(acc));
+              if (++acc == 2) {
+                acc = 0;
+                aph ^= 1u;
+              }
             }
-            umma_commit(empty_bar(s));
-            if (kc == nk - 1) umma_commit(tfull_bar(acc));
-            if (++s == STAGES) {
-              s = 0;
-              ph ^= 1u;
-            }
-          }
-          if (++acc == NACC) {
-            acc = 0;
-            aph ^= 1u;
           }
         }
       }
     }
   } else if (warp < kEpiWarp0) {
     // ------------------------------------------------------------------ converters: raw fp32 -> (hi, lo) tf32
-    const int ct = threadIdx.x - 64;
+    set_max_regs_dec<kRegsConverter>();
+    const int ct = threadIdx.x - kConvWarp0 * 32;
     int s = 0;
     uint32_t ph = 0;
     const bool relu = la.relu_in != 0;
@@ -205,7 +257,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       for (int it = 0; it < n_tiles * nk; ++it) {
         mbar_wait(full_bar(s), ph);
         const uint32_t st = base + s * SM::STAGE_BYTES;
-#pragma unroll 4
+#pragma unroll
         for (int v = ct; v < SM::A_BYTES / 16; v += kNumConv) {
           const uint32_t addr = st + (uint32_t)v * 16u;
           float4 f = lds128(addr);
@@ -231,6 +283,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
+    set_max_regs_inc<kRegsEpilogue>();
+    constexpr int NCOL = BN / 2;             // accumulator columns (and registers) per thread
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns / features
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
@@ -243,119 +297,77 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       const bool valid = row < la.M;
       float lad_acc = 0.f;
       for (int nt = 0; nt < n_tiles; ++nt) {
-        mbar_wait(tfull_bar(acc), aph);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + lane_sel + (uint32_t)(acc * BN);
+        float av[NCOL];
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          mbar_wait(tfull_bar(acc), aph);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + lane_sel + (uint32_t)(acc * BN + half * NCOL);
+          if (ch == 0) {
+            drain_partial<NCOL, true>(tacc, av);
+          } else {
+            drain_partial<NCOL, false>(tacc, av);
+          }
+          tc_fence_before();  // partial accumulator fully read by this warp: hand it back to the MMA warp
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) {
+            acc = 0;
+            aph ^= 1u;
+          }
+        }
         if (EPI == 0) {
-          constexpr int HALF = BN / 2;
-#pragma unroll 1
-          for (int c = 0; c < HALF; c += 32) {
-            const int col = half * HALF + c;
-            uint32_t v[32];
-            tmem_ld32(tacc + (uint32_t)col, v);
-            if (SPLIT) {
-              uint32_t v2[32];
-              tmem_ld32(tacc + (uint32_t)(BN + col), v2);
-              tmem_wait_ld();
+          const int n0 = nt * BN + half * NCOL;
+          const float4* b4 = reinterpret_cast<const float4*>(la.bias + n0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-            } else {
-              tmem_wait_ld();
-            }
-            if (c + 32 >= HALF) {  // accumulator fully read by this warp: hand it back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
-            const int n0 = nt * BN + col;
-            const float4* b4 = reinterpret_cast<const float4*>(la.bias + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              float4 o;
-              o.x = __uint_as_float(v[4 * j + 0]) + b.x;
-              o.y = __uint_as_float(v[4 * j + 1]) + b.y;
-              o.z = __uint_as_float(v[4 * j + 2]) + b.z;
-              o.w = __uint_as_float(v[4 * j + 3]) + b.w;
-              const int n = n0 + 4 * j;
-              if (valid && n < se.n_out) {
-                if (se.residual) {
-                  const float4 r = __ldg(reinterpret_cast<const float4*>(se.residual + row * se.ldr + n));
-                  o.x += r.x;
-                  o.y += r.y;
-                  o.z += r.z;
-                  o.w += r.w;
-                }
-                if (se.relu_out) {
-                  o.x = fmaxf(o.x, 0.f);
-                  o.y = fmaxf(o.y, 0.f);
-                  o.z = fmaxf(o.z, 0.f);
-                  o.w = fmaxf(o.w, 0.f);
-                }
-                *reinterpret_cast<float4*>(se.out + row * se.ldo + n) = o;
+          for (int j = 0; j < NCOL / 4; ++j) {
+            const float4 b = __ldg(b4 + j);
+            float4 o;
+            o.x = av[4 * j + 0] + b.x;
+            o.y = av[4 * j + 1] + b.y;
+            o.z = av[4 * j + 2] + b.z;
+            o.w = av[4 * j + 3] + b.w;
+            const int n = n0 + 4 * j;
+            if (valid && n < se.n_out) {
+              if (se.residual) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(se.residual + row * se.ldr + n));
+                o.x += r.x;
+                o.y += r.y;
+                o.z += r.z;
+                o.w += r.w;
               }
+              if (se.relu_out) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(se.out + row * se.ldo + n) = o;
             }
           }
         } else {
           constexpr int FEATS = BN / PPAD;
           constexpr int FH = FEATS / 2;
+          static_assert(FH * PPAD == NCOL, "feature groups must tile the column half exactly");
           if (nt == 0 && half == 0 && valid && re.n_copy > 0 && re.y != re.x) {
             for (int i = 0; i < re.n_copy; ++i) {  // identity columns (coupling.py:96-98)
               const int cc = __ldg(re.ccols + i);
               re.y[row * re.ldy + cc] = __ldg(re.x + row * re.ldx + cc);
             }
           }
-#pragma unroll 1
-          for (int f = 0; f < FH; ++f) {
-            const int fl = half * FH + f;  // feature within the tile
-            uint32_t v[PPAD];
-            const uint32_t ta = tacc + (uint32_t)(fl * PPAD);
-            if constexpr (PPAD == 24) {
-              tmem_ld8(ta, v);
-              tmem_ld8(ta + 8, v + 8);
-              tmem_ld8(ta + 16, v + 16);
-            } else if constexpr (PPAD == 48) {
-              tmem_ld16(ta, v);
-              tmem_ld16(ta + 16, v + 16);
-              tmem_ld16(ta + 32, v + 32);
-            } else {
-              tmem_ld32(ta, v);
-            }
-            if (SPLIT) {
-              uint32_t v2[PPAD];
-              if constexpr (PPAD == 24) {
-                tmem_ld8(ta + BN, v2);
-                tmem_ld8(ta + BN + 8, v2 + 8);
-                tmem_ld8(ta + BN + 16, v2 + 16);
-              } else if constexpr (PPAD == 48) {
-                tmem_ld16(ta + BN, v2);
-                tmem_ld16(ta + BN + 16, v2 + 16);
-                tmem_ld16(ta + BN + 32, v2 + 32);
-              } else {
-                tmem_ld32(ta + BN, v2);
-              }
-              tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < PPAD; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-            } else {
-              tmem_wait_ld();
-            }
-            if (f == FH - 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(acc));
-            }
+          for (int f = 0; f < FH; ++f) {
+            const int fl = half * FH + f;    // feature within the tile
             const int fg = nt * FEATS + fl;  // feature of the layer
             if (fg < re.D_t) {
               const float* bp = la.bias + (nt * BN + fl * PPAD);
-              float p[PPAD];
+              float* p = av + f * PPAD;
 #pragma unroll
               for (int i = 0; i < PPAD; i += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(bp + i));
-                p[i + 0] = __uint_as_float(v[i + 0]) + b.x;
-                p[i + 1] = __uint_as_float(v[i + 1]) + b.y;
-                p[i + 2] = __uint_as_float(v[i + 2]) + b.z;
-                p[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+                p[i + 0] += b.x;
+                p[i + 1] += b.y;
+                p[i + 2] += b.z;
+                p[i + 3] += b.w;
               }
               const int col = re.tcols ? __ldg(re.tcols + fg) : fg;
               const float xv = valid ? __ldg(re.x + row * re.ldx + col) : 0.f;
@@ -365,10 +377,6 @@ __global__ void __launch_bounds__(kLinThreads, 1)
               lad_acc += lv;
             }
           }
-        }
-        if (++acc == NACC) {
-          acc = 0;
-          aph ^= 1u;
         }
       }
       if (EPI == 1) {
@@ -427,15 +435,19 @@ static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? FC_OK : FC_ERR_CUDA;
 }
 
-static int linear_variant() {
-  static int v = [] {
-    const char* e = getenv("FC_LINEAR_VARIANT");
-    return e ? atoi(e) : 2;  // 2 = split accumulators (most accurate); 0 / 1 = single accumulator, double-buffered
+// k-values per partial accumulator (see "Accumulation" at the top).  Short dot products leave less room between
+// the tensor core's truncation error and the (smaller) rounding noise of an fp32 FMA chain of the same length, so
+// they are drained after every stage.  FC_LINEAR_CHUNK_K overrides for experiments.
+static int chunk_k(int K) {
+  static int forced = [] {
+    const char* e = getenv("FC_LINEAR_CHUNK_K");
+    return e ? atoi(e) : 0;
   }();
-  return v;
+  if (forced > 0) return forced < 16 ? 16 : forced;
+  return K <= 64 ? 16 : 32;
 }
 
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, bool SPLIT>
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD>
 static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, LinArgs la,
                          const StoreEpi& se, const RqsEpi& re, cudaStream_t stream) {
   using SM = LinSmem<BN, BK, STAGES>;
@@ -446,11 +458,12 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   rc = make_map(&tmB, w->w, (uint64_t)2 * w->n_pad, (uint64_t)w->k_pad, (uint64_t)w->k_pad, BN, BK);
   if (rc != FC_OK) return rc;
   la.M = (int)M;
-  la.num_k_chunks = (K + BK - 1) / BK;
+  la.num_k_stages = (K + BK - 1) / BK;
+  la.chunk = chunk_k(K) / BK > 0 ? chunk_k(K) / BK : 1;
   la.num_m_tiles = (int)((M + kBM - 1) / kBM);
   la.n_pad = w->n_pad;
   la.bias = w->bias;
-  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, SPLIT>;
+  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess)
@@ -528,11 +541,7 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
   la.num_n_tiles = (n_out + BN - 1) / BN;
-  if (linear_variant() == 1)
-    return launch_linear<0, BN, 16, 4, 0, 32, false>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
-  if (linear_variant() == 2)
-    return launch_linear<0, BN, 16, 4, 0, 32, true>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
-  return launch_linear<0, BN, 32, 2, 0, 32, false>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  return launch_linear<0, BN, 16, 4, 0, 32>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
 }
 
 extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
@@ -554,26 +563,17 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
   StoreEpi se{};
   RqsEpi re{x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, tcols.idx, ccols.idx, ccols.n, D_t, c, status};
   constexpr int BN = 192;
-  const int v = linear_variant();
   if (c.K == 8) {
     constexpr int PPAD = 24;
     la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
     if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
-    if (v == 1)
-      return launch_linear<1, BN, 16, 5, 8, PPAD, false>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    if (v == 2)
-      return launch_linear<1, BN, 16, 5, 8, PPAD, true>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    return launch_linear<1, BN, 32, 2, 8, PPAD, false>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    return launch_linear<1, BN, 16, 5, 8, PPAD>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   if (c.K == 16) {
     constexpr int PPAD = 48;
     la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
     if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
-    if (v == 1)
-      return launch_linear<1, BN, 16, 5, 16, PPAD, false>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    if (v == 2)
-      return launch_linear<1, BN, 16, 5, 16, PPAD, true>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    return launch_linear<1, BN, 32, 2, 16, PPAD, false>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    return launch_linear<1, BN, 16, 5, 16, PPAD>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   return FC_ERR_UNSUPPORTED;
 }

@@ -63,16 +63,17 @@ def error_profile(gen, dev):
         r = (got - want) / want
         print("  positive operands  {:12s}: mean signed rel err {:+.3e}  rms {:.3e}  max {:.3e}".format(
             name, r.mean().item(), r.pow(2).mean().sqrt().item(), r.abs().max().item()))
-    a = torch.randn(M, K, generator=gen, device=dev)
-    w = torch.randn(N, K, generator=gen, device=dev) / 16
-    pk = fl.pack(w, b)
-    out = fl.linear(a, pk).double()
-    want = a.double() @ w.double().t()
-    ref = torch.nn.functional.linear(a, w, b).double()
-    for name, got in (("ours", out), ("cublas-fp32", ref)):
-        e = (got - want)
-        print("  gaussian operands  {:12s}: rms abs err {:.3e}  max {:.3e}  (rms |out| {:.3f})".format(
-            name, e.pow(2).mean().sqrt().item(), e.abs().max().item(), want.pow(2).mean().sqrt().item()))
+    for K in (32, 64, 256):
+        a = torch.randn(M, K, generator=gen, device=dev)
+        w = torch.randn(N, K, generator=gen, device=dev) / math.sqrt(K)
+        pk = fl.pack(w, b)
+        out = fl.linear(a, pk).double()
+        want = a.double() @ w.double().t()
+        ref = torch.nn.functional.linear(a, w, b).double()
+        for name, got in (("ours", out), ("cublas-fp32", ref)):
+            e = (got - want)
+            print("  gaussian operands K={:3d} {:12s}: rms abs err {:.3e}  max {:.3e}  (rms |out| {:.3f})".format(
+                K, name, e.pow(2).mean().sqrt().item(), e.abs().max().item(), want.pow(2).mean().sqrt().item()))
 
 
 def check_colmap(gen, dev):

@@ -33,7 +33,7 @@ def rel_err(a, b, floor):
     return (a - b).abs() / b.abs().clamp_min(floor)
 
 
-def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0):
+def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0, max_ratio=10.0):
     """Three-way parity (the 1e-5 tolerance sits AT the reference's own fp32 noise floor —
     reference-fp32 vs reference-fp64 already differ by >1e-5 on a small fraction of ill-conditioned elements:
     tiny bins, theta near 0/1, values near 0).  An element passes if
@@ -42,7 +42,9 @@ def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0):
     Elements failing both are tolerated only if, as a population, we are no less accurate than the reference:
         (iii) at most 2% of elements fail (i)&(ii), AND every quantile (50/90/99%) of |ours - ref64| is
               <= (1.5 + 3/sqrt(n(1-q)))x the same quantile of |ref32 - ref64| (+ tol*floor/10), AND
-              max|ours - ref64| <= 10 * max|ref32 - ref64| + tol*floor  (a wrong bin would be ~1e-2).
+              max|ours - ref64| <= max_ratio * max|ref32 - ref64| + tol*floor  (max_ratio = 10; callers that
+              push rows through a whole ill-conditioned stack, where the error is heavy-tailed and the max of a
+              small sample is itself noisy, pass a larger ratio and check each layer separately at 10).
     scripts/accuracy_report.py measures the same ratios on 262k-element samples (profiles/accuracy_*.txt).
     Returns the max of |ours - ref32| / max(|ref32|, floor)."""
     ours = ours.detach().double().cpu()
@@ -67,7 +69,7 @@ def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0):
         # a quantile estimated from m = n (1 - q) tail samples is itself noisy: allow 1.5x + 3 / sqrt(m)
         limit = 1.5 + 3.0 / torch.sqrt(ours.numel() * (1 - q)).clamp_min(1.0)
         pop_ok = (frac <= 2e-2 + 4.0 / ours.numel() and bool((qo <= limit * qr + tol * floor / 10).all())
-                  and float(e64.max()) <= 10 * float(noise.max()) + tol * floor)
+                  and float(e64.max()) <= max_ratio * float(noise.max()) + tol * floor)
         if not pop_ok:
             i = torch.nonzero(bad)[0]
             idx = tuple(i.tolist())

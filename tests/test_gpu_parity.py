@@ -343,7 +343,37 @@ def test_full_size_cfg2_log_prob(dev):
         o32 = restated.flow_log_prob(cpu_state, specs, x[rows].cpu())
         o64 = restated.flow_log_prob({k: (v.double() if v.is_floating_point() else v) for k, v in cpu_state.items()},
                                      specs, x[rows].cpu().double())
-    assert_parity(lp[rows], o32, o64, OUT_TOL, 1.0, "cfg2 full-size log_prob rows")
+    # eight ill-conditioned layers in sequence: the per-row error is heavy-tailed (profiles/r01_tc_error_by_layer.txt)
+    # and the max over 1024 rows is a noisy statistic, so the whole-stack check bounds it at 30x the reference's
+    # own max; every layer is checked on its own at the usual 10x in test_cfg2_layers_match_oracle.
+    assert_parity(lp[rows], o32, o64, OUT_TOL, 1.0, "cfg2 full-size log_prob rows", max_ratio=30.0)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_cfg2_layers_match_oracle(dev, tc, monkeypatch):
+    """Every layer of the full-size cfg 2 model on its own: the layer's input is the fp32 oracle's output of the
+    previous layer, so the comparison sees one conditioner + spline evaluation, not the chaotic amplification of
+    the whole stack.  tc=True is the tensor-core inference path (3xTF32 GEMMs, spline in the epilogue), tc=False
+    the unfused path (torch conditioner + element-wise kernel)."""
+    from flowconductor_b200.nn import tensorcore
+
+    monkeypatch.setattr(tensorcore, "ENABLED", tc)
+    wl = workloads.get_workload("cfg2")
+    flow = workloads.build_flow(wl)
+    state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl)
+    flow.load_state_dict(state)
+    specs = workloads.oracle_specs(wl)
+    state64 = {k: (v.double() if v.is_floating_point() else v) for k, v in state.items()}
+    flow = flow.to(dev)
+    h = torch.randn(4096, 64, generator=torch.Generator().manual_seed(99))
+    with torch.no_grad():
+        for li, (layer, spec) in enumerate(zip(flow._transform._transforms, specs)):
+            y64, l64 = restated.apply_layer(state64, spec, h.double())
+            y32, l32 = restated.apply_layer(state, spec, h)
+            y, lad = layer(h.to(dev))
+            assert_parity(y, y32, y64, OUT_TOL, 1.0, "cfg2 layer {} outputs (tc={})".format(li, tc))
+            assert_parity(lad, l32, l64, OUT_TOL, 1.0, "cfg2 layer {} logabsdet (tc={})".format(li, tc))
+            h = y32
 
 
 @pytest.mark.parametrize("d,k", [(64, 8), (256, 8)])
