@@ -32,6 +32,7 @@ WORKLOAD = "cfg2"
 CPU_SAMPLE_ROWS = 262144      # cpu_baseline leg of the default run (~10-30 s of host work)
 REF_STEP_ROWS = 65536         # --impl reference: rows per step (bounded so K+W steps end within minutes)
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+FALLBACK_BF16_TFLOPS = 2250.0
 
 
 def parse():
@@ -54,6 +55,30 @@ def measured_peak():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """Dense tf32 tensor peak in TFLOP/s = half the measured dense bf16 rate (kind::tf32 UMMAs retire 8 k-values
+    per 128xN instruction where kind::f16 retires 16).  The kernels run inside a long step -> sustained figure."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return (float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2,
+                    "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2 = dense tf32)")
+        except Exception:
+            pass
+    return FALLBACK_BF16_TFLOPS / 2, "fallback (B200_PROFILING.md nominal dense bf16 2250 / 2 = dense tf32)"
+
+
+def profile_json(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return {}
+    return {}
 
 
 def build_state(wl):
@@ -236,7 +261,8 @@ def run_ours(args, wl):
     _cabi.STATS.timing = False
     ms = start.elapsed_time(end)
     launches = _cabi.STATS.total()
-    n_k, k_ms = _cabi.STATS.elapsed_ms("fc_rqs_apply")
+    n_f, f_ms = _cabi.STATS.elapsed_ms("fc_linear_rqs_apply")   # final conditioner layer + spline (tensor cores)
+    n_h, h_ms = _cabi.STATS.elapsed_ms("fc_linear_apply")       # other conditioner layers (tensor cores)
     clocks = sampler.stop() if rank == 0 else None
     ll = float(total.item())
     assert ll == ll, "log-likelihood is NaN"
@@ -270,21 +296,65 @@ def run_ours(args, wl):
     if rank == 0:
         value = world * B * args.steps / (ms * 1e-3)
         e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-        # roofline of the dominant hand-written kernel: the RQ-spline layer (one launch per layer).
-        # algorithmic bytes per sample per launch (SURVEY 8d): x + params + y + lad + identity copy
         first = wl["layers"][0]
         d_t = D // 2
+        H = first["hidden_features"]
         p_per = 3 * first["num_bins"] - 1
+        # (1) the fused final-layer kernel (north_star item 3): tensor bound.  Algorithmic flops per launch =
+        # 2 * rows * H * (D_t * P); the kernel executes 3 tf32 UMMAs per product on N padded to 24 columns
+        # per feature, so the tensor pipe does 3 * 2 * rows * H * (D_t * 24).
+        tpeak, tpeak_src = measured_tensor_peak()
+        alg_flops = 2.0 * B * H * d_t * p_per
+        exec_flops = 3 * 2.0 * B * H * d_t * 24
+        f_each = (f_ms / n_f) if n_f else None
+        roofline = {"bound": "tensor", "kernel": "linear_tf32x3_kernel<EPI=rqs> (fc_linear_rqs_apply: final conditioner "
+                                                 "GEMM + RQ spline epilogue)",
+                    "achieved": (alg_flops / (f_each * 1e-3) / 1e12) if f_each else None, "peak": tpeak,
+                    "unit": "TFLOP/s", "frac": (alg_flops / (f_each * 1e-3) / 1e12 / tpeak) if f_each else None,
+                    "traffic": profile_json("traffic_linear_rqs_apply.json").get("dram_bytes_per_launch"),
+                    "peak_source": tpeak_src, "algorithmic_flops_per_launch": alg_flops,
+                    "tensor_flops_executed_per_launch": exec_flops,
+                    "tensor_pipe_frac": (exec_flops / (f_each * 1e-3) / 1e12 / tpeak) if f_each else None,
+                    "kernel_ms_per_launch": f_each, "kernel_share_of_step": (f_ms / ms) if n_f else None,
+                    "launches_timed": n_f,
+                    "note": "3xTF32 (fp32-faithful): 3 tf32 UMMAs per fp32 product, so frac <= 1/3 * 23/24"}
+        # (2) the other conditioner layers (same kernel, store epilogue): 4 x (H x H) + 1 x (D x H) per flow layer
+        n_layers = len(wl["layers"])
+        hid_alg = 2.0 * B * (4 * H * H + d_t * H) * n_layers * args.steps
+        hid_exec = 3 * 2.0 * B * (4 * H * H + D * H) * n_layers * args.steps  # first layer reads the full-width rows
+        roofline_hidden = {"bound": "tensor", "kernel": "linear_tf32x3_kernel<EPI=store> (fc_linear_apply)",
+                           "achieved": (hid_alg / (h_ms * 1e-3) / 1e12) if n_h else None, "peak": tpeak,
+                           "unit": "TFLOP/s", "frac": (hid_alg / (h_ms * 1e-3) / 1e12 / tpeak) if n_h else None,
+                           "tensor_pipe_frac": (hid_exec / (h_ms * 1e-3) / 1e12 / tpeak) if n_h else None,
+                           "kernel_share_of_step": (h_ms / ms) if n_h else None, "launches_timed": n_h}
+        # (3) the stand-alone element-wise RQ-spline layer kernel (north_star items 1-2; the path taken whenever the
+        # parameters are materialised: training, unsupported conditioners): HBM bound.  Not on the inference step
+        # above, so it is timed here on its own: 10 launches over a materialised [B, D_t * P] parameter tensor.
+        # algorithmic bytes per sample per launch (SURVEY 8d): x + params + y + lad + identity copy
         bytes_per_sample = 4 * d_t + 4 * d_t * p_per + 4 * d_t + 4 + 8 * (D - d_t)
         peak, peak_src = measured_peak()
+        layer0 = flow._transform._transforms[0]
+        prm = torch.randn(B, d_t * p_per, device=dev)
+        _cabi.STATS.reset()
+        with torch.no_grad():
+            for _ in range(3):
+                layer0._coupling_layer(x, prm, False)
+            torch.cuda.synchronize()
+            _cabi.STATS.reset()
+            _cabi.STATS.timing = True
+            for _ in range(10):
+                layer0._coupling_layer(x, prm, False)
+            torch.cuda.synchronize()
+            _cabi.STATS.timing = False
+        n_k, k_ms = _cabi.STATS.elapsed_ms("fc_rqs_apply")
+        del prm
         achieved = bytes_per_sample * B / ((k_ms / max(n_k, 1)) * 1e-3) / 1e9 if n_k else None
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_rqs_apply.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        roofline_hbm = {"bound": "hbm", "kernel": "pipelined_apply_kernel<RqsOp<8>, true> (fc_rqs_apply), timed alone",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": (achieved / peak) if achieved else None,
+                        "traffic": profile_json("traffic_rqs_apply.json").get("dram_bytes_per_launch"),
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_sample * B,
+                        "kernel_ms_per_launch": (k_ms / n_k) if n_k else None, "launches_timed": n_k}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -294,12 +364,7 @@ def run_ours(args, wl):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "pipelined_apply_kernel<RqsOp<8>, true> (fc_rqs_apply)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_sample * B,
-                         "kernel_ms_per_launch": (k_ms / n_k) if n_k else None,
-                         "kernel_share_of_step": (k_ms / ms) if n_k else None, "launches_timed": n_k},
+            "roofline": roofline, "roofline_hidden_layers": roofline_hidden, "roofline_elementwise": roofline_hbm,
             "log_likelihood_sum": ll,
         }
         if world == 1 and not args.no_cpu_baseline:
