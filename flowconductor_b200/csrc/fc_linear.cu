@@ -54,6 +54,8 @@ struct LinArgs {
   int num_m_tiles, num_n_tiles;
   int n_pad;         // rows of one weight plane (lo plane starts at row n_pad of the weight tensor map)
   int relu_in;       // ReLU applied to A while splitting
+  int a_tiled;       // A is stored in the T128 activation layout (include/flowcon_b200.h)
+  int debug;         // experiments only (FC_LINEAR_DEBUG): 1 = converters skip their work, 2 = epilogue skips its math
   const float* bias;  // [n_pad]
 };
 
@@ -64,6 +66,7 @@ struct StoreEpi {
   int64_t ldr;
   int n_out;
   int relu_out;
+  int tiled;  // out (and residual) are stored in the T128 layout; ldo / ldr are then their logical widths
 };
 
 struct RqsEpi {
@@ -81,16 +84,19 @@ struct RqsEpi {
   int32_t* status;
 };
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int CTAS>
 struct LinSmem {
   static constexpr int A_BYTES = kBM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = (BN / CTAS) * BK * 4;  // a CTA pair splits the rows of every weight box
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int BAR_BYTES = 8 * (3 * STAGES + 4) + 16;
+  static constexpr int BAR_BYTES = 8 * (4 * STAGES + 4) + 16;
   static constexpr int LAD_BYTES = 2 * kBM * 4;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + LAD_BYTES + 1024;  // + alignment slack
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
 };
+
+// experiments only (FC_LINEAR_DEBUG & 4): cycles the MMA-issuing thread / one epilogue warp of CTA 0 spend waiting
+__device__ unsigned long long g_lin_prof[16];
 
 template <int N>
 __device__ __forceinline__ void set_max_regs_inc() {
@@ -127,11 +133,23 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
 
 // EPI: 0 = store (bias, optional residual / ReLU), 1 = rational-quadratic spline with KC bins.
 // RQS tile geometry: FEATS features of PPAD accumulator columns each (BN = FEATS * PPAD).
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD>
+// MODE 1: one CTA per SM, independent.
+// MODE 3: clusters of two CTAs work on two row tiles in lock step and SHARE the weight stream: each CTA fetches half
+//   of every weight box and TMA-multicasts it into both shared memories, which halves the L2 -> SM weight traffic
+//   (the weights are re-streamed for every 128-row tile: 512 KB per tile for a 256 x 256 layer, 1.5 MB for the final
+//   layer).  MMAs stay single-CTA; a ring slot is recycled once BOTH CTAs' MMAs have released it.
+// MODE 2: clusters of two CTAs (the two SMs of a TPC) that issue ONE tcgen05.mma.cta_group::2 (256 x BN x 8) per
+//   product: each CTA stages its own 128 rows of A but only HALF of every weight box, so the weight traffic (L2 ->
+//   shared memory AND shared memory -> tensor core) per SM is halved and the ring is 1.5x deeper.  Rank 0 (the leader)
+//   issues the MMAs; rank 1's warp 1 relays "my stage is loaded and converted" to the leader.
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE>
 __global__ void __launch_bounds__(kLinThreads, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const LinArgs la, const StoreEpi se, const RqsEpi re) {
-  using SM = LinSmem<BN, BK, STAGES>;
+  constexpr int CTAS = MODE == 2 ? 2 : 1;  // CTAs per MMA
+  constexpr bool MC = MODE == 3;           // weight boxes multicast inside the cluster
+  constexpr int CL = MODE == 1 ? 1 : 2;    // cluster size = row tiles per work unit
+  using SM = LinSmem<BN, BK, STAGES, CTAS>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 1023u) & ~1023u;
@@ -140,16 +158,20 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (3 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (3 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  auto ready_bar = [&](int s) { return bars + 8u * (3 * STAGES + s); };  // leader only: peer's stage is ready
+  auto tfull_bar = [&](int a) { return bars + 8u * (4 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (4 * STAGES + 2 + a); };  // leader's is the one in use
+  const uint32_t tmem_slot = bars + 8u * (4 * STAGES + 4);
   volatile uint32_t* const tmem_slot_g =
-      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * SM::STAGE_BYTES + 8 * (3 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * SM::STAGE_BYTES + 8 * (4 * STAGES + 4));
   float* const lad_x = reinterpret_cast<float*>(gbase + STAGES * SM::STAGE_BYTES + SM::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 512;
   static_assert(2 * BN <= 512, "two partial accumulators must fit in tensor memory");
+  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / CL, unit_step = (int)gridDim.x / CL;  // cluster index / count
+  const int n_units = (la.num_m_tiles + CL - 1) / CL;                        // 128*CL-row work units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -157,17 +179,28 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(conv_bar(s), kNumConv);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 2 : 1);
+      mbar_init(ready_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 8 * CTAS);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) {
+    if (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+    }
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) {
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
 
@@ -183,15 +216,53 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       if (lane == 0) {
         int s = 0;
         uint32_t ph = 0;
-        for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
+        for (int mp = unit0; mp < n_units; mp += unit_step) {
+          const int mt = mp * CL + rank;
+          // The skip connection of the NEXT row tile of this CTA (one contiguous block in either layout) is pulled
+          // into L2 slice by slice while this tile is computed: fetched by the epilogue in one burst from HBM it
+          // would stall the tile for ~6k cycles (128 KB at one SM's share of the HBM bandwidth).
+          const char* pf_base = nullptr;
+          uint32_t pf_bytes = 0, pf_slice = 0;
+          if (EPI == 0 && se.residual != nullptr) {
+            const int mt_next = (mp + unit_step) * CL + rank;
+            if (mt_next < la.num_m_tiles) {
+              const int64_t rows_left = (int64_t)la.M - (int64_t)mt_next * kBM;
+              const int rows = se.tiled ? kBM : (rows_left < kBM ? (int)rows_left : kBM);
+              pf_base = reinterpret_cast<const char*>(se.residual + (int64_t)mt_next * kBM * se.ldr);
+              pf_bytes = (uint32_t)rows * (uint32_t)se.ldr * 4u;
+              pf_slice = ((pf_bytes / (uint32_t)(nk * n_tiles)) + 15u) & ~15u;
+            }
+          }
+          uint32_t pf_done = 0;
           for (int nt = 0; nt < n_tiles; ++nt) {
+            const int brow = nt * BN + rank * (BN / CL);  // this CTA's share of the weight rows of the tile
             for (int kc = 0; kc < nk; ++kc) {
-              mbar_wait(empty_bar(s), ph ^ 1u);
+              if (pf_done < pf_bytes) {
+                const uint32_t nb = pf_bytes - pf_done < pf_slice ? pf_bytes - pf_done : pf_slice;
+                bulk_prefetch_l2(pf_base + pf_done, nb);
+                pf_done += nb;
+              }
+              if (CL == 2) {
+                mbar_wait_cluster(empty_bar(s), ph ^ 1u);
+              } else {
+                mbar_wait(empty_bar(s), ph ^ 1u);
+              }
               const uint32_t st = base + s * SM::STAGE_BYTES;
               mbar_expect_tx(full_bar(s), SM::A_BYTES + 2 * SM::B_BYTES);
-              tma_load_2d(st, &tmA, kc * BK, mt * kBM, full_bar(s));
-              tma_load_2d(st + 2 * SM::A_BYTES, &tmB, kc * BK, nt * BN, full_bar(s));
-              tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + nt * BN, full_bar(s));
+              if (la.a_tiled) {
+                tma_load_4d(st, &tmA, 0, 0, kc * (BK / 4), mt, full_bar(s));
+              } else {
+                tma_load_2d(st, &tmA, kc * BK, mt * kBM, full_bar(s));
+              }
+              if (MC) {
+                const uint32_t half_off = (uint32_t)rank * (SM::B_BYTES / 2);
+                tma_load_2d_multicast(st + 2 * SM::A_BYTES + half_off, &tmB, kc * BK, brow, full_bar(s), 3);
+                tma_load_2d_multicast(st + 2 * SM::A_BYTES + SM::B_BYTES + half_off, &tmB, kc * BK, la.n_pad + brow,
+                                      full_bar(s), 3);
+              } else {
+                tma_load_2d(st + 2 * SM::A_BYTES, &tmB, kc * BK, brow, full_bar(s));
+                tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + brow, full_bar(s));
+              }
               if (++s == STAGES) {
                 s = 0;
                 ph ^= 1u;
@@ -201,46 +272,123 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- UMMA issuer
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
+      // ---------------------------------------------------------------- UMMA issuer (leader) / relay (peer)
+      if (CTAS == 1 || rank == 0) {
+        // The WHOLE warp walks the loop and waits on the barriers, one elected lane issues: with warp-uniform control
+        // flow the descriptors stay in uniform registers.  (Issued from inside `if (lane == 0)` every tcgen05.mma
+        // was preceded by a ~12-instruction vector->uniform register "waterfall" loop, ~130 dependent instructions
+        // per stage, which is as long as the six MMAs of a stage take to execute: the issuing thread, not the
+        // tensor pipe, set the pace.)
+        constexpr uint32_t idesc = make_idesc_tf32(kBM * CTAS, BN);
         int s = 0, acc = 0;
         uint32_t ph = 0, aph = 0;
-        for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
+        const bool prof = (la.debug & 4) && blockIdx.x == 0;
+        long long t_tempty = 0, t_conv = 0, t_ready = 0, t_stages = 0;
+        const long long t_begin = clock64();
+        // descriptors of ring slot 0; slot s adds s * STAGE_BYTES to the 16-byte-granular address field
+        const bool tiled = la.a_tiled != 0;
+        const uint64_t a_hi0 = tiled ? make_smem_desc_noswizzle(base, kBM * 16, 128) : make_smem_desc(base, BK * 4);
+        const uint64_t a_lo0 = tiled ? make_smem_desc_noswizzle(base + SM::A_BYTES, kBM * 16, 128)
+                                     : make_smem_desc(base + SM::A_BYTES, BK * 4);
+        const uint64_t b_hi0 = make_smem_desc(base + 2 * SM::A_BYTES, BK * 4);
+        const uint64_t b_lo0 = make_smem_desc(base + 2 * SM::A_BYTES + SM::B_BYTES, BK * 4);
+        // 8 k-values further along K: T128 operands (no swizzle) jump two column groups, swizzled ones 32 bytes
+        const uint64_t a_step = tiled ? (uint64_t)((2 * kBM * 16) >> 4) : 2ull;
+        for (int mp = unit0; mp < n_units; mp += unit_step) {
           for (int nt = 0; nt < n_tiles; ++nt) {
             for (int k0 = 0; k0 < nk; k0 += chunk) {
               const int k1 = k0 + chunk < nk ? k0 + chunk : nk;
-              mbar_wait(tempty_bar(acc), aph ^ 1u);
+              long long t0 = prof ? clock64() : 0;
+              if (CTAS == 2) {
+                mbar_wait_cluster(tempty_bar(acc), aph ^ 1u);
+              } else {
+                mbar_wait(tempty_bar(acc), aph ^ 1u);
+              }
+              if (prof) t_tempty += clock64() - t0;
               tc_fence_after();
               const uint32_t d = tmem_base + (uint32_t)(acc * BN);
               for (int kc = k0; kc < k1; ++kc) {
-                mbar_wait(full_bar(s), ph);
+                if (prof) t0 = clock64();
+                // the converters arrive only after THEIR wait on full_bar, so conv_bar also covers the TMA boxes
                 mbar_wait(conv_bar(s), ph);
-                tc_fence_after();
-                const uint32_t st = base + s * SM::STAGE_BYTES;
-                const uint64_t a_hi = make_smem_desc(st, BK * 4);
-                const uint64_t a_lo = make_smem_desc(st + SM::A_BYTES, BK * 4);
-                const uint64_t b_hi = make_smem_desc(st + 2 * SM::A_BYTES, BK * 4);
-                const uint64_t b_lo = make_smem_desc(st + 2 * SM::A_BYTES + SM::B_BYTES, BK * 4);
-#pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {
-                  const uint64_t o = (uint64_t)(kk * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along K in the swizzle span
-                  // small terms first, so they are not absorbed by the large one before they have been summed
-                  umma_tf32_ss(d, a_lo + o, b_hi + o, idesc, (kc > k0 || kk > 0) ? 1u : 0u);
-                  umma_tf32_ss(d, a_hi + o, b_lo + o, idesc, 1u);
-                  umma_tf32_ss(d, a_hi + o, b_hi + o, idesc, 1u);
+                if (prof) {
+                  const long long t1 = clock64();
+                  t_conv += t1 - t0;
+                  t0 = t1;
                 }
-                umma_commit(empty_bar(s));
+                if (CTAS == 2) mbar_wait_cluster(ready_bar(s), ph);
+                if (prof) {
+                  t_ready += clock64() - t0;
+                  ++t_stages;
+                }
+                tc_fence_after();
+                const uint64_t so = (uint64_t)((uint32_t)s * (uint32_t)(SM::STAGE_BYTES >> 4));
+                const uint64_t a_hi = a_hi0 + so, a_lo = a_lo0 + so, b_hi = b_hi0 + so, b_lo = b_lo0 + so;
+                if (elect_one()) {
+#pragma unroll
+                  for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t o = (uint64_t)(kk * 2);  // 8 tf32 = 32 bytes = 2 x 16 B inside the swizzle span
+                    const uint64_t oa = a_step * (uint64_t)kk;
+                    const uint32_t first = (kc > k0 || kk > 0) ? 1u : 0u;
+                    // small terms first, so they are not absorbed by the large one before they have been summed
+                    if (CTAS == 2) {
+                      umma_tf32_ss_pair(d, a_lo + oa, b_hi + o, idesc, first);
+                      umma_tf32_ss_pair(d, a_hi + oa, b_lo + o, idesc, 1u);
+                      umma_tf32_ss_pair(d, a_hi + oa, b_hi + o, idesc, 1u);
+                    } else {
+                      umma_tf32_ss(d, a_lo + oa, b_hi + o, idesc, first);
+                      umma_tf32_ss(d, a_hi + oa, b_lo + o, idesc, 1u);
+                      umma_tf32_ss(d, a_hi + oa, b_hi + o, idesc, 1u);
+                    }
+                  }
+                  if (CTAS == 2) {
+                    umma_commit_pair(empty_bar(s), 3);
+                  } else if (MC) {
+                    umma_commit_multicast(empty_bar(s), 3);
+                  } else {
+                    umma_commit(empty_bar(s));
+                  }
+                  if (kc == k1 - 1) {
+                    if (CTAS == 2) {
+                      umma_commit_pair(tfull_bar(acc), 3);
+                    } else {
+                      umma_commit(tfull_bar(acc));
+                    }
+                  }
+                }
+                __syncwarp();
                 if (++s == STAGES) {
                   s = 0;
                   ph ^= 1u;
                 }
               }
-              umma_commit(tfull_bar(acc));
               if (++acc == 2) {
                 acc = 0;
                 aph ^= 1u;
               }
+            }
+          }
+        }
+        if (prof && lane == 0) {
+          g_lin_prof[0] = (unsigned long long)(clock64() - t_begin);
+          g_lin_prof[1] = (unsigned long long)t_tempty;
+          g_lin_prof[2] = 0;
+          g_lin_prof[3] = (unsigned long long)t_conv;
+          g_lin_prof[4] = (unsigned long long)t_ready;
+          g_lin_prof[5] = (unsigned long long)t_stages;
+        }
+      } else if (CTAS == 2 && lane == 0) {
+        // peer CTA: tell the leader when this CTA's half of a stage has landed and been converted
+        int s = 0;
+        uint32_t ph = 0;
+        for (int mp = unit0; mp < n_units; mp += unit_step) {
+          for (int it = 0; it < n_tiles * nk; ++it) {
+            mbar_wait(full_bar(s), ph);
+            mbar_wait(conv_bar(s), ph);
+            mbar_arrive_remote(ready_bar(s), 0);
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1u;
             }
           }
         }
@@ -253,10 +401,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     int s = 0;
     uint32_t ph = 0;
     const bool relu = la.relu_in != 0;
-    for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
+    for (int mp = unit0; mp < n_units; mp += unit_step) {
       for (int it = 0; it < n_tiles * nk; ++it) {
         mbar_wait(full_bar(s), ph);
         const uint32_t st = base + s * SM::STAGE_BYTES;
+        if (!(la.debug & 1))
 #pragma unroll
         for (int v = ct; v < SM::A_BYTES / 16; v += kNumConv) {
           const uint32_t addr = st + (uint32_t)v * 16u;
@@ -273,7 +422,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           sts128(addr, h0, h1, h2, h3);
           sts128(addr + SM::A_BYTES, l0, l1, l2, l3);
         }
-        fence_proxy_async_smem();
+        if (CTAS == 2) {
+          fence_proxy_async_all();  // the reader is the leader's tensor core
+        } else {
+          fence_proxy_async_smem();
+        }
         mbar_arrive(conv_bar(s));
         if (++s == STAGES) {
           s = 0;
@@ -292,88 +445,152 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     uint32_t aph = 0;
     unsigned status = 0;
     int parity = 0;
-    for (int mt = blockIdx.x; mt < la.num_m_tiles; mt += gridDim.x) {
+    const bool eprof = (la.debug & 4) && blockIdx.x == 0 && warp == kEpiWarp0;
+    long long e_init = 0, e_wait = 0, e_drain = 0, e_final = 0, e_t = 0;
+    const long long e_begin = clock64();
+    for (int mp = unit0; mp < n_units; mp += unit_step) {
+      const int mt = mp * CL + rank;
       const int64_t row = (int64_t)mt * kBM + q * 32 + lane;
       const bool valid = row < la.M;
       float lad_acc = 0.f;
       for (int nt = 0; nt < n_tiles; ++nt) {
         float av[NCOL];
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          mbar_wait(tfull_bar(acc), aph);
-          tc_fence_after();
-          const uint32_t tacc = tmem_base + lane_sel + (uint32_t)(acc * BN + half * NCOL);
-          if (ch == 0) {
-            drain_partial<NCOL, true>(tacc, av);
-          } else {
-            drain_partial<NCOL, false>(tacc, av);
-          }
-          tc_fence_before();  // partial accumulator fully read by this warp: hand it back to the MMA warp
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-          if (++acc == 2) {
-            acc = 0;
-            aph ^= 1u;
-          }
-        }
+        if (eprof) e_t = clock64();
+        // Start of the tile, while its first MMAs are still running: the register accumulators start from the bias
+        // (+ the skip connection), and the spline's inputs are fetched, so that no global-load latency is left
+        // between the last partial accumulator and the stores.
+        const int rt = q * 32 + lane;
+        int64_t o_base = 0, r_base = 0, n_mul = 1;
+        float xv[EPI == 1 ? (BN / PPAD) / 2 : 1];
+        int xcol[EPI == 1 ? (BN / PPAD) / 2 : 1];
         if (EPI == 0) {
+          // T128: element (r, n) of tile mt at mt*128*W + ((n/4)*128 + r)*4: a warp's 32 rows of one column group
+          // are 512 contiguous bytes (coalesced); row-major: 32 rows x 16 B scattered over 32 lines
+          o_base = se.tiled ? (int64_t)mt * kBM * se.ldo + rt * 4 : row * se.ldo;
+          r_base = se.tiled ? (int64_t)mt * kBM * se.ldr + rt * 4 : row * se.ldr;
+          n_mul = se.tiled ? kBM : 1;  // float offset per unit of n (n is a multiple of 4)
           const int n0 = nt * BN + half * NCOL;
           const float4* b4 = reinterpret_cast<const float4*>(la.bias + n0);
+          const bool res = se.residual != nullptr && (valid || se.tiled);
+          // skip connection first, straight into the accumulator registers: 32 independent 16-byte loads in flight
+          // (with the bias first the compiler funnels the residual through one temporary and serialises them).
+          // The producer warp prefetched this tile's residual block into L2 while the previous tile was computed.
+#pragma unroll
+          for (int j = 0; j < NCOL / 4; ++j) {
+            const int n = n0 + 4 * j;
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (res && n < se.n_out) r = __ldg(reinterpret_cast<const float4*>(se.residual + r_base + n * n_mul));
+            av[4 * j + 0] = r.x;
+            av[4 * j + 1] = r.y;
+            av[4 * j + 2] = r.z;
+            av[4 * j + 3] = r.w;
+          }
 #pragma unroll
           for (int j = 0; j < NCOL / 4; ++j) {
             const float4 b = __ldg(b4 + j);
-            float4 o;
-            o.x = av[4 * j + 0] + b.x;
-            o.y = av[4 * j + 1] + b.y;
-            o.z = av[4 * j + 2] + b.z;
-            o.w = av[4 * j + 3] + b.w;
-            const int n = n0 + 4 * j;
-            if (valid && n < se.n_out) {
-              if (se.residual) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(se.residual + row * se.ldr + n));
-                o.x += r.x;
-                o.y += r.y;
-                o.z += r.z;
-                o.w += r.w;
-              }
-              if (se.relu_out) {
-                o.x = fmaxf(o.x, 0.f);
-                o.y = fmaxf(o.y, 0.f);
-                o.z = fmaxf(o.z, 0.f);
-                o.w = fmaxf(o.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(se.out + row * se.ldo + n) = o;
-            }
+            av[4 * j + 0] += b.x;
+            av[4 * j + 1] += b.y;
+            av[4 * j + 2] += b.z;
+            av[4 * j + 3] += b.w;
           }
         } else {
           constexpr int FEATS = BN / PPAD;
           constexpr int FH = FEATS / 2;
-          static_assert(FH * PPAD == NCOL, "feature groups must tile the column half exactly");
-          if (nt == 0 && half == 0 && valid && re.n_copy > 0 && re.y != re.x) {
-            for (int i = 0; i < re.n_copy; ++i) {  // identity columns (coupling.py:96-98)
-              const int cc = __ldg(re.ccols + i);
-              re.y[row * re.ldy + cc] = __ldg(re.x + row * re.ldx + cc);
+          if (nt == 0 && half == 0 && re.n_copy > 0 && re.y != re.x) {
+            // identity columns (coupling.py:96-98): the warp copies its 32 rows one row per step (coalesced)
+            const int64_t row0 = (int64_t)mt * kBM + q * 32;
+            for (int i0 = 0; i0 < re.n_copy; i0 += 32) {
+              const int cc = (i0 + lane < re.n_copy) ? __ldg(re.ccols + i0 + lane) : -1;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                if (cc >= 0 && row0 + r < la.M) re.y[(row0 + r) * re.ldy + cc] = __ldg(re.x + (row0 + r) * re.ldx + cc);
+              }
             }
           }
 #pragma unroll
           for (int f = 0; f < FH; ++f) {
             const int fl = half * FH + f;    // feature within the tile
             const int fg = nt * FEATS + fl;  // feature of the layer
-            if (fg < re.D_t) {
-              const float* bp = la.bias + (nt * BN + fl * PPAD);
-              float* p = av + f * PPAD;
+            const bool live = fg < re.D_t;
+            xcol[f] = live ? (re.tcols ? __ldg(re.tcols + fg) : fg) : 0;
+            xv[f] = (valid && live) ? __ldg(re.x + row * re.ldx + xcol[f]) : 0.f;
+            const float4* bp = reinterpret_cast<const float4*>(la.bias + (nt * BN + fl * PPAD));
 #pragma unroll
-              for (int i = 0; i < PPAD; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bp + i));
-                p[i + 0] += b.x;
-                p[i + 1] += b.y;
-                p[i + 2] += b.z;
-                p[i + 3] += b.w;
+            for (int i = 0; i < PPAD / 4; ++i) {
+              const float4 b = __ldg(bp + i);
+              av[f * PPAD + 4 * i + 0] = b.x;
+              av[f * PPAD + 4 * i + 1] = b.y;
+              av[f * PPAD + 4 * i + 2] = b.z;
+              av[f * PPAD + 4 * i + 3] = b.w;
+            }
+          }
+        }
+        if (eprof) {
+          const long long t = clock64();
+          e_init += t - e_t;
+          e_t = t;
+        }
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          if (CTAS == 2) {
+            mbar_wait_cluster(tfull_bar(acc), aph);
+          } else {
+            mbar_wait(tfull_bar(acc), aph);
+          }
+          if (eprof) {
+            const long long t = clock64();
+            e_wait += t - e_t;
+            e_t = t;
+          }
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + lane_sel + (uint32_t)(acc * BN + half * NCOL);
+          drain_partial<NCOL, false>(tacc, av);
+          tc_fence_before();  // partial accumulator fully read by this warp: hand it back to the MMA warp
+          __syncwarp();
+          if (lane == 0) {
+            if (CTAS == 2) {
+              mbar_arrive_remote(tempty_bar(acc), 0);
+            } else {
+              mbar_arrive(tempty_bar(acc));
+            }
+          }
+          if (++acc == 2) {
+            acc = 0;
+            aph ^= 1u;
+          }
+          if (eprof) {
+            const long long t = clock64();
+            e_drain += t - e_t;
+            e_t = t;
+          }
+        }
+        if (la.debug & 2) continue;
+        if (EPI == 0) {
+          const int n0 = nt * BN + half * NCOL;
+#pragma unroll
+          for (int j = 0; j < NCOL / 4; ++j) {
+            float4 o = make_float4(av[4 * j + 0], av[4 * j + 1], av[4 * j + 2], av[4 * j + 3]);
+            const int n = n0 + 4 * j;
+            if ((valid || se.tiled) && n < se.n_out) {  // T128 buffers hold whole tiles: tail rows are written too
+              if (se.relu_out) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
               }
-              const int col = re.tcols ? __ldg(re.tcols + fg) : fg;
-              const float xv = valid ? __ldg(re.x + row * re.ldx + col) : 0.f;
+              *reinterpret_cast<float4*>(se.out + o_base + n * n_mul) = o;
+            }
+          }
+        } else {
+          constexpr int FEATS = BN / PPAD;
+          constexpr int FH = FEATS / 2;
+          static_assert(FH * PPAD == NCOL, "feature groups must tile the column half exactly");
+#pragma unroll
+          for (int f = 0; f < FH; ++f) {
+            const int fg = nt * FEATS + half * FH + f;  // feature of the layer
+            if (fg < re.D_t) {
               float yv, lv;
-              rqs_eval<KC, true>(re.c, xv, p, yv, lv, status);
-              if (valid) re.y[row * re.ldy + col] = yv;
+              rqs_eval<KC, true>(re.c, xv[f], av + f * PPAD, yv, lv, status);
+              if (valid) re.y[row * re.ldy + xcol[f]] = yv;
               lad_acc += lv;
             }
           }
@@ -392,14 +609,29 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         parity ^= 1;
       }
     }
+    if (eprof && lane == 0) {
+      g_lin_prof[8] = (unsigned long long)(clock64() - e_begin);
+      g_lin_prof[9] = (unsigned long long)e_init;
+      g_lin_prof[10] = (unsigned long long)e_wait;
+      g_lin_prof[11] = (unsigned long long)e_drain;
+    }
     if (EPI == 1 && status != 0 && re.status) atomicOr(re.status, (int)status);
   }
 
+  __syncwarp();  // the role branches leave most warps diverged; the cluster barrier is warp-aligned
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) {
+    cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its partner can still signal it
+  } else {
+    __syncthreads();
+  }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTAS == 2) {
+      tmem_dealloc_pair(tmem_base, kTmemCols);
+    } else {
+      tmem_dealloc(tmem_base, kTmemCols);
+    }
   }
 }
 
@@ -435,6 +667,21 @@ static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? FC_OK : FC_ERR_CUDA;
 }
 
+// T128 activation buffer [tiles][W/4 column groups][128 rows][4 floats]: one (tile, column group) is 2 KB contiguous,
+// described as 8 rows of 256 B so that the TMA moves wide rows; box = BK/4 column groups of one tile.
+static int make_map_t128(CUtensorMap* m, const float* ptr, uint64_t tiles, uint64_t width, int bk) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return FC_ERR_CUDA;
+  const cuuint64_t dims[4] = {64, 8, width / 4, tiles};
+  const cuuint64_t strides[3] = {256, 2048, (cuuint64_t)kBM * width * sizeof(float)};
+  const cuuint32_t box[4] = {64, 8, (cuuint32_t)(bk / 4), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FC_OK : FC_ERR_CUDA;
+}
+
 // k-values per partial accumulator (see "Accumulation" at the top).  Short dot products leave less room between
 // the tensor core's truncation error and the (smaller) rounding noise of an fp32 FMA chain of the same length, so
 // they are drained after every stage.  FC_LINEAR_CHUNK_K overrides for experiments.
@@ -447,15 +694,28 @@ static int chunk_k(int K) {
   return K <= 64 ? 16 : 32;
 }
 
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD>
+// 1 = independent CTAs, 2 = CTA-pair MMAs (cta_group::2), 3 = weight multicast inside 2-CTA clusters
+static int cluster_mode() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_MODE");
+    return e ? atoi(e) : 1;
+  }();
+  return v >= 1 && v <= 3 ? v : 1;
+}
+
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE>
 static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, LinArgs la,
                          const StoreEpi& se, const RqsEpi& re, cudaStream_t stream) {
-  using SM = LinSmem<BN, BK, STAGES>;
+  constexpr int CTAS = MODE == 2 ? 2 : 1;
+  constexpr int CL = MODE == 1 ? 1 : 2;
+  using SM = LinSmem<BN, BK, STAGES, CTAS>;
+  static_assert(SM::TOTAL <= 232448, "shared memory per CTA");
   if (w->n_pad % BN != 0 || w->k_pad % 32 != 0) return FC_ERR_INVALID_ARGUMENT;
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, BK);
+  int rc = la.a_tiled ? make_map_t128(&tmA, A, (uint64_t)((M + kBM - 1) / kBM), (uint64_t)lda, BK)
+                      : make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, BK);
   if (rc != FC_OK) return rc;
-  rc = make_map(&tmB, w->w, (uint64_t)2 * w->n_pad, (uint64_t)w->k_pad, (uint64_t)w->k_pad, BN, BK);
+  rc = make_map(&tmB, w->w, (uint64_t)2 * w->n_pad, (uint64_t)w->k_pad, (uint64_t)w->k_pad, BN / CL, BK);
   if (rc != FC_OK) return rc;
   la.M = (int)M;
   la.num_k_stages = (K + BK - 1) / BK;
@@ -463,23 +723,43 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   la.num_m_tiles = (int)((M + kBM - 1) / kBM);
   la.n_pad = w->n_pad;
   la.bias = w->bias;
-  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD>;
+  static const int debug = [] {
+    const char* e = getenv("FC_LINEAR_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  la.debug = debug;
+  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess)
       return FC_ERR_CUDA;
     configured = true;
   }
-  const int grid = la.num_m_tiles < device_info().sm_count ? la.num_m_tiles : device_info().sm_count;
-  kern<<<grid, kLinThreads, SM::TOTAL, stream>>>(tmA, tmB, la, se, re);
+  const int units = (la.num_m_tiles + CL - 1) / CL;
+  const int max_units = device_info().sm_count / CL;
+  const int grid = (units < max_units ? units : max_units) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kLinThreads);
+  cfg.dynamicSmemBytes = SM::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, la, se, re) != cudaSuccess) return FC_ERR_CUDA;
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
 
-static int check_operand(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w) {
+static int check_operand(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, int a_tiled) {
   if (!A || !w || !w->w || !w->bias || M < 0 || K <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (M >= (int64_t)1 << 31) return FC_ERR_UNSUPPORTED;
   if (K > w->k_pad) return FC_ERR_INVALID_ARGUMENT;
+  if (a_tiled && (lda != K || (K & 15))) return FC_ERR_INVALID_ARGUMENT;  // T128: width == K, a multiple of 16
   // TMA: 16-byte aligned base and row pitch
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3) || lda < K) return FC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(w->w) & 15) || (reinterpret_cast<uintptr_t>(w->bias) & 15)) return FC_ERR_UNSUPPORTED;
@@ -509,6 +789,12 @@ __global__ void pack_kernel(const float* __restrict__ W, int64_t ldw, const floa
 
 using namespace fc;
 
+extern "C" int fc_linear_debug_profile(unsigned long long* out16) {
+  if (!out16) return FC_ERR_INVALID_ARGUMENT;
+  if (cudaMemcpyFromSymbol(out16, g_lin_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return FC_ERR_CUDA;
+  return FC_OK;
+}
+
 extern "C" int fc_linear_pack(const float* W, int64_t w_row_stride, const float* mask, int64_t mask_row_stride,
                               const float* bias, int32_t N, int32_t K, const int32_t* row_map, const int32_t* col_map,
                               int32_t n_pad, int32_t k_pad, float* w_packed, float* bias_packed, void* stream) {
@@ -527,32 +813,38 @@ extern "C" int fc_linear_pack(const float* W, int64_t w_row_stride, const float*
 
 extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w,
                                int32_t relu_in, float* out, int64_t ldo, int32_t n_out, int32_t relu_out,
-                               const float* residual, int64_t ldr, void* stream) {
-  int rc = check_operand(A, lda, M, K, w);
+                               const float* residual, int64_t ldr, int32_t layouts, void* stream) {
+  const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0, o_tiled = (layouts & FC_LINEAR_OUT_T128) != 0;
+  int rc = check_operand(A, lda, M, K, w, a_tiled);
   if (rc != FC_OK) return rc;
   if (!out || n_out <= 0 || n_out > w->n_pad) return FC_ERR_INVALID_ARGUMENT;
   if ((n_out & 3) || (ldo & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return FC_ERR_UNSUPPORTED;
   if (residual && ((ldr & 3) || (reinterpret_cast<uintptr_t>(residual) & 15))) return FC_ERR_UNSUPPORTED;
+  if (o_tiled && (ldo != n_out || (residual && ldr != n_out))) return FC_ERR_INVALID_ARGUMENT;
   if (M == 0) return FC_OK;
   LinArgs la{};
   la.relu_in = relu_in;
-  StoreEpi se{out, ldo, residual, ldr, n_out, relu_out};
+  la.a_tiled = a_tiled;
+  StoreEpi se{out, ldo, residual, ldr, n_out, relu_out, o_tiled};
   RqsEpi re{};
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
   la.num_n_tiles = (n_out + BN - 1) / BN;
-  return launch_linear<0, BN, 16, 4, 0, 32>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  if (cluster_mode() == 2) return launch_linear<0, BN, 16, 6, 0, 32, 2>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  if (cluster_mode() == 3) return launch_linear<0, BN, 16, 4, 0, 32, 3>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  return launch_linear<0, BN, 16, 4, 0, 32, 1>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
 }
 
 extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
                                    int32_t relu_in, const float* x, int64_t x_row_stride, float* y,
                                    int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int32_t D_t,
                                    fc_cols tcols, fc_cols ccols, const fc_rqs_config* cfg, int32_t* status,
-                                   void* stream) {
+                                   int32_t layouts, void* stream) {
   RqsParams c;
   int rc = make_rqs_params(cfg, c);
   if (rc != FC_OK) return rc;
-  rc = check_operand(hidden, ldh, B, H, w);
+  const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0;
+  rc = check_operand(hidden, ldh, B, H, w, a_tiled);
   if (rc != FC_OK) return rc;
   if (!x || !y || !logabsdet || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
@@ -560,6 +852,7 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
   if (B == 0) return FC_OK;
   LinArgs la{};
   la.relu_in = relu_in;
+  la.a_tiled = a_tiled;
   StoreEpi se{};
   RqsEpi re{x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, tcols.idx, ccols.idx, ccols.n, D_t, c, status};
   constexpr int BN = 192;
@@ -567,13 +860,21 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
     constexpr int PPAD = 24;
     la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
     if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
-    return launch_linear<1, BN, 16, 5, 8, PPAD>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    if (cluster_mode() == 2)
+      return launch_linear<1, BN, 16, 7, 8, PPAD, 2>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    if (cluster_mode() == 3)
+      return launch_linear<1, BN, 16, 5, 8, PPAD, 3>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    return launch_linear<1, BN, 16, 5, 8, PPAD, 1>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   if (c.K == 16) {
     constexpr int PPAD = 48;
     la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
     if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
-    return launch_linear<1, BN, 16, 5, 16, PPAD>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    if (cluster_mode() == 2)
+      return launch_linear<1, BN, 16, 7, 16, PPAD, 2>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    if (cluster_mode() == 3)
+      return launch_linear<1, BN, 16, 5, 16, PPAD, 3>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    return launch_linear<1, BN, 16, 5, 16, PPAD, 1>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   return FC_ERR_UNSUPPORTED;
 }

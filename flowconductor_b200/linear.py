@@ -82,22 +82,67 @@ def grouped_row_map(n_groups, group, group_pad, device):
     return (j * group_pad + i).to(torch.int32)
 
 
-def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None):
-    """out = act_out(act_in(a) @ W.T + b (+ residual)); a [M, K] fp32 (row stride a multiple of 4 floats)."""
-    _cabi.require_cuda_f32(a, "activations")
+class T128:
+    """An activation matrix [rows, width] in the T128 layout of include/flowcon_b200.h (128-row tiles, 16-byte
+    column groups slowest inside a tile).  Only the conditioner's own layers read it."""
+    TILE = 128
+
+    def __init__(self, rows, width, device):
+        if width % 16 != 0:
+            raise ValueError("T128 needs a width that is a multiple of 16")
+        self.rows, self.width = rows, width
+        tiles = (rows + self.TILE - 1) // self.TILE
+        self.buf = torch.empty((tiles * self.TILE * width,), dtype=torch.float32, device=device)
+
+    @staticmethod
+    def from_rows(t):
+        """Row-major [rows, width] tensor -> T128 (test helper; the kernels produce T128 directly)."""
+        rows, width = t.shape
+        out = T128(rows, width, t.device)
+        tiles = out.buf.numel() // (T128.TILE * width)
+        padded = torch.zeros((tiles * T128.TILE, width), dtype=torch.float32, device=t.device)
+        padded[:rows] = t
+        out.buf.copy_(padded.view(tiles, T128.TILE, width // 4, 4).permute(0, 2, 1, 3).reshape(-1))
+        return out
+
+    def to_rows(self):
+        tiles = self.buf.numel() // (self.TILE * self.width)
+        return (self.buf.view(tiles, self.width // 4, self.TILE, 4).permute(0, 2, 1, 3)
+                .reshape(tiles * self.TILE, self.width)[:self.rows].contiguous())
+
+
+def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None, out_t128=False):
+    """out = act_out(act_in(a) @ W.T + b (+ residual)).  a: [M, K] fp32 row-major (row stride a multiple of 4
+    floats) or a T128; the result (and the residual) is a T128 when out_t128 is set, else row-major."""
     L = _cabi.lib()
-    a, ap, lda = _cabi.rows(a)
-    M = a.shape[0]
-    if a.shape[1] != packed.k_in:
-        raise ValueError("activations have {} columns, the packed layer expects {}".format(a.shape[1], packed.k_in))
-    if out is None:
-        out = torch.empty((M, packed.n_out), dtype=torch.float32, device=a.device)
+    layouts = 0
+    if isinstance(a, T128):
+        layouts |= _cabi.LINEAR_A_T128
+        M, k_in, ap, lda, dev = a.rows, a.width, a.buf.data_ptr(), a.width, a.buf.device
+    else:
+        _cabi.require_cuda_f32(a, "activations")
+        a, ap, lda = _cabi.rows(a)
+        M, k_in, dev = a.shape[0], a.shape[1], a.device
+    if k_in != packed.k_in:
+        raise ValueError("activations have {} columns, the packed layer expects {}".format(k_in, packed.k_in))
     rp, ldr = None, 0
-    if residual is not None:
-        residual, rp, ldr = _cabi.rows(_cabi.require_cuda_f32(residual, "residual"))
-    with torch.cuda.device(a.device), _cabi.launch("fc_linear_apply", a.device):
-        rc = L.fc_linear_apply(ap, lda, M, a.shape[1], ctypes.byref(packed.struct), int(relu_in), out.data_ptr(),
-                               out.stride(0), packed.n_out, int(relu_out), rp, ldr, _cabi.stream_ptr(a.device))
+    if out_t128:
+        layouts |= _cabi.LINEAR_OUT_T128
+        if out is None:
+            out = T128(M, packed.n_out, dev)
+        op, ldo = out.buf.data_ptr(), out.width
+        if residual is not None:
+            assert isinstance(residual, T128) and residual.width == packed.n_out and residual.rows == M
+            rp, ldr = residual.buf.data_ptr(), residual.width
+    else:
+        if out is None:
+            out = torch.empty((M, packed.n_out), dtype=torch.float32, device=dev)
+        op, ldo = out.data_ptr(), out.stride(0)
+        if residual is not None:
+            residual, rp, ldr = _cabi.rows(_cabi.require_cuda_f32(residual, "residual"))
+    with torch.cuda.device(dev), _cabi.launch("fc_linear_apply", dev):
+        rc = L.fc_linear_apply(ap, lda, M, k_in, ctypes.byref(packed.struct), int(relu_in), op, ldo, packed.n_out,
+                               int(relu_out), rp, ldr, layouts, _cabi.stream_ptr(dev))
     _cabi.check(rc, "fc_linear_apply")
     return out
 
@@ -105,16 +150,22 @@ def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None):
 def linear_rqs(hidden, packed, x, y, logabsdet, accumulate, d_t, tcols, ccols, cfg, status, relu_in=False):
     """Final conditioner layer + rational-quadratic spline in one kernel (fc_linear_rqs_apply).
     Writes y[:, tcols] (and y[:, ccols] = x[:, ccols] unless y is x) and logabsdet in place."""
-    _cabi.require_cuda_f32(hidden, "hidden activations")
     _cabi.require_cuda_f32(x, "inputs")
     L = _cabi.lib()
-    hidden, hp, ldh = _cabi.rows(hidden)
+    layouts = 0
+    if isinstance(hidden, T128):
+        layouts |= _cabi.LINEAR_A_T128
+        B, H, hp, ldh = hidden.rows, hidden.width, hidden.buf.data_ptr(), hidden.width
+    else:
+        _cabi.require_cuda_f32(hidden, "hidden activations")
+        hidden, hp, ldh = _cabi.rows(hidden)
+        B, H = hidden.shape
     assert x.stride(1) == 1 and y.stride(1) == 1 and logabsdet.is_contiguous()
-    B = hidden.shape[0]
     with torch.cuda.device(x.device), _cabi.launch("fc_linear_rqs_apply", x.device):
-        rc = L.fc_linear_rqs_apply(hp, ldh, B, hidden.shape[1], ctypes.byref(packed.struct), int(relu_in),
+        rc = L.fc_linear_rqs_apply(hp, ldh, B, H, ctypes.byref(packed.struct), int(relu_in),
                                    x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), logabsdet.data_ptr(),
                                    int(accumulate), d_t, _cabi.cols(tcols), _cabi.cols(ccols), ctypes.byref(cfg),
-                                   status.data_ptr() if status is not None else None, _cabi.stream_ptr(x.device))
+                                   status.data_ptr() if status is not None else None, layouts,
+                                   _cabi.stream_ptr(x.device))
     _cabi.check(rc, "fc_linear_rqs_apply")
     return y, logabsdet

@@ -12,6 +12,7 @@ in-place version counter).  Training (autograd) keeps using the torch.nn modules
 `flowconductor_b200.ops`: this path has no backward.
 """
 import math
+import threading
 
 import torch
 from torch import nn
@@ -20,6 +21,46 @@ from torch.nn import functional as F
 from .. import _cabi, linear as fl
 
 ENABLED = True  # set False to force the unfused (torch.nn + element-wise kernel) path everywhere
+
+
+# ---------------------------------------------------------------------------------------------------------
+# In-place layers inside a CompositeTransform: a coupling layer rewrites only its transformed columns, so when its
+# input is an intermediate that nothing but the running cascade references, it can work in place and the identity
+# columns need not be copied (coupling.py:96-98 copies them into a fresh tensor).  Two facts are required, and
+# both are established per layer call:  the CASCADE says "this input is my private intermediate" (begin_layer),
+# and the PREVIOUS layer call says "I allocated that tensor myself" (mark_fresh).  User-visible tensors never
+# satisfy both.
+# ---------------------------------------------------------------------------------------------------------
+class _Ownership(threading.local):
+    consent = None      # data_ptr the cascade allows the next layer to overwrite
+    fresh = None        # data_ptr allocated by the layer call that is running / has just returned
+    prev_fresh = None   # ... by the layer call before it
+
+
+_own = _Ownership()
+
+
+def begin_layer(private_input):
+    """Called by CompositeTransform._cascade before each layer; `private_input` is the previous layer's output
+    (None for the first layer, whose input belongs to the caller)."""
+    _own.consent = private_input.data_ptr() if private_input is not None else None
+    _own.prev_fresh, _own.fresh = _own.fresh, None
+
+
+def end_cascade():
+    _own.consent = _own.fresh = _own.prev_fresh = None
+
+
+def mark_fresh(t):
+    _own.fresh = t.data_ptr()
+
+
+def may_overwrite(t):
+    return (INPLACE and not torch.is_grad_enabled() and _own.consent is not None
+            and t.data_ptr() == _own.consent == _own.prev_fresh)
+
+
+INPLACE = True
 
 
 def _is_relu(act):
@@ -111,12 +152,19 @@ def plan_for(net, col_map, k_in, final_kind, final_group=None):
     return plan
 
 
+T128_ENABLED = True  # keep the activations between the conditioner's layers in the T128 layout (coalesced epilogues)
+
+
 def hidden(plan, a):
-    """Everything up to (not including) the final layer: ResidualNet.hidden / MADE.hidden."""
-    h = fl.linear(a, plan.initial)
+    """Everything up to (not including) the final layer: ResidualNet.hidden / MADE.hidden.  Returns a
+    linear.T128 when every hidden width allows it, else a row-major tensor."""
+    t128 = T128_ENABLED and plan.initial.n_out % 16 == 0 and all(
+        l0.n_out % 16 == 0 and l1.n_out % 16 == 0 for l0, l1 in plan.blocks)
+    h = fl.linear(a, plan.initial, out_t128=t128)
     for l0, l1 in plan.blocks:
-        t = fl.linear(h, l0, relu_in=True, relu_out=True)   # relu(W0 relu(h) + b0): only ever consumed through ReLU
-        h = fl.linear(t, l1, residual=h)                    # h + W1 t + b1
+        # relu(W0 relu(h) + b0): only ever consumed through ReLU
+        t = fl.linear(h, l0, relu_in=True, relu_out=True, out_t128=t128)
+        h = fl.linear(t, l1, residual=h, out_t128=t128)  # h + W1 t + b1
     return h
 
 
@@ -142,7 +190,11 @@ def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling,
                           -tb, tb, -tb, tb, float(spline.min_bin_width), float(spline.min_bin_height),
                           float(spline.min_derivative), wh_scale)
     x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
-    y = torch.empty_like(x)
+    if may_overwrite(inputs) and x is inputs:
+        y = x  # private intermediate of the running cascade: transform its columns in place, no identity copy
+    else:
+        y = torch.empty_like(x)
+    mark_fresh(y)
     lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
     fl.linear_rqs(h, plan.final, x, y, lad, False, d_t, tcols, ccols, cfg, None)
     return y, lad

@@ -29,11 +29,19 @@ class CompositeTransform(Transform):
 
     @staticmethod
     def _cascade(inputs, funcs, context):
+        from ..nn import tensorcore
+
         outputs = inputs
         total_logabsdet = inputs.new_zeros(inputs.shape[0])
-        for func in funcs:
-            outputs, logabsdet = func(outputs, context)
-            total_logabsdet = total_logabsdet + logabsdet
+        try:
+            for i, func in enumerate(funcs):
+                # the previous layer's output is referenced by this loop only: a layer may overwrite it in place
+                # (honoured by the tensor-core inference path when that layer allocated the tensor itself)
+                tensorcore.begin_layer(outputs if i > 0 else None)
+                outputs, logabsdet = func(outputs, context)
+                total_logabsdet = total_logabsdet + logabsdet
+        finally:
+            tensorcore.end_cascade()
         return outputs, total_logabsdet
 
     def forward(self, inputs, context=None):

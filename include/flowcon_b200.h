@@ -158,10 +158,21 @@ int fc_linear_pack(const float* W, int64_t w_row_stride, const float* mask, int6
  * Replaces F.linear in ResidualNet / ResidualBlock / MADE hidden layers (resnet.py:39-56,93-99,
  * made.py:71-72,96-124,152-181): relu_in is the pre-activation of the residual blocks, `residual` their skip
  * connection.  A, out, residual: 16-byte aligned, row strides multiples of 4 floats; n_out a multiple of 4.
+ *
+ * `layouts` (FC_LINEAR_A_T128 | FC_LINEAR_OUT_T128): activations between the conditioner's own layers are kept in the
+ * "T128" layout instead of row-major: 128-row tiles, and inside a tile the 16-byte column groups are the slow index,
+ *     element (r, c) of a [M, W] matrix  ->  float offset  (r/128)*128*W + ((c/4)*128 + r%128)*4 + c%4,
+ * W a multiple of 16, buffer size ceil(M/128)*128*W floats (tail rows of the last tile are written, never read
+ * back as results).  One epilogue thread owns one row, so with T128 the 32 threads of a warp store (and re-read as
+ * the skip connection) 512 contiguous bytes per instruction instead of 32 scattered 16-byte pieces, and the next
+ * layer's TMA box of BK k-values is BK/4 contiguous 2 KB runs.  For a T128 operand its stride argument (lda / ldo /
+ * ldr) is W.  The residual always has the layout of `out`.
  */
+#define FC_LINEAR_A_T128 1
+#define FC_LINEAR_OUT_T128 2
 int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w, int32_t relu_in,
                     float* out, int64_t ldo, int32_t n_out, int32_t relu_out, const float* residual, int64_t ldr,
-                    void* stream);
+                    int32_t layouts, void* stream);
 
 /*
  * Final conditioner layer with the rational-quadratic spline in the GEMM epilogue (SURVEY a15 + a1-a6):
@@ -170,12 +181,20 @@ int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_
  *   logabsdet[r] = (accumulate ? logabsdet[r] : 0) + sum_j log|dy/dx|
  * i.e. final_layer (resnet.py:99 / made.py:266-272) + fc_rqs_apply in one kernel.  `w` must have been packed with
  * row_map[j*P + i] = j*P_pad + i.  Supported: linear tails, num_bins 8 or 16 (else FC_ERR_UNSUPPORTED: run
- * fc_linear_apply + fc_rqs_apply).  y may alias x.
+ * fc_linear_apply + fc_rqs_apply).  y may alias x.  layouts: FC_LINEAR_A_T128 if `hidden` is a T128 buffer (ldh = H).
  */
 int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
                         int32_t relu_in, const float* x, int64_t x_row_stride, float* y, int64_t y_row_stride,
                         float* logabsdet, int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
-                        const fc_rqs_config* cfg, int32_t* status, void* stream);
+                        const fc_rqs_config* cfg, int32_t* status, int32_t layouts, void* stream);
+
+/*
+ * Debugging aid: with FC_LINEAR_DEBUG=4 in the environment the last fc_linear_* launch records, for CTA 0, the cycles
+ * its MMA-issuing thread spent waiting on each barrier ([0] total, [1] accumulator free, [2] TMA landed, [3] operand
+ * converted, [4] partner CTA ready, [5] stages) and one epilogue warp's split ([8] total, [9] tile set-up, [10] waiting
+ * for a partial accumulator, [11] draining it).  Synchronises the device.  Not part of the data path.
+ */
+int fc_linear_debug_profile(unsigned long long* out16);
 
 /* Library / build info (also used by the loader test). */
 const char* fc_version(void);

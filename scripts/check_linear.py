@@ -22,13 +22,17 @@ def rel_err(got, want64):
     return (got.double() - want64).abs().max().item() / scale
 
 
-def check_store(M, K, N, relu_in, relu_out, use_res, gen, dev):
+def check_store(M, K, N, relu_in, relu_out, use_res, gen, dev, a_t128=False, o_t128=False):
     a = torch.randn(M, K, generator=gen, device=dev)
     w = torch.randn(N, K, generator=gen, device=dev) / math.sqrt(K)
     b = torch.randn(N, generator=gen, device=dev)
     res = torch.randn(M, N, generator=gen, device=dev) if use_res else None
     pk = fl.pack(w, b)
-    out = fl.linear(a, pk, relu_in=relu_in, relu_out=relu_out, residual=res)
+    a_in = fl.T128.from_rows(a) if a_t128 else a
+    res_in = fl.T128.from_rows(res) if (o_t128 and use_res) else res
+    out = fl.linear(a_in, pk, relu_in=relu_in, relu_out=relu_out, residual=res_in, out_t128=o_t128)
+    if o_t128:
+        out = out.to_rows()
     torch.cuda.synchronize()
     a64 = a.double().relu() if relu_in else a.double()
     want = a64 @ w.double().t() + b.double()
@@ -44,8 +48,8 @@ def check_store(M, K, N, relu_in, relu_out, use_res, gen, dev):
         ref32 = ref32.relu()
     e, e32 = rel_err(out, want), rel_err(ref32, want)
     ok = e < 5e-6
-    print("store M={} K={} N={} relu_in={} relu_out={} res={}: ours {:.2e}  cublas-fp32 {:.2e}  {}".format(
-        M, K, N, relu_in, relu_out, use_res, e, e32, "OK" if ok else "FAIL"))
+    print("store M={} K={} N={} relu_in={} relu_out={} res={} t128(a,out)={}{}: ours {:.2e}  cublas-fp32 {:.2e}  {}".format(
+        M, K, N, relu_in, relu_out, use_res, int(a_t128), int(o_t128), e, e32, "OK" if ok else "FAIL"))
     return ok
 
 
@@ -96,7 +100,7 @@ def rqs_cfg(K, H, inverse=False, identity_init=False):
                            1e-3, 1.0 / math.sqrt(H))
 
 
-def check_rqs(M, D, K, H, gen, dev, inverse=False, coupling=True):
+def check_rqs(M, D, K, H, gen, dev, inverse=False, coupling=True, h_t128=False):
     P = 3 * K - 1
     ppad = fl.RQS_PPAD[K]
     if coupling:
@@ -114,7 +118,7 @@ def check_rqs(M, D, K, H, gen, dev, inverse=False, coupling=True):
     y = torch.empty_like(x)
     lad = torch.empty(M, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    fl.linear_rqs(hid, pk, x, y, lad, False, d_t, tcols, ccols, cfg, status)
+    fl.linear_rqs(fl.T128.from_rows(hid) if h_t128 else hid, pk, x, y, lad, False, d_t, tcols, ccols, cfg, status)
     torch.cuda.synchronize()
     # reference: fp64 GEMM -> fp32 params -> standalone spline kernel
     params = (hid.double() @ w.double().t() + b.double()).float()
@@ -152,6 +156,9 @@ def bench(dev, gen):
 
     t = timeit(lambda: fl.linear(a, pk, relu_in=True, out=out))
     flops = 2.0 * M * H * H
+    at, ot, rt = fl.T128.from_rows(a), fl.T128(M, H, dev), fl.T128.from_rows(out)
+    tt = timeit(lambda: fl.linear(at, pk, relu_in=True, residual=rt, out=ot, out_t128=True))
+    print("hidden linear T128 in/out + residual: {:.3f} ms  {:.1f} TFLOP/s fp32-equivalent".format(tt, flops / tt / 1e9))
     print("hidden linear 1M x 256 x 256: {:.3f} ms  {:.1f} TFLOP/s fp32-equivalent ({:.1f} tf32 tensor TFLOP/s)".format(
         t, flops / t / 1e9, 3 * flops / t / 1e9))
     t2 = timeit(lambda: torch.nn.functional.linear(a, w, b))
@@ -170,6 +177,8 @@ def bench(dev, gen):
     lad = torch.zeros(M, device=dev)
     t3 = timeit(lambda: fl.linear_rqs(a, pkf, x, y, lad, False, d_t, tcols, ccols, cfg, None))
     flops_f = 2.0 * M * H * 768
+    t3t = timeit(lambda: fl.linear_rqs(at, pkf, x, y, lad, False, d_t, tcols, ccols, cfg, None))
+    print("final layer + spline, T128 hidden: {:.3f} ms".format(t3t))
     print("final layer + spline 1M x 256 x 768: {:.3f} ms  {:.1f} TFLOP/s fp32-equivalent".format(t3, flops_f / t3 / 1e9))
 
     def unfused():
@@ -194,7 +203,12 @@ def main():
     ok &= check_store(1000, 256, 256, True, True, True, gen, dev)
     ok &= check_store(40000, 256, 512, True, False, True, gen, dev)
     ok &= check_store(5000, 8, 64, False, True, False, gen, dev)
+    ok &= check_store(1000, 256, 256, False, False, False, gen, dev, a_t128=True)
+    ok &= check_store(1000, 64, 256, False, False, False, gen, dev, o_t128=True)
+    ok &= check_store(1000, 256, 256, True, True, True, gen, dev, a_t128=True, o_t128=True)
+    ok &= check_store(70000, 32, 64, True, False, True, gen, dev, a_t128=True, o_t128=True)
     ok &= check_colmap(gen, dev)
+    ok &= check_rqs(1000, 64, 8, 256, gen, dev, h_t128=True)
     ok &= check_rqs(1000, 64, 8, 256, gen, dev)
     ok &= check_rqs(30000, 64, 8, 256, gen, dev, inverse=True)
     ok &= check_rqs(5000, 16, 16, 256, gen, dev, coupling=False)

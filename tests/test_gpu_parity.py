@@ -405,6 +405,30 @@ def test_full_size_layer_round_trip(dev, d, k):
     assert torch.isfinite(lad).all()
 
 
+def test_tensorcore_path_variants_agree(dev, monkeypatch):
+    """The tensor-core inference path with its optimisations switched off one at a time (in-place intermediates,
+    T128 activation layout) gives bitwise-identical results, and never touches the caller's input."""
+    from flowconductor_b200.nn import tensorcore
+
+    wl = workloads.get_workload("cfg2")
+    flow = workloads.build_flow(wl)
+    state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl)
+    flow.load_state_dict(state)
+    flow = flow.to(dev)
+    x = torch.randn(3000, 64, generator=torch.Generator(device=dev).manual_seed(5), device=dev)
+    x0 = x.clone()
+    outs = []
+    with torch.no_grad():
+        for inplace, t128 in ((True, True), (False, True), (True, False)):
+            monkeypatch.setattr(tensorcore, "INPLACE", inplace)
+            monkeypatch.setattr(tensorcore, "T128_ENABLED", t128)
+            z, lad = flow._transform(x)
+            outs.append((z.clone(), lad.clone()))
+            assert torch.equal(x, x0)
+    for z, lad in outs[1:]:
+        assert torch.equal(z, outs[0][0]) and torch.equal(lad, outs[0][1])
+
+
 def test_full_size_cfg3_training_step_is_finite(dev):
     wl = workloads.get_workload("cfg3")
     flow = workloads.build_flow(wl).to(dev)

@@ -132,3 +132,33 @@ def test_coupling_constructor_contract():
 
 def test_package_metadata():
     assert fcb.__version__
+
+
+def test_inplace_ownership_protocol():
+    """nn/tensorcore.py: a layer may overwrite its input only if the cascade declared it private AND the previous
+    layer call allocated it; user tensors and stale pointers never qualify."""
+    import torch
+    from flowconductor_b200.nn import tensorcore as tcm
+
+    user = torch.zeros(4, 4)
+    with torch.no_grad():
+        tcm.end_cascade()
+        tcm.begin_layer(None)                      # first layer: input belongs to the caller
+        assert not tcm.may_overwrite(user)
+        y0 = torch.empty(4, 4)
+        tcm.mark_fresh(y0)                         # layer 0 allocated its output
+        tcm.begin_layer(y0)                        # cascade: y0 is my private intermediate
+        assert tcm.may_overwrite(y0)
+        assert not tcm.may_overwrite(user)
+        view = user                                # layer 1 returns the user's tensor itself (identity-like layer)
+        tcm.begin_layer(view)
+        assert not tcm.may_overwrite(view)         # nobody marked it fresh in the call that produced it
+        tcm.mark_fresh(y0)
+        tcm.end_cascade()
+        tcm.begin_layer(y0)                        # stale pointer from a finished cascade
+        assert not tcm.may_overwrite(y0)
+        tcm.end_cascade()
+    tcm.mark_fresh(y0)
+    tcm.begin_layer(y0)
+    assert not tcm.may_overwrite(y0)               # autograd enabled: never in place
+    tcm.end_cascade()
