@@ -40,12 +40,18 @@ namespace fc {
 
 using namespace tc;
 
-constexpr int kLinThreads = 512;
+constexpr int kBaseThreads = 256;  // warps 0-7: producer, MMA issuer, allocator, spare, 4 converters
 constexpr int kBM = 128;
 constexpr int kConvWarp0 = 4;
 constexpr int kEpiWarp0 = 8;
 constexpr int kNumConv = 128;  // converter threads (warps 4-7)
-constexpr int kRegsProducer = 40, kRegsConverter = 56, kRegsEpilogue = 208;  // 128*(40+56) + 256*208 == 65536
+// setmaxnreg budgets per warpgroup, EW epilogue warps (the register file holds 65536):
+//   EW = 8 : 512 threads launch with 128;  128*40 + 128*56 + 256*208 = 65536
+//   EW = 16: 768 threads launch with  80;  128*32 + 128*32 + 512*104 = 61440 (= 768 * 80, the CTA's pool)
+template <int EW>
+struct RegBudget {
+  static constexpr int kProducer = EW == 8 ? 40 : 32, kConverter = EW == 8 ? 56 : 32, kEpilogue = EW == 8 ? 208 : 104;
+};
 
 struct LinArgs {
   int M;
@@ -90,7 +96,7 @@ struct LinSmem {
   static constexpr int B_BYTES = (BN / CTAS) * BK * 4;  // a CTA pair splits the rows of every weight box
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 8 * (4 * STAGES + 4) + 16;
-  static constexpr int LAD_BYTES = 2 * kBM * 4;
+  static constexpr int LAD_BYTES = 2 * 3 * kBM * 4;  // per-row partial log-dets of up to 3 other column groups, x2
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + LAD_BYTES + 1024;  // + alignment slack
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
 };
@@ -111,10 +117,10 @@ __device__ __forceinline__ void set_max_regs_dec() {
 // the additions of group j run while the load of group j+1 is in flight.
 template <int N, bool kFirst>
 __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
-  static_assert(N % 32 == 0, "column count per thread must be a multiple of 32");
+  static_assert(N % 16 == 0, "column count per thread must be a multiple of 16");
   if (kFirst) {
 #pragma unroll
-    for (int j = 0; j < N; j += 32) tmem_ld32(taddr + (uint32_t)j, reinterpret_cast<uint32_t*>(acc + j));
+    for (int j = 0; j < N; j += 16) tmem_ld16(taddr + (uint32_t)j, reinterpret_cast<uint32_t*>(acc + j));
     tmem_wait_ld();
     return;
   }
@@ -142,8 +148,8 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
 //   product: each CTA stages its own 128 rows of A but only HALF of every weight box, so the weight traffic (L2 ->
 //   shared memory AND shared memory -> tensor core) per SM is halved and the ring is 1.5x deeper.  Rank 0 (the leader)
 //   issues the MMAs; rank 1's warp 1 relays "my stage is loaded and converted" to the leader.
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE>
-__global__ void __launch_bounds__(kLinThreads, 1)
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW>
+__global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const LinArgs la, const StoreEpi se, const RqsEpi re) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;  // CTAs per MMA
@@ -178,13 +184,13 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), kNumConv);
+      mbar_init(conv_bar(s), 4 * CTAS);  // one arrival per converter warp (of both CTAs of a pair, in the leader)
       mbar_init(empty_bar(s), MC ? 2 : 1);
       mbar_init(ready_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8 * CTAS);
+      mbar_init(tempty_bar(a), EW * CTAS);
     }
     fence_mbar_init();
   }
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   const int n_chunks = (nk + chunk - 1) / chunk;
 
   if (warp < kConvWarp0) {
-    set_max_regs_dec<kRegsProducer>();
+    set_max_regs_dec<RegBudget<EW>::kProducer>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
@@ -309,14 +315,18 @@ __global__ void __launch_bounds__(kLinThreads, 1)
               const uint32_t d = tmem_base + (uint32_t)(acc * BN);
               for (int kc = k0; kc < k1; ++kc) {
                 if (prof) t0 = clock64();
-                // the converters arrive only after THEIR wait on full_bar, so conv_bar also covers the TMA boxes
-                mbar_wait(conv_bar(s), ph);
+                // the converters (of both CTAs of a pair) arrive only after THEIR wait on full_bar, so conv_bar also
+                // covers the TMA boxes
+                if (CTAS == 2) {
+                  mbar_wait_cluster(conv_bar(s), ph);
+                } else {
+                  mbar_wait(conv_bar(s), ph);
+                }
                 if (prof) {
                   const long long t1 = clock64();
                   t_conv += t1 - t0;
                   t0 = t1;
                 }
-                if (CTAS == 2) mbar_wait_cluster(ready_bar(s), ph);
                 if (prof) {
                   t_ready += clock64() - t0;
                   ++t_stages;
@@ -377,26 +387,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           g_lin_prof[4] = (unsigned long long)t_ready;
           g_lin_prof[5] = (unsigned long long)t_stages;
         }
-      } else if (CTAS == 2 && lane == 0) {
-        // peer CTA: tell the leader when this CTA's half of a stage has landed and been converted
-        int s = 0;
-        uint32_t ph = 0;
-        for (int mp = unit0; mp < n_units; mp += unit_step) {
-          for (int it = 0; it < n_tiles * nk; ++it) {
-            mbar_wait(full_bar(s), ph);
-            mbar_wait(conv_bar(s), ph);
-            mbar_arrive_remote(ready_bar(s), 0);
-            if (++s == STAGES) {
-              s = 0;
-              ph ^= 1u;
-            }
-          }
-        }
       }
     }
   } else if (warp < kEpiWarp0) {
     // ------------------------------------------------------------------ converters: raw fp32 -> (hi, lo) tf32
-    set_max_regs_dec<kRegsConverter>();
+    set_max_regs_dec<RegBudget<EW>::kConverter>();
     const int ct = threadIdx.x - kConvWarp0 * 32;
     int s = 0;
     uint32_t ph = 0;
@@ -427,7 +422,14 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         } else {
           fence_proxy_async_smem();
         }
-        mbar_arrive(conv_bar(s));
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 2) {
+            mbar_arrive_remote(conv_bar(s), 0);  // release.cluster: publishes this warp's part of the stage
+          } else {
+            mbar_arrive(conv_bar(s));
+          }
+        }
         if (++s == STAGES) {
           s = 0;
           ph ^= 1u;
@@ -436,10 +438,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    set_max_regs_inc<kRegsEpilogue>();
-    constexpr int NCOL = BN / 2;             // accumulator columns (and registers) per thread
+    set_max_regs_inc<RegBudget<EW>::kEpilogue>();
+    constexpr int NG = EW / 4;               // column groups: 4 warps (one per TMEM lane quarter) each
+    constexpr int NCOL = BN / NG;            // accumulator columns (and registers) per thread
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - kEpiWarp0) >> 2;  // which half of the tile's columns / features
+    const int half = (warp - kEpiWarp0) >> 2;  // which column group of the tile (columns / features)
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     int acc = 0;
     uint32_t aph = 0;
@@ -461,8 +464,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         // between the last partial accumulator and the stores.
         const int rt = q * 32 + lane;
         int64_t o_base = 0, r_base = 0, n_mul = 1;
-        float xv[EPI == 1 ? (BN / PPAD) / 2 : 1];
-        int xcol[EPI == 1 ? (BN / PPAD) / 2 : 1];
+        float xv[EPI == 1 ? (BN / PPAD) / NG : 1];
+        int xcol[EPI == 1 ? (BN / PPAD) / NG : 1];
         if (EPI == 0) {
           // T128: element (r, n) of tile mt at mt*128*W + ((n/4)*128 + r)*4: a warp's 32 rows of one column group
           // are 512 contiguous bytes (coalesced); row-major: 32 rows x 16 B scattered over 32 lines
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           }
         } else {
           constexpr int FEATS = BN / PPAD;
-          constexpr int FH = FEATS / 2;
+          constexpr int FH = FEATS / NG;
           if (nt == 0 && half == 0 && re.n_copy > 0 && re.y != re.x) {
             // identity columns (coupling.py:96-98): the warp copies its 32 rows one row per step (coalesced)
             const int64_t row0 = (int64_t)mt * kBM + q * 32;
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           __syncwarp();
           if (lane == 0) {
             if (CTAS == 2) {
-              mbar_arrive_remote(tempty_bar(acc), 0);
+              mbar_arrive_remote_relaxed(tempty_bar(acc), 0);  // ordered by the tcgen05 fence above
             } else {
               mbar_arrive(tempty_bar(acc));
             }
@@ -582,8 +585,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           }
         } else {
           constexpr int FEATS = BN / PPAD;
-          constexpr int FH = FEATS / 2;
-          static_assert(FH * PPAD == NCOL, "feature groups must tile the column half exactly");
+          constexpr int FH = FEATS / NG;
+          static_assert(FH * PPAD == NCOL && FH >= 1, "feature groups must tile the column group exactly");
 #pragma unroll
           for (int f = 0; f < FH; ++f) {
             const int fg = nt * FEATS + half * FH + f;  // feature of the layer
@@ -599,11 +602,13 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       if (EPI == 1) {
         // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): this thread summed its features in
         // order; the two column halves of a row are combined in a fixed order through shared memory
-        float* ex = lad_x + parity * kBM;
-        if (half == 1) ex[q * 32 + lane] = lad_acc;
-        named_barrier_sync(1, 256);
+        float* ex = lad_x + parity * 3 * kBM;
+        if (half > 0) ex[(half - 1) * kBM + q * 32 + lane] = lad_acc;
+        named_barrier_sync(1, 32 * EW);
         if (half == 0 && valid) {
-          const float tot = lad_acc + ex[q * 32 + lane];
+          float tot = lad_acc;
+#pragma unroll
+          for (int g = 1; g < NG; ++g) tot += ex[(g - 1) * kBM + q * 32 + lane];
           re.lad[row] = re.accumulate ? re.lad[row] + tot : tot;
         }
         parity ^= 1;
@@ -694,6 +699,15 @@ static int chunk_k(int K) {
   return K <= 64 ? 16 : 32;
 }
 
+// epilogue warps: 8 (two column groups, 208 registers each) or 16 (four column groups, 104 registers each)
+static int epilogue_warps() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_EW");
+    return e ? atoi(e) : 8;  // measured on cfg 2: 16 warps drain faster but take issue slots from the MMA warp; no gain
+  }();
+  return v == 16 ? 16 : 8;
+}
+
 // 1 = independent CTAs, 2 = CTA-pair MMAs (cta_group::2), 3 = weight multicast inside 2-CTA clusters
 static int cluster_mode() {
   static int v = [] {
@@ -703,7 +717,7 @@ static int cluster_mode() {
   return v >= 1 && v <= 3 ? v : 1;
 }
 
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE>
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW>
 static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, LinArgs la,
                          const StoreEpi& se, const RqsEpi& re, cudaStream_t stream) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;
@@ -728,7 +742,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
     return e ? atoi(e) : 0;
   }();
   la.debug = debug;
-  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE>;
+  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE, EW>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess)
@@ -740,7 +754,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   const int grid = (units < max_units ? units : max_units) * CL;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kLinThreads);
+  cfg.blockDim = dim3(kBaseThreads + 32 * EW);
   cfg.dynamicSmemBytes = SM::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -830,9 +844,12 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
   la.num_n_tiles = (n_out + BN - 1) / BN;
-  if (cluster_mode() == 2) return launch_linear<0, BN, 16, 6, 0, 32, 2>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
-  if (cluster_mode() == 3) return launch_linear<0, BN, 16, 4, 0, 32, 3>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
-  return launch_linear<0, BN, 16, 4, 0, 32, 1>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  if (cluster_mode() == 2) return epilogue_warps() == 8 ? launch_linear<0, BN, 16, 6, 0, 32, 2, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<0, BN, 16, 6, 0, 32, 2, 16>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  if (cluster_mode() == 3) return epilogue_warps() == 8 ? launch_linear<0, BN, 16, 4, 0, 32, 3, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<0, BN, 16, 4, 0, 32, 3, 16>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  return epilogue_warps() == 8 ? launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<0, BN, 16, 4, 0, 32, 1, 16>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
 }
 
 extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
@@ -861,20 +878,26 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
     la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
     if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
     if (cluster_mode() == 2)
-      return launch_linear<1, BN, 16, 7, 8, PPAD, 2>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 7, 8, PPAD, 2, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<1, BN, 16, 7, 8, PPAD, 2, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
     if (cluster_mode() == 3)
-      return launch_linear<1, BN, 16, 5, 8, PPAD, 3>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    return launch_linear<1, BN, 16, 5, 8, PPAD, 1>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 8, PPAD, 3, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<1, BN, 16, 5, 8, PPAD, 3, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 8, PPAD, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<1, BN, 16, 5, 8, PPAD, 1, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   if (c.K == 16) {
     constexpr int PPAD = 48;
     la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
     if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
     if (cluster_mode() == 2)
-      return launch_linear<1, BN, 16, 7, 16, PPAD, 2>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 7, 16, PPAD, 2, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<1, BN, 16, 7, 16, PPAD, 2, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
     if (cluster_mode() == 3)
-      return launch_linear<1, BN, 16, 5, 16, PPAD, 3>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    return launch_linear<1, BN, 16, 5, 16, PPAD, 1>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 16, PPAD, 3, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<1, BN, 16, 5, 16, PPAD, 3, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+    return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 16, PPAD, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
+                                  : launch_linear<1, BN, 16, 5, 16, PPAD, 1, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   return FC_ERR_UNSUPPORTED;
 }

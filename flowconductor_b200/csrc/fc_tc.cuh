@@ -72,6 +72,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta_ra
       "r"(cta_rank)
       : "memory");
 }
+// same without memory ordering: for hand-offs whose data moves through tensor memory / the async proxy and is
+// ordered by tcgen05 fences (a cluster-scope release is a full fence and costs ~1k cycles)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta_rank)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
