@@ -88,6 +88,7 @@ struct RqsEpi {
   int D_t;
   RqsParams c;
   int32_t* status;
+  int activation;  // EPI 2 (affine): FC_SCALE_*; c.inverse carries the direction
 };
 
 template <int BN, int BK, int STAGES, int CTAS>
@@ -137,7 +138,8 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
   }
 }
 
-// EPI: 0 = store (bias, optional residual / ReLU), 1 = rational-quadratic spline with KC bins.
+// EPI: 0 = store (bias, optional residual / ReLU), 1 = rational-quadratic spline with KC bins,
+//      2 = affine (PPAD = 2 accumulator columns per feature: raw scale, shift).
 // RQS tile geometry: FEATS features of PPAD accumulator columns each (BN = FEATS * PPAD).
 // MODE 1: one CTA per SM, independent.
 // MODE 3: clusters of two CTAs work on two row tiles in lock step and SHARE the weight stream: each CTA fetches half
@@ -464,8 +466,8 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
         // between the last partial accumulator and the stores.
         const int rt = q * 32 + lane;
         int64_t o_base = 0, r_base = 0, n_mul = 1;
-        float xv[EPI == 1 ? (BN / PPAD) / NG : 1];
-        int xcol[EPI == 1 ? (BN / PPAD) / NG : 1];
+        float xv[EPI != 0 ? (BN / PPAD) / NG : 1];
+        int xcol[EPI != 0 ? (BN / PPAD) / NG : 1];
         if (EPI == 0) {
           // T128: element (r, n) of tile mt at mt*128*W + ((n/4)*128 + r)*4: a warp's 32 rows of one column group
           // are 512 contiguous bytes (coalesced); row-major: 32 rows x 16 B scattered over 32 lines
@@ -517,14 +519,20 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
             const bool live = fg < re.D_t;
             xcol[f] = live ? (re.tcols ? __ldg(re.tcols + fg) : fg) : 0;
             xv[f] = (valid && live) ? __ldg(re.x + row * re.ldx + xcol[f]) : 0.f;
-            const float4* bp = reinterpret_cast<const float4*>(la.bias + (nt * BN + fl * PPAD));
+            if constexpr (PPAD % 4 == 0) {
+              const float4* bp = reinterpret_cast<const float4*>(la.bias + (nt * BN + fl * PPAD));
 #pragma unroll
-            for (int i = 0; i < PPAD / 4; ++i) {
-              const float4 b = __ldg(bp + i);
-              av[f * PPAD + 4 * i + 0] = b.x;
-              av[f * PPAD + 4 * i + 1] = b.y;
-              av[f * PPAD + 4 * i + 2] = b.z;
-              av[f * PPAD + 4 * i + 3] = b.w;
+              for (int i = 0; i < PPAD / 4; ++i) {
+                const float4 b = __ldg(bp + i);
+                av[f * PPAD + 4 * i + 0] = b.x;
+                av[f * PPAD + 4 * i + 1] = b.y;
+                av[f * PPAD + 4 * i + 2] = b.z;
+                av[f * PPAD + 4 * i + 3] = b.w;
+              }
+            } else {
+              const float2 b = __ldg(reinterpret_cast<const float2*>(la.bias + (nt * BN + fl * PPAD)));
+              av[f * PPAD + 0] = b.x;
+              av[f * PPAD + 1] = b.y;
             }
           }
         }
@@ -592,14 +600,18 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
             const int fg = nt * FEATS + half * FH + f;  // feature of the layer
             if (fg < re.D_t) {
               float yv, lv;
-              rqs_eval<KC, true>(re.c, xv[f], av + f * PPAD, yv, lv, status);
+              if constexpr (EPI == 2) {
+                affine_eval(xv[f], av[f * PPAD], av[f * PPAD + 1], re.activation, re.c.inverse, yv, lv);
+              } else {
+                rqs_eval<KC, true>(re.c, xv[f], av + f * PPAD, yv, lv, status);
+              }
               if (valid) re.y[row * re.ldy + xcol[f]] = yv;
               lad_acc += lv;
             }
           }
         }
       }
-      if (EPI == 1) {
+      if (EPI != 0) {
         // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): this thread summed its features in
         // order; the two column halves of a row are combined in a fixed order through shared memory
         float* ex = lad_x + parity * 3 * kBM;
@@ -620,7 +632,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
       g_lin_prof[10] = (unsigned long long)e_wait;
       g_lin_prof[11] = (unsigned long long)e_drain;
     }
-    if (EPI == 1 && status != 0 && re.status) atomicOr(re.status, (int)status);
+    if (EPI != 0 && status != 0 && re.status) atomicOr(re.status, (int)status);
   }
 
   __syncwarp();  // the role branches leave most warps diverged; the cluster barrier is warp-aligned
@@ -900,4 +912,29 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
                                   : launch_linear<1, BN, 16, 5, 16, PPAD, 1, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   }
   return FC_ERR_UNSUPPORTED;
+}
+
+extern "C" int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
+                                      int32_t relu_in, const float* x, int64_t x_row_stride, float* y,
+                                      int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int32_t D_t,
+                                      fc_cols tcols, fc_cols ccols, int32_t activation, int32_t inverse,
+                                      int32_t layouts, void* stream) {
+  const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0;
+  int rc = check_operand(hidden, ldh, B, H, w, a_tiled);
+  if (rc != FC_OK) return rc;
+  if (!x || !y || !logabsdet || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
+  if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
+  if (activation < FC_SCALE_SIGMOID2 || activation > FC_SCALE_SOFTPLUS_EPS) return FC_ERR_INVALID_ARGUMENT;
+  if (B == 0) return FC_OK;
+  LinArgs la{};
+  la.relu_in = relu_in;
+  la.a_tiled = a_tiled;
+  StoreEpi se{};
+  RqsEpi re{x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, tcols.idx, ccols.idx, ccols.n, D_t, {}, nullptr,
+            activation};
+  re.c.inverse = inverse;
+  constexpr int BN = 64;  // 32 features per tile: the affine final layer is narrow (2 columns per feature)
+  la.num_n_tiles = (2 * D_t + BN - 1) / BN;
+  if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
+  return launch_linear<2, BN, 16, 8, 0, 2, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
 }

@@ -12,6 +12,7 @@ from . import _cabi
 
 N_TILE_STORE = 256  # fc_linear_apply
 N_TILE_RQS = 192    # fc_linear_rqs_apply
+N_TILE_AFFINE = 64  # fc_linear_affine_apply
 RQS_PPAD = {8: 24, 16: 48}  # accumulator columns per feature for the supported bin counts (P = 3K-1 -> P_pad)
 
 
@@ -111,7 +112,7 @@ class T128:
                 .reshape(tiles * self.TILE, self.width)[:self.rows].contiguous())
 
 
-def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None, out_t128=False):
+def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None, out_t128=False, n_out=None):
     """out = act_out(act_in(a) @ W.T + b (+ residual)).  a: [M, K] fp32 row-major (row stride a multiple of 4
     floats) or a T128; the result (and the residual) is a T128 when out_t128 is set, else row-major."""
     L = _cabi.lib()
@@ -125,23 +126,24 @@ def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None, ou
         M, k_in, dev = a.shape[0], a.shape[1], a.device
     if k_in != packed.k_in:
         raise ValueError("activations have {} columns, the packed layer expects {}".format(k_in, packed.k_in))
+    n_out = packed.n_out if n_out is None else n_out  # may include zero-weight padding columns (<= n_pad)
     rp, ldr = None, 0
     if out_t128:
         layouts |= _cabi.LINEAR_OUT_T128
         if out is None:
-            out = T128(M, packed.n_out, dev)
+            out = T128(M, n_out, dev)
         op, ldo = out.buf.data_ptr(), out.width
         if residual is not None:
-            assert isinstance(residual, T128) and residual.width == packed.n_out and residual.rows == M
+            assert isinstance(residual, T128) and residual.width == n_out and residual.rows == M
             rp, ldr = residual.buf.data_ptr(), residual.width
     else:
         if out is None:
-            out = torch.empty((M, packed.n_out), dtype=torch.float32, device=dev)
+            out = torch.empty((M, n_out), dtype=torch.float32, device=dev)
         op, ldo = out.data_ptr(), out.stride(0)
         if residual is not None:
             residual, rp, ldr = _cabi.rows(_cabi.require_cuda_f32(residual, "residual"))
     with torch.cuda.device(dev), _cabi.launch("fc_linear_apply", dev):
-        rc = L.fc_linear_apply(ap, lda, M, k_in, ctypes.byref(packed.struct), int(relu_in), op, ldo, packed.n_out,
+        rc = L.fc_linear_apply(ap, lda, M, k_in, ctypes.byref(packed.struct), int(relu_in), op, ldo, n_out,
                                int(relu_out), rp, ldr, layouts, _cabi.stream_ptr(dev))
     _cabi.check(rc, "fc_linear_apply")
     return out
@@ -168,4 +170,34 @@ def linear_rqs(hidden, packed, x, y, logabsdet, accumulate, d_t, tcols, ccols, c
                                    status.data_ptr() if status is not None else None, layouts,
                                    _cabi.stream_ptr(x.device))
     _cabi.check(rc, "fc_linear_rqs_apply")
+    return y, logabsdet
+
+
+def affine_row_map(d_t, layout, device):
+    """Packed row of each final-layer output so that feature j's (raw scale, shift) sit in rows (2j, 2j+1)."""
+    j = torch.arange(d_t, device=device)
+    if layout == _cabi.AFFINE_BLOCKED:      # [shift_0..shift_{D-1} | raw_0..raw_{D-1}]  (coupling.py:234-238)
+        return torch.cat((2 * j + 1, 2 * j)).to(torch.int32)
+    return torch.arange(2 * d_t, device=device, dtype=torch.int32)  # already (raw, shift) pairs (autoregressive.py:124-129)
+
+
+def linear_affine(hidden, packed, x, y, logabsdet, accumulate, d_t, tcols, ccols, activation, inverse, relu_in=False):
+    """Final conditioner layer + affine transform in one kernel (fc_linear_affine_apply)."""
+    _cabi.require_cuda_f32(x, "inputs")
+    L = _cabi.lib()
+    layouts = 0
+    if isinstance(hidden, T128):
+        layouts |= _cabi.LINEAR_A_T128
+        B, H, hp, ldh = hidden.rows, hidden.width, hidden.buf.data_ptr(), hidden.width
+    else:
+        _cabi.require_cuda_f32(hidden, "hidden activations")
+        hidden, hp, ldh = _cabi.rows(hidden)
+        B, H = hidden.shape
+    assert x.stride(1) == 1 and y.stride(1) == 1 and logabsdet.is_contiguous()
+    with torch.cuda.device(x.device), _cabi.launch("fc_linear_affine_apply", x.device):
+        rc = L.fc_linear_affine_apply(hp, ldh, B, H, ctypes.byref(packed.struct), int(relu_in), x.data_ptr(),
+                                      x.stride(0), y.data_ptr(), y.stride(0), logabsdet.data_ptr(), int(accumulate),
+                                      d_t, _cabi.cols(tcols), _cabi.cols(ccols), int(activation), int(bool(inverse)),
+                                      layouts, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_linear_affine_apply")
     return y, logabsdet

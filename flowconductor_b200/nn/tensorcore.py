@@ -109,9 +109,7 @@ def usable(net, a, context, *other_inputs):
     if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0):
         return False
     # TMA operand constraints: 16-byte aligned base and row pitch
-    if a.stride(1) != 1 or a.stride(0) % 4 != 0 or a.data_ptr() % 16 != 0:
-        return False
-    return net.final_layer.weight.shape[0] % 4 == 0
+    return a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
 
 
 def _param_key(net):
@@ -140,7 +138,11 @@ def plan_for(net, col_map, k_in, final_kind, final_group=None):
     plan.blocks = [(_pack_layer(b.linear_layers[0]), _pack_layer(b.linear_layers[1])) for b in net.blocks]
     plan.final_kind = final_kind
     fin = net.final_layer
-    if final_kind[0] == "rqs":
+    if final_kind[0] == "affine":
+        d_t = fin.weight.shape[0] // 2
+        rm = fl.affine_row_map(d_t, final_kind[1], fin.weight.device)
+        plan.final = _pack_layer(fin, row_map=rm, n_tile=fl.N_TILE_AFFINE)
+    elif final_kind[0] == "rqs":
         K = final_kind[1]
         P = 3 * K - 1
         d_t = fin.weight.shape[0] // P
@@ -171,7 +173,31 @@ def hidden(plan, a):
 def params(net, a, col_map=None, k_in=None):
     """Full conditioner output [B, out_features] (final layer materialised)."""
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("store",))
-    return fl.linear(hidden(plan, a), plan.final)
+    n = plan.final.n_out
+    n4 = (n + 3) // 4 * 4  # the store epilogue writes 16-byte vectors: round up into the zero-weight padding
+    out = fl.linear(hidden(plan, a), plan.final, n_out=n4)
+    return out if n4 == n else out[:, :n]
+
+
+def _output_buffer(inputs, allow_inplace=True):
+    """(x, y) for a fused final layer: in place when the running cascade owns `inputs`, else a fresh tensor.
+    allow_inplace=False for callers that need `inputs` again (the D passes of an autoregressive inverse)."""
+    x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
+    y = x if (allow_inplace and may_overwrite(inputs) and x is inputs) else torch.empty_like(x)
+    mark_fresh(y)
+    return x, y
+
+
+def affine_layer(net, a, inputs, tcols, ccols, layout, activation, inverse, col_map=None, k_in=None,
+                 allow_inplace=True):
+    """Conditioner + affine transform for one layer (final layer fused: fc_linear_affine_apply)."""
+    d_t = tcols.numel() if tcols is not None else inputs.shape[1]
+    plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("affine", layout))
+    h = hidden(plan, a)
+    x, y = _output_buffer(inputs, allow_inplace)
+    lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
+    fl.linear_affine(h, plan.final, x, y, lad, False, d_t, tcols, ccols, activation, inverse)
+    return y, lad
 
 
 def rqs_fusable(spline, final_out_features, d_t):
@@ -179,7 +205,8 @@ def rqs_fusable(spline, final_out_features, d_t):
             and final_out_features == d_t * (3 * spline.num_bins - 1))
 
 
-def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None):
+def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None,
+              allow_inplace=True):
     """Conditioner + spline for one layer; returns (outputs, logabsdet)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("rqs", spline.num_bins))
@@ -189,12 +216,7 @@ def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling,
     cfg = _cabi.RqsConfig(int(spline.num_bins), _cabi.TAILS_LINEAR, int(bool(spline.identity_init)), int(bool(inverse)),
                           -tb, tb, -tb, tb, float(spline.min_bin_width), float(spline.min_bin_height),
                           float(spline.min_derivative), wh_scale)
-    x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
-    if may_overwrite(inputs) and x is inputs:
-        y = x  # private intermediate of the running cascade: transform its columns in place, no identity copy
-    else:
-        y = torch.empty_like(x)
-    mark_fresh(y)
+    x, y = _output_buffer(inputs, allow_inplace)
     lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
     fl.linear_rqs(h, plan.final, x, y, lad, False, d_t, tcols, ccols, cfg, None)
     return y, lad

@@ -87,6 +87,11 @@ class MaskedAffineAutoregressiveTransform(AutoregressiveTransform):
         return ops.affine_layer(inputs, autoregressive_params, None, None, _cabi.AFFINE_INTERLEAVED,
                                 _cabi.SCALE_SOFTPLUS_EPS, True)
 
+    def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
+        return tensorcore.affine_layer(self.autoregressive_net, conditioner_inputs, inputs, None, None,
+                                       _cabi.AFFINE_INTERLEAVED, _cabi.SCALE_SOFTPLUS_EPS, inverse,
+                                       allow_inplace=not inverse)  # the inverse re-reads `inputs` D times
+
 
 class MaskedSumOfSigmoidsTransform(AutoregressiveTransform):
     """Autoregressive sum-of-sigmoids layer; forward output is shifted by -0.5 (autoregressive.py:309,313)."""
@@ -148,4 +153,5 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
         if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1]):
             return super()._tensorcore_layer(conditioner_inputs, inputs, inverse)
         return tensorcore.rqs_layer(net, conditioner_inputs, inputs, self._spline, None, None, inverse,
-                                    getattr(net, "hidden_features", None))
+                                    getattr(net, "hidden_features", None),
+                                    allow_inplace=not inverse)  # the inverse re-reads `inputs` D times

@@ -115,6 +115,14 @@ class AffineCouplingTransform(CouplingTransform):
         return ops.affine_layer(inputs, transform_params, self._tcols, self._ccols, _cabi.AFFINE_BLOCKED,
                                 self._activation_code, bool(inverse))
 
+    def _tensorcore_layer(self, inputs, inverse):
+        if self._transform_dim_multiplier() != 2:
+            return super()._tensorcore_layer(inputs, inverse)
+        # final layer + scale-and-shift in one kernel
+        return tensorcore.affine_layer(self.transform_net, inputs, inputs, self._tcols, self._ccols,
+                                       _cabi.AFFINE_BLOCKED, self._activation_code, inverse, col_map=self._ccols,
+                                       k_in=self.features)
+
 
 class AdditiveCouplingTransform(AffineCouplingTransform):
     """Shift-only coupling (NICE, coupling.py:255-269): zero log-det, no kernel needed beyond an indexed add."""

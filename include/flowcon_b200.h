@@ -189,6 +189,17 @@ int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, 
                         const fc_rqs_config* cfg, int32_t* status, int32_t layouts, void* stream);
 
 /*
+ * Final conditioner layer with the AFFINE transform in the GEMM epilogue (SURVEY a15 + a7 / a9): final_layer +
+ * fc_affine_apply in one kernel.  `w` must have been packed so that packed row 2j is feature j's raw scale and row
+ * 2j+1 its shift (row_map: blocked coupling layout [shift | raw_scale] -> shift_j at 2j+1, raw_scale_j at 2j; the
+ * autoregressive layout is already interleaved), n_pad a multiple of 64.  activation: FC_SCALE_*.
+ */
+int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
+                           int32_t relu_in, const float* x, int64_t x_row_stride, float* y, int64_t y_row_stride,
+                           float* logabsdet, int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                           int32_t activation, int32_t inverse, int32_t layouts, void* stream);
+
+/*
  * Debugging aid: with FC_LINEAR_DEBUG=4 in the environment the last fc_linear_* launch records, for CTA 0, the cycles
  * its MMA-issuing thread spent waiting on each barrier ([0] total, [1] accumulator free, [2] TMA landed, [3] operand
  * converted, [4] partner CTA ready, [5] stages) and one epilogue warp's split ([8] total, [9] tile set-up, [10] waiting

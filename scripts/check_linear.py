@@ -120,17 +120,50 @@ def check_rqs(M, D, K, H, gen, dev, inverse=False, coupling=True, h_t128=False):
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     fl.linear_rqs(fl.T128.from_rows(hid) if h_t128 else hid, pk, x, y, lad, False, d_t, tcols, ccols, cfg, status)
     torch.cuda.synchronize()
-    # reference: fp64 GEMM -> fp32 params -> standalone spline kernel
+    # reference: fp64 GEMM -> fp32 params -> standalone spline kernel; yardstick: the same with the fp32 cuBLAS GEMM
+    # (what the unfused path does).  The spline amplifies parameter noise (1/slope in the inverse), so the fused path
+    # is judged against the yardstick's own error, quantile by quantile.
+    args = (K, _cabi.TAILS_LINEAR, inverse, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0 / math.sqrt(H))
     params = (hid.double() @ w.double().t() + b.double()).float()
-    y2, lad2, _ = ops.rqs_layer(x, params, tcols, ccols, K, _cabi.TAILS_LINEAR, inverse, False, -3.0, 3.0, -3.0, 3.0,
-                                1e-3, 1e-3, 1e-3, 1.0 / math.sqrt(H))
+    y2, lad2, _ = ops.rqs_layer(x, params, tcols, ccols, *args)
+    y3, lad3, _ = ops.rqs_layer(x, torch.nn.functional.linear(hid, w, b), tcols, ccols, *args)
+    q = torch.tensor([0.5, 0.99, 0.999, 1.0], device=dev)
+
+    def quant(t):
+        return torch.quantile(t.flatten()[: 1 << 22].float(), q)
+
+    ey, ey3 = quant((y - y2).abs()), quant((y3 - y2).abs())
+    el, el3 = quant((lad - lad2).abs()), quant((lad3 - lad2).abs())
+    ok = bool((ey <= 3 * ey3 + 2e-6).all()) and bool((el <= 3 * el3 + 2e-5).all())
+    print("rqs-fused M={} D={} K={} H={} inv={} coupling={}: |dy| q50/99/99.9/max {} (cuBLAS path {})  |dlad| {} ({}) {}"
+          .format(M, D, K, H, inverse, coupling, ["%.1e" % v for v in ey.tolist()], ["%.1e" % v for v in ey3.tolist()],
+                  ["%.1e" % v for v in el.tolist()], ["%.1e" % v for v in el3.tolist()], "OK" if ok else "FAIL"))
+    return ok
+
+
+def check_affine(M, D, H, gen, dev, layout, activation, inverse, h_t128):
+    if layout == _cabi.AFFINE_BLOCKED:
+        tcols = torch.arange(0, D, 2, device=dev, dtype=torch.int32)
+        ccols = torch.arange(1, D, 2, device=dev, dtype=torch.int32)
+        d_t = tcols.numel()
+    else:
+        tcols, ccols, d_t = None, None, D
+    x = torch.randn(M, D, generator=gen, device=dev)
+    hid = torch.randn(M, H, generator=gen, device=dev)
+    w = torch.randn(2 * d_t, H, generator=gen, device=dev) / math.sqrt(H)
+    b = torch.randn(2 * d_t, generator=gen, device=dev) * 0.5
+    pk = fl.pack(w, b, row_map=fl.affine_row_map(d_t, layout, dev), n_tile=fl.N_TILE_AFFINE)
+    y = torch.empty_like(x)
+    lad = torch.empty(M, device=dev)
+    fl.linear_affine(fl.T128.from_rows(hid) if h_t128 else hid, pk, x, y, lad, False, d_t, tcols, ccols, activation,
+                     inverse)
+    params = (hid.double() @ w.double().t() + b.double()).float()
+    y2, lad2 = ops.affine_layer(x, params, tcols, ccols, layout, activation, inverse)
     ey = (y - y2).abs().max().item()
-    el = ((lad - lad2).abs() / lad2.abs().clamp_min(1.0)).max().item()
-    frac_bad = ((y - y2).abs() > 1e-4).float().mean().item()
-    frac_bad_l = (((lad - lad2).abs() / lad2.abs().clamp_min(1.0)) > 1e-3).float().mean().item()
-    ok = frac_bad < 1e-4 and frac_bad_l < 1e-4
-    print("rqs-fused M={} D={} K={} H={} inv={} coupling={}: max|dy| {:.2e} (frac>1e-4: {:.1e})  max rel dlad {:.2e} {}"
-          .format(M, D, K, H, inverse, coupling, ey, frac_bad, el, "OK" if ok else "FAIL"))
+    el = (lad - lad2).abs().max().item()
+    ok = ey < 2e-5 * max(1.0, y2.abs().max().item()) and el < 2e-4
+    print("affine-fused M={} D={} H={} layout={} act={} inv={} t128={}: max|dy| {:.2e} max|dlad| {:.2e} {}".format(
+        M, D, H, layout, activation, inverse, int(h_t128), ey, el, "OK" if ok else "FAIL"))
     return ok
 
 
@@ -213,6 +246,10 @@ def main():
     ok &= check_rqs(30000, 64, 8, 256, gen, dev, inverse=True)
     ok &= check_rqs(5000, 16, 16, 256, gen, dev, coupling=False)
     ok &= check_rqs(3000, 20, 8, 64, gen, dev, coupling=True)
+    ok &= check_affine(1000, 64, 256, gen, dev, _cabi.AFFINE_BLOCKED, _cabi.SCALE_SIGMOID2, False, True)
+    ok &= check_affine(5000, 10, 16, gen, dev, _cabi.AFFINE_BLOCKED, _cabi.SCALE_SOFTPLUS_CLAMP3, True, False)
+    ok &= check_affine(3000, 100, 64, gen, dev, _cabi.AFFINE_INTERLEAVED, _cabi.SCALE_SOFTPLUS_EPS, False, True)
+    ok &= check_affine(300, 2, 32, gen, dev, _cabi.AFFINE_INTERLEAVED, _cabi.SCALE_SOFTPLUS_EPS, True, False)
     print("checks {} in {:.1f}s".format("PASSED" if ok else "FAILED", time.time() - t0))
     error_profile(gen, dev)
     if args.bench:
