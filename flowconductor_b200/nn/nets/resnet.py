@@ -1,13 +1,16 @@
 """Residual MLP conditioner with the parameter names of flowcon/nn/nets/resnet.py (`initial_layer`,
 `blocks.N.linear_layers.{0,1}`, `blocks.N.context_layer`, `final_layer`), so reference state_dicts load.
 
-The hidden layers stay torch (cuBLAS fp32); the final layer is the GEMM the fused-epilogue kernel replaces.
+Inference runs the whole net on the tensor cores (nn/tensorcore.py, final layer fused with the bijection); with
+autograd every dense layer goes through nn/tc_autograd.py (forward and input-gradient GEMMs on the tensor cores).
 `hidden_features` is public on purpose: couplings use it for the 1/sqrt(H) width/height pre-scale
 (coupling.py:554-556).
 """
 import torch
 from torch import nn
 from torch.nn import functional as F
+
+from .. import tc_autograd
 
 
 class ResidualBlock(nn.Module):
@@ -34,7 +37,7 @@ class ResidualBlock(nn.Module):
             h = self.activation(h)
             if i == 1:
                 h = self.dropout(h)
-            h = self.linear_layers[i](h)
+            h = tc_autograd.module_linear(self.linear_layers[i], h)
         if context is not None:
             h = F.glu(torch.cat((h, self.context_layer(context)), dim=1), dim=1)
         return inputs + h
@@ -55,10 +58,11 @@ class ResidualNet(nn.Module):
 
     def hidden(self, inputs, context=None):
         """Everything up to (not including) `final_layer`."""
-        h = self.initial_layer(inputs if context is None else torch.cat((inputs, context), dim=1))
+        h = tc_autograd.module_linear(self.initial_layer,
+                                      inputs if context is None else torch.cat((inputs, context), dim=1))
         for block in self.blocks:
             h = block(h, context=context)
         return h
 
     def forward(self, inputs, context=None):
-        return self.final_layer(self.hidden(inputs, context))
+        return tc_autograd.module_linear(self.final_layer, self.hidden(inputs, context))

@@ -19,6 +19,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .. import _cabi, linear as fl
+from . import tc_autograd
 
 ENABLED = True  # set False to force the unfused (torch.nn + element-wise kernel) path everywhere
 
@@ -97,9 +98,10 @@ def supported_net(net, context):
             return False
         if blk.dropout.p > 0 and blk.training:
             return False
-    if net.initial_layer.weight.shape[0] % 4 != 0:
-        return False
-    return True
+    hidden_width = net.initial_layer.weight.shape[0]
+    # narrow nets stay on the torch path: below a reduction length of 64 the 3xTF32 error floor is above the fp32
+    # FMA chain's rounding noise (nn/tc_autograd.py MIN_K) and there is no time to gain
+    return hidden_width % 4 == 0 and hidden_width >= tc_autograd.MIN_K
 
 
 def usable(net, a, context, *other_inputs):
@@ -117,7 +119,7 @@ def _param_key(net):
 
 
 class _Plan:
-    __slots__ = ("key", "initial", "blocks", "final", "final_kind")
+    __slots__ = ("key", "initial", "blocks", "final", "final_kind", "col_map")
 
 
 def _pack_layer(layer, **kw):
@@ -134,7 +136,9 @@ def plan_for(net, col_map, k_in, final_kind, final_group=None):
         return plan
     plan = _Plan()
     plan.key = key
-    plan.initial = _pack_layer(net.initial_layer, col_map=col_map, k_in=k_in)
+    # a short first reduction (e.g. an 8-wide context) runs as a torch fp32 GEMM, see MIN_K
+    plan.initial = _pack_layer(net.initial_layer, col_map=col_map, k_in=k_in) if k_in >= tc_autograd.MIN_K else None
+    plan.col_map = col_map
     plan.blocks = [(_pack_layer(b.linear_layers[0]), _pack_layer(b.linear_layers[1])) for b in net.blocks]
     plan.final_kind = final_kind
     fin = net.final_layer
@@ -157,12 +161,19 @@ def plan_for(net, col_map, k_in, final_kind, final_group=None):
 T128_ENABLED = True  # keep the activations between the conditioner's layers in the T128 layout (coalesced epilogues)
 
 
-def hidden(plan, a):
+def hidden(net, plan, a):
     """Everything up to (not including) the final layer: ResidualNet.hidden / MADE.hidden.  Returns a
     linear.T128 when every hidden width allows it, else a row-major tensor."""
-    t128 = T128_ENABLED and plan.initial.n_out % 16 == 0 and all(
+    t128 = T128_ENABLED and net.initial_layer.weight.shape[0] % 16 == 0 and all(
         l0.n_out % 16 == 0 and l1.n_out % 16 == 0 for l0, l1 in plan.blocks)
-    h = fl.linear(a, plan.initial, out_t128=t128)
+    if plan.initial is not None:
+        h = fl.linear(a, plan.initial, out_t128=t128)
+    else:
+        lin = net.initial_layer
+        cols = a if plan.col_map is None else a[:, plan.col_map.long()]
+        h = F.linear(cols, lin.weight if getattr(lin, "mask", None) is None else lin.weight * lin.mask, lin.bias)
+        if t128:
+            h = fl.T128.from_rows(h)
     for l0, l1 in plan.blocks:
         # relu(W0 relu(h) + b0): only ever consumed through ReLU
         t = fl.linear(h, l0, relu_in=True, relu_out=True, out_t128=t128)
@@ -175,7 +186,7 @@ def params(net, a, col_map=None, k_in=None):
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("store",))
     n = plan.final.n_out
     n4 = (n + 3) // 4 * 4  # the store epilogue writes 16-byte vectors: round up into the zero-weight padding
-    out = fl.linear(hidden(plan, a), plan.final, n_out=n4)
+    out = fl.linear(hidden(net, plan, a), plan.final, n_out=n4)
     return out if n4 == n else out[:, :n]
 
 
@@ -193,7 +204,7 @@ def affine_layer(net, a, inputs, tcols, ccols, layout, activation, inverse, col_
     """Conditioner + affine transform for one layer (final layer fused: fc_linear_affine_apply)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("affine", layout))
-    h = hidden(plan, a)
+    h = hidden(net, plan, a)
     x, y = _output_buffer(inputs, allow_inplace)
     lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
     fl.linear_affine(h, plan.final, x, y, lad, False, d_t, tcols, ccols, activation, inverse)
@@ -210,7 +221,7 @@ def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling,
     """Conditioner + spline for one layer; returns (outputs, logabsdet)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("rqs", spline.num_bins))
-    h = hidden(plan, a)
+    h = hidden(net, plan, a)
     tb = float(spline.tail_bound)
     wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
     cfg = _cabi.RqsConfig(int(spline.num_bins), _cabi.TAILS_LINEAR, int(bool(spline.identity_init)), int(bool(inverse)),

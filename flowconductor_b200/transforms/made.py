@@ -6,6 +6,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from ..nn import tc_autograd
 from ..utils import torchutils
 
 
@@ -42,7 +43,7 @@ class MaskedLinear(nn.Linear):
         return self.weight * self.mask
 
     def forward(self, x):
-        return F.linear(x, self.masked_weight(), self.bias)
+        return tc_autograd.linear(x, self.weight, self.bias, self.mask)
 
 
 class MaskedFeedforwardBlock(nn.Module):

@@ -240,6 +240,9 @@ def main():
     ok &= check_store(1000, 64, 256, False, False, False, gen, dev, o_t128=True)
     ok &= check_store(1000, 256, 256, True, True, True, gen, dev, a_t128=True, o_t128=True)
     ok &= check_store(70000, 32, 64, True, False, True, gen, dev, a_t128=True, o_t128=True)
+    ok &= check_store(128, 752, 32, False, False, False, gen, dev)       # input-gradient shapes (K = layer width)
+    ok &= check_store(5000, 736, 256, False, False, False, gen, dev)
+    ok &= check_store(128, 48, 16, False, False, False, gen, dev)
     ok &= check_colmap(gen, dev)
     ok &= check_rqs(1000, 64, 8, 256, gen, dev, h_t128=True)
     ok &= check_rqs(1000, 64, 8, 256, gen, dev)

@@ -438,9 +438,9 @@ def test_stacked_autoregressive_layers_tensorcore_vs_unfused(dev, monkeypatch):
 
     torch.manual_seed(11)
     flows = {
-        "affine": T.CompositeTransform([T.MaskedAffineAutoregressiveTransform(6, 16) for _ in range(3)]),
+        "affine": T.CompositeTransform([T.MaskedAffineAutoregressiveTransform(6, 64) for _ in range(3)]),
         "prq": T.CompositeTransform([T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(
-            6, 16, num_bins=8, tails="linear", tail_bound=3.0) for _ in range(3)]),
+            6, 64, num_bins=8, tails="linear", tail_bound=3.0) for _ in range(3)]),
     }
     x = torch.randn(777, 6, generator=torch.Generator().manual_seed(3)).to(dev)
     for name, tr in flows.items():
