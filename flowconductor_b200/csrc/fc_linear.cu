@@ -8,11 +8,11 @@
 //
 // Precision: the reference computes these GEMMs in fp32 (no TF32).  One tf32 UMMA per product would lose 13
 // mantissa bits, so every operand is split  a = a_hi + a_lo  (both tf32-representable, |a - a_hi - a_lo| <=
-// 2^-22 |a|) and the product is accumulated as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  in the fp32 TMEM accumulator
+// 2^-24 |a|) and the product is accumulated as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  in the fp32 TMEM accumulator
 // ("3xTF32": error ~2^-21 per product, the same size as the summation-order noise of an fp32 GEMM with K = 256).
 //   * weights: split once by fc_linear_pack into a [hi | lo] pair of K-major planes (also folds the MADE mask,
 //     the per-feature padding P -> P_pad and the coupling column scatter into the layout);
-//   * activations: TMA lands the raw fp32 tile in shared memory, two converter warps rewrite it in place as a_hi
+//   * activations: TMA lands the raw fp32 tile in shared memory, four converter warps rewrite it in place as a_hi
 //     (optionally after ReLU — the residual blocks are pre-activation, resnet.py:41-47) and write a_lo next to it.
 //
 // Accumulation: the tensor core truncates (rounds toward zero) every time an MMA result is added to the fp32
@@ -31,8 +31,9 @@
 //   warps 4-7   converters     : raw A tile -> (a_hi, a_lo)
 //   warps 8-15  epilogue       : tcgen05.ld each partial accumulator (double-buffered in TMEM, so draining chunk i
 //                                overlaps the MMAs of chunk i+1) into registers, then + bias and either
-//                                ReLU/residual/store or the rational-quadratic spline of 8 (K=8) / 4 (K=16)
-//                                features per 192-column tile.
+//                                ReLU/residual/store, the rational-quadratic spline of 8 (K=8) / 4 (K=16)
+//                                features per 192-column tile, or the affine transform of 32 features per 64 columns.
+// DESIGN.md 4.6 has the measurements behind each of these choices.
 #include "fc_common.cuh"
 #include "fc_tc.cuh"
 
