@@ -50,6 +50,9 @@ WORKLOADS = {
     # reduced-size twins (same classes / masks / tails) used for committed golden vectors
     "cfg2_small": {"features": 64, "context_features": None, "batch": 128,
                    "layers": _prq_coupling_stack(64, 2, 8, 32)},
+    # wide enough (H >= 64) for the tensor-core conditioner path; used by smoke() and the host tests
+    "cfg2_tc_small": {"features": 64, "context_features": None, "batch": 512,
+                      "layers": _prq_coupling_stack(64, 3, 8, 64)},
     "cfg3_small": {"features": 16, "context_features": None, "batch": 128,
                    "layers": _maf_prq_stack(16, 2, 16, 32)},
     "cfg4_small": {"features": 8, "context_features": 8, "batch": 128,

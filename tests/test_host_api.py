@@ -162,3 +162,53 @@ def test_inplace_ownership_protocol():
     tcm.begin_layer(y0)
     assert not tcm.may_overwrite(y0)               # autograd enabled: never in place
     tcm.end_cascade()
+
+
+def test_t128_layout_round_trip_and_row_maps():
+    """Host side of the tensor-core path (linear.py): the T128 activation layout of include/flowcon_b200.h and the
+    packed-row maps of the fused final layers, checked on CPU tensors."""
+    import torch
+    from flowconductor_b200 import _cabi, linear as fl
+
+    t = torch.arange(300 * 32, dtype=torch.float32).reshape(300, 32)
+    tiled = fl.T128.from_rows(t)
+    assert tiled.buf.numel() == 3 * 128 * 32
+    assert torch.equal(tiled.to_rows(), t)
+    # element (r, c) -> (r // 128) * 128 * W + ((c // 4) * 128 + r % 128) * 4 + c % 4
+    for r, c in ((0, 0), (5, 7), (129, 31), (299, 16)):
+        off = (r // 128) * 128 * 32 + ((c // 4) * 128 + r % 128) * 4 + c % 4
+        assert tiled.buf[off].item() == t[r, c].item()
+    try:
+        fl.T128(10, 20, torch.device("cpu"))
+        raise AssertionError("width 20 must be rejected")
+    except ValueError:
+        pass
+    rm = fl.grouped_row_map(3, 23, 24, torch.device("cpu"))
+    assert rm.tolist()[:3] == [0, 1, 2] and rm.tolist()[23] == 24 and rm.tolist()[-1] == 2 * 24 + 22
+    blocked = fl.affine_row_map(3, _cabi.AFFINE_BLOCKED, torch.device("cpu")).tolist()
+    assert blocked == [1, 3, 5, 0, 2, 4]          # [shift_0..2 | raw_0..2] -> (raw_j, shift_j) pairs
+    assert fl.affine_row_map(3, _cabi.AFFINE_INTERLEAVED, torch.device("cpu")).tolist() == [0, 1, 2, 3, 4, 5]
+
+
+def test_tensorcore_path_selection():
+    """nn/tensorcore.py + nn/tc_autograd.py: which conditioners / layers are allowed on the tensor cores."""
+    import torch
+    from flowconductor_b200 import transforms as T
+    from flowconductor_b200.nn import tc_autograd, tensorcore
+    from flowconductor_b200.nn.nets import ResidualNet
+
+    assert tensorcore.supported_net(ResidualNet(32, 100, 64), None)
+    assert not tensorcore.supported_net(ResidualNet(32, 100, 32), None)            # narrower than MIN_K
+    assert not tensorcore.supported_net(ResidualNet(32, 100, 64, context_features=4), None)
+    assert not tensorcore.supported_net(ResidualNet(32, 100, 64, use_batch_norm=True), None)
+    assert not tensorcore.supported_net(ResidualNet(32, 100, 64), torch.zeros(1, 4))  # context passed at call time
+    made = T.MaskedAffineAutoregressiveTransform(6, 64).autoregressive_net
+    assert tensorcore.supported_net(made, None)
+    x = torch.zeros(8, 64)
+    assert not tensorcore.usable(ResidualNet(64, 100, 64), x, None)                # CPU tensors never
+    w = torch.zeros(128, 128)
+    assert not tc_autograd._eligible(x, w)                                          # CPU tensors never
+    # CPU tensors take F.linear (torch), results identical to the reference formula
+    lin = torch.nn.Linear(16, 8)
+    xi = torch.randn(4, 16)
+    assert torch.equal(tc_autograd.module_linear(lin, xi), torch.nn.functional.linear(xi, lin.weight, lin.bias))
