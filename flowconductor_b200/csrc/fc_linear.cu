@@ -92,11 +92,12 @@ struct RqsEpi {
   int activation;  // EPI 2 (affine): FC_SCALE_*; c.inverse carries the direction
 };
 
-template <int BN, int BK, int STAGES, int CTAS>
+template <int BN, int BK, int STAGES, int CTAS, bool TS = false>
 struct LinSmem {
   static constexpr int A_BYTES = kBM * BK * 4;
   static constexpr int B_BYTES = (BN / CTAS) * BK * 4;  // a CTA pair splits the rows of every weight box
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int A_PLANES = TS ? 1 : 2;            // TS: the converted operand lives in tensor memory
+  static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 8 * (4 * STAGES + 4) + 16;
   static constexpr int LAD_BYTES = 2 * 3 * kBM * 4;  // per-row partial log-dets of up to 3 other column groups, x2
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + LAD_BYTES + 1024;  // + alignment slack
@@ -151,14 +152,21 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
 //   product: each CTA stages its own 128 rows of A but only HALF of every weight box, so the weight traffic (L2 ->
 //   shared memory AND shared memory -> tensor core) per SM is halved and the ring is 1.5x deeper.  Rank 0 (the leader)
 //   issues the MMAs; rank 1's warp 1 relays "my stage is loaded and converted" to the leader.
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW>
+// TS: the converters write the (hi, lo) split of the activation tile into TENSOR MEMORY (tcgen05.st; ring of STAGES
+//   slots of 2*BK columns behind the two partial accumulators) and the MMAs take their A operand from there.  Per 8
+//   k-values the shared memory then serves 3 weight-tile reads + the TMA writes + one raw-tile read instead of 3 x
+//   (A + B) reads + TMA writes + raw read + two converted writes: 132 instead of 201 B/cycle at BN = 192 (the
+//   SMEM port delivers 128), and no generic->async proxy hand-off is needed.
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS>
 __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const LinArgs la, const StoreEpi se, const RqsEpi re) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;  // CTAs per MMA
   constexpr bool MC = MODE == 3;           // weight boxes multicast inside the cluster
   constexpr int CL = MODE == 1 ? 1 : 2;    // cluster size = row tiles per work unit
-  using SM = LinSmem<BN, BK, STAGES, CTAS>;
+  using SM = LinSmem<BN, BK, STAGES, CTAS, TS>;
+  static_assert(!TS || (MODE == 1 && 2 * BN + STAGES * 2 * BK <= 512), "TS: operand ring must fit behind the accumulators");
+  constexpr uint32_t kTmemA0 = 2 * BN;  // first column of the operand ring (TS)
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 1023u) & ~1023u;
@@ -265,12 +273,12 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
               }
               if (MC) {
                 const uint32_t half_off = (uint32_t)rank * (SM::B_BYTES / 2);
-                tma_load_2d_multicast(st + 2 * SM::A_BYTES + half_off, &tmB, kc * BK, brow, full_bar(s), 3);
-                tma_load_2d_multicast(st + 2 * SM::A_BYTES + SM::B_BYTES + half_off, &tmB, kc * BK, la.n_pad + brow,
+                tma_load_2d_multicast(st + SM::A_PLANES * SM::A_BYTES + half_off, &tmB, kc * BK, brow, full_bar(s), 3);
+                tma_load_2d_multicast(st + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES + half_off, &tmB, kc * BK, la.n_pad + brow,
                                       full_bar(s), 3);
               } else {
-                tma_load_2d(st + 2 * SM::A_BYTES, &tmB, kc * BK, brow, full_bar(s));
-                tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + brow, full_bar(s));
+                tma_load_2d(st + SM::A_PLANES * SM::A_BYTES, &tmB, kc * BK, brow, full_bar(s));
+                tma_load_2d(st + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + brow, full_bar(s));
               }
               if (++s == STAGES) {
                 s = 0;
@@ -299,8 +307,8 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
         const uint64_t a_hi0 = tiled ? make_smem_desc_noswizzle(base, kBM * 16, 128) : make_smem_desc(base, BK * 4);
         const uint64_t a_lo0 = tiled ? make_smem_desc_noswizzle(base + SM::A_BYTES, kBM * 16, 128)
                                      : make_smem_desc(base + SM::A_BYTES, BK * 4);
-        const uint64_t b_hi0 = make_smem_desc(base + 2 * SM::A_BYTES, BK * 4);
-        const uint64_t b_lo0 = make_smem_desc(base + 2 * SM::A_BYTES + SM::B_BYTES, BK * 4);
+        const uint64_t b_hi0 = make_smem_desc(base + SM::A_PLANES * SM::A_BYTES, BK * 4);
+        const uint64_t b_lo0 = make_smem_desc(base + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES, BK * 4);
         // 8 k-values further along K: T128 operands (no swizzle) jump two column groups, swizzled ones 32 bytes
         const uint64_t a_step = tiled ? (uint64_t)((2 * kBM * 16) >> 4) : 2ull;
         for (int mp = unit0; mp < n_units; mp += unit_step) {
@@ -344,7 +352,13 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
                     const uint64_t oa = a_step * (uint64_t)kk;
                     const uint32_t first = (kc > k0 || kk > 0) ? 1u : 0u;
                     // small terms first, so they are not absorbed by the large one before they have been summed
-                    if (CTAS == 2) {
+                    if (TS) {
+                      const uint32_t ta_hi = tmem_base + kTmemA0 + (uint32_t)(s * 2 * BK + kk * 8);
+                      const uint32_t ta_lo = ta_hi + (uint32_t)BK;
+                      umma_tf32_ts(d, ta_lo, b_hi + o, idesc, first);
+                      umma_tf32_ts(d, ta_hi, b_lo + o, idesc, 1u);
+                      umma_tf32_ts(d, ta_hi, b_hi + o, idesc, 1u);
+                    } else if (CTAS == 2) {
                       umma_tf32_ss_pair(d, a_lo + oa, b_hi + o, idesc, first);
                       umma_tf32_ss_pair(d, a_hi + oa, b_lo + o, idesc, 1u);
                       umma_tf32_ss_pair(d, a_hi + oa, b_hi + o, idesc, 1u);
@@ -403,7 +417,37 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
       for (int it = 0; it < n_tiles * nk; ++it) {
         mbar_wait(full_bar(s), ph);
         const uint32_t st = base + s * SM::STAGE_BYTES;
-        if (!(la.debug & 1))
+        if (TS) {
+          tc_fence_after();  // the slot's previous MMAs completed (empty -> TMA -> full): order the stores after them
+          // one thread = one row (= its TMEM lane): read the row's BK raw values, split, store into the operand ring
+          static_assert(!TS || BK == 16, "TS converter is written for BK = 16");
+          const int r = (warp & 3) * 32 + lane;
+          float f[BK];
+#pragma unroll
+          for (int c = 0; c < BK / 4; ++c) {
+            // row-major tile: 64-byte rows, 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3) (TMA 64B swizzle)
+            // T128 tile     : [BK/4 column groups][128 rows][16 B]
+            const uint32_t off = la.a_tiled ? (uint32_t)(c * kBM * 16 + r * 16)
+                                            : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+            const float4 t = lds128(st + off);
+            f[4 * c + 0] = t.x;
+            f[4 * c + 1] = t.y;
+            f[4 * c + 2] = t.z;
+            f[4 * c + 3] = t.w;
+          }
+          uint32_t hi[BK], lo[BK];
+#pragma unroll
+          for (int i = 0; i < BK; ++i) {
+            const float a = relu ? fmaxf(f[i], 0.f) : f[i];
+            hi[i] = to_tf32(a);
+            lo[i] = to_tf32(a - __uint_as_float(hi[i]));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA0 + (uint32_t)(s * 2 * BK);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + BK, lo);
+          tmem_wait_st();
+          tc_fence_before();
+        } else if (!(la.debug & 1))
 #pragma unroll
         for (int v = ct; v < SM::A_BYTES / 16; v += kNumConv) {
           const uint32_t addr = st + (uint32_t)v * 16u;
@@ -420,7 +464,9 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
           sts128(addr, h0, h1, h2, h3);
           sts128(addr + SM::A_BYTES, l0, l1, l2, l3);
         }
-        if (CTAS == 2) {
+        if (TS) {
+          // nothing was written to shared memory
+        } else if (CTAS == 2) {
           fence_proxy_async_all();  // the reader is the leader's tensor core
         } else {
           fence_proxy_async_smem();
@@ -721,6 +767,15 @@ static int epilogue_warps() {
   return v == 16 ? 16 : 8;
 }
 
+// activation operand in tensor memory (final-layer kernels, mode 1); FC_LINEAR_TS=0 switches back to shared memory
+static int operand_in_tmem() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_TS");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 // 1 = independent CTAs, 2 = CTA-pair MMAs (cta_group::2), 3 = weight multicast inside 2-CTA clusters
 static int cluster_mode() {
   static int v = [] {
@@ -730,12 +785,12 @@ static int cluster_mode() {
   return v >= 1 && v <= 3 ? v : 1;
 }
 
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW>
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS = false>
 static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, LinArgs la,
                          const StoreEpi& se, const RqsEpi& re, cudaStream_t stream) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;
   constexpr int CL = MODE == 1 ? 1 : 2;
-  using SM = LinSmem<BN, BK, STAGES, CTAS>;
+  using SM = LinSmem<BN, BK, STAGES, CTAS, TS>;
   static_assert(SM::TOTAL <= 232448, "shared memory per CTA");
   if (w->n_pad % BN != 0 || w->k_pad % 32 != 0) return FC_ERR_INVALID_ARGUMENT;
   CUtensorMap tmA, tmB;
@@ -755,7 +810,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
     return e ? atoi(e) : 0;
   }();
   la.debug = debug;
-  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE, EW>;
+  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE, EW, TS>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess)
@@ -857,12 +912,11 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
   la.num_n_tiles = (n_out + BN - 1) / BN;
-  if (cluster_mode() == 2) return epilogue_warps() == 8 ? launch_linear<0, BN, 16, 6, 0, 32, 2, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<0, BN, 16, 6, 0, 32, 2, 16>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
-  if (cluster_mode() == 3) return epilogue_warps() == 8 ? launch_linear<0, BN, 16, 4, 0, 32, 3, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<0, BN, 16, 4, 0, 32, 3, 16>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
-  return epilogue_warps() == 8 ? launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<0, BN, 16, 4, 0, 32, 1, 16>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cluster_mode() == 2) return launch_linear<0, BN, 16, 6, 0, 32, 2, 8>(A, lda, M, K, w, la, se, re, st);
+  if (cluster_mode() == 3) return launch_linear<0, BN, 16, 4, 0, 32, 3, 8>(A, lda, M, K, w, la, se, re, st);
+  if (epilogue_warps() == 16) return launch_linear<0, BN, 16, 4, 0, 32, 1, 16>(A, lda, M, K, w, la, se, re, st);
+  return launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, st);
 }
 
 extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, int32_t H, const fc_linear_weights* w,
@@ -886,32 +940,20 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
   StoreEpi se{};
   RqsEpi re{x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, tcols.idx, ccols.idx, ccols.n, D_t, c, status};
   constexpr int BN = 192;
-  if (c.K == 8) {
-    constexpr int PPAD = 24;
-    la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
-    if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
-    if (cluster_mode() == 2)
-      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 7, 8, PPAD, 2, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<1, BN, 16, 7, 8, PPAD, 2, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    if (cluster_mode() == 3)
-      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 8, PPAD, 3, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<1, BN, 16, 5, 8, PPAD, 3, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 8, PPAD, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<1, BN, 16, 5, 8, PPAD, 1, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FC_RQS_DISPATCH(KBINS, PP)                                                                                       \
+  {                                                                                                                     \
+    la.num_n_tiles = (D_t + BN / PP - 1) / (BN / PP);                                                                   \
+    if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;                                                 \
+    if (cluster_mode() == 2) return launch_linear<1, BN, 16, 7, KBINS, PP, 2, 8>(hidden, ldh, B, H, w, la, se, re, st);  \
+    if (cluster_mode() == 3) return launch_linear<1, BN, 16, 5, KBINS, PP, 3, 8>(hidden, ldh, B, H, w, la, se, re, st);  \
+    if (epilogue_warps() == 16) return launch_linear<1, BN, 16, 5, KBINS, PP, 1, 16>(hidden, ldh, B, H, w, la, se, re, st); \
+    if (operand_in_tmem()) return launch_linear<1, BN, 16, 4, KBINS, PP, 1, 8, true>(hidden, ldh, B, H, w, la, se, re, st); \
+    return launch_linear<1, BN, 16, 5, KBINS, PP, 1, 8>(hidden, ldh, B, H, w, la, se, re, st);                           \
   }
-  if (c.K == 16) {
-    constexpr int PPAD = 48;
-    la.num_n_tiles = (D_t + BN / PPAD - 1) / (BN / PPAD);
-    if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
-    if (cluster_mode() == 2)
-      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 7, 16, PPAD, 2, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<1, BN, 16, 7, 16, PPAD, 2, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    if (cluster_mode() == 3)
-      return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 16, PPAD, 3, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<1, BN, 16, 5, 16, PPAD, 3, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-    return epilogue_warps() == 8 ? launch_linear<1, BN, 16, 5, 16, PPAD, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream)
-                                  : launch_linear<1, BN, 16, 5, 16, PPAD, 1, 16>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
-  }
+  if (c.K == 8) FC_RQS_DISPATCH(8, 24)
+  if (c.K == 16) FC_RQS_DISPATCH(16, 48)
+#undef FC_RQS_DISPATCH
   return FC_ERR_UNSUPPORTED;
 }
 
@@ -937,5 +979,7 @@ extern "C" int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t 
   constexpr int BN = 64;  // 32 features per tile: the affine final layer is narrow (2 columns per feature)
   la.num_n_tiles = (2 * D_t + BN - 1) / BN;
   if (w->n_pad < la.num_n_tiles * BN) return FC_ERR_INVALID_ARGUMENT;
+  if (operand_in_tmem())
+    return launch_linear<2, BN, 16, 8, 0, 2, 1, 8, true>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   return launch_linear<2, BN, 16, 8, 0, 2, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
 }

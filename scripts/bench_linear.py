@@ -49,6 +49,8 @@ v["t128A,t128O"] = timeit(lambda: fl.linear(at, pk, relu_in=True, out=ot, out_t1
 v["t128A,t128O,res"] = timeit(lambda: fl.linear(at, pk, relu_in=True, out=ot, residual=rt, out_t128=True))
 print("  " + "  ".join("{} {:.3f}".format(k, t) for k, t in v.items()))
 t2 = timeit(lambda: fl.linear_rqs(a, pkf, x, y, lad, False, d_t, tcols, ccols, cfg, None))
+t2i = timeit(lambda: fl.linear_rqs(at, pkf, x, x, lad, False, d_t, tcols, ccols, cfg, None))
+print("final+spline in place, T128 hidden: {:.3f} ms".format(t2i))
 print("mode={} chunk={} debug={}: hidden {:.3f} ms   final+spline {:.3f} ms".format(
     os.environ.get("FC_LINEAR_MODE", "-"), os.environ.get("FC_LINEAR_CHUNK_K", "-"), os.environ.get("FC_LINEAR_DEBUG", "0"),
     t1, t2))
@@ -60,7 +62,8 @@ if int(os.environ.get("FC_LINEAR_DEBUG", "0")) & 4:
     names = ["mma_total", "w_tempty", "w_full", "w_conv", "w_ready", "stages", "", "", "epi_total", "e_init", "e_wait",
              "e_drain"]
     for label, fn in (("hidden t128 res", lambda: fl.linear(at, pk, relu_in=True, out=ot, residual=rt, out_t128=True)),
-                      ("final+spline", lambda: fl.linear_rqs(at, pkf, x, y, lad, False, d_t, tcols, ccols, cfg, None))):
+                      ("final+spline", lambda: fl.linear_rqs(at, pkf, x, y, lad, False, d_t, tcols, ccols, cfg, None)),
+                      ("final+spline in place", lambda: fl.linear_rqs(at, pkf, x, x, lad, False, d_t, tcols, ccols, cfg, None))):
         fn()
         torch.cuda.synchronize()
         L.fc_linear_debug_profile(ctypes.byref(buf))
