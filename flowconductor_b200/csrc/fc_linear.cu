@@ -49,9 +49,11 @@ constexpr int kNumConv = 128;  // converter threads (warps 4-7)
 // setmaxnreg budgets per warpgroup, EW epilogue warps (the register file holds 65536):
 //   EW = 8 : 512 threads launch with 128;  128*40 + 128*56 + 256*208 = 65536
 //   EW = 16: 768 threads launch with  80;  128*32 + 128*32 + 512*104 = 61440 (= 768 * 80, the CTA's pool)
-template <int EW>
+//   EW = 8 + 8 spline warps: 768 threads launch with 80;  128*32 + 128*64 + 256*120 + 256*72 = 61440
+template <int EW, int SW = 0>
 struct RegBudget {
-  static constexpr int kProducer = EW == 8 ? 40 : 32, kConverter = EW == 8 ? 56 : 32, kEpilogue = EW == 8 ? 208 : 104;
+  static constexpr int kProducer = SW ? 32 : (EW == 8 ? 40 : 32), kConverter = SW ? 64 : (EW == 8 ? 56 : 32),
+                       kEpilogue = SW ? 120 : (EW == 8 ? 208 : 104), kSpline = 72;
 };
 
 struct LinArgs {
@@ -92,15 +94,16 @@ struct RqsEpi {
   int activation;  // EPI 2 (affine): FC_SCALE_*; c.inverse carries the direction
 };
 
-template <int BN, int BK, int STAGES, int CTAS, bool TS = false>
+template <int BN, int BK, int STAGES, int CTAS, bool TS = false, int SW = 0>
 struct LinSmem {
   static constexpr int A_BYTES = kBM * BK * 4;
   static constexpr int B_BYTES = (BN / CTAS) * BK * 4;  // a CTA pair splits the rows of every weight box
   static constexpr int A_PLANES = TS ? 1 : 2;            // TS: the converted operand lives in tensor memory
   static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + 2 * B_BYTES;
-  static constexpr int BAR_BYTES = 8 * (4 * STAGES + 4) + 16;
-  static constexpr int LAD_BYTES = 2 * 3 * kBM * 4;  // per-row partial log-dets of up to 3 other column groups, x2
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + LAD_BYTES + 1024;  // + alignment slack
+  static constexpr int PARAMS_BYTES = SW ? kBM * BN * 4 : 0;  // one tile of conditioner outputs for the spline warps
+  static constexpr int BAR_BYTES = 8 * (4 * STAGES + 6) + 16;
+  static constexpr int LAD_BYTES = (SW ? 2 : 2 * 3) * kBM * 4;  // per-row partial log-dets of the other column groups, x2
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + PARAMS_BYTES + BAR_BYTES + LAD_BYTES + 1024;  // + alignment slack
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
 };
 
@@ -157,31 +160,39 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
 //   k-values the shared memory then serves 3 weight-tile reads + the TMA writes + one raw-tile read instead of 3 x
 //   (A + B) reads + TMA writes + raw read + two converted writes: 132 instead of 201 B/cycle at BN = 192 (the
 //   SMEM port delivers 128), and no generic->async proxy hand-off is needed.
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS>
-__global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
+// SW > 0 (spline epilogue, with TS): the bijection moves to SW extra warps.  The drain warps only accumulate the
+//   partial sums and drop the finished parameter tile (128 rows x BN columns, column-major so that a warp's 32 rows are
+//   32 consecutive words) into shared memory; the spline warps evaluate it while the MMAs and drains of the NEXT tile
+//   run.  Without this the MMA warp can only run two partial accumulators ahead of the ~6k cycles the spline of a tile
+//   takes, and waits a third of the time.
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS, int SW>
+__global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const LinArgs la, const StoreEpi se, const RqsEpi re) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;  // CTAs per MMA
   constexpr bool MC = MODE == 3;           // weight boxes multicast inside the cluster
   constexpr int CL = MODE == 1 ? 1 : 2;    // cluster size = row tiles per work unit
-  using SM = LinSmem<BN, BK, STAGES, CTAS, TS>;
+  using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW>;
+  static_assert(SW == 0 || (EPI == 1 && EW == 8 && SW == 8), "spline warps: RQ epilogue, 8 + 8 warps");
   static_assert(!TS || (MODE == 1 && 2 * BN + STAGES * 2 * BK <= 512), "TS: operand ring must fit behind the accumulators");
   constexpr uint32_t kTmemA0 = 2 * BN;  // first column of the operand ring (TS)
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 1023u) & ~1023u;
   unsigned char* const gbase = smem_raw + (base - raw_s);
-  const uint32_t bars = base + STAGES * SM::STAGE_BYTES;
+  const uint32_t params_s = base + STAGES * SM::STAGE_BYTES;  // parameter tile (SW > 0)
+  const uint32_t bars = params_s + SM::PARAMS_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto ready_bar = [&](int s) { return bars + 8u * (3 * STAGES + s); };  // leader only: peer's stage is ready
   auto tfull_bar = [&](int a) { return bars + 8u * (4 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (4 * STAGES + 2 + a); };  // leader's is the one in use
-  const uint32_t tmem_slot = bars + 8u * (4 * STAGES + 4);
-  volatile uint32_t* const tmem_slot_g =
-      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * SM::STAGE_BYTES + 8 * (4 * STAGES + 4));
-  float* const lad_x = reinterpret_cast<float*>(gbase + STAGES * SM::STAGE_BYTES + SM::BAR_BYTES);
+  const uint32_t pfull_bar = bars + 8u * (4 * STAGES + 4), pempty_bar = bars + 8u * (4 * STAGES + 5);
+  const uint32_t tmem_slot = bars + 8u * (4 * STAGES + 6);
+  unsigned char* const gbars = gbase + STAGES * SM::STAGE_BYTES + SM::PARAMS_BYTES;
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbars + 8 * (4 * STAGES + 6));
+  float* const lad_x = reinterpret_cast<float*>(gbars + SM::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 512;
@@ -203,6 +214,8 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EW * CTAS);
     }
+    mbar_init(pfull_bar, EW);
+    mbar_init(pempty_bar, SW > 0 ? SW : 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
   const int n_chunks = (nk + chunk - 1) / chunk;
 
   if (warp < kConvWarp0) {
-    set_max_regs_dec<RegBudget<EW>::kProducer>();
+    set_max_regs_dec<RegBudget<EW, SW>::kProducer>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
@@ -408,7 +421,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
     }
   } else if (warp < kEpiWarp0) {
     // ------------------------------------------------------------------ converters: raw fp32 -> (hi, lo) tf32
-    set_max_regs_dec<RegBudget<EW>::kConverter>();
+    set_max_regs_dec<RegBudget<EW, SW>::kConverter>();
     const int ct = threadIdx.x - kConvWarp0 * 32;
     int s = 0;
     uint32_t ph = 0;
@@ -485,9 +498,10 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    set_max_regs_inc<RegBudget<EW>::kEpilogue>();
+  } else if (warp < kEpiWarp0 + EW) {
+    // ------------------------------------------------------------------ epilogue / drain warps
+    set_max_regs_inc<RegBudget<EW, SW>::kEpilogue>();
+    uint32_t pph = 0;  // phase of the parameter-tile hand-off (SW > 0)
     constexpr int NG = EW / 4;               // column groups: 4 warps (one per TMEM lane quarter) each
     constexpr int NCOL = BN / NG;            // accumulator columns (and registers) per thread
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
@@ -548,7 +562,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
         } else {
           constexpr int FEATS = BN / PPAD;
           constexpr int FH = FEATS / NG;
-          if (nt == 0 && half == 0 && re.n_copy > 0 && re.y != re.x) {
+          if (SW == 0 && nt == 0 && half == 0 && re.n_copy > 0 && re.y != re.x) {
             // identity columns (coupling.py:96-98): the warp copies its 32 rows one row per step (coalesced)
             const int64_t row0 = (int64_t)mt * kBM + q * 32;
             for (int i0 = 0; i0 < re.n_copy; i0 += 32) {
@@ -564,8 +578,10 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
             const int fl = half * FH + f;    // feature within the tile
             const int fg = nt * FEATS + fl;  // feature of the layer
             const bool live = fg < re.D_t;
-            xcol[f] = live ? (re.tcols ? __ldg(re.tcols + fg) : fg) : 0;
-            xv[f] = (valid && live) ? __ldg(re.x + row * re.ldx + xcol[f]) : 0.f;
+            if (SW == 0) {
+              xcol[f] = live ? (re.tcols ? __ldg(re.tcols + fg) : fg) : 0;
+              xv[f] = (valid && live) ? __ldg(re.x + row * re.ldx + xcol[f]) : 0.f;
+            }
             if constexpr (PPAD % 4 == 0) {
               const float4* bp = reinterpret_cast<const float4*>(la.bias + (nt * BN + fl * PPAD));
 #pragma unroll
@@ -638,6 +654,15 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
               *reinterpret_cast<float4*>(se.out + o_base + n * n_mul) = o;
             }
           }
+        } else if (SW > 0) {
+          // hand the finished parameter tile to the spline warps: column-major [BN][128 rows] words
+          mbar_wait(pempty_bar, pph ^ 1u);
+          const uint32_t pbase = params_s + (uint32_t)((half * NCOL) * kBM + q * 32 + lane) * 4u;
+#pragma unroll
+          for (int j = 0; j < NCOL; ++j) sts32(pbase + (uint32_t)(j * kBM * 4), av[j]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pfull_bar);
+          pph ^= 1u;
         } else {
           constexpr int FEATS = BN / PPAD;
           constexpr int FH = FEATS / NG;
@@ -658,7 +683,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
           }
         }
       }
-      if (EPI != 0) {
+      if (EPI != 0 && SW == 0) {
         // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): this thread summed its features in
         // order; the two column halves of a row are combined in a fixed order through shared memory
         float* ex = lad_x + parity * 3 * kBM;
@@ -680,6 +705,83 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * EW, 1)
       g_lin_prof[11] = (unsigned long long)e_drain;
     }
     if (EPI != 0 && status != 0 && re.status) atomicOr(re.status, (int)status);
+  } else {
+    // ------------------------------------------------------------------ spline warps (SW > 0)
+    if constexpr (SW > 0) {
+      set_max_regs_dec<RegBudget<EW, SW>::kSpline>();
+      constexpr int FEATS = BN / PPAD;
+      constexpr int FG = FEATS / 2;             // features per thread and tile: two thread groups of 128 rows
+      const int t = threadIdx.x - 32 * (kEpiWarp0 + EW);
+      const int r = t & (kBM - 1), g = t >> 7;  // row of the tile, feature group
+      uint32_t pph = 0;
+      unsigned status = 0;
+      int parity = 0;
+      for (int mp = unit0; mp < n_units; mp += unit_step) {
+        const int mt = mp * CL + rank;
+        const int64_t row = (int64_t)mt * kBM + r;
+        const bool valid = row < la.M;
+        float lad_acc = 0.f;
+        if (re.n_copy > 0 && re.y != re.x) {
+          // identity columns (coupling.py:96-98): each warp copies its 32 rows, one row per step (coalesced)
+          const int64_t row0 = (int64_t)mt * kBM + (r & ~31);
+          if (g == 0) {
+            for (int i0 = 0; i0 < re.n_copy; i0 += 32) {
+              const int cc = (i0 + lane < re.n_copy) ? __ldg(re.ccols + i0 + lane) : -1;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                if (cc >= 0 && row0 + rr < la.M) re.y[(row0 + rr) * re.ldy + cc] = __ldg(re.x + (row0 + rr) * re.ldx + cc);
+              }
+            }
+          }
+        }
+        for (int nt = 0; nt < n_tiles; ++nt) {
+          float xv[FG];
+          int xcol[FG];
+#pragma unroll
+          for (int f = 0; f < FG; ++f) {  // inputs first: their latency hides behind the wait for the parameters
+            const int fg = nt * FEATS + g * FG + f;
+            const bool live = fg < re.D_t;
+            xcol[f] = live ? (re.tcols ? __ldg(re.tcols + fg) : fg) : 0;
+            xv[f] = (valid && live) ? __ldg(re.x + row * re.ldx + xcol[f]) : 0.f;
+          }
+          mbar_wait(pfull_bar, pph);
+#pragma unroll 1
+          for (int f = 0; f < FG; ++f) {
+            const int fg = nt * FEATS + g * FG + f;
+            float p[PPAD];
+            const uint32_t pb = params_s + (uint32_t)(((g * FG + f) * PPAD) * kBM + r) * 4u;
+#pragma unroll
+            for (int i = 0; i < PPAD; ++i) p[i] = lds32(pb + (uint32_t)(i * kBM * 4));
+            if (fg < re.D_t) {
+              float xval = xv[0];
+              int xc = xcol[0];
+#pragma unroll
+              for (int k = 1; k < FG; ++k) {
+                xval = (k == f) ? xv[k] : xval;
+                xc = (k == f) ? xcol[k] : xc;
+              }
+              float yv, lv;
+              rqs_eval<KC, true>(re.c, xval, p, yv, lv, status);
+              if (valid) re.y[row * re.ldy + xc] = yv;
+              lad_acc += lv;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pempty_bar);
+          pph ^= 1u;
+        }
+        // per-sample log|det J|: the two feature groups of a row are combined in a fixed order
+        float* ex = lad_x + parity * kBM;
+        if (g == 1) ex[r] = lad_acc;
+        named_barrier_sync(2, 32 * SW);
+        if (g == 0 && valid) {
+          const float tot = lad_acc + ex[r];
+          re.lad[row] = re.accumulate ? re.lad[row] + tot : tot;
+        }
+        parity ^= 1;
+      }
+      if (status != 0 && re.status) atomicOr(re.status, (int)status);
+    }
   }
 
   __syncwarp();  // the role branches leave most warps diverged; the cluster barrier is warp-aligned
@@ -776,6 +878,15 @@ static int operand_in_tmem() {
   return v != 0;
 }
 
+// bijection on separate warps (FC_LINEAR_SW=0: inside the drain warps)
+static int spline_warps() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_SW");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 // 1 = independent CTAs, 2 = CTA-pair MMAs (cta_group::2), 3 = weight multicast inside 2-CTA clusters
 static int cluster_mode() {
   static int v = [] {
@@ -785,12 +896,12 @@ static int cluster_mode() {
   return v >= 1 && v <= 3 ? v : 1;
 }
 
-template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS = false>
+template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS = false, int SW = 0>
 static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, LinArgs la,
                          const StoreEpi& se, const RqsEpi& re, cudaStream_t stream) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;
   constexpr int CL = MODE == 1 ? 1 : 2;
-  using SM = LinSmem<BN, BK, STAGES, CTAS, TS>;
+  using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW>;
   static_assert(SM::TOTAL <= 232448, "shared memory per CTA");
   if (w->n_pad % BN != 0 || w->k_pad % 32 != 0) return FC_ERR_INVALID_ARGUMENT;
   CUtensorMap tmA, tmB;
@@ -810,7 +921,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
     return e ? atoi(e) : 0;
   }();
   la.debug = debug;
-  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE, EW, TS>;
+  auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE, EW, TS, SW>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess)
@@ -822,7 +933,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   const int grid = (units < max_units ? units : max_units) * CL;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kBaseThreads + 32 * EW);
+  cfg.blockDim = dim3(kBaseThreads + 32 * (EW + SW));
   cfg.dynamicSmemBytes = SM::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -948,6 +1059,8 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
     if (cluster_mode() == 2) return launch_linear<1, BN, 16, 7, KBINS, PP, 2, 8>(hidden, ldh, B, H, w, la, se, re, st);  \
     if (cluster_mode() == 3) return launch_linear<1, BN, 16, 5, KBINS, PP, 3, 8>(hidden, ldh, B, H, w, la, se, re, st);  \
     if (epilogue_warps() == 16) return launch_linear<1, BN, 16, 5, KBINS, PP, 1, 16>(hidden, ldh, B, H, w, la, se, re, st); \
+    if (operand_in_tmem() && spline_warps())                                                                             \
+      return launch_linear<1, BN, 16, 4, KBINS, PP, 1, 8, true, 8>(hidden, ldh, B, H, w, la, se, re, st);               \
     if (operand_in_tmem()) return launch_linear<1, BN, 16, 4, KBINS, PP, 1, 8, true>(hidden, ldh, B, H, w, la, se, re, st); \
     return launch_linear<1, BN, 16, 5, KBINS, PP, 1, 8>(hidden, ldh, B, H, w, la, se, re, st);                           \
   }
