@@ -94,13 +94,13 @@ struct RqsEpi {
   int activation;  // EPI 2 (affine): FC_SCALE_*; c.inverse carries the direction
 };
 
-template <int BN, int BK, int STAGES, int CTAS, bool TS = false, int SW = 0>
+template <int BN, int BK, int STAGES, int CTAS, bool TS = false, int SW = 0, bool STG = false>
 struct LinSmem {
   static constexpr int A_BYTES = kBM * BK * 4;
   static constexpr int B_BYTES = (BN / CTAS) * BK * 4;  // a CTA pair splits the rows of every weight box
   static constexpr int A_PLANES = TS ? 1 : 2;            // TS: the converted operand lives in tensor memory
   static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + 2 * B_BYTES;
-  static constexpr int PARAMS_BYTES = SW ? kBM * BN * 4 : 0;  // one tile of conditioner outputs for the spline warps
+  static constexpr int PARAMS_BYTES = (SW || STG) ? kBM * BN * 4 : 0;  // parameter tile (spline warps) / staging tile
   static constexpr int BAR_BYTES = 8 * (4 * STAGES + 6) + 16;
   static constexpr int LAD_BYTES = (SW ? 2 : 2 * 3) * kBM * 4;  // per-row partial log-dets of the other column groups, x2
   static constexpr int TOTAL = STAGES * STAGE_BYTES + PARAMS_BYTES + BAR_BYTES + LAD_BYTES + 1024;  // + alignment slack
@@ -144,7 +144,10 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
 }
 
 // EPI: 0 = store (bias, optional residual / ReLU), 1 = rational-quadratic spline with KC bins,
-//      2 = affine (PPAD = 2 accumulator columns per feature: raw scale, shift).
+//      2 = affine (PPAD = 2 accumulator columns per feature: raw scale, shift),
+//      3 = store of T128 outputs through a shared-memory staging tile: the skip connection comes IN by one TMA bulk
+//          load and the result goes OUT by one TMA bulk store per 128 x 128 tile (contiguous 64 KB in the T128
+//          layout), issued by the otherwise idle warp 3; the epilogue warps never touch global memory.
 // RQS tile geometry: FEATS features of PPAD accumulator columns each (BN = FEATS * PPAD).
 // MODE 1: one CTA per SM, independent.
 // MODE 3: clusters of two CTAs work on two row tiles in lock step and SHARE the weight stream: each CTA fetches half
@@ -172,7 +175,8 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
   constexpr int CTAS = MODE == 2 ? 2 : 1;  // CTAs per MMA
   constexpr bool MC = MODE == 3;           // weight boxes multicast inside the cluster
   constexpr int CL = MODE == 1 ? 1 : 2;    // cluster size = row tiles per work unit
-  using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW>;
+  using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW, EPI == 3>;
+  static_assert(EPI != 3 || (TS && BN == 128 && EW == 8 && SW == 0 && MODE == 1), "staged store: 128-wide tiles, A in TMEM");
   static_assert(SW == 0 || (EPI == 1 && EW == 8 && SW == 8), "spline warps: RQ epilogue, 8 + 8 warps");
   static_assert(!TS || (MODE == 1 && 2 * BN + STAGES * 2 * BK <= 512), "TS: operand ring must fit behind the accumulators");
   constexpr uint32_t kTmemA0 = 2 * BN;  // first column of the operand ring (TS)
@@ -214,8 +218,10 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EW * CTAS);
     }
-    mbar_init(pfull_bar, EW);
-    mbar_init(pempty_bar, SW > 0 ? SW : 1);
+    // SW: parameter tile full (drain warps) / empty (spline warps).  EPI 3: staging tile ready to be written (manager,
+    // possibly through the skip connection's TMA bytes) / written by all epilogue warps
+    mbar_init(pfull_bar, EPI == 3 ? 1 : EW);
+    mbar_init(pempty_bar, EPI == 3 ? EW : (SW > 0 ? SW : 1));
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -300,6 +306,30 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
             }
           }
         }
+      }
+    } else if (warp == 3 && EPI == 3) {
+      // ---------------------------------------------------------------- staging manager (EPI 3)
+      if (lane == 0) {
+        constexpr uint32_t kTileBytes = kBM * BN * 4;
+        uint32_t ph = 0;
+        for (int mp = unit0; mp < n_units; mp += unit_step) {
+          const int mt = mp * CL + rank;
+          for (int nt = 0; nt < n_tiles; ++nt) {
+            // a T128 tile of 128 rows x BN columns is contiguous: tile mt, column groups nt*BN/4 ..
+            const int64_t off = (int64_t)mt * kBM * se.ldo + (int64_t)nt * kBM * BN;
+            if (se.residual != nullptr) {
+              mbar_expect_tx(pfull_bar, kTileBytes);
+              bulk_load_1d(params_s, se.residual + (int64_t)mt * kBM * se.ldr + (int64_t)nt * kBM * BN, kTileBytes, pfull_bar);
+            } else {
+              mbar_arrive(pfull_bar);  // nothing to bring in: the tile may be written right away
+            }
+            mbar_wait(pempty_bar, ph);  // all epilogue warps have written their part (generic -> async fenced)
+            bulk_store_1d(se.out + off, params_s, kTileBytes);
+            bulk_store_wait_read();     // the staging tile may be overwritten (next skip connection / next result)
+            ph ^= 1u;
+          }
+        }
+        bulk_store_wait_all();
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- UMMA issuer (leader) / relay (peer)
@@ -527,9 +557,19 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         // between the last partial accumulator and the stores.
         const int rt = q * 32 + lane;
         int64_t o_base = 0, r_base = 0, n_mul = 1;
-        float xv[EPI != 0 ? (BN / PPAD) / NG : 1];
-        int xcol[EPI != 0 ? (BN / PPAD) / NG : 1];
-        if (EPI == 0) {
+        float xv[(EPI == 1 || EPI == 2) ? (BN / PPAD) / NG : 1];
+        int xcol[(EPI == 1 || EPI == 2) ? (BN / PPAD) / NG : 1];
+        if (EPI == 3) {
+          const float4* b4 = reinterpret_cast<const float4*>(la.bias + nt * BN + half * NCOL);
+#pragma unroll
+          for (int j = 0; j < NCOL / 4; ++j) {
+            const float4 b = __ldg(b4 + j);
+            av[4 * j + 0] = b.x;
+            av[4 * j + 1] = b.y;
+            av[4 * j + 2] = b.z;
+            av[4 * j + 3] = b.w;
+          }
+        } else if (EPI == 0) {
           // T128: element (r, n) of tile mt at mt*128*W + ((n/4)*128 + r)*4: a warp's 32 rows of one column group
           // are 512 contiguous bytes (coalesced); row-major: 32 rows x 16 B scattered over 32 lines
           o_base = se.tiled ? (int64_t)mt * kBM * se.ldo + rt * 4 : row * se.ldo;
@@ -638,7 +678,36 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           }
         }
         if (la.debug & 2) continue;
-        if (EPI == 0) {
+        if (EPI == 3) {
+          // finished tile -> staging tile (same [column group][row][4 floats] order as the T128 layout); the skip
+          // connection is already there (TMA), the manager warp stores the tile with one bulk copy
+          mbar_wait(pfull_bar, pph);
+          const uint32_t sb = params_s + (uint32_t)(((half * (NCOL / 4)) * kBM + rt) * 16);
+          const bool res = se.residual != nullptr;
+#pragma unroll
+          for (int j = 0; j < NCOL / 4; ++j) {
+            float4 o = make_float4(av[4 * j + 0], av[4 * j + 1], av[4 * j + 2], av[4 * j + 3]);
+            const uint32_t a = sb + (uint32_t)(j * kBM * 16);
+            if (res) {
+              const float4 r = lds128(a);
+              o.x += r.x;
+              o.y += r.y;
+              o.z += r.z;
+              o.w += r.w;
+            }
+            if (se.relu_out) {
+              o.x = fmaxf(o.x, 0.f);
+              o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f);
+              o.w = fmaxf(o.w, 0.f);
+            }
+            sts128(a, __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w));
+          }
+          fence_proxy_async_smem();  // the bulk store reads the tile through the async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pempty_bar);
+          pph ^= 1u;
+        } else if (EPI == 0) {
           const int n0 = nt * BN + half * NCOL;
 #pragma unroll
           for (int j = 0; j < NCOL / 4; ++j) {
@@ -683,7 +752,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           }
         }
       }
-      if (EPI != 0 && SW == 0) {
+      if ((EPI == 1 || EPI == 2) && SW == 0) {
         // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): this thread summed its features in
         // order; the two column halves of a row are combined in a fixed order through shared memory
         float* ex = lad_x + parity * 3 * kBM;
@@ -704,7 +773,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
       g_lin_prof[10] = (unsigned long long)e_wait;
       g_lin_prof[11] = (unsigned long long)e_drain;
     }
-    if (EPI != 0 && status != 0 && re.status) atomicOr(re.status, (int)status);
+    if ((EPI == 1 || EPI == 2) && status != 0 && re.status) atomicOr(re.status, (int)status);
   } else {
     // ------------------------------------------------------------------ spline warps (SW > 0)
     if constexpr (SW > 0) {
@@ -887,6 +956,15 @@ static int spline_warps() {
   return v != 0;
 }
 
+// T128 outputs through the staged-store kernel (FC_LINEAR_STAGED=0: direct stores from the epilogue warps)
+static int staged_store() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_STAGED");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 // 1 = independent CTAs, 2 = CTA-pair MMAs (cta_group::2), 3 = weight multicast inside 2-CTA clusters
 static int cluster_mode() {
   static int v = [] {
@@ -901,7 +979,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
                          const StoreEpi& se, const RqsEpi& re, cudaStream_t stream) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;
   constexpr int CL = MODE == 1 ? 1 : 2;
-  using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW>;
+  using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW, EPI == 3>;
   static_assert(SM::TOTAL <= 232448, "shared memory per CTA");
   if (w->n_pad % BN != 0 || w->k_pad % 32 != 0) return FC_ERR_INVALID_ARGUMENT;
   CUtensorMap tmA, tmB;
@@ -1027,6 +1105,11 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   if (cluster_mode() == 2) return launch_linear<0, BN, 16, 6, 0, 32, 2, 8>(A, lda, M, K, w, la, se, re, st);
   if (cluster_mode() == 3) return launch_linear<0, BN, 16, 4, 0, 32, 3, 8>(A, lda, M, K, w, la, se, re, st);
   if (epilogue_warps() == 16) return launch_linear<0, BN, 16, 4, 0, 32, 1, 16>(A, lda, M, K, w, la, se, re, st);
+  if (o_tiled && staged_store() && n_out % 128 == 0 && (n_out == ldo) && (!residual || ldr == n_out)) {
+    // T128 output in whole 128-wide tiles: staged kernel (operand in TMEM, TMA bulk in / out)
+    la.num_n_tiles = n_out / 128;
+    return launch_linear<3, 128, 16, 6, 0, 32, 1, 8, true>(A, lda, M, K, w, la, se, re, st);
+  }
   return launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, st);
 }
 
