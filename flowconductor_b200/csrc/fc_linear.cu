@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
   constexpr bool MC = MODE == 3;           // weight boxes multicast inside the cluster
   constexpr int CL = MODE == 1 ? 1 : 2;    // cluster size = row tiles per work unit
   using SM = LinSmem<BN, BK, STAGES, CTAS, TS, SW, EPI == 3>;
-  static_assert(EPI != 3 || (TS && BN == 128 && EW == 8 && SW == 0 && MODE == 1), "staged store: 128-wide tiles, A in TMEM");
+  static_assert(EPI != 3 || (TS && BN == 128 && EW == 8 && SW == 0 && MODE != 3), "staged store: 128-wide tiles, A in TMEM");
   static_assert(SW == 0 || (EPI == 1 && EW == 8 && SW == 8), "spline warps: RQ epilogue, 8 + 8 warps");
-  static_assert(!TS || (MODE == 1 && 2 * BN + STAGES * 2 * BK <= 512), "TS: operand ring must fit behind the accumulators");
+  static_assert(!TS || (MODE != 3 && 2 * BN + STAGES * 2 * BK <= 512), "TS: operand ring must fit behind the accumulators");
   constexpr uint32_t kTmemA0 = 2 * BN;  // first column of the operand ring (TS)
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
@@ -398,9 +398,15 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
                     if (TS) {
                       const uint32_t ta_hi = tmem_base + kTmemA0 + (uint32_t)(s * 2 * BK + kk * 8);
                       const uint32_t ta_lo = ta_hi + (uint32_t)BK;
-                      umma_tf32_ts(d, ta_lo, b_hi + o, idesc, first);
-                      umma_tf32_ts(d, ta_hi, b_lo + o, idesc, 1u);
-                      umma_tf32_ts(d, ta_hi, b_hi + o, idesc, 1u);
+                      if (CTAS == 2) {
+                        umma_tf32_ts_pair(d, ta_lo, b_hi + o, idesc, first);
+                        umma_tf32_ts_pair(d, ta_hi, b_lo + o, idesc, 1u);
+                        umma_tf32_ts_pair(d, ta_hi, b_hi + o, idesc, 1u);
+                      } else {
+                        umma_tf32_ts(d, ta_lo, b_hi + o, idesc, first);
+                        umma_tf32_ts(d, ta_hi, b_lo + o, idesc, 1u);
+                        umma_tf32_ts(d, ta_hi, b_hi + o, idesc, 1u);
+                      }
                     } else if (CTAS == 2) {
                       umma_tf32_ss_pair(d, a_lo + oa, b_hi + o, idesc, first);
                       umma_tf32_ss_pair(d, a_hi + oa, b_lo + o, idesc, 1u);
@@ -516,7 +522,9 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         }
         __syncwarp();
         if (lane == 0) {
-          if (CTAS == 2) {
+          if (CTAS == 2 && TS) {
+            mbar_arrive_remote_relaxed(conv_bar(s), 0);  // operand went to tensor memory: ordered by the tcgen05 fence
+          } else if (CTAS == 2) {
             mbar_arrive_remote(conv_bar(s), 0);  // release.cluster: publishes this warp's part of the stage
           } else {
             mbar_arrive(conv_bar(s));
@@ -956,6 +964,15 @@ static int spline_warps() {
   return v != 0;
 }
 
+// cta_group::2 CTA pairs for the kernels whose operand lives in tensor memory (FC_LINEAR_PAIR=0: single CTAs)
+static int pair_mma() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 // T128 outputs through the staged-store kernel (FC_LINEAR_STAGED=0: direct stores from the epilogue warps)
 static int staged_store() {
   static int v = [] {
@@ -1108,6 +1125,7 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   if (o_tiled && staged_store() && n_out % 128 == 0 && (n_out == ldo) && (!residual || ldr == n_out)) {
     // T128 output in whole 128-wide tiles: staged kernel (operand in TMEM, TMA bulk in / out)
     la.num_n_tiles = n_out / 128;
+    if (pair_mma()) return launch_linear<3, 128, 16, 8, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
     return launch_linear<3, 128, 16, 6, 0, 32, 1, 8, true>(A, lda, M, K, w, la, se, re, st);
   }
   return launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, st);
@@ -1142,6 +1160,8 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
     if (cluster_mode() == 2) return launch_linear<1, BN, 16, 7, KBINS, PP, 2, 8>(hidden, ldh, B, H, w, la, se, re, st);  \
     if (cluster_mode() == 3) return launch_linear<1, BN, 16, 5, KBINS, PP, 3, 8>(hidden, ldh, B, H, w, la, se, re, st);  \
     if (epilogue_warps() == 16) return launch_linear<1, BN, 16, 5, KBINS, PP, 1, 16>(hidden, ldh, B, H, w, la, se, re, st); \
+    if (operand_in_tmem() && spline_warps() && pair_mma())                                                               \
+      return launch_linear<1, BN, 16, 4, KBINS, PP, 2, 8, true, 8>(hidden, ldh, B, H, w, la, se, re, st);               \
     if (operand_in_tmem() && spline_warps())                                                                             \
       return launch_linear<1, BN, 16, 4, KBINS, PP, 1, 8, true, 8>(hidden, ldh, B, H, w, la, se, re, st);               \
     if (operand_in_tmem()) return launch_linear<1, BN, 16, 4, KBINS, PP, 1, 8, true>(hidden, ldh, B, H, w, la, se, re, st); \
