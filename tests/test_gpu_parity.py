@@ -405,6 +405,145 @@ def test_full_size_layer_round_trip(dev, d, k):
     assert torch.isfinite(lad).all()
 
 
+# ------------------------------------------------------------------------------------------------
+# tensor-core GEMM entry points (fc_linear_*), called through the C ABI by flowconductor_b200.linear
+# ------------------------------------------------------------------------------------------------
+def _gemm_err(got, want64):
+    return (got.double() - want64).abs().max().item() / want64.abs().max().item()
+
+
+@pytest.mark.parametrize("M,K,N,relu_in,relu_out,res,a_t,o_t", [
+    (1, 32, 4, False, False, False, False, False),        # a single row, narrowest output
+    (128, 32, 256, False, False, False, False, False),
+    (1000, 256, 256, True, True, True, False, False),     # ragged last tile, ReLU both sides, skip connection
+    (4099, 256, 512, True, False, True, False, False),    # two N tiles of the 256-wide kernel
+    (5000, 8, 64, False, True, False, False, False),      # K shorter than one ring slot
+    (300, 752, 32, False, False, False, False, False),    # input-gradient shape: long reduction, narrow output
+    (1000, 256, 256, False, False, False, True, False),   # T128 in, rows out
+    (1000, 64, 256, False, False, False, False, True),    # rows in, T128 out: staged kernel
+    (1000, 256, 256, True, True, True, True, True),       # staged kernel with skip connection, CTA pairs, ragged
+    (257, 256, 384, True, False, True, True, True),       # three 128-wide tiles, odd number of row tiles
+    (70000, 32, 64, True, False, True, True, True),       # T128 but not a multiple of 128 wide: direct stores
+])
+def test_linear_store_kernels(dev, M, K, N, relu_in, relu_out, res, a_t, o_t):
+    """fc_linear_apply against an fp64 matmul; the yardstick is the fp32 cuBLAS result of the same product."""
+    from flowconductor_b200 import linear as fl
+
+    g = torch.Generator(device=dev).manual_seed(M * 7 + K)
+    a = torch.randn(M, K, generator=g, device=dev)
+    w = torch.randn(N, K, generator=g, device=dev) / math.sqrt(K)
+    b = torch.randn(N, generator=g, device=dev)
+    r = torch.randn(M, N, generator=g, device=dev) if res else None
+    pk = fl.pack(w, b)
+    out = fl.linear(fl.T128.from_rows(a) if a_t else a, pk, relu_in=relu_in, relu_out=relu_out,
+                    residual=(fl.T128.from_rows(r) if (o_t and res) else r), out_t128=o_t)
+    if o_t:
+        out = out.to_rows()
+    a64 = a.double().relu() if relu_in else a.double()
+    want = a64 @ w.double().t() + b.double() + (r.double() if res else 0.0)
+    ref32 = torch.nn.functional.linear(a.relu() if relu_in else a, w, b) + (r if res else 0.0)
+    if relu_out:
+        want, ref32 = want.relu(), ref32.relu()
+    assert out.shape == (M, N) and torch.isfinite(out).all()
+    assert _gemm_err(out, want) <= 2.0 * _gemm_err(ref32, want) + 2e-7
+
+
+def test_linear_pack_folds_mask_and_column_scatter(dev):
+    from flowconductor_b200 import linear as fl
+
+    g = torch.Generator(device=dev).manual_seed(2)
+    x = torch.randn(777, 64, generator=g, device=dev)
+    ident = torch.arange(1, 64, 2, device=dev)
+    w = torch.randn(256, 32, generator=g, device=dev)
+    mask = (torch.rand(256, 32, generator=g, device=dev) > 0.5).float()
+    b = torch.randn(256, generator=g, device=dev)
+    pk = fl.pack(w, b, mask=mask, col_map=ident.to(torch.int32), k_in=64)
+    out = fl.linear(x, pk)
+    want = x[:, ident].double() @ (w * mask).double().t() + b.double()
+    assert _gemm_err(out, want) < 1e-6
+
+
+@pytest.mark.parametrize("M,D,K,H,inverse,coupling,h_t", [
+    (1000, 64, 8, 256, False, True, True), (3001, 64, 8, 256, True, True, False), (500, 16, 16, 256, False, False, True),
+    (129, 20, 8, 64, False, True, False), (1, 6, 8, 64, True, False, False),
+])
+def test_linear_rqs_fused_kernel(dev, M, D, K, H, inverse, coupling, h_t):
+    """fc_linear_rqs_apply (final layer + spline) against fp64 GEMM -> fp32 parameters -> element-wise kernel; the
+    yardstick is the same with the fp32 cuBLAS GEMM (the spline amplifies parameter noise, 1/slope in the inverse)."""
+    from flowconductor_b200 import linear as fl
+
+    g = torch.Generator(device=dev).manual_seed(M + D)
+    P = 3 * K - 1
+    tcols = torch.arange(0, D, 2, device=dev, dtype=torch.int32) if coupling else None
+    ccols = torch.arange(1, D, 2, device=dev, dtype=torch.int32) if coupling else None
+    d_t = D // 2 if coupling else D
+    x = torch.randn(M, D, generator=g, device=dev) * 1.5
+    hid = torch.randn(M, H, generator=g, device=dev)
+    w = torch.randn(d_t * P, H, generator=g, device=dev) * (4.0 / math.sqrt(H))
+    b = torch.randn(d_t * P, generator=g, device=dev)
+    pk = fl.pack(w, b, row_map=fl.grouped_row_map(d_t, P, fl.RQS_PPAD[K], dev), n_tile=fl.N_TILE_RQS)
+    cfg = _cabi.RqsConfig(K, _cabi.TAILS_LINEAR, 0, int(inverse), -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3,
+                          1.0 / math.sqrt(H))
+    y, lad = torch.empty_like(x), torch.empty(M, device=dev)
+    fl.linear_rqs(fl.T128.from_rows(hid) if h_t else hid, pk, x, y, lad, False, d_t, tcols, ccols, cfg, None)
+    args = (K, _cabi.TAILS_LINEAR, inverse, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0 / math.sqrt(H))
+    p64 = (hid.double() @ w.double().t() + b.double()).float()
+    y2, lad2, _ = ops.rqs_layer(x, p64, tcols, ccols, *args)
+    y3, lad3, _ = ops.rqs_layer(x, torch.nn.functional.linear(hid, w, b), tcols, ccols, *args)
+    if coupling:
+        assert torch.equal(y[:, 1::2], x[:, 1::2])
+    q = torch.tensor([0.5, 0.99, 1.0], device=dev)
+    for ours, ref, yard, slack in ((y, y2, y3, 3e-6), (lad, lad2, lad3, 3e-5)):
+        eo = torch.quantile((ours - ref).abs().flatten().float(), q)
+        ey = torch.quantile((yard - ref).abs().flatten().float(), q)
+        assert bool((eo <= 4 * ey + slack * max(1.0, ref.abs().max().item())).all()), (eo, ey)
+
+
+@pytest.mark.parametrize("layout,act,inverse,D,H", [
+    (_cabi.AFFINE_BLOCKED, _cabi.SCALE_SIGMOID2, False, 64, 256), (_cabi.AFFINE_BLOCKED, _cabi.SCALE_SOFTPLUS_CLAMP3, True, 10, 64),
+    (_cabi.AFFINE_INTERLEAVED, _cabi.SCALE_SOFTPLUS_EPS, False, 100, 64), (_cabi.AFFINE_INTERLEAVED, _cabi.SCALE_SOFTPLUS_EPS, True, 2, 64),
+])
+def test_linear_affine_fused_kernel(dev, layout, act, inverse, D, H):
+    from flowconductor_b200 import linear as fl
+
+    g = torch.Generator(device=dev).manual_seed(D)
+    M = 1500
+    blocked = layout == _cabi.AFFINE_BLOCKED
+    tcols = torch.arange(0, D, 2, device=dev, dtype=torch.int32) if blocked else None
+    ccols = torch.arange(1, D, 2, device=dev, dtype=torch.int32) if blocked else None
+    d_t = D // 2 if blocked else D
+    x = torch.randn(M, D, generator=g, device=dev)
+    hid = torch.randn(M, H, generator=g, device=dev)
+    w = torch.randn(2 * d_t, H, generator=g, device=dev) / math.sqrt(H)
+    b = torch.randn(2 * d_t, generator=g, device=dev) * 0.5
+    pk = fl.pack(w, b, row_map=fl.affine_row_map(d_t, layout, dev), n_tile=fl.N_TILE_AFFINE)
+    y, lad = torch.empty_like(x), torch.empty(M, device=dev)
+    fl.linear_affine(fl.T128.from_rows(hid), pk, x, y, lad, False, d_t, tcols, ccols, act, inverse)
+    p64 = (hid.double() @ w.double().t() + b.double()).float()
+    y2, lad2 = ops.affine_layer(x, p64, tcols, ccols, layout, act, inverse)
+    assert (y - y2).abs().max() < 2e-5 * max(1.0, y2.abs().max().item())
+    assert (lad - lad2).abs().max() < 2e-4
+
+
+def test_linear_argument_errors(dev):
+    """The C ABI returns FC_ERR_* (raised by _cabi.check) instead of launching on bad arguments."""
+    from flowconductor_b200 import linear as fl
+
+    w = torch.randn(64, 64, device=dev)
+    pk = fl.pack(w, None)
+    a = torch.randn(10, 64, device=dev)
+    with pytest.raises(ValueError):
+        fl.linear(torch.randn(10, 32, device=dev), pk)        # wrong reduction length
+    with pytest.raises(RuntimeError):
+        fl.linear(torch.randn(10, 65, device=dev)[:, :64], pk)  # row pitch not a multiple of 16 bytes (TMA operand)
+    with pytest.raises(RuntimeError):
+        fl.linear(a.cpu(), pk)                                  # no CPU path
+    out = fl.linear(a[:0], pk)                                  # empty batch: no launch, empty result
+    assert out.shape == (0, 64)
+    with pytest.raises(ValueError):
+        fl.T128(10, 20, dev)
+
+
 def test_tensorcore_path_variants_agree(dev, monkeypatch):
     """The tensor-core inference path with its optimisations switched off one at a time: in-place intermediates
     change nothing bit for bit; the T128 activation layout switches the hidden layers to the staged kernel, which adds
