@@ -469,31 +469,36 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         if (TS) {
           tc_fence_after();  // the slot's previous MMAs completed (empty -> TMA -> full): order the stores after them
           // one thread = one row (= its TMEM lane): read the row's BK raw values, split, store into the operand ring
-          static_assert(!TS || BK == 16, "TS converter is written for BK = 16");
+          static_assert(!TS || BK == 16 || BK == 32, "TS converter: 64- or 128-byte operand rows");
           const int r = (warp & 3) * 32 + lane;
-          float f[BK];
-#pragma unroll
-          for (int c = 0; c < BK / 4; ++c) {
-            // row-major tile: 64-byte rows, 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3) (TMA 64B swizzle)
-            // T128 tile     : [BK/4 column groups][128 rows][16 B]
-            const uint32_t off = la.a_tiled ? (uint32_t)(c * kBM * 16 + r * 16)
-                                            : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-            const float4 t = lds128(st + off);
-            f[4 * c + 0] = t.x;
-            f[4 * c + 1] = t.y;
-            f[4 * c + 2] = t.z;
-            f[4 * c + 3] = t.w;
-          }
-          uint32_t hi[BK], lo[BK];
-#pragma unroll
-          for (int i = 0; i < BK; ++i) {
-            const float a = relu ? fmaxf(f[i], 0.f) : f[i];
-            hi[i] = to_tf32(a);
-            lo[i] = to_tf32(a - __uint_as_float(hi[i]));
-          }
           const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemA0 + (uint32_t)(s * 2 * BK);
-          tmem_st16(ta, hi);
-          tmem_st16(ta + BK, lo);
+#pragma unroll
+          for (int h = 0; h < BK / 16; ++h) {  // 16 k-values at a time
+            float f[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int cc = h * 4 + c;  // 16-byte chunk of the row
+              // row-major tile: BK*4-byte rows, chunk cc of row r sits at chunk cc ^ swz(r) (TMA 64B / 128B swizzle)
+              // T128 tile     : [BK/4 column groups][128 rows][16 B]
+              const int swz = BK == 16 ? ((r >> 1) & 3) : (r & 7);
+              const uint32_t off = la.a_tiled ? (uint32_t)(cc * kBM * 16 + r * 16)
+                                              : (uint32_t)(r * (BK * 4) + ((cc ^ swz) << 4));
+              const float4 t = lds128(st + off);
+              f[4 * c + 0] = t.x;
+              f[4 * c + 1] = t.y;
+              f[4 * c + 2] = t.z;
+              f[4 * c + 3] = t.w;
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = relu ? fmaxf(f[i], 0.f) : f[i];
+              hi[i] = to_tf32(a);
+              lo[i] = to_tf32(a - __uint_as_float(hi[i]));
+            }
+            tmem_st16(ta + (uint32_t)(h * 16), hi);
+            tmem_st16(ta + (uint32_t)(BK + h * 16), lo);
+          }
           tmem_wait_st();
           tc_fence_before();
         } else if (!(la.debug & 1))
@@ -973,6 +978,15 @@ static int pair_mma() {
   return v != 0;
 }
 
+// 32 k-values per ring slot in the staged pair kernel (FC_LINEAR_BK32=0: 16)
+static int wide_slots() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_BK32");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 // T128 outputs through the staged-store kernel (FC_LINEAR_STAGED=0: direct stores from the epilogue warps)
 static int staged_store() {
   static int v = [] {
@@ -1044,6 +1058,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
 }
 
 static int check_operand(const float* A, int64_t lda, int64_t M, int K, const fc_linear_weights* w, int a_tiled) {
+  if (M == 0 && w && K > 0) return FC_OK;  // empty batch: nothing to read (the pointer may be null)
   if (!A || !w || !w->w || !w->bias || M < 0 || K <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (M >= (int64_t)1 << 31) return FC_ERR_UNSUPPORTED;
   if (K > w->k_pad) return FC_ERR_INVALID_ARGUMENT;
@@ -1105,6 +1120,7 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0, o_tiled = (layouts & FC_LINEAR_OUT_T128) != 0;
   int rc = check_operand(A, lda, M, K, w, a_tiled);
   if (rc != FC_OK) return rc;
+  if (M == 0) return FC_OK;  // empty batch (null data pointers are fine)
   if (!out || n_out <= 0 || n_out > w->n_pad) return FC_ERR_INVALID_ARGUMENT;
   if ((n_out & 3) || (ldo & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return FC_ERR_UNSUPPORTED;
   if (residual && ((ldr & 3) || (reinterpret_cast<uintptr_t>(residual) & 15))) return FC_ERR_UNSUPPORTED;
@@ -1125,6 +1141,9 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   if (o_tiled && staged_store() && n_out % 128 == 0 && (n_out == ldo) && (!residual || ldr == n_out)) {
     // T128 output in whole 128-wide tiles: staged kernel (operand in TMEM, TMA bulk in / out)
     la.num_n_tiles = n_out / 128;
+    // (short reductions keep 16-value slots: their partial accumulators are drained every 16 k-values)
+    if (pair_mma() && wide_slots() && K > 64)
+      return launch_linear<3, 128, 32, 4, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
     if (pair_mma()) return launch_linear<3, 128, 16, 8, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
     return launch_linear<3, 128, 16, 6, 0, 32, 1, 8, true>(A, lda, M, K, w, la, se, re, st);
   }
@@ -1142,6 +1161,7 @@ extern "C" int fc_linear_rqs_apply(const float* hidden, int64_t ldh, int64_t B, 
   const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0;
   rc = check_operand(hidden, ldh, B, H, w, a_tiled);
   if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
   if (!x || !y || !logabsdet || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
   if (c.tails != FC_TAILS_LINEAR) return FC_ERR_UNSUPPORTED;  // fused epilogue: linear tails (P = 3K-1) only
@@ -1181,6 +1201,7 @@ extern "C" int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t 
   const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0;
   int rc = check_operand(hidden, ldh, B, H, w, a_tiled);
   if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
   if (!x || !y || !logabsdet || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
   if (activation < FC_SCALE_SIGMOID2 || activation > FC_SCALE_SOFTPLUS_EPS) return FC_ERR_INVALID_ARGUMENT;
