@@ -43,11 +43,12 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     nvcc = _nvcc()
+    extra = ["-DFC_LINEAR_PROFILE=1"] if os.environ.get("FC_LINEAR_PROFILE_BUILD") == "1" else []
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             subprocess.check_call(cmd)

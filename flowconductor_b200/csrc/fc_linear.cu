@@ -107,7 +107,12 @@ struct LinSmem {
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep 1024-byte alignment");
 };
 
-// experiments only (FC_LINEAR_DEBUG & 4): cycles the MMA-issuing thread / one epilogue warp of CTA 0 spend waiting
+// Experiments only: cycles the MMA-issuing thread / one epilogue warp of CTA 0 spend waiting (FC_LINEAR_DEBUG & 4).
+// The counters cost registers in the hot loops, so they are compiled in only with -DFC_LINEAR_PROFILE=1
+// (FC_LINEAR_PROFILE_BUILD=1 python -m flowconductor_b200.build --force); otherwise the record stays zero.
+#ifndef FC_LINEAR_PROFILE
+#define FC_LINEAR_PROFILE 0
+#endif
 __device__ unsigned long long g_lin_prof[16];
 
 template <int N>
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         constexpr uint32_t idesc = make_idesc_tf32(kBM * CTAS, BN);
         int s = 0, acc = 0;
         uint32_t ph = 0, aph = 0;
-        const bool prof = (la.debug & 4) && blockIdx.x == 0;
+        const bool prof = FC_LINEAR_PROFILE && (la.debug & 4) && blockIdx.x == 0;
         long long t_tempty = 0, t_conv = 0, t_ready = 0, t_stages = 0;
         const long long t_begin = clock64();
         // descriptors of ring slot 0; slot s adds s * STAGE_BYTES to the 16-byte-granular address field
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
     uint32_t aph = 0;
     unsigned status = 0;
     int parity = 0;
-    const bool eprof = (la.debug & 4) && blockIdx.x == 0 && warp == kEpiWarp0;
+    const bool eprof = FC_LINEAR_PROFILE && (la.debug & 4) && blockIdx.x == 0 && warp == kEpiWarp0;
     long long e_init = 0, e_wait = 0, e_drain = 0, e_final = 0, e_t = 0;
     const long long e_begin = clock64();
     for (int mp = unit0; mp < n_units; mp += unit_step) {
