@@ -237,4 +237,171 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
   return 1;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Backward on the same per-warp ring.  A slot holds the parameters, the inputs and the upstream gradients of a few
+// consecutive rows (three 1-D TMA bulk loads).  The element adjoint writes the P parameter gradients OVER the
+// parameters in the slot and the input gradient over the inputs; the two finished blocks leave with two TMA bulk
+// stores (cp.async.bulk.global.shared::cta), so the warp issues no global load / store of its own except the per-row
+// grad_logabsdet scalar.  HBM traffic = algorithmic: x, params, grad_y read once; grad_x, grad_params written once.
+// ------------------------------------------------------------------------------------------------------------
+struct PipeBwdArgs {
+  LayerBwdArgs a;
+  int D;
+  int slot_rows, stages, warps;
+};
+
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <class Op>
+__global__ void __launch_bounds__(512) pipelined_backward_kernel(const PipeBwdArgs pa, const Op op) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const LayerBwdArgs& a = pa.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = a.seg, rpw = 32 / seg;
+  const int sub = lane / seg, j0 = lane % seg;
+  const int P = op.P();
+  const int D = pa.D, D_t = a.D_t, S = pa.stages, R = pa.slot_rows;
+  const int row_floats = D_t * P;
+  const int slot_floats = R * (row_floats + 2 * D);
+  const int32_t* __restrict__ tcols = a.tcols;
+  const int32_t* __restrict__ ccols = a.ccols;
+
+  float* const wslots = reinterpret_cast<float*>(smem_raw) + warp * S * slot_floats;
+  const uint32_t wslots_s = smem_u32(wslots);
+  const uint32_t bars_s =
+      smem_u32(smem_raw + (size_t)pa.warps * S * slot_floats * sizeof(float)) + (uint32_t)warp * S * 8u;
+  const uint32_t slot_bytes = (uint32_t)slot_floats * 4u;
+  const uint32_t xoff_bytes = (uint32_t)R * row_floats * 4u;       // inputs behind the parameters,
+  const uint32_t goff_bytes = xoff_bytes + (uint32_t)R * D * 4u;   // upstream gradients behind the inputs
+
+  const int64_t gstride = (int64_t)gridDim.x * pa.warps;
+  const int64_t g0 = (int64_t)blockIdx.x * pa.warps + warp;
+  const int64_t B = a.B;
+  int64_t fetch_row = g0 * R;
+  const int64_t row_step = gstride * R;
+
+  auto issue = [&](int slot) {  // lane 0 only
+    const int rows = (int)min((int64_t)R, B - fetch_row);
+    const uint32_t dst = wslots_s + (uint32_t)slot * slot_bytes;
+    const uint32_t bar = bars_s + (uint32_t)slot * 8u;
+    const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
+    mbar_expect_tx(bar, pbytes + 2 * xbytes);
+    bulk_g2s(dst, a.params + fetch_row * row_floats, pbytes, bar);
+    bulk_g2s(dst + xoff_bytes, a.x + fetch_row * D, xbytes, bar);
+    bulk_g2s(dst + goff_bytes, a.gy + fetch_row * D, xbytes, bar);
+    fetch_row += row_step;
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(bars_s + (uint32_t)s * 8u, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+    for (int s = 0; s < S; ++s)
+      if (fetch_row < B) issue(s);
+  }
+  __syncwarp();
+
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int64_t row0 = g0 * R; row0 < B; row0 += row_step) {
+    mbar_wait(bars_s + (uint32_t)slot * 8u, parity);
+    const int rows = (int)min((int64_t)R, B - row0);
+    float* sp = wslots + slot * slot_floats;
+    float* sx = sp + R * row_floats;
+    const float* sg = sx + R * D;
+    for (int r = sub; r < rows + sub; r += rpw) {  // uniform trip count
+      if (r < rows) {
+        float* xrow = sx + r * D;
+        const float* grow = sg + r * D;
+        const float gl = a.gl ? __ldg(a.gl + row0 + r) : 0.f;
+        for (int j = j0; j < D_t; j += seg) {
+          const int col = tcols ? __ldg(tcols + j) : j;
+          float* pj = sp + r * row_floats + j * P;
+          float gxv;
+          op.backward(xrow[col], pj, grow[col], gl, gxv, pj);  // parameter gradients overwrite the parameters
+          xrow[col] = gxv;                                      // input gradient overwrites the input
+        }
+        for (int i = j0; i < a.n_copy; i += seg) {  // identity columns: grad_x = grad_y
+          const int col = __ldg(ccols + i);
+          xrow[col] = grow[col];
+        }
+      }
+    }
+    fence_proxy_async();  // the bulk stores read the slot through the async proxy
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(a.gp + row0 * row_floats, wslots_s + (uint32_t)slot * slot_bytes, (uint32_t)(rows * row_floats) * 4u);
+      bulk_s2g(a.gx + row0 * D, wslots_s + (uint32_t)slot * slot_bytes + xoff_bytes, (uint32_t)(rows * D) * 4u);
+      bulk_commit();
+      if (fetch_row < B) {
+        bulk_wait_read0();  // the stores have read the slot: it may be refilled
+        issue(slot);
+      }
+    }
+    __syncwarp();
+    if (++slot == S) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait_all0();  // global writes complete before the kernel ends
+}
+
+// Try the pipelined backward kernel; returns 1 if it was launched, 0 if the call does not qualify, <0 on error.
+template <class Op>
+inline int try_launch_pipelined_backward(const LayerBwdArgs& a, const Op& op, int P, int D, cudaStream_t st) {
+  if (env_int("FC_PIPE", 1) == 0 || env_int("FC_PIPE_BWD", 1) == 0) return 0;
+  const int64_t row_floats = (int64_t)a.D_t * P;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a.params) | reinterpret_cast<uintptr_t>(a.x) |
+                         reinterpret_cast<uintptr_t>(a.gy) | reinterpret_cast<uintptr_t>(a.gx) |
+                         reinterpret_cast<uintptr_t>(a.gp)) & 15) == 0;
+  if (!aligned || a.p_stride != row_floats || a.gp_stride != row_floats || a.x_stride != D || a.gy_stride != D ||
+      a.gx_stride != D)
+    return 0;
+  if (a.D_t + a.n_copy != D) return 0;  // whole rows are streamed: the column lists must cover the row
+  if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
+  const DeviceInfo& dev = device_info();
+  const LaneMap lm = lane_map(a.D_t);
+  const int64_t row_bytes = (row_floats + 2 * D) * 4;
+  int slot_rows = lm.rows_per_warp;
+  const int target = env_int("FC_PIPE_BWD_SLOT_BYTES", 4096);
+  while ((int64_t)(slot_rows * 2) * row_bytes <= target) slot_rows *= 2;
+  int stages = env_int("FC_PIPE_BWD_STAGES", 2);
+  int warps = env_int("FC_PIPE_BWD_WARPS", 16);
+  int ctas_per_sm = env_int("FC_PIPE_BWD_CTAS", 2);
+  const int64_t slot_bytes = slot_rows * row_bytes;
+  if (slot_bytes > 96 * 1024) return 0;
+  auto smem_need = [&](int w, int s) { return (int64_t)w * s * (slot_bytes + 8) + 128; };
+  const int64_t sm_budget = 224 * 1024;
+  while ((int64_t)ctas_per_sm * (smem_need(warps, stages) + 1024) > sm_budget) {
+    if (stages > 2) --stages;
+    else if (warps > 8) --warps;
+    else if (ctas_per_sm > 1) --ctas_per_sm;
+    else if (warps > 1) --warps;
+    else return 0;
+  }
+  PipeBwdArgs pa;
+  pa.a = a;
+  pa.a.seg = lm.seg;
+  pa.D = D;
+  pa.slot_rows = slot_rows;
+  pa.stages = stages;
+  pa.warps = warps;
+  const size_t smem = (size_t)smem_need(warps, stages);
+  const int64_t groups = (a.B + slot_rows - 1) / slot_rows;
+  int64_t grid = (int64_t)dev.sm_count * ctas_per_sm;
+  const int64_t need = (groups + warps - 1) / warps;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  if (prepare_kernel(pipelined_backward_kernel<Op>, smem) != FC_OK) return FC_ERR_CUDA;
+  pipelined_backward_kernel<Op><<<(int)grid, warps * 32, smem, st>>>(pa, op);
+  if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  return 1;
+}
+
 }  // namespace fc

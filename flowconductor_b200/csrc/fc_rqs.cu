@@ -90,6 +90,8 @@ extern "C" int fc_rqs_backward(const float* x, int64_t x_row_stride, const float
   {                                                                     \
     RqsOp<KC> op;                                                       \
     op.c = c;                                                           \
+    const int piped = try_launch_pipelined_backward(a, op, c.P, (int)x_row_stride, (cudaStream_t)stream); \
+    if (piped != 0) return piped < 0 ? piped : FC_OK;                   \
     return launch_backward(a, op, smem, (cudaStream_t)stream);          \
   }
   FC_DISPATCH_K(c.K, CALL)

@@ -84,5 +84,7 @@ extern "C" int fc_sos_backward(const float* x, int64_t x_row_stride, const float
   SosOp op;
   op.n = n_sigmoids; op.offset = 0.f; op.inverse = 0; op.iters = 0; op.lim = 0.f;
   const size_t smem = plan_tiles(a, 3 * n_sigmoids + 1);
+  const int piped = try_launch_pipelined_backward(a, op, 3 * n_sigmoids + 1, (int)x_row_stride, (cudaStream_t)stream);
+  if (piped != 0) return piped < 0 ? piped : FC_OK;
   return launch_backward(a, op, smem, (cudaStream_t)stream);
 }

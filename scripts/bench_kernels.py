@@ -82,6 +82,27 @@ def main():
         set_env()
         y1, l1, _ = ops.rqs_layer(*a)
         print("  bit-identical:", bool(torch.equal(y0, y1) and torch.equal(l0, l1)), flush=True)
+    # backward (fc_rqs_backward): x, params, grad_y, grad_lad in; grad_x, grad_params out
+    for name, (a, _) in (cases[0], cases[3]):
+        x, p, tc, cc = a[:4]
+        rest = a[4:]
+        gy = torch.randn_like(x)
+        gl = torch.randn(x.shape[0], device=x.device)
+        nbytes = x.shape[0] * (2 * 4 * p.shape[1] + 3 * 4 * x.shape[1] + 4)
+        res = {}
+        for label, env in (("staged", {"FC_PIPE_BWD": 0}), ("pipelined", {})):
+            set_env(**env)
+            os.environ.pop("FC_PIPE_BWD", None)
+            for k, v in env.items():
+                os.environ[k] = str(v)
+            med, best = timeit(lambda: ops.rqs_layer_backward(x, p, gy, gl, tc, cc, *rest))
+            res[label] = ops.rqs_layer_backward(x, p, gy, gl, tc, cc, *rest)
+            gbs = nbytes / med / 1e6
+            rec = {"kernel": name.replace("rqs_fwd", "rqs_bwd"), "variant": label, "ms_median": med, "ms_best": best,
+                   "GB/s": gbs, "frac_of_measured_peak": gbs / PEAK, "bytes": nbytes}
+            print(json.dumps(rec), flush=True)
+        os.environ.pop("FC_PIPE_BWD", None)
+        print("  bit-identical:", all(bool(torch.equal(u, v)) for u, v in zip(res["staged"], res["pipelined"])), flush=True)
     if args.sweep:
         a, nbytes = cases[0][1]
         best = None
