@@ -5,7 +5,7 @@
 // _inverse (transforms/autoregressive/autoregressive.py:97-129, interleaved [raw_scale, shift] pairs) and
 // StandardNormal._log_prob + the final add of Flow._log_prob (distributions/normal.py:23-33,
 // flows/base.py:48).  16 B/element of traffic: no staging needed, one lane per feature, shuffle log-det.
-#include "fc_staged.cuh"
+#include "fc_pipeline.cuh"
 
 namespace fc {
 
@@ -32,6 +32,87 @@ __device__ __forceinline__ void affine_fetch(const AffineArgs& a, const float* p
   } else {
     raw = prow[2 * j];
     shift = prow[2 * j + 1];
+  }
+}
+
+// Op for the per-warp TMA ring of fc_pipeline.cuh (contiguous rows whose column lists cover the row): parameters
+// per feature are (raw scale, shift) pairs (interleaved) or prow[0] = shift, prow[D_t] = raw scale (blocked).
+struct AffineOp {
+  int D_t, layout, activation, inverse;
+  __device__ __forceinline__ int P() const { return 2; }
+  __device__ __forceinline__ int feature_stride() const { return layout == FC_AFFINE_BLOCKED ? 1 : 2; }
+  __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned&) const {
+    const float raw = layout == FC_AFFINE_BLOCKED ? p[D_t] : p[0];
+    const float shift = layout == FC_AFFINE_BLOCKED ? p[0] : p[1];
+    affine_eval(x, raw, shift, activation, inverse, y, lad);
+  }
+};
+
+// Forward / inverse, general path.  16 B per element and almost no arithmetic: the kernel lives on loads in flight, so every warp
+// handles kU consecutive row groups per step and issues all of their loads (x, raw scale, shift, identity columns)
+// before the first dependent instruction.
+constexpr int kAffineUnroll = 4;
+
+__global__ void __launch_bounds__(kThreads) affine_forward_kernel(const AffineArgs a) {
+  constexpr int kU = kAffineUnroll;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = a.seg, rpw = 32 / seg;
+  const int sub = lane / seg, j0 = lane % seg;
+  const int64_t groups = (a.B + rpw - 1) / rpw;
+  const int64_t steps = (groups + kU - 1) / kU;
+  for (int64_t st = (int64_t)blockIdx.x * kWarps + warp; st < steps; st += (int64_t)gridDim.x * kWarps) {
+    int64_t row[kU];
+    bool ok[kU];
+    float lad_acc[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      row[u] = (st * kU + u) * rpw + sub;
+      ok[u] = row[u] < a.B;
+      lad_acc[u] = 0.f;
+    }
+    for (int j = j0; j < a.D_t; j += seg) {
+      const int col = a.tcols ? __ldg(a.tcols + j) : j;
+      float xv[kU], raw[kU], shift[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (ok[u]) {
+          xv[u] = __ldcs(a.x + row[u] * a.x_stride + col);
+          const float* prow = a.params + row[u] * a.p_stride;
+          if (a.layout == FC_AFFINE_BLOCKED) {
+            shift[u] = __ldcs(prow + j);
+            raw[u] = __ldcs(prow + a.D_t + j);
+          } else {
+            const float2 rs = __ldcs(reinterpret_cast<const float2*>(prow) + j);
+            raw[u] = rs.x;
+            shift[u] = rs.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (ok[u]) {
+          float yv, lv;
+          affine_eval(xv[u], raw[u], shift[u], a.activation, a.inverse, yv, lv);
+          __stcs(a.y + row[u] * a.y_stride + col, yv);
+          lad_acc[u] += lv;
+        }
+      }
+    }
+    for (int i = j0; i < a.n_copy; i += seg) {  // identity columns
+      const int col = __ldg(a.ccols + i);
+      float v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (ok[u]) v[u] = __ldcs(a.x + row[u] * a.x_stride + col);
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (ok[u]) __stcs(a.y + row[u] * a.y_stride + col, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const float tot = seg_reduce_sum(lad_acc[u], seg);
+      if (ok[u] && j0 == 0) a.lad[row[u]] = a.accumulate ? a.lad[row[u]] + tot : tot;
+    }
   }
 }
 
@@ -136,7 +217,24 @@ extern "C" int fc_affine_apply(const float* x, int64_t x_row_stride, const float
   a.B = B; a.D_t = D_t; a.n_copy = ccols.n; a.tcols = tcols.idx; a.ccols = ccols.idx;
   a.accumulate = accumulate_logabsdet; a.layout = layout; a.activation = activation; a.inverse = inverse;
   a.seg = lane_map(D_t).seg;
-  affine_kernel<false><<<affine_grid(B, a.seg), kThreads, 0, (cudaStream_t)stream>>>(a);
+  {  // fast path: whole contiguous rows through the per-warp TMA ring
+    LayerArgs la = {};
+    la.x = x; la.params = params; la.y = y; la.lad = logabsdet; la.status = nullptr;
+    la.x_stride = x_row_stride; la.p_stride = params_row_stride; la.y_stride = y_row_stride;
+    la.B = B; la.D_t = D_t; la.n_copy = ccols.n; la.tcols = tcols.idx; la.ccols = ccols.idx;
+    la.accumulate = accumulate_logabsdet;
+    AffineOp op = {D_t, layout, activation, inverse};
+    const int piped = try_launch_pipelined(la, op, 2, (int)x_row_stride, (cudaStream_t)stream);
+    if (piped != 0) return piped < 0 ? piped : FC_OK;
+  }
+  // interleaved (raw, shift) pairs are read as float2: the parameter rows must keep 8-byte alignment
+  const bool pairs_ok = layout == FC_AFFINE_BLOCKED ||
+                        ((reinterpret_cast<uintptr_t>(params) & 7) == 0 && (params_row_stride & 1) == 0);
+  if (pairs_ok) {
+    affine_forward_kernel<<<affine_grid((B + kAffineUnroll - 1) / kAffineUnroll, a.seg), kThreads, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    affine_kernel<false><<<affine_grid(B, a.seg), kThreads, 0, (cudaStream_t)stream>>>(a);
+  }
   FC_CHECK_LAUNCH();
   return FC_OK;
 }

@@ -60,6 +60,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// Words between the parameter blocks of two neighbouring features: P for the spline / sum-of-sigmoids layouts; an
+// Op may override it (blocked affine parameters [shift(D_t) | raw_scale(D_t)]: 1, the Op reads prow[0] and prow[D_t]).
+template <class Op>
+__device__ __forceinline__ auto feature_stride(const Op& op, int) -> decltype(op.feature_stride()) {
+  return op.feature_stride();
+}
+template <class Op>
+__device__ __forceinline__ int feature_stride(const Op& op, long) {
+  return op.P();
+}
+
 // kSimple: D_t == 32 (one feature per lane, one row per warp pass): the feature loop and the segment logic fold away.
 template <class Op, bool kSimple>
 __global__ void __launch_bounds__(512) pipelined_apply_kernel(const PipeArgs pa, const Op op) {
@@ -130,8 +141,9 @@ __global__ void __launch_bounds__(512) pipelined_apply_kernel(const PipeArgs pa,
     const float* sp = wslots + slot * slot_floats;
     float* sx = wslots + slot * slot_floats + R * row_floats;
     float* xrow = sx + sub * D;                       // strength-reduced row pointers
-    const float* prow = sp + sub * row_floats + j0 * P;
-    const int xstep = rpw * D, pstep = rpw * row_floats, jstep = seg * P;
+    const int fstride = feature_stride(op, 0);
+    const float* prow = sp + sub * row_floats + j0 * fstride;
+    const int xstep = rpw * D, pstep = rpw * row_floats, jstep = seg * fstride;
     for (int r = sub; r < rows + sub; r += rpw, xrow += xstep, prow += pstep) {  // uniform trip count
       const bool row_ok = r < rows;
       float lad_acc = 0.f;
@@ -194,14 +206,16 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
   const DeviceInfo& dev = device_info();
   const LaneMap lm = lane_map(a.D_t);
   const int64_t row_bytes = (row_floats + D) * 4;
-  // slot: about 6 KB, at least one pass of the warp
+  // slot: at least one pass of the warp; short rows (affine: 512 B) are grouped up to ~2 KB — small slots keep the
+  // shared-memory footprint low enough for 2-3 CTAs of 16 warps per SM, which is what hides the latency (measured on
+  // affine coupling rows: 2 KB slots 85 % of the copy peak, 4 KB 68 %, 8 KB 63 %)
   int slot_rows = lm.rows_per_warp;
-  const int target = env_int("FC_PIPE_SLOT_BYTES", 4096);
+  const int target = env_int("FC_PIPE_SLOT_BYTES", 2048);
   while ((int64_t)(slot_rows * 2) * row_bytes <= target) slot_rows *= 2;
   slot_rows = env_int("FC_PIPE_SLOT_ROWS", slot_rows);
   int stages = env_int("FC_PIPE_STAGES", 2);
   int warps = env_int("FC_PIPE_WARPS", 16);
-  int ctas_per_sm = env_int("FC_PIPE_CTAS", 2);
+  int ctas_per_sm = env_int("FC_PIPE_CTAS", slot_rows * row_bytes <= 2048 ? 3 : 2);
   const int64_t slot_bytes = slot_rows * row_bytes;
   if (slot_bytes > 96 * 1024) return 0;  // rows too long for a per-warp ring
   auto smem_need = [&](int w, int s) { return (int64_t)w * s * (slot_bytes + 8) + 128; };

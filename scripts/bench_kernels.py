@@ -61,6 +61,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--B", type=int, default=1 << 20)
+    ap.add_argument("--sweep-case", type=int, default=0)
     args = ap.parse_args()
     out = []
     cases = [("rqs_fwd cfg2 D=64 K=8 coupling", rqs_case(args.B, 64, 8)),
@@ -103,8 +104,32 @@ def main():
             print(json.dumps(rec), flush=True)
         os.environ.pop("FC_PIPE_BWD", None)
         print("  bit-identical:", all(bool(torch.equal(u, v)) for u, v in zip(res["staged"], res["pipelined"])), flush=True)
+    # sum-of-sigmoids (cfg 4 shapes: D = 32, n = 10, P = 31) forward / inverse / backward, affine coupling (16 B/element)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(1)
+    Bs, Ds, ns = args.B, 32, 10
+    xs = torch.randn(Bs, Ds, generator=g, device=dev)
+    ps = torch.randn(Bs, Ds * (3 * ns + 1), generator=g, device=dev)
+    gys, gls = torch.randn_like(xs), torch.randn(Bs, device=dev)
+    set_env()
+    for name, fn, nbytes in (
+            ("sos_fwd cfg4 D=32 n=10", lambda: ops.sos_layer(xs, ps, ns, 0.0, False, 50, 120.0), Bs * (4 * ps.shape[1] + 8 * Ds + 4)),
+            ("sos_inv cfg4 D=32 n=10 (bisection + Newton)", lambda: ops.sos_layer(xs, ps, ns, 0.0, True, 50, 120.0), Bs * (4 * ps.shape[1] + 8 * Ds + 4)),
+            ("sos_bwd cfg4 D=32 n=10", lambda: ops.sos_layer_backward(xs, ps, gys, gls, ns), Bs * (8 * ps.shape[1] + 12 * Ds + 4))):
+        med, best = timeit(fn)
+        gbs = nbytes / med / 1e6
+        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best, "GB/s": gbs,
+                          "frac_of_measured_peak": gbs / PEAK, "bytes": nbytes}), flush=True)
+    xa = torch.randn(args.B * 4, 64, generator=g, device=dev)
+    pa = torch.randn(args.B * 4, 64, generator=g, device=dev)
+    tca = torch.arange(0, 64, 2, dtype=torch.int32, device=dev)
+    cca = torch.arange(1, 64, 2, dtype=torch.int32, device=dev)
+    med, best = timeit(lambda: ops.affine_layer(xa, pa, tca, cca, _cabi.AFFINE_BLOCKED, _cabi.SCALE_SIGMOID2, False))
+    nbytes = xa.shape[0] * (4 * 64 + 4 * 64 + 4 * 64 + 4)
+    print(json.dumps({"kernel": "affine_fwd coupling D=64 (4M rows)", "variant": "pipelined", "ms_median": med, "ms_best": best,
+                      "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK, "bytes": nbytes}), flush=True)
     if args.sweep:
-        a, nbytes = cases[0][1]
+        a, nbytes = cases[args.sweep_case][1]
         best = None
         for warps, stages, ctas, slot in itertools.product((8, 12, 16), (2, 3, 4), (1, 2), (1, 2, 4)):
             set_env(FC_PIPE_WARPS=warps, FC_PIPE_STAGES=stages, FC_PIPE_CTAS=ctas, FC_PIPE_SLOT_ROWS=slot)
