@@ -613,65 +613,113 @@ FC_HD float logaddexpf_(float a, float b) {
   return m + log1pf(expf(-fabsf(a - b)));
 }
 
+// Fast building blocks of the sum-of-sigmoids hot path.  With full-range expf / tanhf / IEEE divisions one element
+// (n = 10) costs ~2000 instructions and the kernel sits at 29 % of the HBM roofline; these keep it near 600.
+//   fc_sigmoid_parts: E = 2^(-|z| log2e) (ex2.approx), r = 1/(1+E): sigma(z), sigma'(z) = E r^2.  The argument
+//     rounding (|z| 1.44 * 2^-24) is a RELATIVE error |z| 8.6e-8 of E, i.e. an absolute error of sigma below
+//     |z| e^-|z| 8.6e-8 <= 3.2e-8.
+//   fc_tanh: sign(t) (1-E)/(1+E), E = e^(-2|t|), switched to the odd Taylor polynomial below |t| = 0.3 where 1-E
+//     would cancel (5 terms: truncation < 2e-8 relative at 0.3).
+FC_HD void fc_sigmoid_parts(float z, float& sig, float& dsig) {
+  const float E = fc_exp2(-fabsf(z) * FC_LOG2E);
+  const float r = fc_rcp(1.f + E);
+  const float Er = E * r;
+  sig = z >= 0.f ? r : Er;
+  dsig = Er * r;
+}
+
+FC_HD float fc_tanh(float t) {
+  const float at = fabsf(t);
+  const float E = fc_exp2(at * (-2.f * FC_LOG2E));
+  const float big = (1.f - E) * fc_rcp(1.f + E);
+  const float t2 = t * t;
+  float poly = fmaf(t2, 62.f / 2835.f, -17.f / 315.f);
+  poly = fmaf(t2, poly, 2.f / 15.f);
+  poly = fmaf(t2, poly, -1.f / 3.f);
+  poly = fmaf(t2 * at, poly, at);  // |t| (1 - t^2/3 + 2 t^4/15 - 17 t^6/315 + 62 t^8/2835)
+  const float m = at < 0.3f ? poly : big;
+  return t < 0.f ? -m : m;
+}
+
+// softplus(z) = max(z, 0) + log1p(e^-|z|)   (torch threshold rule reproduced as in softplus_beta)
+FC_HD float fc_softplus1(float z) { return fmaxf(z, 0.f) + fc_log1p_unit(fc_exp2(-fabsf(z) * FC_LOG2E)); }
+
 // Forward for one element.  raw -> [shift_raw(n) | log_scale_raw(n) | softmax_raw(n) | esp_raw].
 // Returns y (without wrapper offset) and the per-element log-derivative.
-FC_HD void sos_eval(float x, const float* raw, int n, float& y, float& logj) {
-  // softmax weights + eps, renormalised (adaptive_sigmoids.py:133-135)
+// The Jacobian is accumulated in the LINEAR domain,  J = sum_j w_j a_j sigma'(pre_j) + sigma(x - s) + sigma(-x - s)
+// (the derivative of the extended softplus written out), and logj = log J; the reference's log-domain composition
+// (logsumexp :124-130, logaddexp :116, nonlinearities.py:543-552) is the same number and is only used as the fallback
+// when J underflows.
+// NC > 0: compile-time sigmoid count (loops fully unrolled, parameter reads at immediate offsets); NC = 0: runtime n.
+template <int NC>
+FC_HD void sos_eval_t(float x, const float* raw, int n_runtime, float& y, float& logj) {
+  const int n = NC ? NC : n_runtime;
+  // softmax weights + eps, renormalised (adaptive_sigmoids.py:133-135); the numerators are cheap enough (one FMA +
+  // one ex2) to be recomputed per pass instead of kept in a register array of runtime length
   const float* sm = raw + 2 * n;
   float m = -INFINITY;
+#pragma unroll(NC ? NC : 4)
   for (int j = 0; j < n; ++j) m = fmaxf(m, sm[j]);
+  const float ml2 = m * FC_LOG2E;
   float se = 0.f;
-  for (int j = 0; j < n; ++j) se += expf(sm[j] - m);
-  const float inv_se = 1.f / se;
+#pragma unroll(NC ? NC : 4)
+  for (int j = 0; j < n; ++j) se += fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2));
+  const float inv_se = fc_rcp(se);
   float wsum = 0.f;
-  for (int j = 0; j < n; ++j) wsum += expf(sm[j] - m) * inv_se + 1e-6f;
-  const float inv_wsum = 1.f / wsum;
+#pragma unroll(NC ? NC : 4)
+  for (int j = 0; j < n; ++j) wsum += fmaf(fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)), inv_se, 1e-6f);
+  const float inv_wsum = fc_rcp(wsum);
 
   float ysum = 0.f, wtot = 0.f, jac = 0.f;
+#pragma unroll(NC ? NC : 2)
+  for (int j = 0; j < n; ++j) {  // several sigmoids in flight: the chain ex2 -> rcp -> ... of one is ~100 cycles long
+    const float w = fmaf(fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)), inv_se, 1e-6f) * inv_wsum;
+    float sa, dsa;
+    fc_sigmoid_parts(raw[n + j], sa, dsa);
+    const float a = fmaf(sa, 10.f - 0.1f, 0.1f);  // :137-138
+    const float sh = fc_tanh(raw[j]) * 10.f;      // :140
+    const float pre = a * (x - sh);
+    float sig, dsig;
+    fc_sigmoid_parts(pre, sig, dsig);
+    ysum = fmaf(w, sig, ysum);
+    wtot += w;
+    jac = fmaf(w * a, dsig, jac);
+  }
+  const float y_sig = ysum * fc_rcp(wtot);  // :127
+  // extended softplus (nonlinearities.py:519-520, 543-552)
+  const float s = fc_softplus1(raw[3 * n]) + 0.1f;
+  const float y_esp = fc_softplus1(x - s) - fc_softplus1(-(x + s));
+  float s1, s2, unused;
+  fc_sigmoid_parts(x - s, s1, unused);
+  fc_sigmoid_parts(-(x + s), s2, unused);
+  y = y_sig + y_esp;
+  const float J = jac + (s1 + s2);
+  if (J > 1e-30f) {
+    logj = fc_log_deriv(J);
+    return;
+  }
+  // everything is saturated: redo the reduction in the log domain exactly as the reference composes it
+  const float lj_esp = logaddexpf_(x - logaddexpf_(s, x), -softplus1(s + x));
+  float acc = 0.f;
+  float mx = -INFINITY;
   for (int j = 0; j < n; ++j) {
     const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
-    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;  // :137-138
-    const float sh = tanhf(raw[j]) * 10.f;                          // :140
-    const float pre = a * (x - sh);
-    const float E = expf(-fabsf(pre));
-    const float r = 1.f / (1.f + E);
-    const float sig = pre >= 0.f ? r : E * r;          // sigmoid(pre)
-    const float dsig = E * r * r;                      // sigmoid'(pre) = sig (1 - sig)
-    ysum += w * sig;
-    wtot += w;
-    jac += w * a * dsig;
+    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
+    const float pre = a * (x - tanhf(raw[j]) * 10.f);
+    const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
+    mx = fmaxf(mx, term);
   }
-  const float y_sig = ysum / wtot;  // :127
-  // extended softplus
-  const float s = softplus1(raw[3 * n]) + 0.1f;  // nonlinearities.py:519-520
-  const float y_esp = softplus1(x - s) - softplus1(-(x + s));
-  const float lj_esp = logaddexpf_(x - logaddexpf_(s, x), -softplus1(s + x));
-  y = y_sig + y_esp;
-  float lj_sig;
-  if (jac > 1e-30f) {
-    lj_sig = logf(jac);
-  } else {
-    // every sigmoid is saturated: redo the reduction in the log domain (logsumexp, :130)
-    float acc = 0.f;
-    float mx = -INFINITY;
-    for (int j = 0; j < n; ++j) {
-      const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
-      const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
-      const float pre = a * (x - tanhf(raw[j]) * 10.f);
-      const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
-      mx = fmaxf(mx, term);
-    }
-    for (int j = 0; j < n; ++j) {
-      const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
-      const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
-      const float pre = a * (x - tanhf(raw[j]) * 10.f);
-      const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
-      acc += expf(term - mx);
-    }
-    lj_sig = mx + logf(acc);
+  for (int j = 0; j < n; ++j) {
+    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
+    const float pre = a * (x - tanhf(raw[j]) * 10.f);
+    const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
+    acc += expf(term - mx);
   }
-  logj = logaddexpf_(lj_sig, lj_esp);  // :116
+  logj = logaddexpf_(mx + logf(acc), lj_esp);  // :116
 }
+
+FC_HD void sos_eval(float x, const float* raw, int n, float& y, float& logj) { sos_eval_t<0>(x, raw, n, y, logj); }
 
 // sigmoid(x), 1 - sigmoid(x) and sigmoid'(x) without cancellation for saturated arguments.
 FC_HD void sigmoid_parts(float x, float& sig, float& omsig, float& dsig) {

@@ -19,7 +19,11 @@ struct SosOp {
   __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned& status) const {
     float lj;
     if (!inverse) {
-      sos_eval(x, p, n, y, lj);
+      if (n == 10) {  // the default of ConditionalSumOfSigmoidsTransform (conditional.py:746): fully unrolled
+        sos_eval_t<10>(x, p, n, y, lj);
+      } else {
+        sos_eval_t<0>(x, p, n, y, lj);
+      }
       y += offset;
       lad = lj;
     } else {
