@@ -742,41 +742,60 @@ FC_HD float sech2f_(float x) {
 // Linear-domain derivation: J = J_sig + J_esp, logj = log J with
 //   J_sig = sum_j w_j a_j sig'_j   (the reference's logsumexp, adaptive_sigmoids.py:124-130, exponentiated)
 //   y_sig = sum_j w_j sig_j / sum_j w_j.
+// sigma(z), 1 - sigma(z), sigma'(z) on SFU arithmetic (see fc_sigmoid_parts); 1 - tanh^2 the same way
+FC_HD void fc_sigmoid_parts3(float z, float& sig, float& omsig, float& dsig) {
+  const float E = fc_exp2(-fabsf(z) * FC_LOG2E);
+  const float r = fc_rcp(1.f + E);
+  const float Er = E * r;
+  sig = z >= 0.f ? r : Er;
+  omsig = z >= 0.f ? Er : r;
+  dsig = Er * r;
+}
+FC_HD float fc_sech2(float t) {
+  const float E = fc_exp2(fabsf(t) * (-2.f * FC_LOG2E));
+  const float r = fc_rcp(1.f + E);
+  return 4.f * E * r * r;
+}
+
 FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float gl, float& gx, float* graw) {
   const float* sm = raw + 2 * n;
   float m = -INFINITY;
   for (int j = 0; j < n; ++j) m = fmaxf(m, sm[j]);
   float se = 0.f;
-  for (int j = 0; j < n; ++j) se += expf(sm[j] - m);
-  const float inv_se = 1.f / se;
+  const float ml2 = m * FC_LOG2E;
+  for (int j = 0; j < n; ++j) se += fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2));
+  const float inv_se = fc_rcp(se);
   const float wsum = 1.f + 1e-6f * (float)n;  // sum_j (softmax_j + eps)
-  const float inv_wsum = 1.f / wsum;
+  const float inv_wsum = fc_rcp(wsum);
 
   // pass 1: totals
   float ysum = 0.f, jac = 0.f, djac_dx = 0.f;
   for (int j = 0; j < n; ++j) {
-    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
-    const float a = sigmoidf_(raw[n + j]) * 9.9f + 0.1f;
-    const float sh = tanhf(raw[j]) * 10.f;
+    const float w = fmaf(fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)), inv_se, 1e-6f) * inv_wsum;
+    float lsg0, omlsg0, dlsg0;
+    fc_sigmoid_parts3(raw[n + j], lsg0, omlsg0, dlsg0);
+    const float a = fmaf(lsg0, 9.9f, 0.1f);
+    const float sh = fc_tanh(raw[j]) * 10.f;
     float sig, omsig, ds;
-    sigmoid_parts(a * (x - sh), sig, omsig, ds);
+    fc_sigmoid_parts3(a * (x - sh), sig, omsig, ds);
     ysum += w * sig;
     jac += w * a * ds;
     djac_dx += w * a * a * ds * (omsig - sig);
   }
   // extended softplus pieces
   const float er = raw[3 * n];
-  const float s = softplus1(er) + 0.1f;
-  const float ds_der = er > 20.f ? 1.f : sigmoidf_(er);
+  const float s = fc_softplus1(er) + 0.1f;
+  float ds_der, ds_om, ds_d;
+  fc_sigmoid_parts3(er, ds_der, ds_om, ds_d);  // softplus' (1 above the threshold to fp32 precision)
   float sp, omsp, dsp, sn, omsn, dsn;
-  sigmoid_parts(x - s, sp, omsp, dsp);       // d softplus(x-s)/dx and its derivative
-  sigmoid_parts(-(x + s), sn, omsn, dsn);    // d (-softplus(-(x+s)))/dx
+  fc_sigmoid_parts3(x - s, sp, omsp, dsp);       // d softplus(x-s)/dx and its derivative
+  fc_sigmoid_parts3(-(x + s), sn, omsn, dsn);    // d (-softplus(-(x+s)))/dx
   const float j_esp = sp + sn;
   const float dj_esp_dx = dsp - dsn;
   const float dy_esp_ds = -sp + sn;
   const float dj_esp_ds = -dsp - dsn;
   const float J = fmaxf(jac + j_esp, 1e-37f);  // total derivative
-  const float gJ = gl / J;
+  const float gJ = gl * fc_rcp(J);
   gx = gy * (jac + j_esp) + gJ * (djac_dx + dj_esp_dx);
   graw[3 * n] = (gy * dy_esp_ds + gJ * dj_esp_ds) * ds_der;
 
@@ -784,23 +803,25 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
   // softmax path: w_j = (p_j + eps)/wsum ; dL/dw_j = gy * (sig_j - ysum) + gJ * a_j ds_j
   float dot = 0.f;  // sum_j p_j * dL/dp_j
   for (int j = 0; j < n; ++j) {
-    const float pj = expf(sm[j] - m) * inv_se;
-    const float a = sigmoidf_(raw[n + j]) * 9.9f + 0.1f;
+    const float pj = fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)) * inv_se;
+    float lsg0, omlsg0, dlsg0;
+    fc_sigmoid_parts3(raw[n + j], lsg0, omlsg0, dlsg0);
+    const float a = fmaf(lsg0, 9.9f, 0.1f);
     float sig, omsig, ds;
-    sigmoid_parts(a * (x - tanhf(raw[j]) * 10.f), sig, omsig, ds);
+    fc_sigmoid_parts3(a * (x - fc_tanh(raw[j]) * 10.f), sig, omsig, ds);
     const float gw = gy * (sig - ysum) + gJ * a * ds;
     dot += pj * gw * inv_wsum;
   }
   for (int j = 0; j < n; ++j) {
-    const float pj = expf(sm[j] - m) * inv_se;
+    const float pj = fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)) * inv_se;
     const float w = (pj + 1e-6f) * inv_wsum;
     float lsg, omlsg, dlsg;
-    sigmoid_parts(raw[n + j], lsg, omlsg, dlsg);
-    const float a = lsg * 9.9f + 0.1f;
-    const float th = tanhf(raw[j]);
+    fc_sigmoid_parts3(raw[n + j], lsg, omlsg, dlsg);
+    const float a = fmaf(lsg, 9.9f, 0.1f);
+    const float th = fc_tanh(raw[j]);
     const float sh = th * 10.f;
     float sig, omsig, ds;
-    sigmoid_parts(a * (x - sh), sig, omsig, ds);
+    fc_sigmoid_parts3(a * (x - sh), sig, omsig, ds);
     const float dds = ds * (omsig - sig);
     const float gw = gy * (sig - ysum) + gJ * a * ds;
     // pre = a (x - sh):  d/d pre of [gy w sig + gJ w a ds] = gy w ds + gJ w a dds
@@ -810,7 +831,7 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
     // (graw may alias raw: all reads of slot j / n+j / 2n+j of this iteration are done)
     graw[2 * n + j] = pj * (gw * inv_wsum - dot);
     graw[n + j] = ga * 9.9f * dlsg;
-    graw[j] = gsh * 10.f * sech2f_(raw[j] * 1.f);
+    graw[j] = gsh * 10.f * fc_sech2(raw[j]);
   }
 }
 
