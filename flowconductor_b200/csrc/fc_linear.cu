@@ -64,7 +64,7 @@ struct LinArgs {
   int n_pad;         // rows of one weight plane (lo plane starts at row n_pad of the weight tensor map)
   int relu_in;       // ReLU applied to A while splitting
   int a_tiled;       // A is stored in the T128 activation layout (include/flowcon_b200.h)
-  int debug;         // experiments only (FC_LINEAR_DEBUG): 1 = converters skip their work, 2 = epilogue skips its math
+  int debug;         // FC_LINEAR_DEBUG: 4 = record the cycle counters (only in builds with -DFC_LINEAR_PROFILE=1)
   const float* bias;  // [n_pad]
 };
 
@@ -194,7 +194,6 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto ready_bar = [&](int s) { return bars + 8u * (3 * STAGES + s); };  // leader only: peer's stage is ready
   auto tfull_bar = [&](int a) { return bars + 8u * (4 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (4 * STAGES + 2 + a); };  // leader's is the one in use
   const uint32_t pfull_bar = bars + 8u * (4 * STAGES + 4), pempty_bar = bars + 8u * (4 * STAGES + 5);
@@ -217,7 +216,6 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
       mbar_init(full_bar(s), 1);
       mbar_init(conv_bar(s), 4 * CTAS);  // one arrival per converter warp (of both CTAs of a pair, in the leader)
       mbar_init(empty_bar(s), MC ? 2 : 1);
-      mbar_init(ready_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -348,7 +346,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         int s = 0, acc = 0;
         uint32_t ph = 0, aph = 0;
         const bool prof = FC_LINEAR_PROFILE && (la.debug & 4) && blockIdx.x == 0;
-        long long t_tempty = 0, t_conv = 0, t_ready = 0, t_stages = 0;
+        long long t_tempty = 0, t_conv = 0, t_stages = 0;
         const long long t_begin = clock64();
         // descriptors of ring slot 0; slot s adds s * STAGE_BYTES to the 16-byte-granular address field
         const bool tiled = la.a_tiled != 0;
@@ -386,10 +384,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
                   t_conv += t1 - t0;
                   t0 = t1;
                 }
-                if (prof) {
-                  t_ready += clock64() - t0;
-                  ++t_stages;
-                }
+                if (prof) ++t_stages;
                 tc_fence_after();
                 const uint64_t so = (uint64_t)((uint32_t)s * (uint32_t)(SM::STAGE_BYTES >> 4));
                 const uint64_t a_hi = a_hi0 + so, a_lo = a_lo0 + so, b_hi = b_hi0 + so, b_lo = b_lo0 + so;
@@ -455,7 +450,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           g_lin_prof[1] = (unsigned long long)t_tempty;
           g_lin_prof[2] = 0;
           g_lin_prof[3] = (unsigned long long)t_conv;
-          g_lin_prof[4] = (unsigned long long)t_ready;
+          g_lin_prof[4] = 0;
           g_lin_prof[5] = (unsigned long long)t_stages;
         }
       }
@@ -506,7 +501,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           }
           tmem_wait_st();
           tc_fence_before();
-        } else if (!(la.debug & 1))
+        } else
 #pragma unroll
         for (int v = ct; v < SM::A_BYTES / 16; v += kNumConv) {
           const uint32_t addr = st + (uint32_t)v * 16u;
@@ -695,7 +690,6 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
             e_t = t;
           }
         }
-        if (la.debug & 2) continue;
         if (EPI == 3) {
           // finished tile -> staging tile (same [column group][row][4 floats] order as the T128 layout); the skip
           // connection is already there (TMA), the manager warp stores the tile with one bulk copy

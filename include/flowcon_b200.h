@@ -200,10 +200,11 @@ int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t B, int32_t 
                            int32_t activation, int32_t inverse, int32_t layouts, void* stream);
 
 /*
- * Debugging aid: with FC_LINEAR_DEBUG=4 in the environment the last fc_linear_* launch records, for CTA 0, the cycles
- * its MMA-issuing thread spent waiting on each barrier ([0] total, [1] accumulator free, [2] TMA landed, [3] operand
- * converted, [4] partner CTA ready, [5] stages) and one epilogue warp's split ([8] total, [9] tile set-up, [10] waiting
- * for a partial accumulator, [11] draining it).  Synchronises the device.  Not part of the data path.
+ * Debugging aid: in a library built with -DFC_LINEAR_PROFILE=1 and with FC_LINEAR_DEBUG=4 in the environment, the last
+ * fc_linear_* launch records, for CTA 0, the cycles its MMA-issuing warp spent waiting on each barrier ([0] total,
+ * [1] accumulator free, [3] operand landed and converted, [5] ring slots processed) and one epilogue warp's split
+ * ([8] total, [9] tile set-up, [10] waiting for a partial accumulator, [11] draining it); all zero otherwise.
+ * Synchronises the device.  Not part of the data path.
  */
 int fc_linear_debug_profile(unsigned long long* out16);
 
