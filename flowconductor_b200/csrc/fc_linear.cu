@@ -64,6 +64,7 @@ struct LinArgs {
   int n_pad;         // rows of one weight plane (lo plane starts at row n_pad of the weight tensor map)
   int relu_in;       // ReLU applied to A while splitting
   int a_tiled;       // A is stored in the T128 activation layout (include/flowcon_b200.h)
+  int k_slices;      // split-K: the reduction is cut into k_slices ranges of num_k_stages slots, one work unit each
   int debug;         // FC_LINEAR_DEBUG: 4 = record the cycle counters (only in builds with -DFC_LINEAR_PROFILE=1)
   const float* bias;  // [n_pad]
 };
@@ -76,6 +77,7 @@ struct StoreEpi {
   int n_out;
   int relu_out;
   int tiled;  // out (and residual) are stored in the T128 layout; ldo / ldr are then their logical widths
+  int64_t slice_stride;  // split-K: floats between the partial results of consecutive reduction ranges
 };
 
 struct RqsEpi {
@@ -207,7 +209,8 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
   static_assert(2 * BN <= 512, "two partial accumulators must fit in tensor memory");
   const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
   const int unit0 = (int)blockIdx.x / CL, unit_step = (int)gridDim.x / CL;  // cluster index / count
-  const int n_units = (la.num_m_tiles + CL - 1) / CL;                        // 128*CL-row work units
+  const int ks_n = la.k_slices;                                               // reduction ranges (split-K), else 1
+  const int n_units = ((la.num_m_tiles + CL - 1) / CL) * ks_n;               // work units: (row tile(s), range)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -256,14 +259,15 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         int s = 0;
         uint32_t ph = 0;
         for (int mp = unit0; mp < n_units; mp += unit_step) {
-          const int mt = mp * CL + rank;
+          const int mt = (mp / ks_n) * CL + rank;
+          const int k_base = (mp % ks_n) * nk;  // first ring slot of this unit's reduction range (split-K)
           // The skip connection of the NEXT row tile of this CTA (one contiguous block in either layout) is pulled
           // into L2 slice by slice while this tile is computed: fetched by the epilogue in one burst from HBM it
           // would stall the tile for ~6k cycles (128 KB at one SM's share of the HBM bandwidth).
           const char* pf_base = nullptr;
           uint32_t pf_bytes = 0, pf_slice = 0;
           if (EPI == 0 && se.residual != nullptr) {
-            const int mt_next = (mp + unit_step) * CL + rank;
+            const int mt_next = ((mp + unit_step) / ks_n) * CL + rank;
             if (mt_next < la.num_m_tiles) {
               const int64_t rows_left = (int64_t)la.M - (int64_t)mt_next * kBM;
               const int rows = se.tiled ? kBM : (rows_left < kBM ? (int)rows_left : kBM);
@@ -289,18 +293,19 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
               const uint32_t st = base + s * SM::STAGE_BYTES;
               mbar_expect_tx(full_bar(s), SM::A_BYTES + 2 * SM::B_BYTES);
               if (la.a_tiled) {
-                tma_load_4d(st, &tmA, 0, 0, kc * (BK / 4), mt, full_bar(s));
+                tma_load_4d(st, &tmA, 0, 0, (k_base + kc) * (BK / 4), mt, full_bar(s));
               } else {
-                tma_load_2d(st, &tmA, kc * BK, mt * kBM, full_bar(s));
+                tma_load_2d(st, &tmA, (k_base + kc) * BK, mt * kBM, full_bar(s));
               }
               if (MC) {
                 const uint32_t half_off = (uint32_t)rank * (SM::B_BYTES / 2);
-                tma_load_2d_multicast(st + SM::A_PLANES * SM::A_BYTES + half_off, &tmB, kc * BK, brow, full_bar(s), 3);
-                tma_load_2d_multicast(st + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES + half_off, &tmB, kc * BK, la.n_pad + brow,
+                tma_load_2d_multicast(st + SM::A_PLANES * SM::A_BYTES + half_off, &tmB, (k_base + kc) * BK, brow, full_bar(s), 3);
+                tma_load_2d_multicast(st + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES + half_off, &tmB, (k_base + kc) * BK, la.n_pad + brow,
                                       full_bar(s), 3);
               } else {
-                tma_load_2d(st + SM::A_PLANES * SM::A_BYTES, &tmB, kc * BK, brow, full_bar(s));
-                tma_load_2d(st + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES, &tmB, kc * BK, la.n_pad + brow, full_bar(s));
+                tma_load_2d(st + SM::A_PLANES * SM::A_BYTES, &tmB, (k_base + kc) * BK, brow, full_bar(s));
+                tma_load_2d(st + SM::A_PLANES * SM::A_BYTES + SM::B_BYTES, &tmB, (k_base + kc) * BK, la.n_pad + brow,
+                            full_bar(s));
               }
               if (++s == STAGES) {
                 s = 0;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         constexpr uint32_t kTileBytes = kBM * BN * 4;
         uint32_t ph = 0;
         for (int mp = unit0; mp < n_units; mp += unit_step) {
-          const int mt = mp * CL + rank;
+          const int mt = (mp / ks_n) * CL + rank;
           for (int nt = 0; nt < n_tiles; ++nt) {
             // a T128 tile of 128 rows x BN columns is contiguous: tile mt, column groups nt*BN/4 ..
             const int64_t off = (int64_t)mt * kBM * se.ldo + (int64_t)nt * kBM * BN;
@@ -558,7 +563,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
     long long e_init = 0, e_wait = 0, e_drain = 0, e_final = 0, e_t = 0;
     const long long e_begin = clock64();
     for (int mp = unit0; mp < n_units; mp += unit_step) {
-      const int mt = mp * CL + rank;
+      const int mt = (mp / ks_n) * CL + rank;
       const int64_t row = (int64_t)mt * kBM + q * 32 + lane;
       const bool valid = row < la.M;
       float lad_acc = 0.f;
@@ -585,7 +590,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         } else if (EPI == 0) {
           // T128: element (r, n) of tile mt at mt*128*W + ((n/4)*128 + r)*4: a warp's 32 rows of one column group
           // are 512 contiguous bytes (coalesced); row-major: 32 rows x 16 B scattered over 32 lines
-          o_base = se.tiled ? (int64_t)mt * kBM * se.ldo + rt * 4 : row * se.ldo;
+          o_base = (se.tiled ? (int64_t)mt * kBM * se.ldo + rt * 4 : row * se.ldo) + (int64_t)(mp % ks_n) * se.slice_stride;
           r_base = se.tiled ? (int64_t)mt * kBM * se.ldr + rt * 4 : row * se.ldr;
           n_mul = se.tiled ? kBM : 1;  // float offset per unit of n (n is a multiple of 4)
           const int n0 = nt * BN + half * NCOL;
@@ -798,7 +803,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
       unsigned status = 0;
       int parity = 0;
       for (int mp = unit0; mp < n_units; mp += unit_step) {
-        const int mt = mp * CL + rank;
+        const int mt = (mp / ks_n) * CL + rank;
         const int64_t row = (int64_t)mt * kBM + r;
         const bool valid = row < la.M;
         float lad_acc = 0.f;
@@ -1020,6 +1025,8 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   if (rc != FC_OK) return rc;
   la.M = (int)M;
   la.num_k_stages = (K + BK - 1) / BK;
+  if (la.k_slices < 1) la.k_slices = 1;
+  if (la.k_slices > 1) la.num_k_stages = (la.num_k_stages + la.k_slices - 1) / la.k_slices;  // slots per range
   la.chunk = chunk_k(K) / BK > 0 ? chunk_k(K) / BK : 1;
   la.num_m_tiles = (int)((M + kBM - 1) / kBM);
   la.n_pad = w->n_pad;
@@ -1036,7 +1043,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
       return FC_ERR_CUDA;
     configured = true;
   }
-  const int units = (la.num_m_tiles + CL - 1) / CL;
+  const int units = ((la.num_m_tiles + CL - 1) / CL) * la.k_slices;
   const int max_units = device_info().sm_count / CL;
   const int grid = (units < max_units ? units : max_units) * CL;
   cudaLaunchConfig_t cfg = {};
@@ -1128,7 +1135,7 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   LinArgs la{};
   la.relu_in = relu_in;
   la.a_tiled = a_tiled;
-  StoreEpi se{out, ldo, residual, ldr, n_out, relu_out, o_tiled};
+  StoreEpi se{out, ldo, residual, ldr, n_out, relu_out, o_tiled, 0};
   RqsEpi re{};
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
@@ -1218,4 +1225,24 @@ extern "C" int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t 
   if (operand_in_tmem())
     return launch_linear<2, BN, 16, 8, 0, 2, 1, 8, true>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   return launch_linear<2, BN, 16, 8, 0, 2, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+}
+
+extern "C" int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w,
+                                      int32_t k_slices, float* partials, int64_t slice_stride, int64_t ldo,
+                                      int32_t n_out, void* stream) {
+  int rc = check_operand(A, lda, M, K, w, 0);
+  if (rc != FC_OK) return rc;
+  if (M == 0) return FC_OK;
+  if (!partials || n_out <= 0 || n_out > w->n_pad || k_slices < 1) return FC_ERR_INVALID_ARGUMENT;
+  if ((n_out & 3) || (ldo & 3) || (slice_stride & 3) || (reinterpret_cast<uintptr_t>(partials) & 15))
+    return FC_ERR_UNSUPPORTED;
+  if (slice_stride < M * ldo) return FC_ERR_INVALID_ARGUMENT;
+  LinArgs la{};
+  la.k_slices = k_slices;
+  StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, slice_stride};
+  RqsEpi re{};
+  constexpr int BN = 256;
+  if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
+  la.num_n_tiles = (n_out + BN - 1) / BN;
+  return launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, (cudaStream_t)stream);
 }

@@ -175,6 +175,18 @@ int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_
                     int32_t layouts, void* stream);
 
 /*
+ * Split-K form for products whose reduction is long and whose output is small — the weight gradient of a dense
+ * layer, grad_W[N, K_in] = grad_y^T[N, B] * x[B, K_in]^T-packed, reduces over the whole batch (autograd of
+ * resnet.py:26-28 / made.py:71-72; the reference leaves it to torch.mm).  The reduction range [0, K) is cut into
+ * k_slices ranges, every (row tile, range) pair is one work unit, and range s writes its partial product to
+ * partials + s * slice_stride (row stride ldo); the caller sums the k_slices partial results.  `w` must have been packed
+ * with a zero bias.  A: row-major [M, K], 16-byte aligned rows.
+ */
+int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w,
+                           int32_t k_slices, float* partials, int64_t slice_stride, int64_t ldo, int32_t n_out,
+                           void* stream);
+
+/*
  * Final conditioner layer with the rational-quadratic spline in the GEMM epilogue (SURVEY a15 + a1-a6):
  *   params[r, :] = act_in(hidden[r, :H]) * W^T + bias      (never written to memory)
  *   y[r, tcols[j]] = spline(x[r, tcols[j]]; params[r, j*P .. j*P+P-1]),   y[r, ccols[i]] = x[r, ccols[i]],

@@ -448,6 +448,21 @@ def test_linear_store_kernels(dev, M, K, N, relu_in, relu_out, res, a_t, o_t):
     assert _gemm_err(out, want) <= 2.0 * _gemm_err(ref32, want) + 2e-7
 
 
+@pytest.mark.parametrize("N,K,B,slices", [(256, 256, 8192, None), (752, 256, 20000, 7), (64, 100, 4096, 1)])
+def test_linear_splitk_weight_gradient_shape(dev, N, K, B, slices):
+    """fc_linear_splitk_apply: grad_W = grad_y^T @ x as a split-K product over the batch, against fp64."""
+    from flowconductor_b200 import linear as fl
+
+    g = torch.Generator(device=dev).manual_seed(N + B)
+    gy = torch.randn(B, N, generator=g, device=dev)
+    x = torch.randn(B, K, generator=g, device=dev)
+    got = fl.linear_splitk(gy.t().contiguous(), fl.pack(x.t().contiguous(), None), k_slices=slices)
+    want = gy.double().t() @ x.double()
+    ref32 = gy.t() @ x
+    assert got.shape == (N, K)
+    assert _gemm_err(got, want) <= 2.0 * _gemm_err(ref32, want) + 2e-7
+
+
 def test_linear_pack_folds_mask_and_column_scatter(dev):
     from flowconductor_b200 import linear as fl
 
