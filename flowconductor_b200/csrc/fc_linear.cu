@@ -1094,9 +1094,71 @@ __global__ void pack_kernel(const float* __restrict__ W, int64_t ldw, const floa
   }
 }
 
+// Transposing producers for the split-K weight-gradient product: the reduction axis (the batch) has to be the contiguous
+// one for both operands.  32 x 32 tiles through shared memory (padded: conflict-free), coalesced on both sides.
+//   kSplit = false: dst[c][r] = src[r][c]                       (grad_y [B, N] -> [N, B])
+//   kSplit = true : dst[0][c][r] = tf32_hi(src[r][c]), dst[1][c][r] = tf32(src[r][c] - hi)   (x [B, K] -> packed planes)
+template <bool kSplit>
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
+                                                        float* __restrict__ dst, int64_t ldd, int64_t plane_stride) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i;
+    const int c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? __ldcs(src + r * lds + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows) {
+      const float v = tile[tx][ty + 8 * i];
+      if (kSplit) {
+        const uint32_t hi = tc::to_tf32(v);
+        dst[(int64_t)c * ldd + r] = __uint_as_float(hi);
+        dst[plane_stride + (int64_t)c * ldd + r] = __uint_as_float(tc::to_tf32(v - __uint_as_float(hi)));
+      } else {
+        dst[(int64_t)c * ldd + r] = v;
+      }
+    }
+  }
+}
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_linear_transpose(const float* src, int64_t src_row_stride, int64_t rows, int32_t cols, float* dst,
+                                   int64_t dst_row_stride, void* stream) {
+  if (rows < 0 || cols <= 0 || dst_row_stride < rows || src_row_stride < cols) return FC_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return FC_OK;
+  if (!src || !dst) return FC_ERR_INVALID_ARGUMENT;
+  const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  transpose_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_row_stride, rows, cols, dst, dst_row_stride, 0);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+extern "C" int fc_linear_pack_transposed(const float* X, int64_t x_row_stride, int64_t B, int32_t K, int32_t n_pad,
+                                         int32_t k_pad, float* w_packed, float* bias_packed, void* stream) {
+  if (B <= 0 || K <= 0 || !X || !w_packed || !bias_packed || n_pad < K || k_pad < B || (k_pad % 32) || (n_pad % 16))
+    return FC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the padding (rows K..n_pad of both planes, columns B..k_pad) must read as zero
+  if ((n_pad != K || k_pad != B) &&
+      cudaMemsetAsync(w_packed, 0, sizeof(float) * 2 * (size_t)n_pad * k_pad, st) != cudaSuccess)
+    return FC_ERR_CUDA;
+  if (cudaMemsetAsync(bias_packed, 0, sizeof(float) * (size_t)n_pad, st) != cudaSuccess) return FC_ERR_CUDA;
+  const dim3 grid((unsigned)((B + 31) / 32), (unsigned)((K + 31) / 32));
+  transpose_kernel<true><<<grid, 256, 0, st>>>(X, x_row_stride, B, K, w_packed, k_pad, (int64_t)n_pad * k_pad);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
 
 extern "C" int fc_linear_debug_profile(unsigned long long* out16) {
   if (!out16) return FC_ERR_INVALID_ARGUMENT;

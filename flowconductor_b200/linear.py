@@ -226,3 +226,32 @@ def linear_splitk(a, packed, k_slices=None):
     _cabi.check(rc, "fc_linear_splitk_apply")
     out = partials[0] if k_slices == 1 else partials.sum(0)
     return out if n4 == packed.n_out else out[:, :packed.n_out]
+
+
+def transpose(t):
+    """[rows, cols] -> [cols, rows] (fc_linear_transpose; coalesced on both sides)."""
+    _cabi.require_cuda_f32(t, "matrix")
+    L = _cabi.lib()
+    t, tp, ld = _cabi.rows(t)
+    rows, cols = t.shape
+    out = torch.empty((cols, rows), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device), _cabi.launch("fc_linear_transpose", t.device):
+        rc = L.fc_linear_transpose(tp, ld, rows, cols, out.data_ptr(), rows, _cabi.stream_ptr(t.device))
+    _cabi.check(rc, "fc_linear_transpose")
+    return out
+
+
+def pack_transposed(x, n_tile=N_TILE_STORE):
+    """Packed hi / lo planes of x^T (zero bias) for linear_splitk: x [B, K] -> PackedLinear with n_out = K, k_in = B."""
+    _cabi.require_cuda_f32(x, "activations")
+    L = _cabi.lib()
+    x, xp, ld = _cabi.rows(x)
+    B, K = x.shape
+    n_pad, k_pad = _ceil_to(K, n_tile), _ceil_to(B, 32)
+    w = torch.empty((2, n_pad, k_pad), dtype=torch.float32, device=x.device)
+    b = torch.empty((n_pad,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _cabi.launch("fc_linear_pack_transposed", x.device):
+        rc = L.fc_linear_pack_transposed(xp, ld, B, K, n_pad, k_pad, w.data_ptr(), b.data_ptr(),
+                                         _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_linear_pack_transposed")
+    return PackedLinear(w, b, K, B)

@@ -6,8 +6,8 @@ flowcon/transforms/made.py:71-72) as an autograd function whose forward and inpu
 
     forward   y  = x  @ (W*mask)^T + b          tensor cores
     backward  gx = gy @ (W*mask)                tensor cores (the packed operand is the transposed weight)
-              gW = (gy^T @ x) * mask            torch.mm (cuBLAS fp32) by default; WGRAD_TC routes it through the split-K
-              gb = gy.sum(0)                    tensor-core product fc_linear_splitk_apply (see the note at WGRAD_TC)
+              gW = (gy^T @ x) * mask            tensor cores, split-K: the reduction runs over the batch, so it is cut
+              gb = gy.sum(0)                    into ranges that run as independent work units (fc_linear_splitk_apply)
 
 The weights change every optimizer step, so they are re-packed on every call (two tiny kernels per layer).
 Anything the kernel does not cover (CPU tensors, other dtypes, misaligned operands) takes F.linear.
@@ -18,11 +18,11 @@ from torch.nn import functional as F
 from .. import linear as fl
 
 ENABLED = True
-# Weight gradients through fc_linear_splitk_apply.  Off by default: the split-K product itself is 2.5x faster than the
-# cuBLAS fp32 torch.mm (0.28 vs 0.77 ms for 256 x 256 over 262144 rows, 0.80 vs 2.03 ms for 752 x 256), but it needs
-# grad_y and x with the batch as the contiguous axis, and the two torch transposes + the hi/lo packing (0.3 + 0.3..0.9 +
-# 0.3 ms) cost more than that saves.  Worth it once the producing kernels emit the transposed operands themselves.
-WGRAD_TC = False
+# Weight gradients through fc_linear_splitk_apply: grad_y and x are transposed by fc_linear_transpose /
+# fc_linear_pack_transposed (the batch has to be the contiguous reduction axis; x is split into its hi / lo planes on the
+# way), then one split-K product.  Measured over 262144 rows: 256 x 256: 0.60 ms (0.135 + 0.19 + 0.28) vs 0.77 ms for the
+# cuBLAS fp32 torch.mm; 752 x 256: 1.40 vs 2.03 ms.
+WGRAD_TC = True
 # Shortest reduction the tensor-core GEMM is used for.  Every 3xTF32 product carries ~2^-22 relative error (dropped
 # lo*lo term, truncation inside the MMA); an fp32 FMA chain rounds at 2^-24 per step, so its error grows with the
 # chain length.  Measured (scripts/check_linear.py, Gaussian operands): at K = 32 the tensor-core result is 1.3x
@@ -67,7 +67,7 @@ class _TCLinear(torch.autograd.Function):
             if WGRAD_TC and weight.shape[1] >= MIN_K and x.shape[0] >= 4096 and x.shape[0] % 4 == 0:
                 # grad_W[N, K] = grad_y^T[N, B] @ x[B, K]: a reduction over the batch -> split-K on the tensor cores
                 # (both operands transposed once so that the batch is the contiguous reduction axis)
-                gw = fl.linear_splitk(gy.t().contiguous(), fl.pack(x.t().contiguous(), None))
+                gw = fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x))
                 if gw.stride(0) != weight.shape[1]:
                     gw = gw.contiguous()
             else:

@@ -186,6 +186,13 @@ int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, int32_t K, co
                            int32_t k_slices, float* partials, int64_t slice_stride, int64_t ldo, int32_t n_out,
                            void* stream);
 
+/* Operand producers for fc_linear_splitk_apply (the batch has to be the contiguous reduction axis of both operands):
+ * dst[c, r] = src[r, c], and the packed hi / lo planes of X^T (zero bias): packed row c = column c of X. */
+int fc_linear_transpose(const float* src, int64_t src_row_stride, int64_t rows, int32_t cols, float* dst,
+                        int64_t dst_row_stride, void* stream);
+int fc_linear_pack_transposed(const float* X, int64_t x_row_stride, int64_t B, int32_t K, int32_t n_pad, int32_t k_pad,
+                              float* w_packed, float* bias_packed, void* stream);
+
 /*
  * Final conditioner layer with the rational-quadratic spline in the GEMM epilogue (SURVEY a15 + a1-a6):
  *   params[r, :] = act_in(hidden[r, :H]) * W^T + bias      (never written to memory)

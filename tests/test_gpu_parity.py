@@ -457,6 +457,8 @@ def test_linear_splitk_weight_gradient_shape(dev, N, K, B, slices):
     gy = torch.randn(B, N, generator=g, device=dev)
     x = torch.randn(B, K, generator=g, device=dev)
     got = fl.linear_splitk(gy.t().contiguous(), fl.pack(x.t().contiguous(), None), k_slices=slices)
+    got2 = fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x), k_slices=slices)  # the fused operand producers
+    assert torch.equal(got, got2)
     want = gy.double().t() @ x.double()
     ref32 = gy.t() @ x
     assert got.shape == (N, K)
