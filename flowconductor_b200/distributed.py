@@ -77,3 +77,40 @@ def broadcast_parameters(module, src=0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+def host_log_prob(flow, inputs_host, out_host=None, chunk_rows=262144, context_host=None):
+    """`flow.log_prob` for a batch that lives in (pinned) HOST memory: rows are streamed to the GPU in chunks on a copy
+    stream, double-buffered, so that the host-to-device copy of chunk i+1 overlaps the kernels of chunk i, and each
+    chunk's log-probabilities are copied back as soon as they exist.  Returns the host tensor of log-probabilities
+    (valid after the current stream has been synchronised).  No gradient."""
+    dev = next(flow.parameters()).device
+    n, feat = inputs_host.shape
+    if out_host is None:
+        out_host = torch.empty((n,), dtype=torch.float32).pin_memory()
+    main = torch.cuda.current_stream(dev)
+    copier = torch.cuda.Stream(dev)
+    rows = min(chunk_rows, max(n, 1))
+    xbuf = [torch.empty((rows, feat), dtype=torch.float32, device=dev) for _ in range(2)]
+    cbuf = None
+    if context_host is not None:
+        cbuf = [torch.empty((rows, context_host.shape[1]), dtype=torch.float32, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    for ev in free:
+        ev.record(main)
+    with torch.no_grad():
+        for i, lo in enumerate(range(0, n, rows)):
+            hi = min(n, lo + rows)
+            b = i & 1
+            with torch.cuda.stream(copier):
+                copier.wait_event(free[b])            # the kernels of chunk i-2 have finished with this buffer
+                xbuf[b][:hi - lo].copy_(inputs_host[lo:hi], non_blocking=True)
+                if cbuf is not None:
+                    cbuf[b][:hi - lo].copy_(context_host[lo:hi], non_blocking=True)
+                ready[b].record(copier)
+            main.wait_event(ready[b])
+            lp = flow.log_prob(xbuf[b][:hi - lo], context=None if cbuf is None else cbuf[b][:hi - lo])
+            out_host[lo:hi].copy_(lp, non_blocking=True)
+            free[b].record(main)
+    return out_host

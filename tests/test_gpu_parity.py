@@ -623,6 +623,28 @@ def test_stacked_autoregressive_layers_tensorcore_vs_unfused(dev, monkeypatch):
         assert rt_tc.median() <= 2 * rt_un.median() + 1e-6 and rt_tc.max() <= 4 * rt_un.max() + 1e-5, name
 
 
+def test_host_log_prob_streams_chunks(dev):
+    """distributed.host_log_prob (pinned host batch, double-buffered chunks) == flow.log_prob on the whole batch."""
+    from flowconductor_b200 import distributed as fdist
+
+    wl = workloads.get_workload("cfg2_tc_small")
+    flow = workloads.build_flow(wl).to(dev)
+    x = torch.randn(1000, 64, generator=torch.Generator().manual_seed(4)).pin_memory()
+    with torch.no_grad():
+        want = flow.log_prob(x.to(dev))
+    got = fdist.host_log_prob(flow, x, chunk_rows=300)   # 4 chunks, the last one ragged
+    torch.cuda.synchronize()
+    assert got.shape == (1000,) and (got - want.cpu()).abs().max() < 1e-4 * max(1.0, want.abs().max().item())
+    wl4 = workloads.get_workload("cfg4_small")
+    flow4 = workloads.build_flow(wl4).to(dev)
+    x4, c4 = torch.randn(257, 8).pin_memory(), torch.randn(257, 8).pin_memory()
+    with torch.no_grad():
+        want4 = flow4.log_prob(x4.to(dev), context=c4.to(dev))
+    got4 = fdist.host_log_prob(flow4, x4, chunk_rows=100, context_host=c4)
+    torch.cuda.synchronize()
+    assert (got4 - want4.cpu()).abs().max() < 1e-4 * max(1.0, want4.abs().max().item())
+
+
 def test_full_size_cfg3_training_step_is_finite(dev):
     wl = workloads.get_workload("cfg3")
     flow = workloads.build_flow(wl).to(dev)
