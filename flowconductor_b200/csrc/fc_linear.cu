@@ -34,6 +34,8 @@
 //                                ReLU/residual/store, the rational-quadratic spline of 8 (K=8) / 4 (K=16)
 //                                features per 192-column tile, or the affine transform of 32 features per 64 columns.
 // DESIGN.md 4.6 has the measurements behind each of these choices.
+#include <atomic>
+
 #include "fc_common.cuh"
 #include "fc_tc.cuh"
 
@@ -1037,11 +1039,15 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   }();
   la.debug = debug;
   auto kern = linear_tf32x3_kernel<EPI, BN, BK, STAGES, KC, PPAD, MODE, EW, TS, SW>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  // the opt-in shared-memory size is a per-device function attribute: set it once per (instantiation, device)
+  static std::atomic<uint64_t> configured{0};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  const uint64_t dev_bit = 1ull << (dev_id & 63);
+  if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess)
       return FC_ERR_CUDA;
-    configured = true;
+    configured.fetch_or(dev_bit, std::memory_order_release);
   }
   const int units = ((la.num_m_tiles + CL - 1) / CL) * la.k_slices;
   const int max_units = device_info().sm_count / CL;
