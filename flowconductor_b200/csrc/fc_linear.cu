@@ -469,9 +469,16 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
     int s = 0;
     uint32_t ph = 0;
     const bool relu = la.relu_in != 0;
+    const bool cprof = FC_LINEAR_PROFILE && (la.debug & 4) && blockIdx.x == 0 && warp == kConvWarp0;
+    long long c_wait = 0, c_work = 0, c_t = cprof ? clock64() : 0;
     for (int mp = unit0; mp < n_units; mp += unit_step) {
       for (int it = 0; it < n_tiles * nk; ++it) {
         mbar_wait(full_bar(s), ph);
+        if (cprof) {
+          const long long t = clock64();
+          c_wait += t - c_t;
+          c_t = t;
+        }
         const uint32_t st = base + s * SM::STAGE_BYTES;
         if (TS) {
           tc_fence_after();  // the slot's previous MMAs completed (empty -> TMA -> full): order the stores after them
@@ -546,7 +553,16 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           s = 0;
           ph ^= 1u;
         }
+        if (cprof) {
+          const long long t = clock64();
+          c_work += t - c_t;
+          c_t = t;
+        }
       }
+    }
+    if (cprof && lane == 0) {
+      g_lin_prof[12] = (unsigned long long)c_wait;
+      g_lin_prof[13] = (unsigned long long)c_work;
     }
   } else if (warp < kEpiWarp0 + EW) {
     // ------------------------------------------------------------------ epilogue / drain warps

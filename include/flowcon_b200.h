@@ -222,7 +222,8 @@ int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t B, int32_t 
  * Debugging aid: in a library built with -DFC_LINEAR_PROFILE=1 and with FC_LINEAR_DEBUG=4 in the environment, the last
  * fc_linear_* launch records, for CTA 0, the cycles its MMA-issuing warp spent waiting on each barrier ([0] total,
  * [1] accumulator free, [3] operand landed and converted, [5] ring slots processed) and one epilogue warp's split
- * ([8] total, [9] tile set-up, [10] waiting for a partial accumulator, [11] draining it); all zero otherwise.
+ * ([8] total, [9] tile set-up, [10] waiting for a partial accumulator, [11] draining it) and one converter warp's
+ * ([12] waiting for the TMA boxes, [13] converting); all zero otherwise.
  * Synchronises the device.  Not part of the data path.
  */
 int fc_linear_debug_profile(unsigned long long* out16);

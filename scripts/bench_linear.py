@@ -59,8 +59,8 @@ if int(os.environ.get("FC_LINEAR_DEBUG", "0")) & 4:
     import ctypes
     L = _cabi.lib()
     buf = (ctypes.c_ulonglong * 16)()
-    names = ["mma_total", "w_tempty", "w_full", "w_conv", "w_ready", "stages", "", "", "epi_total", "e_init", "e_wait",
-             "e_drain"]
+    names = ["mma_total", "w_tempty", "", "w_conv", "", "stages", "", "", "epi_total", "e_init", "e_wait",
+             "e_drain", "conv_wait_tma", "conv_work"]
     for label, fn in (("hidden t128 res", lambda: fl.linear(at, pk, relu_in=True, out=ot, residual=rt, out_t128=True)),
                       ("final+spline", lambda: fl.linear_rqs(at, pkf, x, y, lad, False, d_t, tcols, ccols, cfg, None)),
                       ("final+spline in place", lambda: fl.linear_rqs(at, pkf, x, x, lad, False, d_t, tcols, ccols, cfg, None))):
