@@ -506,9 +506,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float a = relu ? fmaxf(f[i], 0.f) : f[i];
-              hi[i] = to_tf32(a);
-              lo[i] = to_tf32(a - __uint_as_float(hi[i]));
+              split_tf32(relu ? fmaxf(f[i], 0.f) : f[i], hi[i], lo[i]);
             }
             tmem_st16(ta + (uint32_t)(h * 16), hi);
             tmem_st16(ta + (uint32_t)(BK + h * 16), lo);
@@ -526,9 +524,11 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
             f.z = fmaxf(f.z, 0.f);
             f.w = fmaxf(f.w, 0.f);
           }
-          const uint32_t h0 = to_tf32(f.x), h1 = to_tf32(f.y), h2 = to_tf32(f.z), h3 = to_tf32(f.w);
-          const uint32_t l0 = to_tf32(f.x - __uint_as_float(h0)), l1 = to_tf32(f.y - __uint_as_float(h1)),
-                         l2 = to_tf32(f.z - __uint_as_float(h2)), l3 = to_tf32(f.w - __uint_as_float(h3));
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          split_tf32(f.x, h0, l0);
+          split_tf32(f.y, h1, l1);
+          split_tf32(f.z, h2, l2);
+          split_tf32(f.w, h3, l3);
           sts128(addr, h0, h1, h2, h3);
           sts128(addr + SM::A_BYTES, l0, l1, l2, l3);
         }

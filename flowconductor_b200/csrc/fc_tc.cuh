@@ -306,6 +306,20 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// a = hi + lo with hi, lo tf32-representable (11 significant bits each), both rounded to nearest: Veltkamp's splitting
+// with C = 2^13 + 1 (hi = fl(t - fl(t - a)), t = fl(C a)), applied to a and then to the remainder.  Seven fp32
+// operations per value; cvt.rna.tf32.f32 has no native SASS form on sm_100 (ptxas expands each into ~6 integer /
+// predicate instructions), which made the operand conversion the slowest stage of the GEMM pipeline.  The intrinsics
+// keep nvcc from contracting the sequence into FMAs.  |a| < 2^114 (no overflow of C a).
+__device__ __forceinline__ float veltkamp11(float a) {
+  const float t = __fmul_rn(a, 8193.f);
+  return __fsub_rn(t, __fsub_rn(t, a));
+}
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+  const float h = veltkamp11(a);
+  hi = __float_as_uint(h);
+  lo = __float_as_uint(veltkamp11(__fsub_rn(a, h)));
+}
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
