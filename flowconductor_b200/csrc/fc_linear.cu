@@ -12,8 +12,9 @@
 // ("3xTF32": error ~2^-21 per product, the same size as the summation-order noise of an fp32 GEMM with K = 256).
 //   * weights: split once by fc_linear_pack into a [hi | lo] pair of K-major planes (also folds the MADE mask,
 //     the per-feature padding P -> P_pad and the coupling column scatter into the layout);
-//   * activations: TMA lands the raw fp32 tile in shared memory, four converter warps rewrite it in place as a_hi
-//     (optionally after ReLU — the residual blocks are pre-activation, resnet.py:41-47) and write a_lo next to it.
+//   * activations: TMA lands the raw fp32 tile in shared memory; four converter warps split it (optionally after
+//     ReLU — the residual blocks are pre-activation, resnet.py:41-47) and write (a_hi, a_lo) into a tensor-memory
+//     operand ring (TS kernels) or back into shared memory (a_hi in place, a_lo next to it).
 //
 // Accumulation: the tensor core truncates (rounds toward zero) every time an MMA result is added to the fp32
 // accumulator in TMEM; over the K/8 = 32 dependent additions of a K = 256 dot product that is a systematic error
