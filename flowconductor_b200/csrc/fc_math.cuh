@@ -757,12 +757,16 @@ FC_HD float fc_sech2(float t) {
   return 4.f * E * r * r;
 }
 
-FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float gl, float& gx, float* graw) {
+template <int NC>
+FC_HD void sos_backward_elem_t(float x, const float* raw, int n_runtime, float gy, float gl, float& gx, float* graw) {
+  const int n = NC ? NC : n_runtime;
   const float* sm = raw + 2 * n;
   float m = -INFINITY;
+#pragma unroll(NC ? NC : 4)
   for (int j = 0; j < n; ++j) m = fmaxf(m, sm[j]);
   float se = 0.f;
   const float ml2 = m * FC_LOG2E;
+#pragma unroll(NC ? NC : 4)
   for (int j = 0; j < n; ++j) se += fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2));
   const float inv_se = fc_rcp(se);
   const float wsum = 1.f + 1e-6f * (float)n;  // sum_j (softmax_j + eps)
@@ -770,6 +774,7 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
 
   // pass 1: totals
   float ysum = 0.f, jac = 0.f, djac_dx = 0.f;
+#pragma unroll(NC ? NC : 2)
   for (int j = 0; j < n; ++j) {
     const float w = fmaf(fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)), inv_se, 1e-6f) * inv_wsum;
     float lsg0, omlsg0, dlsg0;
@@ -802,6 +807,7 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
   // pass 2: per-sigmoid parameter gradients
   // softmax path: w_j = (p_j + eps)/wsum ; dL/dw_j = gy * (sig_j - ysum) + gJ * a_j ds_j
   float dot = 0.f;  // sum_j p_j * dL/dp_j
+#pragma unroll(NC ? NC : 2)
   for (int j = 0; j < n; ++j) {
     const float pj = fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)) * inv_se;
     float lsg0, omlsg0, dlsg0;
@@ -812,6 +818,7 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
     const float gw = gy * (sig - ysum) + gJ * a * ds;
     dot += pj * gw * inv_wsum;
   }
+#pragma unroll(NC ? NC : 2)
   for (int j = 0; j < n; ++j) {
     const float pj = fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2)) * inv_se;
     const float w = (pj + 1e-6f) * inv_wsum;
@@ -835,20 +842,25 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
   }
 }
 
+FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float gl, float& gx, float* graw) {
+  sos_backward_elem_t<0>(x, raw, n, gy, gl, gx, graw);
+}
+
 // Numerical inverse for one element: find x with sos(x) = z.  Bracket [-lim, lim] grown until it
 // contains the root (no_analytic_inv/base.py:48-60, per element instead of batch-global), `iters`
 // bisection steps (:67-79), then two Newton steps with the analytic derivative and the reference's
 // +1e-7 damping (:30-33).
-FC_HD void sos_invert(float z, const float* raw, int n, int iters, float lim, float& x, float& logj) {
+template <int NC>
+FC_HD void sos_invert_t(float z, const float* raw, int n, int iters, float lim, float& x, float& logj) {
   float hi = lim, lo = -lim, y, lj;
   for (int g = 0; g < 64; ++g) {
-    sos_eval(hi, raw, n, y, lj);
+    sos_eval_t<NC>(hi, raw, n, y, lj);
     if (!(z > y)) break;
     hi *= 1.5f;
   }
   hi += 1.f;
   for (int g = 0; g < 64; ++g) {
-    sos_eval(lo, raw, n, y, lj);
+    sos_eval_t<NC>(lo, raw, n, y, lj);
     if (!(z < y)) break;
     lo *= 1.5f;
   }
@@ -856,7 +868,7 @@ FC_HD void sos_invert(float z, const float* raw, int n, int iters, float lim, fl
   for (int i = 0; i < iters; ++i) {
     const float mid = 0.5f * (hi + lo);
     if (mid == hi || mid == lo) break;  // fp32 resolution reached
-    sos_eval(mid, raw, n, y, lj);
+    sos_eval_t<NC>(mid, raw, n, y, lj);
     if (y > z) {
       hi = mid;
     } else if (y < z) {
@@ -868,10 +880,14 @@ FC_HD void sos_invert(float z, const float* raw, int n, int iters, float lim, fl
   }
   x = 0.5f * (hi + lo);
   for (int i = 0; i < 2; ++i) {
-    sos_eval(x, raw, n, y, lj);
+    sos_eval_t<NC>(x, raw, n, y, lj);
     x = x - (y - z) / (expf(lj) + 1e-7f);
   }
-  sos_eval(x, raw, n, y, logj);
+  sos_eval_t<NC>(x, raw, n, y, logj);
+}
+
+FC_HD void sos_invert(float z, const float* raw, int n, int iters, float lim, float& x, float& logj) {
+  sos_invert_t<0>(z, raw, n, iters, lim, x, logj);
 }
 
 }  // namespace fc

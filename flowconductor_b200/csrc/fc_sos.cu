@@ -27,7 +27,11 @@ struct SosOp {
       y += offset;
       lad = lj;
     } else {
-      sos_invert(x - offset, p, n, iters, lim, y, lj);
+      if (n == 10) {
+        sos_invert_t<10>(x - offset, p, n, iters, lim, y, lj);
+      } else {
+        sos_invert_t<0>(x - offset, p, n, iters, lim, y, lj);
+      }
       lad = -lj;
     }
     (void)status;
@@ -35,7 +39,11 @@ struct SosOp {
   __device__ __forceinline__ void backward(float x, const float* p, float gy, float gl, float& gx, float* gp) const {
     // gp may alias p (in-place tile): sos_backward_elem finishes every read of slot j / n+j / 2n+j before it
     // writes that slot, and reads the whole softmax block (normaliser, dot product) before the first write.
-    sos_backward_elem(x, p, n, gy, gl, gx, gp);
+    if (n == 10) {
+      sos_backward_elem_t<10>(x, p, n, gy, gl, gx, gp);
+    } else {
+      sos_backward_elem_t<0>(x, p, n, gy, gl, gx, gp);
+    }
   }
 };
 
