@@ -46,6 +46,16 @@ struct AffineOp {
     const float shift = layout == FC_AFFINE_BLOCKED ? p[0] : p[1];
     affine_eval(x, raw, shift, activation, inverse, y, lad);
   }
+  // gp may alias p (the slot is rewritten in place): both parameters are read before the first write
+  __device__ __forceinline__ void backward(float x, const float* p, float gy, float gl, float& gx, float* gp) const {
+    const bool blocked = layout == FC_AFFINE_BLOCKED;
+    const float raw = blocked ? p[D_t] : p[0];
+    const float shift = blocked ? p[0] : p[1];
+    float graw, gshift;
+    affine_backward_elem(x, raw, shift, activation, inverse, gy, gl, gx, graw, gshift);
+    gp[blocked ? D_t : 0] = graw;
+    gp[blocked ? 0 : 1] = gshift;
+  }
 };
 
 // Forward / inverse, general path.  16 B per element and almost no arithmetic: the kernel lives on loads in flight, so every warp
@@ -258,6 +268,16 @@ extern "C" int fc_affine_backward(const float* x, int64_t x_row_stride, const fl
   a.B = B; a.D_t = D_t; a.n_copy = ccols.n; a.tcols = tcols.idx; a.ccols = ccols.idx;
   a.layout = layout; a.activation = activation; a.inverse = inverse;
   a.seg = lane_map(D_t).seg;
+  {  // fast path: whole contiguous rows through the per-warp TMA ring (bulk loads in, bulk stores out)
+    LayerBwdArgs lb = {};
+    lb.x = x; lb.params = params; lb.gy = grad_y; lb.gl = grad_logabsdet; lb.gx = grad_x; lb.gp = grad_params;
+    lb.x_stride = x_row_stride; lb.p_stride = params_row_stride; lb.gy_stride = gy_row_stride;
+    lb.gx_stride = gx_row_stride; lb.gp_stride = gp_row_stride;
+    lb.B = B; lb.D_t = D_t; lb.n_copy = ccols.n; lb.tcols = tcols.idx; lb.ccols = ccols.idx;
+    AffineOp op = {D_t, layout, activation, inverse};
+    const int piped = try_launch_pipelined_backward(lb, op, 2, (int)x_row_stride, (cudaStream_t)stream);
+    if (piped != 0) return piped < 0 ? piped : FC_OK;
+  }
   affine_kernel<true><<<affine_grid(B, a.seg), kThreads, 0, (cudaStream_t)stream>>>(a);
   FC_CHECK_LAUNCH();
   return FC_OK;

@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(512) pipelined_backward_kernel(const PipeBwdAr
 
   int slot = 0;
   uint32_t parity = 0;
+  const int fstride = feature_stride(op, 0);
   for (int64_t row0 = g0 * R; row0 < B; row0 += row_step) {
     mbar_wait(bars_s + (uint32_t)slot * 8u, parity);
     const int rows = (int)min((int64_t)R, B - row0);
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(512) pipelined_backward_kernel(const PipeBwdAr
         const float gl = a.gl ? __ldg(a.gl + row0 + r) : 0.f;
         for (int j = j0; j < D_t; j += seg) {
           const int col = tcols ? __ldg(tcols + j) : j;
-          float* pj = sp + r * row_floats + j * P;
+          float* pj = sp + r * row_floats + j * fstride;
           float gxv;
           op.backward(xrow[col], pj, grow[col], gl, gxv, pj);  // parameter gradients overwrite the parameters
           xrow[col] = gxv;                                      // input gradient overwrites the input
@@ -383,11 +384,11 @@ inline int try_launch_pipelined_backward(const LayerBwdArgs& a, const Op& op, in
   const LaneMap lm = lane_map(a.D_t);
   const int64_t row_bytes = (row_floats + 2 * D) * 4;
   int slot_rows = lm.rows_per_warp;
-  const int target = env_int("FC_PIPE_BWD_SLOT_BYTES", 4096);
+  const int target = env_int("FC_PIPE_BWD_SLOT_BYTES", 2048);
   while ((int64_t)(slot_rows * 2) * row_bytes <= target) slot_rows *= 2;
   int stages = env_int("FC_PIPE_BWD_STAGES", 2);
   int warps = env_int("FC_PIPE_BWD_WARPS", 16);
-  int ctas_per_sm = env_int("FC_PIPE_BWD_CTAS", 2);
+  int ctas_per_sm = env_int("FC_PIPE_BWD_CTAS", slot_rows * row_bytes <= 2048 ? 3 : 2);
   const int64_t slot_bytes = slot_rows * row_bytes;
   if (slot_bytes > 96 * 1024) return 0;
   auto smem_need = [&](int w, int s) { return (int64_t)w * s * (slot_bytes + 8) + 128; };

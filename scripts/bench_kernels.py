@@ -128,6 +128,13 @@ def main():
     nbytes = xa.shape[0] * (4 * 64 + 4 * 64 + 4 * 64 + 4)
     print(json.dumps({"kernel": "affine_fwd coupling D=64 (4M rows)", "variant": "pipelined", "ms_median": med, "ms_best": best,
                       "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK, "bytes": nbytes}), flush=True)
+    gya, gla = torch.randn_like(xa), torch.randn(xa.shape[0], device=dev)
+    med, best = timeit(lambda: ops.affine_layer_backward(xa, pa, gya, gla, tca, cca, _cabi.AFFINE_BLOCKED,
+                                                         _cabi.SCALE_SIGMOID2, False))
+    nbytes = xa.shape[0] * (4 * 64 * 5 + 4)
+    print(json.dumps({"kernel": "affine_bwd coupling D=64 (4M rows)", "variant": "pipelined", "ms_median": med,
+                      "ms_best": best, "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
+                      "bytes": nbytes}), flush=True)
     if args.sweep:
         a, nbytes = cases[args.sweep_case][1]
         best = None
