@@ -112,6 +112,16 @@ struct RqsParams {
 
 // log1p(E) for E in [0, 1]:  2 atanh(E / (2 + E)) = 2 s (1 + s^2/3 + s^4/5 + ... + s^12/13), s <= 1/3
 // (truncation < 1.5e-8 relative).  Branch-free, no integer ops; ~12 instructions.
+FC_HD float fc_log1p_unit_r(float E, float r /* = 1 / (2 + E) */) {
+  const float sv = E * r, s2 = sv * sv;
+  float poly = fmaf(s2, 2.f / 13.f, 2.f / 11.f);
+  poly = fmaf(s2, poly, 2.f / 9.f);
+  poly = fmaf(s2, poly, 2.f / 7.f);
+  poly = fmaf(s2, poly, 2.f / 5.f);
+  poly = fmaf(s2, poly, 2.f / 3.f);
+  poly = fmaf(s2, poly, 2.f);
+  return sv * poly;
+}
 FC_HD float fc_log1p_unit(float E) {
 #if FC_DEVICE_MATH
   float r;
@@ -644,6 +654,85 @@ FC_HD float fc_tanh(float t) {
 // softplus(z) = max(z, 0) + log1p(e^-|z|)   (torch threshold rule reproduced as in softplus_beta)
 FC_HD float fc_softplus1(float z) { return fmaxf(z, 0.f) + fc_log1p_unit(fc_exp2(-fabsf(z) * FC_LOG2E)); }
 
+// --- MUFU-lean forms (compile-time sigmoid count).  The sum-of-sigmoids kernels are bound by the special-function
+// unit (16 results / clk / SM), not by HBM: one element of the n = 10 forward issued ~105 MUFU ops.  Two rules bring
+// that to ~65: (1) softmax numerators are kept in registers instead of being recomputed per pass, (2) reciprocals
+// come in pairs, 1/a and 1/b from ONE rcp of the product (a, b in [1, 3] here, so a b cannot overflow).
+FC_HD void fc_rcp2(float a, float b, float& ra, float& rb) {
+  const float r = fc_rcp(a * b);
+  ra = r * b;
+  rb = r * a;
+}
+// E = e^-|z| of a sigmoid argument
+FC_HD float fc_sig_E(float z) { return fc_exp2(-fabsf(z) * FC_LOG2E); }
+// sigma(z), sigma'(z) [and 1 - sigma(z)] from E and r = 1/(1+E)
+FC_HD void fc_sig_finish(float z, float E, float r, float& sig, float& dsig) {
+  const float Er = E * r;
+  sig = z >= 0.f ? r : Er;
+  dsig = Er * r;
+}
+FC_HD void fc_sig_finish3(float z, float E, float r, float& sig, float& omsig, float& dsig) {
+  const float Er = E * r;
+  sig = z >= 0.f ? r : Er;
+  omsig = z >= 0.f ? Er : r;
+  dsig = Er * r;
+}
+// two sigmoids, one reciprocal
+FC_HD void fc_sigmoid_pair(float z0, float z1, float& s0, float& d0, float& s1, float& d1) {
+  const float E0 = fc_sig_E(z0), E1 = fc_sig_E(z1);
+  float r0, r1;
+  fc_rcp2(1.f + E0, 1.f + E1, r0, r1);
+  fc_sig_finish(z0, E0, r0, s0, d0);
+  fc_sig_finish(z1, E1, r1, s1, d1);
+}
+FC_HD void fc_sigmoid_pair3(float z0, float z1, float& s0, float& o0, float& d0, float& s1, float& o1, float& d1) {
+  const float E0 = fc_sig_E(z0), E1 = fc_sig_E(z1);
+  float r0, r1;
+  fc_rcp2(1.f + E0, 1.f + E1, r0, r1);
+  fc_sig_finish3(z0, E0, r0, s0, o0, d0);
+  fc_sig_finish3(z1, E1, r1, s1, o1, d1);
+}
+// tanh(t) from E = e^(-2|t|) and r = 1/(1+E) (same switch to the Taylor polynomial as fc_tanh); sech^2 = 4 E r^2
+FC_HD float fc_tanh_finish(float t, float E, float r) {
+  const float at = fabsf(t);
+  const float big = (1.f - E) * r;
+  const float t2 = t * t;
+  float poly = fmaf(t2, 62.f / 2835.f, -17.f / 315.f);
+  poly = fmaf(t2, poly, 2.f / 15.f);
+  poly = fmaf(t2, poly, -1.f / 3.f);
+  poly = fmaf(t2 * at, poly, at);
+  const float m = at < 0.3f ? poly : big;
+  return t < 0.f ? -m : m;
+}
+// slope a = 0.1 + 9.9 sigma(raw_scale) and shift sh = 10 tanh(raw_shift) of one sigmoid (adaptive_sigmoids.py
+// :137-140) with one reciprocal; optionally d a / d raw_scale / 9.9 = sigma' and sech^2(raw_shift)
+FC_HD void sos_slope_shift(float raw_shift, float raw_scale, float& a, float& sh, float& dsa, float& sech2) {
+  const float Ea = fc_sig_E(raw_scale);
+  const float Et = fc_exp2(fabsf(raw_shift) * (-2.f * FC_LOG2E));
+  float ra, rt;
+  fc_rcp2(1.f + Ea, 1.f + Et, ra, rt);
+  float sa;
+  fc_sig_finish(raw_scale, Ea, ra, sa, dsa);
+  a = fmaf(sa, 10.f - 0.1f, 0.1f);
+  sh = fc_tanh_finish(raw_shift, Et, rt) * 10.f;
+  sech2 = 4.f * Et * rt * rt;
+}
+// extended softplus (nonlinearities.py:519-552) value and derivative at x for offset s:
+//   y = softplus(x - s) - softplus(-(x + s)),  dy/dx = sigma(x - s) + sigma(-(x + s));  4 MUFU ops
+FC_HD void fc_ext_softplus(float x, float s, float& y, float& dy) {
+  const float z1 = x - s, z2 = -(x + s);
+  const float E1 = fc_sig_E(z1), E2 = fc_sig_E(z2);
+  float r1, r2, q1, q2;
+  fc_rcp2(1.f + E1, 1.f + E2, r1, r2);
+  fc_rcp2(2.f + E1, 2.f + E2, q1, q2);
+  float s1, s2, unused;
+  fc_sig_finish(z1, E1, r1, s1, unused);
+  fc_sig_finish(z2, E2, r2, s2, unused);
+  const float l1 = fc_log1p_unit_r(E1, q1), l2 = fc_log1p_unit_r(E2, q2);
+  y = (fmaxf(z1, 0.f) + l1) - (fmaxf(z2, 0.f) + l2);
+  dy = s1 + s2;
+}
+
 // Forward for one element.  raw -> [shift_raw(n) | log_scale_raw(n) | softmax_raw(n) | esp_raw].
 // Returns y (without wrapper offset) and the per-element log-derivative.
 // The Jacobian is accumulated in the LINEAR domain,  J = sum_j w_j a_j sigma'(pre_j) + sigma(x - s) + sigma(-x - s)
@@ -651,8 +740,100 @@ FC_HD float fc_softplus1(float z) { return fmaxf(z, 0.f) + fc_log1p_unit(fc_exp2
 // (logsumexp :124-130, logaddexp :116, nonlinearities.py:543-552) is the same number and is only used as the fallback
 // when J underflows.
 // NC > 0: compile-time sigmoid count (loops fully unrolled, parameter reads at immediate offsets); NC = 0: runtime n.
+// log-domain Jacobian for a fully saturated element (J underflows in the linear domain): the reduction exactly as
+// the reference composes it (logsumexp :124-130, logaddexp :116, nonlinearities.py:543-552).  Rare; libm arithmetic.
+FC_HD float sos_logj_saturated(float x, const float* raw, int n) {
+  const float* sm = raw + 2 * n;
+  float m = -INFINITY;
+  for (int j = 0; j < n; ++j) m = fmaxf(m, sm[j]);
+  float se = 0.f;
+  for (int j = 0; j < n; ++j) se += expf(sm[j] - m);
+  const float inv_se = 1.f / se;
+  float wsum = 0.f;
+  for (int j = 0; j < n; ++j) wsum += expf(sm[j] - m) * inv_se + 1e-6f;
+  const float inv_wsum = 1.f / wsum;
+  const float s = softplus1(raw[3 * n]) + 0.1f;
+  const float lj_esp = logaddexpf_(x - logaddexpf_(s, x), -softplus1(s + x));
+  float acc = 0.f;
+  float mx = -INFINITY;
+  for (int j = 0; j < n; ++j) {
+    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
+    const float pre = a * (x - tanhf(raw[j]) * 10.f);
+    const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
+    mx = fmaxf(mx, term);
+  }
+  for (int j = 0; j < n; ++j) {
+    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
+    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
+    const float pre = a * (x - tanhf(raw[j]) * 10.f);
+    const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
+    acc += expf(term - mx);
+  }
+  return logaddexpf_(mx + logf(acc), lj_esp);  // :116
+}
+
+// softmax numerators e_j = 2^((t_j - max) log2 e) kept in registers, 1 / sum e_j and 1 / sum (softmax_j + eps)
+// (adaptive_sigmoids.py:133-135)
+template <int NC>
+FC_HD void sos_softmax_numerators(const float* sm, float (&e)[NC], float& inv_se, float& inv_wsum) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) m = fmaxf(m, sm[j]);
+  const float ml2 = m * FC_LOG2E;
+  float se = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    e[j] = fc_exp2(fmaf(sm[j], FC_LOG2E, -ml2));
+    se += e[j];
+  }
+  inv_se = fc_rcp(se);
+  float wsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) wsum += fmaf(e[j], inv_se, 1e-6f);
+  inv_wsum = fc_rcp(wsum);
+}
+
 template <int NC>
 FC_HD void sos_eval_t(float x, const float* raw, int n_runtime, float& y, float& logj) {
+  if constexpr (NC > 0) {
+    // MUFU-lean path (see fc_rcp2): ~65 special-function ops for NC = 10
+    float e[NC], inv_se, inv_wsum;
+    sos_softmax_numerators<NC>(raw + 2 * NC, e, inv_se, inv_wsum);
+    float ysum = 0.f, wtot = 0.f, jac = 0.f;
+#pragma unroll
+    for (int j = 0; j + 1 < NC; j += 2) {
+      float a0, sh0, a1, sh1, u0, u1;
+      sos_slope_shift(raw[j], raw[NC + j], a0, sh0, u0, u1);
+      sos_slope_shift(raw[j + 1], raw[NC + j + 1], a1, sh1, u0, u1);
+      const float w0 = fmaf(e[j], inv_se, 1e-6f) * inv_wsum, w1 = fmaf(e[j + 1], inv_se, 1e-6f) * inv_wsum;
+      float sig0, d0, sig1, d1;
+      fc_sigmoid_pair(a0 * (x - sh0), a1 * (x - sh1), sig0, d0, sig1, d1);
+      ysum = fmaf(w0, sig0, ysum);
+      wtot += w0;
+      jac = fmaf(w0 * a0, d0, jac);
+      ysum = fmaf(w1, sig1, ysum);
+      wtot += w1;
+      jac = fmaf(w1 * a1, d1, jac);
+    }
+    if constexpr (NC & 1) {
+      constexpr int j = NC - 1;
+      float a0, sh0, u0, u1, sig0, d0;
+      sos_slope_shift(raw[j], raw[NC + j], a0, sh0, u0, u1);
+      const float w0 = fmaf(e[j], inv_se, 1e-6f) * inv_wsum;
+      fc_sigmoid_parts(a0 * (x - sh0), sig0, d0);
+      ysum = fmaf(w0, sig0, ysum);
+      wtot += w0;
+      jac = fmaf(w0 * a0, d0, jac);
+    }
+    const float s = fc_softplus1(raw[3 * NC]) + 0.1f;
+    float y_esp, j_esp;
+    fc_ext_softplus(x, s, y_esp, j_esp);
+    y = ysum * fc_rcp(wtot) + y_esp;  // :127
+    const float J = jac + j_esp;
+    logj = J > 1e-30f ? fc_log_deriv(J) : sos_logj_saturated(x, raw, NC);
+    return;
+  }
   const int n = NC ? NC : n_runtime;
   // softmax weights + eps, renormalised (adaptive_sigmoids.py:133-135); the numerators are cheap enough (one FMA +
   // one ex2) to be recomputed per pass instead of kept in a register array of runtime length
@@ -698,25 +879,7 @@ FC_HD void sos_eval_t(float x, const float* raw, int n_runtime, float& y, float&
     logj = fc_log_deriv(J);
     return;
   }
-  // everything is saturated: redo the reduction in the log domain exactly as the reference composes it
-  const float lj_esp = logaddexpf_(x - logaddexpf_(s, x), -softplus1(s + x));
-  float acc = 0.f;
-  float mx = -INFINITY;
-  for (int j = 0; j < n; ++j) {
-    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
-    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
-    const float pre = a * (x - tanhf(raw[j]) * 10.f);
-    const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
-    mx = fmaxf(mx, term);
-  }
-  for (int j = 0; j < n; ++j) {
-    const float w = (expf(sm[j] - m) * inv_se + 1e-6f) * inv_wsum;
-    const float a = sigmoidf_(raw[n + j]) * (10.f - 0.1f) + 0.1f;
-    const float pre = a * (x - tanhf(raw[j]) * 10.f);
-    const float term = logf(w) + logf(a) + (pre - 2.f * softplus1(pre));
-    acc += expf(term - mx);
-  }
-  logj = logaddexpf_(mx + logf(acc), lj_esp);  // :116
+  logj = sos_logj_saturated(x, raw, n);  // everything is saturated
 }
 
 FC_HD void sos_eval(float x, const float* raw, int n, float& y, float& logj) { sos_eval_t<0>(x, raw, n, y, logj); }
@@ -757,8 +920,86 @@ FC_HD float fc_sech2(float t) {
   return 4.f * E * r * r;
 }
 
+// extended-softplus pieces of the backward: j = dy/dx, dj/dx, dy/ds, dj/ds at x, and softplus'(raw offset)
+FC_HD void sos_backward_esp(float x, float er, float& j_esp, float& dj_dx, float& dy_ds, float& dj_ds,
+                            float& dsoftplus) {
+  const float Ee = fc_sig_E(er);
+  float re, qe;
+  fc_rcp2(1.f + Ee, 2.f + Ee, re, qe);
+  const float s = (fmaxf(er, 0.f) + fc_log1p_unit_r(Ee, qe)) + 0.1f;
+  float unused;
+  fc_sig_finish(er, Ee, re, dsoftplus, unused);  // softplus' (1 above the threshold to fp32 precision)
+  float sp, omsp, dsp, sn, omsn, dsn;
+  fc_sigmoid_pair3(x - s, -(x + s), sp, omsp, dsp, sn, omsn, dsn);
+  j_esp = sp + sn;
+  dj_dx = dsp - dsn;
+  dy_ds = -sp + sn;
+  dj_ds = -dsp - dsn;
+}
+
 template <int NC>
 FC_HD void sos_backward_elem_t(float x, const float* raw, int n_runtime, float gy, float gl, float& gx, float* graw) {
+  if constexpr (NC > 0 && (NC % 2 == 0)) {
+    // MUFU-lean path: two passes instead of three (the softmax dot product sum_j p_j dL/dw_j is linear in the
+    // pass-1 totals: dot = [gy (S1 - ysum P) + gJ S2] / wsum with S1 = sum p_j sig_j, S2 = sum p_j a_j sig'_j,
+    // P = sum p_j), softmax numerators in registers, paired reciprocals: ~110 MUFU ops for NC = 10 instead of ~240.
+    float e[NC], inv_se, inv_wsum_unused;
+    sos_softmax_numerators<NC>(raw + 2 * NC, e, inv_se, inv_wsum_unused);
+    const float inv_wsum = fc_rcp(1.f + 1e-6f * (float)NC);  // sum_j (softmax_j + eps)
+    float ysum = 0.f, jac = 0.f, djac_dx = 0.f, S1 = 0.f, S2 = 0.f, P = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; j += 2) {
+      float a0, sh0, a1, sh1, u0, u1;
+      sos_slope_shift(raw[j], raw[NC + j], a0, sh0, u0, u1);
+      sos_slope_shift(raw[j + 1], raw[NC + j + 1], a1, sh1, u0, u1);
+      float sig0, om0, ds0, sig1, om1, ds1;
+      fc_sigmoid_pair3(a0 * (x - sh0), a1 * (x - sh1), sig0, om0, ds0, sig1, om1, ds1);
+      const float p0 = e[j] * inv_se, p1 = e[j + 1] * inv_se;
+      const float w0 = (p0 + 1e-6f) * inv_wsum, w1 = (p1 + 1e-6f) * inv_wsum;
+      ysum += w0 * sig0;
+      jac += w0 * a0 * ds0;
+      djac_dx += w0 * a0 * a0 * ds0 * (om0 - sig0);
+      S1 = fmaf(p0, sig0, S1);
+      S2 = fmaf(p0 * a0, ds0, S2);
+      P += p0;
+      ysum += w1 * sig1;
+      jac += w1 * a1 * ds1;
+      djac_dx += w1 * a1 * a1 * ds1 * (om1 - sig1);
+      S1 = fmaf(p1, sig1, S1);
+      S2 = fmaf(p1 * a1, ds1, S2);
+      P += p1;
+    }
+    float j_esp, dj_esp_dx, dy_esp_ds, dj_esp_ds, ds_der;
+    sos_backward_esp(x, raw[3 * NC], j_esp, dj_esp_dx, dy_esp_ds, dj_esp_ds, ds_der);
+    const float J = fmaxf(jac + j_esp, 1e-37f);
+    const float gJ = gl * fc_rcp(J);
+    gx = gy * (jac + j_esp) + gJ * (djac_dx + dj_esp_dx);
+    graw[3 * NC] = (gy * dy_esp_ds + gJ * dj_esp_ds) * ds_der;
+    const float dot = (gy * (S1 - ysum * P) + gJ * S2) * inv_wsum;
+#pragma unroll
+    for (int j = 0; j < NC; j += 2) {
+      float a0, sh0, dl0, sc0, a1, sh1, dl1, sc1;
+      sos_slope_shift(raw[j], raw[NC + j], a0, sh0, dl0, sc0);
+      sos_slope_shift(raw[j + 1], raw[NC + j + 1], a1, sh1, dl1, sc1);
+      float sig0, om0, ds0, sig1, om1, ds1;
+      fc_sigmoid_pair3(a0 * (x - sh0), a1 * (x - sh1), sig0, om0, ds0, sig1, om1, ds1);
+      const float p0 = e[j] * inv_se, p1 = e[j + 1] * inv_se;
+      const float w0 = (p0 + 1e-6f) * inv_wsum, w1 = (p1 + 1e-6f) * inv_wsum;
+      const float gw0 = gy * (sig0 - ysum) + gJ * a0 * ds0, gw1 = gy * (sig1 - ysum) + gJ * a1 * ds1;
+      // pre = a (x - sh):  d/d pre of [gy w sig + gJ w a ds] = gy w ds + gJ w a dds,  dds = ds (1 - 2 sig)
+      const float gpre0 = gy * w0 * ds0 + gJ * w0 * a0 * (ds0 * (om0 - sig0));
+      const float gpre1 = gy * w1 * ds1 + gJ * w1 * a1 * (ds1 * (om1 - sig1));
+      const float ga0 = gpre0 * (x - sh0) + gJ * w0 * ds0, ga1 = gpre1 * (x - sh1) + gJ * w1 * ds1;
+      // (graw may alias raw: every read of the slots of this pair is done, and the softmax block was read in pass 1)
+      graw[2 * NC + j] = p0 * (gw0 * inv_wsum - dot);
+      graw[2 * NC + j + 1] = p1 * (gw1 * inv_wsum - dot);
+      graw[NC + j] = ga0 * 9.9f * dl0;
+      graw[NC + j + 1] = ga1 * 9.9f * dl1;
+      graw[j] = -gpre0 * a0 * 10.f * sc0;
+      graw[j + 1] = -gpre1 * a1 * 10.f * sc1;
+    }
+    return;
+  }
   const int n = NC ? NC : n_runtime;
   const float* sm = raw + 2 * n;
   float m = -INFINITY;
@@ -846,43 +1087,127 @@ FC_HD void sos_backward_elem(float x, const float* raw, int n, float gy, float g
   sos_backward_elem_t<0>(x, raw, n, gy, gl, gx, graw);
 }
 
-// Numerical inverse for one element: find x with sos(x) = z.  Bracket [-lim, lim] grown until it
-// contains the root (no_analytic_inv/base.py:48-60, per element instead of batch-global), `iters`
-// bisection steps (:67-79), then two Newton steps with the analytic derivative and the reference's
-// +1e-7 damping (:30-33).
+// x-independent part of the transform, kept in registers across the evaluations of the numerical inverse:
+// mixture weights w_j and the reciprocal of their total, slopes a_j, shifts sh_j and the softplus offset s.
+// Same arithmetic, in the same order, as sos_eval_t, so forward and inverse see the same function.
 template <int NC>
-FC_HD void sos_invert_t(float z, const float* raw, int n, int iters, float lim, float& x, float& logj) {
-  float hi = lim, lo = -lim, y, lj;
+struct SosConsts {
+  float w[NC], a[NC], sh[NC];
+  float s, inv_wtot;
+};
+
+template <int NC>
+FC_HD void sos_precompute(const float* raw, SosConsts<NC>& k) {
+  float e[NC], inv_se, inv_wsum;
+  sos_softmax_numerators<NC>(raw + 2 * NC, e, inv_se, inv_wsum);
+  float wtot = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    k.w[j] = fmaf(e[j], inv_se, 1e-6f) * inv_wsum;
+    wtot += k.w[j];
+    float u0, u1;
+    sos_slope_shift(raw[j], raw[NC + j], k.a[j], k.sh[j], u0, u1);
+  }
+  k.inv_wtot = fc_rcp(wtot);
+  k.s = fc_softplus1(raw[3 * NC]) + 0.1f;
+}
+
+// value and (linear-domain) derivative from the precomputed constants: ~1.5 MUFU ops per sigmoid
+template <int NC>
+FC_HD void sos_eval_pre(float x, const SosConsts<NC>& k, float& y, float& J) {
+  float ysum = 0.f, jac = 0.f;
+#pragma unroll
+  for (int j = 0; j + 1 < NC; j += 2) {
+    float sig0, d0, sig1, d1;
+    fc_sigmoid_pair(k.a[j] * (x - k.sh[j]), k.a[j + 1] * (x - k.sh[j + 1]), sig0, d0, sig1, d1);
+    ysum = fmaf(k.w[j], sig0, ysum);
+    jac = fmaf(k.w[j] * k.a[j], d0, jac);
+    ysum = fmaf(k.w[j + 1], sig1, ysum);
+    jac = fmaf(k.w[j + 1] * k.a[j + 1], d1, jac);
+  }
+  if constexpr (NC & 1) {
+    constexpr int j = NC - 1;
+    float sig0, d0;
+    fc_sigmoid_parts(k.a[j] * (x - k.sh[j]), sig0, d0);
+    ysum = fmaf(k.w[j], sig0, ysum);
+    jac = fmaf(k.w[j] * k.a[j], d0, jac);
+  }
+  float y_esp, j_esp;
+  fc_ext_softplus(x, k.s, y_esp, j_esp);
+  y = ysum * k.inv_wtot + y_esp;
+  J = jac + j_esp;
+}
+
+// Numerical inverse for one element: find x with sos(x) = z.
+// The reference grows a batch-global bracket [-lim, lim] until it holds every root (no_analytic_inv/base.py
+// :48-60), halves it `iters` times (:67-79) and polishes with two damped Newton steps (:23-33): ~55 full-batch
+// forward passes.  Here each element keeps its own bracket and runs a safeguarded Newton iteration (a Newton step
+// when it lands inside the bracket and at least halves the previous step, a bisection step otherwise), which reaches
+// the same fp32 root in 4-8 evaluations; `iters` caps the iteration count, and the reference's two damped Newton
+// steps close the solve.  Eval(x, y, J) returns the value and the derivative.
+template <class Eval>
+FC_HD float sos_solve(float z, int iters, float lim, const Eval& eval) {
+  float hi = lim, lo = -lim, y, J;
   for (int g = 0; g < 64; ++g) {
-    sos_eval_t<NC>(hi, raw, n, y, lj);
+    eval(hi, y, J);
     if (!(z > y)) break;
     hi *= 1.5f;
   }
   hi += 1.f;
   for (int g = 0; g < 64; ++g) {
-    sos_eval_t<NC>(lo, raw, n, y, lj);
+    eval(lo, y, J);
     if (!(z < y)) break;
     lo *= 1.5f;
   }
   lo -= 1.f;
+  // the transform is x + O(1) in its linear tails: z itself is a good first iterate
+  float x = fminf(fmaxf(z, lo), hi);
+  float dxold = hi - lo, dx = dxold;
+  const float ftol = 2.4e-7f * fmaxf(1.f, fabsf(z));
+  eval(x, y, J);
+  float f = y - z;
   for (int i = 0; i < iters; ++i) {
-    const float mid = 0.5f * (hi + lo);
-    if (mid == hi || mid == lo) break;  // fp32 resolution reached
-    sos_eval_t<NC>(mid, raw, n, y, lj);
-    if (y > z) {
-      hi = mid;
-    } else if (y < z) {
-      lo = mid;
+    if (f < 0.f) lo = x; else hi = x;
+    const bool inside = ((x - hi) * J - f) * ((x - lo) * J - f) < 0.f;
+    const bool shrinking = fabsf(2.f * f) <= fabsf(dxold * J);
+    dxold = dx;
+    float xn;
+    if (inside && shrinking) {
+      dx = f * fc_rcp(J);
+      xn = x - dx;
     } else {
-      hi = mid;
-      lo = mid;
+      dx = 0.5f * (hi - lo);
+      xn = lo + dx;
     }
+    if (xn == x || !(hi > lo)) break;  // fp32 resolution reached
+    const bool last = fabsf(xn - x) <= 1.2e-7f * fabsf(x);  // a sub-ulp step: the polish below finishes it
+    x = xn;
+    if (last) break;
+    eval(x, y, J);
+    f = y - z;
+    if (fabsf(f) <= ftol) break;  // residual at the rounding noise of y: the polish below finishes
   }
-  x = 0.5f * (hi + lo);
-  for (int i = 0; i < 2; ++i) {
-    sos_eval_t<NC>(x, raw, n, y, lj);
-    x = x - (y - z) / (expf(lj) + 1e-7f);
+  for (int i = 0; i < 2; ++i) {  // base.py:30-33
+    eval(x, y, J);
+    x = x - (y - z) / (J + 1e-7f);
   }
+  return x;
+}
+
+template <int NC>
+FC_HD void sos_invert_t(float z, const float* raw, int n, int iters, float lim, float& x, float& logj) {
+  if constexpr (NC > 0) {
+    SosConsts<NC> k;
+    sos_precompute<NC>(raw, k);
+    x = sos_solve(z, iters, lim, [&](float xx, float& y, float& J) { sos_eval_pre<NC>(xx, k, y, J); });
+  } else {
+    x = sos_solve(z, iters, lim, [&](float xx, float& y, float& J) {
+      float lj;
+      sos_eval_t<0>(xx, raw, n, y, lj);
+      J = expf(lj);
+    });
+  }
+  float y;
   sos_eval_t<NC>(x, raw, n, y, logj);
 }
 

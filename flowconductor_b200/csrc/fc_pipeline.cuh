@@ -71,9 +71,21 @@ __device__ __forceinline__ int feature_stride(const Op& op, long) {
   return op.P();
 }
 
+// Second __launch_bounds__ argument of the forward ring.  0 (unspecified) lets ptxas aim for two resident CTAs, i.e. at
+// most 64 registers per thread, which the HBM-bound spline / affine rings want; an Op that is bound by arithmetic sets
+// kMinBlocks = 1 to get the full 128 registers instead of spills.
+template <class Op, class = void>
+struct PipeMinBlocks {
+  static constexpr int value = 0;
+};
+template <class Op>
+struct PipeMinBlocks<Op, decltype((void)Op::kMinBlocks)> {
+  static constexpr int value = Op::kMinBlocks;
+};
+
 // kSimple: D_t == 32 (one feature per lane, one row per warp pass): the feature loop and the segment logic fold away.
 template <class Op, bool kSimple>
-__global__ void __launch_bounds__(512) pipelined_apply_kernel(const PipeArgs pa, const Op op) {
+__global__ void __launch_bounds__(512, PipeMinBlocks<Op>::value) pipelined_apply_kernel(const PipeArgs pa, const Op op) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LayerArgs& a = pa.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

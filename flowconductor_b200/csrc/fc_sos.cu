@@ -10,30 +10,21 @@
 
 namespace fc {
 
-struct SosOp {
+template <int kMB>
+struct SosOpT {
+  static constexpr int kMinBlocks = kMB;
   int n;
   float offset;
-  int inverse, iters;
-  float lim;
   __device__ __forceinline__ int P() const { return 3 * n + 1; }
   __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned& status) const {
     float lj;
-    if (!inverse) {
-      if (n == 10) {  // the default of ConditionalSumOfSigmoidsTransform (conditional.py:746): fully unrolled
-        sos_eval_t<10>(x, p, n, y, lj);
-      } else {
-        sos_eval_t<0>(x, p, n, y, lj);
-      }
-      y += offset;
-      lad = lj;
+    if (n == 10) {  // the default of ConditionalSumOfSigmoidsTransform (conditional.py:746): fully unrolled
+      sos_eval_t<10>(x, p, n, y, lj);
     } else {
-      if (n == 10) {
-        sos_invert_t<10>(x - offset, p, n, iters, lim, y, lj);
-      } else {
-        sos_invert_t<0>(x - offset, p, n, iters, lim, y, lj);
-      }
-      lad = -lj;
+      sos_eval_t<0>(x, p, n, y, lj);
     }
+    y += offset;
+    lad = lj;
     (void)status;
   }
   __device__ __forceinline__ void backward(float x, const float* p, float gy, float gl, float& gx, float* gp) const {
@@ -44,6 +35,28 @@ struct SosOp {
     } else {
       sos_backward_elem_t<0>(x, p, n, gy, gl, gx, gp);
     }
+  }
+};
+
+using SosOp = SosOpT<0>;
+
+// the numerical inverse is its own kernel instantiation: its register-resident constants must not raise the
+// register count of the forward kernel
+struct SosInverseOp {
+  int n;
+  float offset;
+  int iters;
+  float lim;
+  __device__ __forceinline__ int P() const { return 3 * n + 1; }
+  __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned& status) const {
+    float lj;
+    if (n == 10) {
+      sos_invert_t<10>(x - offset, p, n, iters, lim, y, lj);
+    } else {
+      sos_invert_t<0>(x - offset, p, n, iters, lim, y, lj);
+    }
+    lad = -lj;
+    (void)status;
   }
 };
 
@@ -68,9 +81,23 @@ extern "C" int fc_sos_apply(const float* x, int64_t x_row_stride, const float* p
   a.x_stride = x_row_stride; a.p_stride = params_row_stride; a.y_stride = y_row_stride;
   a.B = B; a.D_t = D; a.n_copy = 0; a.tcols = nullptr; a.ccols = nullptr;
   a.accumulate = accumulate_logabsdet;
-  SosOp op;
-  op.n = n_sigmoids; op.offset = offset; op.inverse = inverse; op.iters = bisection_iterations; op.lim = lim;
   const size_t smem = plan_tiles(a, 3 * n_sigmoids + 1);
+  if (inverse) {
+    SosInverseOp op;
+    op.n = n_sigmoids; op.offset = offset; op.iters = bisection_iterations; op.lim = lim;
+    const int piped = try_launch_pipelined(a, op, 3 * n_sigmoids + 1, (int)x_row_stride, (cudaStream_t)stream);
+    if (piped != 0) return piped < 0 ? piped : FC_OK;
+    return launch_apply(a, op, smem, (cudaStream_t)stream);
+  }
+  static const bool full_regs = env_int("FC_SOS_FULLREGS", 1) != 0;
+  if (full_regs) {  // 128 registers, one CTA per SM: no spills (the kernel is bound by the special-function unit)
+    SosOpT<1> op1;
+    op1.n = n_sigmoids; op1.offset = offset;
+    const int piped1 = try_launch_pipelined(a, op1, 3 * n_sigmoids + 1, (int)x_row_stride, (cudaStream_t)stream);
+    if (piped1 != 0) return piped1 < 0 ? piped1 : FC_OK;
+  }
+  SosOp op;
+  op.n = n_sigmoids; op.offset = offset;
   const int piped = try_launch_pipelined(a, op, 3 * n_sigmoids + 1, (int)x_row_stride, (cudaStream_t)stream);
   if (piped != 0) return piped < 0 ? piped : FC_OK;
   return launch_apply(a, op, smem, (cudaStream_t)stream);
@@ -94,7 +121,7 @@ extern "C" int fc_sos_backward(const float* x, int64_t x_row_stride, const float
   a.gx_stride = gx_row_stride; a.gp_stride = gp_row_stride;
   a.B = B; a.D_t = D; a.n_copy = 0; a.tcols = nullptr; a.ccols = nullptr;
   SosOp op;
-  op.n = n_sigmoids; op.offset = 0.f; op.inverse = 0; op.iters = 0; op.lim = 0.f;
+  op.n = n_sigmoids; op.offset = 0.f;
   const size_t smem = plan_tiles(a, 3 * n_sigmoids + 1);
   const int piped = try_launch_pipelined_backward(a, op, 3 * n_sigmoids + 1, (int)x_row_stride, (cudaStream_t)stream);
   if (piped != 0) return piped < 0 ? piped : FC_OK;

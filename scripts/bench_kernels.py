@@ -114,7 +114,7 @@ def main():
     set_env()
     for name, fn, nbytes in (
             ("sos_fwd cfg4 D=32 n=10", lambda: ops.sos_layer(xs, ps, ns, 0.0, False, 50, 120.0), Bs * (4 * ps.shape[1] + 8 * Ds + 4)),
-            ("sos_inv cfg4 D=32 n=10 (bisection + Newton)", lambda: ops.sos_layer(xs, ps, ns, 0.0, True, 50, 120.0), Bs * (4 * ps.shape[1] + 8 * Ds + 4)),
+            ("sos_inv cfg4 D=32 n=10 (safeguarded Newton)", lambda: ops.sos_layer(xs, ps, ns, 0.0, True, 50, 120.0), Bs * (4 * ps.shape[1] + 8 * Ds + 4)),
             ("sos_bwd cfg4 D=32 n=10", lambda: ops.sos_layer_backward(xs, ps, gys, gls, ns), Bs * (8 * ps.shape[1] + 12 * Ds + 4))):
         med, best = timeit(fn)
         gbs = nbytes / med / 1e6

@@ -71,4 +71,33 @@ void hm_sos_invert(const float* z, const float* params, float* x, float* logj, l
   for (long i = 0; i < n; ++i)
     sos_invert(z[i], params + i * (3 * n_sigmoids + 1), n_sigmoids, iters, lim, x[i], logj[i]);
 }
+
+// compile-time n = 10 instantiations (what the kernels run for the default sigmoid count)
+void hm_sos_apply_n10(const float* x, const float* params, float* y, float* logj, long n) {
+  for (long i = 0; i < n; ++i) sos_eval_t<10>(x[i], params + i * 31, 10, y[i], logj[i]);
+}
+
+void hm_sos_backward_n10(const float* x, const float* params, const float* gy, const float* gl, float* gx, float* gp,
+                         long n) {
+  for (long i = 0; i < n; ++i) sos_backward_elem_t<10>(x[i], params + i * 31, 10, gy[i], gl[i], gx[i], gp + i * 31);
+}
+
+// the instantiation the kernels use for n = 10 (constants precomputed into registers); also returns the largest
+// number of function evaluations any element needed
+long hm_sos_invert_n10(const float* z, const float* params, float* x, float* logj, long n, int iters, float lim) {
+  long worst = 0;
+  for (long i = 0; i < n; ++i) {
+    const float* raw = params + i * 31;
+    sos_invert_t<10>(z[i], raw, 10, iters, lim, x[i], logj[i]);
+    SosConsts<10> k;
+    sos_precompute<10>(raw, k);
+    long evals = 0;
+    sos_solve(z[i], iters, lim, [&](float xx, float& y, float& J) {
+      ++evals;
+      sos_eval_pre<10>(xx, k, y, J);
+    });
+    worst = evals > worst ? evals : worst;
+  }
+  return worst;
+}
 }

@@ -196,3 +196,22 @@ def test_sum_of_sigmoids(hm, gold, name):
     assert ((xi.double() - x.double()).abs() / scale).max() < 1e-3
     assert ((xi.double() - ref).abs() / scale).max() < 1e-3
     assert (-lji.sum(-1).double() - gold[name + "/inv_lad64"]).abs().max() < 5e-3
+    if ns == 10:  # the compile-time-n instantiations (paired reciprocals, two-pass backward) the n = 10 kernels run
+        y10, lj10 = torch.empty_like(x), torch.empty_like(x)
+        hm.hm_sos_apply_n10(fptr(x), fptr(p), fptr(y10), fptr(lj10), ctypes.c_long(x.numel()))
+        assert_parity(y10, gold[name + "/y32"], gold[name + "/y64"], 1e-5, floor, name + " y (n10)")
+        assert_parity(lj10.sum(-1), gold[name + "/lad32"], gold[name + "/lad64"], 1e-5, 1.0, name + " lad (n10)")
+        gx10, gp10 = torch.empty_like(x), torch.empty_like(p)
+        hm.hm_sos_backward_n10(fptr(x), fptr(p), fptr(gy), fptr(gl), fptr(gx10), fptr(gp10), ctypes.c_long(x.numel()))
+        s = max(1e-2, gold[name + "/gx64"].abs().mean().item())
+        assert_parity(gx10, gold[name + "/gx32"], gold[name + "/gx64"], 1e-4, s, name + " gx (n10)")
+        s = max(1e-2, gold[name + "/gp64"].abs().mean().item())
+        assert_parity(gp10, gold[name + "/gp32"], gold[name + "/gp64"], 1e-4, s, name + " gp (n10)")
+        xi10, lji10 = torch.empty_like(x), torch.empty_like(x)
+        hm.hm_sos_invert_n10.restype = ctypes.c_long
+        worst = hm.hm_sos_invert_n10(fptr(z), fptr(p), fptr(xi10), fptr(lji10), ctypes.c_long(x.numel()), 50,
+                                     ctypes.c_float(120.0))
+        assert ((xi10.double() - ref).abs() / scale).max() < 1e-3
+        assert (-lji10.sum(-1).double() - gold[name + "/inv_lad64"]).abs().max() < 5e-3
+        assert worst <= 16, worst  # safeguarded Newton: far fewer evaluations than 50 bisections + brackets
+        print("sos inverse: worst-case evaluations per element", worst)
