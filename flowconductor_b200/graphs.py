@@ -1,0 +1,104 @@
+"""CUDA-graph capture of a fixed-shape call through a flow.
+
+`CompositeTransform._cascade` (flowcon/transforms/base.py:44-52) issues a handful of launches per layer and
+`AutoregressiveTransform.inverse` (flowcon/transforms/autoregressive/autoregressive.py:44-53) repeats the
+whole conditioner D times: at small batches (cfg 1, the per-GPU shards of cfg 3, sampling from a MAF) the step is
+bound by launch latency, not by the kernels.  The B200-first answer is a CUDA graph, not a tracing compiler: the
+launch sequence of one call is recorded once, on static buffers, and replayed with a single `cudaGraphLaunch`.
+
+    g = graphs.capture(flow.log_prob, x_example)            # records flow.log_prob(x) for x.shape rows
+    lp = g(x)                                               # copy-in, replay; returns the static output
+    s = graphs.capture_sampler(flow, 4096)                  # records flow.sample(4096)
+    z = s()                                                 # fresh noise every replay (philox state is graph-safe)
+
+Everything the library launches goes to torch's current stream, so the kernels behind the C ABI are captured like
+any other work; the path has no host synchronisation as long as the splines use linear tails (the domain check of
+`tails=None` reads a device status word on the host, `transforms/splines.py`).  Inference only: the captured call
+runs under `torch.no_grad()`.  There is no CPU fallback: capturing needs CUDA tensors.
+"""
+import torch
+
+__all__ = ["GraphedCall", "capture", "capture_sampler"]
+
+
+def _flatten(out):
+    if isinstance(out, torch.Tensor):
+        return [out]
+    if isinstance(out, (tuple, list)):
+        flat = []
+        for o in out:
+            flat.extend(_flatten(o))
+        return flat
+    raise TypeError("graph-captured callables must return tensors or tuples of tensors")
+
+
+class GraphedCall:
+    """One recorded call `fn(*inputs)` at fixed input shapes.
+
+    The example inputs define shapes, dtypes and the device; they are copied into static buffers owned by this
+    object.  `__call__` copies new inputs into those buffers, replays the graph and returns the static outputs
+    (valid until the next replay — `clone()` what must live longer, or pass `clone=True`)."""
+
+    def __init__(self, fn, *example_inputs, warmup=3, pool=None):
+        if not example_inputs and not torch.cuda.is_available():
+            raise RuntimeError("flowconductor_b200.graphs needs a CUDA device (no CPU fallback)")
+        for t in example_inputs:
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise RuntimeError("graph capture needs CUDA tensors as inputs: flowconductor_b200 runs only on the "
+                                   "GPU (no CPU fallback)")
+        self._fn = fn
+        self._static_in = [t.detach().clone() for t in example_inputs]
+        self.device = self._static_in[0].device if self._static_in else torch.device("cuda", torch.cuda.current_device())
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(self.device), torch.no_grad():
+            # warm-up on a side stream: builds the packed-weight plans, sets kernel attributes, fills the allocator
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    fn(*self._static_in)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(self.graph, pool=pool):
+                self._static_out = fn(*self._static_in)
+        self._flat_out = _flatten(self._static_out)
+        self.replays = 0
+
+    def __call__(self, *inputs, clone=False):
+        if len(inputs) != len(self._static_in):
+            raise ValueError("expected {} inputs, got {}".format(len(self._static_in), len(inputs)))
+        for dst, src in zip(self._static_in, inputs):
+            if src.shape != dst.shape or src.dtype != dst.dtype:
+                raise ValueError("graph was captured for inputs of shape {} / {}, got {} / {}".format(
+                    tuple(dst.shape), dst.dtype, tuple(src.shape), src.dtype))
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        if not clone:
+            return self._static_out
+        if isinstance(self._static_out, torch.Tensor):
+            return self._static_out.clone()
+        return type(self._static_out)(o.clone() if isinstance(o, torch.Tensor) else o for o in self._static_out)
+
+    @property
+    def static_inputs(self):
+        """The graph's own input buffers: fill them in place to skip the copy-in."""
+        return self._static_in
+
+
+def capture(fn, *example_inputs, warmup=3, pool=None):
+    """Record `fn(*example_inputs)` (e.g. `flow.log_prob`, `transform.inverse`) into a CUDA graph."""
+    return GraphedCall(fn, *example_inputs, warmup=warmup, pool=pool)
+
+
+def capture_sampler(flow, num_samples, context=None, with_log_prob=False, warmup=3):
+    """Record `flow.sample(num_samples, context)` (or `sample_and_log_prob`).  The base-density noise is drawn
+    inside the graph; torch registers the philox offset with the capture, so every replay draws fresh noise."""
+    method = flow.sample_and_log_prob if with_log_prob else flow.sample
+    if context is None:
+        if not next(flow.parameters()).is_cuda:
+            raise RuntimeError("graph capture needs the flow on a CUDA device (no CPU fallback)")
+        with torch.cuda.device(next(flow.parameters()).device):
+            return GraphedCall(lambda: method(num_samples), warmup=warmup)
+    return GraphedCall(lambda c: method(num_samples, context=c), context, warmup=warmup)

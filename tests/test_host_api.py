@@ -212,3 +212,11 @@ def test_tensorcore_path_selection():
     lin = torch.nn.Linear(16, 8)
     xi = torch.randn(4, 16)
     assert torch.equal(tc_autograd.module_linear(lin, xi), torch.nn.functional.linear(xi, lin.weight, lin.bias))
+
+
+def test_graph_capture_refuses_cpu_tensors():
+    """graphs.capture has no CPU fallback: it raises before touching CUDA when given host tensors."""
+    from flowconductor_b200 import graphs
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        graphs.capture(lambda x: x * 2, torch.zeros(4, 2))
