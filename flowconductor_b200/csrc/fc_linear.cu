@@ -181,6 +181,7 @@ __device__ __forceinline__ void drain_partial(uint32_t taddr, float* acc) {
 template <int EPI, int BN, int BK, int STAGES, int KC, int PPAD, int MODE, int EW, bool TS, int SW>
 __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                          const LinArgs la, const StoreEpi se, const RqsEpi re) {
   constexpr int CTAS = MODE == 2 ? 2 : 1;  // CTAs per MMA
   constexpr bool MC = MODE == 3;           // weight boxes multicast inside the cluster
@@ -326,16 +327,33 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
         for (int mp = unit0; mp < n_units; mp += unit_step) {
           const int mt = (mp / ks_n) * CL + rank;
           for (int nt = 0; nt < n_tiles; ++nt) {
-            // a T128 tile of 128 rows x BN columns is contiguous: tile mt, column groups nt*BN/4 ..
+            // a T128 tile of 128 rows x BN columns is contiguous: tile mt, column groups nt*BN/4 ..;
+            // a row-major tile moves as BN/32 boxes of 128 rows x 32 columns (128-byte swizzled rows in the staging
+            // tile, tensor maps tmO / tmR; rows and columns outside the matrix are zero-filled / clipped by the TMA)
             const int64_t off = (int64_t)mt * kBM * se.ldo + (int64_t)nt * kBM * BN;
             if (se.residual != nullptr) {
               mbar_expect_tx(pfull_bar, kTileBytes);
-              bulk_load_1d(params_s, se.residual + (int64_t)mt * kBM * se.ldr + (int64_t)nt * kBM * BN, kTileBytes, pfull_bar);
+              if (se.tiled) {
+                bulk_load_1d(params_s, se.residual + (int64_t)mt * kBM * se.ldr + (int64_t)nt * kBM * BN, kTileBytes,
+                             pfull_bar);
+              } else {
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb)
+                  tma_load_2d(params_s + (uint32_t)(cb * kBM * 128), &tmR, nt * BN + cb * 32, mt * kBM, pfull_bar);
+              }
             } else {
               mbar_arrive(pfull_bar);  // nothing to bring in: the tile may be written right away
             }
             mbar_wait(pempty_bar, ph);  // all epilogue warps have written their part (generic -> async fenced)
-            bulk_store_1d(se.out + off, params_s, kTileBytes);
+            if (se.tiled) {
+              bulk_store_1d(se.out + off, params_s, kTileBytes);
+            } else {
+#pragma unroll
+              for (int cb = 0; cb < BN / 32; ++cb)
+                if (nt * BN + cb * 32 < se.n_out)
+                  tma_store_2d(&tmO, nt * BN + cb * 32, mt * kBM, params_s + (uint32_t)(cb * kBM * 128));
+              bulk_commit_group();
+            }
             bulk_store_wait_read();     // the staging tile may be overwritten (next skip connection / next result)
             ph ^= 1u;
           }
@@ -720,10 +738,14 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           mbar_wait(pfull_bar, pph);
           const uint32_t sb = params_s + (uint32_t)(((half * (NCOL / 4)) * kBM + rt) * 16);
           const bool res = se.residual != nullptr;
+          const bool otiled = se.tiled != 0;
 #pragma unroll
           for (int j = 0; j < NCOL / 4; ++j) {
             float4 o = make_float4(av[4 * j + 0], av[4 * j + 1], av[4 * j + 2], av[4 * j + 3]);
-            const uint32_t a = sb + (uint32_t)(j * kBM * 16);
+            // row-major staging: box cb = 32 columns, row rt = 128 bytes, 16-byte chunk ci at ci ^ (rt & 7)
+            const int cg = half * (NCOL / 4) + j;  // 4-column group inside the tile
+            const uint32_t a = otiled ? sb + (uint32_t)(j * kBM * 16)
+                                      : params_s + (uint32_t)((cg >> 3) * kBM * 128 + rt * 128 + (((cg & 7) ^ (rt & 7)) << 4));
             if (res) {
               const float4 r = lds128(a);
               o.x += r.x;
@@ -974,6 +996,16 @@ static int epilogue_warps() {
   return v == 16 ? 16 : 8;
 }
 
+// row-major results through the staged store kernel (TMA tensor-map stores); FC_LINEAR_STAGED_RM=0: direct stores from
+// the shared-memory-operand kernel
+static int staged_row_major() {
+  static int v = [] {
+    const char* e = getenv("FC_LINEAR_STAGED_RM");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
 // activation operand in tensor memory (final-layer kernels, mode 1); FC_LINEAR_TS=0 switches back to shared memory
 static int operand_in_tmem() {
   static int v = [] {
@@ -1042,6 +1074,15 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   if (rc != FC_OK) return rc;
   rc = make_map(&tmB, w->w, (uint64_t)2 * w->n_pad, (uint64_t)w->k_pad, (uint64_t)w->k_pad, BN / CL, BK);
   if (rc != FC_OK) return rc;
+  CUtensorMap tmO = tmA, tmR = tmA;  // only the staged store kernel with a row-major result reads these
+  if (EPI == 3 && !se.tiled) {
+    rc = make_map(&tmO, se.out, (uint64_t)M, (uint64_t)se.n_out, (uint64_t)se.ldo, kBM, 32);
+    if (rc != FC_OK) return rc;
+    if (se.residual) {
+      rc = make_map(&tmR, se.residual, (uint64_t)M, (uint64_t)se.n_out, (uint64_t)se.ldr, kBM, 32);
+      if (rc != FC_OK) return rc;
+    }
+  }
   la.M = (int)M;
   la.num_k_stages = (K + BK - 1) / BK;
   if (la.k_slices < 1) la.k_slices = 1;
@@ -1081,7 +1122,7 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, la, se, re) != cudaSuccess) return FC_ERR_CUDA;
+  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmR, la, se, re) != cudaSuccess) return FC_ERR_CUDA;
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -1237,6 +1278,12 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
       return launch_linear<3, 128, 32, 4, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
     if (pair_mma()) return launch_linear<3, 128, 16, 8, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
     return launch_linear<3, 128, 16, 6, 0, 32, 1, 8, true>(A, lda, M, K, w, la, se, re, st);
+  }
+  if (!o_tiled && staged_store() && staged_row_major() && pair_mma() && w->n_pad % 128 == 0) {
+    // row-major result: same kernel, the staging tile leaves (and the skip connection arrives) through 2-D tensor maps
+    la.num_n_tiles = (n_out + 127) / 128;
+    if (wide_slots() && K > 64) return launch_linear<3, 128, 32, 4, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
+    return launch_linear<3, 128, 16, 8, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
   }
   return launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, st);
 }

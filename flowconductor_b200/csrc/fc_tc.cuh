@@ -133,6 +133,14 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t src, uint32_t
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// 2-D tiled store shared -> global through a tensor map (rows / columns outside the tensor are clipped); joins the
+// issuing thread's current bulk group: close it with bulk_commit_group()
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* t, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(t), "r"(c0), "r"(c1),
+               "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the issuing thread's bulk stores have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

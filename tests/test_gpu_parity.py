@@ -419,6 +419,8 @@ def _gemm_err(got, want64):
     (4099, 256, 512, True, False, True, False, False),    # two N tiles of the 256-wide kernel
     (5000, 8, 64, False, True, False, False, False),      # K shorter than one ring slot
     (300, 752, 32, False, False, False, False, False),    # input-gradient shape: long reduction, narrow output
+    (777, 256, 132, True, True, True, False, False),      # row-major staged store: last 32-column box clipped to 4
+    (130, 96, 100, False, False, True, False, False),     # two row tiles, one partial column tile, skip connection
     (1000, 256, 256, False, False, False, True, False),   # T128 in, rows out
     (1000, 64, 256, False, False, False, False, True),    # rows in, T128 out: staged kernel
     (1000, 256, 256, True, True, True, True, True),       # staged kernel with skip connection, CTA pairs, ragged
