@@ -23,7 +23,7 @@ LINEAR_A_T128, LINEAR_OUT_T128 = 1, 2
 
 EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
-           "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_transpose",
+           "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
            "fc_version", "fc_built_for_sm"]
 
@@ -82,6 +82,7 @@ def lib():
         L.fc_linear_affine_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, vp, i64,
                                              vp, i32, i32, Cols, Cols, i32, i32, i32, vp]
         L.fc_linear_splitk_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp]
+        L.fc_linear_splitk_t_apply.argtypes = [vp, i64, i64, i64, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp]
         L.fc_linear_transpose.argtypes = [vp, i64, i64, i32, vp, i64, vp]
         L.fc_linear_pack_transposed.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp, vp]
         L.fc_version.restype = ctypes.c_char_p

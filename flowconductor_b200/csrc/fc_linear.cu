@@ -66,7 +66,8 @@ struct LinArgs {
   int num_m_tiles, num_n_tiles;
   int n_pad;         // rows of one weight plane (lo plane starts at row n_pad of the weight tensor map)
   int relu_in;       // ReLU applied to A while splitting
-  int a_tiled;       // A is stored in the T128 activation layout (include/flowcon_b200.h)
+  int a_tiled;       // 1: A is stored in the T128 activation layout (include/flowcon_b200.h); 2: A is given TRANSPOSED,
+                     //    [K, M] row-major (weight gradients: grad_y [B, N] is the A operand of grad_y^T x as it lies)
   int k_slices;      // split-K: the reduction is cut into k_slices ranges of num_k_stages slots, one work unit each
   int debug;         // FC_LINEAR_DEBUG: 4 = record the cycle counters (only in builds with -DFC_LINEAR_PROFILE=1)
   const float* bias;  // [n_pad]
@@ -296,7 +297,9 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
               }
               const uint32_t st = base + s * SM::STAGE_BYTES;
               mbar_expect_tx(full_bar(s), SM::A_BYTES + 2 * SM::B_BYTES);
-              if (la.a_tiled) {
+              if (la.a_tiled == 2) {
+                tma_load_2d(st, &tmA, mt * kBM, (k_base + kc) * BK, full_bar(s));  // BK rows of 128 values, as they lie
+              } else if (la.a_tiled) {
                 tma_load_4d(st, &tmA, 0, 0, (k_base + kc) * (BK / 4), mt, full_bar(s));
               } else {
                 tma_load_2d(st, &tmA, (k_base + kc) * BK, mt * kBM, full_bar(s));
@@ -350,8 +353,9 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
             } else {
 #pragma unroll
               for (int cb = 0; cb < BN / 32; ++cb)
-                if (nt * BN + cb * 32 < se.n_out)
-                  tma_store_2d(&tmO, nt * BN + cb * 32, mt * kBM, params_s + (uint32_t)(cb * kBM * 128));
+                if (nt * BN + cb * 32 < se.n_out)  // split-K: range i writes rows [i * slice_rows, ...) of the partials
+                  tma_store_2d(&tmO, nt * BN + cb * 32, (mp % ks_n) * (int)se.slice_stride + mt * kBM,
+                               params_s + (uint32_t)(cb * kBM * 128));
               bulk_commit_group();
             }
             bulk_store_wait_read();     // the staging tile may be overwritten (next skip connection / next result)
@@ -508,6 +512,12 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
 #pragma unroll
           for (int h = 0; h < BK / 16; ++h) {  // 16 k-values at a time
             float f[16];
+            if (la.a_tiled == 2) {
+              // transposed operand: the tile is [BK k-rows][128 values]; this thread's row is column r of every k-row
+              // (a warp reads 32 consecutive words: conflict-free)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = lds32(st + (uint32_t)((h * 16 + i) * (kBM * 4) + r * 4));
+            } else
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int cc = h * 4 + c;  // 16-byte chunk of the row
@@ -960,6 +970,21 @@ static int make_map(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? FC_OK : FC_ERR_CUDA;
 }
 
+// un-swizzled 2-D map: boxes of box_rows x box_cols (box_cols * 4 bytes a multiple of 16)
+static int make_map_plain(CUtensorMap* m, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, int box_rows,
+                          int box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return FC_ERR_CUDA;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FC_OK : FC_ERR_CUDA;
+}
+
 // T128 activation buffer [tiles][W/4 column groups][128 rows][4 floats]: one (tile, column group) is 2 KB contiguous,
 // described as 8 rows of 256 B so that the TMA moves wide rows; box = BK/4 column groups of one tile.
 static int make_map_t128(CUtensorMap* m, const float* ptr, uint64_t tiles, uint64_t width, int bk) {
@@ -1069,14 +1094,17 @@ static int launch_linear(const float* A, int64_t lda, int64_t M, int K, const fc
   static_assert(SM::TOTAL <= 232448, "shared memory per CTA");
   if (w->n_pad % BN != 0 || w->k_pad % 32 != 0) return FC_ERR_INVALID_ARGUMENT;
   CUtensorMap tmA, tmB;
-  int rc = la.a_tiled ? make_map_t128(&tmA, A, (uint64_t)((M + kBM - 1) / kBM), (uint64_t)lda, BK)
-                      : make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, BK);
+  int rc = la.a_tiled == 2 ? make_map_plain(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, kBM)
+           : la.a_tiled    ? make_map_t128(&tmA, A, (uint64_t)((M + kBM - 1) / kBM), (uint64_t)lda, BK)
+                           : make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM, BK);
   if (rc != FC_OK) return rc;
   rc = make_map(&tmB, w->w, (uint64_t)2 * w->n_pad, (uint64_t)w->k_pad, (uint64_t)w->k_pad, BN / CL, BK);
   if (rc != FC_OK) return rc;
   CUtensorMap tmO = tmA, tmR = tmA;  // only the staged store kernel with a row-major result reads these
   if (EPI == 3 && !se.tiled) {
-    rc = make_map(&tmO, se.out, (uint64_t)M, (uint64_t)se.n_out, (uint64_t)se.ldo, kBM, 32);
+    // (split-K: the partial products of all ranges form one matrix of k_slices * slice_stride rows)
+    const uint64_t out_rows = la.k_slices > 1 ? (uint64_t)la.k_slices * (uint64_t)se.slice_stride : (uint64_t)M;
+    rc = make_map(&tmO, se.out, out_rows, (uint64_t)se.n_out, (uint64_t)se.ldo, kBM, 32);
     if (rc != FC_OK) return rc;
     if (se.residual) {
       rc = make_map(&tmR, se.residual, (uint64_t)M, (uint64_t)se.n_out, (uint64_t)se.ldr, kBM, 32);
@@ -1357,6 +1385,32 @@ extern "C" int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t 
   if (operand_in_tmem())
     return launch_linear<2, BN, 16, 8, 0, 2, 1, 8, true>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
   return launch_linear<2, BN, 16, 8, 0, 2, 1, 8>(hidden, ldh, B, H, w, la, se, re, (cudaStream_t)stream);
+}
+
+// Weight-gradient form of the split-K product: At is the A operand TRANSPOSED, [K, M] row-major (grad_y [B, N] as the
+// backward pass holds it), so no transposed copy of it is ever written.  The tile goes to tensor memory through the
+// converter warps (thread m of a row tile reads column m of every k-row), the result leaves through the staged store:
+// partials[i] (rows [i * slice_rows, i * slice_rows + M) of a [k_slices * slice_rows, ldo] matrix, slice_rows a multiple of
+// 256 >= M) holds the product over reduction range i.
+extern "C" int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M, int64_t K, const fc_linear_weights* w,
+                                        int32_t k_slices, float* partials, int64_t slice_rows, int64_t ldo,
+                                        int32_t n_out, void* stream) {
+  if (!At || !w || !w->w || !w->bias || M <= 0 || K <= 0 || M >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31))
+    return FC_ERR_INVALID_ARGUMENT;
+  if (!partials || n_out <= 0 || n_out > w->n_pad || k_slices < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (K > w->k_pad || ldat < M) return FC_ERR_INVALID_ARGUMENT;
+  if ((ldat & 3) || (reinterpret_cast<uintptr_t>(At) & 15) || (n_out & 3) || (ldo & 3) ||
+      (reinterpret_cast<uintptr_t>(partials) & 15))
+    return FC_ERR_UNSUPPORTED;
+  if (slice_rows < M || (slice_rows % 256) || (int64_t)k_slices * slice_rows >= ((int64_t)1 << 31)) return FC_ERR_INVALID_ARGUMENT;
+  if (w->n_pad % 128 != 0) return FC_ERR_INVALID_ARGUMENT;
+  LinArgs la{};
+  la.k_slices = k_slices;
+  la.a_tiled = 2;
+  StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, slice_rows};
+  RqsEpi re{};
+  la.num_n_tiles = (n_out + 127) / 128;
+  return launch_linear<3, 128, 32, 4, 0, 32, 2, 8, true>(At, ldat, M, (int)K, w, la, se, re, (cudaStream_t)stream);
 }
 
 extern "C" int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w,

@@ -228,6 +228,31 @@ def linear_splitk(a, packed, k_slices=None):
     return out if n4 == packed.n_out else out[:, :packed.n_out]
 
 
+def linear_splitk_t(a_t, packed, k_slices=None):
+    """a_t.T @ W.T for a_t given TRANSPOSED ([K, M] row-major, e.g. grad_y [B, N]) — fc_linear_splitk_t_apply: the
+    weight-gradient product without a transposed copy of grad_y.  Returns [M, n_out]; `packed` must carry a zero bias."""
+    _cabi.require_cuda_f32(a_t, "activations")
+    L = _cabi.lib()
+    a_t, ap, ld = _cabi.rows(a_t)
+    K, M = a_t.shape
+    if K != packed.k_in:
+        raise ValueError("activations have {} rows, the packed layer expects {}".format(K, packed.k_in))
+    n4 = (packed.n_out + 3) // 4 * 4
+    if k_slices is None:
+        # two waves of (row-tile pair, range) units over the SM pairs, at least 1024 reduction steps each
+        pairs = (M + 255) // 256
+        clusters = torch.cuda.get_device_properties(a_t.device).multi_processor_count // 2
+        k_slices = max(1, min(K // 1024, (2 * clusters) // pairs))
+    slice_rows = _ceil_to(M, 256)
+    partials = torch.empty((k_slices, slice_rows, n4), dtype=torch.float32, device=a_t.device)
+    with torch.cuda.device(a_t.device), _cabi.launch("fc_linear_splitk_t_apply", a_t.device):
+        rc = L.fc_linear_splitk_t_apply(ap, ld, M, K, ctypes.byref(packed.struct), k_slices, partials.data_ptr(),
+                                        slice_rows, n4, n4, _cabi.stream_ptr(a_t.device))
+    _cabi.check(rc, "fc_linear_splitk_t_apply")
+    out = partials[0] if k_slices == 1 else partials.sum(0)
+    return out[:M] if n4 == packed.n_out else out[:M, :packed.n_out]
+
+
 def transpose(t):
     """[rows, cols] -> [cols, rows] (fc_linear_transpose; coalesced on both sides)."""
     _cabi.require_cuda_f32(t, "matrix")

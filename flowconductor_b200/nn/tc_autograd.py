@@ -23,6 +23,7 @@ ENABLED = True
 # way), then one split-K product.  Measured over 262144 rows: 256 x 256: 0.60 ms (0.135 + 0.19 + 0.28) vs 0.77 ms for the
 # cuBLAS fp32 torch.mm; 752 x 256: 1.40 vs 2.03 ms.
 WGRAD_TC = True
+WGRAD_T = True  # grad_y enters the weight-gradient product untransposed (fc_linear_splitk_t_apply)
 # Shortest reduction the tensor-core GEMM is used for.  Every 3xTF32 product carries ~2^-22 relative error (dropped
 # lo*lo term, truncation inside the MMA); an fp32 FMA chain rounds at 2^-24 per step, so its error grows with the
 # chain length.  Measured (scripts/check_linear.py, Gaussian operands): at K = 32 the tensor-core result is 1.3x
@@ -67,7 +68,9 @@ class _TCLinear(torch.autograd.Function):
             if WGRAD_TC and weight.shape[1] >= MIN_K and x.shape[0] >= 4096 and x.shape[0] % 4 == 0:
                 # grad_W[N, K] = grad_y^T[N, B] @ x[B, K]: a reduction over the batch -> split-K on the tensor cores
                 # (both operands transposed once so that the batch is the contiguous reduction axis)
-                gw = fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x))
+                # (grad_y is read as it lies: the kernel transposes it on its way into tensor memory)
+                gw = fl.linear_splitk_t(gy, fl.pack_transposed(x)) if WGRAD_T else \
+                    fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x))
                 if gw.stride(0) != weight.shape[1]:
                     gw = gw.contiguous()
             else:

@@ -186,6 +186,17 @@ int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, int32_t K, co
                            int32_t k_slices, float* partials, int64_t slice_stride, int64_t ldo, int32_t n_out,
                            void* stream);
 
+/*
+ * The same product with the A operand given TRANSPOSED: At is [K, M] row-major with row stride ldat — for a weight
+ * gradient simply grad_y [B, N] as the backward pass holds it, so no transposed copy of grad_y is written
+ * (fc_linear_transpose is not needed).  Range s writes rows [s * slice_rows, s * slice_rows + M) of the row-major
+ * matrix `partials` ([k_slices * slice_rows, ldo]); slice_rows >= M must be a multiple of 256 (rows M.. of a range
+ * are scratch).  `w` as above (fc_linear_pack_transposed of x), zero bias.
+ */
+int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M, int64_t K, const fc_linear_weights* w,
+                             int32_t k_slices, float* partials, int64_t slice_rows, int64_t ldo, int32_t n_out,
+                             void* stream);
+
 /* Operand producers for fc_linear_splitk_apply (the batch has to be the contiguous reduction axis of both operands):
  * dst[c, r] = src[r, c], and the packed hi / lo planes of X^T (zero bias): packed row c = column c of X. */
 int fc_linear_transpose(const float* src, int64_t src_row_stride, int64_t rows, int32_t cols, float* dst,

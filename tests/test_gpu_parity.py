@@ -461,10 +461,12 @@ def test_linear_splitk_weight_gradient_shape(dev, N, K, B, slices):
     got = fl.linear_splitk(gy.t().contiguous(), fl.pack(x.t().contiguous(), None), k_slices=slices)
     got2 = fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x), k_slices=slices)  # the fused operand producers
     assert torch.equal(got, got2)
+    got3 = fl.linear_splitk_t(gy, fl.pack_transposed(x), k_slices=slices)  # grad_y untransposed (operand via TMEM)
     want = gy.double().t() @ x.double()
     ref32 = gy.t() @ x
-    assert got.shape == (N, K)
+    assert got.shape == (N, K) and got3.shape == (N, K)
     assert _gemm_err(got, want) <= 2.0 * _gemm_err(ref32, want) + 2e-7
+    assert _gemm_err(got3, want) <= 2.0 * _gemm_err(ref32, want) + 2e-7
 
 
 def test_linear_pack_folds_mask_and_column_scatter(dev):
