@@ -82,7 +82,7 @@ def lib():
         L.fc_linear_affine_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, vp, i64,
                                              vp, i32, i32, Cols, Cols, i32, i32, i32, vp]
         L.fc_linear_splitk_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp]
-        L.fc_linear_splitk_t_apply.argtypes = [vp, i64, i64, i64, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp]
+        L.fc_linear_splitk_t_apply.argtypes = [vp, i64, i64, i64, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp, vp]
         L.fc_linear_transpose.argtypes = [vp, i64, i64, i32, vp, i64, vp]
         L.fc_linear_pack_transposed.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp, vp]
         L.fc_version.restype = ctypes.c_char_p

@@ -71,6 +71,8 @@ struct LinArgs {
   int k_slices;      // split-K: the reduction is cut into k_slices ranges of num_k_stages slots, one work unit each
   int debug;         // FC_LINEAR_DEBUG: 4 = record the cycle counters (only in builds with -DFC_LINEAR_PROFILE=1)
   const float* bias;  // [n_pad]
+  float* colsum;      // a_tiled == 2 only, may be null: column sums of A^T per reduction range, [k_slices][slice rows]
+                      // (the bias gradient grad_y.sum(0) comes for free while grad_y passes through the converters)
 };
 
 struct StoreEpi {
@@ -495,6 +497,7 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
     const bool cprof = FC_LINEAR_PROFILE && (la.debug & 4) && blockIdx.x == 0 && warp == kConvWarp0;
     long long c_wait = 0, c_work = 0, c_t = cprof ? clock64() : 0;
     for (int mp = unit0; mp < n_units; mp += unit_step) {
+      float csum = 0.f;  // column sum of this thread's operand row over the unit's reduction range (a_tiled == 2)
       for (int it = 0; it < n_tiles * nk; ++it) {
         mbar_wait(full_bar(s), ph);
         if (cprof) {
@@ -517,6 +520,12 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
               // (a warp reads 32 consecutive words: conflict-free)
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = lds32(st + (uint32_t)((h * 16 + i) * (kBM * 4) + r * 4));
+              if (la.colsum != nullptr && it < nk) {  // first column tile only: later tiles re-read the same operand
+                // pairwise inside the 16 values: the sequential chain is 16x shorter than the range
+                const float s0 = (f[0] + f[1]) + (f[2] + f[3]), s1 = (f[4] + f[5]) + (f[6] + f[7]);
+                const float s2 = (f[8] + f[9]) + (f[10] + f[11]), s3 = (f[12] + f[13]) + (f[14] + f[15]);
+                csum += (s0 + s1) + (s2 + s3);
+              }
             } else
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -587,6 +596,10 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
           c_work += t - c_t;
           c_t = t;
         }
+      }
+      if (TS && la.a_tiled == 2 && la.colsum != nullptr) {
+        const int mt = (mp / ks_n) * CL + rank;
+        la.colsum[(int64_t)(mp % ks_n) * se.slice_stride + mt * kBM + (warp & 3) * 32 + lane] = csum;
       }
     }
     if (cprof && lane == 0) {
@@ -1391,10 +1404,11 @@ extern "C" int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t 
 // backward pass holds it), so no transposed copy of it is ever written.  The tile goes to tensor memory through the
 // converter warps (thread m of a row tile reads column m of every k-row), the result leaves through the staged store:
 // partials[i] (rows [i * slice_rows, i * slice_rows + M) of a [k_slices * slice_rows, ldo] matrix, slice_rows a multiple of
-// 256 >= M) holds the product over reduction range i.
+// 256 >= M) holds the product over reduction range i.  colsum (optional, [k_slices][slice_rows]) receives the column
+// sums of At over each range: summed over the ranges they are the bias gradient grad_y.sum(0).
 extern "C" int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M, int64_t K, const fc_linear_weights* w,
                                         int32_t k_slices, float* partials, int64_t slice_rows, int64_t ldo,
-                                        int32_t n_out, void* stream) {
+                                        int32_t n_out, float* colsum, void* stream) {
   if (!At || !w || !w->w || !w->bias || M <= 0 || K <= 0 || M >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31))
     return FC_ERR_INVALID_ARGUMENT;
   if (!partials || n_out <= 0 || n_out > w->n_pad || k_slices < 1) return FC_ERR_INVALID_ARGUMENT;
@@ -1407,6 +1421,7 @@ extern "C" int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M
   LinArgs la{};
   la.k_slices = k_slices;
   la.a_tiled = 2;
+  la.colsum = colsum;
   StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, slice_rows};
   RqsEpi re{};
   la.num_n_tiles = (n_out + 127) / 128;

@@ -228,9 +228,10 @@ def linear_splitk(a, packed, k_slices=None):
     return out if n4 == packed.n_out else out[:, :packed.n_out]
 
 
-def linear_splitk_t(a_t, packed, k_slices=None):
+def linear_splitk_t(a_t, packed, k_slices=None, column_sums=False):
     """a_t.T @ W.T for a_t given TRANSPOSED ([K, M] row-major, e.g. grad_y [B, N]) — fc_linear_splitk_t_apply: the
-    weight-gradient product without a transposed copy of grad_y.  Returns [M, n_out]; `packed` must carry a zero bias."""
+    weight-gradient product without a transposed copy of grad_y.  Returns [M, n_out]; `packed` must carry a zero bias.
+    column_sums=True also returns a_t.sum(0) (the bias gradient), accumulated while a_t passes through the kernel."""
     _cabi.require_cuda_f32(a_t, "activations")
     L = _cabi.lib()
     a_t, ap, ld = _cabi.rows(a_t)
@@ -245,12 +246,17 @@ def linear_splitk_t(a_t, packed, k_slices=None):
         k_slices = max(1, min(K // 1024, (2 * clusters) // pairs))
     slice_rows = _ceil_to(M, 256)
     partials = torch.empty((k_slices, slice_rows, n4), dtype=torch.float32, device=a_t.device)
+    csum = torch.empty((k_slices, slice_rows), dtype=torch.float32, device=a_t.device) if column_sums else None
     with torch.cuda.device(a_t.device), _cabi.launch("fc_linear_splitk_t_apply", a_t.device):
         rc = L.fc_linear_splitk_t_apply(ap, ld, M, K, ctypes.byref(packed.struct), k_slices, partials.data_ptr(),
-                                        slice_rows, n4, n4, _cabi.stream_ptr(a_t.device))
+                                        slice_rows, n4, n4, csum.data_ptr() if column_sums else None,
+                                        _cabi.stream_ptr(a_t.device))
     _cabi.check(rc, "fc_linear_splitk_t_apply")
     out = partials[0] if k_slices == 1 else partials.sum(0)
-    return out[:M] if n4 == packed.n_out else out[:M, :packed.n_out]
+    out = out[:M] if n4 == packed.n_out else out[:M, :packed.n_out]
+    if column_sums:
+        return out, (csum[0] if k_slices == 1 else csum.sum(0))[:M]
+    return out
 
 
 def transpose(t):

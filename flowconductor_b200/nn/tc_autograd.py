@@ -69,15 +69,19 @@ class _TCLinear(torch.autograd.Function):
                 # grad_W[N, K] = grad_y^T[N, B] @ x[B, K]: a reduction over the batch -> split-K on the tensor cores
                 # (both operands transposed once so that the batch is the contiguous reduction axis)
                 # (grad_y is read as it lies: the kernel transposes it on its way into tensor memory)
-                gw = fl.linear_splitk_t(gy, fl.pack_transposed(x)) if WGRAD_T else \
-                    fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x))
+                if WGRAD_T and ctx.has_bias and ctx.needs_input_grad[2]:
+                    gw, gb = fl.linear_splitk_t(gy, fl.pack_transposed(x), column_sums=True)  # bias gradient for free
+                elif WGRAD_T:
+                    gw = fl.linear_splitk_t(gy, fl.pack_transposed(x))
+                else:
+                    gw = fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x))
                 if gw.stride(0) != weight.shape[1]:
                     gw = gw.contiguous()
             else:
                 gw = gy.t().mm(x)
             if mask is not None:
                 gw = gw * mask
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if gb is None and ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy.sum(0)
         return gx, gw, gb, None
 

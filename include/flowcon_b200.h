@@ -191,11 +191,13 @@ int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, int32_t K, co
  * gradient simply grad_y [B, N] as the backward pass holds it, so no transposed copy of grad_y is written
  * (fc_linear_transpose is not needed).  Range s writes rows [s * slice_rows, s * slice_rows + M) of the row-major
  * matrix `partials` ([k_slices * slice_rows, ldo]); slice_rows >= M must be a multiple of 256 (rows M.. of a range
- * are scratch).  `w` as above (fc_linear_pack_transposed of x), zero bias.
+ * are scratch).  `w` as above (fc_linear_pack_transposed of x), zero bias.  colsum: NULL, or [k_slices][slice_rows]
+ * floats that receive, per range, the column sums of At (entry s * slice_rows + m = sum over the range's rows k of
+ * At[k][m]); their sum over s is grad_y.sum(0), the bias gradient, for free.
  */
 int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M, int64_t K, const fc_linear_weights* w,
                              int32_t k_slices, float* partials, int64_t slice_rows, int64_t ldo, int32_t n_out,
-                             void* stream);
+                             float* colsum, void* stream);
 
 /* Operand producers for fc_linear_splitk_apply (the batch has to be the contiguous reduction axis of both operands):
  * dst[c, r] = src[r, c], and the packed hi / lo planes of X^T (zero bias): packed row c = column c of X. */

@@ -461,7 +461,13 @@ def test_linear_splitk_weight_gradient_shape(dev, N, K, B, slices):
     got = fl.linear_splitk(gy.t().contiguous(), fl.pack(x.t().contiguous(), None), k_slices=slices)
     got2 = fl.linear_splitk(fl.transpose(gy), fl.pack_transposed(x), k_slices=slices)  # the fused operand producers
     assert torch.equal(got, got2)
-    got3 = fl.linear_splitk_t(gy, fl.pack_transposed(x), k_slices=slices)  # grad_y untransposed (operand via TMEM)
+    # grad_y untransposed (operand via TMEM), bias gradient accumulated on the way
+    got3, colsum = fl.linear_splitk_t(gy, fl.pack_transposed(x), k_slices=slices, column_sums=True)
+    assert torch.equal(got3, fl.linear_splitk_t(gy, fl.pack_transposed(x), k_slices=slices))
+    want_cs = gy.double().sum(0)
+    assert colsum.shape == (N,)
+    assert (colsum.double() - want_cs).abs().max() <= 4.0 * (gy.sum(0).double() - want_cs).abs().max() + \
+        2e-6 * want_cs.abs().max()
     want = gy.double().t() @ x.double()
     ref32 = gy.t() @ x
     assert got.shape == (N, K) and got3.shape == (N, K)
