@@ -19,7 +19,7 @@ STATUS_NEGATIVE_DISCRIMINANT = 2
 TAILS_NONE, TAILS_LINEAR = 0, 1
 AFFINE_BLOCKED, AFFINE_INTERLEAVED = 0, 1
 SCALE_SIGMOID2, SCALE_SOFTPLUS_CLAMP3, SCALE_SOFTPLUS_EPS = 0, 1, 2
-LINEAR_A_T128, LINEAR_OUT_T128 = 1, 2
+LINEAR_A_T128, LINEAR_OUT_T128, LINEAR_RESIDUAL_GATES = 1, 2, 4
 
 EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
@@ -84,7 +84,7 @@ def lib():
         L.fc_linear_splitk_apply.argtypes = [vp, i64, i64, i32, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp]
         L.fc_linear_splitk_t_apply.argtypes = [vp, i64, i64, i64, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp, vp]
         L.fc_linear_transpose.argtypes = [vp, i64, i64, i32, vp, i64, vp]
-        L.fc_linear_pack_transposed.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp, vp]
+        L.fc_linear_pack_transposed.argtypes = [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp]
         L.fc_version.restype = ctypes.c_char_p
         for name in EXPORTS:
             if name not in ("fc_version",):

@@ -83,6 +83,8 @@ struct StoreEpi {
   int n_out;
   int relu_out;
   int tiled;  // out (and residual) are stored in the T128 layout; ldo / ldr are then their logical widths
+  int res_mask;  // staged kernel: `residual` is not added, it gates: out = residual > 0 ? out : 0 (the ReLU backward
+                 // of an input-gradient product, masked by the saved pre-activation)
   int64_t slice_stride;  // split-K: floats between the partial results of consecutive reduction ranges
 };
 
@@ -771,10 +773,17 @@ __global__ void __launch_bounds__(kBaseThreads + 32 * (EW + SW), 1)
                                       : params_s + (uint32_t)((cg >> 3) * kBM * 128 + rt * 128 + (((cg & 7) ^ (rt & 7)) << 4));
             if (res) {
               const float4 r = lds128(a);
-              o.x += r.x;
-              o.y += r.y;
-              o.z += r.z;
-              o.w += r.w;
+              if (se.res_mask) {
+                o.x = r.x > 0.f ? o.x : 0.f;
+                o.y = r.y > 0.f ? o.y : 0.f;
+                o.z = r.z > 0.f ? o.z : 0.f;
+                o.w = r.w > 0.f ? o.w : 0.f;
+              } else {
+                o.x += r.x;
+                o.y += r.y;
+                o.z += r.z;
+                o.w += r.w;
+              }
             }
             if (se.relu_out) {
               o.x = fmaxf(o.x, 0.f);
@@ -1205,7 +1214,8 @@ __global__ void pack_kernel(const float* __restrict__ W, int64_t ldw, const floa
 //   kSplit = true : dst[0][c][r] = tf32_hi(src[r][c]), dst[1][c][r] = tf32(src[r][c] - hi)   (x [B, K] -> packed planes)
 template <bool kSplit>
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
-                                                        float* __restrict__ dst, int64_t ldd, int64_t plane_stride) {
+                                                        float* __restrict__ dst, int64_t ldd, int64_t plane_stride,
+                                                        int relu) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
   const int64_t r0 = (int64_t)blockIdx.x * 32;
@@ -1222,7 +1232,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     const int c = c0 + ty + 8 * i;
     const int64_t r = r0 + tx;
     if (c < cols && r < rows) {
-      const float v = tile[tx][ty + 8 * i];
+      const float v = relu ? fmaxf(tile[tx][ty + 8 * i], 0.f) : tile[tx][ty + 8 * i];
       if (kSplit) {
         const uint32_t hi = tc::to_tf32(v);
         dst[(int64_t)c * ldd + r] = __uint_as_float(hi);
@@ -1244,13 +1254,14 @@ extern "C" int fc_linear_transpose(const float* src, int64_t src_row_stride, int
   if (rows == 0) return FC_OK;
   if (!src || !dst) return FC_ERR_INVALID_ARGUMENT;
   const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
-  transpose_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_row_stride, rows, cols, dst, dst_row_stride, 0);
+  transpose_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_row_stride, rows, cols, dst, dst_row_stride, 0, 0);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
 
 extern "C" int fc_linear_pack_transposed(const float* X, int64_t x_row_stride, int64_t B, int32_t K, int32_t n_pad,
-                                         int32_t k_pad, float* w_packed, float* bias_packed, void* stream) {
+                                         int32_t k_pad, int32_t relu, float* w_packed, float* bias_packed,
+                                         void* stream) {
   if (B <= 0 || K <= 0 || !X || !w_packed || !bias_packed || n_pad < K || k_pad < B || (k_pad % 32) || (n_pad % 16))
     return FC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1260,7 +1271,7 @@ extern "C" int fc_linear_pack_transposed(const float* X, int64_t x_row_stride, i
     return FC_ERR_CUDA;
   if (cudaMemsetAsync(bias_packed, 0, sizeof(float) * (size_t)n_pad, st) != cudaSuccess) return FC_ERR_CUDA;
   const dim3 grid((unsigned)((B + 31) / 32), (unsigned)((K + 31) / 32));
-  transpose_kernel<true><<<grid, 256, 0, st>>>(X, x_row_stride, B, K, w_packed, k_pad, (int64_t)n_pad * k_pad);
+  transpose_kernel<true><<<grid, 256, 0, st>>>(X, x_row_stride, B, K, w_packed, k_pad, (int64_t)n_pad * k_pad, relu);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -1291,6 +1302,8 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
                                int32_t relu_in, float* out, int64_t ldo, int32_t n_out, int32_t relu_out,
                                const float* residual, int64_t ldr, int32_t layouts, void* stream) {
   const int a_tiled = (layouts & FC_LINEAR_A_T128) != 0, o_tiled = (layouts & FC_LINEAR_OUT_T128) != 0;
+  const int res_mask = (layouts & FC_LINEAR_RESIDUAL_GATES) != 0;
+  if (res_mask && !residual) return FC_ERR_INVALID_ARGUMENT;
   int rc = check_operand(A, lda, M, K, w, a_tiled);
   if (rc != FC_OK) return rc;
   if (M == 0) return FC_OK;  // empty batch (null data pointers are fine)
@@ -1302,12 +1315,14 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
   LinArgs la{};
   la.relu_in = relu_in;
   la.a_tiled = a_tiled;
-  StoreEpi se{out, ldo, residual, ldr, n_out, relu_out, o_tiled, 0};
+  StoreEpi se{out, ldo, residual, ldr, n_out, relu_out, o_tiled, res_mask, 0};
   RqsEpi re{};
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;
   la.num_n_tiles = (n_out + BN - 1) / BN;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool experimental = cluster_mode() == 2 || cluster_mode() == 3 || epilogue_warps() == 16;
+  if (res_mask && experimental) return FC_ERR_UNSUPPORTED;
   if (cluster_mode() == 2) return launch_linear<0, BN, 16, 6, 0, 32, 2, 8>(A, lda, M, K, w, la, se, re, st);
   if (cluster_mode() == 3) return launch_linear<0, BN, 16, 4, 0, 32, 3, 8>(A, lda, M, K, w, la, se, re, st);
   if (epilogue_warps() == 16) return launch_linear<0, BN, 16, 4, 0, 32, 1, 16>(A, lda, M, K, w, la, se, re, st);
@@ -1326,6 +1341,7 @@ extern "C" int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K
     if (wide_slots() && K > 64) return launch_linear<3, 128, 32, 4, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
     return launch_linear<3, 128, 16, 8, 0, 32, 2, 8, true>(A, lda, M, K, w, la, se, re, st);
   }
+  if (res_mask) return FC_ERR_UNSUPPORTED;  // only the staged kernel gates
   return launch_linear<0, BN, 16, 4, 0, 32, 1, 8>(A, lda, M, K, w, la, se, re, st);
 }
 
@@ -1422,7 +1438,7 @@ extern "C" int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M
   la.k_slices = k_slices;
   la.a_tiled = 2;
   la.colsum = colsum;
-  StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, slice_rows};
+  StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, 0, slice_rows};
   RqsEpi re{};
   la.num_n_tiles = (n_out + 127) / 128;
   return launch_linear<3, 128, 32, 4, 0, 32, 2, 8, true>(At, ldat, M, (int)K, w, la, se, re, (cudaStream_t)stream);
@@ -1440,7 +1456,7 @@ extern "C" int fc_linear_splitk_apply(const float* A, int64_t lda, int64_t M, in
   if (slice_stride < M * ldo) return FC_ERR_INVALID_ARGUMENT;
   LinArgs la{};
   la.k_slices = k_slices;
-  StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, slice_stride};
+  StoreEpi se{partials, ldo, nullptr, 0, n_out, 0, 0, 0, slice_stride};
   RqsEpi re{};
   constexpr int BN = 256;
   if (w->n_pad % BN != 0) return FC_ERR_INVALID_ARGUMENT;

@@ -112,11 +112,14 @@ class T128:
                 .reshape(tiles * self.TILE, self.width)[:self.rows].contiguous())
 
 
-def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None, out_t128=False, n_out=None):
+def linear(a, packed, relu_in=False, relu_out=False, residual=None, out=None, out_t128=False, n_out=None,
+           residual_gates=False):
     """out = act_out(act_in(a) @ W.T + b (+ residual)).  a: [M, K] fp32 row-major (row stride a multiple of 4
-    floats) or a T128; the result (and the residual) is a T128 when out_t128 is set, else row-major."""
+    floats) or a T128; the result (and the residual) is a T128 when out_t128 is set, else row-major.
+    residual_gates=True: the residual is not added, it gates the result, out = where(residual > 0, a @ W.T + b, 0) — the
+    ReLU backward of an input-gradient product."""
     L = _cabi.lib()
-    layouts = 0
+    layouts = _cabi.LINEAR_RESIDUAL_GATES if residual_gates else 0
     if isinstance(a, T128):
         layouts |= _cabi.LINEAR_A_T128
         M, k_in, ap, lda, dev = a.rows, a.width, a.buf.data_ptr(), a.width, a.buf.device
@@ -272,8 +275,9 @@ def transpose(t):
     return out
 
 
-def pack_transposed(x, n_tile=N_TILE_STORE):
-    """Packed hi / lo planes of x^T (zero bias) for linear_splitk: x [B, K] -> PackedLinear with n_out = K, k_in = B."""
+def pack_transposed(x, n_tile=N_TILE_STORE, relu=False):
+    """Packed hi / lo planes of x^T (zero bias) for linear_splitk: x [B, K] -> PackedLinear with n_out = K, k_in = B.
+    relu=True packs max(x, 0)."""
     _cabi.require_cuda_f32(x, "activations")
     L = _cabi.lib()
     x, xp, ld = _cabi.rows(x)
@@ -282,7 +286,7 @@ def pack_transposed(x, n_tile=N_TILE_STORE):
     w = torch.empty((2, n_pad, k_pad), dtype=torch.float32, device=x.device)
     b = torch.empty((n_pad,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device), _cabi.launch("fc_linear_pack_transposed", x.device):
-        rc = L.fc_linear_pack_transposed(xp, ld, B, K, n_pad, k_pad, w.data_ptr(), b.data_ptr(),
+        rc = L.fc_linear_pack_transposed(xp, ld, B, K, n_pad, k_pad, int(relu), w.data_ptr(), b.data_ptr(),
                                          _cabi.stream_ptr(x.device))
     _cabi.check(rc, "fc_linear_pack_transposed")
     return PackedLinear(w, b, K, B)

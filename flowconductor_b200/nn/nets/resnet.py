@@ -30,6 +30,10 @@ class ResidualBlock(nn.Module):
                 nn.init.uniform_(tensor, -1e-3, 1e-3)
 
     def forward(self, inputs, context=None):
+        if (context is None and not self.use_batch_norm and tc_autograd.is_relu(self.activation)
+                and not (self.training and self.dropout.p > 0)
+                and tc_autograd.residual_block_eligible(inputs, self.linear_layers[0], self.linear_layers[1])):
+            return tc_autograd.residual_block(inputs, self.linear_layers[0], self.linear_layers[1])
         h = inputs
         for i in range(2):
             if self.use_batch_norm:

@@ -92,6 +92,10 @@ class MaskedResidualBlock(nn.Module):
                 nn.init.uniform_(tensor, a=-1e-3, b=1e-3)
 
     def forward(self, inputs, context=None):
+        if (context is None and not self.use_batch_norm and tc_autograd.is_relu(self.activation)
+                and not (self.training and self.dropout.p > 0)
+                and tc_autograd.residual_block_eligible(inputs, self.linear_layers[0], self.linear_layers[1])):
+            return tc_autograd.residual_block(inputs, self.linear_layers[0], self.linear_layers[1])
         h = self.batch_norm_layers[0](inputs) if self.use_batch_norm else inputs
         h = self.linear_layers[0](self.activation(h))
         if context is not None:

@@ -170,6 +170,9 @@ int fc_linear_pack(const float* W, int64_t w_row_stride, const float* mask, int6
  */
 #define FC_LINEAR_A_T128 1
 #define FC_LINEAR_OUT_T128 2
+/* `residual` gates instead of being added: out = residual > 0 ? (A W^T + bias) : 0 — the ReLU backward of an
+ * input-gradient product, `residual` being the saved pre-activation (autograd of resnet.py:26-28: F.relu then Linear) */
+#define FC_LINEAR_RESIDUAL_GATES 4
 int fc_linear_apply(const float* A, int64_t lda, int64_t M, int32_t K, const fc_linear_weights* w, int32_t relu_in,
                     float* out, int64_t ldo, int32_t n_out, int32_t relu_out, const float* residual, int64_t ldr,
                     int32_t layouts, void* stream);
@@ -204,6 +207,7 @@ int fc_linear_splitk_t_apply(const float* At, int64_t ldat, int64_t M, int64_t K
 int fc_linear_transpose(const float* src, int64_t src_row_stride, int64_t rows, int32_t cols, float* dst,
                         int64_t dst_row_stride, void* stream);
 int fc_linear_pack_transposed(const float* X, int64_t x_row_stride, int64_t B, int32_t K, int32_t n_pad, int32_t k_pad,
+                              int32_t relu /* pack max(X, 0): the layer's input went through F.relu */,
                               float* w_packed, float* bias_packed, void* stream);
 
 /*

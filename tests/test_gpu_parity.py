@@ -717,3 +717,38 @@ def test_cuda_graph_sampler_draws_fresh_noise(dev):
         lp_g = flow.log_prob(a).mean().item()
         lp_e = flow.log_prob(flow.sample(256)).mean().item()
     assert abs(lp_g - lp_e) < 3.0
+
+
+@pytest.mark.parametrize("rows,width,masked", [(1000, 64, False), (4100, 256, False), (8192, 128, True)])
+def test_fused_residual_block_gradients(dev, rows, width, masked, monkeypatch):
+    """tc_autograd.residual_block (ReLU fused into the GEMM operands, ReLU backward gating the input-gradient epilogue,
+    bias gradients from the weight-gradient kernel) against the same block in fp64 torch; the yardstick is the error of
+    the unfused fp32 torch block."""
+    from flowconductor_b200.nn import nets, tc_autograd
+    from flowconductor_b200.transforms import made as made_module
+
+    torch.manual_seed(rows + width)
+    if masked:
+        deg = torch.arange(width) % 7 + 1
+        block = made_module.MaskedResidualBlock(deg, autoregressive_features=8, zero_initialization=False)
+    else:
+        block = nets.resnet.ResidualBlock(width, None, zero_initialization=False)
+    block = block.to(dev)
+    x = torch.randn(rows, width, device=dev)
+    gy = torch.randn(rows, width, device=dev)
+
+    def run(module, inp, g):
+        inp = inp.clone().requires_grad_(True)
+        out = module(inp)
+        grads = torch.autograd.grad((out * g).sum(), [inp] + list(module.parameters()))
+        return [out.detach()] + [t.detach() for t in grads]
+
+    launches_before = dict(_cabi.STATS.counts)
+    fused = run(block, x, gy)
+    assert _cabi.STATS.counts.get("fc_linear_apply", 0) - launches_before.get("fc_linear_apply", 0) == 4
+    monkeypatch.setattr(tc_autograd, "ENABLED", False)  # plain torch fp32
+    ref32 = run(block, x, gy)
+    ref64 = run(block.double(), x.double(), gy.double())
+    for got, r32, r64 in zip(fused, ref32, ref64):
+        scale = r64.abs().max().item()
+        assert (got.double() - r64).abs().max().item() <= 3.0 * (r32.double() - r64).abs().max().item() + 2e-6 * scale
