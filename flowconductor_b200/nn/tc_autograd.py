@@ -74,7 +74,9 @@ class _TCLinear(torch.autograd.Function):
 def _wgrad(gy, x, weight, mask, want_bias, relu_x=False):
     """(grad_W, grad_b or None) of y = relu?(x) @ (W*mask)^T + b for upstream gy."""
     gb = None
-    if WGRAD_TC and WGRAD_T and weight.shape[1] >= MIN_K and x.shape[0] >= 4096 and x.shape[0] % 4 == 0:
+    # (the reduction runs over the batch, so a narrow layer input does not shorten it: no MIN_K condition here)
+    if (WGRAD_TC and WGRAD_T and x.shape[0] >= 4096 and x.shape[0] % 4 == 0 and gy.shape[1] % 4 == 0
+            and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0):
         xt = fl.pack_transposed(x, relu=relu_x)
         if want_bias:
             gw, gb = fl.linear_splitk_t(gy, xt, column_sums=True)
@@ -146,8 +148,39 @@ def residual_block(x, lin0, lin1):
                                   getattr(lin1, "mask", None))
 
 
+class _TCWgradLinear(torch.autograd.Function):
+    """A layer whose forward reduction is too short for the 3xTF32 product (K < MIN_K, e.g. the first layer of a MADE
+    over 16 features): forward and input gradient stay cuBLAS fp32, the weight gradient — a reduction over the whole
+    batch — still runs on the tensor cores (and returns the bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask):
+        ctx.save_for_backward(x, weight, mask)
+        ctx.has_bias = bias is not None
+        return F.linear(x, weight if mask is None else weight * mask, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, mask = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gy.mm(weight if mask is None else weight * mask)
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            gw, gb = _wgrad(gy, x, weight, mask, want_bias)
+        if gb is None and want_bias:
+            gb = gy.sum(0)
+        return gx, gw, gb, None
+
+
 def linear(x, weight, bias=None, mask=None):
     if not _eligible(x, weight) or gy_misaligned(weight):
+        if (ENABLED and WGRAD_TC and WGRAD_T and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+                and weight.dtype == torch.float32 and x.shape[0] >= 4096 and x.shape[0] % 4 == 0
+                and weight.shape[0] % 4 == 0 and weight.shape[0] >= MIN_K and weight.requires_grad
+                and torch.is_grad_enabled()):
+            return _TCWgradLinear.apply(x, weight, bias, mask)
         return F.linear(x, weight if mask is None else weight * mask, bias)
     return _TCLinear.apply(x, weight, bias, mask)
 

@@ -752,3 +752,26 @@ def test_fused_residual_block_gradients(dev, rows, width, masked, monkeypatch):
     for got, r32, r64 in zip(fused, ref32, ref64):
         scale = r64.abs().max().item()
         assert (got.double() - r64).abs().max().item() <= 3.0 * (r32.double() - r64).abs().max().item() + 2e-6 * scale
+
+
+def test_short_reduction_layer_keeps_tensor_core_weight_gradient(dev, monkeypatch):
+    """A 16 -> 256 layer (first layer of the cfg-3 MADE): forward / input gradient on cuBLAS fp32 (K < MIN_K), weight and
+    bias gradients from fc_linear_splitk_t_apply."""
+    from flowconductor_b200.nn import tc_autograd
+
+    g = torch.Generator(device=dev).manual_seed(9)
+    x = torch.randn(8192, 16, generator=g, device=dev)
+    w = (torch.randn(256, 16, generator=g, device=dev) / 4).requires_grad_(True)
+    b = torch.randn(256, generator=g, device=dev).requires_grad_(True)
+    mask = (torch.rand(256, 16, generator=g, device=dev) > 0.3).float()
+    gy = torch.randn(8192, 256, generator=g, device=dev)
+    before = _cabi.STATS.counts.get("fc_linear_splitk_t_apply", 0)
+    y = tc_autograd.linear(x, w, b, mask)
+    gw, gb = torch.autograd.grad((y * gy).sum(), [w, b])
+    assert _cabi.STATS.counts.get("fc_linear_splitk_t_apply", 0) == before + 1
+    want_w = (gy.double().t() @ x.double()) * mask.double()
+    want_b = gy.double().sum(0)
+    ref_w = (gy.t() @ x) * mask
+    assert torch.equal(y, torch.nn.functional.linear(x, w * mask, b))
+    assert _gemm_err(gw, want_w) <= 2.0 * _gemm_err(ref_w, want_w) + 2e-7
+    assert (gb.double() - want_b).abs().max() <= 2e-6 * want_b.abs().max()
