@@ -10,6 +10,7 @@ from .conditional import (ConditionalPiecewiseRationalQuadraticTransform,  # noq
 from .coupling import (AdditiveCouplingTransform, AffineCouplingTransform, CouplingTransform,  # noqa: F401
                        PiecewiseRationalQuadraticCouplingTransform)
 from .made import MADE, MaskedLinear  # noqa: F401
+from .nonlinearities import PiecewiseRationalQuadraticCDF  # noqa: F401
 from .permutations import Permutation, RandomPermutation, ReversePermutation  # noqa: F401
 from . import splines  # noqa: F401
 from .splines import rational_quadratic_spline, unconstrained_rational_quadratic_spline  # noqa: F401

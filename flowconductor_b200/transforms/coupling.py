@@ -15,6 +15,7 @@ from .. import _cabi, ops
 from ..nn import tensorcore
 from . import splines
 from .base import Transform
+from .nonlinearities import PiecewiseRationalQuadraticCDF
 
 
 class CouplingTransform(Transform):
@@ -24,9 +25,6 @@ class CouplingTransform(Transform):
             raise ValueError("Mask must be a 1-dim tensor.")
         if mask.numel() <= 0:
             raise ValueError("Mask can't be empty.")
-        if unconditional_transform is not None:
-            raise NotImplementedError("unconditional_transform on the identity features is outside the "
-                                      "B200 hot path (SURVEY.md §8f n3)")
         super().__init__()
         self.features = len(mask)
         index = torch.arange(self.features)
@@ -38,7 +36,9 @@ class CouplingTransform(Transform):
         assert self.num_identity_features + self.num_transform_features == self.features
         self.transform_net = transform_net_create_fn(
             self.num_identity_features, self.num_transform_features * self._transform_dim_multiplier())
-        self.unconditional_transform = None
+        # coupling.py:59-64: an optional bijection on the identity features (e.g. an unconditional spline CDF)
+        self.unconditional_transform = (None if unconditional_transform is None
+                                        else unconditional_transform(features=self.num_identity_features))
 
     @property
     def num_identity_features(self):
@@ -70,6 +70,27 @@ class CouplingTransform(Transform):
         return self._run_layer(inputs, context, inverse=True)
 
     def _run_layer(self, inputs, context, inverse):
+        ut = self.unconditional_transform
+        if ut is None:
+            return self._run_conditional(inputs, context, inverse)
+        # coupling.py:90-94 / :116-120: the conditioner always sees the identity features on the DATA side, so the
+        # unconditional transform runs after the layer in the forward direction and before it in the inverse
+        if not inverse:
+            outputs, logabsdet = self._run_conditional(inputs, context, False)
+            outputs, lad_id = self._on_identity(ut, outputs, context, False)
+            return outputs, logabsdet + lad_id
+        inputs, lad_id = self._on_identity(ut, inputs, context, True)
+        outputs, logabsdet = self._run_conditional(inputs, context, True)
+        return outputs, lad_id + logabsdet
+
+    def _on_identity(self, ut, full, context, inverse):
+        """Apply `ut` to the identity columns of a full-width tensor; returns (full-width result, logabsdet)."""
+        if hasattr(ut, "apply_on_columns"):  # our CDF layers: one kernel on the full-width tensor, no gather
+            return ut.apply_on_columns(full, self._ccols, self._tcols, inverse)
+        part, lad = (ut.inverse if inverse else ut)(full[:, self.identity_features], context)
+        return full.index_copy(1, self.identity_features, part), lad
+
+    def _run_conditional(self, inputs, context, inverse):
         if tensorcore.usable(self.transform_net, inputs, context):
             # inference: conditioner on the tensor cores; its first layer reads the full-width inputs through a
             # column-scattered weight, so the identity-column gather (coupling.py:82-86) disappears as well
@@ -142,9 +163,8 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
                  apply_unconditional_transform=False, img_shape=None,
                  min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH, min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT,
                  min_derivative=splines.DEFAULT_MIN_DERIVATIVE):
-        if apply_unconditional_transform:
-            raise NotImplementedError("apply_unconditional_transform is outside the B200 hot path "
-                                      "(SURVEY.md §8f n3)")
+        if apply_unconditional_transform and img_shape:
+            raise NotImplementedError("image-shaped inputs are outside the B200 hot path")
         self.num_bins = num_bins
         self.min_bin_width = min_bin_width
         self.min_bin_height = min_bin_height
@@ -154,7 +174,12 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
         self._spline = splines.RationalQuadraticSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height,
                                                          min_derivative, identity_init=False,
                                                          constrained_box=(0.0, 1.0))
-        super().__init__(mask, transform_net_create_fn, unconditional_transform=None)
+        unconditional = None
+        if apply_unconditional_transform:  # coupling.py:524-535
+            unconditional = lambda features: PiecewiseRationalQuadraticCDF(  # noqa: E731
+                shape=[features], num_bins=num_bins, tails=tails, tail_bound=tail_bound, min_bin_width=min_bin_width,
+                min_bin_height=min_bin_height, min_derivative=min_derivative)
+        super().__init__(mask, transform_net_create_fn, unconditional_transform=unconditional)
 
     def _transform_dim_multiplier(self):
         return self._spline.params_per_feature()

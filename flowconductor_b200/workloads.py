@@ -69,6 +69,14 @@ WORKLOADS = {
                                    "hidden_features": 16, "num_blocks": 2}]},
     "maf_sos_small": {"features": 5, "context_features": None, "batch": 64,
                       "layers": [{"kind": "maf_sos", "n_sigmoids": 6, "hidden_features": 16, "num_blocks": 2}]},
+    # coupling.py:524-535 + nonlinearities.py:406-487: an unconditional RQ CDF on the identity features of every layer
+    "prq_coupling_uncond_small": {"features": 6, "context_features": None, "batch": 64,
+                                  "layers": [{"kind": "prq_coupling", "mask": "alternating_even", "num_bins": 5,
+                                              "tails": "linear", "tail_bound": 3.0, "hidden_features": 16,
+                                              "num_blocks": 2, "unconditional": True},
+                                             {"kind": "prq_coupling", "mask": "alternating_odd", "num_bins": 5,
+                                              "tails": "linear", "tail_bound": 3.0, "hidden_features": 16,
+                                              "num_blocks": 2, "unconditional": True}]},
     "prq_coupling_notails_small": {"features": 6, "context_features": None, "batch": 64,
                                    "layers": [{"kind": "prq_coupling", "mask": "mid_split", "num_bins": 5,
                                                "tails": None, "tail_bound": 1.0, "hidden_features": 16,
@@ -173,7 +181,8 @@ def build_flow(workload, seed=0):
                 mask=make_mask(features, layer["mask"]),
                 transform_net_create_fn=lambda i, o, h=hidden, b=blocks: nets.ResidualNet(
                     i, o, hidden_features=h, num_blocks=b),
-                num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"]))
+                num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
+                apply_unconditional_transform=layer.get("unconditional", False)))
         elif kind == "affine_coupling":
             hidden, blocks = layer["hidden_features"], layer["num_blocks"]
             act = {"sigmoid2": transforms.AffineCouplingTransform.DEFAULT_SCALE_ACTIVATION,

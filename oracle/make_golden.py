@@ -185,7 +185,8 @@ def build_reference_flow(wl, seed=0):
             mask = workloads.make_mask(features, layer["mask"])
             if kind == "prq_coupling":
                 layers.append(transforms.PiecewiseRationalQuadraticCouplingTransform(
-                    mask, create, num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"]))
+                    mask, create, num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
+                    apply_unconditional_transform=layer.get("unconditional", False)))
             else:
                 act = {"sigmoid2": transforms.AffineCouplingTransform.DEFAULT_SCALE_ACTIVATION,
                        "softplus_clamp3": transforms.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION}[
@@ -264,6 +265,9 @@ def make_model(name, with_grad=False, x_scale=1.0, uniform01=False, batch=None):
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(4)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-uncond":  # add one fixture without rewriting the others
+        make_model("prq_coupling_uncond_small", with_grad=True)
+        sys.exit(0)
     make_functions()
     make_model("cfg1", with_grad=True, batch=2048)
     make_model("cfg2_small", with_grad=True)
@@ -273,3 +277,4 @@ if __name__ == "__main__":
     make_model("cond_prq_small", with_grad=True)
     make_model("maf_sos_small")
     make_model("prq_coupling_notails_small", uniform01=True)
+    make_model("prq_coupling_uncond_small", with_grad=True)

@@ -405,16 +405,42 @@ def made_net(state, prefix, inputs, context=None, num_blocks=2):
 # --------------------------------------------------------------------------------------------
 # a5-a10, a14, a16: layers, composition, base density — driven by a plain-data layer spec
 # --------------------------------------------------------------------------------------------
+def rq_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
+    """PiecewiseRationalQuadraticCDF._spline, flowcon/transforms/nonlinearities.py:451-481: learnable spline
+    parameters [D, K] / [D, K] / [D, K-1 or K+1] shared across the batch (`_share_across_batch` :246-247), no 1/sqrt(H)
+    scaling, identity-init off, constrained domain [0, 1] when tails is None."""
+    b = inputs.shape[0]
+    uw = state[prefix + "unnormalized_widths"].to(inputs.dtype)[None].expand(b, -1, -1)
+    uh = state[prefix + "unnormalized_heights"].to(inputs.dtype)[None].expand(b, -1, -1)
+    ud = state[prefix + "unnormalized_derivatives"].to(inputs.dtype)[None].expand(b, -1, -1)
+    if tails is None:
+        y, lad = rational_quadratic_spline(inputs, uw, uh, ud, inverse=inverse)
+    else:
+        y, lad = unconstrained_rational_quadratic_spline(inputs, uw, uh, ud, inverse=inverse, tails=tails,
+                                                         tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
 def _coupling(state, spec, inputs, context, inverse, elementwise):
-    """CouplingTransform.forward/inverse, flowcon/transforms/coupling.py:73-130 (no unconditional
-    transform on the path)."""
+    """CouplingTransform.forward/inverse, flowcon/transforms/coupling.py:73-130.  With an unconditional transform
+    (spec["unconditional"], coupling.py:90-94 / :116-120) the conditioner always sees the identity features on the
+    DATA side: forward transforms them after the conditioner ran, inverse before."""
     p = spec["prefix"]
     idf = state[p + "identity_features"]
     trf = state[p + "transform_features"]
     identity = inputs[:, idf]
     transform = inputs[:, trf]
+    uncond = spec.get("unconditional", False)
+    lad_id = 0.0
+    if uncond and inverse:
+        identity, lad_id = rq_cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
+                                  spec.get("tail_bound", 1.0), True)
     params = residual_net(state, p + "transform_net.", identity, context, spec.get("num_blocks", 2))
     transform, lad = elementwise(transform, params)
+    if uncond and not inverse:
+        identity, lad_id = rq_cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
+                                  spec.get("tail_bound", 1.0), False)
+    lad = lad + lad_id
     outputs = torch.empty_like(inputs)
     outputs[:, idf] = identity
     outputs[:, trf] = transform

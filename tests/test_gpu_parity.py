@@ -238,7 +238,7 @@ def test_sum_of_sigmoids_large_inputs(dev):
 # model level: the drop-in classes with the reference's weights
 # ------------------------------------------------------------------------------------------------
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
-          "maf_sos_small", "prq_coupling_notails_small"]
+          "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small"]
 
 
 def _load(name, dev):
