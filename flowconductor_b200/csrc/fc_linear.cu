@@ -1209,36 +1209,60 @@ __global__ void pack_kernel(const float* __restrict__ W, int64_t ldw, const floa
 }
 
 // Transposing producers for the split-K weight-gradient product: the reduction axis (the batch) has to be the contiguous
-// one for both operands.  32 x 32 tiles through shared memory (padded: conflict-free), coalesced on both sides.
+// one for both operands.  128 x 32 tiles through shared memory, coalesced on both sides.
 //   kSplit = false: dst[c][r] = src[r][c]                       (grad_y [B, N] -> [N, B])
 //   kSplit = true : dst[0][c][r] = tf32_hi(src[r][c]), dst[1][c][r] = tf32(src[r][c] - hi)   (x [B, K] -> packed planes)
 template <bool kSplit>
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
                                                         float* __restrict__ dst, int64_t ldd, int64_t plane_stride,
                                                         int relu) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  // 128 rows x 32 columns per block: 16 independent 128-byte row reads in flight per warp, then 16-byte vector
+  // writes along the (contiguous) row axis of the transposed result.  tile_t[c][r], row stride 132 floats: the
+  // vector reads are conflict-free, the scalar writes 4-way (shared memory is not the limit here, HBM is).
+  __shared__ __align__(16) float tile_t[32][132];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 128;
   const int c0 = blockIdx.y * 32;
+  float v[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t r = r0 + ty + 8 * i;
-    const int c = c0 + tx;
-    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? __ldcs(src + r * lds + c) : 0.f;
+  for (int i = 0; i < 16; ++i) {
+    const int64_t r = r0 + warp + 8 * i;
+    const int c = c0 + lane;
+    v[i] = (r < rows && c < cols) ? __ldcs(src + r * lds + c) : 0.f;
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tile_t[lane][warp + 8 * i] = relu ? fmaxf(v[i], 0.f) : v[i];
   __syncthreads();
+  const bool vec = (ldd & 3) == 0 && (plane_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int c = c0 + ty + 8 * i;
-    const int64_t r = r0 + tx;
-    if (c < cols && r < rows) {
-      const float v = relu ? fmaxf(tile[tx][ty + 8 * i], 0.f) : tile[tx][ty + 8 * i];
+    const int c = c0 + warp * 4 + i;
+    const int64_t r = r0 + 4 * lane;
+    if (c >= cols || r >= rows) continue;
+    const float4 t = *reinterpret_cast<const float4*>(&tile_t[warp * 4 + i][4 * lane]);
+    const float e[4] = {t.x, t.y, t.z, t.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       if (kSplit) {
-        const uint32_t hi = tc::to_tf32(v);
-        dst[(int64_t)c * ldd + r] = __uint_as_float(hi);
-        dst[plane_stride + (int64_t)c * ldd + r] = __uint_as_float(tc::to_tf32(v - __uint_as_float(hi)));
+        const uint32_t h = tc::to_tf32(e[j]);
+        hi[j] = __uint_as_float(h);
+        lo[j] = __uint_as_float(tc::to_tf32(e[j] - hi[j]));
       } else {
-        dst[(int64_t)c * ldd + r] = v;
+        hi[j] = e[j];
+      }
+    }
+    float* d = dst + (int64_t)c * ldd + r;
+    if (vec && r + 3 < rows) {
+      *reinterpret_cast<float4*>(d) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      if (kSplit) *reinterpret_cast<float4*>(d + plane_stride) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r + j < rows) {
+          d[j] = hi[j];
+          if (kSplit) d[plane_stride + j] = lo[j];
+        }
       }
     }
   }
@@ -1253,7 +1277,7 @@ extern "C" int fc_linear_transpose(const float* src, int64_t src_row_stride, int
   if (rows < 0 || cols <= 0 || dst_row_stride < rows || src_row_stride < cols) return FC_ERR_INVALID_ARGUMENT;
   if (rows == 0) return FC_OK;
   if (!src || !dst) return FC_ERR_INVALID_ARGUMENT;
-  const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  const dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((cols + 31) / 32));
   transpose_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_row_stride, rows, cols, dst, dst_row_stride, 0, 0);
   FC_CHECK_LAUNCH();
   return FC_OK;
@@ -1270,7 +1294,7 @@ extern "C" int fc_linear_pack_transposed(const float* X, int64_t x_row_stride, i
       cudaMemsetAsync(w_packed, 0, sizeof(float) * 2 * (size_t)n_pad * k_pad, st) != cudaSuccess)
     return FC_ERR_CUDA;
   if (cudaMemsetAsync(bias_packed, 0, sizeof(float) * (size_t)n_pad, st) != cudaSuccess) return FC_ERR_CUDA;
-  const dim3 grid((unsigned)((B + 31) / 32), (unsigned)((K + 31) / 32));
+  const dim3 grid((unsigned)((B + 127) / 128), (unsigned)((K + 31) / 32));
   transpose_kernel<true><<<grid, 256, 0, st>>>(X, x_row_stride, B, K, w_packed, k_pad, (int64_t)n_pad * k_pad, relu);
   FC_CHECK_LAUNCH();
   return FC_OK;

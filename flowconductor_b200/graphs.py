@@ -18,7 +18,7 @@ runs under `torch.no_grad()`.  There is no CPU fallback: capturing needs CUDA te
 """
 import torch
 
-__all__ = ["GraphedCall", "capture", "capture_sampler"]
+__all__ = ["GraphedCall", "GraphedTrainStep", "capture", "capture_sampler"]
 
 
 def _flatten(out):
@@ -102,3 +102,81 @@ def capture_sampler(flow, num_samples, context=None, with_log_prob=False, warmup
         with torch.cuda.device(next(flow.parameters()).device):
             return GraphedCall(lambda: method(num_samples), warmup=warmup)
     return GraphedCall(lambda c: method(num_samples, context=c), context, warmup=warmup)
+
+
+class GraphedTrainStep:
+    """One whole training step — `zero_grad; loss = loss_fn(*inputs); loss.backward(); [sync_gradients(module)];
+    optimizer.step()` (the loop of examples/toy_2d.py:57-67) — recorded into a CUDA graph.  At small per-GPU shards the
+    step is bound by its ~450 launches, not by the kernels (cfg 3 at 32 768 rows per rank); a replay is one launch.
+
+    * the optimizer must be capturable (`torch.optim.Adam(..., capturable=True)`): its step counter lives on the device;
+    * `sync_gradients` (e.g. `distributed.allreduce_gradients`) is captured with the rest — NCCL collectives are
+      graph-capturable;
+    * the warm-up steps needed before capture run on the example batch and are UNDONE afterwards (parameters and
+      optimizer state are restored in place), so constructing the object does not train.
+    `step(*inputs)` copies the batch into the static buffers, replays, and returns the (static) loss tensor."""
+
+    def __init__(self, module, optimizer, loss_fn, *example_inputs, sync_gradients=None, warmup=3):
+        for t in example_inputs:
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise RuntimeError("graph capture needs CUDA tensors as inputs: flowconductor_b200 runs only on the "
+                                   "GPU (no CPU fallback)")
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise ValueError("the optimizer must be constructed with capturable=True to be recorded in a CUDA graph")
+        self._static_in = [t.detach().clone() for t in example_inputs]
+        self.device = self._static_in[0].device
+        params = [p for p in module.parameters()]
+        saved_params = [p.detach().clone() for p in params]
+        # optimizer state that already exists (training resumed) is restored; state created by the warm-up is zeroed
+        prior = {id(t): t.detach().clone() for st in optimizer.state.values() for t in st.values()
+                 if isinstance(t, torch.Tensor)}
+
+        def one_step():
+            optimizer.zero_grad(set_to_none=True)
+            loss = loss_fn(*self._static_in)
+            loss.backward()
+            if sync_gradients is not None:
+                sync_gradients(module)
+            optimizer.step()
+            return loss
+
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    one_step()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._loss = one_step()
+            # undo the warm-up (and the capture itself does not execute): parameters back to their values, optimizer
+            # state back to "zero steps taken"
+            with torch.no_grad():
+                for p, s0 in zip(params, saved_params):
+                    p.copy_(s0)
+                for st in optimizer.state.values():
+                    for t in st.values():
+                        if isinstance(t, torch.Tensor):
+                            if id(t) in prior:
+                                t.copy_(prior[id(t)])
+                            else:
+                                t.zero_()
+            torch.cuda.synchronize(self.device)
+        self.replays = 0
+
+    def step(self, *inputs):
+        if len(inputs) != len(self._static_in):
+            raise ValueError("expected {} inputs, got {}".format(len(self._static_in), len(inputs)))
+        for dst, src in zip(self._static_in, inputs):
+            if src.shape != dst.shape or src.dtype != dst.dtype:
+                raise ValueError("graph was captured for inputs of shape {}, got {}".format(tuple(dst.shape),
+                                                                                          tuple(src.shape)))
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self._loss
+
+    __call__ = step

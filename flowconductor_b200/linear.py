@@ -243,10 +243,11 @@ def linear_splitk_t(a_t, packed, k_slices=None, column_sums=False):
         raise ValueError("activations have {} rows, the packed layer expects {}".format(K, packed.k_in))
     n4 = (packed.n_out + 3) // 4 * 4
     if k_slices is None:
-        # two waves of (row-tile pair, range) units over the SM pairs, at least 1024 reduction steps each
+        # two waves of (row-tile pair, range) units over the SM pairs, at least 512 reduction steps each (measured at
+        # 32768 rows, 256 x 256: 16 ranges 0.108 ms, 32: 0.067, 64: 0.046, 128: 0.051)
         pairs = (M + 255) // 256
         clusters = torch.cuda.get_device_properties(a_t.device).multi_processor_count // 2
-        k_slices = max(1, min(K // 1024, (2 * clusters) // pairs))
+        k_slices = max(1, min(K // 512, (2 * clusters) // pairs))
     slice_rows = _ceil_to(M, 256)
     partials = torch.empty((k_slices, slice_rows, n4), dtype=torch.float32, device=a_t.device)
     csum = torch.empty((k_slices, slice_rows), dtype=torch.float32, device=a_t.device) if column_sums else None

@@ -54,6 +54,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--graph", action="store_true", help="also time the cfg-3 step replayed from a CUDA graph")
+    ap.add_argument("--rows", type=int, default=0, help="override the cfg-3 global batch (e.g. 32768: one 8-GPU shard)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -89,7 +91,7 @@ def main():
     if want("cfg3_train"):
         wl, flow, state = build("cfg3", dev, trained_like=False)
         fdist.broadcast_parameters(flow)
-        Bg = wl["batch"]
+        Bg = args.rows or wl["batch"]
         B = Bg // world
         x = torch.randn(B, wl["features"], generator=gen, device=dev)
         opt = torch.optim.Adam(flow.parameters(), lr=1e-3, weight_decay=1e-5)
@@ -106,6 +108,16 @@ def main():
              workload="cfg3 MAF-RQS D=16 K=16 5 layers H=256: zero_grad, -log_prob.mean, backward, flat-bucket gradient "
                       "all-reduce, Adam", value=Bg / (ms * 1e-3), unit="samples/s", ms_per_step=ms, rows_per_gpu=B,
              global_rows=Bg, scaling="strong")
+        if args.graph:
+            # the same step recorded into one CUDA graph (gradient all-reduce included): the launch-bound regime
+            from flowconductor_b200 import graphs
+            gopt = torch.optim.Adam(flow.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True)
+            gstep = graphs.GraphedTrainStep(flow, gopt, lambda xb: -flow.log_prob(xb).mean(), x,
+                                            sync_gradients=fdist.allreduce_gradients)
+            ms = timed(lambda: gstep.step(x), dev, world)
+            emit(metric="train_step_samples_per_sec", impl="whole step replayed from one CUDA graph",
+                 workload="cfg3 training step", value=Bg / (ms * 1e-3), unit="samples/s", ms_per_step=ms,
+                 rows_per_gpu=B, global_rows=Bg, scaling="strong")
         if args.cpu and rank == 0:
             from oracle import restated
             specs = workloads.oracle_specs(wl)

@@ -34,3 +34,10 @@ for B, N, K in [(262144, 256, 256), (262144, 752, 256), (32768, 256, 256)]:
     print("B={} N={} K={}: torch.mm {:.3f} ms | transposes + split-K {:.3f} | untransposed grad_y {:.3f} "
           "(pack x^T {:.3f}, product + slice sum {:.3f}; transpose of grad_y was {:.3f})".format(
               B, N, K, t_mm, t_old, t_new, t_pack, t_gemm, t_tr), flush=True)
+
+# reduction ranges per product at a small per-GPU shard (the 8-GPU cfg-3 step: 32768 rows per rank)
+B, N, K = 32768, 256, 256
+gy = torch.randn(B, N, generator=g, device=dev)
+pk = fl.pack_transposed(torch.randn(B, K, generator=g, device=dev))
+print("k_slices sweep at B=32768, 256x256:", "  ".join(
+    "{}: {:.3f} ms".format(ks, timeit(lambda: fl.linear_splitk_t(gy, pk, k_slices=ks))) for ks in (16, 32, 64, 128)))

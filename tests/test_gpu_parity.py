@@ -775,3 +775,53 @@ def test_short_reduction_layer_keeps_tensor_core_weight_gradient(dev, monkeypatc
     assert torch.equal(y, torch.nn.functional.linear(x, w * mask, b))
     assert _gemm_err(gw, want_w) <= 2.0 * _gemm_err(ref_w, want_w) + 2e-7
     assert (gb.double() - want_b).abs().max() <= 2e-6 * want_b.abs().max()
+
+
+@pytest.mark.parametrize("rows,cols", [(4099, 100), (128, 32), (1000, 256), (5, 3)])
+def test_transposing_operand_producers(dev, rows, cols):
+    """fc_linear_transpose / fc_linear_pack_transposed on ragged shapes (vector and scalar store paths)."""
+    from flowconductor_b200 import linear as fl
+
+    g = torch.Generator(device=dev).manual_seed(rows)
+    x = torch.randn(rows, cols, generator=g, device=dev)
+    assert torch.equal(fl.transpose(x), x.t().contiguous())
+    for relu in (False, True):
+        pk = fl.pack_transposed(x, relu=relu)
+        planes = pk.w  # [2, n_pad, k_pad]: tf32 hi / lo planes of x^T, zero padded
+        src = x.relu() if relu else x
+        hi = planes[0, :cols, :rows]
+        assert (hi.contiguous().view(torch.int32) & 0x1FFF).abs().max() == 0  # tf32: low 13 mantissa bits clear
+        assert (hi - src.t()).abs().max() <= 2.0 ** -11 * src.abs().max()
+        lo = planes[1, :cols, :rows]
+        assert (hi.double() + lo.double() - src.t().double()).abs().max() <= 2.0 ** -21 * src.abs().max()
+        assert planes[:, cols:, :].abs().sum() == 0 and planes[:, :, rows:].abs().sum() == 0  # zero padding
+
+
+def test_cuda_graph_training_step_matches_eager(dev):
+    """graphs.GraphedTrainStep: three replayed steps (zero_grad, -log_prob.mean, backward, Adam) leave exactly the
+    parameters three eager steps leave; constructing the graph does not train."""
+    from flowconductor_b200 import graphs
+
+    wl = workloads.get_workload("cfg3_small")
+    flows_ = [workloads.build_flow(wl, seed=2).to(dev) for _ in range(2)]
+    flows_[1].load_state_dict(flows_[0].state_dict())
+    opts = [torch.optim.Adam(f.parameters(), lr=1e-3, weight_decay=1e-5, capturable=True) for f in flows_]
+    g = torch.Generator().manual_seed(8)
+    batches = [torch.randn(256, wl["features"], generator=g).to(dev) for _ in range(3)]
+    before = [p.detach().clone() for p in flows_[1].parameters()]
+    stepper = graphs.GraphedTrainStep(flows_[1], opts[1], lambda x: -flows_[1].log_prob(x).mean(), batches[0])
+    for p, b in zip(flows_[1].parameters(), before):
+        assert torch.equal(p, b)
+    losses = []
+    for x in batches:
+        opts[0].zero_grad(set_to_none=True)
+        loss = -flows_[0].log_prob(x).mean()
+        loss.backward()
+        opts[0].step()
+        losses.append((loss.item(), stepper.step(x).item()))
+    for le, lg in losses:
+        assert le == lg
+    for pe, pg in zip(flows_[0].parameters(), flows_[1].parameters()):
+        assert torch.equal(pe, pg)
+    with pytest.raises(ValueError):
+        graphs.GraphedTrainStep(flows_[0], torch.optim.Adam(flows_[0].parameters()), lambda x: x.sum(), batches[0])
