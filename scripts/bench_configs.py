@@ -175,6 +175,13 @@ def main():
              value=world * chunk * chunks / (ms * 1e-3), unit="samples/s", ms_per_step=ms, rows_per_gpu=chunk * chunks)
         del flow
     if world > 1:
+        if args.graph:
+            # a recorded graph keeps NCCL work objects alive and destroy_process_group() then waits forever: leave
+            # through a barrier and a hard exit instead
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
