@@ -613,6 +613,185 @@ FC_HD void affine_backward_elem(float x, float raw_scale, float shift, int activ
 }
 
 // ------------------------------------------------------------------------------------------------
+// piecewise-linear spline (flowcon/transforms/splines/linear.py:9-105; Mueller et al. 2018): K equal-width bins, the
+// per-feature parameters are the K unnormalised bin probabilities
+// ------------------------------------------------------------------------------------------------
+struct LinSplineParams {
+  int K, tails, inverse;
+  float left, right, bottom, top;
+  float log_k;  // log(K): logabsdet = log(pdf) - log(1/K) (linear.py:94-95)
+};
+
+// softmax of the K raw values (linear.py:53) into p[]; max-subtracted like torch.softmax
+template <int KC>
+FC_HD void linspline_pdf(int K, const float* u, float* p) {
+  float m = -INFINITY;
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) m = fmaxf(m, u[j]);
+  const float ml2 = m * FC_LOG2E;
+  float se = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) {
+    p[j] = fc_exp2(fmaf(u[j], FC_LOG2E, -ml2));
+    se += p[j];
+  }
+  const float inv = fc_rcp(se);
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) p[j] *= inv;
+}
+
+// domain handling as in rqs_domain: linear tails -> identity outside [-b, b] (linear.py:12-22, both ends inclusive);
+// no tails -> the reference raises InputOutsideDomain (linear.py:45-46): flag + clamp
+FC_HD bool linspline_domain(const LinSplineParams& c, float x, float& xs, unsigned& status) {
+  const float lo = c.inverse ? c.bottom : c.left;
+  const float hi = c.inverse ? c.top : c.right;
+  if (c.tails == FC_TAILS_LINEAR) {
+    const bool inside = (x >= lo) && (x <= hi);
+    xs = inside ? x : lo;
+    return inside;
+  }
+  xs = x;
+  if (!(x >= lo && x <= hi)) {
+    status |= FC_STATUS_INPUT_OUTSIDE_DOMAIN;
+    xs = fminf(fmaxf(x, lo), hi);
+    if (!(xs == xs)) xs = lo;
+  }
+  return true;
+}
+
+// forward pieces at a normalised position xn in [0, 1]: bin, position inside it, cdf at the bin's left edge
+template <int KC>
+FC_HD void linspline_forward_bin(int K, float xn, const float* p, int& idx, float& alpha, float& cdf_lo) {
+  const float bin_pos = xn * (float)K;               // linear.py:84
+  idx = (int)floorf(bin_pos);
+  idx = idx >= K ? K - 1 : (idx < 0 ? 0 : idx);      // :86-87
+  alpha = bin_pos - (float)idx;                      // :89
+  cdf_lo = 0.f;                                      // running sum = torch.cumsum (:55), cdf[idx] of the padded cdf (:57)
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) cdf_lo += j < idx ? p[j] : 0.f;
+}
+
+// One element, forward or inverse (c.inverse).  u -> this feature's K raw parameters.
+template <int KC>
+FC_HD void linspline_eval(const LinSplineParams& c, float x, const float* u, float& y, float& lad, unsigned& status) {
+  const int K = KC ? KC : c.K;
+  float p[KC ? KC : FC_MAX_BINS_GENERIC];
+  float xs;
+  const bool inside = linspline_domain(c, x, xs, status);
+  linspline_pdf<KC>(K, u, p);
+  float ys, ls;
+  if (!c.inverse) {
+    const float xn = (xs - c.left) / (c.right - c.left);  // :51
+    int idx;
+    float alpha, cdf_lo;
+    linspline_forward_bin<KC>(K, xn, p, idx, alpha, cdf_lo);
+    float pi = p[0];
+#pragma unroll(KC ? KC : 4)
+    for (int j = 1; j < K; ++j) pi = j == idx ? p[j] : pi;
+    float o = cdf_lo + alpha * pi;                       // :93-94
+    o = fminf(fmaxf(o, 0.f), 1.f);                       // :95
+    ls = fc_log_deriv(pi) + c.log_k;                     // :97-98
+    ys = o * (c.top - c.bottom) + c.bottom;              // :103
+  } else {
+    const float yn = (xs - c.bottom) / (c.top - c.bottom);  // :49
+    // knots c_0 = 0, c_m = p_0 + .. + p_{m-1}, c_K = 1 (forced, :56) + 1e-6 (searchsorted bumps the last knot IN PLACE,
+    // torchutils.py:147-149, before the slopes are taken, linear.py:60-71: the last bin's slope sees the bump)
+    int idx = -1;
+    float run = 0.f, c_lo = 0.f, c_hi = 0.f;
+#pragma unroll(KC ? KC : 4)
+    for (int m = 0; m <= K; ++m) {
+      const float knot = m == K ? 1.f + 1e-6f : run;
+      if (yn >= knot) {
+        idx = m;
+        c_lo = knot;
+      }
+      if (m < K) run += p[m];
+    }
+    idx = idx < 0 ? 0 : (idx > K - 1 ? K - 1 : idx);
+    // upper knot of the bin (second pass keeps the loop branch-free for the unrolled instantiations)
+    run = 0.f;
+    c_lo = 0.f;
+#pragma unroll(KC ? KC : 4)
+    for (int m = 0; m < K; ++m) {
+      c_lo = m == idx ? run : c_lo;
+      run += p[m];
+      c_hi = m == idx ? (m == K - 1 ? 1.f + 1e-6f : run) : c_hi;
+    }
+    const float b_lo = (float)idx / (float)K, b_hi = (float)(idx + 1) / (float)K;  // torch.linspace(0, 1, K + 1)
+    const float slope = (c_hi - c_lo) / (b_hi - b_lo);                             // :66-68
+    const float offset = c_hi - slope * b_hi;                                      // :69
+    float o = (yn - offset) / slope;                                               // :75
+    o = fminf(fmaxf(o, 0.f), 1.f);                                                 // :76
+    ls = -fc_log_deriv(slope);                                                     // :78
+    ys = o * (c.right - c.left) + c.left;                                          // :101
+  }
+  y = inside ? ys : x;
+  lad = inside ? ls : 0.f;
+}
+
+// Backward of linspline_eval for one element (the reference differentiates the op chain; closed form here).
+// Forward direction, inside the domain, S = top - bottom, W = right - left, i = bin, a = position in the bin:
+//   y = S (sum_{j<i} p_j + a p_i) + bottom,  lad = log p_i + log K,  dy/dx = S K p_i / W
+//   dL/dp_j = gy S ([j<i] + a [j=i]) + gl [j=i] / p_i ;   dL/du_j = p_j (dL/dp_j - sum_k p_k dL/dp_k)  (softmax)
+// Inverse direction: out = f^-1(v), lad = -ladf(out); implicit differentiation through the same adjoint:
+//   dL/dv = gy / f'(out) =: g;  parameter gradients = forward adjoint at out with upstream (-g, -gl).
+template <int KC>
+FC_HD void linspline_backward_elem(const LinSplineParams& c, float x, const float* u, float gy, float gl, float& gx,
+                                   float* gu) {
+  const int K = KC ? KC : c.K;
+  float p[KC ? KC : FC_MAX_BINS_GENERIC];
+  float xs;
+  unsigned status = 0;
+  const bool inside = linspline_domain(c, x, xs, status);
+  if (!inside) {  // identity outside the tails: no parameter dependence
+    gx = gy;
+    for (int j = 0; j < K; ++j) gu[j] = 0.f;
+    return;
+  }
+  linspline_pdf<KC>(K, u, p);
+  const float S = c.top - c.bottom, W = c.right - c.left;
+  float pos = xs;  // forward-direction input at which the adjoint is evaluated
+  if (c.inverse) {
+    LinSplineParams ci = c;
+    float out, unused;
+    linspline_eval<KC>(ci, x, u, out, unused, status);
+    pos = out;
+  }
+  const float xn = (pos - c.left) / W;
+  int idx;
+  float alpha, cdf_lo;
+  linspline_forward_bin<KC>(K, xn, p, idx, alpha, cdf_lo);
+  float pi = p[0];
+#pragma unroll(KC ? KC : 4)
+  for (int j = 1; j < K; ++j) pi = j == idx ? p[j] : pi;
+  const float dydx = S * (float)K * pi / W;
+  float gyf = gy, glf = gl;
+  if (c.inverse) {
+    // the reference's inverse takes the last bin's slope from the bumped end knot (1 + 1e-6 - c_{K-1}, see
+    // linspline_eval): visible in d out / d v when that bin's probability is small
+    const float mass = idx == K - 1 ? (1.f + 1e-6f) - cdf_lo : pi;
+    const float g = gy / (S * (float)K * mass / W);
+    gx = g;
+    gyf = -g;
+    glf = -gl;
+  } else {
+    gx = gy * dydx;
+  }
+  const float gi = glf / pi;
+  float dot = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) {
+    const float gp = gyf * S * (j < idx ? 1.f : (j == idx ? alpha : 0.f)) + (j == idx ? gi : 0.f);
+    dot += p[j] * gp;
+  }
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) {
+    const float gp = gyf * S * (j < idx ? 1.f : (j == idx ? alpha : 0.f)) + (j == idx ? gi : 0.f);
+    gu[j] = p[j] * (gp - dot);  // (gu may alias u: p[] was read before the first write)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // sum of sigmoids + extended softplus (adaptive_sigmoids.py:111-142, nonlinearities.py:519-552)
 // ------------------------------------------------------------------------------------------------
 #define FC_SOS_MAX_SIGMOIDS 64

@@ -1,6 +1,7 @@
 """Drop-in subset of `flowcon.transforms` for the element-wise bijection hot path."""
 from .adaptive_sigmoids import SumOfSigmoids  # noqa: F401
 from .autoregressive import (AutoregressiveTransform, MaskedAffineAutoregressiveTransform,  # noqa: F401
+                             MaskedPiecewiseLinearAutoregressiveTransform,
                              MaskedPiecewiseRationalQuadraticAutoregressiveTransform,
                              MaskedSumOfSigmoidsTransform)
 from .base import (CompositeTransform, InputOutsideDomain, InverseNotAvailable, InverseTransform,  # noqa: F401
@@ -8,9 +9,10 @@ from .base import (CompositeTransform, InputOutsideDomain, InverseNotAvailable, 
 from .conditional import (ConditionalPiecewiseRationalQuadraticTransform,  # noqa: F401
                           ConditionalSumOfSigmoidsTransform, ConditionalTransform)
 from .coupling import (AdditiveCouplingTransform, AffineCouplingTransform, CouplingTransform,  # noqa: F401
-                       PiecewiseRationalQuadraticCouplingTransform)
+                       PiecewiseLinearCouplingTransform, PiecewiseRationalQuadraticCouplingTransform)
 from .made import MADE, MaskedLinear  # noqa: F401
-from .nonlinearities import PiecewiseRationalQuadraticCDF  # noqa: F401
+from .nonlinearities import PiecewiseLinearCDF, PiecewiseRationalQuadraticCDF  # noqa: F401
 from .permutations import Permutation, RandomPermutation, ReversePermutation  # noqa: F401
 from . import splines  # noqa: F401
-from .splines import rational_quadratic_spline, unconstrained_rational_quadratic_spline  # noqa: F401
+from .splines import (linear_spline, rational_quadratic_spline, unconstrained_linear_spline,  # noqa: F401
+                      unconstrained_rational_quadratic_spline)

@@ -155,3 +155,26 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
         return tensorcore.rqs_layer(net, conditioner_inputs, inputs, self._spline, None, None, inverse,
                                     getattr(net, "hidden_features", None),
                                     allow_inplace=not inverse)  # the inverse re-reads `inputs` D times
+
+
+class MaskedPiecewiseLinearAutoregressiveTransform(AutoregressiveTransform):
+    """autoregressive.py:321-372: always the constrained unit box (`linear_spline` without tails).  Note the
+    reference's argument order: `num_bins` comes first."""
+
+    def __init__(self, num_bins, features, hidden_features, context_features=None, num_blocks=2,
+                 use_residual_blocks=True, random_mask=False, activation=F.relu, dropout_probability=0.0,
+                 use_batch_norm=False):
+        self.num_bins = num_bins
+        self.features = features
+        self._spline = splines.LinearSplineSettings(num_bins, None, 1.0)
+        super().__init__(_made(self, features, hidden_features, context_features, num_blocks, use_residual_blocks,
+                               random_mask, activation, dropout_probability, use_batch_norm))
+
+    def _output_dim_multiplier(self):
+        return self.num_bins
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return self._spline.apply(inputs, autoregressive_params, None, None, False)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return self._spline.apply(inputs, autoregressive_params, None, None, True)

@@ -15,7 +15,7 @@ from .. import _cabi, ops
 from ..nn import tensorcore
 from . import splines
 from .base import Transform
-from .nonlinearities import PiecewiseRationalQuadraticCDF
+from .nonlinearities import PiecewiseLinearCDF, PiecewiseRationalQuadraticCDF
 
 
 class CouplingTransform(Transform):
@@ -202,3 +202,28 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
         # final layer + spline in one kernel: the [B, D_t*P] parameter tensor never reaches HBM
         return tensorcore.rqs_layer(net, inputs, inputs, self._spline, self._tcols, self._ccols, inverse,
                                     self._scaling_width(), col_map=self._ccols, k_in=self.features)
+
+
+class PiecewiseLinearCouplingTransform(CouplingTransform):
+    """coupling.py:299-352 (Mueller et al. 2018): K raw bin probabilities per transformed feature, no 1/sqrt(H)
+    scaling; tails=None -> the unit box, tails="linear" -> identity outside [-tail_bound, tail_bound]."""
+
+    def __init__(self, mask, transform_net_create_fn, num_bins=10, tails=None, tail_bound=1.0,
+                 apply_unconditional_transform=False, img_shape=None):
+        if apply_unconditional_transform and img_shape:
+            raise NotImplementedError("image-shaped inputs are outside the B200 hot path")
+        self.num_bins = num_bins
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self._spline = splines.LinearSplineSettings(num_bins, tails, tail_bound)
+        unconditional = None
+        if apply_unconditional_transform:  # coupling.py:319-327
+            unconditional = lambda features: PiecewiseLinearCDF(  # noqa: E731
+                shape=[features], num_bins=num_bins, tails=tails, tail_bound=tail_bound)
+        super().__init__(mask, transform_net_create_fn, unconditional_transform=unconditional)
+
+    def _transform_dim_multiplier(self):
+        return self.num_bins
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        return self._spline.apply(inputs, transform_params, self._tcols, self._ccols, inverse)

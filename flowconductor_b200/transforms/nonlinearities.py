@@ -15,7 +15,7 @@ from torch import nn
 from . import splines
 from .base import Transform
 
-__all__ = ["PiecewiseRationalQuadraticCDF"]
+__all__ = ["PiecewiseLinearCDF", "PiecewiseRationalQuadraticCDF"]
 
 
 class PiecewiseRationalQuadraticCDF(Transform):
@@ -63,6 +63,40 @@ class PiecewiseRationalQuadraticCDF(Transform):
         if inputs.dim() != 2 or inputs.shape[1] != self.unnormalized_widths.shape[0]:
             raise ValueError("expected inputs of shape [batch, {}]".format(self.unnormalized_widths.shape[0]))
         return self._spline.apply(inputs, self._shared_params(inputs.shape[0]), None, None, inverse, None)
+
+    def forward(self, inputs, context=None):
+        return self._run(inputs, inverse=False)
+
+    def inverse(self, inputs, context=None):
+        return self._run(inputs, inverse=True)
+
+
+class PiecewiseLinearCDF(Transform):
+    """flowcon/transforms/nonlinearities.py:250-283: a piecewise-linear spline whose `unnormalized_pdf` [*shape, K] is a
+    learnable tensor shared across the batch."""
+
+    def __init__(self, shape, num_bins=10, tails=None, tail_bound=1.0):
+        super().__init__()
+        self.tail_bound = tail_bound
+        self.tails = tails
+        if isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(shape)
+        if len(shape) != 1:
+            raise NotImplementedError("image-shaped CDF layers are outside the B200 hot path")
+        self.unnormalized_pdf = nn.Parameter(torch.randn(*shape, num_bins))
+        self._spline = splines.LinearSplineSettings(num_bins, tails, tail_bound)
+
+    def _shared_params(self, batch_size):
+        return self.unnormalized_pdf.reshape(1, -1).expand(batch_size, -1)
+
+    def apply_on_columns(self, inputs, tcols, ccols, inverse):
+        return self._spline.apply(inputs, self._shared_params(inputs.shape[0]), tcols, ccols, inverse)
+
+    def _run(self, inputs, inverse):
+        if inputs.dim() != 2 or inputs.shape[1] != self.unnormalized_pdf.shape[0]:
+            raise ValueError("expected inputs of shape [batch, {}]".format(self.unnormalized_pdf.shape[0]))
+        return self._spline.apply(inputs, self._shared_params(inputs.shape[0]), None, None, inverse)
 
     def forward(self, inputs, context=None):
         return self._run(inputs, inverse=False)

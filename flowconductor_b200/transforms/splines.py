@@ -104,3 +104,54 @@ class RationalQuadraticSettings:
                                        float(self.min_derivative), float(wh_scale))
         check_status(status, tails)
         return y, lad
+
+
+# ------------------------------------------------------------------------------------------------
+# piecewise-linear spline (flowcon/transforms/splines/linear.py)
+# ------------------------------------------------------------------------------------------------
+class LinearSplineSettings:
+    """Hyper-parameters of a piecewise-linear spline layer and the one kernel call that applies them to a
+    [B, D_t * num_bins] parameter tensor (PiecewiseLinearCouplingTransform._piecewise_cdf, coupling.py:340-352)."""
+
+    def __init__(self, num_bins, tails, tail_bound):
+        if tails not in (None, "linear"):
+            raise RuntimeError("{} tails are not implemented.".format(tails))  # linear.py:22
+        self.num_bins = num_bins
+        self.tails = tails
+        self.tail_bound = tail_bound
+
+    def params_per_feature(self):
+        return self.num_bins
+
+    def apply(self, inputs, params, tcols, ccols, inverse):
+        if self.tails == "linear":
+            tails, lo, hi = _cabi.TAILS_LINEAR, -float(self.tail_bound), float(self.tail_bound)
+        else:
+            tails, lo, hi = _cabi.TAILS_NONE, 0.0, 1.0
+        y, lad, status = ops.linspline_layer(inputs, params, tcols, ccols, int(self.num_bins), tails, bool(inverse),
+                                             lo, hi, lo, hi)
+        check_status(status, tails)
+        return y, lad
+
+
+def _linear_elementwise(inputs, unnormalized_pdf, inverse, tails, left, right, bottom, top):
+    shape = inputs.shape
+    params = unnormalized_pdf.reshape(-1, unnormalized_pdf.shape[-1])
+    # every element is its own row (D_t = 1), so the kernel's per-row log-det IS the per-element one
+    y, lad, status = ops.linspline_layer(inputs.reshape(-1, 1), params, None, None, params.shape[-1], tails,
+                                         bool(inverse), float(left), float(right), float(bottom), float(top))
+    check_status(status, tails)
+    return y.reshape(shape), lad.reshape(shape)
+
+
+def linear_spline(inputs, unnormalized_pdf, inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0):
+    """flowcon/transforms/splines/linear.py:38-105 (per-element outputs and log-dets; raises InputOutsideDomain)."""
+    return _linear_elementwise(inputs, unnormalized_pdf, inverse, _cabi.TAILS_NONE, left, right, bottom, top)
+
+
+def unconstrained_linear_spline(inputs, unnormalized_pdf, inverse=False, tail_bound=1.0, tails="linear"):
+    """linear.py:9-35: identity outside [-tail_bound, tail_bound]."""
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    return _linear_elementwise(inputs, unnormalized_pdf, inverse, _cabi.TAILS_LINEAR, -tail_bound, tail_bound,
+                               -tail_bound, tail_bound)

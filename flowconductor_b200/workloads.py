@@ -77,6 +77,15 @@ WORKLOADS = {
                                              {"kind": "prq_coupling", "mask": "alternating_odd", "num_bins": 5,
                                               "tails": "linear", "tail_bound": 3.0, "hidden_features": 16,
                                               "num_blocks": 2, "unconditional": True}]},
+    # the piecewise-linear family (coupling.py:299-352, autoregressive.py:321-372, nonlinearities.py:250-283)
+    "plin_coupling_small": {"features": 6, "context_features": None, "batch": 64,
+                            "layers": [{"kind": "plin_coupling", "mask": "alternating_even", "num_bins": 8,
+                                        "tails": "linear", "tail_bound": 3.0, "hidden_features": 16, "num_blocks": 2,
+                                        "unconditional": True},
+                                       {"kind": "plin_coupling", "mask": "alternating_odd", "num_bins": 8,
+                                        "tails": "linear", "tail_bound": 3.0, "hidden_features": 16, "num_blocks": 2}]},
+    "maf_plin_small": {"features": 5, "context_features": None, "batch": 64,
+                       "layers": [{"kind": "maf_plin", "num_bins": 10, "hidden_features": 16, "num_blocks": 2}]},
     "prq_coupling_notails_small": {"features": 6, "context_features": None, "batch": 64,
                                    "layers": [{"kind": "prq_coupling", "mask": "mid_split", "num_bins": 5,
                                                "tails": None, "tail_bound": 1.0, "hidden_features": 16,
@@ -100,6 +109,8 @@ def params_per_feature(layer):
         return 2
     if kind in ("maf_sos", "cond_sos"):
         return 3 * layer["n_sigmoids"] + 1
+    if kind in ("plin_coupling", "maf_plin"):
+        return layer["num_bins"]
     raise ValueError(kind)
 
 
@@ -144,7 +155,7 @@ def trained_like_(state, workload, seed=1, weight_gain=8.0):
             continue
         net = {"prq_coupling": "transform_net", "affine_coupling": "transform_net", "maf_affine": "autoregressive_net",
                "maf_prq": "autoregressive_net", "maf_sos": "autoregressive_net", "cond_sos": "conditional_net",
-               "cond_prq": "conditional_net"}[kind]
+               "cond_prq": "conditional_net", "plin_coupling": "transform_net", "maf_plin": "autoregressive_net"}[kind]
         wkey = layer_prefix(i) + net + ".final_layer.weight"
         bkey = layer_prefix(i) + net + ".final_layer.bias"
         p = params_per_feature(layer)
@@ -183,6 +194,18 @@ def build_flow(workload, seed=0):
                     i, o, hidden_features=h, num_blocks=b),
                 num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
                 apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "plin_coupling":
+            hidden, blocks = layer["hidden_features"], layer["num_blocks"]
+            layers.append(transforms.PiecewiseLinearCouplingTransform(
+                mask=make_mask(features, layer["mask"]),
+                transform_net_create_fn=lambda i, o, h=hidden, b=blocks: nets.ResidualNet(
+                    i, o, hidden_features=h, num_blocks=b),
+                num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
+                apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "maf_plin":
+            layers.append(transforms.MaskedPiecewiseLinearAutoregressiveTransform(
+                num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
+                context_features=ctx, num_blocks=layer["num_blocks"]))
         elif kind == "affine_coupling":
             hidden, blocks = layer["hidden_features"], layer["num_blocks"]
             act = {"sigmoid2": transforms.AffineCouplingTransform.DEFAULT_SCALE_ACTIVATION,

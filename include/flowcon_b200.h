@@ -86,6 +86,26 @@ int fc_rqs_backward(const float* x, int64_t x_row_stride, const float* params, i
                     int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, const fc_rqs_config* cfg,
                     void* stream);
 
+/*
+ * Piecewise-linear spline layer: replaces linear_spline / unconstrained_linear_spline
+ * (flowcon/transforms/splines/linear.py:9-105) as called by PiecewiseLinearCouplingTransform._piecewise_cdf
+ * (coupling.py:340-352), MaskedPiecewiseLinearAutoregressiveTransform._elementwise (autoregressive.py:355-366) and
+ * PiecewiseLinearCDF._spline (nonlinearities.py:263-277).  params[r] = per transformed feature num_bins raw bin
+ * probabilities (P = num_bins).  tails = FC_TAILS_LINEAR: identity outside [left, right] (= [-tail_bound, tail_bound],
+ * bottom/top equal left/right); FC_TAILS_NONE: inputs outside the domain set FC_STATUS_INPUT_OUTSIDE_DOMAIN (the
+ * reference raises, linear.py:45-46).  Column lists, strides, logabsdet accumulation and status as for fc_rqs_apply.
+ */
+int fc_linspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride, float* y,
+                       int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B, int32_t D_t,
+                       fc_cols tcols, fc_cols ccols, int32_t num_bins, int32_t tails, float left, float right,
+                       float bottom, float top, int32_t inverse, int32_t* status, void* stream);
+/* adjoint of fc_linspline_apply (either direction): grad_x [B, *] and grad_params [B, D_t * num_bins] */
+int fc_linspline_backward(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                          const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet, float* grad_x,
+                          int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride, int64_t B, int32_t D_t,
+                          fc_cols tcols, fc_cols ccols, int32_t num_bins, int32_t tails, float left, float right,
+                          float bottom, float top, int32_t inverse, void* stream);
+
 /* Affine element-wise transforms. */
 #define FC_AFFINE_BLOCKED 0     /* params[r] = [shift(D_t) | raw_scale(D_t)]      coupling.py:234-238 */
 #define FC_AFFINE_INTERLEAVED 1 /* params[r] = [raw_scale_0, shift_0, raw_scale_1, ...] autoregressive.py:124-129 */

@@ -167,6 +167,44 @@ def make_functions():
 
 
 # ------------------------------------------------------------------------------------------------
+def make_linear_functions():
+    """functions_linear.npz: the reference's linear_spline / unconstrained_linear_spline (splines/linear.py) forward,
+    inverse and autograd gradients, fp32 and fp64, per-element outputs."""
+    from flowcon.transforms.splines import linear as ref_lin
+
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    for name, k, tails, tb, inverse in [("lin_fwd_k8", 8, None, 1.0, False), ("lin_inv_k8", 8, None, 1.0, True),
+                                        ("lin_fwd_tails_k10", 10, "linear", 3.0, False),
+                                        ("lin_inv_tails_k10", 10, "linear", 3.0, True),
+                                        ("lin_fwd_k5", 5, None, 1.0, False)]:
+        n = 512
+        u = torch.randn(n, k, generator=g) * 1.5
+        if tails is None:
+            x = torch.rand(n, generator=g)
+            x[:4] = torch.tensor([0.0, 1.0, 0.5, 1.0 / k])  # domain ends and a bin edge
+        else:
+            x = torch.randn(n, generator=g) * 2.5
+            x[:4] = torch.tensor([-tb, tb, 0.0, 5.0])
+        gy, gl = torch.randn(n, generator=g), torch.randn(n, generator=g)
+        out[name + "/meta"] = np.array([k, 0 if tails is None else 1, tb, 1 if inverse else 0], dtype=np.float64)
+        out[name + "/x"], out[name + "/params"] = np32(x), np32(u)
+        out[name + "/gy"], out[name + "/gl"] = np32(gy), np32(gl)
+        for dt, tag in ((torch.float32, "32"), (torch.float64, "64")):
+            conv = np32 if tag == "32" else np64
+            xx = x.to(dt).clone().requires_grad_(True)
+            uu = u.to(dt).clone().requires_grad_(True)
+            if tails is None:
+                y, lad = ref_lin.linear_spline(xx, uu, inverse=inverse)
+            else:
+                y, lad = ref_lin.unconstrained_linear_spline(xx, uu, inverse=inverse, tail_bound=tb, tails=tails)
+            gx, gu = torch.autograd.grad((y * gy.to(dt)).sum() + (lad * gl.to(dt)).sum(), [xx, uu])
+            out[name + "/y" + tag], out[name + "/lad" + tag] = conv(y), conv(lad)
+            out[name + "/gx" + tag], out[name + "/gp" + tag] = conv(gx), conv(gu)
+    np.savez_compressed(os.path.join(GOLDEN, "functions_linear.npz"), **out)
+    print("functions_linear.npz:", len(out), "arrays")
+
+
 # model-level cases
 # ------------------------------------------------------------------------------------------------
 def build_reference_flow(wl, seed=0):
@@ -192,6 +230,16 @@ def build_reference_flow(wl, seed=0):
                        "softplus_clamp3": transforms.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION}[
                     layer["scale_activation"]]
                 layers.append(transforms.AffineCouplingTransform(mask, create, scale_activation=act))
+        elif kind == "plin_coupling":
+            h, b = layer["hidden_features"], layer["num_blocks"]
+            create = lambda i, o, h=h, b=b: nets.ResidualNet(i, o, hidden_features=h, num_blocks=b)  # noqa: E731
+            layers.append(transforms.PiecewiseLinearCouplingTransform(
+                workloads.make_mask(features, layer["mask"]), create, num_bins=layer["num_bins"], tails=layer["tails"],
+                tail_bound=layer["tail_bound"], apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "maf_plin":
+            layers.append(transforms.MaskedPiecewiseLinearAutoregressiveTransform(
+                num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
+                context_features=ctx, num_blocks=layer["num_blocks"]))
         elif kind == "maf_affine":
             layers.append(transforms.MaskedAffineAutoregressiveTransform(
                 features=features, hidden_features=layer["hidden_features"], context_features=ctx,
@@ -267,6 +315,11 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-uncond":  # add one fixture without rewriting the others
         make_model("prq_coupling_uncond_small", with_grad=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-linear":
+        make_linear_functions()
+        make_model("plin_coupling_small", with_grad=True)
+        make_model("maf_plin_small", with_grad=True, uniform01=True)
         sys.exit(0)
     make_functions()
     make_model("cfg1", with_grad=True, batch=2048)

@@ -219,6 +219,81 @@ def rq_elementwise(inputs, params, num_bins, tails, tail_bound, inverse, wh_divi
 
 
 # --------------------------------------------------------------------------------------------
+# n3: piecewise-linear spline  (flowcon/transforms/splines/linear.py:9-105)
+# --------------------------------------------------------------------------------------------
+def linear_spline(inputs, unnormalized_pdf, inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0):
+    """linear.py:38-105.  K equal-width bins with softmax probabilities; the cdf's last knot is forced to 1 (:56) and,
+    in the inverse, bumped by 1e-6 IN PLACE by `searchsorted` (torchutils.py:147-149) BEFORE the slopes are taken
+    (:60-71), so the last bin's slope and offset see the bump — kept."""
+    if torch.min(inputs) < left or torch.max(inputs) > right:
+        raise InputOutsideDomain()
+    if inverse:
+        inputs = (inputs - bottom) / (top - bottom)
+    else:
+        inputs = (inputs - left) / (right - left)
+    num_bins = unnormalized_pdf.size(-1)
+    pdf = F.softmax(unnormalized_pdf, dim=-1)
+    cdf = torch.cumsum(pdf, dim=-1)
+    cdf[..., -1] = 1.0
+    cdf = F.pad(cdf, pad=(1, 0), mode="constant", value=0.0)
+    if inverse:
+        cdf[..., -1] += 1e-6  # the in-place bump of searchsorted
+        inv_bin_idx = torch.sum(inputs[..., None] >= cdf, dim=-1) - 1
+        bin_boundaries = torch.linspace(0, 1, num_bins + 1).view([1] * inputs.dim() + [-1]).expand(
+            *inputs.shape, -1).to(cdf.dtype)
+        slopes = (cdf[..., 1:] - cdf[..., :-1]) / (bin_boundaries[..., 1:] - bin_boundaries[..., :-1])
+        offsets = cdf[..., 1:] - slopes * bin_boundaries[..., 1:]
+        inv_bin_idx = inv_bin_idx.unsqueeze(-1)
+        input_slopes = slopes.gather(-1, inv_bin_idx)[..., 0]
+        input_offsets = offsets.gather(-1, inv_bin_idx)[..., 0]
+        outputs = (inputs - input_offsets) / input_slopes
+        outputs = torch.clamp(outputs, 0, 1)
+        logabsdet = -torch.log(input_slopes)
+    else:
+        bin_pos = inputs * num_bins
+        bin_idx = torch.floor(bin_pos).long()
+        bin_idx[bin_idx >= num_bins] = num_bins - 1
+        alpha = bin_pos - bin_idx.to(inputs.dtype)
+        input_pdfs = pdf.gather(-1, bin_idx[..., None])[..., 0]
+        outputs = cdf.gather(-1, bin_idx[..., None])[..., 0]
+        outputs = outputs + alpha * input_pdfs
+        outputs = torch.clamp(outputs, 0, 1)
+        logabsdet = torch.log(input_pdfs) - math.log(1.0 / num_bins)
+    if inverse:
+        outputs = outputs * (right - left) + left
+    else:
+        outputs = outputs * (top - bottom) + bottom
+    return outputs, logabsdet
+
+
+def unconstrained_linear_spline(inputs, unnormalized_pdf, inverse=False, tail_bound=1.0, tails="linear"):
+    """linear.py:9-35: identity (logabsdet 0) outside [-tail_bound, tail_bound], both ends inclusive."""
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    inside = (inputs >= -tail_bound) & (inputs <= tail_bound)
+    outputs = torch.where(inside, torch.zeros_like(inputs), inputs)
+    logabsdet = torch.zeros_like(inputs)
+    if torch.any(inside):
+        o, l = linear_spline(inputs[inside], unnormalized_pdf[inside, :], inverse=inverse, left=-tail_bound,
+                             right=tail_bound, bottom=-tail_bound, top=tail_bound)
+        outputs = outputs.masked_scatter(inside, o)
+        logabsdet = logabsdet.masked_scatter(inside, l)
+    return outputs, logabsdet
+
+
+def linear_elementwise(inputs, params, num_bins, tails, tail_bound, inverse):
+    """coupling.py:340-352 (`PiecewiseLinearCouplingTransform._piecewise_cdf`): params [B, D_t*K] viewed [B, D_t, K],
+    no scaling; log-det summed per sample (coupling.py:293)."""
+    b, d = inputs.shape
+    params = params.reshape(b, d, num_bins)
+    if tails is None:
+        y, lad = linear_spline(inputs, params, inverse=inverse)
+    else:
+        y, lad = unconstrained_linear_spline(inputs, params, inverse=inverse, tails=tails, tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
+# --------------------------------------------------------------------------------------------
 # a7 / a9: affine element-wise transforms
 # --------------------------------------------------------------------------------------------
 def affine_scale(unconstrained, activation):
@@ -421,6 +496,17 @@ def rq_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
     return y, sum_except_batch(lad)
 
 
+def linear_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
+    """PiecewiseLinearCDF._spline, flowcon/transforms/nonlinearities.py:263-277: `unnormalized_pdf` [D, K] shared across
+    the batch."""
+    u = state[prefix + "unnormalized_pdf"].to(inputs.dtype)[None].expand(inputs.shape[0], -1, -1)
+    if tails is None:
+        y, lad = linear_spline(inputs, u, inverse=inverse)
+    else:
+        y, lad = unconstrained_linear_spline(inputs, u, inverse=inverse, tails=tails, tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
 def _coupling(state, spec, inputs, context, inverse, elementwise):
     """CouplingTransform.forward/inverse, flowcon/transforms/coupling.py:73-130.  With an unconditional transform
     (spec["unconditional"], coupling.py:90-94 / :116-120) the conditioner always sees the identity features on the
@@ -431,15 +517,16 @@ def _coupling(state, spec, inputs, context, inverse, elementwise):
     identity = inputs[:, idf]
     transform = inputs[:, trf]
     uncond = spec.get("unconditional", False)
+    cdf = linear_cdf if spec["kind"] == "plin_coupling" else rq_cdf
     lad_id = 0.0
     if uncond and inverse:
-        identity, lad_id = rq_cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
-                                  spec.get("tail_bound", 1.0), True)
+        identity, lad_id = cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
+                               spec.get("tail_bound", 1.0), True)
     params = residual_net(state, p + "transform_net.", identity, context, spec.get("num_blocks", 2))
     transform, lad = elementwise(transform, params)
     if uncond and not inverse:
-        identity, lad_id = rq_cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
-                                  spec.get("tail_bound", 1.0), False)
+        identity, lad_id = cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
+                               spec.get("tail_bound", 1.0), False)
     lad = lad + lad_id
     outputs = torch.empty_like(inputs)
     outputs[:, idf] = identity
@@ -480,6 +567,10 @@ def apply_layer(state, spec, inputs, context=None, inverse=False):
         def ew(x, params):
             return rq_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0),
                                   inverse, divisor, ident, constrained_bound=bound)
+    elif kind in ("plin_coupling", "maf_plin"):
+        def ew(x, params):
+            return linear_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0),
+                                      inverse)
     elif kind == "affine_coupling":
         def ew(x, params):
             return affine_elementwise(x, params, "blocked", spec.get("scale_activation", "sigmoid2"), inverse)

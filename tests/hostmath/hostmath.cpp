@@ -72,6 +72,33 @@ void hm_sos_invert(const float* z, const float* params, float* x, float* logj, l
     sos_invert(z[i], params + i * (3 * n_sigmoids + 1), n_sigmoids, iters, lim, x[i], logj[i]);
 }
 
+// piecewise-linear spline: one element per call, K raw parameters each (runtime-K and unrolled instantiations)
+void hm_linspline_apply(const float* x, const float* params, float* y, float* lad, unsigned* status, long n, int k,
+                        int tails, float lo, float hi, int inverse, int unrolled) {
+  LinSplineParams c;
+  c.K = k; c.tails = tails; c.inverse = inverse; c.left = lo; c.right = hi; c.bottom = lo; c.top = hi;
+  c.log_k = (float)log((double)k);
+  for (long i = 0; i < n; ++i) {
+    unsigned st = 0;
+    if (unrolled && k == 8) linspline_eval<8>(c, x[i], params + i * k, y[i], lad[i], st);
+    else if (unrolled && k == 10) linspline_eval<10>(c, x[i], params + i * k, y[i], lad[i], st);
+    else linspline_eval<0>(c, x[i], params + i * k, y[i], lad[i], st);
+    status[0] |= st;
+  }
+}
+
+void hm_linspline_backward(const float* x, const float* params, const float* gy, const float* gl, float* gx, float* gp,
+                           long n, int k, int tails, float lo, float hi, int inverse, int unrolled) {
+  LinSplineParams c;
+  c.K = k; c.tails = tails; c.inverse = inverse; c.left = lo; c.right = hi; c.bottom = lo; c.top = hi;
+  c.log_k = (float)log((double)k);
+  for (long i = 0; i < n; ++i) {
+    if (unrolled && k == 8) linspline_backward_elem<8>(c, x[i], params + i * k, gy[i], gl[i], gx[i], gp + i * k);
+    else if (unrolled && k == 10) linspline_backward_elem<10>(c, x[i], params + i * k, gy[i], gl[i], gx[i], gp + i * k);
+    else linspline_backward_elem<0>(c, x[i], params + i * k, gy[i], gl[i], gx[i], gp + i * k);
+  }
+}
+
 // compile-time n = 10 instantiations (what the kernels run for the default sigmoid count)
 void hm_sos_apply_n10(const float* x, const float* params, float* y, float* logj, long n) {
   for (long i = 0; i < n; ++i) sos_eval_t<10>(x[i], params + i * 31, 10, y[i], logj[i]);

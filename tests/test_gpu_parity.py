@@ -238,7 +238,8 @@ def test_sum_of_sigmoids_large_inputs(dev):
 # model level: the drop-in classes with the reference's weights
 # ------------------------------------------------------------------------------------------------
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
-          "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small"]
+          "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small", "plin_coupling_small",
+          "maf_plin_small"]
 
 
 def _load(name, dev):
@@ -825,3 +826,41 @@ def test_cuda_graph_training_step_matches_eager(dev):
         assert torch.equal(pe, pg)
     with pytest.raises(ValueError):
         graphs.GraphedTrainStep(flows_[0], torch.optim.Adam(flows_[0].parameters()), lambda x: x.sum(), batches[0])
+
+
+@pytest.mark.parametrize("name", ["lin_fwd_k8", "lin_inv_k8", "lin_fwd_tails_k10", "lin_inv_tails_k10", "lin_fwd_k5"])
+def test_linear_spline_kernels(dev, name):
+    """fc_linspline_apply / fc_linspline_backward (through transforms.linear_spline / unconstrained_linear_spline,
+    the reference's functional API) against golden vectors of the reference's splines/linear.py."""
+    gold = load_golden("functions_linear")
+    k, has_tails, tb, inverse = gold[name + "/meta"].tolist()
+    x = gold[name + "/x"].to(dev).requires_grad_(True)
+    u = gold[name + "/params"].to(dev).requires_grad_(True)
+    if has_tails:
+        y, lad = transforms.unconstrained_linear_spline(x, u, inverse=bool(inverse), tail_bound=tb, tails="linear")
+    else:
+        y, lad = transforms.linear_spline(x, u, inverse=bool(inverse))
+    assert_parity(y, gold[name + "/y32"], gold[name + "/y64"], OUT_TOL, 1.0, name + " y")
+    assert_parity(lad, gold[name + "/lad32"], gold[name + "/lad64"], OUT_TOL, 1.0, name + " lad")
+    gx, gu = torch.autograd.grad((y * gold[name + "/gy"].to(dev)).sum() + (lad * gold[name + "/gl"].to(dev)).sum(), [x, u])
+    s = max(1e-2, gold[name + "/gx64"].abs().mean().item())
+    assert_parity(gx, gold[name + "/gx32"], gold[name + "/gx64"], GRAD_TOL, s, name + " gx")
+    s = max(1e-2, gold[name + "/gp64"].abs().mean().item())
+    assert_parity(gu, gold[name + "/gp32"], gold[name + "/gp64"], GRAD_TOL, s, name + " gp")
+
+
+def test_linear_spline_domain_error_and_wide_layer(dev):
+    """linear.py:45-46 raises InputOutsideDomain without tails; a 64-feature layer exercises the TMA-ring kernel and
+    round-trips."""
+    with pytest.raises(transforms.InputOutsideDomain):
+        transforms.linear_spline(torch.tensor([0.5, 1.5], device=dev), torch.zeros(2, 8, device=dev))
+    g = torch.Generator(device=dev).manual_seed(4)
+    layer = transforms.PiecewiseLinearCDF([64], num_bins=8, tails="linear", tail_bound=3.0).to(dev)
+    x = torch.randn(20000, 64, generator=g, device=dev) * 2
+    with torch.no_grad():
+        y, lad = layer(x)
+        xi, ladi = layer.inverse(y)
+        ref_y, ref_lad = restated.linear_cdf({"unnormalized_pdf": layer.unnormalized_pdf.detach().cpu().double()}, "",
+                                             x.cpu().double(), 8, "linear", 3.0, False)
+    assert (y.cpu().double() - ref_y).abs().max() < 2e-5 and (lad.cpu().double() - ref_lad).abs().max() < 2e-4
+    assert (xi - x).abs().max() < 2e-4 and (lad + ladi).abs().max() < 2e-3

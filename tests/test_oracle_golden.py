@@ -145,7 +145,8 @@ def test_sum_of_sigmoids_matches_reference(fn_gold, name):
 
 
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
-          "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small"]
+          "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small", "plin_coupling_small",
+          "maf_plin_small"]
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -173,7 +174,34 @@ def test_flow_matches_reference(name):
         _close(ladi.detach() / ls, gold["inv_lad" + tag] / ls, inv_tol * 10, name + " inverse logabsdet " + tag)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg3_small", "cfg2_small"])
+LINEAR_CASES = ["lin_fwd_k8", "lin_inv_k8", "lin_fwd_tails_k10", "lin_inv_tails_k10", "lin_fwd_k5"]
+
+
+@pytest.mark.parametrize("name", LINEAR_CASES)
+def test_linear_spline_matches_reference(name):
+    """restated.linear_spline / unconstrained_linear_spline against the unmodified reference (functions_linear.npz):
+    outputs, log-dets and autograd gradients, fp32 and fp64."""
+    gold = load_golden("functions_linear")
+    k, has_tails, tb, inverse = gold[name + "/meta"].tolist()
+    for dtype, tag, tol in ((torch.float32, "32", 1e-5), (torch.float64, "64", 1e-12)):
+        x = gold[name + "/x"].to(dtype).requires_grad_(True)
+        u = gold[name + "/params"].to(dtype).requires_grad_(True)
+        if has_tails:
+            y, lad = restated.unconstrained_linear_spline(x, u, inverse=bool(inverse), tail_bound=tb, tails="linear")
+        else:
+            y, lad = restated.linear_spline(x, u, inverse=bool(inverse))
+        gx, gu = torch.autograd.grad((y * gold[name + "/gy"].to(dtype)).sum() + (lad * gold[name + "/gl"].to(dtype)).sum(),
+                                     [x, u])
+        _close(y, gold[name + "/y" + tag], tol, name + " y " + tag)
+        _close(lad, gold[name + "/lad" + tag], tol * 10, name + " lad " + tag)
+        gs = max(1.0, gold[name + "/gx" + tag].abs().max().item())
+        _close(gx / gs, gold[name + "/gx" + tag] / gs, tol * 10, name + " gx " + tag)
+        gs = max(1.0, gold[name + "/gp" + tag].abs().max().item())
+        _close(gu / gs, gold[name + "/gp" + tag] / gs, tol * 10, name + " gp " + tag)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3_small", "cfg2_small", "plin_coupling_small", "maf_plin_small",
+                                  "prq_coupling_uncond_small"])
 def test_flow_parameter_gradients_match_reference(name):
     gold = load_golden(name)
     wl = workloads.get_workload(name)
