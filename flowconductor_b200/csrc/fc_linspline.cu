@@ -42,6 +42,8 @@ static int make_linspline_params(int32_t num_bins, int32_t tails, float left, fl
   c.inverse = inverse != 0;
   c.left = left; c.right = right; c.bottom = bottom; c.top = top;
   c.log_k = (float)log((double)num_bins);
+  c.inv_w = (float)(1.0 / ((double)right - (double)left));
+  c.inv_h = (float)(1.0 / ((double)top - (double)bottom));
   return FC_OK;
 }
 

@@ -619,20 +619,73 @@ FC_HD void affine_backward_elem(float x, float raw_scale, float shift, int activ
 struct LinSplineParams {
   int K, tails, inverse;
   float left, right, bottom, top;
-  float log_k;  // log(K): logabsdet = log(pdf) - log(1/K) (linear.py:94-95)
+  float log_k;          // log(K): logabsdet = log(pdf) - log(1/K) (linear.py:94-95)
+  float inv_w, inv_h;   // 1 / (right - left), 1 / (top - bottom): the normalisations :49-51 as multiplications
 };
+
+// The K raw values of one feature -> registers.  Neighbouring lanes own neighbouring features, K words apart: with
+// scalar loads K = 8 is an 8-way shared-memory bank conflict (K = 23 / 31 / 47 of the other layers are odd, hence
+// conflict-free).  K = 8: two 16-byte loads whose order alternates every 4 lanes (lanes l and l + 4 would hit the same
+// banks); K = 10: five 8-byte loads (10 l mod 32 is distinct over a half warp).  Falls back to scalar loads when the
+// block is not aligned (general strides).
+template <int KC>
+FC_HD void linspline_load(int K, const float* u, float* raw) {
+#if FC_DEVICE_MATH
+  if (KC == 8 && (reinterpret_cast<uintptr_t>(u) & 15) == 0) {
+    const bool sw = ((threadIdx.x >> 2) & 1) != 0;
+    const float4 a = *reinterpret_cast<const float4*>(u + (sw ? 4 : 0));
+    const float4 b = *reinterpret_cast<const float4*>(u + (sw ? 0 : 4));
+    raw[0] = sw ? b.x : a.x; raw[1] = sw ? b.y : a.y; raw[2] = sw ? b.z : a.z; raw[3] = sw ? b.w : a.w;
+    raw[4] = sw ? a.x : b.x; raw[5] = sw ? a.y : b.y; raw[6] = sw ? a.z : b.z; raw[7] = sw ? a.w : b.w;
+    return;
+  }
+  if (KC == 10 && (reinterpret_cast<uintptr_t>(u) & 7) == 0) {
+#pragma unroll
+    for (int h = 0; h < 5; ++h) {
+      const float2 v = *reinterpret_cast<const float2*>(u + 2 * h);
+      raw[2 * h] = v.x;
+      raw[2 * h + 1] = v.y;
+    }
+    return;
+  }
+#endif
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) raw[j] = u[j];
+}
+
+// the mirror image for the K parameter gradients
+template <int KC>
+FC_HD void linspline_store(int K, float* gu, const float* v) {
+#if FC_DEVICE_MATH
+  if (KC == 8 && (reinterpret_cast<uintptr_t>(gu) & 15) == 0) {
+    const bool sw = ((threadIdx.x >> 2) & 1) != 0;
+    const float4 lo = make_float4(v[0], v[1], v[2], v[3]), hi = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(gu + (sw ? 4 : 0)) = sw ? hi : lo;
+    *reinterpret_cast<float4*>(gu + (sw ? 0 : 4)) = sw ? lo : hi;
+    return;
+  }
+  if (KC == 10 && (reinterpret_cast<uintptr_t>(gu) & 7) == 0) {
+#pragma unroll
+    for (int h = 0; h < 5; ++h) *reinterpret_cast<float2*>(gu + 2 * h) = make_float2(v[2 * h], v[2 * h + 1]);
+    return;
+  }
+#endif
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) gu[j] = v[j];
+}
 
 // softmax of the K raw values (linear.py:53) into p[]; max-subtracted like torch.softmax
 template <int KC>
 FC_HD void linspline_pdf(int K, const float* u, float* p) {
+  linspline_load<KC>(K, u, p);
   float m = -INFINITY;
 #pragma unroll(KC ? KC : 4)
-  for (int j = 0; j < K; ++j) m = fmaxf(m, u[j]);
+  for (int j = 0; j < K; ++j) m = fmaxf(m, p[j]);
   const float ml2 = m * FC_LOG2E;
   float se = 0.f;
 #pragma unroll(KC ? KC : 4)
   for (int j = 0; j < K; ++j) {
-    p[j] = fc_exp2(fmaf(u[j], FC_LOG2E, -ml2));
+    p[j] = fc_exp2(fmaf(p[j], FC_LOG2E, -ml2));
     se += p[j];
   }
   const float inv = fc_rcp(se);
@@ -681,7 +734,7 @@ FC_HD void linspline_eval(const LinSplineParams& c, float x, const float* u, flo
   linspline_pdf<KC>(K, u, p);
   float ys, ls;
   if (!c.inverse) {
-    const float xn = (xs - c.left) / (c.right - c.left);  // :51
+    const float xn = (xs - c.left) * c.inv_w;  // :51
     int idx;
     float alpha, cdf_lo;
     linspline_forward_bin<KC>(K, xn, p, idx, alpha, cdf_lo);
@@ -693,7 +746,7 @@ FC_HD void linspline_eval(const LinSplineParams& c, float x, const float* u, flo
     ls = fc_log_deriv(pi) + c.log_k;                     // :97-98
     ys = o * (c.top - c.bottom) + c.bottom;              // :103
   } else {
-    const float yn = (xs - c.bottom) / (c.top - c.bottom);  // :49
+    const float yn = (xs - c.bottom) * c.inv_h;  // :49
     // knots c_0 = 0, c_m = p_0 + .. + p_{m-1}, c_K = 1 (forced, :56) + 1e-6 (searchsorted bumps the last knot IN PLACE,
     // torchutils.py:147-149, before the slopes are taken, linear.py:60-71: the last bin's slope sees the bump)
     int idx = -1;
@@ -717,10 +770,12 @@ FC_HD void linspline_eval(const LinSplineParams& c, float x, const float* u, flo
       run += p[m];
       c_hi = m == idx ? (m == K - 1 ? 1.f + 1e-6f : run) : c_hi;
     }
-    const float b_lo = (float)idx / (float)K, b_hi = (float)(idx + 1) / (float)K;  // torch.linspace(0, 1, K + 1)
-    const float slope = (c_hi - c_lo) / (b_hi - b_lo);                             // :66-68
+    // bin boundaries torch.linspace(0, 1, K + 1): b_m = m / K, so the slope's denominator :66-68 is 1 / K (the
+    // reference's fp32 difference of two linspace values carries a rounding error the fp64 reference does not have)
+    const float b_hi = (float)(idx + 1) * fc_rcp((float)K);
+    const float slope = (c_hi - c_lo) * (float)K;
     const float offset = c_hi - slope * b_hi;                                      // :69
-    float o = (yn - offset) / slope;                                               // :75
+    float o = fc_div(yn - offset, slope);                                          // :75
     o = fminf(fmaxf(o, 0.f), 1.f);                                                 // :76
     ls = -fc_log_deriv(slope);                                                     // :78
     ys = o * (c.right - c.left) + c.left;                                          // :101
@@ -745,11 +800,13 @@ FC_HD void linspline_backward_elem(const LinSplineParams& c, float x, const floa
   const bool inside = linspline_domain(c, x, xs, status);
   if (!inside) {  // identity outside the tails: no parameter dependence
     gx = gy;
-    for (int j = 0; j < K; ++j) gu[j] = 0.f;
+#pragma unroll(KC ? KC : 4)
+    for (int j = 0; j < K; ++j) p[j] = 0.f;
+    linspline_store<KC>(K, gu, p);
     return;
   }
   linspline_pdf<KC>(K, u, p);
-  const float S = c.top - c.bottom, W = c.right - c.left;
+  const float S = c.top - c.bottom;
   float pos = xs;  // forward-direction input at which the adjoint is evaluated
   if (c.inverse) {
     LinSplineParams ci = c;
@@ -757,27 +814,27 @@ FC_HD void linspline_backward_elem(const LinSplineParams& c, float x, const floa
     linspline_eval<KC>(ci, x, u, out, unused, status);
     pos = out;
   }
-  const float xn = (pos - c.left) / W;
+  const float xn = (pos - c.left) * c.inv_w;
   int idx;
   float alpha, cdf_lo;
   linspline_forward_bin<KC>(K, xn, p, idx, alpha, cdf_lo);
   float pi = p[0];
 #pragma unroll(KC ? KC : 4)
   for (int j = 1; j < K; ++j) pi = j == idx ? p[j] : pi;
-  const float dydx = S * (float)K * pi / W;
+  const float dydx = S * (float)K * pi * c.inv_w;
   float gyf = gy, glf = gl;
   if (c.inverse) {
     // the reference's inverse takes the last bin's slope from the bumped end knot (1 + 1e-6 - c_{K-1}, see
     // linspline_eval): visible in d out / d v when that bin's probability is small
     const float mass = idx == K - 1 ? (1.f + 1e-6f) - cdf_lo : pi;
-    const float g = gy / (S * (float)K * mass / W);
+    const float g = fc_div(gy, S * (float)K * mass * c.inv_w);
     gx = g;
     gyf = -g;
     glf = -gl;
   } else {
     gx = gy * dydx;
   }
-  const float gi = glf / pi;
+  const float gi = fc_div(glf, pi);
   float dot = 0.f;
 #pragma unroll(KC ? KC : 4)
   for (int j = 0; j < K; ++j) {
@@ -787,8 +844,9 @@ FC_HD void linspline_backward_elem(const LinSplineParams& c, float x, const floa
 #pragma unroll(KC ? KC : 4)
   for (int j = 0; j < K; ++j) {
     const float gp = gyf * S * (j < idx ? 1.f : (j == idx ? alpha : 0.f)) + (j == idx ? gi : 0.f);
-    gu[j] = p[j] * (gp - dot);  // (gu may alias u: p[] was read before the first write)
+    p[j] = p[j] * (gp - dot);
   }
+  linspline_store<KC>(K, gu, p);  // (gu may alias u: everything was read before the first write)
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -135,6 +135,20 @@ def main():
     print(json.dumps({"kernel": "affine_bwd coupling D=64 (4M rows)", "variant": "pipelined", "ms_median": med,
                       "ms_best": best, "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                       "bytes": nbytes}), flush=True)
+    # piecewise-linear spline, coupling shapes of cfg 2 (D = 64, 32 transformed + 32 copied, K = 8): 4 (K + 2) B/element
+    xl = torch.randn(args.B, 64, generator=g, device=dev)
+    pl = torch.randn(args.B, 32 * 8, generator=g, device=dev)
+    gyl, gll = torch.randn_like(xl), torch.randn(args.B, device=dev)
+    lin = (8, _cabi.TAILS_LINEAR, False, -3.0, 3.0, -3.0, 3.0)
+    for name, fn, nbytes in (
+            ("linspline_fwd D=64 K=8 coupling", lambda: ops.linspline_layer(xl, pl, tca, cca, *lin),
+             args.B * (4 * 64 + 4 * 256 + 4 * 64 + 4)),
+            ("linspline_bwd D=64 K=8 coupling", lambda: ops.linspline_layer_backward(xl, pl, gyl, gll, tca, cca, *lin),
+             args.B * (4 * 64 * 3 + 4 * 256 * 2 + 4))):
+        med, best = timeit(fn)
+        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
+                          "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
+                          "bytes": nbytes}), flush=True)
     if args.sweep:
         a, nbytes = cases[args.sweep_case][1]
         best = None

@@ -78,6 +78,8 @@ void hm_linspline_apply(const float* x, const float* params, float* y, float* la
   LinSplineParams c;
   c.K = k; c.tails = tails; c.inverse = inverse; c.left = lo; c.right = hi; c.bottom = lo; c.top = hi;
   c.log_k = (float)log((double)k);
+  c.inv_w = 1.f / (hi - lo);
+  c.inv_h = 1.f / (hi - lo);
   for (long i = 0; i < n; ++i) {
     unsigned st = 0;
     if (unrolled && k == 8) linspline_eval<8>(c, x[i], params + i * k, y[i], lad[i], st);
@@ -92,6 +94,8 @@ void hm_linspline_backward(const float* x, const float* params, const float* gy,
   LinSplineParams c;
   c.K = k; c.tails = tails; c.inverse = inverse; c.left = lo; c.right = hi; c.bottom = lo; c.top = hi;
   c.log_k = (float)log((double)k);
+  c.inv_w = 1.f / (hi - lo);
+  c.inv_h = 1.f / (hi - lo);
   for (long i = 0; i < n; ++i) {
     if (unrolled && k == 8) linspline_backward_elem<8>(c, x[i], params + i * k, gy[i], gl[i], gx[i], gp + i * k);
     else if (unrolled && k == 10) linspline_backward_elem<10>(c, x[i], params + i * k, gy[i], gl[i], gx[i], gp + i * k);
