@@ -25,6 +25,10 @@ STRICT = False
 def check_status(status, tails):
     """Turn the device status word into the reference's exceptions."""
     if tails == _cabi.TAILS_NONE or STRICT:
+        if status.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("a spline without linear tails checks its inputs' domain on the host (the reference "
+                               "raises InputOutsideDomain, rational_quadratic.py:81-82 / linear.py:45-46): that "
+                               "synchronisation cannot be recorded into a CUDA graph — use tails='linear'")
         code = int(status.item())
         if code & _cabi.STATUS_INPUT_OUTSIDE_DOMAIN:
             raise InputOutsideDomain()
