@@ -422,6 +422,7 @@ def _gemm_err(got, want64):
     (300, 752, 32, False, False, False, False, False),    # input-gradient shape: long reduction, narrow output
     (777, 256, 132, True, True, True, False, False),      # row-major staged store: last 32-column box clipped to 4
     (130, 96, 100, False, False, True, False, False),     # two row tiles, one partial column tile, skip connection
+    (70001, 256, 256, True, False, True, False, False),   # row-major staged store, ~4 work units per CTA pair, ragged
     (1000, 256, 256, False, False, False, True, False),   # T128 in, rows out
     (1000, 64, 256, False, False, False, False, True),    # rows in, T128 out: staged kernel
     (1000, 256, 256, True, True, True, True, True),       # staged kernel with skip connection, CTA pairs, ragged
@@ -451,7 +452,8 @@ def test_linear_store_kernels(dev, M, K, N, relu_in, relu_out, res, a_t, o_t):
     assert _gemm_err(out, want) <= 2.0 * _gemm_err(ref32, want) + 2e-7
 
 
-@pytest.mark.parametrize("N,K,B,slices", [(256, 256, 8192, None), (752, 256, 20000, 7), (64, 100, 4096, 1)])
+@pytest.mark.parametrize("N,K,B,slices", [(256, 256, 8192, None), (752, 256, 20000, 7), (64, 100, 4096, 1),
+                                          (256, 256, 131072, None)])  # 148 ranges: two work units per CTA pair
 def test_linear_splitk_weight_gradient_shape(dev, N, K, B, slices):
     """fc_linear_splitk_apply: grad_W = grad_y^T @ x as a split-K product over the batch, against fp64."""
     from flowconductor_b200 import linear as fl
