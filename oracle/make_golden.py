@@ -205,6 +205,46 @@ def make_linear_functions():
     print("functions_linear.npz:", len(out), "arrays")
 
 
+def make_quadratic_functions():
+    """functions_quadratic.npz: the reference's quadratic_spline / unconstrained_quadratic_spline
+    (splines/quadratic.py), forward, inverse and autograd gradients, fp32 and fp64, per-element outputs."""
+    from flowcon.transforms.splines import quadratic as ref_q
+
+    out = {}
+    g = torch.Generator().manual_seed(78)
+    for name, k, tails, tb, inverse in [("quad_fwd_k8", 8, None, 1.0, False), ("quad_inv_k8", 8, None, 1.0, True),
+                                        ("quad_fwd_tails_k10", 10, "linear", 3.0, False),
+                                        ("quad_inv_tails_k10", 10, "linear", 3.0, True),
+                                        ("quad_fwd_k5", 5, None, 1.0, False)]:
+        n = 512
+        uw = torch.randn(n, k, generator=g) * 1.5
+        uh = torch.randn(n, k + 1 if tails is None else k - 1, generator=g) * 1.5
+        if tails is None:
+            x = torch.rand(n, generator=g)
+            x[:3] = torch.tensor([0.0, 1.0, 0.5])
+        else:
+            x = torch.randn(n, generator=g) * 2.5
+            x[:4] = torch.tensor([-tb, tb, 0.0, 5.0])
+        gy, gl = torch.randn(n, generator=g), torch.randn(n, generator=g)
+        out[name + "/meta"] = np.array([k, 0 if tails is None else 1, tb, 1 if inverse else 0], dtype=np.float64)
+        out[name + "/x"], out[name + "/uw"], out[name + "/uh"] = np32(x), np32(uw), np32(uh)
+        out[name + "/gy"], out[name + "/gl"] = np32(gy), np32(gl)
+        for dt, tag in ((torch.float32, "32"), (torch.float64, "64")):
+            conv = np32 if tag == "32" else np64
+            xx = x.to(dt).clone().requires_grad_(True)
+            ww = uw.to(dt).clone().requires_grad_(True)
+            hh = uh.to(dt).clone().requires_grad_(True)
+            if tails is None:
+                y, lad = ref_q.quadratic_spline(xx, ww, hh, inverse=inverse)
+            else:
+                y, lad = ref_q.unconstrained_quadratic_spline(xx, ww, hh, inverse=inverse, tail_bound=tb, tails=tails)
+            gx, gw, gh = torch.autograd.grad((y * gy.to(dt)).sum() + (lad * gl.to(dt)).sum(), [xx, ww, hh])
+            out[name + "/y" + tag], out[name + "/lad" + tag] = conv(y), conv(lad)
+            out[name + "/gx" + tag], out[name + "/gw" + tag], out[name + "/gh" + tag] = conv(gx), conv(gw), conv(gh)
+    np.savez_compressed(os.path.join(GOLDEN, "functions_quadratic.npz"), **out)
+    print("functions_quadratic.npz:", len(out), "arrays")
+
+
 # model-level cases
 # ------------------------------------------------------------------------------------------------
 def build_reference_flow(wl, seed=0):
@@ -315,6 +355,9 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-uncond":  # add one fixture without rewriting the others
         make_model("prq_coupling_uncond_small", with_grad=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-quadratic-functions":
+        make_quadratic_functions()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-linear":
         make_linear_functions()

@@ -174,6 +174,33 @@ def test_flow_matches_reference(name):
         _close(ladi.detach() / ls, gold["inv_lad" + tag] / ls, inv_tol * 10, name + " inverse logabsdet " + tag)
 
 
+QUADRATIC_CASES = ["quad_fwd_k8", "quad_inv_k8", "quad_fwd_tails_k10", "quad_inv_tails_k10", "quad_fwd_k5"]
+
+
+@pytest.mark.parametrize("name", QUADRATIC_CASES)
+def test_quadratic_spline_matches_reference(name):
+    """restated.quadratic_spline / unconstrained_quadratic_spline against the unmodified reference
+    (functions_quadratic.npz): outputs, log-dets and autograd gradients, fp32 and fp64."""
+    gold = load_golden("functions_quadratic")
+    k, has_tails, tb, inverse = gold[name + "/meta"].tolist()
+    for dtype, tag, tol in ((torch.float32, "32", 2e-5), (torch.float64, "64", 1e-11)):
+        x = gold[name + "/x"].to(dtype).requires_grad_(True)
+        uw = gold[name + "/uw"].to(dtype).requires_grad_(True)
+        uh = gold[name + "/uh"].to(dtype).requires_grad_(True)
+        if has_tails:
+            y, lad = restated.unconstrained_quadratic_spline(x, uw, uh, inverse=bool(inverse), tail_bound=tb)
+        else:
+            y, lad = restated.quadratic_spline(x, uw, uh, inverse=bool(inverse))
+        grads = torch.autograd.grad((y * gold[name + "/gy"].to(dtype)).sum() + (lad * gold[name + "/gl"].to(dtype)).sum(),
+                                    [x, uw, uh])
+        _close(y, gold[name + "/y" + tag], tol, name + " y " + tag)
+        _close(lad, gold[name + "/lad" + tag], tol * 10, name + " lad " + tag)
+        for got, key in zip(grads, ("gx", "gw", "gh")):
+            ref = gold[name + "/" + key + tag]
+            gs = max(1.0, ref.abs().max().item())
+            _close(got / gs, ref / gs, tol * 20, name + " " + key + " " + tag)
+
+
 LINEAR_CASES = ["lin_fwd_k8", "lin_inv_k8", "lin_fwd_tails_k10", "lin_inv_tails_k10", "lin_fwd_k5"]
 
 
