@@ -1452,4 +1452,278 @@ FC_HD void sos_invert(float z, const float* raw, int n, int iters, float lim, fl
   sos_invert_t<0>(z, raw, n, iters, lim, x, logj);
 }
 
+// ------------------------------------------------------------------------------------------------
+// piecewise-quadratic spline (flowcon/transforms/splines/quadratic.py:11-159): a piecewise-linear pdf over K bins
+// (K widths, K+1 knot heights) integrated to a piecewise-quadratic cdf.  Per-feature parameters: K raw widths, then
+// K+1 raw heights (no tails) or K-1 (linear tails: the two boundary heights are derived, :87-101).
+// ------------------------------------------------------------------------------------------------
+struct QuadSplineParams {
+  int K, tails, inverse;
+  float left, right, bottom, top, inv_w, inv_h;
+  float min_w, min_h, wh_scale;
+};
+
+#define FC_QK(KC) ((KC) ? (KC) : FC_MAX_BINS_GENERIC)
+
+// normalised bin widths w[K], un-normalised knot heights E[K+1], their area, normalised heights H[K+1]; sm[] keeps the
+// softmax for the backward; for linear tails cst = boundary constant and den its denominator
+template <int KC>
+struct QuadKnots {
+  float sm[FC_QK(KC)], w[FC_QK(KC)], E[FC_QK(KC) + 1], H[FC_QK(KC) + 1];
+  float area, cst, den;
+};
+
+template <int KC>
+FC_HD void quad_prepare(const QuadSplineParams& c, const float* u, QuadKnots<KC>& q) {
+  const int K = KC ? KC : c.K;
+  const float s = c.wh_scale;  // coupling.py:409-411: raw widths and heights divided by sqrt(hidden)
+  float m = -INFINITY;
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) m = fmaxf(m, u[j]);
+  const float sl2 = s * FC_LOG2E, ml2 = m * sl2;
+  float se = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) {
+    q.sm[j] = fc_exp2(fmaf(u[j], sl2, -ml2));
+    se += q.sm[j];
+  }
+  const float inv = fc_rcp(se), coef = 1.f - c.min_w * (float)K;
+#pragma unroll(KC ? KC : 4)
+  for (int j = 0; j < K; ++j) {
+    q.sm[j] *= inv;
+    q.w[j] = fmaf(coef, q.sm[j], c.min_w);  // quadratic.py:81-82
+  }
+  const float* uh = u + K;
+  if (c.tails == FC_TAILS_LINEAR) {  // K-1 raw heights -> E[1..K-1]; E[0] = E[K] = constant (:87-101)
+#pragma unroll(KC ? KC : 4)
+    for (int j = 0; j < K - 1; ++j) q.E[j + 1] = fc_softplus1(uh[j] * s) + 1e-3f;  // :84
+    float num = 0.25f * q.w[0] * q.E[1] + 0.25f * q.w[K - 1] * q.E[K - 1];
+#pragma unroll(KC ? KC : 4)
+    for (int i = 0; i + 2 < K; ++i) num = fmaf(0.5f * (q.E[i + 1] + q.E[i + 2]), q.w[i + 1], num);
+    q.den = 1.f - 0.25f * q.w[0] - 0.25f * q.w[K - 1];
+    q.cst = fc_div(num, q.den);
+    q.E[0] = q.cst;
+    q.E[K] = q.cst;
+  } else {
+#pragma unroll(KC ? KC + 1 : 4)
+    for (int j = 0; j <= K; ++j) q.E[j] = fc_softplus1(uh[j] * s) + 1e-3f;
+    q.cst = 0.f;
+    q.den = 1.f;
+  }
+  float area = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int i = 0; i < K; ++i) area = fmaf(0.5f * (q.E[i] + q.E[i + 1]), q.w[i], area);  // :103-106
+  q.area = area;
+  const float ia = fc_rcp(area) * (1.f - c.min_h);
+#pragma unroll(KC ? KC + 1 : 4)
+  for (int j = 0; j <= K; ++j) q.H[j] = fmaf(q.E[j], ia, c.min_h);  // :107-108
+}
+
+// the bin of a normalised position: by location (forward) or by left-cdf (inverse); both knot vectors have their last
+// knot forced to 1 and bumped by 1e-6 for the comparison (:110-123, torchutils.py:147-149).  Returns the bin's left
+// location, width, left cdf and the two knot heights.
+template <int KC>
+FC_HD void quad_locate(int K, const QuadKnots<KC>& q, float pos, bool by_cdf, int& idx, float& loc, float& bw,
+                       float& lcdf, float& hl, float& hr) {
+  idx = 0;
+  float rl = 0.f, rc = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int m = 1; m <= K; ++m) {
+    rl += q.w[m - 1];
+    rc = fmaf(0.5f * (q.H[m - 1] + q.H[m]), q.w[m - 1], rc);
+    const float knot = m == K ? 1.f + 1e-6f : (by_cdf ? rc : rl);
+    idx += pos >= knot ? 1 : 0;
+  }
+  idx = idx > K - 1 ? K - 1 : idx;
+  loc = 0.f;
+  lcdf = 0.f;
+  bw = q.w[0];
+  hl = q.H[0];
+  hr = q.H[1];
+  rl = 0.f;
+  rc = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int m = 0; m < K; ++m) {
+    if (m == idx) {
+      loc = rl;
+      lcdf = rc;
+      bw = q.w[m];
+      hl = q.H[m];
+      hr = q.H[m + 1];
+    }
+    rl += q.w[m];
+    rc = fmaf(0.5f * (q.H[m] + q.H[m + 1]), q.w[m], rc);
+  }
+}
+
+FC_HD bool quad_domain(const QuadSplineParams& c, float x, float& xs, unsigned& status) {
+  const float lo = c.inverse ? c.bottom : c.left;
+  const float hi = c.inverse ? c.top : c.right;
+  if (c.tails == FC_TAILS_LINEAR) {
+    const bool inside = (x >= lo) && (x <= hi);  // quadratic.py:22
+    xs = inside ? x : lo;
+    return inside;
+  }
+  xs = x;
+  if (!(x >= lo && x <= hi)) {  // :67-68 raises InputOutsideDomain
+    status |= FC_STATUS_INPUT_OUTSIDE_DOMAIN;
+    xs = fminf(fmaxf(x, lo), hi);
+    if (!(xs == xs)) xs = lo;
+  }
+  return true;
+}
+
+template <int KC>
+FC_HD void quadspline_eval(const QuadSplineParams& c, float x, const float* u, float& y, float& lad, unsigned& status) {
+  const int K = KC ? KC : c.K;
+  float xs;
+  const bool inside = quad_domain(c, x, xs, status);
+  QuadKnots<KC> q;
+  quad_prepare<KC>(c, u, q);
+  int idx;
+  float loc, bw, lcdf, hl, hr, ys, ls;
+  if (!c.inverse) {
+    const float xn = (xs - c.left) * c.inv_w;
+    quad_locate<KC>(K, q, xn, false, idx, loc, bw, lcdf, hl, hr);
+    const float alpha = fc_div(xn - loc, bw);                                  // :144
+    const float a = 0.5f * (hr - hl) * bw, b = hl * bw;                        // :130-132
+    float o = fmaf(fmaf(a, alpha, b), alpha, lcdf);                            // :145
+    o = fminf(fmaxf(o, 0.f), 1.f);
+    ls = fc_log_deriv(fmaf(alpha, hr - hl, hl));                               // :147-149
+    ys = o * (c.top - c.bottom) + c.bottom;
+  } else {
+    const float yn = (xs - c.bottom) * c.inv_h;
+    quad_locate<KC>(K, q, yn, true, idx, loc, bw, lcdf, hl, hr);
+    const float a = 0.5f * (hr - hl) * bw, b = hl * bw, r = yn - lcdf;
+    // root of a alpha^2 + b alpha - r = 0 (:134-136) in the cancellation-free form 2 r / (b + sqrt(b^2 + 4 a r)):
+    // identical to (-b + sqrt(b^2 - 4 a c_)) / (2 a), and finite when the two knot heights coincide (a = 0)
+    const float disc = fmaxf(fmaf(4.f * a, r, b * b), 0.f);
+    const float alpha = fc_div(2.f * r, b + fc_sqrt(disc));
+    float o = fmaf(alpha, bw, loc);                                            // :137
+    o = fminf(fmaxf(o, 0.f), 1.f);
+    ls = -fc_log_deriv(fmaf(alpha, hr - hl, hl));                              // :139-141
+    ys = o * (c.right - c.left) + c.left;
+  }
+  y = inside ? ys : x;
+  lad = inside ? ls : 0.f;
+}
+
+// Backward of quadspline_eval for one element: closed-form reverse pass through bin quantities -> normalised heights ->
+// area normalisation (-> boundary constant with linear tails) -> softplus / softmax.  The inverse direction by implicit
+// differentiation through the forward adjoint at out = f^-1(v) (as rqs_backward_elem).  gu may alias u.
+template <int KC>
+FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const float* u, float gy, float gl, float& gx,
+                                    float* gu) {
+  const int K = KC ? KC : c.K;
+  const int NH = c.tails == FC_TAILS_LINEAR ? K - 1 : K + 1;
+  float xs;
+  unsigned status = 0;
+  const bool inside = quad_domain(c, x, xs, status);
+  if (!inside) {
+    gx = gy;
+    for (int j = 0; j < K + NH; ++j) gu[j] = 0.f;
+    return;
+  }
+  QuadKnots<KC> q;
+  quad_prepare<KC>(c, u, q);
+  float pos = xs;
+  if (c.inverse) {
+    float out, unused;
+    quadspline_eval<KC>(c, x, u, out, unused, status);
+    pos = out;
+  }
+  const float S = c.top - c.bottom;
+  const float xn = (pos - c.left) * c.inv_w;
+  int idx;
+  float loc, bw, lcdf, hl, hr;
+  quad_locate<KC>(K, q, xn, false, idx, loc, bw, lcdf, hl, hr);
+  const float alpha = fc_div(xn - loc, bw);
+  const float d = hr - hl, Dv = fmaf(alpha, d, hl), inv_bw = fc_rcp(bw), inv_D = fc_rcp(Dv);
+  float gyS, glf;
+  if (c.inverse) {
+    // dL/dv = (g_out - gl * d ladf/d out) / f'(out),  f' = S D inv_w,  d ladf / d out = d / (D bw) inv_w
+    const float g = fc_div(gy - gl * d * inv_D * inv_bw * c.inv_w, S * Dv * c.inv_w);
+    gx = g;
+    gyS = -g * S;
+    glf = -gl;
+  } else {
+    gx = (gy * S * Dv + gl * d * inv_D * inv_bw) * c.inv_w;
+    gyS = gy * S;
+    glf = gl;
+  }
+  const float g_alpha = gyS * bw * Dv + glf * d * inv_D;
+  const float g_bw = gyS * (0.5f * d * alpha * alpha + hl * alpha) - g_alpha * alpha * inv_bw;
+  const float g_hr = gyS * 0.5f * bw * alpha * alpha + glf * alpha * inv_D;
+  const float g_hl = gyS * (bw * alpha - 0.5f * bw * alpha * alpha) + glf * (1.f - alpha) * inv_D;
+  const float g_loc = -g_alpha * inv_bw;
+  float gw[FC_QK(KC)], gH[FC_QK(KC) + 1];
+#pragma unroll(KC ? KC + 1 : 4)
+  for (int j = 0; j <= K; ++j) gH[j] = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int i = 0; i < K; ++i) {
+    const bool below = i < idx;
+    gw[i] = below ? g_loc + gyS * 0.5f * (q.H[i] + q.H[i + 1]) : (i == idx ? g_bw : 0.f);
+    const float t = below ? gyS * 0.5f * q.w[i] : 0.f;
+    gH[i] += t + (i == idx ? g_hl : 0.f);
+    gH[i + 1] += t + (i == idx ? g_hr : 0.f);
+  }
+  // H = min_h + (1 - min_h) E / area
+  const float ia = fc_rcp(q.area), k1 = (1.f - c.min_h) * ia;
+  float dotE = 0.f;
+#pragma unroll(KC ? KC + 1 : 4)
+  for (int j = 0; j <= K; ++j) dotE = fmaf(gH[j], q.E[j], dotE);
+  const float g_area = -k1 * ia * dotE;
+  float gE[FC_QK(KC) + 1];
+#pragma unroll(KC ? KC + 1 : 4)
+  for (int j = 0; j <= K; ++j) {
+    const float wl = j > 0 ? q.w[j - 1] : 0.f, wr = j < K ? q.w[j] : 0.f;
+    gE[j] = fmaf(k1, gH[j], g_area * 0.5f * (wl + wr));
+  }
+#pragma unroll(KC ? KC : 4)
+  for (int i = 0; i < K; ++i) gw[i] = fmaf(g_area * 0.5f, q.E[i] + q.E[i + 1], gw[i]);
+  const float s = c.wh_scale;
+  const float* uh = u + K;
+  float gh[FC_QK(KC) + 1];  // raw-height gradients (NH of them)
+  if (c.tails == FC_TAILS_LINEAR) {
+    const float gC = gE[0] + gE[K];
+    const float g_num = fc_div(gC, q.den), g_den = -g_num * q.cst;
+    // e_j = E[j+1], j = 0..K-2
+#pragma unroll(KC ? KC : 4)
+    for (int j = 0; j < K - 1; ++j) {
+      float dn = 0.f;
+      if (j >= 1) dn += 0.5f * q.w[j];
+      if (j + 3 <= K) dn += 0.5f * q.w[j + 1];
+      if (j == 0) dn += 0.25f * q.w[0];
+      if (j == K - 2) dn += 0.25f * q.w[K - 1];
+      float sg, unused;
+      fc_sigmoid_parts(uh[j] * s, sg, unused);
+      gh[j] = (gE[j + 1] + g_num * dn) * sg * s;
+    }
+#pragma unroll(KC ? KC : 4)
+    for (int mI = 0; mI < K; ++mI) {
+      float dn;
+      if (mI == 0) dn = 0.25f * q.E[1];
+      else if (mI == K - 1) dn = 0.25f * q.E[K - 1];
+      else dn = 0.5f * (q.E[mI] + q.E[mI + 1]);
+      const float dd = (mI == 0 || mI == K - 1) ? -0.25f : 0.f;
+      gw[mI] += g_num * dn + g_den * dd;
+    }
+  } else {
+#pragma unroll(KC ? KC + 1 : 4)
+    for (int j = 0; j <= K; ++j) {
+      float sg, unused;
+      fc_sigmoid_parts(uh[j] * s, sg, unused);
+      gh[j] = gE[j] * sg * s;
+    }
+  }
+  // w = min_w + (1 - min_w K) softmax(s uw)
+  const float coef = 1.f - c.min_w * (float)K;
+  float dot = 0.f;
+#pragma unroll(KC ? KC : 4)
+  for (int i = 0; i < K; ++i) dot = fmaf(q.sm[i], gw[i] * coef, dot);
+#pragma unroll(KC ? KC : 4)
+  for (int i = 0; i < K; ++i) gu[i] = s * q.sm[i] * (gw[i] * coef - dot);
+  for (int j = 0; j < NH; ++j) gu[K + j] = gh[j];
+}
+
 }  // namespace fc

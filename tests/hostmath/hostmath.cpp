@@ -103,6 +103,38 @@ void hm_linspline_backward(const float* x, const float* params, const float* gy,
   }
 }
 
+// piecewise-quadratic spline: one element per call, params [uw(K) ; uh(K+1 or K-1)]
+static QuadSplineParams hm_quad_params(int k, int tails, float lo, float hi, int inverse) {
+  QuadSplineParams c;
+  c.K = k; c.tails = tails; c.inverse = inverse; c.left = lo; c.right = hi; c.bottom = lo; c.top = hi;
+  c.inv_w = 1.f / (hi - lo); c.inv_h = 1.f / (hi - lo); c.min_w = 1e-3f; c.min_h = 1e-3f; c.wh_scale = 1.f;
+  return c;
+}
+
+void hm_quadspline_apply(const float* x, const float* params, float* y, float* lad, unsigned* status, long n, int k,
+                         int tails, float lo, float hi, int inverse, int unrolled) {
+  const QuadSplineParams c = hm_quad_params(k, tails, lo, hi, inverse);
+  const int P = tails ? 2 * k - 1 : 2 * k + 1;
+  for (long i = 0; i < n; ++i) {
+    unsigned st = 0;
+    if (unrolled && k == 8) quadspline_eval<8>(c, x[i], params + i * P, y[i], lad[i], st);
+    else if (unrolled && k == 10) quadspline_eval<10>(c, x[i], params + i * P, y[i], lad[i], st);
+    else quadspline_eval<0>(c, x[i], params + i * P, y[i], lad[i], st);
+    status[0] |= st;
+  }
+}
+
+void hm_quadspline_backward(const float* x, const float* params, const float* gy, const float* gl, float* gx, float* gp,
+                            long n, int k, int tails, float lo, float hi, int inverse, int unrolled) {
+  const QuadSplineParams c = hm_quad_params(k, tails, lo, hi, inverse);
+  const int P = tails ? 2 * k - 1 : 2 * k + 1;
+  for (long i = 0; i < n; ++i) {
+    if (unrolled && k == 8) quadspline_backward_elem<8>(c, x[i], params + i * P, gy[i], gl[i], gx[i], gp + i * P);
+    else if (unrolled && k == 10) quadspline_backward_elem<10>(c, x[i], params + i * P, gy[i], gl[i], gx[i], gp + i * P);
+    else quadspline_backward_elem<0>(c, x[i], params + i * P, gy[i], gl[i], gx[i], gp + i * P);
+  }
+}
+
 // compile-time n = 10 instantiations (what the kernels run for the default sigmoid count)
 void hm_sos_apply_n10(const float* x, const float* params, float* y, float* logj, long n) {
   for (long i = 0; i < n; ++i) sos_eval_t<10>(x[i], params + i * 31, 10, y[i], logj[i]);

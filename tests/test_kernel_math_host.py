@@ -242,3 +242,32 @@ def test_linear_spline(hm, name, unrolled):
     assert_parity(gx, gold[name + "/gx32"], gold[name + "/gx64"], 1e-4, s, name + " gx")
     s = max(1e-2, gold[name + "/gp64"].abs().mean().item())
     assert_parity(gp, gold[name + "/gp32"], gold[name + "/gp64"], 1e-4, s, name + " gp")
+
+
+@pytest.mark.parametrize("name", ["quad_fwd_k8", "quad_inv_k8", "quad_fwd_tails_k10", "quad_inv_tails_k10", "quad_fwd_k5"])
+@pytest.mark.parametrize("unrolled", [0, 1])
+def test_quadratic_spline(hm, name, unrolled):
+    """quadspline_eval / quadspline_backward_elem (fc_math.cuh) against the reference's quadratic_spline golden vectors."""
+    gold = load_golden("functions_quadratic")
+    k, has_tails, tb, inverse = gold[name + "/meta"].tolist()
+    k, has_tails, inverse = int(k), int(has_tails), int(inverse)
+    lo, hi = (-tb, tb) if has_tails else (0.0, 1.0)
+    x = gold[name + "/x"].contiguous()
+    p = torch.cat([gold[name + "/uw"], gold[name + "/uh"]], dim=-1).contiguous()
+    y, lad = torch.empty_like(x), torch.empty_like(x)
+    status = torch.zeros(1, dtype=torch.int32)
+    hm.hm_quadspline_apply(fptr(x), fptr(p), fptr(y), fptr(lad), fptr(status), ctypes.c_long(x.numel()), k, has_tails,
+                           ctypes.c_float(lo), ctypes.c_float(hi), inverse, unrolled)
+    assert int(status.item()) == 0
+    assert_parity(y, gold[name + "/y32"], gold[name + "/y64"], 1e-5, 1.0, name + " y")
+    assert_parity(lad, gold[name + "/lad32"], gold[name + "/lad64"], 1e-5, 1.0, name + " lad")
+    gy, gl = gold[name + "/gy"].contiguous(), gold[name + "/gl"].contiguous()
+    gx, gp = torch.empty_like(x), torch.empty_like(p)
+    hm.hm_quadspline_backward(fptr(x), fptr(p), fptr(gy), fptr(gl), fptr(gx), fptr(gp), ctypes.c_long(x.numel()), k,
+                              has_tails, ctypes.c_float(lo), ctypes.c_float(hi), inverse, unrolled)
+    s = max(1e-2, gold[name + "/gx64"].abs().mean().item())
+    assert_parity(gx, gold[name + "/gx32"], gold[name + "/gx64"], 1e-4, s, name + " gx")
+    g32 = torch.cat([gold[name + "/gw32"], gold[name + "/gh32"]], dim=-1)
+    g64 = torch.cat([gold[name + "/gw64"], gold[name + "/gh64"]], dim=-1)
+    s = max(1e-2, g64.abs().mean().item())
+    assert_parity(gp, g32, g64, 1e-4, s, name + " gp")
