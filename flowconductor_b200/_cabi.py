@@ -21,7 +21,8 @@ AFFINE_BLOCKED, AFFINE_INTERLEAVED = 0, 1
 SCALE_SIGMOID2, SCALE_SOFTPLUS_CLAMP3, SCALE_SOFTPLUS_EPS = 0, 1, 2
 LINEAR_A_T128, LINEAR_OUT_T128, LINEAR_RESIDUAL_GATES = 1, 2, 4
 
-EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_linspline_apply", "fc_linspline_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
+EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_linspline_apply", "fc_linspline_backward",
+           "fc_quadspline_apply", "fc_quadspline_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
@@ -34,6 +35,13 @@ class RqsConfig(ctypes.Structure):
                 ("inverse", ctypes.c_int32), ("left", ctypes.c_float), ("right", ctypes.c_float),
                 ("bottom", ctypes.c_float), ("top", ctypes.c_float), ("min_bin_width", ctypes.c_float),
                 ("min_bin_height", ctypes.c_float), ("min_derivative", ctypes.c_float), ("wh_scale", ctypes.c_float)]
+
+
+class QuadSplineConfig(ctypes.Structure):
+    """struct fc_quadspline_config"""
+    _fields_ = [("num_bins", ctypes.c_int32), ("tails", ctypes.c_int32), ("inverse", ctypes.c_int32),
+                ("left", ctypes.c_float), ("right", ctypes.c_float), ("bottom", ctypes.c_float), ("top", ctypes.c_float),
+                ("min_bin_width", ctypes.c_float), ("min_bin_height", ctypes.c_float), ("wh_scale", ctypes.c_float)]
 
 
 class Cols(ctypes.Structure):
@@ -72,6 +80,10 @@ def lib():
                                          f32, f32, i32, vp, vp]
         L.fc_linspline_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols, i32,
                                             i32, f32, f32, f32, f32, i32, vp]
+        L.fc_quadspline_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, Cols, Cols,
+                                          ctypes.POINTER(QuadSplineConfig), vp, vp]
+        L.fc_quadspline_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols,
+                                             ctypes.POINTER(QuadSplineConfig), vp]
         L.fc_affine_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, Cols, Cols, i32, i32, i32, vp]
         L.fc_affine_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols, i32,
                                          i32, i32, vp]

@@ -2,6 +2,7 @@
 from .adaptive_sigmoids import SumOfSigmoids  # noqa: F401
 from .autoregressive import (AutoregressiveTransform, MaskedAffineAutoregressiveTransform,  # noqa: F401
                              MaskedPiecewiseLinearAutoregressiveTransform,
+                             MaskedPiecewiseQuadraticAutoregressiveTransform,
                              MaskedPiecewiseRationalQuadraticAutoregressiveTransform,
                              MaskedSumOfSigmoidsTransform)
 from .base import (CompositeTransform, InputOutsideDomain, InverseNotAvailable, InverseTransform,  # noqa: F401
@@ -9,10 +10,13 @@ from .base import (CompositeTransform, InputOutsideDomain, InverseNotAvailable, 
 from .conditional import (ConditionalPiecewiseRationalQuadraticTransform,  # noqa: F401
                           ConditionalSumOfSigmoidsTransform, ConditionalTransform)
 from .coupling import (AdditiveCouplingTransform, AffineCouplingTransform, CouplingTransform,  # noqa: F401
-                       PiecewiseLinearCouplingTransform, PiecewiseRationalQuadraticCouplingTransform)
+                       PiecewiseLinearCouplingTransform, PiecewiseQuadraticCouplingTransform,
+                       PiecewiseRationalQuadraticCouplingTransform)
 from .made import MADE, MaskedLinear  # noqa: F401
-from .nonlinearities import PiecewiseLinearCDF, PiecewiseRationalQuadraticCDF  # noqa: F401
+from .nonlinearities import (PiecewiseLinearCDF, PiecewiseQuadraticCDF,  # noqa: F401
+                            PiecewiseRationalQuadraticCDF)
 from .permutations import Permutation, RandomPermutation, ReversePermutation  # noqa: F401
 from . import splines  # noqa: F401
-from .splines import (linear_spline, rational_quadratic_spline, unconstrained_linear_spline,  # noqa: F401
+from .splines import (linear_spline, quadratic_spline, rational_quadratic_spline,  # noqa: F401
+                      unconstrained_linear_spline, unconstrained_quadratic_spline,
                       unconstrained_rational_quadratic_spline)

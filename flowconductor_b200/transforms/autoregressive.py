@@ -178,3 +178,34 @@ class MaskedPiecewiseLinearAutoregressiveTransform(AutoregressiveTransform):
 
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._spline.apply(inputs, autoregressive_params, None, None, True)
+
+
+class MaskedPiecewiseQuadraticAutoregressiveTransform(AutoregressiveTransform):
+    """autoregressive.py:375-457.  `transforms.made.MADE` has no `hidden_features`, so no pre-scale is applied (:426);
+    the min_derivative argument is accepted and unused, as in the reference."""
+
+    def __init__(self, features, hidden_features, context_features=None, num_bins=10, num_blocks=2, tails=None,
+                 tail_bound=1.0, use_residual_blocks=True, random_mask=False, activation=F.relu,
+                 dropout_probability=0.0, use_batch_norm=False, min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT, min_derivative=splines.DEFAULT_MIN_DERIVATIVE):
+        self.num_bins = num_bins
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.min_derivative = min_derivative
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self.features = features
+        if tails not in (None, "linear"):
+            raise ValueError(tails)
+        self._spline = splines.QuadraticSplineSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height)
+        super().__init__(_made(self, features, hidden_features, context_features, num_blocks, use_residual_blocks,
+                               random_mask, activation, dropout_probability, use_batch_norm))
+
+    def _output_dim_multiplier(self):
+        return self.num_bins * 2 - 1 if self.tails == "linear" else self.num_bins * 2 + 1
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return self._spline.apply(inputs, autoregressive_params, None, None, False, None)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return self._spline.apply(inputs, autoregressive_params, None, None, True, None)

@@ -15,7 +15,7 @@ from .. import _cabi, ops
 from ..nn import tensorcore
 from . import splines
 from .base import Transform
-from .nonlinearities import PiecewiseLinearCDF, PiecewiseRationalQuadraticCDF
+from .nonlinearities import PiecewiseLinearCDF, PiecewiseQuadraticCDF, PiecewiseRationalQuadraticCDF
 
 
 class CouplingTransform(Transform):
@@ -227,3 +227,33 @@ class PiecewiseLinearCouplingTransform(CouplingTransform):
 
     def _coupling_layer(self, inputs, transform_params, inverse):
         return self._spline.apply(inputs, transform_params, self._tcols, self._ccols, inverse)
+
+
+class PiecewiseQuadraticCouplingTransform(CouplingTransform):
+    """coupling.py:355-427 (Mueller et al. 2018): per transformed feature K raw widths and K+1 raw knot heights (K-1 with
+    linear tails), both divided by sqrt(hidden) when the conditioner exposes `hidden_features` (:409-411)."""
+
+    def __init__(self, mask, transform_net_create_fn, num_bins=10, tails=None, tail_bound=1.0,
+                 apply_unconditional_transform=False, img_shape=None, min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT):
+        if apply_unconditional_transform and img_shape:
+            raise NotImplementedError("image-shaped inputs are outside the B200 hot path")
+        self.num_bins = num_bins
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self._spline = splines.QuadraticSplineSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height)
+        unconditional = None
+        if apply_unconditional_transform:  # coupling.py:379-389
+            unconditional = lambda features: PiecewiseQuadraticCDF(  # noqa: E731
+                shape=[features], num_bins=num_bins, tails=tails, tail_bound=tail_bound, min_bin_width=min_bin_width,
+                min_bin_height=min_bin_height)
+        super().__init__(mask, transform_net_create_fn, unconditional_transform=unconditional)
+
+    def _transform_dim_multiplier(self):
+        return self._spline.params_per_feature()
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        hidden = getattr(self.transform_net, "hidden_features", None)
+        return self._spline.apply(inputs, transform_params, self._tcols, self._ccols, inverse, hidden)

@@ -159,3 +159,71 @@ def unconstrained_linear_spline(inputs, unnormalized_pdf, inverse=False, tail_bo
         raise RuntimeError("{} tails are not implemented.".format(tails))
     return _linear_elementwise(inputs, unnormalized_pdf, inverse, _cabi.TAILS_LINEAR, -tail_bound, tail_bound,
                                -tail_bound, tail_bound)
+
+
+# ------------------------------------------------------------------------------------------------
+# piecewise-quadratic spline (flowcon/transforms/splines/quadratic.py)
+# ------------------------------------------------------------------------------------------------
+class QuadraticSplineSettings:
+    """Hyper-parameters of a piecewise-quadratic spline layer and the kernel call that applies them to a
+    [B, D_t * P] parameter tensor, P = 2K+1 (no tails) / 2K-1 (linear tails): per feature [K raw widths ; raw heights]
+    (PiecewiseQuadraticCouplingTransform._piecewise_cdf, coupling.py:403-427)."""
+
+    def __init__(self, num_bins, tails, tail_bound, min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=DEFAULT_MIN_BIN_HEIGHT):
+        if tails not in (None, "linear"):
+            raise RuntimeError("{} tails are not implemented.".format(tails))  # quadratic.py:36
+        self.num_bins = num_bins
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+
+    def params_per_feature(self):
+        return self.num_bins * 2 - 1 if self.tails == "linear" else self.num_bins * 2 + 1
+
+    def apply(self, inputs, params, tcols, ccols, inverse, hidden_for_scaling):
+        if self.tails == "linear":
+            tails, lo, hi = _cabi.TAILS_LINEAR, -float(self.tail_bound), float(self.tail_bound)
+        else:
+            tails, lo, hi = _cabi.TAILS_NONE, 0.0, 1.0
+        wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
+        y, lad, status = ops.quadspline_layer(inputs, params, tcols, ccols, int(self.num_bins), tails, bool(inverse),
+                                              lo, hi, lo, hi, float(self.min_bin_width), float(self.min_bin_height),
+                                              float(wh_scale))
+        check_status(status, tails)
+        return y, lad
+
+
+def _quadratic_elementwise(inputs, unnormalized_widths, unnormalized_heights, inverse, tails, left, right, bottom, top,
+                           min_bin_width, min_bin_height):
+    shape = inputs.shape
+    num_bins = unnormalized_widths.shape[-1]
+    params = torch.cat((unnormalized_widths, unnormalized_heights), dim=-1)
+    params = params.reshape(-1, params.shape[-1])
+    y, lad, status = ops.quadspline_layer(inputs.reshape(-1, 1), params, None, None, num_bins, tails, bool(inverse),
+                                          float(left), float(right), float(bottom), float(top), float(min_bin_width),
+                                          float(min_bin_height), 1.0)
+    check_status(status, tails)
+    return y.reshape(shape), lad.reshape(shape)
+
+
+def quadratic_spline(inputs, unnormalized_widths, unnormalized_heights, inverse=False, left=0.0, right=1.0, bottom=0.0,
+                     top=1.0, min_bin_width=DEFAULT_MIN_BIN_WIDTH, min_bin_height=DEFAULT_MIN_BIN_HEIGHT):
+    """flowcon/transforms/splines/quadratic.py:55-159 (per-element outputs and log-dets)."""
+    if unnormalized_heights.shape[-1] != unnormalized_widths.shape[-1] + 1:
+        raise ValueError("quadratic_spline expects num_bins + 1 raw heights (use unconstrained_quadratic_spline for the "
+                         "num_bins - 1 form)")
+    return _quadratic_elementwise(inputs, unnormalized_widths, unnormalized_heights, inverse, _cabi.TAILS_NONE, left,
+                                  right, bottom, top, min_bin_width, min_bin_height)
+
+
+def unconstrained_quadratic_spline(inputs, unnormalized_widths, unnormalized_heights, inverse=False, tail_bound=1.0,
+                                   tails="linear", min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+                                   min_bin_height=DEFAULT_MIN_BIN_HEIGHT):
+    """quadratic.py:11-52: identity outside [-tail_bound, tail_bound]; num_bins - 1 raw heights."""
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    assert unnormalized_heights.shape[-1] == unnormalized_widths.shape[-1] - 1  # quadratic.py:34
+    return _quadratic_elementwise(inputs, unnormalized_widths, unnormalized_heights, inverse, _cabi.TAILS_LINEAR,
+                                  -tail_bound, tail_bound, -tail_bound, tail_bound, min_bin_width, min_bin_height)

@@ -86,6 +86,16 @@ WORKLOADS = {
                                         "tails": "linear", "tail_bound": 3.0, "hidden_features": 16, "num_blocks": 2}]},
     "maf_plin_small": {"features": 5, "context_features": None, "batch": 64,
                        "layers": [{"kind": "maf_plin", "num_bins": 10, "hidden_features": 16, "num_blocks": 2}]},
+    # the piecewise-quadratic family (coupling.py:355-427, autoregressive.py:375-457, nonlinearities.py:286-340)
+    "pquad_coupling_small": {"features": 6, "context_features": None, "batch": 64,
+                             "layers": [{"kind": "pquad_coupling", "mask": "alternating_even", "num_bins": 8,
+                                         "tails": "linear", "tail_bound": 3.0, "hidden_features": 16, "num_blocks": 2,
+                                         "unconditional": True},
+                                        {"kind": "pquad_coupling", "mask": "alternating_odd", "num_bins": 8,
+                                         "tails": "linear", "tail_bound": 3.0, "hidden_features": 16, "num_blocks": 2}]},
+    "maf_pquad_small": {"features": 5, "context_features": None, "batch": 64,
+                        "layers": [{"kind": "maf_pquad", "num_bins": 10, "tails": "linear", "tail_bound": 3.0,
+                                    "hidden_features": 16, "num_blocks": 2}]},
     "prq_coupling_notails_small": {"features": 6, "context_features": None, "batch": 64,
                                    "layers": [{"kind": "prq_coupling", "mask": "mid_split", "num_bins": 5,
                                                "tails": None, "tail_bound": 1.0, "hidden_features": 16,
@@ -111,6 +121,8 @@ def params_per_feature(layer):
         return 3 * layer["n_sigmoids"] + 1
     if kind in ("plin_coupling", "maf_plin"):
         return layer["num_bins"]
+    if kind in ("pquad_coupling", "maf_pquad"):
+        return 2 * layer["num_bins"] - 1 if layer.get("tails") == "linear" else 2 * layer["num_bins"] + 1
     raise ValueError(kind)
 
 
@@ -155,13 +167,16 @@ def trained_like_(state, workload, seed=1, weight_gain=8.0):
             continue
         net = {"prq_coupling": "transform_net", "affine_coupling": "transform_net", "maf_affine": "autoregressive_net",
                "maf_prq": "autoregressive_net", "maf_sos": "autoregressive_net", "cond_sos": "conditional_net",
-               "cond_prq": "conditional_net", "plin_coupling": "transform_net", "maf_plin": "autoregressive_net"}[kind]
+               "cond_prq": "conditional_net", "plin_coupling": "transform_net", "maf_plin": "autoregressive_net",
+               "pquad_coupling": "transform_net", "maf_pquad": "autoregressive_net"}[kind]
         wkey = layer_prefix(i) + net + ".final_layer.weight"
         bkey = layer_prefix(i) + net + ".final_layer.bias"
         p = params_per_feature(layer)
         n_out = state[bkey].numel()
         noise = torch.randn(n_out, generator=g, dtype=torch.float32)
         std = torch.ones(n_out)
+        if kind == "pquad_coupling":
+            std = std * 4.0  # every slot is divided by sqrt(H)
         if kind in ("prq_coupling", "cond_prq"):
             std = std.view(-1, p)
             std[:, : 2 * layer["num_bins"]] = 16.0
@@ -202,6 +217,19 @@ def build_flow(workload, seed=0):
                     i, o, hidden_features=h, num_blocks=b),
                 num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
                 apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "pquad_coupling":
+            hidden, blocks = layer["hidden_features"], layer["num_blocks"]
+            layers.append(transforms.PiecewiseQuadraticCouplingTransform(
+                mask=make_mask(features, layer["mask"]),
+                transform_net_create_fn=lambda i, o, h=hidden, b=blocks: nets.ResidualNet(
+                    i, o, hidden_features=h, num_blocks=b),
+                num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
+                apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "maf_pquad":
+            layers.append(transforms.MaskedPiecewiseQuadraticAutoregressiveTransform(
+                features=features, hidden_features=layer["hidden_features"], context_features=ctx,
+                num_bins=layer["num_bins"], num_blocks=layer["num_blocks"], tails=layer["tails"],
+                tail_bound=layer["tail_bound"]))
         elif kind == "maf_plin":
             layers.append(transforms.MaskedPiecewiseLinearAutoregressiveTransform(
                 num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],

@@ -106,6 +106,33 @@ int fc_linspline_backward(const float* x, int64_t x_row_stride, const float* par
                           fc_cols tcols, fc_cols ccols, int32_t num_bins, int32_t tails, float left, float right,
                           float bottom, float top, int32_t inverse, void* stream);
 
+/*
+ * Piecewise-quadratic spline layer: replaces quadratic_spline / unconstrained_quadratic_spline
+ * (flowcon/transforms/splines/quadratic.py:11-159) as called by PiecewiseQuadraticCouplingTransform._piecewise_cdf
+ * (coupling.py:403-427), MaskedPiecewiseQuadraticAutoregressiveTransform._elementwise (autoregressive.py) and
+ * PiecewiseQuadraticCDF._spline (nonlinearities.py:309-334).  params[r] = per transformed feature
+ * [num_bins raw widths ; raw knot heights], num_bins + 1 heights without tails (P = 2K+1), num_bins - 1 with linear tails
+ * (P = 2K-1, the two boundary heights are derived, quadratic.py:87-101).  Raw widths AND heights are multiplied by
+ * wh_scale (1/sqrt(hidden) when the conditioner exposes hidden_features, coupling.py:409-411; else 1).
+ */
+typedef struct fc_quadspline_config {
+  int32_t num_bins;
+  int32_t tails;   /* FC_TAILS_* */
+  int32_t inverse; /* 0 forward, 1 inverse */
+  float left, right, bottom, top;
+  float min_bin_width, min_bin_height; /* quadratic.py:7-8 defaults 1e-3 */
+  float wh_scale;
+} fc_quadspline_config;
+
+int fc_quadspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride, float* y,
+                        int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B, int32_t D_t,
+                        fc_cols tcols, fc_cols ccols, const fc_quadspline_config* cfg, int32_t* status, void* stream);
+/* adjoint of fc_quadspline_apply (either direction): grad_x [B, *] and grad_params [B, D_t * P] */
+int fc_quadspline_backward(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                           const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet, float* grad_x,
+                           int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride, int64_t B, int32_t D_t,
+                           fc_cols tcols, fc_cols ccols, const fc_quadspline_config* cfg, void* stream);
+
 /* Affine element-wise transforms. */
 #define FC_AFFINE_BLOCKED 0     /* params[r] = [shift(D_t) | raw_scale(D_t)]      coupling.py:234-238 */
 #define FC_AFFINE_INTERLEAVED 1 /* params[r] = [raw_scale_0, shift_0, raw_scale_1, ...] autoregressive.py:124-129 */

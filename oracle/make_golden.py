@@ -276,6 +276,17 @@ def build_reference_flow(wl, seed=0):
             layers.append(transforms.PiecewiseLinearCouplingTransform(
                 workloads.make_mask(features, layer["mask"]), create, num_bins=layer["num_bins"], tails=layer["tails"],
                 tail_bound=layer["tail_bound"], apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "pquad_coupling":
+            h, b = layer["hidden_features"], layer["num_blocks"]
+            create = lambda i, o, h=h, b=b: nets.ResidualNet(i, o, hidden_features=h, num_blocks=b)  # noqa: E731
+            layers.append(transforms.PiecewiseQuadraticCouplingTransform(
+                workloads.make_mask(features, layer["mask"]), create, num_bins=layer["num_bins"], tails=layer["tails"],
+                tail_bound=layer["tail_bound"], apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "maf_pquad":
+            layers.append(transforms.MaskedPiecewiseQuadraticAutoregressiveTransform(
+                features=features, hidden_features=layer["hidden_features"], context_features=ctx,
+                num_bins=layer["num_bins"], num_blocks=layer["num_blocks"], tails=layer["tails"],
+                tail_bound=layer["tail_bound"]))
         elif kind == "maf_plin":
             layers.append(transforms.MaskedPiecewiseLinearAutoregressiveTransform(
                 num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
@@ -358,6 +369,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-quadratic-functions":
         make_quadratic_functions()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-quadratic-models":
+        make_model("pquad_coupling_small", with_grad=True)
+        make_model("maf_pquad_small", with_grad=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-linear":
         make_linear_functions()

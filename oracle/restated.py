@@ -585,6 +585,30 @@ def rq_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
     return y, sum_except_batch(lad)
 
 
+def quadratic_elementwise(inputs, params, num_bins, tails, tail_bound, inverse):
+    """coupling.py:403-427 / autoregressive.py:417-450: params [B, D_t * P] viewed [B, D_t, P], widths first."""
+    b, d = inputs.shape
+    params = params.reshape(b, d, -1)
+    uw, uh = params[..., :num_bins], params[..., num_bins:]
+    if tails is None:
+        y, lad = quadratic_spline(inputs, uw, uh, inverse=inverse)
+    else:
+        y, lad = unconstrained_quadratic_spline(inputs, uw, uh, inverse=inverse, tails=tails, tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
+def quadratic_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
+    """PiecewiseQuadraticCDF._spline, nonlinearities.py:309-334: parameters shared across the batch."""
+    b = inputs.shape[0]
+    uw = state[prefix + "unnormalized_widths"].to(inputs.dtype)[None].expand(b, -1, -1)
+    uh = state[prefix + "unnormalized_heights"].to(inputs.dtype)[None].expand(b, -1, -1)
+    if tails is None:
+        y, lad = quadratic_spline(inputs, uw, uh, inverse=inverse)
+    else:
+        y, lad = unconstrained_quadratic_spline(inputs, uw, uh, inverse=inverse, tails=tails, tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
 def linear_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
     """PiecewiseLinearCDF._spline, flowcon/transforms/nonlinearities.py:263-277: `unnormalized_pdf` [D, K] shared across
     the batch."""
@@ -606,7 +630,7 @@ def _coupling(state, spec, inputs, context, inverse, elementwise):
     identity = inputs[:, idf]
     transform = inputs[:, trf]
     uncond = spec.get("unconditional", False)
-    cdf = linear_cdf if spec["kind"] == "plin_coupling" else rq_cdf
+    cdf = {"plin_coupling": linear_cdf, "pquad_coupling": quadratic_cdf}.get(spec["kind"], rq_cdf)
     lad_id = 0.0
     if uncond and inverse:
         identity, lad_id = cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
@@ -656,6 +680,13 @@ def apply_layer(state, spec, inputs, context=None, inverse=False):
         def ew(x, params):
             return rq_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0),
                                   inverse, divisor, ident, constrained_bound=bound)
+    elif kind in ("pquad_coupling", "maf_pquad"):
+        # coupling.py:409-411: widths and heights / sqrt(hidden) when the conditioner exposes it (ResidualNet yes, MADE no)
+        div = math.sqrt(spec["hidden_features"]) if kind == "pquad_coupling" else 1.0
+
+        def ew(x, params):
+            return quadratic_elementwise(x, params / div, spec["num_bins"], spec.get("tails"),
+                                         spec.get("tail_bound", 1.0), inverse)
     elif kind in ("plin_coupling", "maf_plin"):
         def ew(x, params):
             return linear_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0),

@@ -239,7 +239,7 @@ def test_sum_of_sigmoids_large_inputs(dev):
 # ------------------------------------------------------------------------------------------------
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
           "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small", "plin_coupling_small",
-          "maf_plin_small"]
+          "maf_plin_small", "pquad_coupling_small", "maf_pquad_small"]
 
 
 def _load(name, dev):
@@ -910,3 +910,40 @@ def test_cfg3_gradients_tensorcore_path_vs_cublas_path(dev, monkeypatch):
         errs[enabled] = worst
     # the tensor-core path is as close to fp64 as the cuBLAS fp32 path (factor 3 + an absolute floor)
     assert errs[True] <= 3.0 * errs[False] + 1e-4, errs
+
+
+@pytest.mark.parametrize("name", ["quad_fwd_k8", "quad_inv_k8", "quad_fwd_tails_k10", "quad_inv_tails_k10", "quad_fwd_k5"])
+def test_quadratic_spline_kernels(dev, name):
+    """fc_quadspline_apply / fc_quadspline_backward (through transforms.quadratic_spline /
+    unconstrained_quadratic_spline) against golden vectors of the reference's splines/quadratic.py."""
+    gold = load_golden("functions_quadratic")
+    k, has_tails, tb, inverse = gold[name + "/meta"].tolist()
+    x = gold[name + "/x"].to(dev).requires_grad_(True)
+    uw = gold[name + "/uw"].to(dev).requires_grad_(True)
+    uh = gold[name + "/uh"].to(dev).requires_grad_(True)
+    if has_tails:
+        y, lad = transforms.unconstrained_quadratic_spline(x, uw, uh, inverse=bool(inverse), tail_bound=tb)
+    else:
+        y, lad = transforms.quadratic_spline(x, uw, uh, inverse=bool(inverse))
+    assert_parity(y, gold[name + "/y32"], gold[name + "/y64"], OUT_TOL, 1.0, name + " y")
+    assert_parity(lad, gold[name + "/lad32"], gold[name + "/lad64"], OUT_TOL, 1.0, name + " lad")
+    gx, gw, gh = torch.autograd.grad((y * gold[name + "/gy"].to(dev)).sum() + (lad * gold[name + "/gl"].to(dev)).sum(),
+                                     [x, uw, uh])
+    for got, key in ((gx, "gx"), (gw, "gw"), (gh, "gh")):
+        s = max(1e-2, gold[name + "/" + key + "64"].abs().mean().item())
+        assert_parity(got, gold[name + "/" + key + "32"], gold[name + "/" + key + "64"], GRAD_TOL, s, name + " " + key)
+
+
+def test_quadratic_spline_wide_layer_round_trip(dev):
+    """A 64-feature PiecewiseQuadraticCDF (TMA-ring kernel): forward against the fp64 oracle, inverse round trip."""
+    g = torch.Generator(device=dev).manual_seed(5)
+    layer = transforms.PiecewiseQuadraticCDF([64], num_bins=8, tails="linear", tail_bound=3.0).to(dev)
+    x = torch.randn(20000, 64, generator=g, device=dev) * 2
+    with torch.no_grad():
+        y, lad = layer(x)
+        xi, ladi = layer.inverse(y)
+        st = {"unnormalized_widths": layer.unnormalized_widths.detach().cpu().double(),
+              "unnormalized_heights": layer.unnormalized_heights.detach().cpu().double()}
+        ref_y, ref_lad = restated.quadratic_cdf(st, "", x.cpu().double(), 8, "linear", 3.0, False)
+    assert (y.cpu().double() - ref_y).abs().max() < 2e-5 and (lad.cpu().double() - ref_lad).abs().max() < 5e-4
+    assert (xi - x).abs().max() < 5e-4 and (lad + ladi).abs().max() < 5e-3

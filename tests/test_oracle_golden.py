@@ -146,7 +146,7 @@ def test_sum_of_sigmoids_matches_reference(fn_gold, name):
 
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
           "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small", "plin_coupling_small",
-          "maf_plin_small"]
+          "maf_plin_small", "pquad_coupling_small", "maf_pquad_small"]
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -228,7 +228,7 @@ def test_linear_spline_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg3_small", "cfg2_small", "plin_coupling_small", "maf_plin_small",
-                                  "prq_coupling_uncond_small"])
+                                  "prq_coupling_uncond_small", "pquad_coupling_small", "maf_pquad_small"])
 def test_flow_parameter_gradients_match_reference(name):
     gold = load_golden(name)
     wl = workloads.get_workload(name)
