@@ -149,6 +149,18 @@ def main():
         print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
                           "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                           "bytes": nbytes}), flush=True)
+    # piecewise-quadratic spline, same coupling shapes: K = 8 with linear tails -> P = 15, 4 (P + 2) B/element
+    pq = torch.randn(args.B, 32 * 15, generator=g, device=dev)
+    quad = (8, _cabi.TAILS_LINEAR, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1.0 / 16.0)
+    for name, fn, nbytes in (
+            ("quadspline_fwd D=64 K=8 coupling", lambda: ops.quadspline_layer(xl, pq, tca, cca, *quad),
+             args.B * (4 * 64 + 4 * 480 + 4 * 64 + 4)),
+            ("quadspline_bwd D=64 K=8 coupling", lambda: ops.quadspline_layer_backward(xl, pq, gyl, gll, tca, cca, *quad),
+             args.B * (4 * 64 * 3 + 4 * 480 * 2 + 4))):
+        med, best = timeit(fn)
+        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
+                          "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
+                          "bytes": nbytes}), flush=True)
     if args.sweep:
         a, nbytes = cases[args.sweep_case][1]
         best = None
