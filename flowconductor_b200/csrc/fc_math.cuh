@@ -738,9 +738,9 @@ FC_HD void linspline_eval(const LinSplineParams& c, float x, const float* u, flo
     int idx;
     float alpha, cdf_lo;
     linspline_forward_bin<KC>(K, xn, p, idx, alpha, cdf_lo);
-    float pi = p[0];
+    float pi = 0.f;  // p[idx] as a masked sum (a select chain becomes an indexed load and pushes p[] to local memory)
 #pragma unroll(KC ? KC : 4)
-    for (int j = 1; j < K; ++j) pi = j == idx ? p[j] : pi;
+    for (int j = 0; j < K; ++j) pi = fmaf(j == idx ? 1.f : 0.f, p[j], pi);
     float o = cdf_lo + alpha * pi;                       // :93-94
     o = fminf(fmaxf(o, 0.f), 1.f);                       // :95
     ls = fc_log_deriv(pi) + c.log_k;                     // :97-98
@@ -818,9 +818,9 @@ FC_HD void linspline_backward_elem(const LinSplineParams& c, float x, const floa
   int idx;
   float alpha, cdf_lo;
   linspline_forward_bin<KC>(K, xn, p, idx, alpha, cdf_lo);
-  float pi = p[0];
+  float pi = 0.f;
 #pragma unroll(KC ? KC : 4)
-  for (int j = 1; j < K; ++j) pi = j == idx ? p[j] : pi;
+  for (int j = 0; j < K; ++j) pi = fmaf(j == idx ? 1.f : 0.f, p[j], pi);
   const float dydx = S * (float)K * pi * c.inv_w;
   float gyf = gy, glf = gl;
   if (c.inverse) {
@@ -1478,44 +1478,44 @@ FC_HD void quad_prepare(const QuadSplineParams& c, const float* u, QuadKnots<KC>
   const int K = KC ? KC : c.K;
   const float s = c.wh_scale;  // coupling.py:409-411: raw widths and heights divided by sqrt(hidden)
   float m = -INFINITY;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j < K; ++j) m = fmaxf(m, u[j]);
   const float sl2 = s * FC_LOG2E, ml2 = m * sl2;
   float se = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j < K; ++j) {
     q.sm[j] = fc_exp2(fmaf(u[j], sl2, -ml2));
     se += q.sm[j];
   }
   const float inv = fc_rcp(se), coef = 1.f - c.min_w * (float)K;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j < K; ++j) {
     q.sm[j] *= inv;
     q.w[j] = fmaf(coef, q.sm[j], c.min_w);  // quadratic.py:81-82
   }
   const float* uh = u + K;
   if (c.tails == FC_TAILS_LINEAR) {  // K-1 raw heights -> E[1..K-1]; E[0] = E[K] = constant (:87-101)
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
     for (int j = 0; j < K - 1; ++j) q.E[j + 1] = fc_softplus1(uh[j] * s) + 1e-3f;  // :84
     float num = 0.25f * q.w[0] * q.E[1] + 0.25f * q.w[K - 1] * q.E[K - 1];
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
     for (int i = 0; i + 2 < K; ++i) num = fmaf(0.5f * (q.E[i + 1] + q.E[i + 2]), q.w[i + 1], num);
     q.den = 1.f - 0.25f * q.w[0] - 0.25f * q.w[K - 1];
     q.cst = fc_div(num, q.den);
     q.E[0] = q.cst;
     q.E[K] = q.cst;
   } else {
-#pragma unroll(KC ? KC + 1 : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
     for (int j = 0; j <= K; ++j) q.E[j] = fc_softplus1(uh[j] * s) + 1e-3f;
     q.cst = 0.f;
     q.den = 1.f;
   }
   float area = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int i = 0; i < K; ++i) area = fmaf(0.5f * (q.E[i] + q.E[i + 1]), q.w[i], area);  // :103-106
   q.area = area;
   const float ia = fc_rcp(area) * (1.f - c.min_h);
-#pragma unroll(KC ? KC + 1 : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j <= K; ++j) q.H[j] = fmaf(q.E[j], ia, c.min_h);  // :107-108
 }
 
@@ -1527,7 +1527,7 @@ FC_HD void quad_locate(int K, const QuadKnots<KC>& q, float pos, bool by_cdf, in
                        float& lcdf, float& hl, float& hr) {
   idx = 0;
   float rl = 0.f, rc = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int m = 1; m <= K; ++m) {
     rl += q.w[m - 1];
     rc = fmaf(0.5f * (q.H[m - 1] + q.H[m]), q.w[m - 1], rc);
@@ -1537,20 +1537,22 @@ FC_HD void quad_locate(int K, const QuadKnots<KC>& q, float pos, bool by_cdf, in
   idx = idx > K - 1 ? K - 1 : idx;
   loc = 0.f;
   lcdf = 0.f;
-  bw = q.w[0];
-  hl = q.H[0];
-  hr = q.H[1];
+  bw = 0.f;
+  hl = 0.f;
+  hr = 0.f;
   rl = 0.f;
   rc = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int m = 0; m < K; ++m) {
-    if (m == idx) {
-      loc = rl;
-      lcdf = rc;
-      bw = q.w[m];
-      hl = q.H[m];
-      hr = q.H[m + 1];
-    }
+    // masked accumulation (exactly one m matches; sel is 0 or 1, so the FMAs are exact): a chain of conditional
+    // assignments is turned into q.w[idx]-style indexed loads by the compiler, which forces the knot arrays into
+    // local memory
+    const float sel = m == idx ? 1.f : 0.f;
+    loc = fmaf(sel, rl, loc);
+    lcdf = fmaf(sel, rc, lcdf);
+    bw = fmaf(sel, q.w[m], bw);
+    hl = fmaf(sel, q.H[m], hl);
+    hr = fmaf(sel, q.H[m + 1], hr);
     rl += q.w[m];
     rc = fmaf(0.5f * (q.H[m] + q.H[m + 1]), q.w[m], rc);
   }
@@ -1621,7 +1623,9 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
   const bool inside = quad_domain(c, x, xs, status);
   if (!inside) {
     gx = gy;
-    for (int j = 0; j < K + NH; ++j) gu[j] = 0.f;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+    for (int j = 0; j < 2 * K + 1; ++j)
+      if (j < K + NH) gu[j] = 0.f;
     return;
   }
   QuadKnots<KC> q;
@@ -1657,9 +1661,9 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
   const float g_hl = gyS * (bw * alpha - 0.5f * bw * alpha * alpha) + glf * (1.f - alpha) * inv_D;
   const float g_loc = -g_alpha * inv_bw;
   float gw[FC_QK(KC)], gH[FC_QK(KC) + 1];
-#pragma unroll(KC ? KC + 1 : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j <= K; ++j) gH[j] = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int i = 0; i < K; ++i) {
     const bool below = i < idx;
     gw[i] = below ? g_loc + gyS * 0.5f * (q.H[i] + q.H[i + 1]) : (i == idx ? g_bw : 0.f);
@@ -1670,16 +1674,16 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
   // H = min_h + (1 - min_h) E / area
   const float ia = fc_rcp(q.area), k1 = (1.f - c.min_h) * ia;
   float dotE = 0.f;
-#pragma unroll(KC ? KC + 1 : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j <= K; ++j) dotE = fmaf(gH[j], q.E[j], dotE);
   const float g_area = -k1 * ia * dotE;
   float gE[FC_QK(KC) + 1];
-#pragma unroll(KC ? KC + 1 : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int j = 0; j <= K; ++j) {
     const float wl = j > 0 ? q.w[j - 1] : 0.f, wr = j < K ? q.w[j] : 0.f;
     gE[j] = fmaf(k1, gH[j], g_area * 0.5f * (wl + wr));
   }
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int i = 0; i < K; ++i) gw[i] = fmaf(g_area * 0.5f, q.E[i] + q.E[i + 1], gw[i]);
   const float s = c.wh_scale;
   const float* uh = u + K;
@@ -1688,7 +1692,7 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
     const float gC = gE[0] + gE[K];
     const float g_num = fc_div(gC, q.den), g_den = -g_num * q.cst;
     // e_j = E[j+1], j = 0..K-2
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
     for (int j = 0; j < K - 1; ++j) {
       float dn = 0.f;
       if (j >= 1) dn += 0.5f * q.w[j];
@@ -1699,7 +1703,7 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
       fc_sigmoid_parts(uh[j] * s, sg, unused);
       gh[j] = (gE[j + 1] + g_num * dn) * sg * s;
     }
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
     for (int mI = 0; mI < K; ++mI) {
       float dn;
       if (mI == 0) dn = 0.25f * q.E[1];
@@ -1709,7 +1713,7 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
       gw[mI] += g_num * dn + g_den * dd;
     }
   } else {
-#pragma unroll(KC ? KC + 1 : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
     for (int j = 0; j <= K; ++j) {
       float sg, unused;
       fc_sigmoid_parts(uh[j] * s, sg, unused);
@@ -1719,11 +1723,13 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
   // w = min_w + (1 - min_w K) softmax(s uw)
   const float coef = 1.f - c.min_w * (float)K;
   float dot = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int i = 0; i < K; ++i) dot = fmaf(q.sm[i], gw[i] * coef, dot);
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int i = 0; i < K; ++i) gu[i] = s * q.sm[i] * (gw[i] * coef - dot);
-  for (int j = 0; j < NH; ++j) gu[K + j] = gh[j];
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 0; j <= K; ++j)
+    if (j < NH) gu[K + j] = gh[j];
 }
 
 }  // namespace fc

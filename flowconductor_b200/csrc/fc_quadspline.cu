@@ -12,6 +12,7 @@ namespace fc {
 
 template <int KC>
 struct QuadSplineOp {
+  static constexpr int kMinBlocks = 1;  // arithmetic-heavy: the full 128 registers instead of spills (fc_pipeline.cuh)
   QuadSplineParams c;
   __device__ __forceinline__ int P() const { return c.tails == FC_TAILS_LINEAR ? 2 * c.K - 1 : 2 * c.K + 1; }
   __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned& status) const {
