@@ -673,7 +673,8 @@ def test_full_size_cfg3_training_step_is_finite(dev):
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2_tc_small", "cfg3_small", "cfg4_small"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_tc_small", "cfg3_small", "cfg4_small", "plin_coupling_small",
+                                  "pquad_coupling_small", "prq_coupling_uncond_small"])
 def test_cuda_graph_replay_matches_eager(dev, name):
     """graphs.capture: a replayed graph of log_prob and of the inverse cascade returns exactly
     what the eager call returns, for new inputs copied into the static buffers, and leaves the inputs untouched."""
