@@ -222,48 +222,40 @@ def rq_elementwise(inputs, params, num_bins, tails, tail_bound, inverse, wh_divi
 # n3: piecewise-linear spline  (flowcon/transforms/splines/linear.py:9-105)
 # --------------------------------------------------------------------------------------------
 def linear_spline(inputs, unnormalized_pdf, inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0):
-    """linear.py:38-105.  K equal-width bins with softmax probabilities; the cdf's last knot is forced to 1 (:56) and,
-    in the inverse, bumped by 1e-6 IN PLACE by `searchsorted` (torchutils.py:147-149) BEFORE the slopes are taken
-    (:60-71), so the last bin's slope and offset see the bump — kept."""
+    """linear.py:38-105.  K equal-width bins with softmax probabilities; forward: bin = floor(u K), value = cdf at the
+    bin's left edge + position * probability (:84-95); inverse: bin by searchsorted on the cdf, then the bin's affine
+    map inverted through slope / offset (:60-78).  Quirk kept: `searchsorted` bumps the forced last cdf knot (1.0, :56)
+    by 1e-6 IN PLACE (torchutils.py:147-149) before the slopes are taken, so the last bin's slope sees the bump."""
     if torch.min(inputs) < left or torch.max(inputs) > right:
-        raise InputOutsideDomain()
-    if inverse:
-        inputs = (inputs - bottom) / (top - bottom)
-    else:
-        inputs = (inputs - left) / (right - left)
-    num_bins = unnormalized_pdf.size(-1)
+        raise InputOutsideDomain()  # :45-46
+    lo, hi = (bottom, top) if inverse else (left, right)
+    u = (inputs - lo) / (hi - lo)
+    k = unnormalized_pdf.size(-1)
     pdf = F.softmax(unnormalized_pdf, dim=-1)
     cdf = torch.cumsum(pdf, dim=-1)
     cdf[..., -1] = 1.0
     cdf = F.pad(cdf, pad=(1, 0), mode="constant", value=0.0)
     if inverse:
-        cdf[..., -1] += 1e-6  # the in-place bump of searchsorted
-        inv_bin_idx = torch.sum(inputs[..., None] >= cdf, dim=-1) - 1
-        bin_boundaries = torch.linspace(0, 1, num_bins + 1).view([1] * inputs.dim() + [-1]).expand(
-            *inputs.shape, -1).to(cdf.dtype)
-        slopes = (cdf[..., 1:] - cdf[..., :-1]) / (bin_boundaries[..., 1:] - bin_boundaries[..., :-1])
-        offsets = cdf[..., 1:] - slopes * bin_boundaries[..., 1:]
-        inv_bin_idx = inv_bin_idx.unsqueeze(-1)
-        input_slopes = slopes.gather(-1, inv_bin_idx)[..., 0]
-        input_offsets = offsets.gather(-1, inv_bin_idx)[..., 0]
-        outputs = (inputs - input_offsets) / input_slopes
-        outputs = torch.clamp(outputs, 0, 1)
-        logabsdet = -torch.log(input_slopes)
+        cdf[..., -1] += 1e-6
+        idx = (torch.sum(u[..., None] >= cdf, dim=-1) - 1).unsqueeze(-1)
+        edges = torch.linspace(0, 1, k + 1).view([1] * u.dim() + [-1]).expand(*u.shape, -1).to(cdf.dtype)
+        slopes = (cdf[..., 1:] - cdf[..., :-1]) / (edges[..., 1:] - edges[..., :-1])
+        offsets = cdf[..., 1:] - slopes * edges[..., 1:]
+        slope = slopes.gather(-1, idx)[..., 0]
+        out = torch.clamp((u - offsets.gather(-1, idx)[..., 0]) / slope, 0, 1)
+        logabsdet = -torch.log(slope)
+        out = out * (right - left) + left
     else:
-        bin_pos = inputs * num_bins
-        bin_idx = torch.floor(bin_pos).long()
-        bin_idx[bin_idx >= num_bins] = num_bins - 1
-        alpha = bin_pos - bin_idx.to(inputs.dtype)
-        input_pdfs = pdf.gather(-1, bin_idx[..., None])[..., 0]
-        outputs = cdf.gather(-1, bin_idx[..., None])[..., 0]
-        outputs = outputs + alpha * input_pdfs
-        outputs = torch.clamp(outputs, 0, 1)
-        logabsdet = torch.log(input_pdfs) - math.log(1.0 / num_bins)
-    if inverse:
-        outputs = outputs * (right - left) + left
-    else:
-        outputs = outputs * (top - bottom) + bottom
-    return outputs, logabsdet
+        pos = u * k
+        idx = torch.floor(pos).long()
+        idx[idx >= k] = k - 1
+        frac = pos - idx.to(u.dtype)
+        p = pdf.gather(-1, idx[..., None])[..., 0]
+        out = cdf.gather(-1, idx[..., None])[..., 0]
+        out = torch.clamp(out + frac * p, 0, 1)
+        logabsdet = torch.log(p) - math.log(1.0 / k)
+        out = out * (top - bottom) + bottom
+    return out, logabsdet
 
 
 def unconstrained_linear_spline(inputs, unnormalized_pdf, inverse=False, tail_bound=1.0, tails="linear"):
@@ -296,72 +288,70 @@ def linear_elementwise(inputs, params, num_bins, tails, tail_bound, inverse):
 # --------------------------------------------------------------------------------------------
 # n3: piecewise-quadratic spline  (flowcon/transforms/splines/quadratic.py:11-159)
 # --------------------------------------------------------------------------------------------
+def _quadratic_knots(raw_w, raw_h, floor_w, floor_h):
+    """Bin widths and knot heights of the piecewise-linear pdf, quadratic.py:81-108.
+    widths: softmax with a floor (:81-82).  heights: softplus + 1e-3 (:84); when only K-1 raw heights are given the two
+    boundary knots get the value that turns into exactly 1 after normalisation (:86-101); then divide by the
+    trapezoid area of the un-normalised pdf and apply the height floor (:103-108)."""
+    k = raw_w.shape[-1]
+    w = floor_w + (1 - floor_w * k) * F.softmax(raw_w, dim=-1)
+    e = F.softplus(raw_h) + 1e-3
+    if e.shape[-1] == k - 1:
+        half_first, half_last = 0.5 * w[..., 0], 0.5 * w[..., -1]
+        inner = torch.sum(((e[..., :-1] + e[..., 1:]) / 2) * w[..., 1:-1], dim=-1)
+        edge = (0.5 * half_first * e[..., 0] + 0.5 * half_last * e[..., -1] + inner) / (1 - 0.5 * half_first
+                                                                                       - 0.5 * half_last)
+        edge = edge[..., None]
+        e = torch.cat([edge, e, edge], dim=-1)
+    area = torch.sum(((e[..., :-1] + e[..., 1:]) / 2) * w, dim=-1)[..., None]
+    h = floor_h + (1 - floor_h) * (e / area)
+    return w, h
+
+
+def _padded_cumsum_to_one(x):
+    """cumsum with the last entry forced to 1 and a leading 0 (quadratic.py:110-118, linear.py:55-57)."""
+    c = torch.cumsum(x, dim=-1)
+    c[..., -1] = 1.0
+    return F.pad(c, pad=(1, 0), mode="constant", value=0.0)
+
+
 def quadratic_spline(inputs, unnormalized_widths, unnormalized_heights, inverse=False, left=0.0, right=1.0, bottom=0.0,
                      top=1.0, min_bin_width=1e-3, min_bin_height=1e-3):
     """quadratic.py:55-159: piecewise-linear pdf (K widths, K+1 knot heights) integrated to a piecewise-quadratic cdf.
-    With K-1 raw heights (linear tails) the two boundary heights are the constant that makes them 1 after
-    normalisation (:87-101)."""
+    Operation order of the reference kept: normalise the input (:70-73), knots (:81-108), left-cdf and location
+    vectors (:110-118), bin by searchsorted on the cdf (inverse) or the locations (forward) (:120-123), per-bin
+    polynomial a alpha^2 + b alpha + c (:130-132), root / evaluation (:134-149), rescale (:151-154)."""
     if torch.min(inputs) < left or torch.max(inputs) > right:
-        raise InputOutsideDomain()
-    if inverse:
-        inputs = (inputs - bottom) / (top - bottom)
-    else:
-        inputs = (inputs - left) / (right - left)
-    num_bins = unnormalized_widths.shape[-1]
-    if min_bin_width * num_bins > 1.0:
+        raise InputOutsideDomain()  # :67-68
+    lo, hi = (bottom, top) if inverse else (left, right)
+    u = (inputs - lo) / (hi - lo)
+    k = unnormalized_widths.shape[-1]
+    if min_bin_width * k > 1.0:
         raise ValueError("Minimal bin width too large for the number of bins")
-    if min_bin_height * num_bins > 1.0:
+    if min_bin_height * k > 1.0:
         raise ValueError("Minimal bin height too large for the number of bins")
-    widths = F.softmax(unnormalized_widths, dim=-1)
-    widths = min_bin_width + (1 - min_bin_width * num_bins) * widths
-    unnorm_heights_exp = F.softplus(unnormalized_heights) + 1e-3
-    if unnorm_heights_exp.shape[-1] == num_bins - 1:
-        first_widths = 0.5 * widths[..., 0]
-        last_widths = 0.5 * widths[..., -1]
-        numerator = (0.5 * first_widths * unnorm_heights_exp[..., 0] + 0.5 * last_widths * unnorm_heights_exp[..., -1]
-                     + torch.sum(((unnorm_heights_exp[..., :-1] + unnorm_heights_exp[..., 1:]) / 2) * widths[..., 1:-1],
-                                 dim=-1))
-        constant = numerator / (1 - 0.5 * first_widths - 0.5 * last_widths)
-        constant = constant[..., None]
-        unnorm_heights_exp = torch.cat([constant, unnorm_heights_exp, constant], dim=-1)
-    unnormalized_area = torch.sum(((unnorm_heights_exp[..., :-1] + unnorm_heights_exp[..., 1:]) / 2) * widths,
-                                  dim=-1)[..., None]
-    heights = unnorm_heights_exp / unnormalized_area
-    heights = min_bin_height + (1 - min_bin_height) * heights
-    bin_left_cdf = torch.cumsum(((heights[..., :-1] + heights[..., 1:]) / 2) * widths, dim=-1)
-    bin_left_cdf[..., -1] = 1.0
-    bin_left_cdf = F.pad(bin_left_cdf, pad=(1, 0), mode="constant", value=0.0)
-    bin_locations = torch.cumsum(widths, dim=-1)
-    bin_locations[..., -1] = 1.0
-    bin_locations = F.pad(bin_locations, pad=(1, 0), mode="constant", value=0.0)
+    w, h = _quadratic_knots(unnormalized_widths, unnormalized_heights, min_bin_width, min_bin_height)
+    left_cdf = _padded_cumsum_to_one(((h[..., :-1] + h[..., 1:]) / 2) * w)
+    locations = _padded_cumsum_to_one(w)
+    idx = bin_index(left_cdf if inverse else locations, u)[..., None]
+    loc = locations.gather(-1, idx)[..., 0]
+    bw = w.gather(-1, idx)[..., 0]
+    c = left_cdf.gather(-1, idx)[..., 0]
+    h_left = h.gather(-1, idx)[..., 0]
+    h_right = h.gather(-1, idx + 1)[..., 0]
+    a = 0.5 * (h_right - h_left) * bw
+    b = h_left * bw
     if inverse:
-        bin_idx = bin_index(bin_left_cdf, inputs)[..., None]
+        alpha = (-b + torch.sqrt(b.pow(2) - 4 * a * (c - u))) / (2 * a)
+        out = torch.clamp(alpha * bw + loc, 0, 1)
+        logabsdet = -torch.log(alpha * (h_right - h_left) + h_left)
+        out = out * (right - left) + left
     else:
-        bin_idx = bin_index(bin_locations, inputs)[..., None]
-    input_bin_locations = bin_locations.gather(-1, bin_idx)[..., 0]
-    input_bin_widths = widths.gather(-1, bin_idx)[..., 0]
-    input_left_cdf = bin_left_cdf.gather(-1, bin_idx)[..., 0]
-    input_left_heights = heights.gather(-1, bin_idx)[..., 0]
-    input_right_heights = heights.gather(-1, bin_idx + 1)[..., 0]
-    a = 0.5 * (input_right_heights - input_left_heights) * input_bin_widths
-    b = input_left_heights * input_bin_widths
-    c = input_left_cdf
-    if inverse:
-        c_ = c - inputs
-        alpha = (-b + torch.sqrt(b.pow(2) - 4 * a * c_)) / (2 * a)
-        outputs = alpha * input_bin_widths + input_bin_locations
-        outputs = torch.clamp(outputs, 0, 1)
-        logabsdet = -torch.log((alpha * (input_right_heights - input_left_heights) + input_left_heights))
-    else:
-        alpha = (inputs - input_bin_locations) / input_bin_widths
-        outputs = a * alpha.pow(2) + b * alpha + c
-        outputs = torch.clamp(outputs, 0, 1)
-        logabsdet = torch.log((alpha * (input_right_heights - input_left_heights) + input_left_heights))
-    if inverse:
-        outputs = outputs * (right - left) + left
-    else:
-        outputs = outputs * (top - bottom) + bottom
-    return outputs, logabsdet
+        alpha = (u - loc) / bw
+        out = torch.clamp(a * alpha.pow(2) + b * alpha + c, 0, 1)
+        logabsdet = torch.log(alpha * (h_right - h_left) + h_left)
+        out = out * (top - bottom) + bottom
+    return out, logabsdet
 
 
 def unconstrained_quadratic_spline(inputs, unnormalized_widths, unnormalized_heights, inverse=False, tail_bound=1.0,
