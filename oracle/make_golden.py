@@ -245,6 +245,35 @@ def make_quadratic_functions():
     print("functions_quadratic.npz:", len(out), "arrays")
 
 
+def make_cubic_functions():
+    """functions_cubic.npz: the reference's cubic_spline (splines/cubic.py) forward and inverse with autograd
+    gradients, fp32 and fp64 (groundwork: the oracle restatement is pinned, no kernel consumes it yet)."""
+    from flowcon.transforms.splines import cubic as ref_c
+
+    out = {}
+    g = torch.Generator().manual_seed(79)
+    for name, k, inverse in [("cubic_fwd_k8", 8, False), ("cubic_inv_k8", 8, True), ("cubic_fwd_k5", 5, False),
+                             ("cubic_inv_k5", 5, True)]:
+        n = 512
+        uw, uh = torch.randn(n, k, generator=g), torch.randn(n, k, generator=g)
+        dl, dr = torch.randn(n, 1, generator=g), torch.randn(n, 1, generator=g)
+        x = torch.rand(n, generator=g) * 0.998 + 0.001
+        gy, gl = torch.randn(n, generator=g), torch.randn(n, generator=g)
+        out[name + "/meta"] = np.array([k, 1 if inverse else 0], dtype=np.float64)
+        for key, t in (("x", x), ("uw", uw), ("uh", uh), ("dl", dl), ("dr", dr), ("gy", gy), ("gl", gl)):
+            out[name + "/" + key] = np32(t)
+        for dt, tag in ((torch.float32, "32"), (torch.float64, "64")):
+            conv = np32 if tag == "32" else np64
+            args = [t.to(dt).clone().requires_grad_(True) for t in (x, uw, uh, dl, dr)]
+            y, lad = ref_c.cubic_spline(*args, inverse=inverse)
+            grads = torch.autograd.grad((y * gy.to(dt)).sum() + (lad * gl.to(dt)).sum(), args)
+            out[name + "/y" + tag], out[name + "/lad" + tag] = conv(y), conv(lad)
+            for key, gr in zip(("gx", "gw", "gh", "gdl", "gdr"), grads):
+                out[name + "/" + key + tag] = conv(gr)
+    np.savez_compressed(os.path.join(GOLDEN, "functions_cubic.npz"), **out)
+    print("functions_cubic.npz:", len(out), "arrays")
+
+
 # model-level cases
 # ------------------------------------------------------------------------------------------------
 def build_reference_flow(wl, seed=0):
@@ -366,6 +395,9 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-uncond":  # add one fixture without rewriting the others
         make_model("prq_coupling_uncond_small", with_grad=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-cubic-functions":
+        make_cubic_functions()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-quadratic-functions":
         make_quadratic_functions()

@@ -373,6 +373,101 @@ def unconstrained_quadratic_spline(inputs, unnormalized_widths, unnormalized_hei
 
 
 # --------------------------------------------------------------------------------------------
+# n3 (groundwork for the next round: no kernel yet): cubic spline  (flowcon/transforms/splines/cubic.py:15-267)
+# --------------------------------------------------------------------------------------------
+def _cbrt(x):
+    """flowcon/utils/torchutils.py:152-154."""
+    return torch.sign(x) * torch.exp(torch.log(torch.abs(x)) / 3.0)
+
+
+def _cubic_coefficients(raw_w, raw_h, raw_dl, raw_dr, floor_w, floor_h):
+    """Knots and per-bin cubic coefficients, cubic.py:98-138: floored softmax widths / heights and their forced-to-one
+    cumulative sums (:98-110); bin slopes; interior knot derivatives by the monotone (Steffen-type) rule
+    min(|s_i|, |s_{i+1}|, weighted mean) * (sign s_i + sign s_{i+1}) (:112-132); boundary derivatives
+    sigmoid(raw) * 3 * slope (:121-126); a, b, c, d of a t^3 + b t^2 + c t + d with t measured from the bin's left edge."""
+    k = raw_w.shape[-1]
+    w = floor_w + (1 - floor_w * k) * F.softmax(raw_w, dim=-1)
+    h = floor_h + (1 - floor_h * k) * F.softmax(raw_h, dim=-1)
+    cum_w = _padded_cumsum_to_one(w)
+    cum_h = _padded_cumsum_to_one(h)
+    slope = h / w
+    bound_abs = torch.min(torch.abs(slope[..., :-1]), torch.abs(slope[..., 1:]))
+    bound_mean = 0.5 * (w[..., 1:] * slope[..., :-1] + w[..., :-1] * slope[..., 1:]) / (w[..., :-1] + w[..., 1:])
+    inner = torch.min(bound_abs, bound_mean) * (torch.sign(slope[..., :-1]) + torch.sign(slope[..., 1:]))
+    d_left = torch.sigmoid(raw_dl) * 3 * slope[..., 0][..., None]
+    d_right = torch.sigmoid(raw_dr) * 3 * slope[..., -1][..., None]
+    deriv = torch.cat([d_left, inner, d_right], dim=-1)
+    a = (deriv[..., :-1] + deriv[..., 1:] - 2 * slope) / w.pow(2)
+    b = (3 * slope - 2 * deriv[..., :-1] - deriv[..., 1:]) / w
+    return cum_w, cum_h, a, b, deriv[..., :-1], cum_h[..., :-1]
+
+
+def _cubic_root_in_bin(a, b, c, d, target, lo, hi, eps, quadratic_threshold):
+    """Root of a t^3 + b t^2 + c t + d = target inside [lo, hi] (absolute position = t + lo), cubic.py:152-237 (Blinn
+    2007): one real root -> Cardano with cube roots (:176-187); three real roots -> trigonometric form, pick the root
+    inside the bin (first one whose [lo - eps, hi + eps] test passes, via argsort of the masks, :191-225); |a| below the
+    threshold -> the quadratic's root (:229-234, applied last, overriding)."""
+    b3 = (b / a) / 3.0
+    c3 = (c / a) / 3.0
+    d0 = (d - target) / a
+    delta_1 = -b3.pow(2) + c3
+    delta_2 = -c3 * b3 + d0
+    delta_3 = b3 * d0 - c3.pow(2)
+    disc = 4.0 * delta_1 * delta_3 - delta_2.pow(2)
+    dep_1 = -2.0 * b3 * delta_1 + delta_2
+    three = disc >= 0
+    one = disc < 0
+    out = torch.zeros_like(target)
+    sq = torch.sqrt(-disc[one])
+    out[one] = _cbrt((-dep_1[one] + sq) / 2.0) + _cbrt((-dep_1[one] - sq) / 2.0) - b3[one] + lo[one]
+    theta = torch.atan2(torch.sqrt(disc[three]), -dep_1[three]) / 3.0
+    cos_t, sin_t = torch.cos(theta), torch.sin(theta)
+    scale = 2 * torch.sqrt(-delta_1[three])
+    shift = -b3[three] + lo[three]
+    cands = torch.stack([cos_t, -0.5 * cos_t - 0.5 * math.sqrt(3) * sin_t, -0.5 * cos_t + 0.5 * math.sqrt(3) * sin_t],
+                        dim=-1) * scale[..., None] + shift[..., None]
+    ok = ((lo[three][..., None] - eps) < cands).to(target.dtype) * (cands < (hi[three][..., None] + eps)).to(target.dtype)
+    pick = torch.argsort(ok, dim=-1, descending=True)[..., 0][..., None]
+    out[three] = torch.gather(cands, dim=-1, index=pick).view(-1)
+    near_quadratic = a.abs() < quadratic_threshold
+    qa, qb, qc = b[near_quadratic], c[near_quadratic], d[near_quadratic] - target[near_quadratic]
+    out[near_quadratic] = (-qb + torch.sqrt(qb.pow(2) - 4 * qa * qc)) / (2 * qa) + lo[near_quadratic]
+    return out
+
+
+def cubic_spline(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left, unnorm_derivatives_right,
+                 inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0, min_bin_width=1e-3, min_bin_height=1e-3,
+                 eps=1e-5, quadratic_threshold=1e-3):
+    """cubic.py:63-267 (inputs are flat [n] with [n, K] parameters, as the reference's masked call sites pass them)."""
+    if torch.min(inputs) < left or torch.max(inputs) > right:
+        raise InputOutsideDomain()
+    k = unnormalized_widths.shape[-1]
+    if min_bin_width * k > 1.0:
+        raise ValueError("Minimal bin width too large for the number of bins")
+    if min_bin_height * k > 1.0:
+        raise ValueError("Minimal bin height too large for the number of bins")
+    lo, hi = (bottom, top) if inverse else (left, right)
+    u = (inputs - lo) / (hi - lo)
+    cum_w, cum_h, a, b, c, d = _cubic_coefficients(unnormalized_widths, unnormalized_heights, unnorm_derivatives_left,
+                                                   unnorm_derivatives_right, min_bin_width, min_bin_height)
+    idx = bin_index(cum_h if inverse else cum_w, u)[..., None]
+    ai, bi, ci, di = (t.gather(-1, idx)[..., 0] for t in (a, b, c, d))
+    x_lo = cum_w.gather(-1, idx)[..., 0]
+    x_hi = cum_w.gather(-1, idx + 1)[..., 0]
+    if inverse:
+        out = _cubic_root_in_bin(ai, bi, ci, di, u, x_lo, x_hi, eps, quadratic_threshold)
+        t = out - x_lo
+        logabsdet = -torch.log(3 * ai * t.pow(2) + 2 * bi * t + ci)
+        out = out * (right - left) + left
+    else:
+        t = u - x_lo
+        out = ai * t.pow(3) + bi * t.pow(2) + ci * t + di
+        logabsdet = torch.log(3 * ai * t.pow(2) + 2 * bi * t + ci)
+        out = out * (top - bottom) + bottom
+    return out, logabsdet
+
+
+# --------------------------------------------------------------------------------------------
 # a7 / a9: affine element-wise transforms
 # --------------------------------------------------------------------------------------------
 def affine_scale(unconstrained, activation):

@@ -174,6 +174,26 @@ def test_flow_matches_reference(name):
         _close(ladi.detach() / ls, gold["inv_lad" + tag] / ls, inv_tol * 10, name + " inverse logabsdet " + tag)
 
 
+@pytest.mark.parametrize("name", ["cubic_fwd_k8", "cubic_inv_k8", "cubic_fwd_k5", "cubic_inv_k5"])
+def test_cubic_spline_matches_reference(name):
+    """restated.cubic_spline against the unmodified reference (functions_cubic.npz): groundwork for the last member of
+    SURVEY 8f n3 — the oracle is pinned, the kernel comes next round."""
+    gold = load_golden("functions_cubic")
+    k, inverse = gold[name + "/meta"].tolist()
+    for dtype, tag, tol in ((torch.float32, "32", 5e-5), (torch.float64, "64", 1e-10)):
+        args = [gold[name + "/" + key].to(dtype).requires_grad_(True) for key in ("x", "uw", "uh", "dl", "dr")]
+        y, lad = restated.cubic_spline(*args, inverse=bool(inverse))
+        grads = torch.autograd.grad((y * gold[name + "/gy"].to(dtype)).sum() + (lad * gold[name + "/gl"].to(dtype)).sum(),
+                                    args)
+        _close(y, gold[name + "/y" + tag], tol, name + " y " + tag)
+        ls = max(1.0, gold[name + "/lad" + tag].abs().max().item())
+        _close(lad / ls, gold[name + "/lad" + tag] / ls, tol * 10, name + " lad " + tag)
+        for got, key in zip(grads, ("gx", "gw", "gh", "gdl", "gdr")):
+            ref = gold[name + "/" + key + tag]
+            gs = max(1.0, ref.abs().max().item())
+            _close(got / gs, ref / gs, tol * 50, name + " " + key + " " + tag)
+
+
 QUADRATIC_CASES = ["quad_fwd_k8", "quad_inv_k8", "quad_fwd_tails_k10", "quad_inv_tails_k10", "quad_fwd_k5"]
 
 
