@@ -34,7 +34,16 @@
 //                                overlaps the MMAs of chunk i+1) into registers, then + bias and either
 //                                ReLU/residual/store, the rational-quadratic spline of 8 (K=8) / 4 (K=16)
 //                                features per 192-column tile, or the affine transform of 32 features per 64 columns.
-// DESIGN.md 4.6 has the measurements behind each of these choices.
+//   warp 3      staging manager (EPI 3): brings the skip connection into the staging tile and stores the finished tile —
+//                                one bulk copy for a T128 tile, four 2-D tensor-map boxes (128 rows x 32 columns,
+//                                128-byte swizzled rows) for a row-major result; split-K ranges land in consecutive
+//                                row blocks of one partials matrix.
+// Operand forms of A (LinArgs::a_tiled): 0 row-major [M, K] (swizzled TMA boxes), 1 the T128 activation layout,
+// 2 TRANSPOSED [K, M] row-major — the weight-gradient product grad_y^T x reads grad_y as it lies: converter thread m
+// (= TMEM lane m) reads column m of every k-row of an un-swizzled BK x 128 box, and can accumulate the column sums
+// (the bias gradient) on the way (LinArgs::colsum).  StoreEpi::res_mask turns the staged skip-connection tile into a
+// gate (ReLU backward of an input-gradient product).
+// DESIGN.md 4.6 (inference) and 4.8 (training) have the measurements behind each of these choices.
 #include <atomic>
 
 #include "fc_common.cuh"
