@@ -1732,4 +1732,268 @@ FC_HD void quadspline_backward_elem(const QuadSplineParams& c, float x, const fl
     if (j < NH) gu[K + j] = gh[j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// cubic spline (flowcon/transforms/splines/cubic.py:15-267) — element math only, host-validated against the reference's
+// golden vectors (tests/test_kernel_math_host.py); the kernel wiring is the next step.
+// Per-feature parameters: K raw widths, K raw heights, raw left / right boundary derivative (P = 2K + 2).
+// ------------------------------------------------------------------------------------------------
+struct CubicSplineParams {
+  int K, tails, inverse;
+  float left, right, bottom, top, inv_w, inv_h;
+  float min_w, min_h, wh_scale;
+};
+
+template <int KC>
+struct CubicKnots {
+  float smw[FC_QK(KC)], smh[FC_QK(KC)], w[FC_QK(KC)], h[FC_QK(KC)], s[FC_QK(KC)], dv[FC_QK(KC) + 1];
+  float sig_l, sig_r;
+};
+
+template <int KC>
+FC_HD void cubic_softmax_floor(int K, const float* u, float scale, float floor_v, float* sm, float* out) {
+  float m = -INFINITY;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 0; j < K; ++j) m = fmaxf(m, u[j]);
+  const float sl2 = scale * FC_LOG2E, ml2 = m * sl2;
+  float se = 0.f;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 0; j < K; ++j) {
+    sm[j] = fc_exp2(fmaf(u[j], sl2, -ml2));
+    se += sm[j];
+  }
+  const float inv = fc_rcp(se), coef = 1.f - floor_v * (float)K;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 0; j < K; ++j) {
+    sm[j] *= inv;
+    out[j] = fmaf(coef, sm[j], floor_v);
+  }
+}
+
+// widths, heights, bin slopes and the K+1 knot derivatives (cubic.py:98-132): boundary knots sigmoid(raw) * 3 * slope,
+// interior knots the monotone rule min(min(s_l, s_r), weighted mean) * (sign s_l + sign s_r) = 2 min(...) (slopes > 0)
+template <int KC>
+FC_HD void cubic_prepare(const CubicSplineParams& c, const float* u, CubicKnots<KC>& q) {
+  const int K = KC ? KC : c.K;
+  cubic_softmax_floor<KC>(K, u, c.wh_scale, c.min_w, q.smw, q.w);
+  cubic_softmax_floor<KC>(K, u + K, c.wh_scale, c.min_h, q.smh, q.h);
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 0; j < K; ++j) q.s[j] = fc_div(q.h[j], q.w[j]);
+  float unused;
+  fc_sigmoid_parts(u[2 * K], q.sig_l, unused);
+  fc_sigmoid_parts(u[2 * K + 1], q.sig_r, unused);
+  q.dv[0] = q.sig_l * 3.f * q.s[0];
+  q.dv[K] = q.sig_r * 3.f * q.s[K - 1];
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 1; j < K; ++j) {
+    const float m1 = fminf(q.s[j - 1], q.s[j]);
+    const float m2 = fc_div(0.5f * (q.w[j] * q.s[j - 1] + q.w[j - 1] * q.s[j]), q.w[j - 1] + q.w[j]);
+    q.dv[j] = 2.f * fminf(m1, m2);
+  }
+}
+
+// bin of a normalised position (by cumulative width forward, cumulative height inverse; last knot forced to 1 and
+// bumped for the comparison) and its quantities, gathered with masked sums (see quad_locate)
+template <int KC>
+FC_HD void cubic_locate(int K, const CubicKnots<KC>& q, float pos, bool by_height, int& idx, float& x_lo, float& y_lo,
+                        float& w, float& s, float& d0, float& d1) {
+  idx = 0;
+  float rw = 0.f, rh = 0.f;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int m = 1; m <= K; ++m) {
+    rw += q.w[m - 1];
+    rh += q.h[m - 1];
+    const float knot = m == K ? 1.f + 1e-6f : (by_height ? rh : rw);
+    idx += pos >= knot ? 1 : 0;
+  }
+  idx = idx > K - 1 ? K - 1 : idx;
+  x_lo = y_lo = w = s = d0 = d1 = 0.f;
+  rw = 0.f;
+  rh = 0.f;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int m = 0; m < K; ++m) {
+    const float sel = m == idx ? 1.f : 0.f;
+    x_lo = fmaf(sel, rw, x_lo);
+    y_lo = fmaf(sel, rh, y_lo);
+    w = fmaf(sel, q.w[m], w);
+    s = fmaf(sel, q.s[m], s);
+    d0 = fmaf(sel, q.dv[m], d0);
+    d1 = fmaf(sel, q.dv[m + 1], d1);
+    rw += q.w[m];
+    rh += q.h[m];
+  }
+}
+
+FC_HD bool cubic_domain(const CubicSplineParams& c, float x, float& xs, unsigned& status) {
+  const float lo = c.inverse ? c.bottom : c.left;
+  const float hi = c.inverse ? c.top : c.right;
+  if (c.tails == FC_TAILS_LINEAR) {
+    const bool inside = (x >= lo) && (x <= hi);  // cubic.py:30
+    xs = inside ? x : lo;
+    return inside;
+  }
+  xs = x;
+  if (!(x >= lo && x <= hi)) {  // :84-85 raises InputOutsideDomain
+    status |= FC_STATUS_INPUT_OUTSIDE_DOMAIN;
+    xs = fminf(fmaxf(x, lo), hi);
+    if (!(xs == xs)) xs = lo;
+  }
+  return true;
+}
+
+template <int KC>
+FC_HD void cubicspline_eval(const CubicSplineParams& c, float x, const float* u, float& y, float& lad,
+                            unsigned& status) {
+  const int K = KC ? KC : c.K;
+  float xs;
+  const bool inside = cubic_domain(c, x, xs, status);
+  CubicKnots<KC> q;
+  cubic_prepare<KC>(c, u, q);
+  int idx;
+  float x_lo, y_lo, w, s, d0, d1, ys, ls;
+  const float pos = c.inverse ? (xs - c.bottom) * c.inv_h : (xs - c.left) * c.inv_w;
+  cubic_locate<KC>(K, q, pos, c.inverse != 0, idx, x_lo, y_lo, w, s, d0, d1);
+  const float iw = fc_rcp(w);
+  const float a = (d0 + d1 - 2.f * s) * iw * iw;   // cubic.py:134-137
+  const float b = (3.f * s - 2.f * d0 - d1) * iw;
+  if (!c.inverse) {
+    const float t = pos - x_lo;
+    const float o = fmaf(fmaf(fmaf(a, t, b), t, d0), t, y_lo);          // :241-247
+    ls = fc_log_deriv(fmaf(fmaf(3.f * a, t, 2.f * b), t, d0));          // :249-255
+    ys = o * (c.top - c.bottom) + c.bottom;
+  } else {
+    // The reference solves the cubic in closed form (Blinn 2007, :152-237).  The polynomial is monotone on its bin by
+    // construction of the knot derivatives, so a safeguarded Newton iteration on [0, w] finds the same root, needs no
+    // case analysis (one / three real roots / nearly quadratic), and has no a -> 0 singularity.
+    const float r = pos - y_lo;
+    float lo = 0.f, hi = w;
+    float t = fminf(fmaxf(fc_div(r, s), 0.f), w);  // the chord's root as first iterate
+    for (int it = 0; it < 24; ++it) {
+      const float f = fmaf(fmaf(fmaf(a, t, b), t, d0), t, -r);
+      const float fp = fmaf(fmaf(3.f * a, t, 2.f * b), t, d0);
+      if (f > 0.f) hi = t; else lo = t;
+      float tn = t - fc_div(f, fp);
+      if (!(tn > lo && tn < hi)) tn = 0.5f * (lo + hi);
+      if (tn == t) break;
+      t = tn;
+    }
+    ls = -fc_log_deriv(fmaf(fmaf(3.f * a, t, 2.f * b), t, d0));         // :229-235
+    ys = (t + x_lo) * (c.right - c.left) + c.left;
+  }
+  y = inside ? ys : x;
+  lad = inside ? ls : 0.f;
+}
+
+// Backward: closed-form reverse pass (bin polynomial -> knot derivatives (min rule: the gradient follows the active
+// branch) -> slopes -> floored softmaxes); inverse direction by implicit differentiation at out = f^-1(v).
+template <int KC>
+FC_HD void cubicspline_backward_elem(const CubicSplineParams& c, float x, const float* u, float gy, float gl, float& gx,
+                                     float* gu) {
+  const int K = KC ? KC : c.K;
+  float xs;
+  unsigned status = 0;
+  const bool inside = cubic_domain(c, x, xs, status);
+  if (!inside) {
+    gx = gy;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+    for (int j = 0; j < 2 * K + 2; ++j) gu[j] = 0.f;
+    return;
+  }
+  CubicKnots<KC> q;
+  cubic_prepare<KC>(c, u, q);
+  float posx = xs;
+  if (c.inverse) {
+    float out, unused;
+    cubicspline_eval<KC>(c, x, u, out, unused, status);
+    posx = out;
+  }
+  const float S = c.top - c.bottom;
+  const float un = (posx - c.left) * c.inv_w;
+  int idx;
+  float x_lo, y_lo, w, s, d0, d1;
+  cubic_locate<KC>(K, q, un, false, idx, x_lo, y_lo, w, s, d0, d1);
+  const float iw = fc_rcp(w);
+  const float a = (d0 + d1 - 2.f * s) * iw * iw, b = (3.f * s - 2.f * d0 - d1) * iw;
+  const float t = un - x_lo;
+  const float Dv = fmaf(fmaf(3.f * a, t, 2.f * b), t, d0), iD = fc_rcp(Dv);
+  const float D2 = fmaf(6.f * a, t, 2.f * b);  // P''(t)
+  float gyS, glf;
+  if (c.inverse) {
+    const float g = fc_div(gy - gl * D2 * iD * c.inv_w, S * Dv * c.inv_w);
+    gx = g;
+    gyS = -g * S;
+    glf = -gl;
+  } else {
+    gx = (gy * S * Dv + gl * D2 * iD) * c.inv_w;
+    gyS = gy * S;
+    glf = gl;
+  }
+  const float g_t = gyS * Dv + glf * D2 * iD;
+  const float g_a = gyS * t * t * t + glf * 3.f * t * t * iD;
+  const float g_b = gyS * t * t + glf * 2.f * t * iD;
+  const float g_c = gyS * t + glf * iD;
+  // a, b, c -> d0, d1, s, w of the bin
+  const float g_d0 = g_a * iw * iw - 2.f * g_b * iw + g_c;
+  const float g_d1 = g_a * iw * iw - g_b * iw;
+  const float g_s = -2.f * g_a * iw * iw + 3.f * g_b * iw;
+  const float g_wb = -(2.f * a * g_a + b * g_b) * iw;
+  float gw[FC_QK(KC)], gh[FC_QK(KC)], gs[FC_QK(KC)];
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int i = 0; i < K; ++i) {
+    const bool below = i < idx;
+    gw[i] = (below ? -g_t : 0.f) + (i == idx ? g_wb : 0.f);  // x_lo = sum_{j<idx} w_j
+    gh[i] = below ? gyS : 0.f;                               // y_lo = sum_{j<idx} h_j
+    gs[i] = i == idx ? g_s : 0.f;
+  }
+  // knot derivatives idx and idx + 1
+  float g_dl = 0.f, g_dr = 0.f;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int j = 0; j <= K; ++j) {
+    const float g = (j == idx ? g_d0 : 0.f) + (j == idx + 1 ? g_d1 : 0.f);
+    if (j == 0) {
+      g_dl = g * 3.f * q.s[0] * q.sig_l * (1.f - q.sig_l);
+      gs[0] += g * 3.f * q.sig_l;
+    } else if (j == K) {
+      g_dr = g * 3.f * q.s[K - 1] * q.sig_r * (1.f - q.sig_r);
+      gs[K - 1] += g * 3.f * q.sig_r;
+    } else {
+      const float sl = q.s[j - 1], sr = q.s[j], wl = q.w[j - 1], wr = q.w[j];
+      const float m1 = fminf(sl, sr);
+      const float N = wr * sl + wl * sr, Dn = wl + wr, iDn = fc_rcp(Dn);
+      const float m2 = 0.5f * N * iDn;
+      if (m1 <= m2) {  // min over the two slopes is active
+        gs[j - 1] += sl <= sr ? 2.f * g : 0.f;
+        gs[j] += sl <= sr ? 0.f : 2.f * g;
+      } else {         // the weighted mean is active: dv = N / Dn
+        const float gN = g * iDn, gDn = -g * N * iDn * iDn;
+        gs[j - 1] += gN * wr;
+        gs[j] += gN * wl;
+        gw[j] += gN * sl + gDn;
+        gw[j - 1] += gN * sr + gDn;
+      }
+    }
+  }
+  // s = h / w
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int i = 0; i < K; ++i) {
+    const float iwi = fc_rcp(q.w[i]);
+    gh[i] += gs[i] * iwi;
+    gw[i] -= gs[i] * q.s[i] * iwi;
+  }
+  // floored softmaxes of the scaled raw values
+  const float sc = c.wh_scale, cw = 1.f - c.min_w * (float)K, ch = 1.f - c.min_h * (float)K;
+  float dotw = 0.f, doth = 0.f;
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int i = 0; i < K; ++i) {
+    dotw = fmaf(q.smw[i], gw[i] * cw, dotw);
+    doth = fmaf(q.smh[i], gh[i] * ch, doth);
+  }
+#pragma unroll(KC ? 2 * KC + 2 : 4)
+  for (int i = 0; i < K; ++i) {
+    gu[i] = sc * q.smw[i] * (gw[i] * cw - dotw);
+    gu[K + i] = sc * q.smh[i] * (gh[i] * ch - doth);
+  }
+  gu[2 * K] = g_dl;
+  gu[2 * K + 1] = g_dr;
+}
+
 }  // namespace fc

@@ -135,6 +135,35 @@ void hm_quadspline_backward(const float* x, const float* params, const float* gy
   }
 }
 
+// cubic spline (element math only so far): params [uw(K) ; uh(K) ; dl ; dr], unit box, no tails
+static CubicSplineParams hm_cubic_params(int k, int inverse) {
+  CubicSplineParams c;
+  c.K = k; c.tails = 0; c.inverse = inverse; c.left = 0.f; c.right = 1.f; c.bottom = 0.f; c.top = 1.f;
+  c.inv_w = 1.f; c.inv_h = 1.f; c.min_w = 1e-3f; c.min_h = 1e-3f; c.wh_scale = 1.f;
+  return c;
+}
+
+void hm_cubicspline_apply(const float* x, const float* params, float* y, float* lad, long n, int k, int inverse,
+                          int unrolled) {
+  const CubicSplineParams c = hm_cubic_params(k, inverse);
+  const int P = 2 * k + 2;
+  for (long i = 0; i < n; ++i) {
+    unsigned st = 0;
+    if (unrolled && k == 8) cubicspline_eval<8>(c, x[i], params + i * P, y[i], lad[i], st);
+    else cubicspline_eval<0>(c, x[i], params + i * P, y[i], lad[i], st);
+  }
+}
+
+void hm_cubicspline_backward(const float* x, const float* params, const float* gy, const float* gl, float* gx, float* gp,
+                             long n, int k, int inverse, int unrolled) {
+  const CubicSplineParams c = hm_cubic_params(k, inverse);
+  const int P = 2 * k + 2;
+  for (long i = 0; i < n; ++i) {
+    if (unrolled && k == 8) cubicspline_backward_elem<8>(c, x[i], params + i * P, gy[i], gl[i], gx[i], gp + i * P);
+    else cubicspline_backward_elem<0>(c, x[i], params + i * P, gy[i], gl[i], gx[i], gp + i * P);
+  }
+}
+
 // compile-time n = 10 instantiations (what the kernels run for the default sigmoid count)
 void hm_sos_apply_n10(const float* x, const float* params, float* y, float* logj, long n) {
   for (long i = 0; i < n; ++i) sos_eval_t<10>(x[i], params + i * 31, 10, y[i], logj[i]);

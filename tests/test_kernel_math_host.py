@@ -271,3 +271,28 @@ def test_quadratic_spline(hm, name, unrolled):
     g64 = torch.cat([gold[name + "/gw64"], gold[name + "/gh64"]], dim=-1)
     s = max(1e-2, g64.abs().mean().item())
     assert_parity(gp, g32, g64, 1e-4, s, name + " gp")
+
+
+@pytest.mark.parametrize("name", ["cubic_fwd_k8", "cubic_inv_k8", "cubic_fwd_k5", "cubic_inv_k5"])
+@pytest.mark.parametrize("unrolled", [0, 1])
+def test_cubic_spline_element_math(hm, name, unrolled):
+    """cubicspline_eval / cubicspline_backward_elem (fc_math.cuh; not wired into a kernel yet) against the reference's
+    cubic_spline golden vectors: the inverse is a safeguarded Newton iteration instead of Blinn's closed form."""
+    gold = load_golden("functions_cubic")
+    k, inverse = (int(v) for v in gold[name + "/meta"].tolist())
+    x = gold[name + "/x"].contiguous()
+    p = torch.cat([gold[name + "/uw"], gold[name + "/uh"], gold[name + "/dl"], gold[name + "/dr"]], dim=-1).contiguous()
+    y, lad = torch.empty_like(x), torch.empty_like(x)
+    hm.hm_cubicspline_apply(fptr(x), fptr(p), fptr(y), fptr(lad), ctypes.c_long(x.numel()), k, inverse, unrolled)
+    assert_parity(y, gold[name + "/y32"], gold[name + "/y64"], 1e-5, 1.0, name + " y")
+    assert_parity(lad, gold[name + "/lad32"], gold[name + "/lad64"], 1e-5, 1.0, name + " lad")
+    gy, gl = gold[name + "/gy"].contiguous(), gold[name + "/gl"].contiguous()
+    gx, gp = torch.empty_like(x), torch.empty_like(p)
+    hm.hm_cubicspline_backward(fptr(x), fptr(p), fptr(gy), fptr(gl), fptr(gx), fptr(gp), ctypes.c_long(x.numel()), k,
+                               inverse, unrolled)
+    s = max(1e-2, gold[name + "/gx64"].abs().mean().item())
+    assert_parity(gx, gold[name + "/gx32"], gold[name + "/gx64"], 1e-4, s, name + " gx")
+    g32 = torch.cat([gold[name + "/" + key + "32"] for key in ("gw", "gh", "gdl", "gdr")], dim=-1)
+    g64 = torch.cat([gold[name + "/" + key + "64"] for key in ("gw", "gh", "gdl", "gdr")], dim=-1)
+    s = max(1e-2, g64.abs().mean().item())
+    assert_parity(gp, g32, g64, 1e-4, s, name + " gp")
