@@ -22,7 +22,7 @@ SCALE_SIGMOID2, SCALE_SOFTPLUS_CLAMP3, SCALE_SOFTPLUS_EPS = 0, 1, 2
 LINEAR_A_T128, LINEAR_OUT_T128, LINEAR_RESIDUAL_GATES = 1, 2, 4
 
 EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_linspline_apply", "fc_linspline_backward",
-           "fc_quadspline_apply", "fc_quadspline_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
+           "fc_quadspline_apply", "fc_quadspline_backward", "fc_cubicspline_apply", "fc_cubicspline_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
@@ -84,6 +84,8 @@ def lib():
                                           ctypes.POINTER(QuadSplineConfig), vp, vp]
         L.fc_quadspline_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols,
                                              ctypes.POINTER(QuadSplineConfig), vp]
+        L.fc_cubicspline_apply.argtypes = L.fc_quadspline_apply.argtypes
+        L.fc_cubicspline_backward.argtypes = L.fc_quadspline_backward.argtypes
         L.fc_affine_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, Cols, Cols, i32, i32, i32, vp]
         L.fc_affine_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols, i32,
                                          i32, i32, vp]

@@ -1,0 +1,120 @@
+// fc_cubicspline.cu — cubic spline layer (forward / inverse / backward) for sm_100a  (SURVEY.md §8(f) n3).
+//
+// Replaces cubic_spline / unconstrained_cubic_spline (flowcon/transforms/splines/cubic.py:15-267) for
+// PiecewiseCubicCouplingTransform (coupling.py:429-500), MaskedPiecewiseCubicAutoregressiveTransform
+// (autoregressive.py:460-523) and PiecewiseCubicCDF (nonlinearities.py:342-404).  Same kernel skeletons as the other
+// spline layers; element math: fc_math.cuh (the inverse is a safeguarded Newton iteration on the bin instead of the
+// reference's closed-form case analysis).  Per transformed feature P = 2K + 2 parameters
+// [K raw widths ; K raw heights ; raw left derivative ; raw right derivative]; configuration struct shared with the
+// quadratic layer (fc_quadspline_config).
+#include "fc_pipeline.cuh"
+
+namespace fc {
+
+template <int KC>
+struct CubicSplineOp {
+  static constexpr int kMinBlocks = 1;  // arithmetic-heavy: the full 128 registers instead of spills (fc_pipeline.cuh)
+  CubicSplineParams c;
+  __device__ __forceinline__ int P() const { return 2 * c.K + 2; }
+  __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned& status) const {
+    cubicspline_eval<KC>(c, x, p, y, lad, status);
+  }
+  __device__ __forceinline__ void backward(float x, const float* p, float gy, float gl, float& gx, float* gp) const {
+    cubicspline_backward_elem<KC>(c, x, p, gy, gl, gx, gp);
+  }
+};
+
+#define FC_DISPATCH_CUBIC_K(K, CALL) \
+  switch (K) {                      \
+    case 4: CALL(4); break;         \
+    case 8: CALL(8); break;         \
+    case 10: CALL(10); break;       \
+    default: CALL(0); break;        \
+  }
+
+static int make_cubicspline_params(const fc_quadspline_config* cfg, CubicSplineParams& c) {
+  if (!cfg) return FC_ERR_INVALID_ARGUMENT;
+  if (cfg->num_bins < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (cfg->num_bins > FC_MAX_BINS_GENERIC) return FC_ERR_UNSUPPORTED;
+  if (cfg->tails != FC_TAILS_NONE && cfg->tails != FC_TAILS_LINEAR) return FC_ERR_INVALID_ARGUMENT;
+  if (!(cfg->right > cfg->left) || !(cfg->top > cfg->bottom)) return FC_ERR_INVALID_ARGUMENT;
+  // cubic.py:89-92
+  if (cfg->min_bin_width * cfg->num_bins > 1.f || cfg->min_bin_height * cfg->num_bins > 1.f) return FC_ERR_INVALID_ARGUMENT;
+  c.K = cfg->num_bins;
+  c.tails = cfg->tails;
+  c.inverse = cfg->inverse != 0;
+  c.left = cfg->left; c.right = cfg->right; c.bottom = cfg->bottom; c.top = cfg->top;
+  c.inv_w = (float)(1.0 / ((double)cfg->right - (double)cfg->left));
+  c.inv_h = (float)(1.0 / ((double)cfg->top - (double)cfg->bottom));
+  c.min_w = cfg->min_bin_width;
+  c.min_h = cfg->min_bin_height;
+  c.wh_scale = cfg->wh_scale;
+  return FC_OK;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_cubicspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                                   float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,
+                                   int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                                   const fc_quadspline_config* cfg, int32_t* status, void* stream) {
+  CubicSplineParams c;
+  int rc = make_cubicspline_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  rc = check_layer_args(x, params, y, B, D_t, tcols, ccols);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!logabsdet) return FC_ERR_INVALID_ARGUMENT;
+  LayerArgs a;
+  a.x = x; a.params = params; a.y = y; a.lad = logabsdet; a.status = status;
+  a.x_stride = x_row_stride; a.p_stride = params_row_stride; a.y_stride = y_row_stride;
+  a.B = B; a.D_t = D_t; a.n_copy = ccols.n; a.tcols = tcols.idx; a.ccols = ccols.idx;
+  a.accumulate = accumulate_logabsdet;
+  const int P = 2 * c.K + 2;
+  const size_t smem = plan_tiles(a, P);
+#define CALL(KC)                                                                               \
+  {                                                                                            \
+    CubicSplineOp<KC> op;                                                                       \
+    op.c = c;                                                                                  \
+    const int piped = try_launch_pipelined(a, op, P, (int)x_row_stride, (cudaStream_t)stream); \
+    if (piped != 0) return piped < 0 ? piped : FC_OK;                                          \
+    return launch_apply(a, op, smem, (cudaStream_t)stream);                                    \
+  }
+  FC_DISPATCH_CUBIC_K(c.K, CALL)
+#undef CALL
+  return FC_OK;
+}
+
+extern "C" int fc_cubicspline_backward(const float* x, int64_t x_row_stride, const float* params,
+                                      int64_t params_row_stride, const float* grad_y, int64_t gy_row_stride,
+                                      const float* grad_logabsdet, float* grad_x, int64_t gx_row_stride,
+                                      float* grad_params, int64_t gp_row_stride, int64_t B, int32_t D_t, fc_cols tcols,
+                                      fc_cols ccols, const fc_quadspline_config* cfg, void* stream) {
+  CubicSplineParams c;
+  int rc = make_cubicspline_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  rc = check_layer_args(x, params, grad_x, B, D_t, tcols, ccols);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  if (!grad_y || !grad_params) return FC_ERR_INVALID_ARGUMENT;
+  LayerBwdArgs a;
+  a.x = x; a.params = params; a.gy = grad_y; a.gl = grad_logabsdet; a.gx = grad_x; a.gp = grad_params;
+  a.x_stride = x_row_stride; a.p_stride = params_row_stride; a.gy_stride = gy_row_stride;
+  a.gx_stride = gx_row_stride; a.gp_stride = gp_row_stride;
+  a.B = B; a.D_t = D_t; a.n_copy = ccols.n; a.tcols = tcols.idx; a.ccols = ccols.idx;
+  const int P = 2 * c.K + 2;
+  const size_t smem = plan_tiles(a, P);
+#define CALL(KC)                                                                                        \
+  {                                                                                                     \
+    CubicSplineOp<KC> op;                                                                                \
+    op.c = c;                                                                                           \
+    const int piped = try_launch_pipelined_backward(a, op, P, (int)x_row_stride, (cudaStream_t)stream); \
+    if (piped != 0) return piped < 0 ? piped : FC_OK;                                                   \
+    return launch_backward(a, op, smem, (cudaStream_t)stream);                                          \
+  }
+  FC_DISPATCH_CUBIC_K(c.K, CALL)
+#undef CALL
+  return FC_OK;
+}

@@ -286,6 +286,95 @@ quadspline_layer.register_autograd(_quadspline_backward, setup_context=_quadspli
 
 
 # ------------------------------------------------------------------------------------------------
+# cubic spline layer (same configuration struct as the quadratic layer)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("flowcon_b200::cubicspline_layer", mutates_args=())
+def cubicspline_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: Optional[Tensor], num_bins: int,
+                     tails: int, inverse: bool, left: float, right: float, bottom: float, top: float,
+                     min_bin_width: float, min_bin_height: float, wh_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    _cabi.require_cuda_f32(x, "inputs")
+    _cabi.require_cuda_f32(params, "transform params")
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    p_per = 2 * num_bins + 2
+    if params.shape[1] != d_t * p_per:
+        raise ValueError("transform params have {} columns, expected {} x {}".format(params.shape[1], d_t, p_per))
+    if min_bin_width * num_bins > 1.0:  # cubic.py:89-92
+        raise ValueError("Minimal bin width too large for the number of bins")
+    if min_bin_height * num_bins > 1.0:
+        raise ValueError("Minimal bin height too large for the number of bins")
+    y = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
+    lad = torch.empty((B,), dtype=x.dtype, device=x.device)
+    status = torch.zeros((1,), dtype=torch.int32, device=x.device)
+    cfg = _quad_cfg(num_bins, tails, inverse, left, right, bottom, top, min_bin_width, min_bin_height, wh_scale)
+    with torch.cuda.device(x.device), _cabi.launch("fc_cubicspline_apply", x.device):
+        rc = L.fc_cubicspline_apply(xp, xs, pp, ps, y.data_ptr(), y.shape[1], lad.data_ptr(), 0, B, d_t,
+                                   _cabi.cols(tcols), _cabi.cols(ccols), ctypes.byref(cfg), status.data_ptr(),
+                                   _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_cubicspline_apply")
+    return y, lad, status
+
+
+@cubicspline_layer.register_fake
+def _(x, params, tcols, ccols, num_bins, tails, inverse, left, right, bottom, top, min_bin_width, min_bin_height,
+      wh_scale):
+    return torch.empty_like(x), x.new_empty((x.shape[0],)), x.new_empty((1,), dtype=torch.int32)
+
+
+@torch.library.custom_op("flowcon_b200::cubicspline_layer_backward", mutates_args=())
+def cubicspline_layer_backward(x: Tensor, params: Tensor, grad_y: Tensor, grad_lad: Optional[Tensor],
+                              tcols: Optional[Tensor], ccols: Optional[Tensor], num_bins: int, tails: int,
+                              inverse: bool, left: float, right: float, bottom: float, top: float,
+                              min_bin_width: float, min_bin_height: float, wh_scale: float) -> Tuple[Tensor, Tensor]:
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    grad_y, gyp, gys = _cabi.rows(_cabi.require_cuda_f32(grad_y, "grad outputs"))
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    gx = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
+    gp = torch.empty((B, params.shape[1]), dtype=x.dtype, device=x.device)
+    if tcols is not None and (tcols.numel() + (ccols.numel() if ccols is not None else 0)) < x.shape[1]:
+        gx.zero_()
+    glp = None
+    if grad_lad is not None:
+        grad_lad = grad_lad.contiguous()
+        glp = grad_lad.data_ptr()
+    cfg = _quad_cfg(num_bins, tails, inverse, left, right, bottom, top, min_bin_width, min_bin_height, wh_scale)
+    with torch.cuda.device(x.device), _cabi.launch("fc_cubicspline_backward", x.device):
+        rc = L.fc_cubicspline_backward(xp, xs, pp, ps, gyp, gys, glp, gx.data_ptr(), gx.shape[1], gp.data_ptr(),
+                                      gp.shape[1], B, d_t, _cabi.cols(tcols), _cabi.cols(ccols), ctypes.byref(cfg),
+                                      _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_cubicspline_backward")
+    return gx, gp
+
+
+@cubicspline_layer_backward.register_fake
+def _(x, params, grad_y, grad_lad, tcols, ccols, *args):
+    return torch.empty_like(x), torch.empty_like(params)
+
+
+def _cubicspline_setup(ctx, inputs, output):
+    x, params, tcols, ccols = inputs[:4]
+    ctx.save_for_backward(x, params, tcols, ccols)
+    ctx.hyper = inputs[4:]
+
+
+def _cubicspline_backward(ctx, gy, gl, gstatus):
+    x, params, tcols, ccols = ctx.saved_tensors
+    if gy is None:
+        gy = torch.zeros_like(x)
+    gx, gp = cubicspline_layer_backward(x, params, gy, gl, tcols, ccols, *ctx.hyper)
+    return (gx, gp) + (None,) * (2 + len(ctx.hyper))
+
+
+cubicspline_layer.register_autograd(_cubicspline_backward, setup_context=_cubicspline_setup)
+
+
+# ------------------------------------------------------------------------------------------------
 # affine layer
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("flowcon_b200::affine_layer", mutates_args=())

@@ -209,3 +209,26 @@ class MaskedPiecewiseQuadraticAutoregressiveTransform(AutoregressiveTransform):
 
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._spline.apply(inputs, autoregressive_params, None, None, True, None)
+
+
+class MaskedPiecewiseCubicAutoregressiveTransform(AutoregressiveTransform):
+    """autoregressive.py:460-523: the constrained unit box (`cubic_spline` without tails); `num_bins` comes first as in
+    the reference; MADE exposes no `hidden_features`, so no pre-scale (:507-509)."""
+
+    def __init__(self, num_bins, features, hidden_features, context_features=None, num_blocks=2,
+                 use_residual_blocks=True, random_mask=False, activation=F.relu, dropout_probability=0.0,
+                 use_batch_norm=False):
+        self.num_bins = num_bins
+        self.features = features
+        self._spline = splines.CubicSplineSettings(num_bins, None, 1.0)
+        super().__init__(_made(self, features, hidden_features, context_features, num_blocks, use_residual_blocks,
+                               random_mask, activation, dropout_probability, use_batch_norm))
+
+    def _output_dim_multiplier(self):
+        return self.num_bins * 2 + 2
+
+    def _elementwise_forward(self, inputs, autoregressive_params):
+        return self._spline.apply(inputs, autoregressive_params, None, None, False, None)
+
+    def _elementwise_inverse(self, inputs, autoregressive_params):
+        return self._spline.apply(inputs, autoregressive_params, None, None, True, None)

@@ -15,7 +15,8 @@ from .. import _cabi, ops
 from ..nn import tensorcore
 from . import splines
 from .base import Transform
-from .nonlinearities import PiecewiseLinearCDF, PiecewiseQuadraticCDF, PiecewiseRationalQuadraticCDF
+from .nonlinearities import (PiecewiseCubicCDF, PiecewiseLinearCDF, PiecewiseQuadraticCDF,
+                            PiecewiseRationalQuadraticCDF)
 
 
 class CouplingTransform(Transform):
@@ -253,6 +254,36 @@ class PiecewiseQuadraticCouplingTransform(CouplingTransform):
 
     def _transform_dim_multiplier(self):
         return self._spline.params_per_feature()
+
+    def _coupling_layer(self, inputs, transform_params, inverse):
+        hidden = getattr(self.transform_net, "hidden_features", None)
+        return self._spline.apply(inputs, transform_params, self._tcols, self._ccols, inverse, hidden)
+
+
+class PiecewiseCubicCouplingTransform(CouplingTransform):
+    """coupling.py:429-500: per transformed feature [K raw widths ; K raw heights ; raw left / right derivative]; widths
+    and heights divided by sqrt(hidden) when the conditioner exposes `hidden_features` (:477-479)."""
+
+    def __init__(self, mask, transform_net_create_fn, num_bins=10, tails=None, tail_bound=1.0,
+                 apply_unconditional_transform=False, img_shape=None, min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT):
+        if apply_unconditional_transform and img_shape:
+            raise NotImplementedError("image-shaped inputs are outside the B200 hot path")
+        self.num_bins = num_bins
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self._spline = splines.CubicSplineSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height)
+        unconditional = None
+        if apply_unconditional_transform:  # coupling.py:449-459
+            unconditional = lambda features: PiecewiseCubicCDF(  # noqa: E731
+                shape=[features], num_bins=num_bins, tails=tails, tail_bound=tail_bound, min_bin_width=min_bin_width,
+                min_bin_height=min_bin_height)
+        super().__init__(mask, transform_net_create_fn, unconditional_transform=unconditional)
+
+    def _transform_dim_multiplier(self):
+        return self.num_bins * 2 + 2
 
     def _coupling_layer(self, inputs, transform_params, inverse):
         hidden = getattr(self.transform_net, "hidden_features", None)

@@ -15,7 +15,7 @@ from torch import nn
 from . import splines
 from .base import Transform
 
-__all__ = ["PiecewiseLinearCDF", "PiecewiseQuadraticCDF", "PiecewiseRationalQuadraticCDF"]
+__all__ = ["PiecewiseCubicCDF", "PiecewiseLinearCDF", "PiecewiseQuadraticCDF", "PiecewiseRationalQuadraticCDF"]
 
 
 class PiecewiseRationalQuadraticCDF(Transform):
@@ -127,6 +127,48 @@ class PiecewiseQuadraticCDF(Transform):
 
     def _shared_params(self, batch_size):
         p = torch.cat((self.unnormalized_widths, self.unnormalized_heights), dim=-1)
+        return p.reshape(1, -1).expand(batch_size, -1)
+
+    def apply_on_columns(self, inputs, tcols, ccols, inverse):
+        return self._spline.apply(inputs, self._shared_params(inputs.shape[0]), tcols, ccols, inverse, None)
+
+    def _run(self, inputs, inverse):
+        if inputs.dim() != 2 or inputs.shape[1] != self.unnormalized_widths.shape[0]:
+            raise ValueError("expected inputs of shape [batch, {}]".format(self.unnormalized_widths.shape[0]))
+        return self._spline.apply(inputs, self._shared_params(inputs.shape[0]), None, None, inverse, None)
+
+    def forward(self, inputs, context=None):
+        return self._run(inputs, inverse=False)
+
+    def inverse(self, inputs, context=None):
+        return self._run(inputs, inverse=True)
+
+
+class PiecewiseCubicCDF(Transform):
+    """flowcon/transforms/nonlinearities.py:342-404: learnable `unnormalized_widths` / `unnormalized_heights` [*shape, K]
+    and `unnorm_derivatives_left` / `unnorm_derivatives_right` [*shape, 1], shared across the batch."""
+
+    def __init__(self, shape, num_bins=10, tails=None, tail_bound=1.0, min_bin_width=splines.DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=splines.DEFAULT_MIN_BIN_HEIGHT):
+        super().__init__()
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.tail_bound = tail_bound
+        self.tails = tails
+        if isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(shape)
+        if len(shape) != 1:
+            raise NotImplementedError("image-shaped CDF layers are outside the B200 hot path")
+        self.unnormalized_widths = nn.Parameter(torch.randn(*shape, num_bins))
+        self.unnormalized_heights = nn.Parameter(torch.randn(*shape, num_bins))
+        self.unnorm_derivatives_left = nn.Parameter(torch.randn(*shape, 1))
+        self.unnorm_derivatives_right = nn.Parameter(torch.randn(*shape, 1))
+        self._spline = splines.CubicSplineSettings(num_bins, tails, tail_bound, min_bin_width, min_bin_height)
+
+    def _shared_params(self, batch_size):
+        p = torch.cat((self.unnormalized_widths, self.unnormalized_heights, self.unnorm_derivatives_left,
+                       self.unnorm_derivatives_right), dim=-1)
         return p.reshape(1, -1).expand(batch_size, -1)
 
     def apply_on_columns(self, inputs, tcols, ccols, inverse):

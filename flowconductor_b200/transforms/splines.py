@@ -227,3 +227,73 @@ def unconstrained_quadratic_spline(inputs, unnormalized_widths, unnormalized_hei
     assert unnormalized_heights.shape[-1] == unnormalized_widths.shape[-1] - 1  # quadratic.py:34
     return _quadratic_elementwise(inputs, unnormalized_widths, unnormalized_heights, inverse, _cabi.TAILS_LINEAR,
                                   -tail_bound, tail_bound, -tail_bound, tail_bound, min_bin_width, min_bin_height)
+
+
+# ------------------------------------------------------------------------------------------------
+# cubic spline (flowcon/transforms/splines/cubic.py)
+# ------------------------------------------------------------------------------------------------
+class CubicSplineSettings:
+    """Hyper-parameters of a cubic-spline layer and the kernel call that applies them to a [B, D_t * (2K+2)] parameter
+    tensor: per feature [K raw widths ; K raw heights ; raw left derivative ; raw right derivative]
+    (PiecewiseCubicCouplingTransform._piecewise_cdf, coupling.py:468-500)."""
+
+    def __init__(self, num_bins, tails, tail_bound, min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=DEFAULT_MIN_BIN_HEIGHT):
+        if tails not in (None, "linear"):
+            raise RuntimeError("{} tails are not implemented.".format(tails))  # cubic.py:40
+        self.num_bins = num_bins
+        self.tails = tails
+        self.tail_bound = tail_bound
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+
+    def params_per_feature(self):
+        return self.num_bins * 2 + 2
+
+    def apply(self, inputs, params, tcols, ccols, inverse, hidden_for_scaling):
+        if self.tails == "linear":
+            tails, lo, hi = _cabi.TAILS_LINEAR, -float(self.tail_bound), float(self.tail_bound)
+        else:
+            tails, lo, hi = _cabi.TAILS_NONE, 0.0, 1.0
+        wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
+        y, lad, status = ops.cubicspline_layer(inputs, params, tcols, ccols, int(self.num_bins), tails, bool(inverse),
+                                               lo, hi, lo, hi, float(self.min_bin_width), float(self.min_bin_height),
+                                               float(wh_scale))
+        check_status(status, tails)
+        return y, lad
+
+
+def _cubic_elementwise(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left,
+                       unnorm_derivatives_right, inverse, tails, left, right, bottom, top, min_bin_width, min_bin_height):
+    shape = inputs.shape
+    num_bins = unnormalized_widths.shape[-1]
+    params = torch.cat((unnormalized_widths, unnormalized_heights, unnorm_derivatives_left, unnorm_derivatives_right),
+                       dim=-1)
+    params = params.reshape(-1, params.shape[-1])
+    y, lad, status = ops.cubicspline_layer(inputs.reshape(-1, 1), params, None, None, num_bins, tails, bool(inverse),
+                                           float(left), float(right), float(bottom), float(top), float(min_bin_width),
+                                           float(min_bin_height), 1.0)
+    check_status(status, tails)
+    return y.reshape(shape), lad.reshape(shape)
+
+
+def cubic_spline(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left, unnorm_derivatives_right,
+                 inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0, min_bin_width=DEFAULT_MIN_BIN_WIDTH,
+                 min_bin_height=DEFAULT_MIN_BIN_HEIGHT, eps=1e-5, quadratic_threshold=1e-3):
+    """flowcon/transforms/splines/cubic.py:63-267 (per-element outputs and log-dets).  `eps` and `quadratic_threshold`
+    steer the reference's closed-form root selection; the kernel's Newton inverse does not need them."""
+    return _cubic_elementwise(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left,
+                              unnorm_derivatives_right, inverse, _cabi.TAILS_NONE, left, right, bottom, top,
+                              min_bin_width, min_bin_height)
+
+
+def unconstrained_cubic_spline(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left,
+                               unnorm_derivatives_right, inverse=False, tail_bound=1.0, tails="linear",
+                               min_bin_width=DEFAULT_MIN_BIN_WIDTH, min_bin_height=DEFAULT_MIN_BIN_HEIGHT, eps=1e-5,
+                               quadratic_threshold=1e-3):
+    """cubic.py:15-60: identity outside [-tail_bound, tail_bound]."""
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    return _cubic_elementwise(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left,
+                              unnorm_derivatives_right, inverse, _cabi.TAILS_LINEAR, -tail_bound, tail_bound,
+                              -tail_bound, tail_bound, min_bin_width, min_bin_height)

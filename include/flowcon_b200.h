@@ -133,6 +133,23 @@ int fc_quadspline_backward(const float* x, int64_t x_row_stride, const float* pa
                            int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride, int64_t B, int32_t D_t,
                            fc_cols tcols, fc_cols ccols, const fc_quadspline_config* cfg, void* stream);
 
+/*
+ * Cubic spline layer: replaces cubic_spline / unconstrained_cubic_spline
+ * (flowcon/transforms/splines/cubic.py:15-267) as called by PiecewiseCubicCouplingTransform._piecewise_cdf
+ * (coupling.py:468-500), MaskedPiecewiseCubicAutoregressiveTransform._elementwise (autoregressive.py:491-517) and
+ * PiecewiseCubicCDF._spline (nonlinearities.py:363-398).  params[r] = per transformed feature
+ * [num_bins raw widths ; num_bins raw heights ; raw left derivative ; raw right derivative] (P = 2K+2); raw widths and
+ * heights are multiplied by cfg->wh_scale.  The configuration struct is the quadratic layer's.  The inverse solves the
+ * bin's monotone cubic by a safeguarded Newton iteration (the reference: closed form after Blinn 2007).
+ */
+int fc_cubicspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride, float* y,
+                         int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B, int32_t D_t,
+                         fc_cols tcols, fc_cols ccols, const fc_quadspline_config* cfg, int32_t* status, void* stream);
+int fc_cubicspline_backward(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
+                            const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet, float* grad_x,
+                            int64_t gx_row_stride, float* grad_params, int64_t gp_row_stride, int64_t B, int32_t D_t,
+                            fc_cols tcols, fc_cols ccols, const fc_quadspline_config* cfg, void* stream);
+
 /* Affine element-wise transforms. */
 #define FC_AFFINE_BLOCKED 0     /* params[r] = [shift(D_t) | raw_scale(D_t)]      coupling.py:234-238 */
 #define FC_AFFINE_INTERLEAVED 1 /* params[r] = [raw_scale_0, shift_0, raw_scale_1, ...] autoregressive.py:124-129 */
