@@ -164,6 +164,19 @@ void hm_cubicspline_backward(const float* x, const float* params, const float* g
   }
 }
 
+// the same with a pre-scale on the raw widths / heights (coupling.py:477-479: / sqrt(hidden))
+void hm_cubicspline_scaled(const float* x, const float* params, const float* gy, const float* gl, float* y, float* lad,
+                           float* gx, float* gp, long n, int k, int inverse, float scale) {
+  CubicSplineParams c = hm_cubic_params(k, inverse);
+  c.wh_scale = scale;
+  const int P = 2 * k + 2;
+  for (long i = 0; i < n; ++i) {
+    unsigned st = 0;
+    cubicspline_eval<0>(c, x[i], params + i * P, y[i], lad[i], st);
+    cubicspline_backward_elem<0>(c, x[i], params + i * P, gy[i], gl[i], gx[i], gp + i * P);
+  }
+}
+
 // compile-time n = 10 instantiations (what the kernels run for the default sigmoid count)
 void hm_sos_apply_n10(const float* x, const float* params, float* y, float* logj, long n) {
   for (long i = 0; i < n; ++i) sos_eval_t<10>(x[i], params + i * 31, 10, y[i], logj[i]);

@@ -296,3 +296,29 @@ def test_cubic_spline_element_math(hm, name, unrolled):
     g64 = torch.cat([gold[name + "/" + key + "64"] for key in ("gw", "gh", "gdl", "gdr")], dim=-1)
     s = max(1e-2, g64.abs().mean().item())
     assert_parity(gp, g32, g64, 1e-4, s, name + " gp")
+
+
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_cubic_spline_width_height_prescale(hm, inverse):
+    """wh_scale (1/sqrt(hidden) of the coupling layer): evaluating raw parameters p with scale s equals evaluating the
+    pre-multiplied parameters with scale 1, and the width / height gradients pick up the factor s."""
+    gold = load_golden("functions_cubic")
+    name = "cubic_inv_k8" if inverse else "cubic_fwd_k8"
+    k, scale = 8, 0.25
+    x = gold[name + "/x"].contiguous()
+    p = torch.cat([gold[name + "/uw"], gold[name + "/uh"], gold[name + "/dl"], gold[name + "/dr"]], dim=-1).contiguous()
+    p_raw = p.clone()
+    p_raw[:, :2 * k] /= scale
+    gy, gl = gold[name + "/gy"].contiguous(), gold[name + "/gl"].contiguous()
+    outs = []
+    for params, sc in ((p_raw.contiguous(), scale), (p, 1.0)):
+        y, lad, gx, gp = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x), torch.empty_like(p)
+        hm.hm_cubicspline_scaled(fptr(x), fptr(params), fptr(gy), fptr(gl), fptr(y), fptr(lad), fptr(gx), fptr(gp),
+                                 ctypes.c_long(x.numel()), k, inverse, ctypes.c_float(sc))
+        outs.append((y, lad, gx, gp))
+    (y0, l0, gx0, gp0), (y1, l1, gx1, gp1) = outs
+    assert (y0 - y1).abs().max() < 1e-5 and (l0 - l1).abs().max() < 1e-4
+    assert (gx0 - gx1).abs().max() <= 1e-4 * max(1.0, gx1.abs().max().item())
+    gs = max(1.0, gp1.abs().max().item())
+    assert (gp0[:, :2 * k] - scale * gp1[:, :2 * k]).abs().max() <= 1e-4 * gs
+    assert (gp0[:, 2 * k:] - gp1[:, 2 * k:]).abs().max() <= 1e-4 * gs
