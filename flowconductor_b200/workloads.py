@@ -96,6 +96,14 @@ WORKLOADS = {
     "maf_pquad_small": {"features": 5, "context_features": None, "batch": 64,
                         "layers": [{"kind": "maf_pquad", "num_bins": 10, "tails": "linear", "tail_bound": 3.0,
                                     "hidden_features": 16, "num_blocks": 2}]},
+    # cubic family (coupling.py:429-500, nonlinearities.py:342-404)
+    "pcubic_coupling_small": {"features": 6, "context_features": None, "batch": 64,
+                              "layers": [{"kind": "pcubic_coupling", "mask": "alternating_even", "num_bins": 8,
+                                          "tails": "linear", "tail_bound": 3.0, "hidden_features": 16, "num_blocks": 2,
+                                          "unconditional": True},
+                                         {"kind": "pcubic_coupling", "mask": "alternating_odd", "num_bins": 8,
+                                          "tails": "linear", "tail_bound": 3.0, "hidden_features": 16,
+                                          "num_blocks": 2}]},
     "prq_coupling_notails_small": {"features": 6, "context_features": None, "batch": 64,
                                    "layers": [{"kind": "prq_coupling", "mask": "mid_split", "num_bins": 5,
                                                "tails": None, "tail_bound": 1.0, "hidden_features": 16,
@@ -121,6 +129,8 @@ def params_per_feature(layer):
         return 3 * layer["n_sigmoids"] + 1
     if kind in ("plin_coupling", "maf_plin"):
         return layer["num_bins"]
+    if kind == "pcubic_coupling":
+        return 2 * layer["num_bins"] + 2
     if kind in ("pquad_coupling", "maf_pquad"):
         return 2 * layer["num_bins"] - 1 if layer.get("tails") == "linear" else 2 * layer["num_bins"] + 1
     raise ValueError(kind)
@@ -168,15 +178,16 @@ def trained_like_(state, workload, seed=1, weight_gain=8.0):
         net = {"prq_coupling": "transform_net", "affine_coupling": "transform_net", "maf_affine": "autoregressive_net",
                "maf_prq": "autoregressive_net", "maf_sos": "autoregressive_net", "cond_sos": "conditional_net",
                "cond_prq": "conditional_net", "plin_coupling": "transform_net", "maf_plin": "autoregressive_net",
-               "pquad_coupling": "transform_net", "maf_pquad": "autoregressive_net"}[kind]
+               "pquad_coupling": "transform_net", "maf_pquad": "autoregressive_net",
+               "pcubic_coupling": "transform_net"}[kind]
         wkey = layer_prefix(i) + net + ".final_layer.weight"
         bkey = layer_prefix(i) + net + ".final_layer.bias"
         p = params_per_feature(layer)
         n_out = state[bkey].numel()
         noise = torch.randn(n_out, generator=g, dtype=torch.float32)
         std = torch.ones(n_out)
-        if kind == "pquad_coupling":
-            std = std * 4.0  # every slot is divided by sqrt(H)
+        if kind in ("pquad_coupling", "pcubic_coupling"):
+            std = std * 4.0  # the width / height slots are divided by sqrt(H)
         if kind in ("prq_coupling", "cond_prq"):
             std = std.view(-1, p)
             std[:, : 2 * layer["num_bins"]] = 16.0
@@ -220,6 +231,14 @@ def build_flow(workload, seed=0):
         elif kind == "pquad_coupling":
             hidden, blocks = layer["hidden_features"], layer["num_blocks"]
             layers.append(transforms.PiecewiseQuadraticCouplingTransform(
+                mask=make_mask(features, layer["mask"]),
+                transform_net_create_fn=lambda i, o, h=hidden, b=blocks: nets.ResidualNet(
+                    i, o, hidden_features=h, num_blocks=b),
+                num_bins=layer["num_bins"], tails=layer["tails"], tail_bound=layer["tail_bound"],
+                apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "pcubic_coupling":
+            hidden, blocks = layer["hidden_features"], layer["num_blocks"]
+            layers.append(transforms.PiecewiseCubicCouplingTransform(
                 mask=make_mask(features, layer["mask"]),
                 transform_net_create_fn=lambda i, o, h=hidden, b=blocks: nets.ResidualNet(
                     i, o, hidden_features=h, num_blocks=b),

@@ -311,6 +311,12 @@ def build_reference_flow(wl, seed=0):
             layers.append(transforms.PiecewiseQuadraticCouplingTransform(
                 workloads.make_mask(features, layer["mask"]), create, num_bins=layer["num_bins"], tails=layer["tails"],
                 tail_bound=layer["tail_bound"], apply_unconditional_transform=layer.get("unconditional", False)))
+        elif kind == "pcubic_coupling":
+            h, b = layer["hidden_features"], layer["num_blocks"]
+            create = lambda i, o, h=h, b=b: nets.ResidualNet(i, o, hidden_features=h, num_blocks=b)  # noqa: E731
+            layers.append(transforms.PiecewiseCubicCouplingTransform(
+                workloads.make_mask(features, layer["mask"]), create, num_bins=layer["num_bins"], tails=layer["tails"],
+                tail_bound=layer["tail_bound"], apply_unconditional_transform=layer.get("unconditional", False)))
         elif kind == "maf_pquad":
             layers.append(transforms.MaskedPiecewiseQuadraticAutoregressiveTransform(
                 features=features, hidden_features=layer["hidden_features"], context_features=ctx,
@@ -398,6 +404,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-cubic-functions":
         make_cubic_functions()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-cubic-models":
+        make_model("pcubic_coupling_small", with_grad=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-quadratic-functions":
         make_quadratic_functions()

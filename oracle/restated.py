@@ -435,6 +435,52 @@ def _cubic_root_in_bin(a, b, c, d, target, lo, hi, eps, quadratic_threshold):
     return out
 
 
+def unconstrained_cubic_spline(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left,
+                               unnorm_derivatives_right, inverse=False, tail_bound=1.0, tails="linear"):
+    """cubic.py:15-60: identity (logabsdet 0) outside [-tail_bound, tail_bound]."""
+    if tails != "linear":
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    inside = (inputs >= -tail_bound) & (inputs <= tail_bound)
+    outputs = torch.where(inside, torch.zeros_like(inputs), inputs)
+    logabsdet = torch.zeros_like(inputs)
+    if torch.any(inside):
+        o, l = cubic_spline(inputs[inside], unnormalized_widths[inside, :], unnormalized_heights[inside, :],
+                            unnorm_derivatives_left[inside, :], unnorm_derivatives_right[inside, :], inverse=inverse,
+                            left=-tail_bound, right=tail_bound, bottom=-tail_bound, top=tail_bound)
+        outputs = outputs.masked_scatter(inside, o)
+        logabsdet = logabsdet.masked_scatter(inside, l)
+    return outputs, logabsdet
+
+
+def cubic_elementwise(inputs, params, num_bins, tails, tail_bound, inverse, divisor):
+    """coupling.py:468-500: params [B, D_t * (2K+2)] viewed [B, D_t, 2K+2]; widths and heights / sqrt(hidden)."""
+    b, d = inputs.shape
+    params = params.reshape(b, d, -1)
+    uw, uh = params[..., :num_bins] / divisor, params[..., num_bins : 2 * num_bins] / divisor
+    dl, dr = params[..., 2 * num_bins][..., None], params[..., 2 * num_bins + 1][..., None]
+    if tails is None:
+        flat = [t.reshape(b * d, -1) for t in (uw, uh, dl, dr)]
+        y, lad = cubic_spline(inputs.reshape(b * d), *flat, inverse=inverse)
+        y, lad = y.reshape(b, d), lad.reshape(b, d)
+    else:
+        y, lad = unconstrained_cubic_spline(inputs, uw, uh, dl, dr, inverse=inverse, tails=tails, tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
+def cubic_cdf(state, prefix, inputs, num_bins, tails, tail_bound, inverse):
+    """PiecewiseCubicCDF._spline, nonlinearities.py:363-398: parameters shared across the batch."""
+    b = inputs.shape[0]
+    ps = [state[prefix + n].to(inputs.dtype)[None].expand(b, -1, -1) for n in
+          ("unnormalized_widths", "unnormalized_heights", "unnorm_derivatives_left", "unnorm_derivatives_right")]
+    if tails is None:
+        d = inputs.shape[1]
+        y, lad = cubic_spline(inputs.reshape(b * d), *[t.reshape(b * d, -1) for t in ps], inverse=inverse)
+        y, lad = y.reshape(b, d), lad.reshape(b, d)
+    else:
+        y, lad = unconstrained_cubic_spline(inputs, *ps, inverse=inverse, tails=tails, tail_bound=tail_bound)
+    return y, sum_except_batch(lad)
+
+
 def cubic_spline(inputs, unnormalized_widths, unnormalized_heights, unnorm_derivatives_left, unnorm_derivatives_right,
                  inverse=False, left=0.0, right=1.0, bottom=0.0, top=1.0, min_bin_width=1e-3, min_bin_height=1e-3,
                  eps=1e-5, quadratic_threshold=1e-3):
@@ -715,7 +761,8 @@ def _coupling(state, spec, inputs, context, inverse, elementwise):
     identity = inputs[:, idf]
     transform = inputs[:, trf]
     uncond = spec.get("unconditional", False)
-    cdf = {"plin_coupling": linear_cdf, "pquad_coupling": quadratic_cdf}.get(spec["kind"], rq_cdf)
+    cdf = {"plin_coupling": linear_cdf, "pquad_coupling": quadratic_cdf, "pcubic_coupling": cubic_cdf}.get(
+        spec["kind"], rq_cdf)
     lad_id = 0.0
     if uncond and inverse:
         identity, lad_id = cdf(state, p + "unconditional_transform.", identity, spec["num_bins"], spec.get("tails"),
@@ -765,6 +812,10 @@ def apply_layer(state, spec, inputs, context=None, inverse=False):
         def ew(x, params):
             return rq_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0),
                                   inverse, divisor, ident, constrained_bound=bound)
+    elif kind == "pcubic_coupling":
+        def ew(x, params):
+            return cubic_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0), inverse,
+                                     math.sqrt(spec["hidden_features"]))
     elif kind in ("pquad_coupling", "maf_pquad"):
         # coupling.py:409-411: widths and heights / sqrt(hidden) when the conditioner exposes it (ResidualNet yes, MADE no)
         div = math.sqrt(spec["hidden_features"]) if kind == "pquad_coupling" else 1.0
