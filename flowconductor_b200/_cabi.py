@@ -26,7 +26,10 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_linspline_apply", "fc_linsplin
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
+           "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_error",
            "fc_version", "fc_built_for_sm"]
+COND_MAX_LAYERS = 10
+COND_INITIAL, COND_BLOCK_FIRST, COND_BLOCK_SECOND, COND_FINAL = 0, 1, 2, 3
 
 
 class RqsConfig(ctypes.Structure):
@@ -53,6 +56,19 @@ class LinearWeights(ctypes.Structure):
     """struct fc_linear_weights"""
     _fields_ = [("w", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("n_pad", ctypes.c_int32),
                 ("k_pad", ctypes.c_int32)]
+
+
+class ConditionerLayer(ctypes.Structure):
+    """struct fc_conditioner_layer"""
+    _fields_ = [("kind", ctypes.c_int32), ("n_tiles", ctypes.c_int32), ("relu_next", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("w_offset", ctypes.c_int64), ("bias", ctypes.c_void_p),
+                ("winv", ctypes.c_void_p)]
+
+
+class Conditioner(ctypes.Structure):
+    """struct fc_conditioner"""
+    _fields_ = [("weights", ctypes.c_void_p), ("n_layers", ctypes.c_int32), ("hidden", ctypes.c_int32),
+                ("k_in", ctypes.c_int32), ("reserved", ctypes.c_int32), ("layers", ConditionerLayer * COND_MAX_LAYERS)]
 
 
 class LibraryMissing(RuntimeError):
@@ -103,10 +119,16 @@ def lib():
         L.fc_linear_splitk_t_apply.argtypes = [vp, i64, i64, i64, ctypes.POINTER(LinearWeights), i32, vp, i64, i64, i32, vp, vp]
         L.fc_linear_transpose.argtypes = [vp, i64, i64, i32, vp, i64, vp]
         L.fc_linear_pack_transposed.argtypes = [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp]
+        L.fc_conditioner_layer_bytes.argtypes = [i32, i32, i32]
+        L.fc_conditioner_pack_layer.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+        L.fc_conditioner_rqs_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, vp, i64, vp, i32, i32,
+                                               Cols, Cols, ctypes.POINTER(RqsConfig), vp, vp]
+        L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.fc_version.restype = ctypes.c_char_p
         for name in EXPORTS:
             if name not in ("fc_version",):
                 getattr(L, name).restype = ctypes.c_int
+        L.fc_conditioner_layer_bytes.restype = ctypes.c_int64
         _lib = L
     return _lib
 

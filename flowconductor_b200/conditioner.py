@@ -1,0 +1,143 @@
+"""Host side of the fused conditioner kernel (csrc/fc_conditioner.cu, C ABI `fc_conditioner_*`).
+
+`PackedConditioner` is the packed form of a whole ResidualNet (flowcon/nn/nets/resnet.py:59-100) or residual MADE
+(flowcon/transforms/made.py:205-283): every layer's weights as fp16 (hi, lo) planes in the shared-memory image of the
+kernel's weight ring, in one buffer, plus the per-layer bias / inverse-scale vectors and the layer table
+(`struct fc_conditioner`).  `rqs_apply` launches conditioner + rational-quadratic spline as ONE kernel on torch's current
+stream.  No fallback: CPU tensors or a missing library raise.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+HIDDEN_WIDTHS = (128, 256)
+MAX_K_IN = 256
+RQS_PPAD = {8: 24, 16: 48}
+MAX_BLOCKS = (_cabi.COND_MAX_LAYERS - 2) // 2
+
+
+def _ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+class PackedConditioner:
+    """Packed weights of a whole conditioner.  Keeps the device buffers alive; `struct` is what the C ABI takes."""
+
+    def __init__(self, weights, vectors, struct, hidden, k_in, n_final_tiles, num_bins):
+        self.weights, self.vectors, self.struct = weights, vectors, struct
+        self.hidden, self.k_in, self.n_final_tiles, self.num_bins = hidden, k_in, n_final_tiles, num_bins
+
+
+def _pack_layer(L, dev, blob, offset, layer, mask, n_pad, k_pad, bn, row_map=None, col_map=None):
+    w = _cabi.require_cuda_f32(layer.weight.detach(), "weight")
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    N, K = w.shape
+    b = layer.bias
+    if b is not None:
+        b = _cabi.require_cuda_f32(b.detach(), "bias").contiguous()
+    if mask is not None:
+        mask = _cabi.require_cuda_f32(mask.detach(), "mask")
+        if mask.stride(1) != 1:
+            mask = mask.contiguous()
+    vec = torch.empty((2, n_pad), dtype=torch.float32, device=dev)
+    for m in (row_map, col_map):
+        if m is not None:
+            assert m.dtype == torch.int32 and m.is_cuda and m.is_contiguous()
+    with _cabi.launch("fc_conditioner_pack_layer", dev):
+        rc = L.fc_conditioner_pack_layer(w.data_ptr(), w.stride(0), mask.data_ptr() if mask is not None else None,
+                                         mask.stride(0) if mask is not None else 0,
+                                         b.data_ptr() if b is not None else None, N, K,
+                                         row_map.data_ptr() if row_map is not None else None,
+                                         col_map.data_ptr() if col_map is not None else None, n_pad, k_pad, bn,
+                                         blob.data_ptr() + offset, vec[0].data_ptr(), vec[1].data_ptr(),
+                                         _cabi.stream_ptr(dev))
+    _cabi.check(rc, "fc_conditioner_pack_layer")
+    return vec
+
+
+def supported_shape(hidden, k_in, num_blocks, num_bins):
+    return (hidden in HIDDEN_WIDTHS and 0 < k_in <= MAX_K_IN and k_in % 4 == 0 and 1 <= num_blocks <= MAX_BLOCKS
+            and num_bins in RQS_PPAD)
+
+
+def pack_rqs(net, num_bins, d_t, col_map=None, k_in=None):
+    """Pack `net` (initial_layer, blocks[*].linear_layers[0..1], final_layer; optional `.mask` per layer, made.py:72)
+    for `fc_conditioner_rqs_apply`.  col_map / k_in: scatter of the first layer's input columns (a coupling layer's
+    conditioner reads the full-width inputs: coupling.py:82-86 folded into the weights)."""
+    L = _cabi.lib()
+    init, fin = net.initial_layer, net.final_layer
+    dev = init.weight.device
+    hidden = init.weight.shape[0]
+    k_in = init.weight.shape[1] if k_in is None else k_in
+    nb = len(net.blocks)
+    if not supported_shape(hidden, k_in, nb, num_bins):
+        raise ValueError("conditioner shape not supported by the fused kernel")
+    P, ppad = 3 * num_bins - 1, RQS_PPAD[num_bins]
+    if fin.weight.shape[0] != d_t * P:
+        raise ValueError("final layer has {} outputs, expected {} x {}".format(fin.weight.shape[0], d_t, P))
+    feats = 96 // ppad
+    n_final_tiles = (d_t + feats - 1) // feats
+    layers = [(init, _cabi.COND_INITIAL, 128, _ceil_to(k_in, 64), hidden)]
+    for blk in net.blocks:
+        layers.append((blk.linear_layers[0], _cabi.COND_BLOCK_FIRST, 128, hidden, hidden))
+        layers.append((blk.linear_layers[1], _cabi.COND_BLOCK_SECOND, 128, hidden, hidden))
+    layers.append((fin, _cabi.COND_FINAL, 96, hidden, n_final_tiles * 96))
+    sizes = [int(L.fc_conditioner_layer_bytes(n_pad, k_pad, bn)) for (_, _, bn, k_pad, n_pad) in layers]
+    assert all(s > 0 for s in sizes)
+    blob = torch.empty((sum(sizes),), dtype=torch.uint8, device=dev)
+    assert blob.data_ptr() % 16 == 0
+    st = _cabi.Conditioner()
+    st.weights = blob.data_ptr()
+    st.n_layers, st.hidden, st.k_in = len(layers), hidden, k_in
+    vectors = []
+    offset = 0
+    with torch.cuda.device(dev):
+        for i, ((layer, kind, bn, k_pad, n_pad), size) in enumerate(zip(layers, sizes)):
+            row_map = None
+            if kind == _cabi.COND_FINAL:
+                j = torch.arange(d_t, device=dev).repeat_interleave(P)
+                ii = torch.arange(P, device=dev).repeat(d_t)
+                row_map = (j * ppad + ii).to(torch.int32)
+            vec = _pack_layer(L, dev, blob, offset, layer, getattr(layer, "mask", None), n_pad, k_pad, bn, row_map=row_map,
+                              col_map=col_map if kind == _cabi.COND_INITIAL else None)
+            vectors.append(vec)
+            e = st.layers[i]
+            e.kind, e.n_tiles = kind, n_pad // bn
+            # the next layer multiplies relu(result) unless it is the final layer (resnet.py:99 / made.py:282: the final
+            # layer reads the residual stream itself) or this is the final layer
+            nxt = layers[i + 1][1] if i + 1 < len(layers) else None
+            e.relu_next = int(nxt in (_cabi.COND_BLOCK_FIRST, _cabi.COND_BLOCK_SECOND))
+            e.w_offset = offset
+            e.bias, e.winv = vec[0].data_ptr(), vec[1].data_ptr()
+            offset += size
+    return PackedConditioner(blob, vectors, st, hidden, k_in, n_final_tiles, num_bins)
+
+
+def rqs_apply(packed, a, x, y, logabsdet, accumulate, d_t, tcols, ccols, cfg, status=None):
+    """Whole conditioner + rational-quadratic spline in one kernel (fc_conditioner_rqs_apply).  a: [B, k_in] matrix the
+    initial layer multiplies; writes y[:, tcols] (and y[:, ccols] = x[:, ccols] unless y is x) and logabsdet."""
+    _cabi.require_cuda_f32(a, "conditioner inputs")
+    _cabi.require_cuda_f32(x, "inputs")
+    L = _cabi.lib()
+    a, ap, lda = _cabi.rows(a)
+    if a.shape[1] != packed.k_in:
+        raise ValueError("conditioner inputs have {} columns, the packed net expects {}".format(a.shape[1], packed.k_in))
+    assert x.stride(1) == 1 and y.stride(1) == 1 and logabsdet.is_contiguous()
+    B = a.shape[0]
+    with torch.cuda.device(x.device), _cabi.launch("fc_conditioner_rqs_apply", x.device):
+        rc = L.fc_conditioner_rqs_apply(ctypes.byref(packed.struct), ap, lda, B, x.data_ptr(), x.stride(0), y.data_ptr(),
+                                        y.stride(0), logabsdet.data_ptr(), int(accumulate), d_t, _cabi.cols(tcols),
+                                        _cabi.cols(ccols), ctypes.byref(cfg),
+                                        status.data_ptr() if status is not None else None, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_conditioner_rqs_apply")
+    return y, logabsdet
+
+
+def kernel_error():
+    """Non-zero if a barrier wait inside the last fused kernels timed out (synchronises; debugging aid)."""
+    out = ctypes.c_int32(0)
+    _cabi.check(_cabi.lib().fc_conditioner_error(ctypes.byref(out)), "fc_conditioner_error")
+    return out.value

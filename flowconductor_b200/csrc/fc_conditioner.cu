@@ -1,0 +1,811 @@
+// fc_conditioner.cu — a WHOLE conditioner network and the bijection it parameterises in ONE persistent kernel
+// (DESIGN.md 4.12).
+//
+// Replaces, per flow layer, ResidualNet.forward (flowcon/nn/nets/resnet.py:92-100: initial layer, pre-activation
+// residual blocks :39-56, final layer) or the residual MADE (flowcon/transforms/made.py:274-283, blocks :170-181,
+// MaskedLinear :71-72) TOGETHER WITH the rational-quadratic spline that consumes its output
+// (flowcon/transforms/splines/rational_quadratic.py:13-181 through coupling.py:549-582 / autoregressive.py:578-615).
+// The per-layer kernels of fc_linear.cu write every [B, H] activation to HBM and read it back (12.8 GB per flow layer
+// at cfg 2); here a 128-row activation tile never leaves the SM:
+//
+//   registers      fp32 accumulators of the layer being computed (one thread = one row x 64 columns per N tile)
+//   tensor memory  the layer's A operand [128 rows x K <= 256] as fp16 (hi, lo) planes (256 columns), and two partial
+//                  accumulators of 128 columns (256 columns)
+//   shared memory  the residual stream h [256 columns][128 rows] fp32 (128 KB, touched only by the thread that owns
+//                  the entry), a ring of weight slots streamed from L2 by 1-D TMA bulk copies, barriers
+//
+// Arithmetic: "3xFP16".  The reference computes these products in fp32.  Every operand is split a = hi + lo with hi, lo
+// fp16 (11 significant bits each, like the tf32 split of fc_linear.cu) after scaling by an exact power of two — per
+// (row, 64-value chunk) for the activations, per output row for the weights — so that the largest magnitude sits in
+// [2^13, 2^14): hi + lo then reproduces the scaled value to 2^-22 relative (2^-38 of the chunk's maximum for small
+// entries), and nothing overflows fp16.  Products  lo*hi + hi*lo + hi*hi  run as tcgen05.mma.kind::f16 (twice the
+// tf32 rate, measured: scripts/microbench/tmem_rate.cu) into an fp32 accumulator in tensor memory.  As in
+// fc_linear.cu the tensor core truncates on accumulation, so every 64 k-values (12 MMAs) the partial sum is handed
+// to the row's thread, which adds  partial * 2^-e(row, chunk)  into a register accumulator with round-to-nearest while
+// the next partial is computed in the other TMEM buffer; the weight scale 2^-e(n) is applied together with the bias.
+//
+// The thread that owns (row, 64 columns) applies bias / skip connection / ReLU to its finished values, converts them
+// to the (hi, lo) operand of the NEXT layer and writes that straight into tensor memory (tcgen05.st): there are no
+// converter warps and no activation traffic at all.  The final layer runs in N tiles of 96 columns (4 features x 24
+// padded parameters for 8 bins, 2 x 48 for 16 bins); its rows' threads evaluate the spline of N tile j between the
+// partial-accumulator drains of N tile j + 1, and the last N tile's splines after the NEXT row tile's first operand has
+// been handed to the tensor core, so the tensor pipe does not wait for the bijection.
+//
+// CTA pairs (cta_group::2): one MMA covers 256 rows (128 per SM); each SM stages half of every weight slot.
+// Warps: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 3 relay ("my half of the slot has landed" to
+// the leader), 4-11 row threads.  Every mbarrier wait is bounded (kTimeoutCycles): a protocol error ends the kernel
+// with a code in the error word instead of hanging the GPU.
+#include <atomic>
+#include <cuda_fp16.h>
+
+#include "fc_common.cuh"
+#include "fc_tc.cuh"
+
+namespace fc {
+
+using namespace tc;
+
+constexpr int kCM = 128;              // rows per CTA (= TMEM lanes)
+constexpr int kSlotBytes = 16384;     // ring slot per CTA: (hi | lo) planes of <= 64 weight rows x 64 fp16
+constexpr int kCondStages = 5;
+constexpr int kCondThreads = 384;     // 4 control warps + 8 row warps
+constexpr int kMaxCondLayers = FC_COND_MAX_LAYERS;
+constexpr uint32_t kTmemAcc = 0;      // two partial accumulators, 128 columns apart
+constexpr uint32_t kTmemA = 256;      // operand: hi plane (128 columns = 256 fp16), lo plane 128 columns further
+constexpr long long kTimeoutCycles = 4000000000ll;
+
+struct CondLayerDev {
+  int n_tiles;       // N tiles of the layer
+  int bn;            // columns per N tile: 128 (hidden layers), 96 (final layer)
+  int k_chunks;      // 64-value reduction chunks = ring slots per N tile
+  int k_steps_last;  // 16-value MMA steps in the last chunk (1..4)
+  int kind;          // FC_COND_*: 0 initial (h = out), 1 first of a block (operand only), 2 second of a block (h += out),
+                     // 3 final (parameters)
+  int relu_next;     // the next layer's operand is relu(result)
+  unsigned w_off16;  // first slot of the layer inside the packed weights, in 16-byte units
+  unsigned cta_bytes;  // bytes per slot and CTA: 2 planes x bn/2 rows x 128 B
+  const float* bias;   // [n_tiles * bn]
+  const float* winv;   // [n_tiles * bn] exact powers of two: 1 / weight-row scale
+};
+
+struct CondArgs {
+  const unsigned char* weights;
+  const float* a;  // conditioner input [M, k_in] row-major
+  long long lda;
+  int k_in;
+  long long M;
+  int num_tiles;  // 256-row tiles (one per CTA pair and step)
+  int n_layers;
+  int slots_per_tile;
+  CondLayerDev L[kMaxCondLayers];
+  // bijection
+  const float* x;
+  long long ldx;
+  float* y;
+  long long ldy;
+  float* lad;
+  int accumulate;
+  const int32_t* tcols;
+  const int32_t* ccols;
+  int n_copy;
+  int D_t;
+  RqsParams c;
+  int32_t* status;
+  int32_t* error;  // device word: 0, or the code of the first wait that timed out
+};
+
+__device__ int32_t g_cond_error;
+
+template <int N>
+__device__ __forceinline__ void cond_set_max_regs_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void cond_set_max_regs_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {  // A, B = f16 (format 0), D = f32, K-major
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 256 x N x 16 across the pair, A (this CTA's 128 rows, 8 packed f16x2 columns) from tensor memory
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Bounded waits.  `abort_s` is a shared-memory flag of this CTA: once any role has given up, the others stop waiting too.
+__device__ __forceinline__ bool cond_wait(uint32_t bar, uint32_t parity, volatile int* abort_s) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*abort_s != 0 || clock64() - t0 > kTimeoutCycles) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ bool try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool cond_wait_cluster(uint32_t bar, uint32_t parity, volatile int* abort_s) {
+  if (try_wait_cluster(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!try_wait_cluster(bar, parity)) {
+    if (*abort_s != 0 || clock64() - t0 > kTimeoutCycles) return false;
+  }
+  return true;
+}
+
+// acc[0..N) += inv_s * (N consecutive TMEM columns of this thread's lane); 16 columns per tcgen05.ld, the FMAs of group j
+// run while the load of group j + 1 is in flight
+template <int N>
+__device__ __forceinline__ void drain_scaled(uint32_t taddr, float inv_s, float* acc) {
+  static_assert(N % 16 == 0, "16 columns per load");
+  uint32_t v[2][16];
+  tmem_ld16(taddr, v[0]);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < N; j += 16) {
+    const int cur = (j >> 4) & 1;
+    if (j + 16 < N) tmem_ld16(taddr + (uint32_t)(j + 16), v[cur ^ 1]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[j + i] = fmaf(__uint_as_float(v[cur][i]), inv_s, acc[j + i]);
+    if (j + 16 < N) tmem_wait_ld();
+  }
+}
+
+// 64 fp32 values of one row -> the (hi, lo) fp16 planes of operand chunk `chunk` in tensor memory, scaled by the power
+// of two that puts the largest magnitude into [2^13, 2^14).  Returns 1 / scale (exact).
+__device__ __forceinline__ float produce_chunk(const float* v, uint32_t ta_chunk /* TMEM address of the hi plane */) {
+  float m = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) m = fmaxf(m, fabsf(v[j]));
+  m = fmaxf(m, 1e-30f);
+  const uint32_t E = __float_as_uint(m) >> 23;  // biased exponent (m > 0)
+  const float s = __uint_as_float((267u - E) << 23);      // 2^(13 - (E - 127))
+  const float inv_s = __uint_as_float((E - 13u) << 23);   // 2^((E - 127) - 13)
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+      const float a0 = v[g * 32 + 2 * p] * s, a1 = v[g * 32 + 2 * p + 1] * s;
+      const __half2 h2 = __floats2half2_rn(a0, a1);  // k even in the low half
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      hi[p] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[p] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    tmem_st16(ta_chunk + (uint32_t)(g * 16), hi);
+    tmem_st16(ta_chunk + 128u + (uint32_t)(g * 16), lo);
+  }
+  return inv_s;
+}
+
+struct CondSmem {
+  static constexpr int RING_BYTES = kCondStages * kSlotBytes;
+  static constexpr int H_BYTES = 256 * kCM * 4;      // residual stream [256 columns][128 rows]
+  static constexpr int SC_BYTES = 2 * 4 * kCM * 4;   // 1 / operand scale: [layer parity][chunk][row]
+  static constexpr int LAD_BYTES = kCM * 4;
+  static constexpr int BAR_BYTES = 8 * (3 * kCondStages + 7) + 16;
+  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + BAR_BYTES + 1024;
+};
+
+// KC bins, PPAD accumulator columns per feature, NT = hidden width / 128
+template <int KC, int PPAD, int NT>
+__global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(const CondArgs a) {
+  constexpr int KCH = 2 * NT;         // 64-value chunks of a hidden-width reduction
+  constexpr int FEATS = 96 / PPAD;    // features per final N tile
+  constexpr int NF = FEATS / 2;       // ... per thread (two threads share a row)
+  static_assert(NF >= 1 && NF * 2 * PPAD == 96, "final N tile: 96 columns");
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_s = s32(smem_raw);
+  const uint32_t base = (raw_s + 1023u) & ~1023u;
+  unsigned char* const gbase = smem_raw + (base - raw_s);
+  float* const hs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES);
+  float* const scs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES + CondSmem::H_BYTES);
+  float* const ladx = scs + 2 * 4 * kCM;
+  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + CondSmem::LAD_BYTES;
+  unsigned char* const gbars = gbase + (bars - base);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto ready_bar = [&](int s) { return bars + 8u * (kCondStages + s); };   // leader's: both halves have landed
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * kCondStages + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (3 * kCondStages + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (3 * kCondStages + 2 + i); };  // leader's
+  auto opnd_bar = [&](int g) { return bars + 8u * (3 * kCondStages + 4 + g); };    // leader's
+  const uint32_t lad_bar = bars + 8u * (3 * kCondStages + 6);  // the second column half's log-det partials are written
+  const uint32_t tmem_slot = bars + 8u * (3 * kCondStages + 7);
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbars + 8 * (3 * kCondStages + 7));
+  volatile int* const abort_s = reinterpret_cast<volatile int*>(gbars + 8 * (3 * kCondStages + 7) + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cl0 = (int)blockIdx.x >> 1, cl_step = (int)gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    *abort_s = 0;
+    for (int s = 0; s < kCondStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 16);  // 8 row warps of each CTA
+      mbar_init(opnd_bar(i), 16);
+    }
+    mbar_init(lad_bar, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+#define COND_FAIL(code)                                  \
+  {                                                      \
+    *abort_s = 1;                                        \
+    atomicCAS(a.error, 0, (int)(code) + 100 * warp);     \
+    goto teardown;                                       \
+  }
+
+  if (warp < 4) {
+    cond_set_max_regs_dec<40>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- weight producer
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
+          for (int l = 0; l < a.n_layers; ++l) {
+            const CondLayerDev& L = a.L[l];
+            const unsigned char* src = a.weights + ((size_t)L.w_off16 << 4) + (size_t)rank * L.cta_bytes;
+            const int n_slots = L.n_tiles * L.k_chunks;
+            for (int i = 0; i < n_slots; ++i) {
+              if (!cond_wait_cluster(empty_bar(s), ph ^ 1u, abort_s)) COND_FAIL(1);
+              mbar_expect_tx(full_bar(s), L.cta_bytes);
+              bulk_load_1d(base + (uint32_t)(s * kSlotBytes), src, L.cta_bytes, full_bar(s));
+              src += 2 * (size_t)L.cta_bytes;
+              if (++s == kCondStages) {
+                s = 0;
+                ph ^= 1u;
+              }
+            }
+          }
+          // next row tile's conditioner input -> L2 while this one is computed (contiguous rows only)
+          const int nxt = tile + cl_step;
+          if (nxt < a.num_tiles && a.lda == a.k_in) {
+            const long long r0 = (long long)nxt * 256 + rank * kCM;
+            long long rows = a.M - r0;
+            rows = rows > kCM ? kCM : rows;
+            if (rows > 0) bulk_prefetch_l2(a.a + r0 * a.lda, (uint32_t)(rows * a.lda * 4));
+          }
+        }
+      }
+    } else if (warp == 3) {
+      // ---------------------------------------------------------------- relay: this CTA's half of a slot has landed
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
+          for (int i = 0; i < a.slots_per_tile; ++i) {
+            if (!cond_wait(full_bar(s), ph, abort_s)) COND_FAIL(2);
+            if (rank == 0) {
+              mbar_arrive(ready_bar(s));
+            } else {
+              mbar_arrive_remote_relaxed(ready_bar(s), 0);
+            }
+            if (++s == kCondStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (whole warp walks, one lane issues)
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0, lcount = 0;
+      const uint64_t b0 = make_smem_desc(base, 128);
+      for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
+        for (int l = 0; l < a.n_layers; ++l, ++lcount) {
+          const CondLayerDev& L = a.L[l];
+          const uint32_t idesc = make_idesc_f16(2 * kCM, L.bn);
+          const uint64_t lo_off = (uint64_t)((L.cta_bytes >> 1) >> 4);
+          for (int nt = 0; nt < L.n_tiles; ++nt) {
+            for (int c = 0; c < L.k_chunks; ++c) {
+              if (nt == 0 && (c & 1) == 0) {  // operand chunks c, c + 1 written (by both CTAs)
+                if (!cond_wait_cluster(opnd_bar(c >> 1), lcount & 1u, abort_s)) COND_FAIL(3);
+              }
+              if (!cond_wait_cluster(tempty_bar(acc), aph ^ 1u, abort_s)) COND_FAIL(4);
+              if (!cond_wait_cluster(ready_bar(s), ph, abort_s)) COND_FAIL(5);
+              tc_fence_after();
+              const int steps = (c == L.k_chunks - 1) ? L.k_steps_last : 4;
+              const uint64_t b_hi = b0 + (uint64_t)((uint32_t)s * (uint32_t)(kSlotBytes >> 4)), b_lo = b_hi + lo_off;
+              const uint32_t d = tmem_base + kTmemAcc + (uint32_t)(acc * 128);
+              const uint32_t a_hi = tmem_base + kTmemA + (uint32_t)(c * 32), a_lo = a_hi + 128u;
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (kk < steps) {
+                    const uint64_t o = (uint64_t)(kk * 2);  // 16 fp16 = 32 bytes inside the swizzle span
+                    // small terms first
+                    umma_f16_ts_pair(d, a_lo + (uint32_t)(kk * 8), b_hi + o, idesc, kk > 0 ? 1u : 0u);
+                    umma_f16_ts_pair(d, a_hi + (uint32_t)(kk * 8), b_lo + o, idesc, 1u);
+                    umma_f16_ts_pair(d, a_hi + (uint32_t)(kk * 8), b_hi + o, idesc, 1u);
+                  }
+                }
+                umma_commit_pair(empty_bar(s), 3);
+                umma_commit_pair(tfull_bar(acc), 3);
+              }
+              __syncwarp();
+              if (++s == kCondStages) {
+                s = 0;
+                ph ^= 1u;
+              }
+              if (++acc == 2) {
+                acc = 0;
+                aph ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ row threads
+    cond_set_max_regs_inc<232>();
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int rl = q * 32 + lane;  // row inside the CTA's tile = TMEM lane
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    int acc_i = 0;
+    uint32_t aph = 0, lcount = 0, lph = 0;
+    unsigned status = 0;
+    // pending bijection work: the parameters of the last finished final-layer N tile
+    float pp[NF * PPAD];
+    float pxv[NF];
+    int pxc[NF];
+    bool plive[NF];
+    long long prow = 0;
+    bool pvalid = false, pending = false;
+    float lad_acc = 0.f;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      pxv[f] = 0.f;
+      pxc[f] = 0;
+      plive[f] = false;
+    }
+#pragma unroll
+    for (int j = 0; j < NF * PPAD; ++j) pp[j] = 0.f;
+
+    auto signal_operand = [&]() {
+      tmem_wait_st();
+      __threadfence_block();  // the scale words written next to the operand
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_remote_relaxed(opnd_bar(0), 0);
+        mbar_arrive_remote_relaxed(opnd_bar(1), 0);
+      }
+    };
+    auto spline = [&](int f) {
+      if (plive[f]) {
+        float yv, lv;
+        rqs_eval<KC, true>(a.c, pxv[f], pp + f * PPAD, yv, lv, status);
+        if (pvalid) a.y[prow * a.ldy + pxc[f]] = yv;
+        lad_acc += lv;
+      }
+    };
+
+    for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
+      const long long row = (long long)tile * 256 + rank * kCM + rl;
+      const bool valid = row < a.M;
+      // ---- operand of the initial layer: this row of the conditioner input, chunks half, half + 2
+      {
+        const CondLayerDev& L0 = a.L[0];
+        float* sc_next = scs + (lcount & 1u) * (4 * kCM);
+        for (int c = half; c < L0.k_chunks; c += 2) {
+          float v[64];
+          const float* src = a.a + row * a.lda + c * 64;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && c * 64 + 4 * j < a.k_in) t = __ldg(reinterpret_cast<const float4*>(src) + j);
+            v[4 * j + 0] = t.x;
+            v[4 * j + 1] = t.y;
+            v[4 * j + 2] = t.z;
+            v[4 * j + 3] = t.w;
+          }
+          sc_next[c * kCM + rl] = produce_chunk(v, tmem_base + lane_sel + kTmemA + (uint32_t)(c * 32));
+        }
+        signal_operand();
+      }
+      // ---- finish the previous row tile while the initial layer's MMAs run
+      if (pending) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) spline(f);
+        // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): the two column halves of a row are
+        // combined in a fixed order
+        if (half == 1) {
+          ladx[rl] = lad_acc;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(lad_bar);  // release: orders the 32 stores above
+        } else {
+          if (!cond_wait(lad_bar, lph, abort_s)) COND_FAIL(8);
+          if (pvalid) {
+            const float tot = lad_acc + ladx[rl];
+            a.lad[prow] = a.accumulate ? a.lad[prow] + tot : tot;
+          }
+        }
+        lph ^= 1u;
+        lad_acc = 0.f;
+        pending = false;
+      }
+      // identity columns (coupling.py:96-98) when the layer does not work in place
+      if (a.n_copy > 0 && a.y != a.x && half == 0) {
+        const long long row0 = (long long)tile * 256 + rank * kCM + q * 32;
+        for (int i0 = 0; i0 < a.n_copy; i0 += 32) {
+          const int cc = (i0 + lane < a.n_copy) ? __ldg(a.ccols + i0 + lane) : -1;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            if (cc >= 0 && row0 + r < a.M) a.y[(row0 + r) * a.ldy + cc] = __ldg(a.x + (row0 + r) * a.ldx + cc);
+          }
+        }
+      }
+      // ---- hidden layers
+      for (int l = 0; l < a.n_layers - 1; ++l, ++lcount) {
+        const CondLayerDev& L = a.L[l];
+        const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
+        float* sc_next = scs + ((lcount + 1u) & 1u) * (4 * kCM);
+        float av[NT * 64];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) av[nt * 64 + j] = 0.f;
+          for (int c = 0; c < L.k_chunks; ++c) {
+            if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(6);
+            tc_fence_after();
+            const float inv_s = sc_cur[c * kCM + rl];
+            drain_scaled<64>(tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + half * 64), inv_s, av + nt * 64);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote_relaxed(tempty_bar(acc_i), 0);
+            if (++acc_i == 2) {
+              acc_i = 0;
+              aph ^= 1u;
+            }
+          }
+          // bias, weight scale, skip connection, ReLU
+          const int n0 = nt * 128 + half * 64;
+          const float4* b4 = reinterpret_cast<const float4*>(L.bias + n0);
+          const float4* w4 = reinterpret_cast<const float4*>(L.winv + n0);
+          float* hcol = hs + n0 * kCM + rl;
+          const bool add_h = L.kind == FC_COND_BLOCK_SECOND, put_h = L.kind != FC_COND_BLOCK_FIRST;
+          const bool relu = L.relu_next != 0;
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 b = __ldg(b4 + j4), w = __ldg(w4 + j4);
+            const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * j4 + i;
+              float v = fmaf(av[nt * 64 + j], ww[i], bb[i]);
+              if (add_h) v += hcol[j * kCM];
+              if (put_h) hcol[j * kCM] = v;
+              av[nt * 64 + j] = relu ? fmaxf(v, 0.f) : v;
+            }
+          }
+        }
+        // every MMA of this layer has completed (the last partial accumulator has been drained): the operand in
+        // tensor memory may be overwritten with the next layer's
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int cidx = nt * 2 + half;
+          sc_next[cidx * kCM + rl] = produce_chunk(av + nt * 64, tmem_base + lane_sel + kTmemA + (uint32_t)(cidx * 32));
+        }
+        signal_operand();
+      }
+      // ---- final layer: N tiles of 96 parameter columns; the spline of N tile j - 1 runs between the drains of N tile j
+      {
+        const CondLayerDev& L = a.L[a.n_layers - 1];
+        const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
+        for (int nt = 0; nt < L.n_tiles; ++nt) {
+          float pv[NF * PPAD];
+          float xv[NF];
+          int xc[NF];
+          bool live[NF];
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            const int fg = nt * FEATS + half * NF + f;
+            live[f] = fg < a.D_t;
+            xc[f] = live[f] ? (a.tcols ? __ldg(a.tcols + fg) : fg) : 0;
+            xv[f] = (valid && live[f]) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < NF * PPAD; ++j) pv[j] = 0.f;
+#pragma unroll
+          for (int c = 0; c < KCH; ++c) {
+            if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(7);
+            tc_fence_after();
+            const float inv_s = sc_cur[c * kCM + rl];
+            drain_scaled<NF * PPAD>(tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + half * (NF * PPAD)), inv_s, pv);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote_relaxed(tempty_bar(acc_i), 0);
+            if (++acc_i == 2) {
+              acc_i = 0;
+              aph ^= 1u;
+            }
+            if (pending && (c * NF) % KCH == 0) spline((c * NF) / KCH);
+          }
+          const int n0 = nt * 96 + half * (NF * PPAD);
+          const float4* b4 = reinterpret_cast<const float4*>(L.bias + n0);
+          const float4* w4 = reinterpret_cast<const float4*>(L.winv + n0);
+#pragma unroll
+          for (int j4 = 0; j4 < NF * PPAD / 4; ++j4) {
+            const float4 b = __ldg(b4 + j4), w = __ldg(w4 + j4);
+            pp[4 * j4 + 0] = fmaf(pv[4 * j4 + 0], w.x, b.x);
+            pp[4 * j4 + 1] = fmaf(pv[4 * j4 + 1], w.y, b.y);
+            pp[4 * j4 + 2] = fmaf(pv[4 * j4 + 2], w.z, b.z);
+            pp[4 * j4 + 3] = fmaf(pv[4 * j4 + 3], w.w, b.w);
+          }
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            pxv[f] = xv[f];
+            pxc[f] = xc[f];
+            plive[f] = live[f];
+          }
+          prow = row;
+          pvalid = valid;
+          pending = true;
+        }
+        ++lcount;
+      }
+    }
+    if (pending) {
+#pragma unroll
+      for (int f = 0; f < NF; ++f) spline(f);
+      if (half == 1) {
+        ladx[rl] = lad_acc;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lad_bar);
+      } else {
+        if (!cond_wait(lad_bar, lph, abort_s)) COND_FAIL(9);
+        if (pvalid) {
+          const float tot = lad_acc + ladx[rl];
+          a.lad[prow] = a.accumulate ? a.lad[prow] + tot : tot;
+        }
+      }
+    }
+    if (status != 0 && a.status) atomicOr(a.status, (int)status);
+  }
+
+teardown:
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its partner can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+#undef COND_FAIL
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Packing: one nn.Linear / MaskedLinear -> ring slots of fp16 (hi, lo) planes in the shared-memory image the MMA reads
+// (K-major rows of 64 fp16 = 128 bytes, 16-byte chunks XOR-swizzled with the row index: the 128-byte swizzle), one
+// slot per (N tile, 64-value chunk), each slot [rank 0: hi | lo][rank 1: hi | lo].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void cond_pack_init_kernel(float* bias_out, float* winv_out, int n_pad) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    bias_out[i] = 0.f;
+    winv_out[i] = 1.f;
+  }
+}
+
+// one block per source weight row
+__global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ mask,
+                                                        int64_t ldm, const float* __restrict__ bias,
+                                                        const int32_t* __restrict__ row_map,
+                                                        const int32_t* __restrict__ col_map, int N, int K, int bn,
+                                                        int k_chunks, unsigned char* __restrict__ out,
+                                                        float* __restrict__ bias_out, float* __restrict__ winv_out) {
+  __shared__ float red[4];
+  const int n = blockIdx.x;
+  float m = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float w = W[n * ldw + k];
+    if (mask) w *= mask[n * ldm + k];  // MaskedLinear: weight * mask (made.py:72)
+    m = fmaxf(m, fabsf(w));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float s = 1.f, inv_s = 1.f;
+  if (m > 1e-30f && m < 1e30f) {
+    const uint32_t E = __float_as_uint(m) >> 23;
+    s = __uint_as_float((267u - E) << 23);
+    inv_s = __uint_as_float((E - 13u) << 23);
+  }
+  const int rn = row_map ? row_map[n] : n;
+  const int bnh = bn >> 1;
+  const int nt = rn / bn, r_in = rn % bn, rank = r_in / bnh, r = r_in % bnh;
+  const size_t cta_bytes = (size_t)2 * bnh * 128;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float w = W[n * ldw + k];
+    if (mask) w *= mask[n * ldm + k];
+    w *= s;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    const int ck = col_map ? col_map[k] : k;
+    const int c = ck >> 6, kk = ck & 63;
+    const size_t slot = ((size_t)(nt * k_chunks + c) * 2 + rank) * cta_bytes;
+    const size_t off = (size_t)r * 128 + (size_t)((((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2);
+    *reinterpret_cast<__half*>(out + slot + off) = hi;
+    *reinterpret_cast<__half*>(out + slot + (size_t)bnh * 128 + off) = lo;
+  }
+  if (threadIdx.x == 0) {
+    bias_out[rn] = bias ? bias[n] : 0.f;
+    winv_out[rn] = inv_s;
+  }
+}
+
+template <int KC, int PPAD, int NT>
+static int launch_conditioner(const CondArgs& args, cudaStream_t stream) {
+  auto kern = conditioner_f16x3_kernel<KC, PPAD, NT>;
+  static_assert(CondSmem::TOTAL <= 232448, "shared memory per CTA");
+  static std::atomic<uint64_t> configured{0};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  const uint64_t dev_bit = 1ull << (dev_id & 63);
+  if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CondSmem::TOTAL) != cudaSuccess)
+      return FC_ERR_CUDA;
+    configured.fetch_or(dev_bit, std::memory_order_release);
+  }
+  const int max_pairs = device_info().sm_count / 2;
+  const int pairs = args.num_tiles < max_pairs ? args.num_tiles : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(kCondThreads);
+  cfg.dynamicSmemBytes = CondSmem::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, args) != cudaSuccess) return FC_ERR_CUDA;
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int64_t fc_conditioner_layer_bytes(int32_t n_pad, int32_t k_pad, int32_t bn) {
+  if (n_pad <= 0 || k_pad <= 0 || (bn != 128 && bn != 96) || n_pad % bn != 0 || k_pad % 64 != 0) return FC_ERR_INVALID_ARGUMENT;
+  return (int64_t)(n_pad / bn) * (k_pad / 64) * 2 * (2 * (bn / 2) * 128);
+}
+
+extern "C" int fc_conditioner_pack_layer(const float* W, int64_t w_row_stride, const float* mask, int64_t mask_row_stride,
+                                         const float* bias, int32_t N, int32_t K, const int32_t* row_map,
+                                         const int32_t* col_map, int32_t n_pad, int32_t k_pad, int32_t bn, void* w_packed,
+                                         float* bias_packed, float* winv_packed, void* stream) {
+  if (!W || !w_packed || !bias_packed || !winv_packed || N <= 0 || K <= 0 || n_pad < N || k_pad < K)
+    return FC_ERR_INVALID_ARGUMENT;
+  const int64_t bytes = fc_conditioner_layer_bytes(n_pad, k_pad, bn);
+  if (bytes < 0) return (int)bytes;
+  if (reinterpret_cast<uintptr_t>(w_packed) & 15) return FC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(w_packed, 0, (size_t)bytes, st) != cudaSuccess) return FC_ERR_CUDA;
+  cond_pack_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(bias_packed, winv_packed, n_pad);
+  cond_pack_kernel<<<N, 128, 0, st>>>(W, w_row_stride, mask, mask_row_stride, bias, row_map, col_map, N, K, bn, k_pad / 64,
+                                      reinterpret_cast<unsigned char*>(w_packed), bias_packed, winv_packed);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+extern "C" int fc_conditioner_error(int32_t* out) {
+  if (!out) return FC_ERR_INVALID_ARGUMENT;
+  if (cudaMemcpyFromSymbol(out, g_cond_error, sizeof(int32_t)) != cudaSuccess) return FC_ERR_CUDA;
+  return FC_OK;
+}
+
+extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                                        int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                                        int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                                        const fc_rqs_config* cfg, int32_t* status, void* stream) {
+  RqsParams c;
+  int rc = make_rqs_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  if (!net || !net->weights || net->n_layers < 2 || net->n_layers > kMaxCondLayers) return FC_ERR_INVALID_ARGUMENT;
+  if (B < 0 || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
+  if (B == 0) return FC_OK;
+  if (!a || !x || !y || !logabsdet) return FC_ERR_INVALID_ARGUMENT;
+  if (B >= ((int64_t)1 << 31)) return FC_ERR_UNSUPPORTED;
+  if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
+  if (c.tails != FC_TAILS_LINEAR || (c.K != 8 && c.K != 16)) return FC_ERR_UNSUPPORTED;
+  if (net->hidden != 128 && net->hidden != 256) return FC_ERR_UNSUPPORTED;
+  if (net->k_in <= 0 || net->k_in > 256 || (net->k_in & 3) || (lda & 3) || lda < net->k_in ||
+      (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(net->weights) & 15))
+    return FC_ERR_UNSUPPORTED;
+  const int ppad = c.K == 8 ? 24 : 48;
+  const int kch = net->hidden / 64;
+  CondArgs args{};
+  args.weights = reinterpret_cast<const unsigned char*>(net->weights);
+  args.a = a;
+  args.lda = lda;
+  args.k_in = net->k_in;
+  args.M = B;
+  args.num_tiles = (int)((B + 255) / 256);
+  args.n_layers = net->n_layers;
+  args.slots_per_tile = 0;
+  for (int l = 0; l < net->n_layers; ++l) {
+    const fc_conditioner_layer& s = net->layers[l];
+    CondLayerDev& d = args.L[l];
+    const bool last = l == net->n_layers - 1;
+    if (!s.bias || !s.winv || s.n_tiles <= 0 || s.w_offset < 0 || (s.w_offset & 15)) return FC_ERR_INVALID_ARGUMENT;
+    if (last != (s.kind == FC_COND_FINAL) || (l == 0) != (s.kind == FC_COND_INITIAL)) return FC_ERR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(s.bias) & 15) || (reinterpret_cast<uintptr_t>(s.winv) & 15)) return FC_ERR_UNSUPPORTED;
+    d.n_tiles = s.n_tiles;
+    d.bn = last ? 96 : 128;
+    const int k = l == 0 ? net->k_in : net->hidden;
+    d.k_chunks = (k + 63) / 64;
+    d.k_steps_last = ((k - (d.k_chunks - 1) * 64) + 15) / 16;
+    if (!last && s.n_tiles != net->hidden / 128) return FC_ERR_INVALID_ARGUMENT;
+    if (last && (int64_t)s.n_tiles * (96 / ppad) < D_t) return FC_ERR_INVALID_ARGUMENT;
+    if (l > 0 && d.k_chunks != kch) return FC_ERR_INVALID_ARGUMENT;
+    d.kind = s.kind;
+    d.relu_next = s.relu_next;
+    d.w_off16 = (unsigned)(s.w_offset >> 4);
+    d.cta_bytes = (unsigned)(2 * (d.bn / 2) * 128);
+    d.bias = s.bias;
+    d.winv = s.winv;
+    args.slots_per_tile += d.n_tiles * d.k_chunks;
+  }
+  args.x = x;
+  args.ldx = x_row_stride;
+  args.y = y;
+  args.ldy = y_row_stride;
+  args.lad = logabsdet;
+  args.accumulate = accumulate_logabsdet;
+  args.tcols = tcols.idx;
+  args.ccols = ccols.idx;
+  args.n_copy = ccols.n;
+  args.D_t = D_t;
+  args.c = c;
+  args.status = status;
+  void* err_ptr = nullptr;
+  if (cudaGetSymbolAddress(&err_ptr, g_cond_error) != cudaSuccess) return FC_ERR_CUDA;
+  args.error = reinterpret_cast<int32_t*>(err_ptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (net->hidden == 256) {
+    if (c.K == 8) return launch_conditioner<8, 24, 2>(args, st);
+    return launch_conditioner<16, 48, 2>(args, st);
+  }
+  if (c.K == 8) return launch_conditioner<8, 24, 1>(args, st);
+  return launch_conditioner<16, 48, 1>(args, st);
+}

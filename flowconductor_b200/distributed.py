@@ -29,13 +29,15 @@ def shard_rows(tensor, rank=None, world_size=None):
 
 
 def reduce_log_likelihood(local_log_prob, group=None):
-    """(sum over ALL ranks of log_prob, total row count): local fp64 sum, then one 2-element all-reduce."""
+    """(sum over ALL ranks of log_prob, total row count), both 0-dim fp64 DEVICE tensors: local fp64 sum, then one
+    2-element all-reduce.  No host synchronisation: the caller decides when (and whether) to read them back
+    (`float(total)`, `int(count)`)."""
     packed = torch.stack((local_log_prob.double().sum(),
                           torch.tensor(float(local_log_prob.numel()), dtype=torch.float64,
                                        device=local_log_prob.device)))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    return packed[0], int(packed[1].item())
+    return packed[0], packed[1]
 
 
 def sharded_log_prob(flow, inputs, context=None, chunk_rows=None):
@@ -75,8 +77,13 @@ def broadcast_parameters(module, src=0, group=None):
     """Make every replica identical to rank `src` (parameters and buffers)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
+    from .nn import tensorcore
+
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    # the collective wrote through .data: neither the pointers nor the version counters of the parameters moved, so the
+    # packed tensor-core weights cached on the conditioners would be stale
+    tensorcore.invalidate(module)
 
 
 def host_log_prob(flow, inputs_host, out_host=None, chunk_rows=262144, context_host=None):

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .. import _cabi, linear as fl
+from .. import _cabi, conditioner as fcond, linear as fl
 from . import tc_autograd
 
 ENABLED = True  # set False to force the unfused (torch.nn + element-wise kernel) path everywhere
@@ -33,8 +33,8 @@ ENABLED = True  # set False to force the unfused (torch.nn + element-wise kernel
 # satisfy both.
 # ---------------------------------------------------------------------------------------------------------
 class _Ownership(threading.local):
-    consent = None      # data_ptr the cascade allows the next layer to overwrite
-    fresh = None        # data_ptr allocated by the layer call that is running / has just returned
+    consent = None      # the tensor the cascade allows the next layer to overwrite (consumed by the first kernel layer)
+    fresh = None        # the tensor allocated by the layer call that is running / has just returned
     prev_fresh = None   # ... by the layer call before it
 
 
@@ -44,7 +44,7 @@ _own = _Ownership()
 def begin_layer(private_input):
     """Called by CompositeTransform._cascade before each layer; `private_input` is the previous layer's output
     (None for the first layer, whose input belongs to the caller)."""
-    _own.consent = private_input.data_ptr() if private_input is not None else None
+    _own.consent = private_input
     _own.prev_fresh, _own.fresh = _own.fresh, None
 
 
@@ -53,12 +53,20 @@ def end_cascade():
 
 
 def mark_fresh(t):
-    _own.fresh = t.data_ptr()
+    _own.fresh = t
 
 
 def may_overwrite(t):
-    return (INPLACE and not torch.is_grad_enabled() and _own.consent is not None
-            and t.data_ptr() == _own.consent == _own.prev_fresh)
+    """True exactly once per cascade step, and only for the very tensor object the cascade handed to its direct child:
+    a view of it, a tensor that merely shares its storage, or a second kernel layer called by a wrapper transform on the
+    same input never qualify (identity, not data_ptr, is compared; the consent is consumed on first use)."""
+    ok = (INPLACE and not torch.is_grad_enabled() and _own.consent is not None
+          and t is _own.consent and t is _own.prev_fresh)
+    return ok
+
+
+def consume_consent():
+    _own.consent = None
 
 
 INPLACE = True
@@ -116,6 +124,28 @@ def usable(net, a, context, *other_inputs):
 
 def _param_key(net):
     return tuple((p.data_ptr(), p._version) for p in net.parameters())
+
+
+def invalidate(module):
+    """Drop the packed-weight plans cached on `module` and its sub-modules.  The cache key is (data pointer, in-place
+    version counter) of every parameter; a write through `.data` (EMA swaps such as `p.data.copy_(...)`, collectives on
+    `p.data`) changes neither, so code that updates weights that way must call this afterwards.  Optimizer steps,
+    `load_state_dict` and `distributed.broadcast_parameters` are covered without it."""
+    for m in module.modules():
+        if getattr(m, "_fc_plan", None) is not None:
+            object.__setattr__(m, "_fc_plan", None)
+        if getattr(m, "_fc_cond_plan", None) is not None:
+            object.__setattr__(m, "_fc_cond_plan", None)
+
+
+def plan_keys(module):
+    """{net: key} of every conditioner under `module` that has a cached plan (graphs.GraphedCall compares them at
+    replay: a captured graph contains no pack kernels and would otherwise keep using the old weights)."""
+    keys = {}
+    for m in module.modules():
+        if getattr(m, "_fc_plan", None) is not None or getattr(m, "_fc_cond_plan", None) is not None:
+            keys[m] = _param_key(m)
+    return keys
 
 
 class _Plan:
@@ -195,6 +225,7 @@ def _output_buffer(inputs, allow_inplace=True):
     allow_inplace=False for callers that need `inputs` again (the D passes of an autoregressive inverse)."""
     x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
     y = x if (allow_inplace and may_overwrite(inputs) and x is inputs) else torch.empty_like(x)
+    consume_consent()  # whatever this call decided, no later kernel layer of the same cascade step may write in place
     mark_fresh(y)
     return x, y
 
@@ -216,17 +247,42 @@ def rqs_fusable(spline, final_out_features, d_t):
             and final_out_features == d_t * (3 * spline.num_bins - 1))
 
 
+FUSED_CONDITIONER = True  # whole conditioner + spline as ONE persistent kernel (csrc/fc_conditioner.cu) where it applies
+
+
+def cond_plan_for(net, col_map, k_in, num_bins, d_t):
+    """PackedConditioner of `net`, cached on the module like the per-layer plans (same key rules)."""
+    key = (_param_key(net), num_bins, k_in, d_t)
+    plan = getattr(net, "_fc_cond_plan", None)
+    if plan is not None and plan[0] == key:
+        return plan[1]
+    packed = fcond.pack_rqs(net, num_bins, d_t, col_map=col_map, k_in=k_in)
+    object.__setattr__(net, "_fc_cond_plan", (key, packed))
+    return packed
+
+
+def conditioner_fusable(net, k_in, num_bins):
+    return FUSED_CONDITIONER and fcond.supported_shape(net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins)
+
+
 def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None,
               allow_inplace=True):
     """Conditioner + spline for one layer; returns (outputs, logabsdet)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
-    plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("rqs", spline.num_bins))
-    h = hidden(net, plan, a)
+    k_in = k_in if k_in is not None else a.shape[1]
     tb = float(spline.tail_bound)
     wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
     cfg = _cabi.RqsConfig(int(spline.num_bins), _cabi.TAILS_LINEAR, int(bool(spline.identity_init)), int(bool(inverse)),
                           -tb, tb, -tb, tb, float(spline.min_bin_width), float(spline.min_bin_height),
                           float(spline.min_derivative), wh_scale)
+    if conditioner_fusable(net, k_in, int(spline.num_bins)):
+        packed = cond_plan_for(net, col_map, k_in, int(spline.num_bins), d_t)
+        x, y = _output_buffer(inputs, allow_inplace)
+        lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
+        fcond.rqs_apply(packed, a, x, y, lad, False, d_t, tcols, ccols, cfg, None)
+        return y, lad
+    plan = plan_for(net, col_map, k_in, ("rqs", spline.num_bins))
+    h = hidden(net, plan, a)
     x, y = _output_buffer(inputs, allow_inplace)
     lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
     fl.linear_rqs(h, plan.final, x, y, lad, False, d_t, tcols, ccols, cfg, None)

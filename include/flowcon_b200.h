@@ -309,6 +309,59 @@ int fc_linear_affine_apply(const float* hidden, int64_t ldh, int64_t B, int32_t 
  */
 int fc_linear_debug_profile(unsigned long long* out16);
 
+/*
+ * A WHOLE conditioner network + the rational-quadratic spline it parameterises in one persistent kernel
+ * (csrc/fc_conditioner.cu).  Replaces ResidualNet.forward (flowcon/nn/nets/resnet.py:92-100) or the
+ * residual MADE.forward (flowcon/transforms/made.py:274-283) followed by the spline of coupling.py:549-582 /
+ * autoregressive.py:578-615: the [B, hidden] activations and the [B, D_t * P] parameters never exist in memory.
+ * Arithmetic: "3xFP16" — every fp32 product as three fp16 tensor-core products of exactly scaled (hi, lo) splits,
+ * partial sums drained into fp32 registers every 64 k-values (same error as an fp32 FMA chain).
+ *
+ * Layers: [initial] ([block first] [block second])* [final].  Each layer's weights are packed by
+ * fc_conditioner_pack_layer into one contiguous buffer (`weights` + w_offset; size fc_conditioner_layer_bytes):
+ * bn = 128 columns per N tile for every layer but the final one (bn = 96: 4 features x 24 padded parameters for 8
+ * bins, 2 x 48 for 16 bins — row_map[j*P + i] = j*P_pad + i as for fc_linear_rqs_apply), k_pad = the layer's input width
+ * rounded up to 64, n_pad = n_tiles * bn; row_map / col_map / mask as for fc_linear_pack.  bias / winv: [n_pad] floats
+ * written by the packer (winv = the exact power of two that undoes the weight row's fp16 scaling).
+ * Supported: hidden width 128 or 256, input width k_in <= 256 (a multiple of 4), at most FC_COND_MAX_LAYERS layers,
+ * linear tails with 8 or 16 bins; everything else FC_ERR_UNSUPPORTED (run the per-layer fc_linear_* kernels).
+ */
+#define FC_COND_MAX_LAYERS 10
+#define FC_COND_INITIAL 0      /* h = W a + b */
+#define FC_COND_BLOCK_FIRST 1  /* t = W relu(h) + b            (resnet.py:41-44) */
+#define FC_COND_BLOCK_SECOND 2 /* h = h + W relu(t) + b        (resnet.py:45-56) */
+#define FC_COND_FINAL 3        /* params = W h + b             (resnet.py:99, no activation in front) */
+typedef struct fc_conditioner_layer {
+  int32_t kind;      /* FC_COND_* */
+  int32_t n_tiles;   /* N tiles: hidden / 128, or ceil(D_t / features per 96-column tile) for the final layer */
+  int32_t relu_next; /* the following layer multiplies relu(result) */
+  int32_t reserved;
+  int64_t w_offset;  /* byte offset of the layer's packed weights inside `weights` (a multiple of 16) */
+  const float* bias; /* device [n_tiles * bn] */
+  const float* winv; /* device [n_tiles * bn] */
+} fc_conditioner_layer;
+typedef struct fc_conditioner {
+  const void* weights; /* device, 16-byte aligned */
+  int32_t n_layers, hidden, k_in, reserved;
+  fc_conditioner_layer layers[FC_COND_MAX_LAYERS];
+} fc_conditioner;
+
+int64_t fc_conditioner_layer_bytes(int32_t n_pad, int32_t k_pad, int32_t bn);
+int fc_conditioner_pack_layer(const float* W, int64_t w_row_stride, const float* mask, int64_t mask_row_stride,
+                              const float* bias, int32_t N, int32_t K, const int32_t* row_map, const int32_t* col_map,
+                              int32_t n_pad, int32_t k_pad, int32_t bn, void* w_packed, float* bias_packed,
+                              float* winv_packed, void* stream);
+/* a: the matrix the initial layer multiplies ([B, k_in], row stride lda; for a coupling layer the full-width inputs
+ * with the identity-column gather folded into col_map, for a MADE the inputs).  x / y / logabsdet / tcols / ccols / cfg /
+ * status exactly as for fc_linear_rqs_apply; y may alias x. */
+int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                             int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                             int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                             const fc_rqs_config* cfg, int32_t* status, void* stream);
+/* Debugging aid: every barrier wait inside the kernel is bounded; if one ever times out the kernel ends early and leaves
+ * a non-zero code (wait site + 100 * warp) here.  Synchronises the device.  Not part of the data path. */
+int fc_conditioner_error(int32_t* out);
+
 /* Library / build info (also used by the loader test). */
 const char* fc_version(void);
 int fc_built_for_sm(void); /* 100 */
