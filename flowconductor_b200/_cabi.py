@@ -26,7 +26,7 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_linspline_apply", "fc_linsplin
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
-           "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_error",
+           "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_error", "fc_conditioner_profile",
            "fc_version", "fc_built_for_sm"]
 COND_MAX_LAYERS = 10
 COND_INITIAL, COND_BLOCK_FIRST, COND_BLOCK_SECOND, COND_FINAL = 0, 1, 2, 3
@@ -124,6 +124,7 @@ def lib():
         L.fc_conditioner_rqs_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, vp, i64, vp, i32, i32,
                                                Cols, Cols, ctypes.POINTER(RqsConfig), vp, vp]
         L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
+        L.fc_conditioner_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
         L.fc_version.restype = ctypes.c_char_p
         for name in EXPORTS:
             if name not in ("fc_version",):

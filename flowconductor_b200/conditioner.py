@@ -141,3 +141,16 @@ def kernel_error():
     out = ctypes.c_int32(0)
     _cabi.check(_cabi.lib().fc_conditioner_error(ctypes.byref(out)), "fc_conditioner_error")
     return out.value
+
+
+PROFILE_FIELDS = {0: "mma total", 1: "mma wait operand", 2: "mma wait accumulator", 3: "mma wait weights", 4: "mma slots",
+                  8: "row total", 9: "row initial operand", 10: "row deferred bijection", 11: "row hidden wait",
+                  12: "row hidden drain", 13: "row hidden bias/skip/relu", 14: "row hidden convert", 15: "row final wait",
+                  16: "row final drain", 17: "row final bijection"}
+
+
+def kernel_profile():
+    """Cycle counters of the last fused launch (library built with FC_LINEAR_PROFILE_BUILD=1; zeros otherwise)."""
+    buf = (ctypes.c_uint64 * 32)()
+    _cabi.check(_cabi.lib().fc_conditioner_profile(buf), "fc_conditioner_profile")
+    return {name: int(buf[i]) for i, name in PROFILE_FIELDS.items()}

@@ -47,7 +47,8 @@ using namespace tc;
 
 constexpr int kCM = 128;              // rows per CTA (= TMEM lanes)
 constexpr int kSlotBytes = 16384;     // ring slot per CTA: (hi | lo) planes of <= 64 weight rows x 64 fp16
-constexpr int kCondStages = 5;
+constexpr int kCondStages = 4;
+constexpr int kVecBytes = 28672;      // bias (fp32) + weight-scale exponent (1 byte) per output column of every layer
 constexpr int kCondThreads = 384;     // 4 control warps + 8 row warps
 constexpr int kMaxCondLayers = FC_COND_MAX_LAYERS;
 constexpr uint32_t kTmemAcc = 0;      // two partial accumulators, 128 columns apart
@@ -64,6 +65,7 @@ struct CondLayerDev {
   int relu_next;     // the next layer's operand is relu(result)
   unsigned w_off16;  // first slot of the layer inside the packed weights, in 16-byte units
   unsigned cta_bytes;  // bytes per slot and CTA: 2 planes x bn/2 rows x 128 B
+  int col0;            // first column of the layer in the shared-memory bias / exponent vectors
   const float* bias;   // [n_tiles * bn]
   const float* winv;   // [n_tiles * bn] exact powers of two: 1 / weight-row scale
 };
@@ -77,6 +79,7 @@ struct CondArgs {
   int num_tiles;  // 256-row tiles (one per CTA pair and step)
   int n_layers;
   int slots_per_tile;
+  int total_cols;  // output columns of all layers (a multiple of 4): size of the bias / scale-exponent vectors in shared memory
   CondLayerDev L[kMaxCondLayers];
   // bijection
   const float* x;
@@ -95,6 +98,22 @@ struct CondArgs {
 };
 
 __device__ int32_t g_cond_error;
+
+// Experiments only (-DFC_COND_PROFILE=1: FC_LINEAR_PROFILE_BUILD=1 python -m flowconductor_b200.build --force): cycles CTA 0's
+// MMA-issuing warp and its first row warp spend in each phase; fc_conditioner_profile() reads them back.
+#ifndef FC_COND_PROFILE
+#define FC_COND_PROFILE 0
+#endif
+__device__ unsigned long long g_cond_prof[32];
+#if FC_COND_PROFILE
+#define CPROF_DECL(name) long long name = 0
+#define CPROF_T0(t) const long long t = clock64()
+#define CPROF_ADD(name, t) name += clock64() - (t)
+#else
+#define CPROF_DECL(name)
+#define CPROF_T0(t)
+#define CPROF_ADD(name, t)
+#endif
 
 template <int N>
 __device__ __forceinline__ void cond_set_max_regs_inc() {
@@ -152,27 +171,21 @@ __device__ __forceinline__ bool cond_wait_cluster(uint32_t bar, uint32_t parity,
   return true;
 }
 
-// acc[0..N) += inv_s * (N consecutive TMEM columns of this thread's lane); 16 columns per tcgen05.ld, the FMAs of group j
-// run while the load of group j + 1 is in flight
+// acc[0..N) += inv_s * (N consecutive TMEM columns of this thread's lane): all loads in flight, one wait
 template <int N>
 __device__ __forceinline__ void drain_scaled(uint32_t taddr, float inv_s, float* acc) {
   static_assert(N % 16 == 0, "16 columns per load");
-  uint32_t v[2][16];
-  tmem_ld16(taddr, v[0]);
+  uint32_t v[N];
+#pragma unroll
+  for (int j = 0; j < N; j += 16) tmem_ld16(taddr + (uint32_t)j, v + j);
   tmem_wait_ld();
 #pragma unroll
-  for (int j = 0; j < N; j += 16) {
-    const int cur = (j >> 4) & 1;
-    if (j + 16 < N) tmem_ld16(taddr + (uint32_t)(j + 16), v[cur ^ 1]);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[j + i] = fmaf(__uint_as_float(v[cur][i]), inv_s, acc[j + i]);
-    if (j + 16 < N) tmem_wait_ld();
-  }
+  for (int j = 0; j < N; ++j) acc[j] = fmaf(__uint_as_float(v[j]), inv_s, acc[j]);
 }
 
-// 64 fp32 values of one row -> the (hi, lo) fp16 planes of operand chunk `chunk` in tensor memory, scaled by the power
-// of two that puts the largest magnitude into [2^13, 2^14).  Returns 1 / scale (exact).
-__device__ __forceinline__ float produce_chunk(const float* v, uint32_t ta_chunk /* TMEM address of the hi plane */) {
+// 64 fp32 values of one row -> packed (hi, lo) fp16 words of one operand chunk (w[0..32) hi plane, w[32..64) lo plane),
+// scaled by the power of two that puts the largest magnitude into [2^13, 2^14).  Returns 1 / scale (exact).
+__device__ __forceinline__ float convert_chunk(const float* v, uint32_t* w) {
   float m = 0.f;
 #pragma unroll
   for (int j = 0; j < 64; ++j) m = fmaxf(m, fabsf(v[j]));
@@ -181,20 +194,27 @@ __device__ __forceinline__ float produce_chunk(const float* v, uint32_t ta_chunk
   const float s = __uint_as_float((267u - E) << 23);      // 2^(13 - (E - 127))
   const float inv_s = __uint_as_float((E - 13u) << 23);   // 2^((E - 127) - 13)
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-      const float a0 = v[g * 32 + 2 * p] * s, a1 = v[g * 32 + 2 * p + 1] * s;
-      const __half2 h2 = __floats2half2_rn(a0, a1);  // k even in the low half
-      const float2 hf = __half22float2(h2);
-      const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-      hi[p] = *reinterpret_cast<const uint32_t*>(&h2);
-      lo[p] = *reinterpret_cast<const uint32_t*>(&l2);
-    }
-    tmem_st16(ta_chunk + (uint32_t)(g * 16), hi);
-    tmem_st16(ta_chunk + 128u + (uint32_t)(g * 16), lo);
+  for (int p = 0; p < 32; ++p) {
+    const float a0 = v[2 * p] * s, a1 = v[2 * p + 1] * s;
+    const __half2 h2 = __floats2half2_rn(a0, a1);  // k even in the low half
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    w[p] = *reinterpret_cast<const uint32_t*>(&h2);
+    w[32 + p] = *reinterpret_cast<const uint32_t*>(&l2);
   }
+  return inv_s;
+}
+// ... into tensor memory: hi plane at ta_chunk (32 columns), lo plane 128 columns further
+__device__ __forceinline__ void store_chunk(const uint32_t* w, uint32_t ta_chunk) {
+  tmem_st16(ta_chunk, w);
+  tmem_st16(ta_chunk + 16u, w + 16);
+  tmem_st16(ta_chunk + 128u, w + 32);
+  tmem_st16(ta_chunk + 144u, w + 48);
+}
+__device__ __forceinline__ float produce_chunk(const float* v, uint32_t ta_chunk) {
+  uint32_t w[64];
+  const float inv_s = convert_chunk(v, w);
+  store_chunk(w, ta_chunk);
   return inv_s;
 }
 
@@ -204,7 +224,7 @@ struct CondSmem {
   static constexpr int SC_BYTES = 2 * 4 * kCM * 4;   // 1 / operand scale: [layer parity][chunk][row]
   static constexpr int LAD_BYTES = kCM * 4;
   static constexpr int BAR_BYTES = 8 * (3 * kCondStages + 7) + 16;
-  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + BAR_BYTES + 1024;
+  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + kVecBytes + BAR_BYTES + 1024;
 };
 
 // KC bins, PPAD accumulator columns per feature, NT = hidden width / 128
@@ -221,7 +241,10 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   float* const hs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES);
   float* const scs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES + CondSmem::H_BYTES);
   float* const ladx = scs + 2 * 4 * kCM;
-  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + CondSmem::LAD_BYTES;
+  // bias[total_cols] floats, then the biased exponents of 1 / weight scale, one byte per column
+  float* const vbias = ladx + kCM;
+  unsigned char* const vexp = reinterpret_cast<unsigned char*>(vbias + a.total_cols);
+  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + CondSmem::LAD_BYTES + kVecBytes;
   unsigned char* const gbars = gbase + (bars - base);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto ready_bar = [&](int s) { return bars + 8u * (kCondStages + s); };   // leader's: both halves have landed
@@ -254,6 +277,15 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  // per-column vectors of every layer -> shared memory (read in every row tile by every row thread)
+  for (int l = 0; l < a.n_layers; ++l) {
+    const CondLayerDev& L = a.L[l];
+    const int n = L.n_tiles * L.bn;
+    for (int i = threadIdx.x; i < n; i += kCondThreads) {
+      vbias[L.col0 + i] = __ldg(L.bias + i);
+      vexp[L.col0 + i] = (unsigned char)(__float_as_uint(__ldg(L.winv + i)) >> 23);
+    }
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -324,6 +356,11 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       int s = 0, acc = 0;
       uint32_t ph = 0, aph = 0, lcount = 0;
       const uint64_t b0 = make_smem_desc(base, 128);
+      CPROF_DECL(m_opnd);
+      CPROF_DECL(m_tempty);
+      CPROF_DECL(m_ready);
+      CPROF_DECL(m_chunks);
+      CPROF_T0(m_begin);
       for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
         for (int l = 0; l < a.n_layers; ++l, ++lcount) {
           const CondLayerDev& L = a.L[l];
@@ -331,11 +368,26 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           const uint64_t lo_off = (uint64_t)((L.cta_bytes >> 1) >> 4);
           for (int nt = 0; nt < L.n_tiles; ++nt) {
             for (int c = 0; c < L.k_chunks; ++c) {
-              if (nt == 0 && (c & 1) == 0) {  // operand chunks c, c + 1 written (by both CTAs)
-                if (!cond_wait_cluster(opnd_bar(c >> 1), lcount & 1u, abort_s)) COND_FAIL(3);
+              {
+                CPROF_T0(t0);
+                if (nt == 0 && (c & 1) == 0) {  // operand chunks c, c + 1 written (by both CTAs)
+                  if (!cond_wait_cluster(opnd_bar(c >> 1), lcount & 1u, abort_s)) COND_FAIL(3);
+                }
+                CPROF_ADD(m_opnd, t0);
               }
-              if (!cond_wait_cluster(tempty_bar(acc), aph ^ 1u, abort_s)) COND_FAIL(4);
-              if (!cond_wait_cluster(ready_bar(s), ph, abort_s)) COND_FAIL(5);
+              {
+                CPROF_T0(t0);
+                if (!cond_wait_cluster(tempty_bar(acc), aph ^ 1u, abort_s)) COND_FAIL(4);
+                CPROF_ADD(m_tempty, t0);
+              }
+              {
+                CPROF_T0(t0);
+                if (!cond_wait_cluster(ready_bar(s), ph, abort_s)) COND_FAIL(5);
+                CPROF_ADD(m_ready, t0);
+              }
+#if FC_COND_PROFILE
+              ++m_chunks;
+#endif
               tc_fence_after();
               const int steps = (c == L.k_chunks - 1) ? L.k_steps_last : 4;
               const uint64_t b_hi = b0 + (uint64_t)((uint32_t)s * (uint32_t)(kSlotBytes >> 4)), b_lo = b_hi + lo_off;
@@ -368,6 +420,15 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           }
         }
       }
+#if FC_COND_PROFILE
+      if (blockIdx.x == 0 && lane == 0) {
+        g_cond_prof[0] = (unsigned long long)(clock64() - m_begin);
+        g_cond_prof[1] = (unsigned long long)m_opnd;
+        g_cond_prof[2] = (unsigned long long)m_tempty;
+        g_cond_prof[3] = (unsigned long long)m_ready;
+        g_cond_prof[4] = (unsigned long long)m_chunks;
+      }
+#endif
     }
   } else {
     // ------------------------------------------------------------------ row threads
@@ -386,6 +447,16 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     long long prow = 0;
     bool pvalid = false, pending = false;
     float lad_acc = 0.f;
+    CPROF_DECL(r_l0);
+    CPROF_DECL(r_flush);
+    CPROF_DECL(r_wait_h);
+    CPROF_DECL(r_drain_h);
+    CPROF_DECL(r_final_h);
+    CPROF_DECL(r_prod_h);
+    CPROF_DECL(r_wait_f);
+    CPROF_DECL(r_drain_f);
+    CPROF_DECL(r_spline);
+    CPROF_T0(r_begin);
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       pxv[f] = 0.f;
@@ -405,6 +476,13 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         mbar_arrive_remote_relaxed(opnd_bar(1), 0);
       }
     };
+    auto signal_group = [&](int g) {
+      tmem_wait_st();
+      __threadfence_block();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_relaxed(opnd_bar(g), 0);
+    };
     auto spline = [&](int f) {
       if (plive[f]) {
         float yv, lv;
@@ -419,6 +497,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       const bool valid = row < a.M;
       // ---- operand of the initial layer: this row of the conditioner input, chunks half, half + 2
       {
+        CPROF_T0(t_l0);
         const CondLayerDev& L0 = a.L[0];
         float* sc_next = scs + (lcount & 1u) * (4 * kCM);
         for (int c = half; c < L0.k_chunks; c += 2) {
@@ -436,8 +515,10 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           sc_next[c * kCM + rl] = produce_chunk(v, tmem_base + lane_sel + kTmemA + (uint32_t)(c * 32));
         }
         signal_operand();
+        CPROF_ADD(r_l0, t_l0);
       }
       // ---- finish the previous row tile while the initial layer's MMAs run
+      CPROF_T0(t_flush);
       if (pending) {
 #pragma unroll
         for (int f = 0; f < NF; ++f) spline(f);
@@ -469,20 +550,34 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           }
         }
       }
+      CPROF_ADD(r_flush, t_flush);
       // ---- hidden layers
       for (int l = 0; l < a.n_layers - 1; ++l, ++lcount) {
         const CondLayerDev& L = a.L[l];
         const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
         float* sc_next = scs + ((lcount + 1u) & 1u) * (4 * kCM);
         float av[NT * 64];
+        uint32_t pw[64];
+        float pre_inv = 0.f;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) av[nt * 64 + j] = 0.f;
           for (int c = 0; c < L.k_chunks; ++c) {
+            CPROF_T0(t_w);
             if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(6);
+            CPROF_ADD(r_wait_h, t_w);
+            CPROF_T0(t_d);
             tc_fence_after();
             const float inv_s = sc_cur[c * kCM + rl];
+            if (NT == 2 && nt == 1 && c == L.k_chunks - 1) {
+              // every MMA of this layer has completed: the operand in tensor memory may be overwritten.  Chunks 0 / 1 of
+              // the next operand were converted while the second N tile ran; hand them over first, so that the next
+              // layer's MMAs start while this thread finishes the second N tile
+              store_chunk(pw, tmem_base + lane_sel + kTmemA + (uint32_t)(half * 32));
+              sc_next[half * kCM + rl] = pre_inv;
+              signal_group(0);
+            }
             drain_scaled<64>(tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + half * 64), inv_s, av + nt * 64);
             tc_fence_before();
             __syncwarp();
@@ -491,36 +586,50 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
               acc_i = 0;
               aph ^= 1u;
             }
+            CPROF_ADD(r_drain_h, t_d);
           }
+          CPROF_T0(t_f);
           // bias, weight scale, skip connection, ReLU
           const int n0 = nt * 128 + half * 64;
-          const float4* b4 = reinterpret_cast<const float4*>(L.bias + n0);
-          const float4* w4 = reinterpret_cast<const float4*>(L.winv + n0);
+          const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
+          const uint32_t* e4 = reinterpret_cast<const uint32_t*>(vexp + L.col0 + n0);
           float* hcol = hs + n0 * kCM + rl;
           const bool add_h = L.kind == FC_COND_BLOCK_SECOND, put_h = L.kind != FC_COND_BLOCK_FIRST;
           const bool relu = L.relu_next != 0;
 #pragma unroll
           for (int j4 = 0; j4 < 16; ++j4) {
-            const float4 b = __ldg(b4 + j4), w = __ldg(w4 + j4);
-            const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+            const float4 b = b4[j4];
+            const uint32_t ew = e4[j4];
+            const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int j = 4 * j4 + i;
-              float v = fmaf(av[nt * 64 + j], ww[i], bb[i]);
+              const float wi = __uint_as_float(((ew >> (8 * i)) & 0xffu) << 23);
+              float v = fmaf(av[nt * 64 + j], wi, bb[i]);
               if (add_h) v += hcol[j * kCM];
               if (put_h) hcol[j * kCM] = v;
               av[nt * 64 + j] = relu ? fmaxf(v, 0.f) : v;
             }
           }
+          CPROF_ADD(r_final_h, t_f);
+          if (NT == 2 && nt == 0) {
+            // this half of operand chunks 0 / 1 is final: convert now, while the second N tile is being computed
+            pre_inv = convert_chunk(av, pw);
+          }
         }
-        // every MMA of this layer has completed (the last partial accumulator has been drained): the operand in
-        // tensor memory may be overwritten with the next layer's
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int cidx = nt * 2 + half;
-          sc_next[cidx * kCM + rl] = produce_chunk(av + nt * 64, tmem_base + lane_sel + kTmemA + (uint32_t)(cidx * 32));
+        CPROF_T0(t_p);
+        // every MMA of this layer has completed (its last partial accumulator has been drained)
+        {
+          const int cidx = (NT - 1) * 2 + half;
+          sc_next[cidx * kCM + rl] =
+              produce_chunk(av + (NT - 1) * 64, tmem_base + lane_sel + kTmemA + (uint32_t)(cidx * 32));
         }
-        signal_operand();
+        if (NT == 2) {
+          signal_group(1);
+        } else {
+          signal_operand();
+        }
+        CPROF_ADD(r_prod_h, t_p);
       }
       // ---- final layer: N tiles of 96 parameter columns; the spline of N tile j - 1 runs between the drains of N tile j
       {
@@ -542,7 +651,10 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           for (int j = 0; j < NF * PPAD; ++j) pv[j] = 0.f;
 #pragma unroll
           for (int c = 0; c < KCH; ++c) {
+            CPROF_T0(t_w);
             if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(7);
+            CPROF_ADD(r_wait_f, t_w);
+            CPROF_T0(t_d);
             tc_fence_after();
             const float inv_s = sc_cur[c * kCM + rl];
             drain_scaled<NF * PPAD>(tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + half * (NF * PPAD)), inv_s, pv);
@@ -553,18 +665,22 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
               acc_i = 0;
               aph ^= 1u;
             }
+            CPROF_ADD(r_drain_f, t_d);
+            CPROF_T0(t_s);
             if (pending && (c * NF) % KCH == 0) spline((c * NF) / KCH);
+            CPROF_ADD(r_spline, t_s);
           }
           const int n0 = nt * 96 + half * (NF * PPAD);
-          const float4* b4 = reinterpret_cast<const float4*>(L.bias + n0);
-          const float4* w4 = reinterpret_cast<const float4*>(L.winv + n0);
+          const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
+          const uint32_t* e4 = reinterpret_cast<const uint32_t*>(vexp + L.col0 + n0);
 #pragma unroll
           for (int j4 = 0; j4 < NF * PPAD / 4; ++j4) {
-            const float4 b = __ldg(b4 + j4), w = __ldg(w4 + j4);
-            pp[4 * j4 + 0] = fmaf(pv[4 * j4 + 0], w.x, b.x);
-            pp[4 * j4 + 1] = fmaf(pv[4 * j4 + 1], w.y, b.y);
-            pp[4 * j4 + 2] = fmaf(pv[4 * j4 + 2], w.z, b.z);
-            pp[4 * j4 + 3] = fmaf(pv[4 * j4 + 3], w.w, b.w);
+            const float4 b = b4[j4];
+            const uint32_t ew = e4[j4];
+            pp[4 * j4 + 0] = fmaf(pv[4 * j4 + 0], __uint_as_float((ew & 0xffu) << 23), b.x);
+            pp[4 * j4 + 1] = fmaf(pv[4 * j4 + 1], __uint_as_float(((ew >> 8) & 0xffu) << 23), b.y);
+            pp[4 * j4 + 2] = fmaf(pv[4 * j4 + 2], __uint_as_float(((ew >> 16) & 0xffu) << 23), b.z);
+            pp[4 * j4 + 3] = fmaf(pv[4 * j4 + 3], __uint_as_float((ew >> 24) << 23), b.w);
           }
 #pragma unroll
           for (int f = 0; f < NF; ++f) {
@@ -595,6 +711,20 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       }
     }
     if (status != 0 && a.status) atomicOr(a.status, (int)status);
+#if FC_COND_PROFILE
+    if (blockIdx.x == 0 && warp == 4 && lane == 0) {
+      g_cond_prof[8] = (unsigned long long)(clock64() - r_begin);
+      g_cond_prof[9] = (unsigned long long)r_l0;
+      g_cond_prof[10] = (unsigned long long)r_flush;
+      g_cond_prof[11] = (unsigned long long)r_wait_h;
+      g_cond_prof[12] = (unsigned long long)r_drain_h;
+      g_cond_prof[13] = (unsigned long long)r_final_h;
+      g_cond_prof[14] = (unsigned long long)r_prod_h;
+      g_cond_prof[15] = (unsigned long long)r_wait_f;
+      g_cond_prof[16] = (unsigned long long)r_drain_f;
+      g_cond_prof[17] = (unsigned long long)r_spline;
+    }
+#endif
   }
 
 teardown:
@@ -728,6 +858,12 @@ extern "C" int fc_conditioner_pack_layer(const float* W, int64_t w_row_stride, c
   return FC_OK;
 }
 
+extern "C" int fc_conditioner_profile(unsigned long long* out32) {
+  if (!out32) return FC_ERR_INVALID_ARGUMENT;
+  if (cudaMemcpyFromSymbol(out32, g_cond_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return FC_ERR_CUDA;
+  return FC_OK;
+}
+
 extern "C" int fc_conditioner_error(int32_t* out) {
   if (!out) return FC_ERR_INVALID_ARGUMENT;
   if (cudaMemcpyFromSymbol(out, g_cond_error, sizeof(int32_t)) != cudaSuccess) return FC_ERR_CUDA;
@@ -784,8 +920,11 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
     d.cta_bytes = (unsigned)(2 * (d.bn / 2) * 128);
     d.bias = s.bias;
     d.winv = s.winv;
+    d.col0 = args.total_cols;
+    args.total_cols += d.n_tiles * d.bn;
     args.slots_per_tile += d.n_tiles * d.k_chunks;
   }
+  if (args.total_cols * 5 > kVecBytes) return FC_ERR_UNSUPPORTED;  // per-column vectors must fit in shared memory
   args.x = x;
   args.ldx = x_row_stride;
   args.y = y;

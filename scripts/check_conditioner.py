@@ -86,6 +86,10 @@ def timing(name, dev, steps=5):
         ms = t0.elapsed_time(t1) / steps
         print("%s log_prob %d rows, fused=%s: %.2f ms/step, %.2f M samples/s, sum %.6e, error word %d" % (
             name, B, fused, ms, B / ms / 1e3, lp.double().sum().item(), conditioner.kernel_error()))
+        if fused:
+            prof = conditioner.kernel_profile()
+            if prof["mma total"]:
+                print("   profile (cycles, CTA 0, last launch):", prof)
     tensorcore.FUSED_CONDITIONER = True
 
 
