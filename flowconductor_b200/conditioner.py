@@ -42,7 +42,7 @@ def _pack_layer(L, dev, blob, offset, layer, mask, n_pad, k_pad, bn, row_map=Non
         mask = _cabi.require_cuda_f32(mask.detach(), "mask")
         if mask.stride(1) != 1:
             mask = mask.contiguous()
-    vec = torch.empty((2, n_pad), dtype=torch.float32, device=dev)
+    vec = (torch.empty((n_pad,), dtype=torch.float32, device=dev), torch.empty((2,), dtype=torch.float32, device=dev))
     for m in (row_map, col_map):
         if m is not None:
             assert m.dtype == torch.int32 and m.is_cuda and m.is_contiguous()

@@ -48,7 +48,7 @@ using namespace tc;
 constexpr int kCM = 128;              // rows per CTA (= TMEM lanes)
 constexpr int kSlotBytes = 16384;     // ring slot per CTA: (hi | lo) planes of <= 64 weight rows x 64 fp16
 constexpr int kCondStages = 4;
-constexpr int kVecBytes = 28672;      // bias (fp32) + weight-scale exponent (1 byte) per output column of every layer
+constexpr int kVecBytes = 28672;      // bias of every output column of every layer (fp32), then 1 / weight scale per layer
 constexpr int kCondThreads = 384;     // 4 control warps + 8 row warps
 constexpr int kMaxCondLayers = FC_COND_MAX_LAYERS;
 constexpr uint32_t kTmemAcc = 0;      // two partial accumulators, 128 columns apart
@@ -67,7 +67,7 @@ struct CondLayerDev {
   unsigned cta_bytes;  // bytes per slot and CTA: 2 planes x bn/2 rows x 128 B
   int col0;            // first column of the layer in the shared-memory bias / exponent vectors
   const float* bias;   // [n_tiles * bn]
-  const float* winv;   // [n_tiles * bn] exact powers of two: 1 / weight-row scale
+  const float* winv;   // [1] exact power of two: 1 / the layer's weight scale
 };
 
 struct CondArgs {
@@ -179,8 +179,15 @@ __device__ __forceinline__ void drain_scaled(uint32_t taddr, float inv_s, float*
 #pragma unroll
   for (int j = 0; j < N; j += 16) tmem_ld16(taddr + (uint32_t)j, v + j);
   tmem_wait_ld();
+  // packed fp32x2 arithmetic (sm_100: one issue slot for two IEEE fmas)
+  const float2 s2 = make_float2(inv_s, inv_s);
 #pragma unroll
-  for (int j = 0; j < N; ++j) acc[j] = fmaf(__uint_as_float(v[j]), inv_s, acc[j]);
+  for (int j = 0; j < N; j += 2) {
+    const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), s2,
+                                make_float2(acc[j], acc[j + 1]));
+    acc[j] = r.x;
+    acc[j + 1] = r.y;
+  }
 }
 
 // 64 fp32 values of one row -> packed (hi, lo) fp16 words of one operand chunk (w[0..32) hi plane, w[32..64) lo plane),
@@ -193,12 +200,13 @@ __device__ __forceinline__ float convert_chunk(const float* v, uint32_t* w) {
   const uint32_t E = __float_as_uint(m) >> 23;  // biased exponent (m > 0)
   const float s = __uint_as_float((267u - E) << 23);      // 2^(13 - (E - 127))
   const float inv_s = __uint_as_float((E - 13u) << 23);   // 2^((E - 127) - 13)
+  const float2 s2 = make_float2(s, s), neg1 = make_float2(-1.f, -1.f);
 #pragma unroll
   for (int p = 0; p < 32; ++p) {
-    const float a0 = v[2 * p] * s, a1 = v[2 * p + 1] * s;
-    const __half2 h2 = __floats2half2_rn(a0, a1);  // k even in the low half
-    const float2 hf = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    const float2 a2 = __fmul2_rn(make_float2(v[2 * p], v[2 * p + 1]), s2);
+    const __half2 h2 = __floats2half2_rn(a2.x, a2.y);  // k even in the low half
+    const float2 r2 = __ffma2_rn(__half22float2(h2), neg1, a2);  // a - hi, exact
+    const __half2 l2 = __floats2half2_rn(r2.x, r2.y);
     w[p] = *reinterpret_cast<const uint32_t*>(&h2);
     w[32 + p] = *reinterpret_cast<const uint32_t*>(&l2);
   }
@@ -241,9 +249,9 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   float* const hs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES);
   float* const scs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES + CondSmem::H_BYTES);
   float* const ladx = scs + 2 * 4 * kCM;
-  // bias[total_cols] floats, then the biased exponents of 1 / weight scale, one byte per column
+  // bias[total_cols], then 1 / weight scale of each layer
   float* const vbias = ladx + kCM;
-  unsigned char* const vexp = reinterpret_cast<unsigned char*>(vbias + a.total_cols);
+  float* const vwinv = vbias + a.total_cols;
   const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + CondSmem::LAD_BYTES + kVecBytes;
   unsigned char* const gbars = gbase + (bars - base);
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -281,10 +289,8 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   for (int l = 0; l < a.n_layers; ++l) {
     const CondLayerDev& L = a.L[l];
     const int n = L.n_tiles * L.bn;
-    for (int i = threadIdx.x; i < n; i += kCondThreads) {
-      vbias[L.col0 + i] = __ldg(L.bias + i);
-      vexp[L.col0 + i] = (unsigned char)(__float_as_uint(__ldg(L.winv + i)) >> 23);
-    }
+    for (int i = threadIdx.x; i < n; i += kCondThreads) vbias[L.col0 + i] = __ldg(L.bias + i);
+    if (threadIdx.x == 0) vwinv[l] = __ldg(L.winv);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -559,17 +565,42 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         float av[NT * 64];
         uint32_t pw[64];
         float pre_inv = 0.f;
+        const float winv_l = vwinv[l];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
+          const int n0 = nt * 128 + half * 64;
+          float* hcol = hs + n0 * kCM + rl;
+          {
+            // the register accumulators start from the bias (all lanes read the same words: broadcast) plus, in the second
+            // layer of a block, the skip connection (resnet.py:56 / made.py:181: inputs + temps) — fetched while the
+            // first partial sums are still being computed
+            const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
+            const bool add_h = L.kind == FC_COND_BLOCK_SECOND;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) av[nt * 64 + j] = 0.f;
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 b = b4[j4];
+              av[nt * 64 + 4 * j4 + 0] = b.x;
+              av[nt * 64 + 4 * j4 + 1] = b.y;
+              av[nt * 64 + 4 * j4 + 2] = b.z;
+              av[nt * 64 + 4 * j4 + 3] = b.w;
+            }
+            if (add_h) {
+#pragma unroll
+              for (int j = 0; j < 64; j += 2) {
+                const float2 r = __fadd2_rn(make_float2(av[nt * 64 + j], av[nt * 64 + j + 1]),
+                                            make_float2(hcol[j * kCM], hcol[(j + 1) * kCM]));
+                av[nt * 64 + j] = r.x;
+                av[nt * 64 + j + 1] = r.y;
+              }
+            }
+          }
           for (int c = 0; c < L.k_chunks; ++c) {
             CPROF_T0(t_w);
             if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(6);
             CPROF_ADD(r_wait_h, t_w);
             CPROF_T0(t_d);
             tc_fence_after();
-            const float inv_s = sc_cur[c * kCM + rl];
+            const float inv_s = sc_cur[c * kCM + rl] * winv_l;  // both exact powers of two
             if (NT == 2 && nt == 1 && c == L.k_chunks - 1) {
               // every MMA of this layer has completed: the operand in tensor memory may be overwritten.  Chunks 0 / 1 of
               // the next operand were converted while the second N tile ran; hand them over first, so that the next
@@ -589,27 +620,15 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             CPROF_ADD(r_drain_h, t_d);
           }
           CPROF_T0(t_f);
-          // bias, weight scale, skip connection, ReLU
-          const int n0 = nt * 128 + half * 64;
-          const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
-          const uint32_t* e4 = reinterpret_cast<const uint32_t*>(vexp + L.col0 + n0);
-          float* hcol = hs + n0 * kCM + rl;
-          const bool add_h = L.kind == FC_COND_BLOCK_SECOND, put_h = L.kind != FC_COND_BLOCK_FIRST;
-          const bool relu = L.relu_next != 0;
+          // residual stream, ReLU
+          if (L.kind == FC_COND_INITIAL || (L.kind == FC_COND_BLOCK_SECOND && L.relu_next)) {
+            // (after the last block nothing reads the residual stream again)
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4) {
-            const float4 b = b4[j4];
-            const uint32_t ew = e4[j4];
-            const float bb[4] = {b.x, b.y, b.z, b.w};
+            for (int j = 0; j < 64; ++j) hcol[j * kCM] = av[nt * 64 + j];
+          }
+          if (L.relu_next) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int j = 4 * j4 + i;
-              const float wi = __uint_as_float(((ew >> (8 * i)) & 0xffu) << 23);
-              float v = fmaf(av[nt * 64 + j], wi, bb[i]);
-              if (add_h) v += hcol[j * kCM];
-              if (put_h) hcol[j * kCM] = v;
-              av[nt * 64 + j] = relu ? fmaxf(v, 0.f) : v;
-            }
+            for (int j = 0; j < 64; ++j) av[nt * 64 + j] = fmaxf(av[nt * 64 + j], 0.f);
           }
           CPROF_ADD(r_final_h, t_f);
           if (NT == 2 && nt == 0) {
@@ -635,6 +654,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       {
         const CondLayerDev& L = a.L[a.n_layers - 1];
         const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
+        const float winv_f = vwinv[a.n_layers - 1];
         for (int nt = 0; nt < L.n_tiles; ++nt) {
           float pv[NF * PPAD];
           float xv[NF];
@@ -647,8 +667,18 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             xc[f] = live[f] ? (a.tcols ? __ldg(a.tcols + fg) : fg) : 0;
             xv[f] = (valid && live[f]) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
           }
+          const int n0 = nt * 96 + half * (NF * PPAD);
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
 #pragma unroll
-          for (int j = 0; j < NF * PPAD; ++j) pv[j] = 0.f;
+            for (int j4 = 0; j4 < NF * PPAD / 4; ++j4) {
+              const float4 b = b4[j4];
+              pv[4 * j4 + 0] = b.x;
+              pv[4 * j4 + 1] = b.y;
+              pv[4 * j4 + 2] = b.z;
+              pv[4 * j4 + 3] = b.w;
+            }
+          }
 #pragma unroll
           for (int c = 0; c < KCH; ++c) {
             CPROF_T0(t_w);
@@ -656,7 +686,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             CPROF_ADD(r_wait_f, t_w);
             CPROF_T0(t_d);
             tc_fence_after();
-            const float inv_s = sc_cur[c * kCM + rl];
+            const float inv_s = sc_cur[c * kCM + rl] * winv_f;
             drain_scaled<NF * PPAD>(tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + half * (NF * PPAD)), inv_s, pv);
             tc_fence_before();
             __syncwarp();
@@ -670,18 +700,8 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             if (pending && (c * NF) % KCH == 0) spline((c * NF) / KCH);
             CPROF_ADD(r_spline, t_s);
           }
-          const int n0 = nt * 96 + half * (NF * PPAD);
-          const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
-          const uint32_t* e4 = reinterpret_cast<const uint32_t*>(vexp + L.col0 + n0);
 #pragma unroll
-          for (int j4 = 0; j4 < NF * PPAD / 4; ++j4) {
-            const float4 b = b4[j4];
-            const uint32_t ew = e4[j4];
-            pp[4 * j4 + 0] = fmaf(pv[4 * j4 + 0], __uint_as_float((ew & 0xffu) << 23), b.x);
-            pp[4 * j4 + 1] = fmaf(pv[4 * j4 + 1], __uint_as_float(((ew >> 8) & 0xffu) << 23), b.y);
-            pp[4 * j4 + 2] = fmaf(pv[4 * j4 + 2], __uint_as_float(((ew >> 16) & 0xffu) << 23), b.z);
-            pp[4 * j4 + 3] = fmaf(pv[4 * j4 + 3], __uint_as_float((ew >> 24) << 23), b.w);
-          }
+          for (int j = 0; j < NF * PPAD; ++j) pp[j] = pv[j];
 #pragma unroll
           for (int f = 0; f < NF; ++f) {
             pxv[f] = xv[f];
@@ -744,20 +764,14 @@ teardown:
 // slot per (N tile, 64-value chunk), each slot [rank 0: hi | lo][rank 1: hi | lo].
 // ------------------------------------------------------------------------------------------------------------
 __global__ void cond_pack_init_kernel(float* bias_out, float* winv_out, int n_pad) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-    bias_out[i] = 0.f;
-    winv_out[i] = 1.f;
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) bias_out[i] = 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *winv_out = 0.f;  // holds max |w| (as ordered bits) until the pack kernel ran
 }
 
-// one block per source weight row
-__global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ mask,
-                                                        int64_t ldm, const float* __restrict__ bias,
-                                                        const int32_t* __restrict__ row_map,
-                                                        const int32_t* __restrict__ col_map, int N, int K, int bn,
-                                                        int k_chunks, unsigned char* __restrict__ out,
-                                                        float* __restrict__ bias_out, float* __restrict__ winv_out) {
-  __shared__ float red[4];
+// largest magnitude of the (masked) weight matrix: non-negative floats order like their bit patterns
+__global__ void __launch_bounds__(128) cond_pack_max_kernel(const float* __restrict__ W, int64_t ldw,
+                                                            const float* __restrict__ mask, int64_t ldm, int K,
+                                                            float* __restrict__ max_out) {
   const int n = blockIdx.x;
   float m = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -767,13 +781,23 @@ __global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict_
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < 1e30f) atomicMax(reinterpret_cast<unsigned int*>(max_out), __float_as_uint(m));
+}
+
+// one block per source weight row; the last block to finish replaces max |w| by 1 / scale
+__global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ mask,
+                                                        int64_t ldm, const float* __restrict__ bias,
+                                                        const int32_t* __restrict__ row_map,
+                                                        const int32_t* __restrict__ col_map, int N, int K, int bn,
+                                                        int k_chunks, unsigned char* __restrict__ out,
+                                                        float* __restrict__ bias_out, const float* __restrict__ max_in,
+                                                        float* __restrict__ scale_out) {
+  const int n = blockIdx.x;
+  const float m = *max_in;
   float s = 1.f, inv_s = 1.f;
-  if (m > 1e-30f && m < 1e30f) {
+  if (m > 1e-30f) {
     const uint32_t E = __float_as_uint(m) >> 23;
-    s = __uint_as_float((267u - E) << 23);
+    s = __uint_as_float((267u - E) << 23);       // the largest weight lands in [2^13, 2^14)
     inv_s = __uint_as_float((E - 13u) << 23);
   }
   const int rn = row_map ? row_map[n] : n;
@@ -795,7 +819,7 @@ __global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict_
   }
   if (threadIdx.x == 0) {
     bias_out[rn] = bias ? bias[n] : 0.f;
-    winv_out[rn] = inv_s;
+    if (n == 0) *scale_out = inv_s;
   }
 }
 
@@ -851,9 +875,11 @@ extern "C" int fc_conditioner_pack_layer(const float* W, int64_t w_row_stride, c
   if (reinterpret_cast<uintptr_t>(w_packed) & 15) return FC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(w_packed, 0, (size_t)bytes, st) != cudaSuccess) return FC_ERR_CUDA;
-  cond_pack_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(bias_packed, winv_packed, n_pad);
+  // winv_packed[1] holds max |w| until the pack kernel has read it, winv_packed[0] receives 1 / scale
+  cond_pack_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(bias_packed, winv_packed + 1, n_pad);
+  cond_pack_max_kernel<<<N, 128, 0, st>>>(W, w_row_stride, mask, mask_row_stride, K, winv_packed + 1);
   cond_pack_kernel<<<N, 128, 0, st>>>(W, w_row_stride, mask, mask_row_stride, bias, row_map, col_map, N, K, bn, k_pad / 64,
-                                      reinterpret_cast<unsigned char*>(w_packed), bias_packed, winv_packed);
+                                      reinterpret_cast<unsigned char*>(w_packed), bias_packed, winv_packed + 1, winv_packed);
   FC_CHECK_LAUNCH();
   return FC_OK;
 }
@@ -905,7 +931,7 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
     const bool last = l == net->n_layers - 1;
     if (!s.bias || !s.winv || s.n_tiles <= 0 || s.w_offset < 0 || (s.w_offset & 15)) return FC_ERR_INVALID_ARGUMENT;
     if (last != (s.kind == FC_COND_FINAL) || (l == 0) != (s.kind == FC_COND_INITIAL)) return FC_ERR_INVALID_ARGUMENT;
-    if ((reinterpret_cast<uintptr_t>(s.bias) & 15) || (reinterpret_cast<uintptr_t>(s.winv) & 15)) return FC_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(s.bias) & 3) || (reinterpret_cast<uintptr_t>(s.winv) & 3)) return FC_ERR_UNSUPPORTED;
     d.n_tiles = s.n_tiles;
     d.bn = last ? 96 : 128;
     const int k = l == 0 ? net->k_in : net->hidden;
@@ -924,7 +950,7 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
     args.total_cols += d.n_tiles * d.bn;
     args.slots_per_tile += d.n_tiles * d.k_chunks;
   }
-  if (args.total_cols * 5 > kVecBytes) return FC_ERR_UNSUPPORTED;  // per-column vectors must fit in shared memory
+  if (args.total_cols * 4 + 4 * kMaxCondLayers > kVecBytes) return FC_ERR_UNSUPPORTED;  // biases must fit in shared memory
   args.x = x;
   args.ldx = x_row_stride;
   args.y = y;

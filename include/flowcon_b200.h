@@ -321,8 +321,9 @@ int fc_linear_debug_profile(unsigned long long* out16);
  * fc_conditioner_pack_layer into one contiguous buffer (`weights` + w_offset; size fc_conditioner_layer_bytes):
  * bn = 128 columns per N tile for every layer but the final one (bn = 96: 4 features x 24 padded parameters for 8
  * bins, 2 x 48 for 16 bins — row_map[j*P + i] = j*P_pad + i as for fc_linear_rqs_apply), k_pad = the layer's input width
- * rounded up to 64, n_pad = n_tiles * bn; row_map / col_map / mask as for fc_linear_pack.  bias / winv: [n_pad] floats
- * written by the packer (winv = the exact power of two that undoes the weight row's fp16 scaling).
+ * rounded up to 64, n_pad = n_tiles * bn; row_map / col_map / mask as for fc_linear_pack.  The packer also writes bias
+ * ([n_pad] floats) and winv (2 floats: [0] = the exact power of two that undoes the layer's fp16 weight scaling, [1]
+ * scratch).
  * Supported: hidden width 128 or 256, input width k_in <= 256 (a multiple of 4), at most FC_COND_MAX_LAYERS layers,
  * linear tails with 8 or 16 bins; everything else FC_ERR_UNSUPPORTED (run the per-layer fc_linear_* kernels).
  */
@@ -338,7 +339,7 @@ typedef struct fc_conditioner_layer {
   int32_t reserved;
   int64_t w_offset;  /* byte offset of the layer's packed weights inside `weights` (a multiple of 16) */
   const float* bias; /* device [n_tiles * bn] */
-  const float* winv; /* device [n_tiles * bn] */
+  const float* winv; /* device [2], see above */
 } fc_conditioner_layer;
 typedef struct fc_conditioner {
   const void* weights; /* device, 16-byte aligned */
