@@ -27,14 +27,16 @@
 // The thread that owns (row, 64 columns) applies bias / skip connection / ReLU to its finished values, converts them
 // to the (hi, lo) operand of the NEXT layer and writes that straight into tensor memory (tcgen05.st): there are no
 // converter warps and no activation traffic at all.  The final layer runs in N tiles of 96 columns (4 features x 24
-// padded parameters for 8 bins, 2 x 48 for 16 bins); its rows' threads evaluate the spline of N tile j between the
-// partial-accumulator drains of N tile j + 1, and the last N tile's splines after the NEXT row tile's first operand has
-// been handed to the tensor core, so the tensor pipe does not wait for the bijection.
+// padded parameters for 8 bins, 2 x 48 for 16 bins): the row threads only accumulate its partial sums and drop each
+// finished 128 x 96 parameter tile into shared memory (two buffers in the residual stream's space, which is dead by
+// then); four more warps — one thread per row — evaluate the splines from there while the tensor core and the row
+// threads are already on the next N tile (and, for the last N tiles, on the next row tile's first layers).  Measured
+// before this split: with the spline inside the row threads the final layer took 2.3x its MMA time.
 //
 // CTA pairs (cta_group::2): one MMA covers 256 rows (128 per SM); each SM stages half of every weight slot.
 // Warps: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 3 relay ("my half of the slot has landed" to
-// the leader), 4-11 row threads.  Every mbarrier wait is bounded (kTimeoutCycles): a protocol error ends the kernel
-// with a code in the error word instead of hanging the GPU.
+// the leader), 4-11 row threads (two per row), 12-15 bijection threads (one per row).  Every mbarrier wait is bounded
+// (kTimeoutCycles): a protocol error ends the kernel with a code in the error word instead of hanging the GPU.
 #include <atomic>
 #include <cuda_fp16.h>
 
@@ -48,6 +50,8 @@ using namespace tc;
 constexpr int kCM = 128;              // rows per CTA (= TMEM lanes)
 constexpr int kSlotBytes = 16384;     // ring slot per CTA: (hi | lo) planes of <= 64 weight rows x 64 fp16
 constexpr int kCondStages = 4;
+constexpr int kCondThreads = 512;     // 4 control warps, 8 row warps, 4 bijection warps
+constexpr int kRowWarps = 8, kBijWarps = 4;
 constexpr int kVecBytes = 20480;      // bias of every output column of every layer (fp32), then 1 / weight scale per layer
 constexpr int kMaxCondLayers = FC_COND_MAX_LAYERS;
 constexpr uint32_t kTmemAcc = 0;      // two partial accumulators, 128 columns apart
@@ -174,18 +178,26 @@ __device__ __forceinline__ bool cond_wait_cluster(uint32_t bar, uint32_t parity,
 template <int N>
 __device__ __forceinline__ void drain_scaled(uint32_t taddr, float inv_s, float* acc) {
   static_assert(N % 16 == 0, "16 columns per load");
-  uint32_t v[N];
-#pragma unroll
-  for (int j = 0; j < N; j += 16) tmem_ld16(taddr + (uint32_t)j, v + j);
-  tmem_wait_ld();
-  // packed fp32x2 arithmetic (sm_100: one issue slot for two IEEE fmas)
+  // packed fp32x2 arithmetic (sm_100: one issue slot for two IEEE fmas); at most 32 columns in flight (registers)
   const float2 s2 = make_float2(inv_s, inv_s);
 #pragma unroll
-  for (int j = 0; j < N; j += 2) {
-    const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), s2,
-                                make_float2(acc[j], acc[j + 1]));
-    acc[j] = r.x;
-    acc[j + 1] = r.y;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    constexpr int kStep = 32;
+    const int n = N - j0 < kStep ? N - j0 : kStep;
+    uint32_t v[kStep];
+#pragma unroll
+    for (int j = 0; j < kStep; j += 16)
+      if (j < n) tmem_ld16(taddr + (uint32_t)(j0 + j), v + j);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < kStep; j += 2) {
+      if (j < n) {
+        const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), s2,
+                                    make_float2(acc[j0 + j], acc[j0 + j + 1]));
+        acc[j0 + j] = r.x;
+        acc[j0 + j + 1] = r.y;
+      }
+    }
   }
 }
 
@@ -229,19 +241,13 @@ struct CondSmem {
   static constexpr int RING_BYTES = kCondStages * kSlotBytes;
   static constexpr int H_BYTES = 256 * kCM * 4;      // residual stream [256 columns][128 rows]
   static constexpr int SC_BYTES = 2 * 4 * kCM * 4;   // 1 / operand scale: [layer parity][chunk][row]
-  static constexpr int LAD_BYTES = 4 * kCM * 4;      // per-row log-det partials of the other column groups
-  static constexpr int MX_BYTES = 2 * 4 * kCM * 4;   // 16 row warps: chunk maxima exchanged between the two threads of a pair
-  static constexpr int BAR_BYTES = 8 * (3 * kCondStages + 7 + 8) + 16;
-  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + MX_BYTES + kVecBytes + BAR_BYTES + 1024;
+  static constexpr int BAR_BYTES = 8 * (3 * kCondStages + 11) + 16;
+  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + kVecBytes + BAR_BYTES + 1024;
 };
 
-// KC bins, PPAD accumulator columns per feature, NT = hidden width / 128, RW row warps: 8 (a row's columns are shared by
-// two threads) or 16 (by four: twice the warps to hide tcgen05.ld / shared-memory / SFU latencies behind, half the serial
-// work per thread at the layer boundaries; 112 registers per thread — 8 bins only)
-template <int KC, int PPAD, int NT, int RW>
-__global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(const CondArgs a) {
-  constexpr int kCondThreads = 128 + 32 * RW;
-  static_assert(RW == 8 || (RW == 16 && PPAD == 24 && NT == 2), "16 row warps: 8 bins, hidden width 256");
+// KC bins, PPAD accumulator columns per feature, NT = hidden width / 128
+template <int KC, int PPAD, int NT>
+__global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(const CondArgs a) {
   constexpr int KCH = 2 * NT;         // 64-value chunks of a hidden-width reduction
   constexpr int FEATS = 96 / PPAD;    // features per final N tile
   constexpr int NF = FEATS / 2;       // ... per thread (two threads share a row)
@@ -252,13 +258,10 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
   unsigned char* const gbase = smem_raw + (base - raw_s);
   float* const hs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES);
   float* const scs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES + CondSmem::H_BYTES);
-  float* const ladx = scs + 2 * 4 * kCM;
-  float* const mxs = ladx + 4 * kCM;
   // bias[total_cols], then 1 / weight scale of each layer
-  float* const vbias = mxs + 2 * 4 * kCM;
+  float* const vbias = scs + 2 * 4 * kCM;
   float* const vwinv = vbias + a.total_cols;
-  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + CondSmem::LAD_BYTES +
-                        CondSmem::MX_BYTES + kVecBytes;
+  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + kVecBytes;
   unsigned char* const gbars = gbase + (bars - base);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto ready_bar = [&](int s) { return bars + 8u * (kCondStages + s); };   // leader's: both halves have landed
@@ -266,16 +269,14 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
   auto tfull_bar = [&](int i) { return bars + 8u * (3 * kCondStages + i); };
   auto tempty_bar = [&](int i) { return bars + 8u * (3 * kCondStages + 2 + i); };  // leader's
   auto opnd_bar = [&](int g) { return bars + 8u * (3 * kCondStages + 4 + g); };    // leader's
-  const uint32_t lad_bar = bars + 8u * (3 * kCondStages + 6);  // the second column half's log-det partials are written
-  auto pair_bar = [&](int i) { return bars + 8u * (3 * kCondStages + 7 + i); };  // 16 row warps: one per warp pair
-  const uint32_t tmem_slot = bars + 8u * (3 * kCondStages + 15);
-  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbars + 8 * (3 * kCondStages + 15));
-  volatile int* const abort_s = reinterpret_cast<volatile int*>(gbars + 8 * (3 * kCondStages + 15) + 8);
+  // parameter tiles (final layer): written by the row warps / consumed by the bijection warps
+  auto pfull_bar = [&](int b) { return bars + 8u * (3 * kCondStages + 6 + b); };
+  auto pempty_bar = [&](int b) { return bars + 8u * (3 * kCondStages + 8 + b); };
+  const uint32_t tmem_slot = bars + 8u * (3 * kCondStages + 10);
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbars + 8 * (3 * kCondStages + 10));
+  volatile int* const abort_s = reinterpret_cast<volatile int*>(gbars + 8 * (3 * kCondStages + 10) + 8);
 
-  // RW = 16: the row warps come first and the four control warps last — the warp scheduler favours higher warp ids, and
-  // the MMA-issuing warp must never wait for an issue slot behind sixteen busy row warps
-  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp = RW == 16 ? (warp_id >= 16 ? warp_id - 16 : warp_id + 4) : warp_id;  // logical: 0-3 control, 4.. row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int cl0 = (int)blockIdx.x >> 1, cl_step = (int)gridDim.x >> 1;
 
@@ -288,11 +289,11 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 2 * RW);  // the row warps of both CTAs
-      mbar_init(opnd_bar(i), 2 * RW);
+      mbar_init(tempty_bar(i), 2 * kRowWarps);  // the row warps of both CTAs
+      mbar_init(opnd_bar(i), 2 * kRowWarps);
+      mbar_init(pfull_bar(i), kRowWarps);
+      mbar_init(pempty_bar(i), kBijWarps);
     }
-    mbar_init(lad_bar, RW == 8 ? 4 : 12);
-    for (int i = 0; i < 8; ++i) mbar_init(pair_bar(i), 2);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
   }
 
   if (warp < 4) {
-    cond_set_max_regs_dec<(RW == 8 ? 40 : 56)>();
+    cond_set_max_regs_dec<40>();
     if (warp == 0) {
       // ---------------------------------------------------------------- weight producer
       if (lane == 0) {
@@ -447,376 +448,23 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
       }
 #endif
     }
-  } else if constexpr (RW == 16) {
-    // ------------------------------------------------------------------ row threads, four per row
-    // Thread (row, quarter qt) owns columns [32 qt, 32 qt + 32) of every 128-column N tile and feature qt of every final N
-    // tile.  Operand chunk c of the next layer = columns [64 c, 64 c + 64) = the values of the two threads of a PAIR
-    // (quarters 2p, 2p + 1 of N tile c / 2... see `cidx`); the chunk's scale needs the maximum over both, exchanged
-    // through shared memory and the pair's mbarrier.
-    cond_set_max_regs_inc<104>();
-    const int wq = warp & 3, qt = (warp - 4) >> 2, sub = qt & 1, pr = qt >> 1;
-    const int rl = wq * 32 + lane;  // row inside the CTA's tile = TMEM lane
-    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;
-    const uint32_t my_pair_bar = pair_bar(pr * 4 + wq);
-    int acc_i = 0;
-    uint32_t aph = 0, lcount = 0, lph = 0, xph = 0;
-    unsigned status = 0;
-    // parameters of the last finished final-layer N tile: parked in this thread's own residual-stream slots (nothing
-    // reads the residual stream after the last block, and only this thread ever touches these words)
-    float* const ppark = hs + (qt * 32) * kCM + rl;
-    float pxv = 0.f;
-    int pxc = 0;
-    bool plive = false;
-    long long prow = 0;
-    bool pvalid = false, pending = false;
-    float lad_acc = 0.f;
-    CPROF_DECL(r_l0);
-    CPROF_DECL(r_flush);
-    CPROF_DECL(r_wait_h);
-    CPROF_DECL(r_drain_h);
-    CPROF_DECL(r_final_h);
-    CPROF_DECL(r_prod_h);
-    CPROF_DECL(r_wait_f);
-    CPROF_DECL(r_drain_f);
-    CPROF_DECL(r_spline);
-    CPROF_T0(r_begin);
-
-    auto signal_group = [&](int g) {
-      tmem_wait_st();
-      __threadfence_block();  // the scale words written next to the operand
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote_relaxed(opnd_bar(g), 0);
-    };
-    auto spline = [&]() {
-      if (plive) {
-        float pp[PPAD];
-#pragma unroll
-        for (int j = 0; j < PPAD; ++j) pp[j] = ppark[j * kCM];
-        float yv, lv;
-        rqs_eval<KC, true>(a.c, pxv, pp, yv, lv, status);
-        if (pvalid) a.y[prow * a.ldy + pxc] = yv;
-        lad_acc += lv;
-      }
-    };
-    // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): the four column groups of a row are combined
-    // in a fixed order
-    auto finish_row = [&]() -> bool {
-      if (qt > 0) {
-        ladx[(qt - 1) * kCM + rl] = lad_acc;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(lad_bar);  // release: orders the 32 stores above
-      } else {
-        if (!cond_wait(lad_bar, lph, abort_s)) return false;
-        if (pvalid) {
-          const float tot = ((lad_acc + ladx[rl]) + ladx[kCM + rl]) + ladx[2 * kCM + rl];
-          a.lad[prow] = a.accumulate ? a.lad[prow] + tot : tot;
-        }
-      }
-      lph ^= 1u;
-      lad_acc = 0.f;
-      pending = false;
-      return true;
-    };
-    // maximum magnitude of the pair's 64 values (this thread's 32 and the partner's)
-    auto pair_max = [&](const float* v, float& m) -> bool {
-      m = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(v[j]));
-      float* buf = mxs + (xph & 1u) * (4 * kCM);
-      buf[qt * kCM + rl] = m;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(my_pair_bar);
-      if (!cond_wait(my_pair_bar, xph & 1u, abort_s)) return false;
-      m = fmaxf(m, buf[(qt ^ 1) * kCM + rl]);
-      ++xph;
-      return true;
-    };
-    // 32 values -> 16 packed hi words + 16 packed lo words of half an operand chunk, scaled so that the chunk's largest
-    // magnitude m lands in [2^13, 2^14); returns 1 / scale
-    auto convert_half = [&](const float* v, float m, uint32_t* w) -> float {
-      m = fmaxf(m, 1e-30f);
-      const uint32_t E = __float_as_uint(m) >> 23;
-      const float s = __uint_as_float((267u - E) << 23);
-      const float2 s2 = make_float2(s, s), neg1 = make_float2(-1.f, -1.f);
-#pragma unroll
-      for (int p = 0; p < 16; ++p) {
-        const float2 a2 = __fmul2_rn(make_float2(v[2 * p], v[2 * p + 1]), s2);
-        const __half2 h2 = __floats2half2_rn(a2.x, a2.y);
-        const float2 r2 = __ffma2_rn(__half22float2(h2), neg1, a2);
-        const __half2 l2 = __floats2half2_rn(r2.x, r2.y);
-        w[p] = *reinterpret_cast<const uint32_t*>(&h2);
-        w[16 + p] = *reinterpret_cast<const uint32_t*>(&l2);
-      }
-      return __uint_as_float((E - 13u) << 23);
-    };
-    auto store_half = [&](const uint32_t* w, int cidx) {
-      const uint32_t ta = tmem_base + lane_sel + kTmemA + (uint32_t)(cidx * 32 + sub * 16);
-      tmem_st16(ta, w);
-      tmem_st16(ta + 128u, w + 16);
-    };
-
-    for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
-      const long long row = (long long)tile * 256 + rank * kCM + rl;
-      const bool valid = row < a.M;
-      // ---- operand of the initial layer: pair pr converts chunks pr, pr + 2 of this row of the conditioner input
-      {
-        CPROF_T0(t_l0);
-        const CondLayerDev& L0 = a.L[0];
-        float* sc_next = scs + (lcount & 1u) * (4 * kCM);
-        for (int c = pr; c < L0.k_chunks; c += 2) {
-          float v[32];
-          const float* src = a.a + row * a.lda + c * 64 + sub * 32;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && c * 64 + sub * 32 + 4 * j < a.k_in) t = __ldg(reinterpret_cast<const float4*>(src) + j);
-            v[4 * j + 0] = t.x;
-            v[4 * j + 1] = t.y;
-            v[4 * j + 2] = t.z;
-            v[4 * j + 3] = t.w;
-          }
-          float m;
-          if (!pair_max(v, m)) COND_FAIL(10);
-          uint32_t w[32];
-          const float inv = convert_half(v, m, w);
-          store_half(w, c);
-          if (sub == 0) sc_next[c * kCM + rl] = inv;
-        }
-        signal_group(0);
-        signal_group(1);
-        CPROF_ADD(r_l0, t_l0);
-      }
-      // ---- finish the previous row tile while the initial layer's MMAs run
-      CPROF_T0(t_flush);
-      if (pending) {
-        spline();
-        if (!finish_row()) COND_FAIL(8);
-      }
-      // identity columns (coupling.py:96-98) when the layer does not work in place
-      if (a.n_copy > 0 && a.y != a.x && qt == 0) {
-        const long long row0 = (long long)tile * 256 + rank * kCM + wq * 32;
-        for (int i0 = 0; i0 < a.n_copy; i0 += 32) {
-          const int cc = (i0 + lane < a.n_copy) ? __ldg(a.ccols + i0 + lane) : -1;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            if (cc >= 0 && row0 + r < a.M) a.y[(row0 + r) * a.ldy + cc] = __ldg(a.x + (row0 + r) * a.ldx + cc);
-          }
-        }
-      }
-      CPROF_ADD(r_flush, t_flush);
-      // ---- hidden layers
-      for (int l = 0; l < a.n_layers - 1; ++l, ++lcount) {
-        const CondLayerDev& L = a.L[l];
-        const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
-        float* sc_next = scs + ((lcount + 1u) & 1u) * (4 * kCM);
-        float av[64];
-        uint32_t pw[32];
-        float pre_inv = 0.f;
-        const float winv_l = vwinv[l];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const int n0 = nt * 128 + qt * 32;
-          float* hcol = hs + n0 * kCM + rl;
-          {
-            // the register accumulators start from the bias plus, in the second layer of a block, the skip connection
-            // (resnet.py:56 / made.py:181) — fetched while the first partial sums are still being computed
-            const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b = b4[j4];
-              av[nt * 32 + 4 * j4 + 0] = b.x;
-              av[nt * 32 + 4 * j4 + 1] = b.y;
-              av[nt * 32 + 4 * j4 + 2] = b.z;
-              av[nt * 32 + 4 * j4 + 3] = b.w;
-            }
-            if (L.kind == FC_COND_BLOCK_SECOND) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float2 r = __fadd2_rn(make_float2(av[nt * 32 + j], av[nt * 32 + j + 1]),
-                                            make_float2(hcol[j * kCM], hcol[(j + 1) * kCM]));
-                av[nt * 32 + j] = r.x;
-                av[nt * 32 + j + 1] = r.y;
-              }
-            }
-          }
-          for (int c = 0; c < L.k_chunks; ++c) {
-            CPROF_T0(t_w);
-            if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(6);
-            CPROF_ADD(r_wait_h, t_w);
-            CPROF_T0(t_d);
-            tc_fence_after();
-            const float inv_s = sc_cur[c * kCM + rl] * winv_l;  // both exact powers of two
-            if (nt == 1 && c == L.k_chunks - 1) {
-              // every MMA of this layer has completed: the operand in tensor memory may be overwritten.  Chunks 0 / 1 of
-              // the next operand were converted while the second N tile ran; hand them over first, so that the next
-              // layer's MMAs start while this thread finishes the second N tile
-              store_half(pw, pr);
-              if (sub == 0) sc_next[pr * kCM + rl] = pre_inv;
-              signal_group(0);
-            }
-            drain_scaled<32>(tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + qt * 32), inv_s, av + nt * 32);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote_relaxed(tempty_bar(acc_i), 0);
-            if (++acc_i == 2) {
-              acc_i = 0;
-              aph ^= 1u;
-            }
-            CPROF_ADD(r_drain_h, t_d);
-          }
-          CPROF_T0(t_f);
-          // residual stream, ReLU
-          if (L.kind == FC_COND_INITIAL || (L.kind == FC_COND_BLOCK_SECOND && L.relu_next)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) hcol[j * kCM] = av[nt * 32 + j];
-          }
-          if (L.relu_next) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) av[nt * 32 + j] = fmaxf(av[nt * 32 + j], 0.f);
-          }
-          CPROF_ADD(r_final_h, t_f);
-          CPROF_T0(t_p);
-          float m;
-          if (!pair_max(av + nt * 32, m)) COND_FAIL(11);
-          if (nt == 0) {
-            // this quarter of operand chunks 0 / 1 is final: convert now, while the second N tile is being computed
-            pre_inv = convert_half(av, m, pw);
-          } else {
-            uint32_t w[32];
-            const float inv = convert_half(av + 32, m, w);
-            store_half(w, 2 + pr);
-            if (sub == 0) sc_next[(2 + pr) * kCM + rl] = inv;
-            signal_group(1);
-          }
-          CPROF_ADD(r_prod_h, t_p);
-        }
-      }
-      // ---- final layer: N tiles of 96 parameter columns = 4 features, one per thread of the row; the spline of N tile
-      // j - 1 runs between the drains of N tile j
-      {
-        const CondLayerDev& L = a.L[a.n_layers - 1];
-        const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
-        const float winv_f = vwinv[a.n_layers - 1];
-        for (int nt = 0; nt < L.n_tiles; ++nt) {
-          float pv[PPAD];
-          const int fg = nt * 4 + qt;
-          const bool live = fg < a.D_t;
-          const int xc = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : 0;
-          const float xv = (valid && live) ? __ldg(a.x + row * a.ldx + xc) : 0.f;
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + nt * 96 + qt * PPAD);
-#pragma unroll
-            for (int j4 = 0; j4 < PPAD / 4; ++j4) {
-              const float4 b = b4[j4];
-              pv[4 * j4 + 0] = b.x;
-              pv[4 * j4 + 1] = b.y;
-              pv[4 * j4 + 2] = b.z;
-              pv[4 * j4 + 3] = b.w;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < KCH; ++c) {
-            CPROF_T0(t_w);
-            if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(7);
-            CPROF_ADD(r_wait_f, t_w);
-            CPROF_T0(t_d);
-            tc_fence_after();
-            const float inv_s = sc_cur[c * kCM + rl] * winv_f;
-            {
-              // 24 columns: one 16-column and one 8-column load
-              const uint32_t ta = tmem_base + lane_sel + kTmemAcc + (uint32_t)(acc_i * 128 + qt * PPAD);
-              uint32_t v[24];
-              tmem_ld16(ta, v);
-              tmem_ld8(ta + 16u, v + 16);
-              tmem_wait_ld();
-              const float2 s2 = make_float2(inv_s, inv_s);
-#pragma unroll
-              for (int j = 0; j < 24; j += 2) {
-                const float2 r = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), s2,
-                                            make_float2(pv[j], pv[j + 1]));
-                pv[j] = r.x;
-                pv[j + 1] = r.y;
-              }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote_relaxed(tempty_bar(acc_i), 0);
-            if (++acc_i == 2) {
-              acc_i = 0;
-              aph ^= 1u;
-            }
-            CPROF_ADD(r_drain_f, t_d);
-            CPROF_T0(t_s);
-            if (pending && c == 0) spline();
-            CPROF_ADD(r_spline, t_s);
-          }
-#pragma unroll
-          for (int j = 0; j < PPAD; ++j) ppark[j * kCM] = pv[j];
-          pxv = xv;
-          pxc = xc;
-          plive = live;
-          prow = row;
-          pvalid = valid;
-          pending = true;
-        }
-        ++lcount;
-      }
-    }
-    if (pending) {
-      spline();
-      if (!finish_row()) COND_FAIL(9);
-    }
-    if (status != 0 && a.status) atomicOr(a.status, (int)status);
-#if FC_COND_PROFILE
-    if (blockIdx.x == 0 && warp == 4 && lane == 0) {
-      g_cond_prof[8] = (unsigned long long)(clock64() - r_begin);
-      g_cond_prof[9] = (unsigned long long)r_l0;
-      g_cond_prof[10] = (unsigned long long)r_flush;
-      g_cond_prof[11] = (unsigned long long)r_wait_h;
-      g_cond_prof[12] = (unsigned long long)r_drain_h;
-      g_cond_prof[13] = (unsigned long long)r_final_h;
-      g_cond_prof[14] = (unsigned long long)r_prod_h;
-      g_cond_prof[15] = (unsigned long long)r_wait_f;
-      g_cond_prof[16] = (unsigned long long)r_drain_f;
-      g_cond_prof[17] = (unsigned long long)r_spline;
-    }
-#endif
-  } else {
+  } else if (warp < 4 + kRowWarps) {
     // ------------------------------------------------------------------ row threads, two per row
-    cond_set_max_regs_inc<232>();
+    cond_set_max_regs_inc<184>();
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int rl = q * 32 + lane;  // row inside the CTA's tile = TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     int acc_i = 0;
-    uint32_t aph = 0, lcount = 0, lph = 0;
-    unsigned status = 0;
-    // pending bijection work: the parameters of the last finished final-layer N tile
-    float pp[NF * PPAD];
-    float pxv[NF];
-    int pxc[NF];
-    bool plive[NF];
-    long long prow = 0;
-    bool pvalid = false, pending = false;
-    float lad_acc = 0.f;
+    uint32_t aph = 0, lcount = 0, pt = 0;  // pt: parameter tiles handed to the bijection warps so far
     CPROF_DECL(r_l0);
-    CPROF_DECL(r_flush);
     CPROF_DECL(r_wait_h);
     CPROF_DECL(r_drain_h);
     CPROF_DECL(r_final_h);
     CPROF_DECL(r_prod_h);
     CPROF_DECL(r_wait_f);
     CPROF_DECL(r_drain_f);
-    CPROF_DECL(r_spline);
+    CPROF_DECL(r_hand);
     CPROF_T0(r_begin);
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      pxv[f] = 0.f;
-      pxc[f] = 0;
-      plive[f] = false;
-    }
-#pragma unroll
-    for (int j = 0; j < NF * PPAD; ++j) pp[j] = 0.f;
 
     auto signal_operand = [&]() {
       tmem_wait_st();
@@ -834,14 +482,6 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(opnd_bar(g), 0);
-    };
-    auto spline = [&](int f) {
-      if (plive[f]) {
-        float yv, lv;
-        rqs_eval<KC, true>(a.c, pxv[f], pp + f * PPAD, yv, lv, status);
-        if (pvalid) a.y[prow * a.ldy + pxc[f]] = yv;
-        lad_acc += lv;
-      }
     };
 
     for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
@@ -869,40 +509,6 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
         signal_operand();
         CPROF_ADD(r_l0, t_l0);
       }
-      // ---- finish the previous row tile while the initial layer's MMAs run
-      CPROF_T0(t_flush);
-      if (pending) {
-#pragma unroll
-        for (int f = 0; f < NF; ++f) spline(f);
-        // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): the two column halves of a row are
-        // combined in a fixed order
-        if (half == 1) {
-          ladx[rl] = lad_acc;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(lad_bar);  // release: orders the 32 stores above
-        } else {
-          if (!cond_wait(lad_bar, lph, abort_s)) COND_FAIL(8);
-          if (pvalid) {
-            const float tot = lad_acc + ladx[rl];
-            a.lad[prow] = a.accumulate ? a.lad[prow] + tot : tot;
-          }
-        }
-        lph ^= 1u;
-        lad_acc = 0.f;
-        pending = false;
-      }
-      // identity columns (coupling.py:96-98) when the layer does not work in place
-      if (a.n_copy > 0 && a.y != a.x && half == 0) {
-        const long long row0 = (long long)tile * 256 + rank * kCM + q * 32;
-        for (int i0 = 0; i0 < a.n_copy; i0 += 32) {
-          const int cc = (i0 + lane < a.n_copy) ? __ldg(a.ccols + i0 + lane) : -1;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            if (cc >= 0 && row0 + r < a.M) a.y[(row0 + r) * a.ldy + cc] = __ldg(a.x + (row0 + r) * a.ldx + cc);
-          }
-        }
-      }
-      CPROF_ADD(r_flush, t_flush);
       // ---- hidden layers
       for (int l = 0; l < a.n_layers - 1; ++l, ++lcount) {
         const CondLayerDev& L = a.L[l];
@@ -912,6 +518,13 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
         uint32_t pw[64];
         float pre_inv = 0.f;
         const float winv_l = vwinv[l];
+        if (l == 0 && pt > 0) {
+          // the residual stream's space still holds the previous row tile's last parameter tiles: wait until the bijection
+          // warps have consumed both buffers (as if about to write each of them again)
+          const uint32_t n0w = (pt + 1u) >> 1, n1w = pt >> 1;  // writes so far to buffer 0 / 1
+          if (!cond_wait(pempty_bar(0), (n0w & 1u) ^ 1u, abort_s)) COND_FAIL(8);
+          if (n1w > 0 && !cond_wait(pempty_bar(1), (n1w & 1u) ^ 1u, abort_s)) COND_FAIL(9);
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int n0 = nt * 128 + half * 64;
@@ -996,23 +609,14 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
         }
         CPROF_ADD(r_prod_h, t_p);
       }
-      // ---- final layer: N tiles of 96 parameter columns; the spline of N tile j - 1 runs between the drains of N tile j
+      // ---- final layer: N tiles of 96 parameter columns, accumulated here and handed to the bijection warps through
+      // two parameter tiles [96 columns][128 rows] in the (now dead) residual stream's space
       {
         const CondLayerDev& L = a.L[a.n_layers - 1];
         const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
         const float winv_f = vwinv[a.n_layers - 1];
-        for (int nt = 0; nt < L.n_tiles; ++nt) {
+        for (int nt = 0; nt < L.n_tiles; ++nt, ++pt) {
           float pv[NF * PPAD];
-          float xv[NF];
-          int xc[NF];
-          bool live[NF];
-#pragma unroll
-          for (int f = 0; f < NF; ++f) {
-            const int fg = nt * FEATS + half * NF + f;
-            live[f] = fg < a.D_t;
-            xc[f] = live[f] ? (a.tcols ? __ldg(a.tcols + fg) : fg) : 0;
-            xv[f] = (valid && live[f]) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
-          }
           const int n0 = nt * 96 + half * (NF * PPAD);
           {
             const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
@@ -1042,53 +646,110 @@ __global__ void __launch_bounds__(128 + 32 * RW, 1) conditioner_f16x3_kernel(con
               aph ^= 1u;
             }
             CPROF_ADD(r_drain_f, t_d);
-            CPROF_T0(t_s);
-            if (pending && (c * NF) % KCH == 0) spline((c * NF) / KCH);
-            CPROF_ADD(r_spline, t_s);
           }
+          CPROF_T0(t_h);
+          const uint32_t b = pt & 1u, nw = pt >> 1;  // buffer, and how often it has been written before
+          if (!cond_wait(pempty_bar(b), (nw & 1u) ^ 1u, abort_s)) COND_FAIL(10);
+          float* pcol = hs + (b * 96 + half * (NF * PPAD)) * kCM + rl;
 #pragma unroll
-          for (int j = 0; j < NF * PPAD; ++j) pp[j] = pv[j];
-#pragma unroll
-          for (int f = 0; f < NF; ++f) {
-            pxv[f] = xv[f];
-            pxc[f] = xc[f];
-            plive[f] = live[f];
-          }
-          prow = row;
-          pvalid = valid;
-          pending = true;
+          for (int j = 0; j < NF * PPAD; ++j) pcol[j * kCM] = pv[j];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pfull_bar(b));  // release: orders the warp's stores above
+          CPROF_ADD(r_hand, t_h);
         }
         ++lcount;
       }
     }
-    if (pending) {
-#pragma unroll
-      for (int f = 0; f < NF; ++f) spline(f);
-      if (half == 1) {
-        ladx[rl] = lad_acc;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(lad_bar);
-      } else {
-        if (!cond_wait(lad_bar, lph, abort_s)) COND_FAIL(9);
-        if (pvalid) {
-          const float tot = lad_acc + ladx[rl];
-          a.lad[prow] = a.accumulate ? a.lad[prow] + tot : tot;
-        }
-      }
-    }
-    if (status != 0 && a.status) atomicOr(a.status, (int)status);
 #if FC_COND_PROFILE
     if (blockIdx.x == 0 && warp == 4 && lane == 0) {
       g_cond_prof[8] = (unsigned long long)(clock64() - r_begin);
       g_cond_prof[9] = (unsigned long long)r_l0;
-      g_cond_prof[10] = (unsigned long long)r_flush;
       g_cond_prof[11] = (unsigned long long)r_wait_h;
       g_cond_prof[12] = (unsigned long long)r_drain_h;
       g_cond_prof[13] = (unsigned long long)r_final_h;
       g_cond_prof[14] = (unsigned long long)r_prod_h;
       g_cond_prof[15] = (unsigned long long)r_wait_f;
       g_cond_prof[16] = (unsigned long long)r_drain_f;
-      g_cond_prof[17] = (unsigned long long)r_spline;
+      g_cond_prof[10] = (unsigned long long)r_hand;
+    }
+#endif
+  } else {
+    // ------------------------------------------------------------------ bijection threads, one per row
+    cond_set_max_regs_dec<104>();
+    const int r = threadIdx.x - 32 * (4 + kRowWarps);  // row inside the CTA's tile
+    unsigned status = 0;
+    uint32_t pt = 0;
+    CPROF_DECL(b_wait);
+    CPROF_DECL(b_work);
+    CPROF_T0(b_begin);
+    const int n_final = a.L[a.n_layers - 1].n_tiles;
+    for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
+      const long long row = (long long)tile * 256 + rank * kCM + r;
+      const bool valid = row < a.M;
+      // identity columns (coupling.py:96-98) when the layer does not work in place: each warp copies its 32 rows, one row
+      // per step (coalesced)
+      if (a.n_copy > 0 && a.y != a.x) {
+        const long long row0 = (long long)tile * 256 + rank * kCM + (r & ~31);
+        for (int i0 = 0; i0 < a.n_copy; i0 += 32) {
+          const int cc = (i0 + lane < a.n_copy) ? __ldg(a.ccols + i0 + lane) : -1;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (cc >= 0 && row0 + rr < a.M) a.y[(row0 + rr) * a.ldy + cc] = __ldg(a.x + (row0 + rr) * a.ldx + cc);
+          }
+        }
+      }
+      float lad_acc = 0.f;
+      for (int nt = 0; nt < n_final; ++nt, ++pt) {
+        float xv[FEATS];
+        int xc[FEATS];
+#pragma unroll
+        for (int f = 0; f < FEATS; ++f) {  // inputs first: their latency hides behind the wait for the parameters
+          const int fg = nt * FEATS + f;
+          const bool live = fg < a.D_t;
+          xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
+          xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
+        }
+        const uint32_t b = pt & 1u;
+        {
+          CPROF_T0(t_w);
+          if (!cond_wait(pfull_bar(b), (pt >> 1) & 1u, abort_s)) COND_FAIL(11);
+          CPROF_ADD(b_wait, t_w);
+        }
+        CPROF_T0(t_s);
+        const float* pcol = hs + (b * 96) * kCM + r;
+        // two features at a time: their evaluations are independent instruction streams the scheduler can interleave
+        constexpr int IL = (KC <= 8 && FEATS % 2 == 0) ? 2 : 1;
+#pragma unroll
+        for (int f0 = 0; f0 < FEATS; f0 += IL) {
+          float p[IL][PPAD];
+#pragma unroll
+          for (int i = 0; i < IL; ++i)
+#pragma unroll
+            for (int j = 0; j < PPAD; ++j) p[i][j] = pcol[((f0 + i) * PPAD + j) * kCM];
+          float yv[IL], lv[IL];
+#pragma unroll
+          for (int i = 0; i < IL; ++i) rqs_eval<KC, true>(a.c, xv[f0 + i], p[i], yv[i], lv[i], status);
+#pragma unroll
+          for (int i = 0; i < IL; ++i) {
+            if (xc[f0 + i] >= 0) {
+              if (valid) a.y[row * a.ldy + xc[f0 + i]] = yv[i];
+              lad_acc += lv[i];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pempty_bar(b));
+        CPROF_ADD(b_work, t_s);
+      }
+      // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): one thread summed all features of its row in order
+      if (valid) a.lad[row] = a.accumulate ? a.lad[row] + lad_acc : lad_acc;
+    }
+    if (status != 0 && a.status) atomicOr(a.status, (int)status);
+#if FC_COND_PROFILE
+    if (blockIdx.x == 0 && warp == 4 + kRowWarps && lane == 0) {
+      g_cond_prof[16 + 2] = (unsigned long long)(clock64() - b_begin);
+      g_cond_prof[16 + 3] = (unsigned long long)b_wait;
+      g_cond_prof[16 + 4] = (unsigned long long)b_work;
     }
 #endif
   }
@@ -1169,10 +830,9 @@ __global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict_
   }
 }
 
-template <int KC, int PPAD, int NT, int RW>
+template <int KC, int PPAD, int NT>
 static int launch_conditioner(const CondArgs& args, cudaStream_t stream) {
-  constexpr int kCondThreads = 128 + 32 * RW;
-  auto kern = conditioner_f16x3_kernel<KC, PPAD, NT, RW>;
+  auto kern = conditioner_f16x3_kernel<KC, PPAD, NT>;
   static_assert(CondSmem::TOTAL <= 232448, "shared memory per CTA");
   static std::atomic<uint64_t> configured{0};
   int dev_id = 0;
@@ -1314,15 +974,10 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
   if (cudaGetSymbolAddress(&err_ptr, g_cond_error) != cudaSuccess) return FC_ERR_CUDA;
   args.error = reinterpret_cast<int32_t*>(err_ptr);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int row_warps = [] {  // FC_COND_RW=8: two threads per row everywhere (experiments)
-    const char* e = getenv("FC_COND_RW");
-    return e ? atoi(e) : 16;
-  }();
   if (net->hidden == 256) {
-    if (c.K == 8 && row_warps == 16) return launch_conditioner<8, 24, 2, 16>(args, st);
-    if (c.K == 8) return launch_conditioner<8, 24, 2, 8>(args, st);
-    return launch_conditioner<16, 48, 2, 8>(args, st);
+    if (c.K == 8) return launch_conditioner<8, 24, 2>(args, st);
+    return launch_conditioner<16, 48, 2>(args, st);
   }
-  if (c.K == 8) return launch_conditioner<8, 24, 1, 8>(args, st);
-  return launch_conditioner<16, 48, 1, 8>(args, st);
+  if (c.K == 8) return launch_conditioner<8, 24, 1>(args, st);
+  return launch_conditioner<16, 48, 1>(args, st);
 }

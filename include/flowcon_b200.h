@@ -364,9 +364,10 @@ int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* a, int64_t 
 int fc_conditioner_error(int32_t* out);
 /* Debugging aid (library built with -DFC_COND_PROFILE=1, else all zero): cycles CTA 0's MMA-issuing warp ([0] total, [1]
  * waiting for the operand, [2] for a free partial accumulator, [3] for a weight slot, [4] slots) and its first row warp
- * ([8] total, [9] initial operand, [10] deferred bijection, [11]/[12]/[13]/[14] hidden layers: waiting for a partial
- * accumulator / draining / bias-skip-ReLU / converting the next operand, [15]/[16]/[17] final layer: waiting / draining /
- * bijection) spent in the last fc_conditioner_* launch.  Synchronises the device. */
+ * ([8] total, [9] initial operand, [10] parameter hand-off, [11]/[12]/[13]/[14] hidden layers: waiting for a partial
+ * accumulator / draining / skip-ReLU / converting the next operand, [15]/[16] final layer: waiting / draining) and its
+ * first bijection warp ([18] total, [19] waiting for parameters, [20] evaluating) spent in the last fc_conditioner_*
+ * launch.  Synchronises the device. */
 int fc_conditioner_profile(unsigned long long* out32);
 
 /* Library / build info (also used by the loader test). */
