@@ -16,9 +16,10 @@
 //
 // Arithmetic: "3xFP16".  The reference computes these products in fp32.  Every operand is split a = hi + lo with hi, lo
 // fp16 (11 significant bits each, like the tf32 split of fc_linear.cu) after scaling by an exact power of two — per
-// (row, 64-value chunk) for the activations, per output row for the weights — so that the largest magnitude sits in
-// [2^13, 2^14): hi + lo then reproduces the scaled value to 2^-22 relative (2^-38 of the chunk's maximum for small
-// entries), and nothing overflows fp16.  Products  lo*hi + hi*lo + hi*hi  run as tcgen05.mma.kind::f16 (twice the
+// (row, 64-value chunk) for the activations, per layer for the weights — so that the largest magnitude sits in
+// [2^7, 2^14) (activations; the sum of the chunk's magnitudes is scaled into [2^13, 2^14)) or [2^13, 2^14) (weights):
+// hi + lo then reproduces the scaled value to 2^-22 relative (2^-32 of the chunk's maximum for small entries), and
+// nothing overflows fp16.  Products  lo*hi + hi*lo + hi*hi  run as tcgen05.mma.kind::f16 (twice the
 // tf32 rate, measured: scripts/microbench/tmem_rate.cu) into an fp32 accumulator in tensor memory.  As in
 // fc_linear.cu the tensor core truncates on accumulation, so every 64 k-values (12 MMAs) the partial sum is handed
 // to the row's thread, which adds  partial * 2^-e(row, chunk)  into a register accumulator with round-to-nearest while
@@ -204,10 +205,20 @@ __device__ __forceinline__ void drain_scaled(uint32_t taddr, float inv_s, float*
 // 64 fp32 values of one row -> packed (hi, lo) fp16 words of one operand chunk (w[0..32) hi plane, w[32..64) lo plane),
 // scaled by the power of two that puts the largest magnitude into [2^13, 2^14).  Returns 1 / scale (exact).
 __device__ __forceinline__ float convert_chunk(const float* v, uint32_t* w) {
-  float m = 0.f;
+  // The scale only has to put the chunk's largest magnitude somewhere into [2^7, 2^14) (see the header comment: hi + lo
+  // then still carries 2^-22 relative, 2^-32 of the maximum for small entries).  The sum of the magnitudes bounds the
+  // maximum from above within a factor of 64, and costs 64 full-rate additions in four independent chains; a running
+  // maximum compiles to a chain of 3-input min/max instructions that issue once per ~8 cycles (measured:
+  // scripts/microbench/alu_rate.cu, 320 -> 75 cycles per chunk).
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 64; ++j) m = fmaxf(m, fabsf(v[j]));
-  m = fmaxf(m, 1e-30f);
+  for (int j = 0; j < 64; j += 4) {
+    m0 += fabsf(v[j]);
+    m1 += fabsf(v[j + 1]);
+    m2 += fabsf(v[j + 2]);
+    m3 += fabsf(v[j + 3]);
+  }
+  float m = fminf(fmaxf((m0 + m1) + (m2 + m3), 1e-30f), 1e30f);
   const uint32_t E = __float_as_uint(m) >> 23;  // biased exponent (m > 0)
   const float s = __uint_as_float((267u - E) << 23);      // 2^(13 - (E - 127))
   const float inv_s = __uint_as_float((E - 13u) << 23);   // 2^((E - 127) - 13)
@@ -241,8 +252,9 @@ struct CondSmem {
   static constexpr int RING_BYTES = kCondStages * kSlotBytes;
   static constexpr int H_BYTES = 256 * kCM * 4;      // residual stream [256 columns][128 rows]
   static constexpr int SC_BYTES = 2 * 4 * kCM * 4;   // 1 / operand scale: [layer parity][chunk][row]
-  static constexpr int BAR_BYTES = 8 * (3 * kCondStages + 11) + 16;
-  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + kVecBytes + BAR_BYTES + 1024;
+  static constexpr int LAD_BYTES = 2 * 2 * kCM * 4;  // per-row log-det partial sums of the two row threads, double-buffered
+  static constexpr int BAR_BYTES = 8 * (3 * kCondStages + 12) + 16;
+  static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + kVecBytes + BAR_BYTES + 1024;
 };
 
 // KC bins, PPAD accumulator columns per feature, NT = hidden width / 128
@@ -250,18 +262,21 @@ template <int KC, int PPAD, int NT>
 __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(const CondArgs a) {
   constexpr int KCH = 2 * NT;         // 64-value chunks of a hidden-width reduction
   constexpr int FEATS = 96 / PPAD;    // features per final N tile
-  constexpr int NF = FEATS / 2;       // ... per thread (two threads share a row)
-  static_assert(NF >= 1 && NF * 2 * PPAD == 96, "final N tile: 96 columns");
+  constexpr int NF = FEATS / 2;       // ... per row thread (two threads share a row)
+  constexpr int NF_OWN = (NF + 1) / 2;  // features of an N tile a row thread evaluates itself ...
+  constexpr int NF_BIJ = NF - NF_OWN;   // ... and hands to its row's bijection thread (8 bins: one each; 16 bins: 1 / 0)
+  static_assert(NF >= 1 && NF * 2 * PPAD == 96 && NF_OWN == 1, "final N tile: 96 columns");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 1023u) & ~1023u;
   unsigned char* const gbase = smem_raw + (base - raw_s);
   float* const hs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES);
   float* const scs = reinterpret_cast<float*>(gbase + CondSmem::RING_BYTES + CondSmem::H_BYTES);
+  float* const ladx = scs + 2 * 4 * kCM;  // [tile parity][column half][row]
   // bias[total_cols], then 1 / weight scale of each layer
-  float* const vbias = scs + 2 * 4 * kCM;
+  float* const vbias = ladx + 2 * 2 * kCM;
   float* const vwinv = vbias + a.total_cols;
-  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + kVecBytes;
+  const uint32_t bars = base + CondSmem::RING_BYTES + CondSmem::H_BYTES + CondSmem::SC_BYTES + CondSmem::LAD_BYTES + kVecBytes;
   unsigned char* const gbars = gbase + (bars - base);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto ready_bar = [&](int s) { return bars + 8u * (kCondStages + s); };   // leader's: both halves have landed
@@ -272,9 +287,10 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   // parameter tiles (final layer): written by the row warps / consumed by the bijection warps
   auto pfull_bar = [&](int b) { return bars + 8u * (3 * kCondStages + 6 + b); };
   auto pempty_bar = [&](int b) { return bars + 8u * (3 * kCondStages + 8 + b); };
-  const uint32_t tmem_slot = bars + 8u * (3 * kCondStages + 10);
-  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbars + 8 * (3 * kCondStages + 10));
-  volatile int* const abort_s = reinterpret_cast<volatile int*>(gbars + 8 * (3 * kCondStages + 10) + 8);
+  const uint32_t lad_bar = bars + 8u * (3 * kCondStages + 10);  // the row threads' log-det partial sums of a row tile are written
+  const uint32_t tmem_slot = bars + 8u * (3 * kCondStages + 11);
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbars + 8 * (3 * kCondStages + 11));
+  volatile int* const abort_s = reinterpret_cast<volatile int*>(gbars + 8 * (3 * kCondStages + 11) + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -294,6 +310,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       mbar_init(pfull_bar(i), kRowWarps);
       mbar_init(pempty_bar(i), kBijWarps);
     }
+    mbar_init(lad_bar, kRowWarps);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
@@ -455,7 +472,17 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     const int rl = q * 32 + lane;  // row inside the CTA's tile = TMEM lane
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     int acc_i = 0;
-    uint32_t aph = 0, lcount = 0, pt = 0;  // pt: parameter tiles handed to the bijection warps so far
+    uint32_t aph = 0, lcount = 0, pt = 0, tcount = 0;  // pt: parameter tiles handed to the bijection warps so far
+    unsigned status = 0;
+    // pending bijection work: this thread's own feature of the last finished final-layer N tile
+    float pp[PPAD];
+    float pxv = 0.f, lad_acc = 0.f;
+    int pxc = -1;
+    long long prow = 0;
+    bool pvalid = false, pending = false;
+#pragma unroll
+    for (int j = 0; j < PPAD; ++j) pp[j] = 0.f;
+    CPROF_DECL(r_spline);
     CPROF_DECL(r_l0);
     CPROF_DECL(r_wait_h);
     CPROF_DECL(r_drain_h);
@@ -483,6 +510,23 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(opnd_bar(g), 0);
     };
+    auto spline = [&]() {
+      if (pxc >= 0) {
+        float yv, lv;
+        rqs_eval<KC, true>(a.c, pxv, pp, yv, lv, status);
+        if (pvalid) a.y[prow * a.ldy + pxc] = yv;
+        lad_acc += lv;
+      }
+      pending = false;
+    };
+    // this thread's share of the row tile's log|det J| goes to the row's bijection thread, which sums and stores it
+    auto finish_tile = [&]() {
+      ladx[((tcount & 1u) * 2 + half) * kCM + rl] = lad_acc;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(lad_bar);  // release: orders the warp's stores above
+      lad_acc = 0.f;
+      ++tcount;
+    };
 
     for (int tile = cl0; tile < a.num_tiles; tile += cl_step) {
       const long long row = (long long)tile * 256 + rank * kCM + rl;
@@ -509,6 +553,13 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         signal_operand();
         CPROF_ADD(r_l0, t_l0);
       }
+      // ---- finish the previous row tile while the initial layer's MMAs run
+      if (pending) {
+        CPROF_T0(t_s);
+        spline();
+        finish_tile();
+        CPROF_ADD(r_spline, t_s);
+      }
       // ---- hidden layers
       for (int l = 0; l < a.n_layers - 1; ++l, ++lcount) {
         const CondLayerDev& L = a.L[l];
@@ -518,7 +569,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         uint32_t pw[64];
         float pre_inv = 0.f;
         const float winv_l = vwinv[l];
-        if (l == 0 && pt > 0) {
+        if (l == 0 && pt > 0 && NF_BIJ > 0) {
           // the residual stream's space still holds the previous row tile's last parameter tiles: wait until the bijection
           // warps have consumed both buffers (as if about to write each of them again)
           const uint32_t n0w = (pt + 1u) >> 1, n1w = pt >> 1;  // writes so far to buffer 0 / 1
@@ -609,14 +660,19 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         }
         CPROF_ADD(r_prod_h, t_p);
       }
-      // ---- final layer: N tiles of 96 parameter columns, accumulated here and handed to the bijection warps through
-      // two parameter tiles [96 columns][128 rows] in the (now dead) residual stream's space
+      // ---- final layer: N tiles of 96 parameter columns.  Of the features whose parameters it accumulates, a row thread
+      // evaluates one itself — the spline of N tile j - 1 between the drains of N tile j — and hands the other to the row's
+      // bijection thread through one of two parameter tiles in the (now dead) residual stream's space
       {
         const CondLayerDev& L = a.L[a.n_layers - 1];
         const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
         const float winv_f = vwinv[a.n_layers - 1];
         for (int nt = 0; nt < L.n_tiles; ++nt, ++pt) {
           float pv[NF * PPAD];
+          const int fg = nt * FEATS + half * NF;  // this thread's own feature
+          const bool live = fg < a.D_t;
+          const int xc = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
+          const float xv = (valid && live) ? __ldg(a.x + row * a.ldx + xc) : 0.f;
           const int n0 = nt * 96 + half * (NF * PPAD);
           {
             const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
@@ -646,20 +702,39 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
               aph ^= 1u;
             }
             CPROF_ADD(r_drain_f, t_d);
+            if (c == 0 && pending) {
+              CPROF_T0(t_s);
+              spline();
+              CPROF_ADD(r_spline, t_s);
+            }
           }
-          CPROF_T0(t_h);
-          const uint32_t b = pt & 1u, nw = pt >> 1;  // buffer, and how often it has been written before
-          if (!cond_wait(pempty_bar(b), (nw & 1u) ^ 1u, abort_s)) COND_FAIL(10);
-          float* pcol = hs + (b * 96 + half * (NF * PPAD)) * kCM + rl;
+          if constexpr (NF_BIJ > 0) {
+            CPROF_T0(t_h);
+            const uint32_t b = pt & 1u, nw = pt >> 1;  // buffer, and how often it has been written before
+            if (!cond_wait(pempty_bar(b), (nw & 1u) ^ 1u, abort_s)) COND_FAIL(10);
+            float* pcol = hs + (b * (2 * NF_BIJ * PPAD) + half * (NF_BIJ * PPAD)) * kCM + rl;
 #pragma unroll
-          for (int j = 0; j < NF * PPAD; ++j) pcol[j * kCM] = pv[j];
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pfull_bar(b));  // release: orders the warp's stores above
-          CPROF_ADD(r_hand, t_h);
+            for (int j = 0; j < NF_BIJ * PPAD; ++j) pcol[j * kCM] = pv[NF_OWN * PPAD + j];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pfull_bar(b));  // release: orders the warp's stores above
+            CPROF_ADD(r_hand, t_h);
+          }
+#pragma unroll
+          for (int j = 0; j < PPAD; ++j) pp[j] = pv[j];
+          pxv = xv;
+          pxc = xc;
+          prow = row;
+          pvalid = valid;
+          pending = true;
         }
         ++lcount;
       }
     }
+    if (pending) {
+      spline();
+      finish_tile();
+    }
+    if (status != 0 && a.status) atomicOr(a.status, (int)status);
 #if FC_COND_PROFILE
     if (blockIdx.x == 0 && warp == 4 && lane == 0) {
       g_cond_prof[8] = (unsigned long long)(clock64() - r_begin);
@@ -671,6 +746,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       g_cond_prof[15] = (unsigned long long)r_wait_f;
       g_cond_prof[16] = (unsigned long long)r_drain_f;
       g_cond_prof[10] = (unsigned long long)r_hand;
+      g_cond_prof[17] = (unsigned long long)r_spline;
     }
 #endif
   } else {
@@ -678,7 +754,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     cond_set_max_regs_dec<104>();
     const int r = threadIdx.x - 32 * (4 + kRowWarps);  // row inside the CTA's tile
     unsigned status = 0;
-    uint32_t pt = 0;
+    uint32_t pt = 0, tcount = 0;
     CPROF_DECL(b_wait);
     CPROF_DECL(b_work);
     CPROF_T0(b_begin);
@@ -699,50 +775,52 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         }
       }
       float lad_acc = 0.f;
-      for (int nt = 0; nt < n_final; ++nt, ++pt) {
-        float xv[FEATS];
-        int xc[FEATS];
+      if constexpr (NF_BIJ > 0) {
+        for (int nt = 0; nt < n_final; ++nt, ++pt) {
+          // the features the two row threads of this row hand over: the last NF_BIJ of each half of the N tile
+          float xv[2 * NF_BIJ];
+          int xc[2 * NF_BIJ];
 #pragma unroll
-        for (int f = 0; f < FEATS; ++f) {  // inputs first: their latency hides behind the wait for the parameters
-          const int fg = nt * FEATS + f;
-          const bool live = fg < a.D_t;
-          xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
-          xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
-        }
-        const uint32_t b = pt & 1u;
-        {
-          CPROF_T0(t_w);
-          if (!cond_wait(pfull_bar(b), (pt >> 1) & 1u, abort_s)) COND_FAIL(11);
-          CPROF_ADD(b_wait, t_w);
-        }
-        CPROF_T0(t_s);
-        const float* pcol = hs + (b * 96) * kCM + r;
-        // two features at a time: their evaluations are independent instruction streams the scheduler can interleave
-        constexpr int IL = (KC <= 8 && FEATS % 2 == 0) ? 2 : 1;
+          for (int f = 0; f < 2 * NF_BIJ; ++f) {  // inputs first: their latency hides behind the wait for the parameters
+            const int fg = nt * FEATS + (f / NF_BIJ) * NF + NF_OWN + (f % NF_BIJ);
+            const bool live = fg < a.D_t;
+            xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
+            xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
+          }
+          const uint32_t b = pt & 1u;
+          {
+            CPROF_T0(t_w);
+            if (!cond_wait(pfull_bar(b), (pt >> 1) & 1u, abort_s)) COND_FAIL(11);
+            CPROF_ADD(b_wait, t_w);
+          }
+          CPROF_T0(t_s);
+          const float* pcol = hs + (b * (2 * NF_BIJ * PPAD)) * kCM + r;
 #pragma unroll
-        for (int f0 = 0; f0 < FEATS; f0 += IL) {
-          float p[IL][PPAD];
+          for (int f = 0; f < 2 * NF_BIJ; ++f) {
+            float p[PPAD];
 #pragma unroll
-          for (int i = 0; i < IL; ++i)
-#pragma unroll
-            for (int j = 0; j < PPAD; ++j) p[i][j] = pcol[((f0 + i) * PPAD + j) * kCM];
-          float yv[IL], lv[IL];
-#pragma unroll
-          for (int i = 0; i < IL; ++i) rqs_eval<KC, true>(a.c, xv[f0 + i], p[i], yv[i], lv[i], status);
-#pragma unroll
-          for (int i = 0; i < IL; ++i) {
-            if (xc[f0 + i] >= 0) {
-              if (valid) a.y[row * a.ldy + xc[f0 + i]] = yv[i];
-              lad_acc += lv[i];
+            for (int j = 0; j < PPAD; ++j) p[j] = pcol[(f * PPAD + j) * kCM];
+            float yv, lv;
+            rqs_eval<KC, true>(a.c, xv[f], p, yv, lv, status);
+            if (xc[f] >= 0) {
+              if (valid) a.y[row * a.ldy + xc[f]] = yv;
+              lad_acc += lv;
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pempty_bar(b));
+          CPROF_ADD(b_work, t_s);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pempty_bar(b));
-        CPROF_ADD(b_work, t_s);
       }
-      // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): one thread summed all features of its row in order
-      if (valid) a.lad[row] = a.accumulate ? a.lad[row] + lad_acc : lad_acc;
+      // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): the row's three evaluating threads summed their
+      // features in order; the partial sums are combined in a fixed order
+      if (!cond_wait(lad_bar, tcount & 1u, abort_s)) COND_FAIL(12);
+      {
+        const float* lx = ladx + (tcount & 1u) * (2 * kCM);
+        const float tot = (lx[r] + lx[kCM + r]) + lad_acc;
+        if (valid) a.lad[row] = a.accumulate ? a.lad[row] + tot : tot;
+      }
+      ++tcount;
     }
     if (status != 0 && a.status) atomicOr(a.status, (int)status);
 #if FC_COND_PROFILE
