@@ -21,7 +21,7 @@ AFFINE_BLOCKED, AFFINE_INTERLEAVED = 0, 1
 SCALE_SIGMOID2, SCALE_SOFTPLUS_CLAMP3, SCALE_SOFTPLUS_EPS = 0, 1, 2
 LINEAR_A_T128, LINEAR_OUT_T128, LINEAR_RESIDUAL_GATES = 1, 2, 4
 
-EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_linspline_apply", "fc_linspline_backward",
+EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_rqs_bins", "fc_linspline_apply", "fc_linspline_backward",
            "fc_quadspline_apply", "fc_quadspline_backward", "fc_cubicspline_apply", "fc_cubicspline_backward", "fc_affine_apply", "fc_affine_backward", "fc_sos_apply",
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
@@ -92,6 +92,7 @@ def lib():
                                    ctypes.POINTER(RqsConfig), vp, vp]
         L.fc_rqs_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols,
                                       ctypes.POINTER(RqsConfig), vp]
+        L.fc_rqs_bins.argtypes = [vp, i64, vp, i64, i64, i32, Cols, ctypes.POINTER(RqsConfig), vp, vp, vp]
         L.fc_linspline_apply.argtypes = [vp, i64, vp, i64, vp, i64, vp, i32, i64, i32, Cols, Cols, i32, i32, f32, f32,
                                          f32, f32, i32, vp, vp]
         L.fc_linspline_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, Cols, Cols, i32,

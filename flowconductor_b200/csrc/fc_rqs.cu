@@ -33,9 +33,59 @@ struct RqsOp {
     default: CALL(0); break;   \
   }
 
+// Debug / parity aid: the bin every element falls into, computed by exactly the device arithmetic of the layer kernels
+// (rqs_domain + rqs_locate of fc_math.cuh: base-2 softmax on the SFU, running-sum knots, "last true wins" search).
+template <int KC>
+__global__ void rqs_bins_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ params,
+                                int64_t p_stride, const int32_t* __restrict__ tcols, int64_t B, int D_t, RqsParams c,
+                                int32_t* __restrict__ bins, float* __restrict__ knot_dist) {
+  const int64_t total = B * D_t;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D_t;
+    const int j = (int)(i % D_t);
+    const float xv = x[r * x_stride + (tcols ? tcols[j] : j)];
+    const float* p = params + r * p_stride + (int64_t)j * c.P;
+    unsigned status = 0;
+    float xs;
+    const bool inside = rqs_domain(c, xv, xs, status);
+    const int K = KC ? KC : c.K;
+    float ew[KC ? KC : FC_MAX_BINS_GENERIC], eh[KC ? KC : FC_MAX_BINS_GENERIC];
+    float inv_w, inv_h;
+    RqsBin b;
+    rqs_locate<KC>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
+    bins[i] = inside ? b.k : -1;
+    if (knot_dist) {
+      // distance to the nearest knot of the searched axis, in units of the interval length
+      const float lo = c.inverse ? b.ch : b.cw, sz = c.inverse ? b.h : b.w;
+      const float span = c.inverse ? (c.top - c.bottom) : (c.right - c.left);
+      knot_dist[i] = inside ? fminf(fabsf(xs - lo), fabsf(lo + sz - xs)) / span : INFINITY;
+    }
+  }
+}
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_rqs_bins(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride, int64_t B,
+                           int32_t D_t, fc_cols tcols, const fc_rqs_config* cfg, int32_t* bins, float* knot_dist,
+                           void* stream) {
+  RqsParams c;
+  int rc = make_rqs_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  if (B < 0 || D_t <= 0 || (tcols.idx && tcols.n != D_t)) return FC_ERR_INVALID_ARGUMENT;
+  if (B == 0) return FC_OK;
+  if (!x || !params || !bins) return FC_ERR_INVALID_ARGUMENT;
+  const int64_t total = B * D_t;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+#define CALL(KC)                                                                                                        \
+  rqs_bins_kernel<KC><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_row_stride, params, params_row_stride, tcols.idx, B, \
+                                                                D_t, c, bins, knot_dist);
+  FC_DISPATCH_K(c.K, CALL)
+#undef CALL
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
 
 extern "C" int fc_rqs_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
                             float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,

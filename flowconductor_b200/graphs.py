@@ -39,7 +39,12 @@ class GraphedCall:
     object.  `__call__` copies new inputs into those buffers, replays the graph and returns the static outputs
     (valid until the next replay — `clone()` what must live longer, or pass `clone=True`)."""
 
-    def __init__(self, fn, *example_inputs, warmup=3, pool=None):
+    def __init__(self, fn, *example_inputs, warmup=3, pool=None, module=None):
+        """module: the nn.Module whose conditioners `fn` runs (default: `fn.__self__` when `fn` is a bound method of a
+        module).  The recorded graph contains no weight-packing kernels — the packed tensor-core weights were built during
+        the warm-up — so every replay first compares the module's parameter keys (pointer, in-place version) and the
+        packed-weight cache generation with those at capture, and records the graph again when the weights have moved on
+        (optimizer step, load_state_dict, `tensorcore.invalidate`)."""
         if not example_inputs and not torch.cuda.is_available():
             raise RuntimeError("flowconductor_b200.graphs needs a CUDA device (no CPU fallback)")
         for t in example_inputs:
@@ -49,6 +54,23 @@ class GraphedCall:
         self._fn = fn
         self._static_in = [t.detach().clone() for t in example_inputs]
         self.device = self._static_in[0].device if self._static_in else torch.device("cuda", torch.cuda.current_device())
+        if module is None and isinstance(getattr(fn, "__self__", None), torch.nn.Module):
+            module = fn.__self__
+        self._module = module
+        self._warmup, self._pool = warmup, pool
+        self.records = 0
+        self.replays = 0
+        self._record()
+
+    def _weights_state(self):
+        from .nn import tensorcore
+
+        if self._module is None:
+            return None
+        return (tensorcore.cache_generation(), tensorcore.module_param_key(self._module))
+
+    def _record(self):
+        fn, warmup, pool = self._fn, self._warmup, self._pool
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.device(self.device), torch.no_grad():
             # warm-up on a side stream: builds the packed-weight plans, sets kernel attributes, fills the allocator
@@ -62,7 +84,8 @@ class GraphedCall:
             with torch.cuda.graph(self.graph, pool=pool):
                 self._static_out = fn(*self._static_in)
         self._flat_out = _flatten(self._static_out)
-        self.replays = 0
+        self._state = self._weights_state()  # after the warm-up built the plans
+        self.records += 1
 
     def __call__(self, *inputs, clone=False):
         if len(inputs) != len(self._static_in):
@@ -73,6 +96,8 @@ class GraphedCall:
                     tuple(dst.shape), dst.dtype, tuple(src.shape), src.dtype))
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        if self._module is not None and self._weights_state() != self._state:
+            self._record()  # the weights changed since capture: the graph holds stale packed copies
         self.graph.replay()
         self.replays += 1
         if not clone:
@@ -100,8 +125,8 @@ def capture_sampler(flow, num_samples, context=None, with_log_prob=False, warmup
         if not next(flow.parameters()).is_cuda:
             raise RuntimeError("graph capture needs the flow on a CUDA device (no CPU fallback)")
         with torch.cuda.device(next(flow.parameters()).device):
-            return GraphedCall(lambda: method(num_samples), warmup=warmup)
-    return GraphedCall(lambda c: method(num_samples, context=c), context, warmup=warmup)
+            return GraphedCall(lambda: method(num_samples), warmup=warmup, module=flow)
+    return GraphedCall(lambda c: method(num_samples, context=c), context, warmup=warmup, module=flow)
 
 
 class GraphedTrainStep:

@@ -126,6 +126,18 @@ def _param_key(net):
     return tuple((p.data_ptr(), p._version) for p in net.parameters())
 
 
+_generation = [0]  # bumped whenever a packed-weight plan is built or dropped
+
+
+def cache_generation():
+    return _generation[0]
+
+
+def module_param_key(module):
+    """(pointer, in-place version) of every parameter under `module`: changes on optimizer steps / load_state_dict."""
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
 def invalidate(module):
     """Drop the packed-weight plans cached on `module` and its sub-modules.  The cache key is (data pointer, in-place
     version counter) of every parameter; a write through `.data` (EMA swaps such as `p.data.copy_(...)`, collectives on
@@ -136,16 +148,7 @@ def invalidate(module):
             object.__setattr__(m, "_fc_plan", None)
         if getattr(m, "_fc_cond_plan", None) is not None:
             object.__setattr__(m, "_fc_cond_plan", None)
-
-
-def plan_keys(module):
-    """{net: key} of every conditioner under `module` that has a cached plan (graphs.GraphedCall compares them at
-    replay: a captured graph contains no pack kernels and would otherwise keep using the old weights)."""
-    keys = {}
-    for m in module.modules():
-        if getattr(m, "_fc_plan", None) is not None or getattr(m, "_fc_cond_plan", None) is not None:
-            keys[m] = _param_key(m)
-    return keys
+    _generation[0] += 1
 
 
 class _Plan:
@@ -185,6 +188,7 @@ def plan_for(net, col_map, k_in, final_kind, final_group=None):
     else:
         plan.final = _pack_layer(fin)
     object.__setattr__(net, "_fc_plan", plan)
+    _generation[0] += 1
     return plan
 
 
@@ -258,6 +262,7 @@ def cond_plan_for(net, col_map, k_in, num_bins, d_t):
         return plan[1]
     packed = fcond.pack_rqs(net, num_bins, d_t, col_map=col_map, k_in=k_in)
     object.__setattr__(net, "_fc_cond_plan", (key, packed))
+    _generation[0] += 1
     return packed
 
 

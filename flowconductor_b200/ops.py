@@ -53,6 +53,28 @@ def rqs_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: Optiona
     return y, lad, status
 
 
+def rqs_bins(x, params, tcols, num_bins, tails, inverse, identity_init, left, right, bottom, top, min_bin_width,
+             min_bin_height, min_derivative, wh_scale):
+    """Parity aid (fc_rqs_bins): (bins int32 [B, D_t], knot distance [B, D_t]) as the kernels' own arithmetic sees them;
+    bin -1 = outside the linear tails.  Same argument meaning as `rqs_layer`."""
+    _cabi.require_cuda_f32(x, "inputs")
+    _cabi.require_cuda_f32(params, "transform params")
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    params, pp, ps = _cabi.rows(params)
+    B = x.shape[0]
+    d_t = tcols.numel() if tcols is not None else x.shape[1]
+    bins = torch.empty((B, d_t), dtype=torch.int32, device=x.device)
+    dist = torch.empty((B, d_t), dtype=torch.float32, device=x.device)
+    cfg = _cfg(num_bins, tails, inverse, identity_init, left, right, bottom, top, min_bin_width, min_bin_height,
+               min_derivative, wh_scale)
+    with torch.cuda.device(x.device), _cabi.launch("fc_rqs_bins", x.device):
+        rc = L.fc_rqs_bins(xp, xs, pp, ps, B, d_t, _cabi.cols(tcols), ctypes.byref(cfg), bins.data_ptr(), dist.data_ptr(),
+                           _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_rqs_bins")
+    return bins, dist
+
+
 @rqs_layer.register_fake
 def _(x, params, tcols, ccols, num_bins, tails, inverse, identity_init, left, right, bottom, top, min_bin_width,
       min_bin_height, min_derivative, wh_scale):

@@ -104,6 +104,10 @@ WORKLOADS = {
                                          {"kind": "pcubic_coupling", "mask": "alternating_odd", "num_bins": 8,
                                           "tails": "linear", "tail_bound": 3.0, "hidden_features": 16,
                                           "num_blocks": 2}]},
+    # autoregressive.py:460-523: the constrained unit box (cubic_spline without tails), no pre-scale (MADE has no
+    # hidden_features)
+    "maf_pcubic_small": {"features": 5, "context_features": None, "batch": 64,
+                         "layers": [{"kind": "maf_pcubic", "num_bins": 8, "hidden_features": 16, "num_blocks": 2}]},
     "prq_coupling_notails_small": {"features": 6, "context_features": None, "batch": 64,
                                    "layers": [{"kind": "prq_coupling", "mask": "mid_split", "num_bins": 5,
                                                "tails": None, "tail_bound": 1.0, "hidden_features": 16,
@@ -129,7 +133,7 @@ def params_per_feature(layer):
         return 3 * layer["n_sigmoids"] + 1
     if kind in ("plin_coupling", "maf_plin"):
         return layer["num_bins"]
-    if kind == "pcubic_coupling":
+    if kind in ("pcubic_coupling", "maf_pcubic"):
         return 2 * layer["num_bins"] + 2
     if kind in ("pquad_coupling", "maf_pquad"):
         return 2 * layer["num_bins"] - 1 if layer.get("tails") == "linear" else 2 * layer["num_bins"] + 1
@@ -179,7 +183,7 @@ def trained_like_(state, workload, seed=1, weight_gain=8.0):
                "maf_prq": "autoregressive_net", "maf_sos": "autoregressive_net", "cond_sos": "conditional_net",
                "cond_prq": "conditional_net", "plin_coupling": "transform_net", "maf_plin": "autoregressive_net",
                "pquad_coupling": "transform_net", "maf_pquad": "autoregressive_net",
-               "pcubic_coupling": "transform_net"}[kind]
+               "pcubic_coupling": "transform_net", "maf_pcubic": "autoregressive_net"}[kind]
         wkey = layer_prefix(i) + net + ".final_layer.weight"
         bkey = layer_prefix(i) + net + ".final_layer.bias"
         p = params_per_feature(layer)
@@ -251,6 +255,10 @@ def build_flow(workload, seed=0):
                 tail_bound=layer["tail_bound"]))
         elif kind == "maf_plin":
             layers.append(transforms.MaskedPiecewiseLinearAutoregressiveTransform(
+                num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
+                context_features=ctx, num_blocks=layer["num_blocks"]))
+        elif kind == "maf_pcubic":
+            layers.append(transforms.MaskedPiecewiseCubicAutoregressiveTransform(
                 num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
                 context_features=ctx, num_blocks=layer["num_blocks"]))
         elif kind == "affine_coupling":

@@ -75,6 +75,16 @@ int fc_rqs_apply(const float* x, int64_t x_row_stride, const float* params, int6
                  int32_t* status, void* stream);
 
 /*
+ * Parity aid (not on the data path): the bin index the kernels' own arithmetic selects for every transformed element
+ * — what searchsorted (utils/torchutils.py:147-149) returns inside rational_quadratic_spline (:115-118) — and
+ * optionally the element's distance to the nearest knot of the searched axis in units of the interval length.
+ * bins / knot_dist: [B, D_t] row-major; bin -1 = outside the linear tails (identity).  The north-star criterion "bin
+ * indices identical except for inputs within 1e-6 of a knot" is asserted with this on the GPU.
+ */
+int fc_rqs_bins(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride, int64_t B,
+                int32_t D_t, fc_cols tcols, const fc_rqs_config* cfg, int32_t* bins, float* knot_dist, void* stream);
+
+/*
  * Backward of fc_rqs_apply (the reference differentiates its op chain with autograd).
  * grad_params is written densely ([B, D_t*P], zero where the reference's gradient is zero).
  *   grad_x[r, tcols[j]] = grad_y[r, tcols[j]] * dy/dx + grad_logabsdet[r] * d lad/dx

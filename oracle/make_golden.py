@@ -326,6 +326,10 @@ def build_reference_flow(wl, seed=0):
             layers.append(transforms.MaskedPiecewiseLinearAutoregressiveTransform(
                 num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
                 context_features=ctx, num_blocks=layer["num_blocks"]))
+        elif kind == "maf_pcubic":
+            layers.append(transforms.MaskedPiecewiseCubicAutoregressiveTransform(
+                num_bins=layer["num_bins"], features=features, hidden_features=layer["hidden_features"],
+                context_features=ctx, num_blocks=layer["num_blocks"]))
         elif kind == "maf_affine":
             layers.append(transforms.MaskedAffineAutoregressiveTransform(
                 features=features, hidden_features=layer["hidden_features"], context_features=ctx,
@@ -407,6 +411,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-cubic-models":
         make_model("pcubic_coupling_small", with_grad=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-maf-cubic":
+        make_model("maf_pcubic_small", with_grad=True, uniform01=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-quadratic-functions":
         make_quadratic_functions()

@@ -816,6 +816,11 @@ def apply_layer(state, spec, inputs, context=None, inverse=False):
         def ew(x, params):
             return cubic_elementwise(x, params, spec["num_bins"], spec.get("tails"), spec.get("tail_bound", 1.0), inverse,
                                      math.sqrt(spec["hidden_features"]))
+    elif kind == "maf_pcubic":
+        # autoregressive.py:492-517: always the constrained unit box; the /sqrt(hidden) of :507-509 never happens
+        # (transforms.made.MADE has no `hidden_features` attribute)
+        def ew(x, params):
+            return cubic_elementwise(x, params, spec["num_bins"], None, 1.0, inverse, 1.0)
     elif kind in ("pquad_coupling", "maf_pquad"):
         # coupling.py:409-411: widths and heights / sqrt(hidden) when the conditioner exposes it (ResidualNet yes, MADE no)
         div = math.sqrt(spec["hidden_features"]) if kind == "pquad_coupling" else 1.0

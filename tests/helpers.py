@@ -80,3 +80,25 @@ def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0, max_ratio=
                     ["%.2e" % v for v in qo.tolist()], ["%.2e" % v for v in qr.tolist()], float(e64.max()),
                     float(noise.max())))
     return worst
+
+
+def parity_report(ours, ref32, ref64, tol, floor, slack=4.0):
+    """The numbers behind assert_parity, for the logs (print the strict-fail fraction): fraction of elements
+    failing criterion (i) alone, fraction failing both (i) and (ii), and the error quantiles of ours / the reference's own
+    fp32 against fp64."""
+    ours = ours.detach().double().cpu()
+    r32 = ref32.detach().double().cpu()
+    r64 = ref64.detach().double().cpu()
+    if ours.numel() == 0:
+        return "empty"
+    e32 = (ours - r32).abs()
+    e64 = (ours - r64).abs()
+    noise = (r32 - r64).abs()
+    fail1 = ~(e32 <= tol * r32.abs().clamp_min(floor))
+    fail2 = ~(e64 <= slack * noise + tol * r64.abs().clamp_min(floor))
+    q = torch.tensor([0.5, 0.99, 1.0], dtype=torch.float64)
+    qo = torch.quantile(e64.flatten(), q).tolist()
+    qr = torch.quantile(noise.flatten(), q).tolist()
+    return ("strict-fail (i) %.2e, (i)&(ii) %.2e of %d; |ours-fp64| p50/p99/max %.1e/%.1e/%.1e, |ref32-fp64| %.1e/%.1e/%.1e"
+            % (float(fail1.double().mean()), float((fail1 & fail2).double().mean()), ours.numel(), qo[0], qo[1], qo[2],
+               qr[0], qr[1], qr[2]))

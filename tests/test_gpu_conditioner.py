@@ -1,0 +1,288 @@
+"""GPU parity tests of the fused conditioner kernel (csrc/fc_conditioner.cu, C ABI fc_conditioner_*) and of the round-2
+parity items: bin indices on the device, the D = 256 (cfg 5) shapes, the in-place ownership protocol, packed-weight cache
+invalidation.  Everything goes through the C ABI (ctypes) like the rest of the GPU suite."""
+import math
+
+import pytest
+import torch
+from torch import nn
+
+from flowconductor_b200 import _cabi, conditioner as fcond, graphs, ops, transforms, workloads
+from flowconductor_b200.nn import tensorcore
+from flowconductor_b200.nn.nets.resnet import ResidualNet
+from flowconductor_b200.transforms.made import MADE
+from oracle import restated
+from tests.helpers import assert_parity, load_golden, parity_report
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# bin indices on the device (north_star: identical except for inputs within 1e-6 of a knot)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rq_fwd_lin_k8", "rq_inv_lin_k8", "rq_fwd_lin_k16_id", "rq_inv_lin_k16_id",
+                                  "rq_fwd_none_k5", "rq_inv_none_k5", "rq_fwd_lin_k10_b1"])
+def test_bin_indices_match_reference_on_gpu(dev, name):
+    """The bins selected by the DEVICE arithmetic (ex2.approx softmax, running-sum knots: fc_rqs_bins runs the same
+    rqs_locate as the layer kernels) against the bins of the unmodified reference's searchsorted
+    (flowcon/utils/torchutils.py:147-149) stored with the golden vectors.  Every mismatch is reported with its distance to
+    the nearest knot in units of the interval; none may be further than 1e-6 from a knot."""
+    gold = load_golden("functions")
+    k, lin, tb, inv, ident = gold[name + "/meta"].tolist()
+    k = int(k)
+    x = gold[name + "/x"].to(dev)
+    p = gold[name + "/params"].to(dev)
+    n, d = x.shape
+    lo, hi = (-tb, tb) if lin else (0.0, 1.0)
+    tails = _cabi.TAILS_LINEAR if lin else _cabi.TAILS_NONE
+    bins, dist = ops.rqs_bins(x, p.reshape(n, -1), None, k, tails, bool(inv), bool(ident), lo, hi, lo, hi, 1e-3, 1e-3, 1e-3,
+                              1.0)
+    ref = gold[name + "/bin"].to(dev)
+    inside = (x >= lo) & (x <= hi)
+    assert bool((bins[~inside] == -1).all())
+    mism = inside & (bins.long() != ref)
+    # distance of the input to the nearest REFERENCE knot, normalised
+    knots = gold[name + "/knots"].to(dev)
+    dref = (x[..., None] - knots).abs().min(-1).values / (hi - lo)
+    lines = ["(%d, %d): ours %d reference %d, knot distance %.3e (device) %.3e (reference)" % (
+        i, j, bins[i, j], ref[i, j], dist[i, j], dref[i, j]) for i, j in torch.nonzero(mism).tolist()]
+    print("%s: %d elements, %d inside, %d bin mismatches" % (name, x.numel(), int(inside.sum()), len(lines)))
+    for line in lines:
+        print("   " + line)
+    assert bool((dref[mism] <= 1e-6).all()), "bin mismatch further than 1e-6 from a knot:\n" + "\n".join(lines)
+    assert float(mism.float().mean()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# fc_conditioner_rqs_apply against an fp64 conditioner + the element-wise kernel
+# ------------------------------------------------------------------------------------------------
+def _random_net(kind, d_in, hidden, out, blocks, dev, seed):
+    torch.manual_seed(seed)
+    if kind == "resnet":
+        net = ResidualNet(d_in, out, hidden, num_blocks=blocks)
+    else:
+        net = MADE(d_in, hidden, num_blocks=blocks, output_multiplier=out // d_in)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, p in net.named_parameters():  # away from the near-identity initialisation of the blocks
+            scale = 1.5 / math.sqrt(p.shape[-1]) if p.dim() == 2 else 0.3
+            p.copy_(torch.randn(p.shape, generator=g) * scale)
+        net.final_layer.weight.mul_(3.0)
+    return net.to(dev)
+
+
+def _net_fp64(net, a):
+    """The conditioner in fp64 (masks applied as made.py:72 does)."""
+    def lin(layer, t):
+        w = layer.weight.double()
+        if getattr(layer, "mask", None) is not None:
+            w = w * layer.mask.double()
+        return torch.nn.functional.linear(t, w, layer.bias.double())
+
+    h = lin(net.initial_layer, a.double())
+    for blk in net.blocks:
+        t = lin(blk.linear_layers[0], torch.relu(h))
+        h = h + lin(blk.linear_layers[1], torch.relu(t))
+    return lin(net.final_layer, h)
+
+
+@pytest.mark.parametrize("kind,B,D,K,H,blocks,inverse,inplace", [
+    ("resnet", 1000, 64, 8, 256, 2, False, False),     # cfg 2 shape, ragged last tile, fresh output (identity columns copied)
+    ("resnet", 4096, 64, 8, 256, 2, True, True),       # inverse, in place
+    ("resnet", 1, 64, 8, 256, 1, False, False),        # a single row
+    ("resnet", 257, 20, 8, 128, 3, False, True),       # hidden width 128, three blocks, one row into the second tile pair
+    ("resnet", 700, 256, 8, 256, 2, False, False),     # cfg 5 shape: 128 transformed features, 32 final N tiles, k_in 256
+    ("made", 1500, 16, 16, 256, 2, False, False),      # cfg 3 shape: masked layers, 16 bins, k_in 16
+    ("made", 300, 8, 8, 128, 1, True, False),
+])
+def test_conditioner_kernel(dev, kind, B, D, K, H, blocks, inverse, inplace):
+    P = 3 * K - 1
+    coupling = kind == "resnet"
+    d_t = D // 2 if coupling else D
+    tcols = torch.arange(0, D, 2, device=dev, dtype=torch.int32) if coupling else None
+    ccols = torch.arange(1, D, 2, device=dev, dtype=torch.int32) if coupling else None
+    net = _random_net(kind, d_t if coupling else D, H, d_t * P, blocks, dev, seed=B + D)
+    g = torch.Generator(device=dev).manual_seed(B)
+    x = torch.randn(B, D, generator=g, device=dev) * 1.5
+    wh = 1.0 / math.sqrt(H) if coupling else 1.0
+    cfg = _cabi.RqsConfig(K, _cabi.TAILS_LINEAR, int(not coupling), int(inverse), -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, wh)
+    packed = fcond.pack_rqs(net, K, d_t, col_map=ccols, k_in=D)
+    xin = x.clone()
+    y = xin if inplace else torch.empty_like(x)
+    lad = torch.full((B,), 7.0, device=dev)  # accumulate = False must overwrite
+    fcond.rqs_apply(packed, xin, xin, y, lad, False, d_t, tcols, ccols, cfg, None)
+    torch.cuda.synchronize()
+    assert fcond.kernel_error() == 0
+    a = x[:, 1::2] if coupling else x
+    with torch.no_grad():
+        p64 = _net_fp64(net, a).float()
+        p32 = net(a)
+    args = (K, _cabi.TAILS_LINEAR, inverse, not coupling, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, wh)
+    y2, lad2, _ = ops.rqs_layer(x, p64, tcols, ccols, *args)
+    y3, lad3, _ = ops.rqs_layer(x, p32, tcols, ccols, *args)
+    if coupling:
+        assert torch.equal(y[:, 1::2], x[:, 1::2])
+    q = torch.tensor([0.5, 0.99, 1.0], device=dev)
+    for ours, ref, yard, slack in ((y, y2, y3, 3e-6), (lad, lad2, lad3, 3e-5)):
+        eo = torch.quantile((ours - ref).abs().flatten().float(), q)
+        ey = torch.quantile((yard - ref).abs().flatten().float(), q)
+        assert bool((eo <= 4 * ey + slack * max(1.0, ref.abs().max().item())).all()), (eo, ey)
+    # accumulate = True adds to what is there
+    lad_acc = torch.full((B,), 2.0, device=dev)
+    fcond.rqs_apply(packed, x, x, torch.empty_like(x), lad_acc, True, d_t, tcols, ccols, cfg, None)
+    assert torch.allclose(lad_acc, lad + 2.0, atol=1e-5, rtol=1e-6)
+
+
+def test_conditioner_argument_errors(dev):
+    net = _random_net("resnet", 32, 64, 32 * 23, 2, dev, seed=0)  # hidden width 64: not covered
+    with pytest.raises(ValueError):
+        fcond.pack_rqs(net, 8, 32)
+    net = _random_net("resnet", 32, 256, 32 * 23, 2, dev, seed=0)
+    packed = fcond.pack_rqs(net, 8, 32, k_in=32)
+    x = torch.randn(10, 32, device=dev)
+    cfg = _cabi.RqsConfig(8, _cabi.TAILS_NONE, 0, 0, 0.0, 1.0, 0.0, 1.0, 1e-3, 1e-3, 1e-3, 1.0)
+    with pytest.raises(RuntimeError, match="unsupported"):  # tails=None is not fused
+        fcond.rqs_apply(packed, x, x, torch.empty_like(x), torch.empty(10, device=dev), False, 32, None, None, cfg)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        fcond.rqs_apply(packed, x.cpu(), x, torch.empty_like(x), torch.empty(10, device=dev), False, 32, None, None, cfg)
+    # empty batch: nothing launched, nothing touched
+    cfg = _cabi.RqsConfig(8, _cabi.TAILS_LINEAR, 0, 0, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 1.0)
+    e = torch.empty(0, 32, device=dev)
+    fcond.rqs_apply(packed, e, e, torch.empty_like(e), torch.empty(0, device=dev), False, 32, None, None, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# cfg 5 (D = 256) and cfg 3 (MADE, 16 bins) layer by layer against the oracle, every inference path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,rows", [("cfg5", 4096), ("cfg3", 2048), ("cfg2", 4096)])
+@pytest.mark.parametrize("path", ["fused", "perlayer", "unfused"])
+def test_layers_match_oracle(dev, name, rows, path, monkeypatch):
+    """Every layer of the full-size model on its own (input = the fp32 oracle's output of the previous layer), three-way
+    against the fp32 / fp64 oracle at the strict criteria.  fused = one persistent kernel per layer (3xFP16), perlayer =
+    round 1's per-layer tensor-core kernels (3xTF32), unfused = torch conditioner + element-wise kernel."""
+    monkeypatch.setattr(tensorcore, "ENABLED", path != "unfused")
+    monkeypatch.setattr(tensorcore, "FUSED_CONDITIONER", path == "fused")
+    wl = workloads.get_workload(name)
+    flow = workloads.build_flow(wl)
+    state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl)
+    flow.load_state_dict(state)
+    specs = workloads.oracle_specs(wl)
+    state64 = {k: (v.double() if v.is_floating_point() else v) for k, v in state.items()}
+    flow = flow.to(dev)
+    h = torch.randn(rows, wl["features"], generator=torch.Generator().manual_seed(99))
+    report = []
+    with torch.no_grad():
+        for li, (layer, spec) in enumerate(zip(flow._transform._transforms, specs)):
+            y64, l64 = restated.apply_layer(state64, spec, h.double())
+            y32, l32 = restated.apply_layer(state, spec, h)
+            _cabi.STATS.reset()
+            y, lad = layer(h.to(dev))
+            if spec["kind"] != "permutation":
+                fused_calls = _cabi.STATS.counts.get("fc_conditioner_rqs_apply", 0)
+                assert fused_calls == (1 if path == "fused" else 0), _cabi.STATS.counts
+            assert_parity(y, y32, y64, OUT_TOL, 1.0, "%s layer %d outputs (%s)" % (name, li, path))
+            assert_parity(lad, l32, l64, OUT_TOL, 1.0, "%s layer %d logabsdet (%s)" % (name, li, path))
+            report.append((li, parity_report(y, y32, y64, OUT_TOL, 1.0), parity_report(lad, l32, l64, OUT_TOL, 1.0)))
+            h = y32
+    for li, ry, rl in report:
+        print("%s layer %d (%s): outputs %s | logabsdet %s" % (name, li, path, ry, rl))
+
+
+def test_fused_and_perlayer_paths_agree_on_a_whole_flow(dev, monkeypatch):
+    """cfg 2 at 20 000 rows, whole stack: the two tensor-core paths differ only by rounding (different splits and
+    summation orders), log_prob agrees to the noise of either against the oracle; inverse(forward) per layer."""
+    wl = workloads.get_workload("cfg2")
+    flow = workloads.build_flow(wl)
+    flow.load_state_dict(workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl))
+    flow = flow.to(dev)
+    x = torch.randn(20000, 64, generator=torch.Generator(device=dev).manual_seed(5), device=dev)
+    out = {}
+    with torch.no_grad():
+        for fused in (True, False):
+            monkeypatch.setattr(tensorcore, "FUSED_CONDITIONER", fused)
+            out[fused] = flow.log_prob(x)
+        monkeypatch.setattr(tensorcore, "FUSED_CONDITIONER", True)
+        layer = flow._transform._transforms[0]
+        y, lad = layer(x)
+        xr, ladr = layer.inverse(y)
+    rel = (out[True] - out[False]).abs() / out[False].abs().clamp_min(1.0)
+    assert rel.median() < 2e-6 and torch.quantile(rel, 0.999) < 2e-4
+    assert torch.equal(xr[:, 1::2], x[:, 1::2])
+    err = (xr - x).abs()
+    assert err.median() < 1e-6 and torch.quantile(err.flatten()[: 1 << 20], 0.999) < 2e-4
+    assert (lad + ladr).abs().median() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side protocols around the kernels
+# ------------------------------------------------------------------------------------------------
+class _ReusesItsInput(transforms.Transform):
+    """A wrapper layer that calls a kernel layer and then reads its own input again: the inner layer must
+    not have overwritten it."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+
+    def forward(self, inputs, context=None):
+        y, lad = self.inner(inputs, context)
+        y2, lad2 = self.inner(inputs, context)  # a second kernel layer on the same input
+        return y + 0.0 * (y2 - inputs), lad
+
+
+def test_in_place_consent_is_consumed_by_the_first_kernel_layer(dev):
+    wl = workloads.get_workload("cfg2_tc_small")
+    flow = workloads.build_flow(wl)
+    flow.load_state_dict(workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl))
+    flow = flow.to(dev)
+    layers = list(flow._transform._transforms)
+    plain = transforms.CompositeTransform(layers)
+    wrapped = transforms.CompositeTransform([layers[0], _ReusesItsInput(layers[1]), layers[2]])
+    x = torch.randn(512, 64, generator=torch.Generator(device=dev).manual_seed(0), device=dev)
+    with torch.no_grad():
+        want, lad_want = plain(x.clone())
+        got, lad_got = wrapped(x.clone())
+    assert torch.equal(want, got) and torch.equal(lad_want, lad_got)
+    # a view of the cascade's intermediate never qualifies either
+    t = torch.randn(8, 4, device=dev)
+    with torch.no_grad():
+        tensorcore.begin_layer(t)
+        tensorcore.mark_fresh(t)
+        tensorcore.begin_layer(t)
+        assert tensorcore.may_overwrite(t) and not tensorcore.may_overwrite(t[:, :]) and not tensorcore.may_overwrite(t.clone())
+        tensorcore.consume_consent()
+        assert not tensorcore.may_overwrite(t)
+        tensorcore.end_cascade()
+
+
+def test_packed_weights_follow_parameter_updates(dev):
+    """writes through .data change neither pointer nor version; `tensorcore.invalidate` and
+    `distributed.broadcast_parameters` drop the cached plans, and a captured graph re-records when the weights moved on."""
+    wl = workloads.get_workload("cfg2_tc_small")
+    flow = workloads.build_flow(wl)
+    flow.load_state_dict(workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl))
+    flow = flow.to(dev)
+    x = torch.randn(256, 64, generator=torch.Generator(device=dev).manual_seed(0), device=dev)
+    with torch.no_grad():
+        before = flow.log_prob(x).clone()
+        g = graphs.capture(flow.log_prob, x)
+        assert torch.equal(g(x), before)
+        for p in flow.parameters():  # an optimizer-like in-place update bumps the version counter
+            p.add_(0.01 * torch.randn_like(p))
+        after = flow.log_prob(x).clone()
+        assert not torch.equal(before, after)
+        assert torch.equal(g(x), after), "graph replay must notice the new weights"
+        net = flow._transform._transforms[0].transform_net
+        net.final_layer.bias.data.add_(0.5)  # .data write: invisible to the cache key ...
+        tensorcore.invalidate(flow)           # ... so the caller says so
+        again = flow.log_prob(x)
+        assert not torch.equal(after, again)
+        assert torch.equal(g(x), again)
