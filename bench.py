@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — Flow.log_prob samples/s of the RQ-spline coupling flow (BASELINE.json configs[1]:
-D=64, K=8 bins, 8 layers, H=256, linear tails at 3.0, batch 1M synthetic Gaussian, fp32).
+"""bench.py — Flow.log_prob samples/s of the RQ-spline coupling flow (BASELINE.json configs[1]: D=64, K=8 bins, 8 layers,
+H=256, linear tails at 3.0, batch 1M synthetic Gaussian, fp32), plus the other two bench-size configs on request.
 
-    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W      # CPU port of the reference (oracle), host cores
+    python bench.py --gpus N --steps K --warmup W                       # this repo's CUDA path, cfg 2 (the metric's config)
+    python bench.py --impl reference --steps K --warmup W               # the UNMODIFIED reference on the host cores
+    python bench.py --workload cfg5 [--rows R]                          # D=256 flow, R (default 100M) rows streamed in 1M-row
+                                                                        # chunks generated on device, sharded over the ranks
+    python bench.py --workload cfg3_train [--graph]                     # MAF-RQS training step with gradient all-reduce
 
-A step is one `flow.log_prob` pass over one batch resident in HBM (per GPU: weak scaling — every rank owns
-its own 1M-row shard, no data-path collective; one 2-element all-reduce of the log-likelihood sum per step).
-Prints ONE JSON line (contract in the task statement): value = whole-job samples/s with inputs resident,
-e2e = same through the public host-batch API (`distributed.host_log_prob`: pinned HOST buffers, chunked H2D of the
-batch overlapping the kernels + D2H of log_prob, all inside the timed region), roofline = the RQ-spline layer kernel against the measured HBM copy peak, cpu_baseline = the
-oracle port on the box's host cores on a bounded sample.
+cfg 2: a step is one `flow.log_prob` pass over one batch resident in HBM (per GPU: weak scaling — every rank owns its own
+1M-row shard, no data-path collective; one 2-element all-reduce of the log-likelihood sum per step).  Prints ONE JSON line
+(contract in the task statement): value = whole-job samples/s with inputs resident; e2e = the same through the public
+host-batch API (`distributed.host_log_prob`: pinned HOST buffers, chunked H2D overlapping the kernels + D2H of log_prob,
+all inside the timed region); roofline = the fused conditioner + spline kernel against the measured dense fp16 tensor rate
+(and roofline_elementwise = the stand-alone RQ-spline layer kernel against the measured HBM copy peak); cpu_baseline = the
+unmodified reference (oracle/_ref) on the box's host cores on a bounded sample; gpu_eager_baseline = the unmodified
+reference in eager mode on this GPU (the real "before" number).
 """
 import argparse
 import json
@@ -30,9 +35,12 @@ METRIC = "flow_log_prob_samples_per_sec"
 UNIT = "samples/s"
 WORKLOAD = "cfg2"
 CPU_SAMPLE_ROWS = 262144      # cpu_baseline leg of the default run (~10-30 s of host work)
-REF_STEP_ROWS = 65536         # --impl reference: rows per step (bounded so K+W steps end within minutes)
+# --impl reference: rows per step.  The reference's CPU path runs at ~1.5-3 k samples/s per 8 cores: the
+# 1M-row step of our arm would take 5-10 minutes EACH, so the step is a bounded sample of the same workload (the
+# per-sample rate is flat in the batch size: 33.0 k/s at 262144 rows vs 34.1 k/s at 65536).
+REF_STEP_ROWS = {"cfg2": 65536, "cfg5": 16384, "cfg3_train": 8192}
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
-FALLBACK_BF16_TFLOPS = 2250.0
+FALLBACK_BF16_TFLOPS = 1400.0  # sustained dense bf16 (same guide)
 
 
 def parse():
@@ -41,9 +49,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=WORKLOAD)
-    ap.add_argument("--batch", type=int, default=None, help="rows per GPU (default: the workload's batch)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["cfg2", "cfg5", "cfg3_train"])
+    ap.add_argument("--batch", type=int, default=None, help="cfg2: rows per GPU (default: the workload's batch)")
+    ap.add_argument("--rows", type=int, default=None, help="cfg5 / cfg3_train: GLOBAL rows per step (default 100M / 262144)")
+    ap.add_argument("--graph", action="store_true", help="cfg3_train: replay the whole step from one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -58,17 +69,17 @@ def measured_peak():
 
 
 def measured_tensor_peak():
-    """Dense tf32 tensor peak in TFLOP/s = half the measured dense bf16 rate (kind::tf32 UMMAs retire 8 k-values
-    per 128xN instruction where kind::f16 retires 16).  The kernels run inside a long step -> sustained figure."""
+    """Dense fp16 / bf16 tensor peak in TFLOP/s (the fused kernel issues kind::f16 UMMAs).  The kernel runs inside a long
+    step -> the sustained figure."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            return (float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2,
-                    "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2 = dense tf32)")
+            return (float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "measured (MEASURED_PEAKS.json bf16_tflops_sustained: dense 16-bit tensor rate under the power cap)")
         except Exception:
             pass
-    return FALLBACK_BF16_TFLOPS / 2, "fallback (B200_PROFILING.md nominal dense bf16 2250 / 2 = dense tf32)"
+    return FALLBACK_BF16_TFLOPS, "fallback (B200_PROFILING.md sustained dense bf16)"
 
 
 def profile_json(name):
@@ -81,11 +92,13 @@ def profile_json(name):
     return {}
 
 
-def build_state(wl):
+def build_state(wl, trained_like=True):
     from flowconductor_b200 import workloads
 
     flow = workloads.build_flow(wl, seed=0)
-    state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl, seed=1)
+    state = {k: v.clone() for k, v in flow.state_dict().items()}
+    if trained_like:
+        state = workloads.trained_like_(state, wl, seed=1)
     flow.load_state_dict(state)
     return flow, state
 
@@ -146,84 +159,230 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU port of the reference (oracle) — used for cpu_baseline and for --impl reference
+# the reference (test infrastructure: oracle/): unmodified package from oracle/_ref (or /root/reference) when it can be
+# imported, else the restatement oracle/restated.py
 # ------------------------------------------------------------------------------------------------
+def reference_flow(wl, state, device="cpu"):
+    """The workload built from the UNMODIFIED reference's own classes with our state_dict, or None."""
+    try:
+        from oracle import locate
+
+        if not locate.have_reference():
+            return None
+        from oracle import make_golden
+
+        flow = make_golden.build_reference_flow(wl)
+        flow.load_state_dict(state)
+        return flow.to(device).eval()
+    except Exception as exc:  # noqa: BLE001  (the reference is optional test infrastructure)
+        sys.stderr.write("reference import failed: {}\n".format(exc))
+        return None
+
+
 def cpu_log_prob_rate(wl, state, rows, repeats=1, warmup=0):
-    """samples/s of oracle.restated.flow_log_prob on the host cores (all threads), fp32."""
+    """(samples/s, seconds per pass, kind) of the reference's log_prob on the host cores (all threads), fp32."""
     from flowconductor_b200 import workloads
-    from oracle import restated
 
     torch.set_num_threads(os.cpu_count() or 1)
-    specs = workloads.oracle_specs(wl)
     x = torch.randn(rows, wl["features"], generator=torch.Generator().manual_seed(1234))
+    ref = reference_flow(wl, state)
+    if ref is not None:
+        kind = "reference"
+
+        def run():
+            ref.log_prob(x)
+    else:
+        from oracle import restated
+
+        kind = "port"
+        specs = workloads.oracle_specs(wl)
+
+        def run():
+            restated.flow_log_prob(state, specs, x)
     times = []
     with torch.no_grad():
         for i in range(warmup + repeats):
             t0 = time.perf_counter()
-            restated.flow_log_prob(state, specs, x)
+            run()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return rows * len(times) / sum(times), sum(times) / len(times)
+    return rows * len(times) / sum(times), sum(times) / len(times), kind
+
+
+def cpu_train_step_rate(wl, state, rows, repeats, warmup):
+    """cfg 3 training step of the reference on the host cores: zero_grad, -log_prob.mean, backward, Adam."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = reference_flow(wl, state)
+    kind = "reference"
+    if ref is None:
+        from flowconductor_b200 import workloads
+        from oracle import restated
+
+        kind = "port"
+        specs = workloads.oracle_specs(wl)
+        params = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in state.items()}
+        plist = [p for p in params.values() if p.requires_grad]
+
+        def loss_fn(xb):
+            return -restated.flow_log_prob(params, specs, xb).mean()
+    else:
+        ref.train()
+        plist = list(ref.parameters())
+
+        def loss_fn(xb):
+            return -ref.log_prob(xb).mean()
+    opt = torch.optim.Adam(plist, lr=1e-3, weight_decay=1e-5)
+    x = torch.randn(rows, wl["features"], generator=torch.Generator().manual_seed(1234))
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss_fn(x).backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return rows * len(times) / sum(times), sum(times) / len(times), kind
 
 
 def run_reference(args, wl):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
-    Python/PyTorch, so there is no compiled oracle/_ref).  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores.  Rank 0 only; the
+    other ranks of a torchrun launch exit without work — this is NOT an N-GPU run, whatever --gpus says."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    _, state = build_state(wl)
-    rate, sec = cpu_log_prob_rate(wl, state, REF_STEP_ROWS, repeats=args.steps, warmup=args.warmup)
+    rows = REF_STEP_ROWS[args.workload]
+    if args.workload == "cfg3_train":
+        _, state = build_state(wl, trained_like=False)
+        rate, sec, kind = cpu_train_step_rate(wl, state, rows, args.steps, args.warmup)
+        metric = "train_step_samples_per_sec"
+    else:
+        _, state = build_state(wl)
+        rate, sec, kind = cpu_log_prob_rate(wl, state, rows, repeats=args.steps, warmup=args.warmup)
+        metric = METRIC
     cores = os.cpu_count() or 1
-    sample = "{} rows of {} per step, {} steps after {} warm-up, torch CPU fp32".format(
-        REF_STEP_ROWS, wl["name"], args.steps, args.warmup)
+    sample = ("{} rows of {} per step ({} steps after {} warm-up), {} on torch CPU fp32, all {} host threads; bounded sample of "
+              "the GPU arm's workload: the full-size step would take minutes each on the host".format(
+                  rows, wl["name"], args.steps, args.warmup,
+                  "the unmodified reference (oracle/_ref)" if kind == "reference" else "oracle/restated.py", cores))
+    cfg = config_dict(args, wl, rows, 1)
+    cfg["parallelism"] = "host CPU only, rank 0 (launched with --gpus {}: the GPUs are idle in this arm)".format(args.gpus)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(wl, REF_STEP_ROWS, args.gpus),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def config_dict(wl, rows_per_gpu, n_gpus):
-    first = wl["layers"][0]
-    return {"workload": "{}: PiecewiseRationalQuadraticCouplingTransform flow log_prob, D={}, K={}, {} layers, H={}, "
-                        "tails=linear@{}".format(wl["name"], wl["features"], first.get("num_bins"),
-                                                 len(wl["layers"]), first.get("hidden_features"),
-                                                 first.get("tail_bound")),
-            "rows_per_gpu": rows_per_gpu, "global_rows": rows_per_gpu * n_gpus,
+def config_dict(args, wl, rows_per_gpu, n_gpus):
+    first = [l for l in wl["layers"] if l["kind"] != "permutation"][0]
+    n_layers = len([l for l in wl["layers"] if l["kind"] != "permutation"])
+    if args.workload == "cfg3_train":
+        what = ("{}: MaskedPiecewiseRationalQuadraticAutoregressiveTransform (MAF-RQS) training step (zero_grad, "
+                "-log_prob.mean, backward, gradient all-reduce, Adam), D={}, K={}, {} layers, H={}".format(
+                    wl["name"], wl["features"], first.get("num_bins"), n_layers, first.get("hidden_features")))
+        l2 = "activations of one step (GBs) exceed the 126 MB L2"
+    else:
+        what = ("{}: PiecewiseRationalQuadraticCouplingTransform flow log_prob, D={}, K={}, {} layers, H={}, "
+                "tails=linear@{}".format(wl["name"], wl["features"], first.get("num_bins"), n_layers,
+                                         first.get("hidden_features"), first.get("tail_bound")))
+        l2 = "inputs_larger_than_l2 (x is {} MB per 1M rows vs 126 MB L2)".format(wl["features"] * 4)
+    return {"workload": what, "rows_per_gpu": rows_per_gpu, "global_rows": rows_per_gpu * n_gpus,
             "parallelism": "row-sharded x{} (replicated weights, no data-path collective)".format(n_gpus),
-            "weights": "random init seed 0 + trained-like perturbation seed 1 (SURVEY 8d)",
-            "l2": "inputs_larger_than_l2 (x 268 MB + 3 GB of spline parameters per layer vs 126 MB L2)"}
+            "weights": "random init seed 0" + ("" if args.workload == "cfg3_train"
+                                               else " + trained-like perturbation seed 1 (SURVEY 8d)"),
+            "l2": l2}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, wl):
+def setup_dist(args):
     import torch.distributed as dist
-
-    from flowconductor_b200 import _cabi
-    from flowconductor_b200 import distributed as fdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus {} needs torchrun (one process per GPU)".format(args.gpus))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus {} needs torchrun (one process per GPU)".format(args.gpus))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    _cabi.lib()
+    return world, rank, local_rank, dev
 
+
+def conditioner_flops(wl):
+    """(algorithmic, executed-on-the-tensor-pipe) flops per row of ONE flow layer's conditioner (2 * (D_id H +
+    2 nb H^2 + H D_t P); executed: 3 fp16 products per fp32 product on the padded shapes — the first layer reads the
+    full-width row padded to 64, the final layer 24 columns per feature in 96-column tiles)."""
+    first = [l for l in wl["layers"] if l["kind"] != "permutation"][0]
+    D, H, nb, K = wl["features"], first["hidden_features"], first["num_blocks"], first["num_bins"]
+    coupling = first["kind"] == "prq_coupling"
+    d_t = D // 2 if coupling else D
+    d_in = D - d_t if coupling else D
+    p_per = 3 * K - 1
+    ppad = {8: 24, 16: 48}[K]
+    feats = 96 // ppad
+    alg = 2.0 * (d_in * H + 2 * nb * H * H + H * d_t * p_per)
+    k0_pad = (D + 63) // 64 * 64
+    n_final = (d_t + feats - 1) // feats * 96
+    executed = 3 * 2.0 * (k0_pad * H + 2 * nb * H * H + H * n_final)
+    return alg, executed
+
+
+def gpu_eager_baseline(wl, state, x):
+    """The UNMODIFIED reference in eager mode on this GPU (fp32, TF32 off — torch's default), same weights, same rows."""
+    ref = None
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = reference_flow(wl, state, device=x.device)
+        if ref is None:
+            return {"unavailable": "reference package not importable (oracle/_ref missing)"}
+        rows = x.shape[0]
+        with torch.no_grad():
+            while True:
+                try:
+                    ref.log_prob(x[:rows])
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    rows //= 2
+                    if rows < 1024:
+                        raise
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            reps = 3
+            for _ in range(reps):
+                ref.log_prob(x[:rows])
+            e.record()
+            torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / reps
+        return {"value": rows / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "rows": rows, "kind": "reference",
+                "how": "unmodified reference package (oracle/_ref) on cuda, eager mode, fp32, allow_tf32=False, same "
+                       "state_dict, {} passes after 1 warm-up".format(reps)}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": "{}: {}".format(type(exc).__name__, str(exc)[:200])}
+    finally:
+        del ref
+        torch.cuda.empty_cache()
+
+
+def run_cfg2(args, wl):
+    import torch.distributed as dist
+
+    from flowconductor_b200 import _cabi
+    from flowconductor_b200 import distributed as fdist
+
+    world, rank, local_rank, dev = setup_dist(args)
+    _cabi.lib()
     flow, state = build_state(wl)
     flow = flow.to(dev).eval()
     B = args.batch or wl["batch"]
@@ -238,7 +397,7 @@ def run_ours(args, wl):
     def step(inp):
         with torch.no_grad():
             lp = flow.log_prob(inp)
-            total, count = (lp.double().sum(), lp.numel()) if world == 1 else fdist.reduce_log_likelihood(lp)
+            total = lp.double().sum() if world == 1 else fdist.reduce_log_likelihood(lp)[0]
         return lp, total
 
     for _ in range(args.warmup):
@@ -261,8 +420,8 @@ def run_ours(args, wl):
     _cabi.STATS.timing = False
     ms = start.elapsed_time(end)
     launches = _cabi.STATS.total()
-    n_f, f_ms = _cabi.STATS.elapsed_ms("fc_linear_rqs_apply")   # final conditioner layer + spline (tensor cores)
-    n_h, h_ms = _cabi.STATS.elapsed_ms("fc_linear_apply")       # other conditioner layers (tensor cores)
+    counts = dict(_cabi.STATS.counts)
+    n_c, c_ms = _cabi.STATS.elapsed_ms("fc_conditioner_rqs_apply")  # whole conditioner + spline, one launch per flow layer
     clocks = sampler.stop() if rank == 0 else None
     ll = float(total.item())
     assert ll == ll, "log-likelihood is NaN"
@@ -296,36 +455,27 @@ def run_ours(args, wl):
         e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
         first = wl["layers"][0]
         d_t = D // 2
-        H = first["hidden_features"]
         p_per = 3 * first["num_bins"] - 1
-        # (1) the fused final-layer kernel (north_star item 3): tensor bound.  Algorithmic flops per launch =
-        # 2 * rows * H * (D_t * P); the kernel executes 3 tf32 UMMAs per product on N padded to 24 columns
-        # per feature, so the tensor pipe does 3 * 2 * rows * H * (D_t * 24).
+        # (1) the dominant kernel: the whole conditioner + spline of one flow layer (north_star item 3 widened to SURVEY
+        # 8f n1): tensor bound.  Algorithmic flops per launch = rows * 2 (D_id H + 4 H^2 + H D_t P).
         tpeak, tpeak_src = measured_tensor_peak()
-        alg_flops = 2.0 * B * H * d_t * p_per
-        exec_flops = 3 * 2.0 * B * H * d_t * 24
-        f_each = (f_ms / n_f) if n_f else None
-        roofline = {"bound": "tensor", "kernel": "linear_tf32x3_kernel<EPI=rqs> (fc_linear_rqs_apply: final conditioner "
-                                                 "GEMM + RQ spline epilogue)",
-                    "achieved": (alg_flops / (f_each * 1e-3) / 1e12) if f_each else None, "peak": tpeak,
-                    "unit": "TFLOP/s", "frac": (alg_flops / (f_each * 1e-3) / 1e12 / tpeak) if f_each else None,
-                    "traffic": profile_json("traffic_linear_rqs_apply.json").get("dram_bytes_per_launch"),
+        alg_row, exec_row = conditioner_flops(wl)
+        alg_flops, exec_flops = alg_row * B, exec_row * B
+        c_each = (c_ms / n_c) if n_c else None
+        roofline = {"bound": "tensor",
+                    "kernel": "conditioner_f16x3_kernel<8, 24, 2> (fc_conditioner_rqs_apply: initial layer, 2 residual "
+                              "blocks, final layer and RQ spline of one flow layer in one persistent tcgen05 kernel)",
+                    "achieved": (alg_flops / (c_each * 1e-3) / 1e12) if c_each else None, "peak": tpeak,
+                    "unit": "TFLOP/s", "frac": (alg_flops / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
+                    "traffic": profile_json("traffic_conditioner_rqs_apply.json").get("dram_bytes_per_launch"),
                     "peak_source": tpeak_src, "algorithmic_flops_per_launch": alg_flops,
                     "tensor_flops_executed_per_launch": exec_flops,
-                    "tensor_pipe_frac": (exec_flops / (f_each * 1e-3) / 1e12 / tpeak) if f_each else None,
-                    "kernel_ms_per_launch": f_each, "kernel_share_of_step": (f_ms / ms) if n_f else None,
-                    "launches_timed": n_f,
-                    "note": "3xTF32 (fp32-faithful): 3 tf32 UMMAs per fp32 product, so frac <= 1/3 * 23/24"}
-        # (2) the other conditioner layers (same kernel, store epilogue): 4 x (H x H) + 1 x (D x H) per flow layer
-        n_layers = len(wl["layers"])
-        hid_alg = 2.0 * B * (4 * H * H + d_t * H) * n_layers * args.steps
-        hid_exec = 3 * 2.0 * B * (4 * H * H + D * H) * n_layers * args.steps  # first layer reads the full-width rows
-        roofline_hidden = {"bound": "tensor", "kernel": "linear_tf32x3_kernel<EPI=store> (fc_linear_apply)",
-                           "achieved": (hid_alg / (h_ms * 1e-3) / 1e12) if n_h else None, "peak": tpeak,
-                           "unit": "TFLOP/s", "frac": (hid_alg / (h_ms * 1e-3) / 1e12 / tpeak) if n_h else None,
-                           "tensor_pipe_frac": (hid_exec / (h_ms * 1e-3) / 1e12 / tpeak) if n_h else None,
-                           "kernel_share_of_step": (h_ms / ms) if n_h else None, "launches_timed": n_h}
-        # (3) the stand-alone element-wise RQ-spline layer kernel (north_star items 1-2; the path taken whenever the
+                    "tensor_pipe_frac": (exec_flops / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
+                    "kernel_ms_per_launch": c_each, "kernel_share_of_step": (c_ms / ms) if n_c else None,
+                    "launches_timed": n_c,
+                    "note": "3xFP16 (fp32-faithful): 3 fp16 UMMAs per fp32 product on padded shapes, so frac <= "
+                            "{:.3f}".format(alg_row / exec_row)}
+        # (2) the stand-alone element-wise RQ-spline layer kernel (north_star items 1-2; the path taken whenever the
         # parameters are materialised: training, unsupported conditioners): HBM bound.  Not on the inference step
         # above, so it is timed here on its own: 10 launches over a materialised [B, D_t * P] parameter tensor.
         # algorithmic bytes per sample per launch: x + params + y + lad + identity copy
@@ -357,22 +507,251 @@ def run_ours(args, wl):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(wl, B, world),
+            "config": config_dict(args, wl, B, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "gpu_launches_by_entry_point": counts,
             "clocks": clocks,
-            "roofline": roofline, "roofline_hidden_layers": roofline_hidden, "roofline_elementwise": roofline_hbm,
+            "roofline": roofline, "roofline_elementwise": roofline_hbm,
+            "log_likelihood_sum": ll,
+        }
+        if world == 1 and not args.no_eager_baseline:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(wl, state, x)
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, kind = cpu_log_prob_rate(wl, state, CPU_SAMPLE_ROWS, repeats=1, warmup=0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                                    "sample": "{} rows of {} log_prob, one pass ({:.1f} s), {} on torch CPU fp32, all host "
+                                              "threads".format(CPU_SAMPLE_ROWS, wl["name"], sec,
+                                                               "the unmodified reference (oracle/_ref)"
+                                                               if kind == "reference" else "oracle/restated.py")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cfg5(args, wl):
+    """BASELINE configs[4]: batch-sharded log_prob of the D=256 flow over `--rows` (default 100M) rows in total, streamed in
+    1M-row chunks generated on the device (seed 1234 + rank * 1000 + chunk), running fp64 sum, one 2-element
+    all-reduce per step.  The rows are SHARDED over the ranks: strong scaling."""
+    import torch.distributed as dist
+
+    from flowconductor_b200 import _cabi
+    from flowconductor_b200 import distributed as fdist
+
+    world, rank, local_rank, dev = setup_dist(args)
+    _cabi.lib()
+    flow, state = build_state(wl)
+    flow = flow.to(dev).eval()
+    D, chunk = wl["features"], wl["batch"]
+    total_rows = args.rows or wl["total_rows"]
+    lo, hi = fdist.shard_bounds(total_rows, rank, world)
+    my_rows = hi - lo
+    bounds = [(c0, min(my_rows, c0 + chunk)) for c0 in range(0, my_rows, chunk)]
+    xbuf = torch.empty(chunk, D, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        acc = torch.zeros((), dtype=torch.float64, device=dev)
+        with torch.no_grad():
+            for ci, (c0, c1) in enumerate(bounds):
+                g = torch.Generator(device=dev).manual_seed(1234 + rank * 1000 + ci)
+                xc = xbuf[: c1 - c0]
+                xc.normal_(generator=g)
+                acc += flow.log_prob(xc).double().sum()
+            packed = torch.stack((acc, torch.tensor(float(my_rows), dtype=torch.float64, device=dev)))
+            if world > 1:
+                dist.all_reduce(packed)
+        return packed
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _cabi.STATS.reset()
+    _cabi.STATS.timing = True
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        packed = step()
+    end.record()
+    barrier()
+    _cabi.STATS.timing = False
+    ms = start.elapsed_time(end)
+    launches = _cabi.STATS.total()
+    n_c, c_ms = _cabi.STATS.elapsed_ms("fc_conditioner_rqs_apply")
+    clocks = sampler.stop() if rank == 0 else None
+    ll, count = packed.tolist()
+    assert ll == ll and int(count) == total_rows, (ll, count, total_rows)
+
+    # e2e: the same rows from pinned HOST memory (a 4M-row host buffer re-read until the shard is covered), chunked H2D
+    # overlapping the kernels, D2H of every chunk's log_prob
+    host_rows = min(my_rows, 4 * chunk)
+    x_host = torch.randn(host_rows, D).pin_memory()
+    out_host = torch.empty(host_rows, dtype=torch.float32).pin_memory()
+    passes = (my_rows + host_rows - 1) // host_rows
+
+    def e2e_step():
+        for _ in range(passes):
+            fdist.host_log_prob(flow, x_host, out_host, chunk_rows=262144)
+
+    e2e_step()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 2))
+    s2.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2.record()
+    barrier()
+    ms_e2e = s2.elapsed_time(e2)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        tpeak, tpeak_src = measured_tensor_peak()
+        alg_row, exec_row = conditioner_flops(wl)
+        c_each = (c_ms / n_c) if n_c else None
+        rows_per_launch = my_rows / max(len(bounds), 1)
+        line = {
+            "metric": METRIC, "value": total_rows * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(args, wl, my_rows, 1), global_rows=total_rows, chunk_rows=chunk,
+                           parallelism="{} rows sharded over {} rank(s), streamed in {}-row chunks generated on device; "
+                                       "no data-path collective".format(total_rows, world, chunk)),
+            "e2e": {"value": passes * host_rows * world * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": passes * host_rows * D * 4, "d2h_bytes_per_step": passes * host_rows * 4,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conditioner_f16x3_kernel<8, 24, 2> (fc_conditioner_rqs_apply)",
+                         "achieved": (alg_row * rows_per_launch / (c_each * 1e-3) / 1e12) if c_each else None,
+                         "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": (alg_row * rows_per_launch / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
+                         "traffic": None, "peak_source": tpeak_src,
+                         "tensor_pipe_frac": (exec_row * rows_per_launch / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
+                         "kernel_ms_per_launch": c_each, "kernel_share_of_step": (c_ms / ms) if n_c else None,
+                         "launches_timed": n_c},
             "log_likelihood_sum": ll,
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, sec = cpu_log_prob_rate(wl, state, CPU_SAMPLE_ROWS, repeats=1, warmup=0)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "{} rows of {} log_prob, one pass ({:.1f} s), oracle/restated.py on "
-                                              "torch CPU fp32, all host threads".format(CPU_SAMPLE_ROWS, wl["name"],
-                                                                                        sec)}
+            rows = REF_STEP_ROWS["cfg5"]
+            rate, sec, kind = cpu_log_prob_rate(wl, state, rows, repeats=1, warmup=0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                                    "sample": "{} rows of cfg5 log_prob, one pass ({:.1f} s), torch CPU fp32".format(rows, sec)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cfg3_train(args, wl):
+    """BASELINE configs[2]: MAF-RQS training step — zero_grad; loss = -log_prob(x).mean(); backward; flat-bucket gradient
+    all-reduce (NCCL); Adam(lr=1e-3, weight_decay=1e-5) — as in examples/toy_2d.py:57-67.  The 262144-row global batch is
+    SHARDED over the ranks: strong scaling."""
+    import torch.distributed as dist
+
+    from flowconductor_b200 import _cabi, graphs
+    from flowconductor_b200 import distributed as fdist
+
+    world, rank, local_rank, dev = setup_dist(args)
+    _cabi.lib()
+    flow, state = build_state(wl, trained_like=False)
+    flow = flow.to(dev).train()
+    fdist.broadcast_parameters(flow)
+    Bg = args.rows or wl["batch"]
+    B = Bg // world
+    x = torch.randn(B, wl["features"], generator=torch.Generator(device=dev).manual_seed(1234 + rank), device=dev)
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-3, weight_decay=1e-5, capturable=args.graph)
+
+    def eager_step():
+        opt.zero_grad(set_to_none=True)
+        loss = -flow.log_prob(x).mean()
+        loss.backward()
+        fdist.allreduce_gradients(flow)
+        opt.step()
+        return loss
+
+    if args.graph:
+        gstep = graphs.GraphedTrainStep(flow, opt, lambda xb: -flow.log_prob(xb).mean(), x,
+                                        sync_gradients=fdist.allreduce_gradients)
+
+        def step():
+            return gstep.step(x)
+    else:
+        step = eager_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _cabi.STATS.reset()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        loss = step()
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end)
+    launches = _cabi.STATS.total()
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: the step fed from pinned host memory, loss read back on the host
+    x_host = x.cpu().pin_memory()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s2.record()
+    for _ in range(args.steps):
+        x.copy_(x_host, non_blocking=True)
+        float(step().item())
+    e2.record()
+    barrier()
+    ms_e2e = s2.elapsed_time(e2)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        line = {
+            "metric": "train_step_samples_per_sec", "value": Bg * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(args, wl, B, 1), global_rows=Bg,
+                           parallelism="data-parallel x{}: global batch sharded, one flat-bucket NCCL all-reduce of all "
+                                       "gradients per step{}".format(world, "; whole step replayed from one CUDA graph"
+                                                                     if args.graph else "")),
+            "e2e": {"value": Bg * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * wl["features"] * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches if not args.graph else None, "clocks": clocks, "loss": float(loss.item()),
+            "roofline": None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, kind = cpu_train_step_rate(wl, state, REF_STEP_ROWS["cfg3_train"], 1, 0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                                    "sample": "{} rows, one training step ({:.1f} s), torch CPU fp32".format(
+                                        REF_STEP_ROWS["cfg3_train"], sec)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        if args.graph:
+            # a recorded graph keeps NCCL work objects alive and destroy_process_group() then waits forever: leave through
+            # a barrier and a hard exit instead
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -380,11 +759,15 @@ def main():
     args = parse()
     from flowconductor_b200 import workloads
 
-    wl = workloads.get_workload(args.workload)
+    wl = workloads.get_workload("cfg3" if args.workload == "cfg3_train" else args.workload)
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.workload == "cfg5":
+        run_cfg5(args, wl)
+    elif args.workload == "cfg3_train":
+        run_cfg3_train(args, wl)
     else:
-        run_ours(args, wl)
+        run_cfg2(args, wl)
 
 
 if __name__ == "__main__":

@@ -6,3 +6,10 @@ Mirrors the `flowcon` API for that path only (`transforms`, `flows`, `distributi
 library, or with CPU tensors, raises.
 """
 __version__ = "0.1.0"
+
+
+def patch_reference(flowcon=None, wrap=None):
+    """Install the kernels behind the reference package's own spline functions (see flowconductor_b200/patch.py)."""
+    from .patch import patch_reference as _patch
+
+    return _patch(flowcon, wrap)

@@ -3,16 +3,17 @@
 The reference is pure Python on PyTorch; it imports here once a few stub packages
 (`oracle/stubs`: matplotlib, UMNN, torchdiffeq, torchtestcase, parameterized) are on sys.path
 (see SURVEY.md Appendix A).  The reference tree lives at /root/reference in the build
-container and does NOT exist on the GPU box, so nothing that runs there may depend on this
-module; it is used by `oracle/make_golden.py` and by the not-gpu tests that pin the restatement
-(`oracle/restated.py`) against the live reference when it is available.
+container and does NOT exist on the GPU box; `oracle/build_ref.py` leaves an unmodified copy of
+its package under `oracle/_ref/` (git-ignored, shipped with gpurun), which is what is found there.
+Used by `oracle/make_golden.py`, by the not-gpu tests that pin the restatement (`oracle/restated.py`)
+against the live reference, by bench.py's reference legs and by tests/test_reference_suite.py.
 """
 import os
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 STUBS = os.path.join(_HERE, "stubs")
-CANDIDATES = [os.environ.get("FLOWCON_REFERENCE", ""), "/root/reference"]
+CANDIDATES = [os.environ.get("FLOWCON_REFERENCE", ""), "/root/reference", os.path.join(_HERE, "_ref")]
 
 
 def reference_root():

@@ -1,0 +1,59 @@
+"""TEST INFRASTRUCTURE ONLY — pytest plugin that runs the REFERENCE's own test-suite against the CUDA kernels
+(VERDICT r1 item 9).
+
+    cd oracle/_ref && PYTHONPATH=<repo>:<repo>/oracle/stubs python -m pytest -p oracle.refsuite_plugin \
+        tests/transforms/splines tests/transforms/coupling_test.py ...
+
+It imports the unmodified reference (oracle/_ref or /root/reference), calls `flowconductor_b200.patch_reference` so
+that the reference's layers evaluate their splines through libflowcon_b200.so, and — because the reference's tests build
+CPU tensors while the kernels take CUDA tensors only — wraps every patched function so that its tensor arguments are
+moved to cuda:0 and its results back (autograd flows through `.to()`).  The arithmetic under test is the GPU kernel.
+"""
+import functools
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CALLS = {"n": 0}
+
+
+def _to_cuda_and_back(fn):
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        CALLS["n"] += 1
+        moved = [a.to("cuda") if isinstance(a, torch.Tensor) else a for a in args]
+        kw = {k: (v.to("cuda") if isinstance(v, torch.Tensor) else v) for k, v in kwargs.items()}
+        src = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        out = fn(*moved, **kw)
+        dev = src.device if src is not None else torch.device("cpu")
+        dt = src.dtype if src is not None else torch.float32
+        return tuple(o.to(device=dev, dtype=dt) for o in out)
+
+    def f32(*args, **kwargs):  # the kernels are fp32; the reference's tests are too (default dtype)
+        args = [a.float() if isinstance(a, torch.Tensor) and a.is_floating_point() else a for a in args]
+        return wrapped(*args, **kwargs)
+
+    return functools.wraps(fn)(f32)
+
+
+def pytest_configure(config):
+    from oracle import locate
+
+    flowcon = locate.import_reference()
+    import flowconductor_b200
+
+    undo = flowconductor_b200.patch_reference(flowcon, wrap=_to_cuda_and_back)
+    config._fc_undo = undo
+    sys.stderr.write("refsuite: patched {} bindings of the reference with the CUDA kernels\n".format(len(undo.patched)))
+
+
+def pytest_unconfigure(config):
+    sys.stderr.write("refsuite: {} calls went through the patched functions\n".format(CALLS["n"]))
+    undo = getattr(config, "_fc_undo", None)
+    if undo is not None:
+        undo()

@@ -33,14 +33,14 @@ def rel_err(a, b, floor):
     return (a - b).abs() / b.abs().clamp_min(floor)
 
 
-def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0, max_ratio=10.0):
+def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0, max_ratio=10.0, max_fail_frac=2e-2):
     """Three-way parity (the 1e-5 tolerance sits AT the reference's own fp32 noise floor —
     reference-fp32 vs reference-fp64 already differ by >1e-5 on a small fraction of ill-conditioned elements:
     tiny bins, theta near 0/1, values near 0).  An element passes if
         (i)  |ours - ref32| <= tol * max(|ref32|, floor),                                   or
         (ii) |ours - ref64| <= slack * |ref32 - ref64| + tol * max(|ref64|, floor).
     Elements failing both are tolerated only if, as a population, we are no less accurate than the reference:
-        (iii) at most 2% of elements fail (i)&(ii), AND every quantile (50/90/99%) of |ours - ref64| is
+        (iii) at most 2% (max_fail_frac) of elements fail (i)&(ii), AND every quantile (50/90/99%) of |ours - ref64| is
               <= (1.5 + 3/sqrt(n(1-q)))x the same quantile of |ref32 - ref64| (+ tol*floor/10), AND
               max|ours - ref64| <= max_ratio * max|ref32 - ref64| + tol*floor  (max_ratio = 10; callers that
               push rows through a whole ill-conditioned stack, where the error is heavy-tailed and the max of a
@@ -68,7 +68,7 @@ def assert_parity(ours, ref32, ref64, tol, floor, what="", slack=4.0, max_ratio=
         qr = torch.quantile(noise.flatten(), q)
         # a quantile estimated from m = n (1 - q) tail samples is itself noisy: allow 1.5x + 3 / sqrt(m)
         limit = 1.5 + 3.0 / torch.sqrt(ours.numel() * (1 - q)).clamp_min(1.0)
-        pop_ok = (frac <= 2e-2 + 4.0 / ours.numel() and bool((qo <= limit * qr + tol * floor / 10).all())
+        pop_ok = (frac <= max_fail_frac + 4.0 / ours.numel() and bool((qo <= limit * qr + tol * floor / 10).all())
                   and float(e64.max()) <= max_ratio * float(noise.max()) + tol * floor)
         if not pop_ok:
             i = torch.nonzero(bad)[0]

@@ -1,0 +1,34 @@
+"""The REFERENCE's own hot-path tests, run against the CUDA kernels.
+
+`flowconductor_b200.patch_reference()` installs the kernels behind the reference package's spline functions; the
+reference's unmodified test files (oracle/_ref/tests, a copy made by oracle/build_ref.py) then exercise them through the
+reference's own layer classes: tests/transforms/splines/*_test.py (forward / inverse consistency of every spline family),
+coupling_test.py (piecewise couplings incl. PRQ with and without tails), autoregressive_test.py, nonlinearities_test.py
+(the CDF layers incl. the domain exception)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+SUITES = ["tests/transforms/splines/rational_quadratic_test.py", "tests/transforms/splines/linear_test.py",
+          "tests/transforms/splines/quadratic_test.py", "tests/transforms/splines/cubic_test.py",
+          "tests/transforms/coupling_test.py", "tests/transforms/autoregressive_test.py",
+          "tests/transforms/nonlinearities_test.py"]
+
+
+@pytest.mark.gpu
+def test_reference_test_suite_passes_on_the_kernels():
+    if not os.path.isdir(os.path.join(REF, "tests")):
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "oracle", "stubs"), REF, env.get("PYTHONPATH", "")])
+    cmd = [sys.executable, "-W", "ignore", "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "oracle.refsuite_plugin",
+           "-x", "--no-header", "-rf"] + SUITES
+    res = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((res.stdout + "\n" + res.stderr).splitlines()[-40:])
+    print(tail)
+    assert res.returncode == 0, tail
+    assert "refsuite: patched" in res.stderr and " 0 calls went through" not in res.stderr, tail
