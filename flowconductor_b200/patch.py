@@ -17,9 +17,11 @@ globals that were bound at import (autoregressive/autoregressive.py:9-19, condit
 autoregressive/deep_sigmoid.py:7-17).  There is no CPU fallback: the patched functions raise on CPU tensors like every
 other entry point of this package.
 """
+import functools
 import importlib
 
 from .transforms import splines as _ours
+from .transforms.base import InputOutsideDomain as _OurInputOutsideDomain
 
 FUNCTIONS = ("rational_quadratic_spline", "unconstrained_rational_quadratic_spline", "linear_spline",
              "unconstrained_linear_spline", "quadratic_spline", "unconstrained_quadratic_spline", "cubic_spline",
@@ -42,6 +44,18 @@ def patch_reference(flowcon=None, wrap=None):
         src = getattr(importlib.import_module("flowcon.transforms.splines"), name, None)
         if src is not None:
             originals[name] = src
+    ref_exc = importlib.import_module("flowcon.transforms.base").InputOutsideDomain
+
+    def reference_exceptions(fn):
+        # the reference's callers (and its tests) catch flowcon.transforms.base.InputOutsideDomain
+        @functools.wraps(fn)
+        def call(*args, **kwargs):
+            try:
+                return fn(*args, **kwargs)
+            except _OurInputOutsideDomain:
+                raise ref_exc() from None
+        return call
+
     saved = []
     for modname in MODULES:
         try:
@@ -50,7 +64,7 @@ def patch_reference(flowcon=None, wrap=None):
             continue
         for name, orig in originals.items():
             if getattr(mod, name, None) is orig:
-                repl = getattr(_ours, name)
+                repl = reference_exceptions(getattr(_ours, name))
                 if wrap is not None:
                     repl = wrap(repl)
                 saved.append((mod, name, orig))

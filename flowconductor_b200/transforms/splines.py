@@ -70,6 +70,22 @@ def unconstrained_rational_quadratic_spline(inputs, unnormalized_widths, unnorma
                                             min_derivative=DEFAULT_MIN_DERIVATIVE, enable_identity_init=False):
     if tails != "linear":
         raise RuntimeError("{} tails are not implemented.".format(tails))
+    num_bins = unnormalized_widths.shape[-1]
+    if unnormalized_derivatives.shape[-1] != num_bins - 1:
+        # The reference pads WHATEVER it is given with the boundary constant on both sides and then reads knot
+        # derivatives 0..K of the padded vector (rational_quadratic.py:33-36,120-130) — its own unit tests pass K + 1 raw
+        # derivatives (tests/transforms/splines/rational_quadratic_test.py:71), in which case the right boundary knot takes
+        # a raw value, not the constant.  Same result here: the constrained kernel on [-tail_bound, tail_bound] with the
+        # first K + 1 entries of the padded vector, identity outside.
+        constant = math.log(math.exp(1 - min_derivative) - 1)
+        padded = torch.nn.functional.pad(unnormalized_derivatives, (1, 1), value=constant)
+        if padded.shape[-1] < num_bins + 1:
+            raise RuntimeError("unnormalized_derivatives needs at least num_bins - 1 entries")
+        inside = (inputs >= -tail_bound) & (inputs <= tail_bound)
+        y, lad = _elementwise(inputs.clamp(-tail_bound, tail_bound), unnormalized_widths, unnormalized_heights,
+                              padded[..., : num_bins + 1], inverse, _cabi.TAILS_NONE, -tail_bound, tail_bound, -tail_bound,
+                              tail_bound, min_bin_width, min_bin_height, min_derivative, enable_identity_init)
+        return torch.where(inside, y, inputs), torch.where(inside, lad, torch.zeros_like(lad))
     return _elementwise(inputs, unnormalized_widths, unnormalized_heights, unnormalized_derivatives, inverse,
                         _cabi.TAILS_LINEAR, -tail_bound, tail_bound, -tail_bound, tail_bound, min_bin_width,
                         min_bin_height, min_derivative, enable_identity_init)
