@@ -148,6 +148,8 @@ def invalidate(module):
             object.__setattr__(m, "_fc_plan", None)
         if getattr(m, "_fc_cond_plan", None) is not None:
             object.__setattr__(m, "_fc_cond_plan", None)
+        if getattr(m, "_fc_made_plan", None) is not None:
+            object.__setattr__(m, "_fc_made_plan", None)
     _generation[0] += 1
 
 

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 from torch.nn import functional as F
 
-from .. import _cabi, ops
+from .. import _cabi, made_inverse, ops
 from ..nn import tensorcore
 from . import made as made_module
 from . import splines
@@ -16,8 +16,9 @@ from .base import Transform
 
 
 class AutoregressiveTransform(Transform):
-    """Forward: one conditioner pass + one element-wise kernel.  Inverse: D passes, each re-running the
-    conditioner on the partially inverted outputs (autoregressive.py:44-53) — D x the forward cost."""
+    """Forward: one conditioner pass + one element-wise kernel.  Inverse: where the layer supports it, ONE kernel that
+    evaluates the MADE incrementally (`_incremental_inverse`, csrc/fc_made_inverse.cu); otherwise D passes, each re-running
+    the conditioner on the partially inverted outputs (autoregressive.py:44-53) — D x the forward cost."""
 
     def __init__(self, autoregressive_net):
         super().__init__()
@@ -30,6 +31,10 @@ class AutoregressiveTransform(Transform):
         return self._elementwise_forward(inputs, params)
 
     def inverse(self, inputs, context=None):
+        if made_inverse.usable(self.autoregressive_net, inputs, context):
+            result = self._incremental_inverse(inputs)
+            if result is not None:
+                return result
         outputs = torch.zeros_like(inputs)
         logabsdet = None
         fast = tensorcore.usable(self.autoregressive_net, outputs, context, inputs)
@@ -47,6 +52,10 @@ class AutoregressiveTransform(Transform):
         if inverse:
             return self._elementwise_inverse(inputs, params)
         return self._elementwise_forward(inputs, params)
+
+    def _incremental_inverse(self, inputs):
+        """(outputs, logabsdet) from the incremental-MADE kernel, or None if this layer / network is not covered."""
+        return None
 
     def _output_dim_multiplier(self):
         raise NotImplementedError()
@@ -86,6 +95,12 @@ class MaskedAffineAutoregressiveTransform(AutoregressiveTransform):
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return ops.affine_layer(inputs, autoregressive_params, None, None, _cabi.AFFINE_INTERLEAVED,
                                 _cabi.SCALE_SOFTPLUS_EPS, True)
+
+    def _incremental_inverse(self, inputs):
+        prog = made_inverse.program_for(self.autoregressive_net, 2)
+        if prog is None:
+            return None
+        return made_inverse.apply_affine(prog, inputs, _cabi.SCALE_SOFTPLUS_EPS)
 
     def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
         return tensorcore.affine_layer(self.autoregressive_net, conditioner_inputs, inputs, None, None,
@@ -147,6 +162,19 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
 
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._elementwise(inputs, autoregressive_params, inverse=True)
+
+    def _incremental_inverse(self, inputs):
+        prog = made_inverse.program_for(self.autoregressive_net, self._spline.params_per_feature())
+        if prog is None:
+            return None
+        hidden = getattr(self.autoregressive_net, "hidden_features", None)
+        cfg, tails = self._spline.config(True, hidden)
+        status = torch.zeros((1,), dtype=torch.int32, device=inputs.device) if tails == _cabi.TAILS_NONE or splines.STRICT \
+            else None
+        outputs, logabsdet = made_inverse.apply_rqs(prog, inputs, cfg, status)
+        if status is not None:
+            splines.check_status(status, tails)
+        return outputs, logabsdet
 
     def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
         net = self.autoregressive_net

@@ -112,6 +112,18 @@ class RationalQuadraticSettings:
     def params_per_feature(self):
         return self.num_bins * 3 - 1 if self.tails == "linear" else self.num_bins * 3 + 1
 
+    def config(self, inverse, hidden_for_scaling):
+        """(struct fc_rqs_config, tails constant) of these settings."""
+        if self.tails == "linear":
+            tails, lo, hi = _cabi.TAILS_LINEAR, -self.tail_bound, self.tail_bound
+        else:
+            tails, (lo, hi) = _cabi.TAILS_NONE, self.constrained_box
+        wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
+        cfg = _cabi.RqsConfig(int(self.num_bins), tails, int(bool(self.identity_init)), int(bool(inverse)), float(lo),
+                              float(hi), float(lo), float(hi), float(self.min_bin_width), float(self.min_bin_height),
+                              float(self.min_derivative), float(wh_scale))
+        return cfg, tails
+
     def apply(self, inputs, params, tcols, ccols, inverse, hidden_for_scaling):
         if self.tails == "linear":
             tails, lo, hi = _cabi.TAILS_LINEAR, -self.tail_bound, self.tail_bound

@@ -380,6 +380,46 @@ int fc_conditioner_error(int32_t* out);
  * launch.  Synchronises the device. */
 int fc_conditioner_profile(unsigned long long* out32);
 
+/*
+ * The INVERSE of a masked autoregressive layer in one kernel, MADE evaluated incrementally (csrc/fc_made_inverse.cu;
+ * SURVEY 8(f) n2).  Replaces AutoregressiveTransform.inverse (flowcon/transforms/autoregressive/autoregressive.py:44-53:
+ * D passes of the whole conditioner, flowcon/transforms/made.py:274-283, each followed by the element-wise inverse) for
+ * a residual MADE without context: pass f computes only the hidden units that become valid with feature f - 1 and the
+ * parameters of feature f.  The caller (flowconductor_b200/made_inverse.py) compiles the network into a program:
+ *
+ *   step:  units [j0, j0 + nj) of `out_array` = bias[b_off ...] + W . act(`in_array`[0 .. k_count)) (+ `res_array`[j0 ...])
+ *
+ * Arrays: 0 = the features (inputs of the MADE: inverted so far), 1 .. n_arrays = hidden-layer outputs in an order of the
+ * units in which every masked weight row is a prefix of its input (sorted by degree, made.py:28-51); out_array 0 = the
+ * parameter tile of the feature being inverted (j0 = offset inside its P parameters).  act = ReLU when relu_in.  After a
+ * step with feature >= 0 the bijection's inverse of that feature is evaluated from the parameter tile.  The step's weights
+ * are `weights + 4 * w_off4`: [k_count][4 * nj4] floats (masked, k-major, the 4 * nj4 - nj padding columns ignored).
+ * nj <= FC_MADE_MAX_NJ.  Shared memory bounds the network: fc_made_inverse_smem_bytes(...) must not exceed the device's
+ * opt-in limit (FC_ERR_UNSUPPORTED otherwise: run the D-pass inverse).
+ */
+#define FC_MADE_MAX_NJ 24
+typedef struct fc_made_step {
+  int32_t in_array, out_array, k_count, j0;
+  int32_t nj, nj4, relu_in, res_array;
+  int32_t feature, w_off4, b_off, reserved;
+} fc_made_step;
+typedef struct fc_made_program {
+  const fc_made_step* steps; /* device, 16-byte aligned */
+  const float* weights;      /* device, 16-byte aligned */
+  const float* bias;         /* device */
+  int32_t n_steps, features, params_per_feature, n_arrays, hidden, reserved;
+} fc_made_program;
+int64_t fc_made_inverse_smem_bytes(int32_t features, int32_t params_per_feature, int32_t n_arrays, int32_t hidden);
+/* z: the layer's inputs in the inverse direction [B, features]; x: outputs (may alias z); logabsdet [B] as the reference's
+ * inverse returns it (the negated forward log-determinant at x).  cfg->inverse must be 1. */
+int fc_made_inverse_rqs(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x, int64_t x_row_stride,
+                        float* logabsdet, int32_t accumulate_logabsdet, int64_t B, const fc_rqs_config* cfg,
+                        int32_t* status, void* stream);
+/* interleaved (raw scale, shift) parameters, autoregressive.py:97-129 */
+int fc_made_inverse_affine(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                           int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                           int32_t activation, void* stream);
+
 /* Library / build info (also used by the loader test). */
 const char* fc_version(void);
 int fc_built_for_sm(void); /* 100 */

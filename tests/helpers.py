@@ -102,3 +102,39 @@ def parity_report(ours, ref32, ref64, tol, floor, slack=4.0):
     return ("strict-fail (i) %.2e, (i)&(ii) %.2e of %d; |ours-fp64| p50/p99/max %.1e/%.1e/%.1e, |ref32-fp64| %.1e/%.1e/%.1e"
             % (float(fail1.double().mean()), float((fail1 & fail2).double().mean()), ours.numel(), qo[0], qo[1], qo[2],
                qr[0], qr[1], qr[2]))
+
+
+def emulate_made_program(prog, z, invert_feature):
+    """Interpret a compiled MADE-inverse program (flowconductor_b200/made_inverse.py) exactly as csrc/fc_made_inverse.cu
+    does, in fp64 torch on the CPU.  z [B, D]; invert_feature(z_f [B], params [B, P]) -> (x_f [B], lad_f [B]).
+    Returns (x [B, D], logabsdet [B])."""
+    z = z.double()
+    B = z.shape[0]
+    X = z.t().clone()
+    H = torch.zeros((prog.n_arrays, prog.hidden, B), dtype=torch.float64)
+    PT = torch.zeros((prog.params_per_feature, B), dtype=torch.float64)
+    lad = torch.zeros((B,), dtype=torch.float64)
+    w = prog.weights.detach().double().cpu()
+    bias = prog.bias.detach().double().cpu()
+    for st in prog.steps_np.tolist():
+        in_a, out_a, k, j0, nj, nj4, relu, res, feat, woff, boff, _ = st
+        assert 1 <= nj <= 24 and nj4 == (nj + 3) // 4
+        v = bias[boff:boff + nj][:, None].expand(nj, B).clone()
+        if k > 0:
+            src = X if in_a == 0 else H[in_a - 1]
+            a = src[:k]
+            if relu:
+                a = a.clamp_min(0)
+            wb = w[woff * 4: woff * 4 + k * 4 * nj4].reshape(k, 4 * nj4)[:, :nj]
+            v = v + wb.t() @ a
+        if res:
+            v = v + H[res - 1][j0:j0 + nj]
+        if out_a > 0:
+            H[out_a - 1][j0:j0 + nj] = v
+        else:
+            PT[j0:j0 + nj] = v
+        if feat >= 0:
+            xf, lf = invert_feature(X[feat].clone(), PT.t().clone())
+            X[feat] = xf
+            lad = lad + lf
+    return X.t().contiguous(), lad
