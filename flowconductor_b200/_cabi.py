@@ -27,7 +27,7 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_rqs_bins", "fc_linspline_apply
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
            "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_error", "fc_conditioner_profile",
-           "fc_made_inverse_smem_bytes", "fc_made_inverse_rqs", "fc_made_inverse_affine",
+           "fc_made_inverse_smem_bytes", "fc_made_inverse_profile", "fc_made_inverse_rqs", "fc_made_inverse_affine",
            "fc_version", "fc_built_for_sm"]
 COND_MAX_LAYERS = 10
 COND_INITIAL, COND_BLOCK_FIRST, COND_BLOCK_SECOND, COND_FINAL = 0, 1, 2, 3
@@ -74,9 +74,9 @@ class Conditioner(ctypes.Structure):
 
 class MadeProgramStruct(ctypes.Structure):
     """struct fc_made_program"""
-    _fields_ = [("steps", ctypes.c_void_p), ("weights", ctypes.c_void_p), ("bias", ctypes.c_void_p),
-                ("n_steps", ctypes.c_int32), ("features", ctypes.c_int32), ("params_per_feature", ctypes.c_int32),
-                ("n_arrays", ctypes.c_int32), ("hidden", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+    _fields_ = [("phases", ctypes.c_void_p), ("weights", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("n_phases", ctypes.c_int32), ("features", ctypes.c_int32), ("params_per_feature", ctypes.c_int32),
+                ("n_arrays", ctypes.c_int32), ("hidden", ctypes.c_int32), ("n_bias", ctypes.c_int32)]
 
 
 class LibraryMissing(RuntimeError):
@@ -134,7 +134,8 @@ def lib():
                                                Cols, Cols, ctypes.POINTER(RqsConfig), vp, vp]
         L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.fc_conditioner_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
-        L.fc_made_inverse_smem_bytes.argtypes = [i32, i32, i32, i32]
+        L.fc_made_inverse_smem_bytes.argtypes = [i32, i32, i32, i32, i32]
+        L.fc_made_inverse_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
         L.fc_made_inverse_rqs.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64,
                                           ctypes.POINTER(RqsConfig), vp, vp]
         L.fc_made_inverse_affine.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64, i32, vp]

@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     nvcc = _nvcc()
-    extra = ["-DFC_LINEAR_PROFILE=1", "-DFC_COND_PROFILE=1"] if os.environ.get("FC_LINEAR_PROFILE_BUILD") == "1" else []
+    extra = ["-DFC_LINEAR_PROFILE=1", "-DFC_COND_PROFILE=1", "-DFC_MADE_PROFILE=1"] if os.environ.get("FC_LINEAR_PROFILE_BUILD") == "1" else []
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")

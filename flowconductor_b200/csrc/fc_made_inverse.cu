@@ -10,22 +10,27 @@
 // feature f.  Summed over the D passes that is HALF of one conditioner evaluation instead of D of them (cfg 3: 32 x
 // fewer multiply-adds), and nothing but the inputs and outputs touches HBM.
 //
-// The host (flowconductor_b200/made_inverse.py) turns a residual MADE into a straight-line PROGRAM of steps — "units
-// [j0, j0 + nj) of array `out` = bias + W[:, :k_count] . act(array `in`[:k_count]) (+ array `res`)" — and lays the masked,
-// degree-sorted weights out in step order; after the step that completes a feature's parameters the bijection's
-// inverse is evaluated for that feature.  The kernel is an interpreter for that program:
+// The host (flowconductor_b200/made_inverse.py) turns a residual MADE into a straight-line PROGRAM of phases and lays
+// the masked, degree-sorted weights out in the order the kernel consumes them.  A phase is a [rows x width] weight
+// matrix whose column groups are TASKS, one per warp: "units [j0, j0 + nj) of array `out` (+)= W . act(array `in`
+// [k0, k0 + kn))".  Per pass there is one WIDE phase — everything that depends only on earlier passes: for every
+// layer the products of the pass's new units with the units that were already final (the bulk of the work), the
+// first layer of the new units, and the same for the feature's parameters — followed by one NARROW phase per layer
+// for the dependent chain (the new units of one layer times the new units of the layer below: H / (D - 1) k-values)
+// and the inversion of the feature.  The kernel is an interpreter for that program:
 //
 //   * one CTA = 32 rows (lane = row).  The row tile's state lives in shared memory as [unit][32 rows] fp32 arrays:
-//     the features inverted so far, one array per hidden layer output (1 + 2 x blocks arrays of H units), the
-//     parameter tile of the feature being inverted.  That state (5 KB per row at cfg 3) is what limits a CTA to 32
-//     rows, and is why this is an fp32 CUDA-core kernel: the products are 32 x <=24 x k slivers on a serial chain of
-//     ~100 steps, far below a tcgen05 tile.
+//     the features inverted so far, one array per hidden layer output (1 + 2 x blocks arrays of H units, holding
+//     partial sums until a unit is final), the parameter tile of the feature being inverted.  That state (5 KB per
+//     row at cfg 3) is what limits a CTA to 32 rows, and is why this is an fp32 CUDA-core kernel: the products are
+//     32 x <=24 x k slivers on a serial chain, far below a tcgen05 tile.
 //   * the weights are one linear stream, identical for every row tile: a producer warp walks the program and feeds a
-//     ring of 6 KB slots (<= 64 k-values x <= 24 outputs) with 1-D TMA bulk copies on mbarriers; it runs ahead across
-//     steps and row tiles.
-//   * the 8 compute warps split the reduction: warp w multiplies k = w, w + 8, ... of a slot (one conflict-free
-//     activation load per k, the slot's weight row broadcast as 128-bit loads, packed fp32x2 FMAs into 24
-//     accumulators), the partial sums meet in shared memory, bias / skip connection are added and the units stored.
+//     ring of 8 KB slots (a few rows of the phase's matrix) with 1-D TMA bulk copies on mbarriers; it runs ahead
+//     across phases and row tiles.
+//   * the 8 compute warps each own one task of the phase (a slice of the OUTPUTS, so no cross-warp reduction): per
+//     k-value one conflict-free activation load, the task's weights broadcast as 128-bit loads, packed fp32x2 FMAs
+//     into <= 24 accumulators; bias / the partial sum of the wide phase / the skip connection are added when the
+//     task stores its units.  One CTA barrier per phase.
 //   * warp 0 then inverts the feature (same element arithmetic as the layer kernels: fc_math.cuh) and the next pass
 //     starts.  log|det J| is the sum of the per-feature terms (what the reference's last pass returns).
 #include "fc_common.cuh"
@@ -36,21 +41,23 @@ namespace fc {
 using namespace tc;
 
 constexpr int kMR = 32;                 // rows per CTA
-constexpr int kMW = 8;                  // compute warps
+constexpr int kMW = FC_MADE_TASKS;      // compute warps = tasks per phase (8)
 constexpr int kMThreads = (kMW + 1) * 32;
-constexpr int kMSlotK = 64;             // k-values per ring slot
-constexpr int kMJT = FC_MADE_MAX_NJ;    // outputs per step (24)
-constexpr int kMStages = 4;
-constexpr int kMSlotBytes = kMSlotK * kMJT * 4;
-constexpr int kMRingBytes = kMStages * kMSlotBytes;
-constexpr int kMScratchFloats = kMW * kMJT * kMR;
+constexpr int kMJT = FC_MADE_MAX_NJ;    // outputs per task (24)
+constexpr int kMJL = kMJT / 4;          // ... per lane (6)
+constexpr int kMMaxStages = 8;
+constexpr int kMSlotBytes = 8192;       // ring slot: floor(2048 / width) rows of the phase's matrix
+constexpr int kMSlotFloats = kMSlotBytes / 4;
+constexpr int kMPhaseInt4 = (4 + 12 * kMW) / 4;  // one fc_made_phase = header + 8 tasks = 25 x int4
+constexpr int kMRecFloats = FC_MADE_RECORD_FLOATS;  // the phase record at the head of the phase's weights (padded to 512 B)
 
 struct MadeArgs {
-  const int4* steps;  // fc_made_step[n_steps] as 3 x int4 each
-  int n_steps;
+  const int4* phases;  // fc_made_phase[n_phases]
+  int n_phases;
   const float* weights;
   const float* bias;
-  int D, PS, n_arrays, hidden;
+  int n_bias;
+  int D, P, n_arrays, hidden, stages;
   const float* z;
   long long ldz;
   float* x;
@@ -62,6 +69,26 @@ struct MadeArgs {
   int32_t* status;
 };
 
+// Experiments only (-DFC_MADE_PROFILE=1: FC_LINEAR_PROFILE_BUILD=1 python -m flowconductor_b200.build --force): cycles warps 0
+// and 5 of CTA 0 spend in each part of the interpreter loop; fc_made_inverse_profile() reads them back.
+#ifndef FC_MADE_PROFILE
+#define FC_MADE_PROFILE 0
+#endif
+__device__ unsigned long long g_made_prof[32];
+#if FC_MADE_PROFILE
+// clock read that cannot be scheduled before `dep` is available
+__device__ __forceinline__ long long made_clock_after(int dep) {
+  long long t;
+  asm volatile("{.reg .u64 c; mov.u64 c, %%clock64; add.u64 %0, c, %1;}" : "=l"(t) : "l"((long long)(dep >> 30)) : "memory");
+  return t;
+}
+#define MPROF_T(t, dep) const long long t = made_clock_after(dep)
+#define MPROF_ADD(i, t1, t0) prof[i] += (t1) - (t0)
+#else
+#define MPROF_T(t, dep)
+#define MPROF_ADD(i, t1, t0)
+#endif
+
 // Bounded mbarrier wait: a protocol error ends the kernel with a trap (the launch fails) instead of hanging the GPU.
 __device__ __forceinline__ void made_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -71,23 +98,59 @@ __device__ __forceinline__ void made_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int NJ4>
-__device__ __forceinline__ void made_kloop(float2 (&acc)[kMJT / 2], const float* __restrict__ in_k, const float* __restrict__ slot,
-                                           int nk, int warp, bool relu) {
-#pragma unroll 4
-  for (int kk = warp; kk < nk; kk += kMW) {
-    float av = in_k[kk * kMR];
-    if (relu) av = fmaxf(av, 0.f);
-    const float2 a2 = make_float2(av, av);
-    const float4* wr = reinterpret_cast<const float4*>(slot + kk * (NJ4 * 4));
+// One task's share of a ring slot.  A lane owns 4 rows x JL outputs (register tile: a broadcast-only mapping — lane = row,
+// every weight read by all 32 lanes — is bound by shared-memory wavefronts, 4 per 128-bit broadcast load; measured):
+//   acc[i] (rows 0,1) and acc[kMJL + i] (rows 2,3) += act(in[r][4 rows]) * w[r][i]   for r in [0, n), i in [0, JL)
+// `in` advances 32 floats per k-value, `w` one row (`width` floats) of the phase's matrix.
+template <int JL>
+__device__ __forceinline__ void made_kloop(float2 (&acc)[2 * kMJL], const float* __restrict__ in, const float* __restrict__ w,
+                                           int width, int n, bool relu) {
+#pragma unroll(JL <= 2 ? 8 : 4)
+  for (int r = 0; r < n; ++r) {
+    float4 a4 = *reinterpret_cast<const float4*>(in + r * kMR);
+    if (relu) {
+      a4.x = fmaxf(a4.x, 0.f);
+      a4.y = fmaxf(a4.y, 0.f);
+      a4.z = fmaxf(a4.z, 0.f);
+      a4.w = fmaxf(a4.w, 0.f);
+    }
+    const float2 a01 = make_float2(a4.x, a4.y), a23 = make_float2(a4.z, a4.w);
+    const float* wr = w + r * width;
+    float wv[JL];
+    if constexpr (JL % 4 == 0) {
 #pragma unroll
-    for (int q = 0; q < NJ4; ++q) {
-      const float4 w = wr[q];
-      acc[2 * q] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[2 * q]);
-      acc[2 * q + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[2 * q + 1]);
+      for (int i = 0; i < JL; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(wr + i);
+        wv[i] = t.x, wv[i + 1] = t.y, wv[i + 2] = t.z, wv[i + 3] = t.w;
+      }
+    } else if constexpr (JL % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < JL; i += 2) {
+        const float2 t = *reinterpret_cast<const float2*>(wr + i);
+        wv[i] = t.x, wv[i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < JL; ++i) wv[i] = wr[i];
+    }
+#pragma unroll
+    for (int i = 0; i < JL; ++i) {
+      const float2 w2 = make_float2(wv[i], wv[i]);
+      acc[i] = __ffma2_rn(a01, w2, acc[i]);
+      acc[kMJL + i] = __ffma2_rn(a23, w2, acc[kMJL + i]);
     }
   }
 }
+
+struct MadeSmem {
+  // [ring: stages x 8 KB][X: D x 32][H: n_arrays x hidden x 32][PT: P x 32][bias: n_bias (padded to 4)][barriers]
+  static __host__ __device__ size_t floats_after_ring(int D, int P, int n_arrays, int hidden, int n_bias) {
+    return (size_t)D * kMR + (size_t)n_arrays * hidden * kMR + (size_t)P * kMR + (size_t)((n_bias + 3) & ~3);
+  }
+  static __host__ __device__ size_t total(int stages, int D, int P, int n_arrays, int hidden, int n_bias) {
+    return (size_t)stages * kMSlotBytes + 4 * floats_after_ring(D, P, n_arrays, hidden, n_bias) + 8 * 2 * kMMaxStages + 128;
+  }
+};
 
 template <class Op>
 __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeArgs a, const Op op) {
@@ -95,23 +158,26 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 127u) & ~127u;
   unsigned char* const gbase = smem_raw + (base - raw_s);
+  const int stages = a.stages;
   float* const ring_g = reinterpret_cast<float*>(gbase);
-  float* const X = reinterpret_cast<float*>(gbase + kMRingBytes);    // [D][32]: z until a feature is inverted, then x
-  float* const H = X + a.D * kMR;                                    // [n_arrays][hidden][32]
-  float* const PT = H + (size_t)a.n_arrays * a.hidden * kMR;         // [32 rows][PS]
-  float* const SC = PT + kMR * a.PS;                                 // [warp][24][32] partial sums
-  const uint32_t bars = base + kMRingBytes + 4u * (uint32_t)(a.D * kMR + a.n_arrays * a.hidden * kMR + kMR * a.PS + kMScratchFloats);
+  float* const X = reinterpret_cast<float*>(gbase + (size_t)stages * kMSlotBytes);  // [D][32]: z until a feature is inverted, then x
+  float* const H = X + a.D * kMR;                                                    // [n_arrays][hidden][32]
+  float* const PT = H + (size_t)a.n_arrays * a.hidden * kMR;                         // [P][32] parameters of the feature
+  float* const BS = PT + a.P * kMR;                                                  // every layer's bias
+  const uint32_t bars = base + (uint32_t)(stages * kMSlotBytes) +
+                        4u * (uint32_t)MadeSmem::floats_after_ring(a.D, a.P, a.n_arrays, a.hidden, a.n_bias);
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (kMStages + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (kMMaxStages + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), kMW);
     }
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < a.n_bias; i += kMThreads) BS[i] = __ldg(a.bias + i);
   __syncthreads();
 
   if (warp == kMW) {
@@ -120,21 +186,28 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        for (int i = 0; i < a.n_steps; ++i) {
-          const int4 s0 = __ldg(a.steps + 3 * i), s1 = __ldg(a.steps + 3 * i + 1), s2 = __ldg(a.steps + 3 * i + 2);
-          const int k_count = s0.z, nj4 = s1.y;
-          const float* src = a.weights + (size_t)(unsigned)s2.y * 4;
-          for (int k0 = 0; k0 < k_count; k0 += kMSlotK) {
-            const int nk = k_count - k0 < kMSlotK ? k_count - k0 : kMSlotK;
-            const uint32_t bytes = (uint32_t)(nk * nj4 * 16);
+        int4 hd = __ldg(a.phases);
+        for (int p = 0; p < a.n_phases; ++p) {
+          const int rows = hd.x, width = hd.y;
+          const float* src = a.weights + (size_t)(unsigned)hd.z * 4;
+          if (p + 1 < a.n_phases) hd = __ldg(a.phases + (size_t)(p + 1) * kMPhaseInt4);  // in flight while this phase is fed
+          // first slot: the phase record (kMRecFloats) + as many rows as fit behind it; then whole slots of rows
+          int r0 = 0, cap = (kMSlotFloats - kMRecFloats) / width, lead = kMRecFloats;
+          do {
+            const int nr = rows - r0 < cap ? rows - r0 : cap;
+            const uint32_t bytes = (uint32_t)((lead + nr * width) * 4);
             made_wait(empty_bar(s), ph ^ 1u);
             mbar_expect_tx(full_bar(s), bytes);
-            bulk_load_1d(base + (uint32_t)(s * kMSlotBytes), src + (size_t)k0 * nj4 * 4, bytes, full_bar(s));
-            if (++s == kMStages) {
+            bulk_load_1d(base + (uint32_t)(s * kMSlotBytes), src, bytes, full_bar(s));
+            src += lead + nr * width;
+            r0 += nr;
+            cap = kMSlotFloats / width;
+            lead = 0;
+            if (++s == stages) {
               s = 0;
               ph ^= 1u;
             }
-          }
+          } while (r0 < rows);
         }
       }
     }
@@ -143,9 +216,14 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
 
   // -------------------------------------------------------------------- compute warps
   const int tid = threadIdx.x;  // 0..255
+  const int jg = lane >> 3, rg = lane & 7;  // this lane's outputs jg * JL .. and rows 4 rg .. 4 rg + 3
   int s = 0;
   uint32_t ph = 0;
   unsigned status = 0;
+#if FC_MADE_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long prof_begin = clock64();
+#endif
   const int D = a.D;
   const size_t arr_floats = (size_t)a.hidden * kMR;
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -156,69 +234,109 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
     }
     float lad_acc = 0.f;
     named_barrier_sync(1, kMW * 32);
-    for (int i = 0; i < a.n_steps; ++i) {
-      const int4 s0 = __ldg(a.steps + 3 * i), s1 = __ldg(a.steps + 3 * i + 1), s2 = __ldg(a.steps + 3 * i + 2);
-      const int in_array = s0.x, out_array = s0.y, k_count = s0.z, j0 = s0.w;
-      const int nj = s1.x, nj4 = s1.y, relu_in = s1.z, res_array = s1.w;
-      const int feature = s2.x, b_off = s2.z;
-      float2 acc[kMJT / 2];
+    for (int p = 0; p < a.n_phases; ++p) {
+      MPROF_T(p_t0, p);
+      // the phase record travels at the head of the phase's first weight slot (a global read of it here would cost an L2
+      // round trip per phase on the serial chain: measured)
+      made_wait(full_bar(s), ph);
+      const int4* rec = reinterpret_cast<const int4*>(ring_g + s * kMSlotFloats);
+      const int4 hd = rec[0], t0 = rec[1 + 3 * warp], t1 = rec[2 + 3 * warp], t2 = rec[3 + 3 * warp];
+      const int rows = hd.x, width = hd.y, feature = hd.w;
+      const int in_array = t0.x, out_array = t0.y, k0 = t0.z, kn = t0.w;
+      const int j0 = t1.x, nj = t1.y, c0 = t1.z, flags = t1.w;
+      const int res_array = t2.x, b_off = t2.y;
+      const int jl = (nj + 3) >> 2;  // outputs per lane
+      const bool relu = (flags & FC_MADE_RELU_IN) != 0;
+      MPROF_T(p_t1, rows + width + kn + b_off);
+      MPROF_ADD(0, p_t1, p_t0);
+      float2 acc[2 * kMJL];
 #pragma unroll
-      for (int j = 0; j < kMJT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
-      const float* in = (in_array == 0 ? X : H + (size_t)(in_array - 1) * arr_floats) + lane;
-      for (int k0 = 0; k0 < k_count; k0 += kMSlotK) {
-        const int nk = k_count - k0 < kMSlotK ? k_count - k0 : kMSlotK;
-        made_wait(full_bar(s), ph);
-        const float* slot = ring_g + s * (kMSlotBytes / 4);
-        const float* in_k = in + (size_t)k0 * kMR;
-        switch (nj4) {
-          case 1: made_kloop<1>(acc, in_k, slot, nk, warp, relu_in != 0); break;
-          case 2: made_kloop<2>(acc, in_k, slot, nk, warp, relu_in != 0); break;
-          case 3: made_kloop<3>(acc, in_k, slot, nk, warp, relu_in != 0); break;
-          case 4: made_kloop<4>(acc, in_k, slot, nk, warp, relu_in != 0); break;
-          case 5: made_kloop<5>(acc, in_k, slot, nk, warp, relu_in != 0); break;
-          default: made_kloop<6>(acc, in_k, slot, nk, warp, relu_in != 0); break;
+      for (int j = 0; j < 2 * kMJL; ++j) acc[j] = make_float2(0.f, 0.f);
+      const float* in = (in_array == 0 ? X : H + (size_t)(in_array - 1) * arr_floats) + (size_t)k0 * kMR + 4 * rg;
+      int r0 = 0, cap = (kMSlotFloats - kMRecFloats) / width, lead = kMRecFloats;
+      do {
+        const int nr = rows - r0 < cap ? rows - r0 : cap;
+        MPROF_T(s_t0, r0);
+        if (r0 > 0) made_wait(full_bar(s), ph);
+        MPROF_T(s_t1, r0);
+        MPROF_ADD(1, s_t1, s_t0);
+        int n = kn - r0;  // this task's k-values inside the slot
+        n = n < nr ? n : nr;
+        if (nj > 0 && n > 0) {
+          const float* w = ring_g + s * kMSlotFloats + lead + c0 + jg * jl;
+          const float* in_r = in + (size_t)r0 * kMR;
+          switch (jl) {
+            case 1: made_kloop<1>(acc, in_r, w, width, n, relu); break;
+            case 2: made_kloop<2>(acc, in_r, w, width, n, relu); break;
+            case 3: made_kloop<3>(acc, in_r, w, width, n, relu); break;
+            case 4: made_kloop<4>(acc, in_r, w, width, n, relu); break;
+            case 5: made_kloop<5>(acc, in_r, w, width, n, relu); break;
+            default: made_kloop<6>(acc, in_r, w, width, n, relu); break;
+          }
         }
         __syncwarp();
+        MPROF_T(s_t2, __float_as_int(acc[0].x + acc[3].y + acc[7].x + acc[11].y));
+        MPROF_ADD(2, s_t2, s_t1);
         if (lane == 0) mbar_arrive(empty_bar(s));
-        if (++s == kMStages) {
+        if (++s == stages) {
           s = 0;
           ph ^= 1u;
         }
-      }
-      // partial sums of this warp's share of the reduction
-      {
-        float* sc = SC + (warp * kMJT) * kMR + lane;
+        r0 += nr;
+        cap = kMSlotFloats / width;
+        lead = 0;
+      } while (r0 < rows);
+      MPROF_T(p_t2, p);
+      // this task's units: bias or the partial sum stored by an earlier phase, skip connection
+      if (nj > 0) {
+        float* out = (out_array > 0 ? H + (size_t)(out_array - 1) * arr_floats : PT) + (size_t)j0 * kMR + 4 * rg;
+        const float* res = res_array > 0 ? H + (size_t)(res_array - 1) * arr_floats + (size_t)j0 * kMR + 4 * rg : nullptr;
+        const bool init = (flags & FC_MADE_INIT_BIAS) != 0;
 #pragma unroll
-        for (int j = 0; j < kMJT / 2; ++j) {
-          if (2 * j < nj) sc[(2 * j) * kMR] = acc[j].x;
-          if (2 * j + 1 < nj) sc[(2 * j + 1) * kMR] = acc[j].y;
+        for (int i = 0; i < kMJL; ++i) {
+          const int j = jg * jl + i;
+          if (i < jl && j < nj) {
+            float4 v = make_float4(acc[i].x, acc[i].y, acc[kMJL + i].x, acc[kMJL + i].y);
+            float4* o = reinterpret_cast<float4*>(out + j * kMR);
+            if (init) {
+              const float b = BS[b_off + j];
+              v.x += b, v.y += b, v.z += b, v.w += b;
+            } else {
+              const float4 t = *o;
+              v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+            }
+            if (res) {
+              const float4 t = *reinterpret_cast<const float4*>(res + j * kMR);
+              v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+            }
+            *o = v;
+          }
         }
       }
+      MPROF_T(p_t3, p);
+      MPROF_ADD(3, p_t3, p_t2);
       named_barrier_sync(1, kMW * 32);
-      for (int jj = warp; jj < nj; jj += kMW) {
-        float v = __ldg(a.bias + b_off + jj);
-        const float* sc = SC + jj * kMR + lane;
-#pragma unroll
-        for (int w = 0; w < kMW; ++w) v += sc[w * (kMJT * kMR)];
-        if (res_array > 0) v += H[(size_t)(res_array - 1) * arr_floats + (size_t)(j0 + jj) * kMR + lane];
-        if (out_array > 0) {
-          H[(size_t)(out_array - 1) * arr_floats + (size_t)(j0 + jj) * kMR + lane] = v;
-        } else {
-          PT[lane * a.PS + j0 + jj] = v;
-        }
-      }
-      named_barrier_sync(1, kMW * 32);
+      MPROF_T(p_t4, p);
+      MPROF_ADD(4, p_t4, p_t3);
       if (feature >= 0) {
         // the feature's parameters are complete: invert it (autoregressive.py:50-52 for the one column that becomes final)
         if (warp == 0) {
           const float zf = X[feature * kMR + lane];
           float xf, lf;
-          op.eval(zf, PT + lane * a.PS, xf, lf, status);
+          op.eval(zf, PT + lane, xf, lf, status);
           X[feature * kMR + lane] = xf;
           lad_acc += lf;
         }
         named_barrier_sync(1, kMW * 32);
+        MPROF_T(p_t5, __float_as_int(lad_acc));
+        MPROF_ADD(5, p_t5, p_t4);
       }
+#if FC_MADE_PROFILE
+      {
+        MPROF_T(p_t6, p);
+        prof[rows > 40 ? 6 : 7] += p_t6 - p_t0;
+      }
+#endif
     }
     for (int i = tid; i < kMR * D; i += kMW * 32) {
       const int r = i / D, f = i - r * D;
@@ -231,44 +349,66 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
     named_barrier_sync(1, kMW * 32);
   }
   if (warp == 0 && status != 0 && a.status) atomicOr(a.status, (int)status);
+#if FC_MADE_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {
+    unsigned long long* o = g_made_prof + (warp == 0 ? 0 : 8);
+    for (int i = 0; i < 6; ++i) o[i] = (unsigned long long)prof[i];
+    o[6] = (unsigned long long)(clock64() - prof_begin);
+    g_made_prof[16 + (warp == 0 ? 0 : 2)] = (unsigned long long)prof[6];
+    g_made_prof[17 + (warp == 0 ? 0 : 2)] = (unsigned long long)prof[7];
+  }
+#endif
 }
 
+// Bijections: `pc` points at this row's column of the parameter tile ([P][32 rows]: parameter i at pc[32 i]).
 template <int KC>
 struct MadeRqsOp {
   RqsParams c;
-  __device__ __forceinline__ void eval(float z, const float* p, float& x, float& lad, unsigned& status) const {
-    rqs_eval<KC>(c, z, p, x, lad, status);
+  __device__ __forceinline__ void eval(float z, const float* pc, float& x, float& lad, unsigned& status) const {
+    constexpr int PM = 3 * (KC ? KC : FC_MAX_BINS_GENERIC) + 1;
+    float p[PM];
+    if constexpr (KC != 0) {
+#pragma unroll
+      for (int i = 0; i < PM; ++i) p[i] = i < c.P ? pc[i * kMR] : 0.f;
+    } else {
+      for (int i = 0; i < c.P; ++i) p[i] = pc[i * kMR];
+    }
+    rqs_eval<KC, (KC != 0)>(c, z, p, x, lad, status);
   }
 };
 
 struct MadeAffineOp {  // interleaved (raw scale, shift) pairs: autoregressive.py:124-129
   int activation;
-  __device__ __forceinline__ void eval(float z, const float* p, float& x, float& lad, unsigned&) const {
-    affine_eval(z, p[0], p[1], activation, 1, x, lad);
+  __device__ __forceinline__ void eval(float z, const float* pc, float& x, float& lad, unsigned&) const {
+    affine_eval(z, pc[0], pc[kMR], activation, 1, x, lad);
   }
 };
 
-static size_t made_smem_bytes(int D, int PS, int n_arrays, int hidden) {
-  return (size_t)kMRingBytes + 4ull * ((size_t)D * kMR + (size_t)n_arrays * hidden * kMR + (size_t)kMR * PS + kMScratchFloats) +
-         8 * 2 * kMStages + 128;
+static int made_stages(int D, int P, int n_arrays, int hidden, int n_bias) {
+  const size_t fixed = MadeSmem::total(0, D, P, n_arrays, hidden, n_bias);
+  const size_t limit = (size_t)device_info().max_smem_optin;
+  if (fixed + 2 * kMSlotBytes > limit) return 0;
+  const size_t st = (limit - fixed) / kMSlotBytes;
+  return (int)(st > kMMaxStages ? kMMaxStages : st);
 }
 
 static int made_check(const fc_made_program* prog, const float* z, int64_t ldz, float* x, int64_t ldx, float* lad, int64_t B,
                       int P, MadeArgs& a) {
-  if (!prog || !prog->steps || !prog->weights || !prog->bias || prog->n_steps <= 0) return FC_ERR_INVALID_ARGUMENT;
-  if (prog->features <= 0 || prog->hidden <= 0 || prog->n_arrays <= 0 || prog->params_per_feature != P)
+  if (!prog || !prog->phases || !prog->weights || !prog->bias || prog->n_phases <= 0) return FC_ERR_INVALID_ARGUMENT;
+  if (prog->features <= 0 || prog->hidden <= 0 || prog->n_arrays <= 0 || prog->params_per_feature != P || prog->n_bias <= 0)
     return FC_ERR_INVALID_ARGUMENT;
   if (B < 0) return FC_ERR_INVALID_ARGUMENT;
   if (B > 0 && (!z || !x || !lad)) return FC_ERR_INVALID_ARGUMENT;
   if (ldz < prog->features || ldx < prog->features) return FC_ERR_INVALID_ARGUMENT;
-  if ((reinterpret_cast<uintptr_t>(prog->weights) & 15) || (reinterpret_cast<uintptr_t>(prog->steps) & 15)) return FC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(prog->weights) & 15) || (reinterpret_cast<uintptr_t>(prog->phases) & 15)) return FC_ERR_UNSUPPORTED;
   if (B >= ((int64_t)1 << 31) * kMR) return FC_ERR_UNSUPPORTED;
-  a.steps = reinterpret_cast<const int4*>(prog->steps);
-  a.n_steps = prog->n_steps;
+  a.phases = reinterpret_cast<const int4*>(prog->phases);
+  a.n_phases = prog->n_phases;
   a.weights = prog->weights;
   a.bias = prog->bias;
+  a.n_bias = prog->n_bias;
   a.D = prog->features;
-  a.PS = (P & 1) ? P : P + 1;  // odd row stride of the parameter tile: conflict-free for lane = row
+  a.P = P;
   a.n_arrays = prog->n_arrays;
   a.hidden = prog->hidden;
   a.z = z;
@@ -278,14 +418,15 @@ static int made_check(const fc_made_program* prog, const float* z, int64_t ldz, 
   a.lad = lad;
   a.M = B;
   a.num_tiles = (int)((B + kMR - 1) / kMR);
-  if (made_smem_bytes(a.D, a.PS, a.n_arrays, a.hidden) > (size_t)device_info().max_smem_optin) return FC_ERR_UNSUPPORTED;
+  a.stages = made_stages(a.D, a.P, a.n_arrays, a.hidden, a.n_bias);
+  if (a.stages < 2) return FC_ERR_UNSUPPORTED;
   return FC_OK;
 }
 
 template <class Op>
 static int launch_made(const MadeArgs& a, const Op& op, cudaStream_t stream) {
   auto kern = made_inverse_kernel<Op>;
-  const size_t smem = made_smem_bytes(a.D, a.PS, a.n_arrays, a.hidden);
+  const size_t smem = MadeSmem::total(a.stages, a.D, a.P, a.n_arrays, a.hidden, a.n_bias);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return FC_ERR_CUDA;
   const int sms = device_info().sm_count;
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
@@ -298,10 +439,16 @@ static int launch_made(const MadeArgs& a, const Op& op, cudaStream_t stream) {
 
 using namespace fc;
 
-extern "C" int64_t fc_made_inverse_smem_bytes(int32_t features, int32_t params_per_feature, int32_t n_arrays, int32_t hidden) {
-  if (features <= 0 || params_per_feature <= 0 || n_arrays <= 0 || hidden <= 0) return FC_ERR_INVALID_ARGUMENT;
-  const int PS = (params_per_feature & 1) ? params_per_feature : params_per_feature + 1;
-  return (int64_t)made_smem_bytes(features, PS, n_arrays, hidden);
+extern "C" int fc_made_inverse_profile(unsigned long long* out32) {
+  if (!out32) return FC_ERR_INVALID_ARGUMENT;
+  if (cudaMemcpyFromSymbol(out32, g_made_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return FC_ERR_CUDA;
+  return FC_OK;
+}
+
+extern "C" int64_t fc_made_inverse_smem_bytes(int32_t features, int32_t params_per_feature, int32_t n_arrays, int32_t hidden,
+                                              int32_t n_bias) {
+  if (features <= 0 || params_per_feature <= 0 || n_arrays <= 0 || hidden <= 0 || n_bias <= 0) return FC_ERR_INVALID_ARGUMENT;
+  return (int64_t)MadeSmem::total(2, features, params_per_feature, n_arrays, hidden, n_bias);  // with the smallest weight ring
 }
 
 extern "C" int fc_made_inverse_rqs(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,

@@ -17,39 +17,54 @@ import torch
 from . import _cabi
 
 MAX_NJ = 24      # FC_MADE_MAX_NJ
+TASKS = 8        # FC_MADE_TASKS
 ROWS = 32        # rows per CTA of the kernel
 SMEM_LIMIT = 232448  # opt-in shared memory per CTA on sm_100
-
-STEP_FIELDS = ("in_array", "out_array", "k_count", "j0", "nj", "nj4", "relu_in", "res_array", "feature", "w_off4", "b_off",
-               "reserved")
+SLOT_FLOATS = 2048   # ring slot of the kernel
+RELU_IN, INIT_BIAS = 1, 2
+PHASE_INTS = 4 + 12 * TASKS
+RECORD_FLOATS = 128  # FC_MADE_RECORD_FLOATS: the phase record (padded) in front of the phase's matrix
+TASK_FIELDS = ("in_array", "out_array", "k0", "kn", "j0", "nj", "c0", "flags", "res_array", "b_off", "reserved0", "reserved1")
 
 
 class MadeProgram:
-    """Compiled program + its device buffers (`steps`, `weights`, `bias` keep the memory alive)."""
+    """Compiled program + its device buffers (`phases`, `weights`, `bias` keep the memory alive)."""
 
-    def __init__(self, steps_np, weights, bias, features, params_per_feature, n_arrays, hidden, device):
-        self.steps_np = steps_np  # [n_steps, 12] int32 (host copy: tests, debugging)
-        self.steps = torch.from_numpy(steps_np.copy()).to(device)
+    def __init__(self, phases_np, weights, bias, features, params_per_feature, n_arrays, hidden, device):
+        self.phases_np = phases_np  # [n_phases, 100] int32 (host copy: tests, debugging)
+        self.phases = torch.from_numpy(phases_np.copy()).to(device)
         self.weights, self.bias = weights, bias
         self.features, self.params_per_feature, self.n_arrays, self.hidden = features, params_per_feature, n_arrays, hidden
         self.struct = None
         if weights.is_cuda:
             st = _cabi.MadeProgramStruct()
-            st.steps, st.weights, st.bias = self.steps.data_ptr(), weights.data_ptr(), bias.data_ptr()
-            st.n_steps, st.features, st.params_per_feature = steps_np.shape[0], features, params_per_feature
-            st.n_arrays, st.hidden = n_arrays, hidden
+            st.phases, st.weights, st.bias = self.phases.data_ptr(), weights.data_ptr(), bias.data_ptr()
+            st.n_phases, st.features, st.params_per_feature = phases_np.shape[0], features, params_per_feature
+            st.n_arrays, st.hidden, st.n_bias = n_arrays, hidden, bias.numel()
             self.struct = st
 
     @property
-    def n_steps(self):
-        return self.steps_np.shape[0]
+    def n_phases(self):
+        return self.phases_np.shape[0]
+
+    def tasks(self):
+        """[(phase index, header dict, [task dicts])] of the host copy (tests)."""
+        out = []
+        for i, row in enumerate(self.phases_np.tolist()):
+            hdr = dict(zip(("rows", "width", "w_off4", "feature"), row[:4]))
+            ts = [dict(zip(TASK_FIELDS, row[4 + 12 * t: 16 + 12 * t])) for t in range(TASKS)]
+            out.append((i, hdr, [t for t in ts if t["nj"] > 0]))
+        return out
 
 
-def smem_bytes(features, params_per_feature, n_arrays, hidden):
-    """Mirror of fc_made_inverse_smem_bytes (kept in sync by tests/test_host_api.py)."""
-    ps = params_per_feature if params_per_feature % 2 else params_per_feature + 1
-    ring = 4 * 64 * MAX_NJ * 4
-    return ring + 4 * (features * ROWS + n_arrays * hidden * ROWS + ROWS * ps + 8 * MAX_NJ * ROWS) + 8 * 2 * 4 + 128
+def smem_bytes(features, params_per_feature, n_arrays, hidden, n_bias=None):
+    """Mirror of fc_made_inverse_smem_bytes (kept in sync by tests/test_host_api.py): the row tile's state, every bias, and
+    the smallest weight ring (2 slots)."""
+    if n_bias is None:
+        n_bias = n_arrays * hidden + features * params_per_feature
+    ring = 2 * SLOT_FLOATS * 4
+    return ring + 4 * (features * ROWS + n_arrays * hidden * ROWS + params_per_feature * ROWS + (n_bias + 3) // 4 * 4) \
+        + 8 * 2 * 8 + 128
 
 
 def _prefix_counts(mask):
@@ -75,6 +90,19 @@ def supported_made(net):
         if blk.dropout.p > 0 and blk.training:
             return False
     return True
+
+
+def _split_even(n, parts):
+    """n outputs -> at most `parts` consecutive slices whose widths are multiples of 4 (the last one may be ragged)."""
+    n4 = (n + 3) // 4
+    parts = max(1, min(parts, n4))
+    base, extra = divmod(n4, parts)
+    out, j = [], 0
+    for i in range(parts):
+        w = 4 * (base + (1 if i < extra else 0))
+        out.append((j, min(w, n - j)))
+        j += w
+    return [(a, b) for a, b in out if b > 0]
 
 
 def compile_made(net, params_per_feature):
@@ -105,7 +133,7 @@ def compile_made(net, params_per_feature):
         layers.append((fin, n_arrays, 0, 0, 0))
         sorted_w, counts, bias_parts, bias_base = [], [], [], []
         off = 0
-        for idx, (lin, in_a, out_a, _, _) in enumerate(layers):
+        for lin, in_a, out_a, _, _ in layers:
             w = (lin.weight * lin.mask).detach().float()
             m = lin.mask.detach().float()
             b = lin.bias.detach().float() if lin.bias is not None else torch.zeros(w.shape[0], device=dev)
@@ -121,57 +149,104 @@ def compile_made(net, params_per_feature):
             bias_parts.append(b)
             bias_base.append(off)
             off += b.numel()
-        producer = {layers[i][2]: i for i in range(len(layers) - 1)}  # hidden array -> index of the layer that writes it
-        ready = [0] * (n_arrays + 1)
-        steps, blocks = [], []
+        fl = len(layers) - 1
+        phases, blocks = [], []
         w_floats = [0]
 
-        def emit(li, j_lo, j_hi, k_count, feature, j_base):
-            lin, in_a, out_a, relu_in, res_a = layers[li]
-            j = j_lo
-            while j < j_hi:
-                nj = min(MAX_NJ, j_hi - j)
-                nj4 = (nj + 3) // 4
-                last = j + nj >= j_hi
-                assert w_floats[0] % 4 == 0
-                steps.append([in_a, out_a, k_count, j - j_base, nj, nj4, relu_in, res_a,
-                              feature if (last and feature is not None) else -1, w_floats[0] // 4, bias_base[li] + j, 0])
-                if k_count > 0:
-                    blk = torch.zeros((k_count, 4 * nj4), dtype=torch.float32, device=dev)
-                    blk[:, :nj] = sorted_w[li][j:j + nj, :k_count].t()
-                    blocks.append(blk.reshape(-1))
-                    w_floats[0] += k_count * 4 * nj4
-                j += nj
+        def add_phase(tasks, feature):
+            """tasks: [(layer index, j_lo, nj, k0, kn, init_bias, final, j_base)] -> one phase record + its weight matrix."""
+            assert 0 < len(tasks) <= TASKS
+            rows = max(t[4] for t in tasks)
+            width = sum(4 * ((t[2] + 3) // 4) for t in tasks)
+            assert width <= SLOT_FLOATS - RECORD_FLOATS and w_floats[0] % 4 == 0
+            rec = [rows, width, w_floats[0] // 4, feature]
+            mat = torch.zeros((max(rows, 1), width), dtype=torch.float32, device=dev) if rows > 0 else None
+            c0 = 0
+            for li, j_lo, nj, k0, kn, init_bias, final, j_base in tasks:
+                _, in_a, out_a, relu_in, res_a = layers[li]
+                flags = (RELU_IN if relu_in else 0) | (INIT_BIAS if init_bias else 0)
+                rec += [in_a, out_a, k0, kn, j_lo - j_base, nj, c0, flags, res_a if final else 0, bias_base[li] + j_lo, 0, 0]
+                if kn > 0:
+                    mat[:kn, c0:c0 + nj] = sorted_w[li][j_lo:j_lo + nj, k0:k0 + kn].t()
+                c0 += 4 * ((nj + 3) // 4)
+            rec += [0] * (PHASE_INTS - len(rec))
+            phases.append(rec)
+            # the record itself travels through the kernel's weight ring, in front of the matrix
+            rec_words = torch.tensor(rec + [0] * (RECORD_FLOATS - PHASE_INTS), dtype=torch.int32, device=dev)
+            blocks.append(rec_words.view(torch.float32))
+            w_floats[0] += RECORD_FLOATS
+            if rows > 0:
+                blocks.append(mat.reshape(-1))
+                w_floats[0] += rows * width
 
-        def ensure(arr, upto, n_inverted):
-            """Make units [0, upto) of hidden array `arr` available (recursively what they read)."""
-            if arr == 0:
-                return upto <= n_inverted
-            if ready[arr] >= upto:
-                return True
-            li = producer[arr]
-            _, in_a, _, _, res_a = layers[li]
-            lo = ready[arr]
-            need = int(counts[li][lo:upto].max())
-            if not ensure(in_a, need, n_inverted):
-                return False
-            if res_a and not ensure(res_a, upto, n_inverted):
-                return False
-            emit(li, lo, upto, need, None, 0)
-            ready[arr] = upto
-            return True
+        def chunks(li, j_lo, j_hi, k0, kn, init_bias, final, j_base):
+            return [(li, j, min(MAX_NJ, j_hi - j), k0, kn, init_bias, final, j_base) for j in range(j_lo, j_hi, MAX_NJ)]
 
-        fl = len(layers) - 1
+        def balance(tasks):
+            """Fewer than 8 tasks: halve the widest ones so that every warp has work."""
+            tasks = list(tasks)
+            while len(tasks) < TASKS:
+                i = max(range(len(tasks)), key=lambda t: tasks[t][2])
+                li, j, nj, k0, kn, ib, fn, jb = tasks[i]
+                if nj <= 4:
+                    break
+                half = 4 * (((nj + 3) // 4 + 1) // 2)
+                tasks[i:i + 1] = [(li, j, half, k0, kn, ib, fn, jb), (li, j + half, nj - half, k0, kn, ib, fn, jb)]
+            return tasks
+
+        def emit(tasks, feature=-1):
+            for i in range(0, len(tasks), TASKS):
+                last = i + TASKS >= len(tasks)
+                add_phase(tasks[i:i + TASKS], feature if last else -1)
+
+        ready = 0  # units [0, ready) of EVERY hidden array are final
         for f in range(D):
             c = counts[fl][f * P:(f + 1) * P]
-            need = int(c.max())
-            if not ensure(n_arrays, need, f):  # feature f may read features < f only
-                return None
-            emit(fl, f * P, (f + 1) * P, need, f, f * P)
-        steps_np = np.asarray(steps, dtype=np.int32).reshape(-1, len(STEP_FIELDS))
+            hi = int(c.max())
+            lo = ready
+            if hi < lo:
+                return None  # features must need non-decreasing prefixes (degrees 1..D in order)
+            new = hi > lo
+            if new:
+                # the initial layer of the new units reads features < f only (else the net is not autoregressive in order)
+                kx = int(counts[0][lo:hi].max())
+                if kx > f:
+                    return None
+                for li in range(1, fl):
+                    need = int(counts[li][lo:hi].max())
+                    if need > hi:
+                        return None
+            # ---- wide phase: everything that depends on earlier passes only
+            wide = []
+            if new:
+                wide += chunks(0, lo, hi, 0, int(counts[0][lo:hi].max()), True, True, 0)
+                if lo > 0:
+                    for li in range(1, fl):
+                        wide += chunks(li, lo, hi, 0, lo, True, False, 0)
+            if lo > 0 or not new:
+                # the feature's parameters from the units that were final before this pass (bias only when there are none),
+                # split evenly over the warps the layers above leave free
+                free = TASKS - len(wide) % TASKS
+                parts = max(free if free >= (P + MAX_NJ - 1) // MAX_NJ else TASKS, 1)
+                wide += [(fl, f * P + j, nj, 0, min(lo, hi), True, False, f * P) for j, nj in _split_even(P, parts)]
+            if not new:
+                # nothing new to compute: the wide phase completes the parameters
+                emit(balance(wide), f)
+                continue
+            if wide:
+                emit(balance(wide))
+            # ---- the dependent chain: one narrow phase per layer over the new units of the layer below
+            for li in range(1, fl):
+                need = int(counts[li][lo:hi].max())
+                tasks = [(li, lo + j, nj, lo, max(need - lo, 0), lo == 0, True, 0) for j, nj in _split_even(hi - lo, TASKS)]
+                emit(tasks)
+            tasks = [(fl, f * P + j, nj, lo, hi - lo, lo == 0, False, f * P) for j, nj in _split_even(P, TASKS)]
+            emit(tasks, f)
+            ready = hi
+        phases_np = np.asarray(phases, dtype=np.int32).reshape(-1, PHASE_INTS)
         weights = torch.cat(blocks) if blocks else torch.zeros((4,), dtype=torch.float32, device=dev)
         bias = torch.cat(bias_parts).contiguous()
-    return MadeProgram(steps_np, weights.contiguous(), bias, D, P, n_arrays, H, dev)
+    return MadeProgram(phases_np, weights.contiguous(), bias, D, P, n_arrays, H, dev)
 
 
 def _io(prog, z, inplace_ok=False):
@@ -205,6 +280,18 @@ def apply_affine(prog, z, activation):
                                       z.shape[0], int(activation), _cabi.stream_ptr(z.device))
     _cabi.check(rc, "fc_made_inverse_affine")
     return x, lad
+
+
+PROFILE_FIELDS = ("phase records", "wait weights", "multiply", "store units", "phase barrier", "invert feature", "total")
+
+
+def kernel_profile():
+    """Cycle counters of the last launch (library built with FC_LINEAR_PROFILE_BUILD=1; zeros otherwise)."""
+    buf = (ctypes.c_uint64 * 32)()
+    _cabi.check(_cabi.lib().fc_made_inverse_profile(buf), "fc_made_inverse_profile")
+    return {"warp0": {n: int(buf[i]) for i, n in enumerate(PROFILE_FIELDS)},
+            "warp5": {n: int(buf[8 + i]) for i, n in enumerate(PROFILE_FIELDS)},
+            "wide/narrow phases": [int(buf[16 + i]) for i in range(4)]}
 
 
 ENABLED = True  # False: every autoregressive inverse takes the D-pass path

@@ -385,31 +385,51 @@ int fc_conditioner_profile(unsigned long long* out32);
  * SURVEY 8(f) n2).  Replaces AutoregressiveTransform.inverse (flowcon/transforms/autoregressive/autoregressive.py:44-53:
  * D passes of the whole conditioner, flowcon/transforms/made.py:274-283, each followed by the element-wise inverse) for
  * a residual MADE without context: pass f computes only the hidden units that become valid with feature f - 1 and the
- * parameters of feature f.  The caller (flowconductor_b200/made_inverse.py) compiles the network into a program:
+ * parameters of feature f.  The caller (flowconductor_b200/made_inverse.py) compiles the network into a program of
+ * PHASES; a phase is a [rows x width] fp32 weight matrix at `weights + 4 * w_off4 + FC_MADE_RECORD_FLOATS` (row-major, masked,
+ * zero-padded; the FC_MADE_RECORD_FLOATS words in front of it are a bit copy of the phase's own record, which the kernel
+ * receives through its weight ring instead of reading `phases` on the serial chain; width <= 1920) whose
+ * column groups are up to FC_MADE_TASKS tasks that run concurrently (one per warp):
  *
- *   step:  units [j0, j0 + nj) of `out_array` = bias[b_off ...] + W . act(`in_array`[0 .. k_count)) (+ `res_array`[j0 ...])
+ *   task:  units [j0, j0 + nj) of `out_array`  =  (bias[b_off ...] if FC_MADE_INIT_BIAS else their stored partial sums)
+ *                                                 + W[0 .. kn)[c0 .. c0 + nj) . act(`in_array`[k0 .. k0 + kn))  (+ `res_array`[j0 ...])
  *
  * Arrays: 0 = the features (inputs of the MADE: inverted so far), 1 .. n_arrays = hidden-layer outputs in an order of the
  * units in which every masked weight row is a prefix of its input (sorted by degree, made.py:28-51); out_array 0 = the
- * parameter tile of the feature being inverted (j0 = offset inside its P parameters).  act = ReLU when relu_in.  After a
- * step with feature >= 0 the bijection's inverse of that feature is evaluated from the parameter tile.  The step's weights
- * are `weights + 4 * w_off4`: [k_count][4 * nj4] floats (masked, k-major, the 4 * nj4 - nj padding columns ignored).
- * nj <= FC_MADE_MAX_NJ.  Shared memory bounds the network: fc_made_inverse_smem_bytes(...) must not exceed the device's
- * opt-in limit (FC_ERR_UNSUPPORTED otherwise: run the D-pass inverse).
+ * parameter tile of the feature being inverted (j0 = offset inside its P parameters).  act = ReLU with FC_MADE_RELU_IN.
+ * c0 and width are multiples of 4, nj <= FC_MADE_MAX_NJ, kn <= rows; nj = 0 marks an unused task slot.  After a phase with
+ * feature >= 0 the bijection's inverse of that feature is evaluated from the parameter tile.  Shared memory bounds the
+ * network: fc_made_inverse_smem_bytes(...) must not exceed the device's opt-in limit (FC_ERR_UNSUPPORTED otherwise: run the
+ * D-pass inverse).
  */
 #define FC_MADE_MAX_NJ 24
-typedef struct fc_made_step {
-  int32_t in_array, out_array, k_count, j0;
-  int32_t nj, nj4, relu_in, res_array;
-  int32_t feature, w_off4, b_off, reserved;
-} fc_made_step;
+#define FC_MADE_TASKS 8
+#define FC_MADE_RECORD_FLOATS 128 /* the phase's record, struct fc_made_phase padded to 512 bytes, precedes its matrix in `weights` */
+#define FC_MADE_RELU_IN 1
+#define FC_MADE_INIT_BIAS 2
+typedef struct fc_made_task {
+  int32_t in_array, out_array, k0, kn;
+  int32_t j0, nj, c0, flags;
+  int32_t res_array, b_off, reserved0, reserved1;
+} fc_made_task;
+typedef struct fc_made_phase {
+  int32_t rows, width, w_off4, feature;
+  fc_made_task tasks[FC_MADE_TASKS];
+} fc_made_phase;
 typedef struct fc_made_program {
-  const fc_made_step* steps; /* device, 16-byte aligned */
-  const float* weights;      /* device, 16-byte aligned */
-  const float* bias;         /* device */
-  int32_t n_steps, features, params_per_feature, n_arrays, hidden, reserved;
+  const fc_made_phase* phases; /* device, 16-byte aligned */
+  const float* weights;        /* device, 16-byte aligned */
+  const float* bias;           /* device */
+  int32_t n_phases, features, params_per_feature, n_arrays, hidden;
+  int32_t n_bias;              /* floats in `bias` (staged in shared memory) */
 } fc_made_program;
-int64_t fc_made_inverse_smem_bytes(int32_t features, int32_t params_per_feature, int32_t n_arrays, int32_t hidden);
+/* Debugging aid (library built with -DFC_MADE_PROFILE=1, else all zero): cycles warp 0 ([0..6]) and warp 5 ([8..14]) of CTA 0
+ * spent in the last fc_made_inverse_* launch: [0] reading phase records, [1] waiting for weight slots, [2] multiplying,
+ * [3] storing units, [4] phase barriers, [5] inverting features (+ barrier), [6] total.  Synchronises the device. */
+int fc_made_inverse_profile(unsigned long long* out32);
+/* shared memory the kernel needs with its smallest weight ring (it takes more stages when there is room) */
+int64_t fc_made_inverse_smem_bytes(int32_t features, int32_t params_per_feature, int32_t n_arrays, int32_t hidden,
+                                   int32_t n_bias);
 /* z: the layer's inputs in the inverse direction [B, features]; x: outputs (may alias z); logabsdet [B] as the reference's
  * inverse returns it (the negated forward log-determinant at x).  cfg->inverse must be 1. */
 int fc_made_inverse_rqs(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x, int64_t x_row_stride,

@@ -107,34 +107,42 @@ def parity_report(ours, ref32, ref64, tol, floor, slack=4.0):
 def emulate_made_program(prog, z, invert_feature):
     """Interpret a compiled MADE-inverse program (flowconductor_b200/made_inverse.py) exactly as csrc/fc_made_inverse.cu
     does, in fp64 torch on the CPU.  z [B, D]; invert_feature(z_f [B], params [B, P]) -> (x_f [B], lad_f [B]).
-    Returns (x [B, D], logabsdet [B])."""
+    Returns (x [B, D], logabsdet [B]).  Unwritten state is NaN, so a task that reads a unit before it is final fails."""
     z = z.double()
     B = z.shape[0]
     X = z.t().clone()
-    H = torch.zeros((prog.n_arrays, prog.hidden, B), dtype=torch.float64)
-    PT = torch.zeros((prog.params_per_feature, B), dtype=torch.float64)
+    H = torch.full((prog.n_arrays, prog.hidden, B), float("nan"), dtype=torch.float64)
+    PT = torch.full((prog.params_per_feature, B), float("nan"), dtype=torch.float64)
     lad = torch.zeros((B,), dtype=torch.float64)
     w = prog.weights.detach().double().cpu()
     bias = prog.bias.detach().double().cpu()
-    for st in prog.steps_np.tolist():
-        in_a, out_a, k, j0, nj, nj4, relu, res, feat, woff, boff, _ = st
-        assert 1 <= nj <= 24 and nj4 == (nj + 3) // 4
-        v = bias[boff:boff + nj][:, None].expand(nj, B).clone()
-        if k > 0:
-            src = X if in_a == 0 else H[in_a - 1]
-            a = src[:k]
-            if relu:
-                a = a.clamp_min(0)
-            wb = w[woff * 4: woff * 4 + k * 4 * nj4].reshape(k, 4 * nj4)[:, :nj]
-            v = v + wb.t() @ a
-        if res:
-            v = v + H[res - 1][j0:j0 + nj]
-        if out_a > 0:
-            H[out_a - 1][j0:j0 + nj] = v
-        else:
-            PT[j0:j0 + nj] = v
+    for _, hdr, tasks in prog.tasks():
+        rows, width, woff, feat = hdr["rows"], hdr["width"], hdr["w_off4"], hdr["feature"]
+        assert width % 4 == 0 and 0 < width <= 2048 - 128 and len(tasks) >= 1
+        rec = prog.weights.detach().cpu()[woff * 4: woff * 4 + 100].view(torch.int32)
+        assert rec.tolist() == prog.phases_np[_].tolist()  # the record's copy in front of the matrix
+        mat = w[woff * 4 + 128: woff * 4 + 128 + rows * width].reshape(rows, width)
+        results = []
+        for t in tasks:  # all tasks of a phase read the state as it was before the phase
+            nj, kn, k0, j0, c0 = t["nj"], t["kn"], t["k0"], t["j0"], t["c0"]
+            assert 1 <= nj <= 24 and c0 % 4 == 0 and kn <= rows
+            dst = H[t["out_array"] - 1] if t["out_array"] > 0 else PT
+            v = bias[t["b_off"]:t["b_off"] + nj][:, None].expand(nj, B).clone() if t["flags"] & 2 else dst[j0:j0 + nj].clone()
+            if kn > 0:
+                src = X if t["in_array"] == 0 else H[t["in_array"] - 1]
+                a = src[k0:k0 + kn]
+                if t["flags"] & 1:
+                    a = a.clamp_min(0)
+                v = v + mat[:kn, c0:c0 + nj].t() @ a
+            if t["res_array"]:
+                v = v + H[t["res_array"] - 1][j0:j0 + nj]
+            results.append((dst, j0, nj, v))
+        for dst, j0, nj, v in results:
+            dst[j0:j0 + nj] = v
         if feat >= 0:
+            assert not torch.isnan(PT).any()
             xf, lf = invert_feature(X[feat].clone(), PT.t().clone())
             X[feat] = xf
             lad = lad + lf
+            PT.fill_(float("nan"))
     return X.t().contiguous(), lad

@@ -54,18 +54,22 @@ def test_program_reproduces_d_pass_inverse(name):
 
 
 def test_program_structure_cfg3():
-    """cfg 3 (D=16, H=256, 2 blocks, P=47): 15 degree groups x 5 hidden layers + 16 features x 2 parameter chunks."""
+    """cfg 3 (D=16, H=256, 2 blocks, P=47): per pass one wide phase + 4 chain phases + the feature's chain phase."""
     wl = workloads.get_workload("cfg3")
     flow = workloads.build_flow(wl)
     layer = [t for t in flow._transform._transforms if hasattr(t, "autoregressive_net")][0]
     prog = made_inverse.compile_made(layer.autoregressive_net, 47)
-    assert prog is not None and prog.n_steps == 15 * 5 + 16 * 2
-    steps = prog.steps_np
-    assert steps[:, 4].max() <= made_inverse.MAX_NJ
-    feats = steps[steps[:, 8] >= 0, 8]
-    assert feats.tolist() == list(range(16))
+    assert prog is not None
+    phases = prog.tasks()
+    feats = [h["feature"] for _, h, _ in phases if h["feature"] >= 0]
+    assert feats == list(range(16))
+    assert prog.n_phases == 1 + 15 * 6  # feature 0: bias only; then (wide, 4 layers, parameters) per pass
+    macs = 0
+    for _, hdr, tasks in phases:
+        assert hdr["width"] == sum(4 * ((t["nj"] + 3) // 4) for t in tasks) and hdr["width"] <= 2048 - 128
+        assert hdr["rows"] == max(t["kn"] for t in tasks)
+        macs += sum(t["kn"] * t["nj"] for t in tasks)
     # multiply-adds of the whole inverse vs 16 full conditioner passes (the point of n2)
-    macs = int((steps[:, 2].astype(np.int64) * steps[:, 4]).sum())
     full = 16 * 256 + 4 * 256 * 256 + 256 * 752
     assert macs < 0.6 * full and 16 * full / macs > 25
     assert made_inverse.smem_bytes(16, 47, prog.n_arrays, 256) <= made_inverse.SMEM_LIMIT
