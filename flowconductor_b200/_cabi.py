@@ -26,7 +26,7 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_rqs_bins", "fc_linspline_apply
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
-           "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_error", "fc_conditioner_profile",
+           "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_sos_apply", "fc_conditioner_error", "fc_conditioner_profile",
            "fc_made_inverse_smem_bytes", "fc_made_inverse_profile", "fc_made_inverse_rqs", "fc_made_inverse_affine",
            "fc_version", "fc_built_for_sm"]
 COND_MAX_LAYERS = 10
@@ -132,6 +132,8 @@ def lib():
         L.fc_conditioner_pack_layer.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp]
         L.fc_conditioner_rqs_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, vp, i64, vp, i32, i32,
                                                Cols, Cols, ctypes.POINTER(RqsConfig), vp, vp]
+        L.fc_conditioner_sos_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, vp, i64, vp, i32, i32,
+                                               Cols, Cols, i32, f32, vp]
         L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.fc_conditioner_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
         L.fc_made_inverse_smem_bytes.argtypes = [i32, i32, i32, i32, i32]
@@ -212,6 +214,31 @@ class LaunchStats:
 
 STATS = LaunchStats()
 
+# NVTX ranges (the reference has no tracing): with FC_NVTX=1 in the environment, or `_cabi.NVTX = True`, every
+# C-ABI launch is bracketed by an NVTX range named after its entry point, and CompositeTransform brackets every layer
+# ("layer 3: PiecewiseRationalQuadraticCouplingTransform.forward"), so an nsys / ncu --nvtx timeline reads in the reference's
+# own vocabulary.  Off by default: two host calls per launch.
+NVTX = os.environ.get("FC_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    """Context manager: an NVTX range when NVTX is on, nothing otherwise."""
+    __slots__ = ("name", "on")
+
+    def __init__(self, name):
+        self.name = name
+        self.on = NVTX
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 class launch:
     __slots__ = ("name", "device", "start")
@@ -222,6 +249,8 @@ class launch:
 
     def __enter__(self):
         STATS.counts[self.name] = STATS.counts.get(self.name, 0) + 1
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
         self.start = None
         if STATS.timing:
             self.start = torch.cuda.Event(enable_timing=True)
@@ -233,4 +262,6 @@ class launch:
             end = torch.cuda.Event(enable_timing=True)
             end.record(torch.cuda.current_stream(self.device))
             STATS.events.setdefault(self.name, []).append((self.start, end))
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
         return False

@@ -12,9 +12,12 @@ import torch
 
 from . import _cabi
 
-HIDDEN_WIDTHS = (128, 256)
+HIDDEN_WIDTHS = (128, 256)  # what the kernel runs; narrower nets are zero-padded to 128 at pack time (exact: the padding
+                            # units are relu(0) = 0 and multiply zero weights)
 MAX_K_IN = 256
 RQS_PPAD = {8: 24, 16: 48}
+SOS_PPAD = 48               # 3 n + 1 = 31 parameters per feature for n = 10, two features per 96-column tile
+SOS_SIGMOIDS = (10,)
 MAX_BLOCKS = (_cabi.COND_MAX_LAYERS - 2) // 2
 
 
@@ -27,6 +30,7 @@ class PackedConditioner:
 
     def __init__(self, weights, vectors, struct, hidden, k_in, n_final_tiles, num_bins):
         self.weights, self.vectors, self.struct = weights, vectors, struct
+        # hidden: the width the kernel runs (128 / 256); num_bins: bins of the spline, or None for other bijections
         self.hidden, self.k_in, self.n_final_tiles, self.num_bins = hidden, k_in, n_final_tiles, num_bins
 
 
@@ -58,24 +62,36 @@ def _pack_layer(L, dev, blob, offset, layer, mask, n_pad, k_pad, bn, row_map=Non
     return vec
 
 
+def padded_hidden(hidden):
+    """Width the kernel runs for a net of this hidden width, or None."""
+    if hidden <= 0 or hidden % 4:
+        return None
+    return 128 if hidden <= 128 else (256 if hidden <= 256 else None)
+
+
 def supported_shape(hidden, k_in, num_blocks, num_bins):
-    return (hidden in HIDDEN_WIDTHS and 0 < k_in <= MAX_K_IN and k_in % 4 == 0 and 1 <= num_blocks <= MAX_BLOCKS
-            and num_bins in RQS_PPAD)
+    return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
+            and 1 <= num_blocks <= MAX_BLOCKS and num_bins in RQS_PPAD)
 
 
-def pack_rqs(net, num_bins, d_t, col_map=None, k_in=None):
+def supported_sos_shape(hidden, k_in, num_blocks, n_sigmoids):
+    return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
+            and 1 <= num_blocks <= MAX_BLOCKS and n_sigmoids in SOS_SIGMOIDS)
+
+
+def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
     """Pack `net` (initial_layer, blocks[*].linear_layers[0..1], final_layer; optional `.mask` per layer, made.py:72)
-    for `fc_conditioner_rqs_apply`.  col_map / k_in: scatter of the first layer's input columns (a coupling layer's
-    conditioner reads the full-width inputs: coupling.py:82-86 folded into the weights)."""
+    for the `fc_conditioner_*_apply` kernels: P parameters per feature in `ppad` accumulator columns.  col_map / k_in:
+    scatter of the first layer's input columns (a coupling layer's conditioner reads the full-width inputs:
+    coupling.py:82-86 folded into the weights)."""
     L = _cabi.lib()
     init, fin = net.initial_layer, net.final_layer
     dev = init.weight.device
-    hidden = init.weight.shape[0]
+    hidden = padded_hidden(init.weight.shape[0])
     k_in = init.weight.shape[1] if k_in is None else k_in
     nb = len(net.blocks)
-    if not supported_shape(hidden, k_in, nb, num_bins):
+    if hidden is None or not (0 < k_in <= MAX_K_IN and k_in % 4 == 0 and 1 <= nb <= MAX_BLOCKS) or 96 % ppad or P > ppad:
         raise ValueError("conditioner shape not supported by the fused kernel")
-    P, ppad = 3 * num_bins - 1, RQS_PPAD[num_bins]
     if fin.weight.shape[0] != d_t * P:
         raise ValueError("final layer has {} outputs, expected {} x {}".format(fin.weight.shape[0], d_t, P))
     feats = 96 // ppad
@@ -116,6 +132,20 @@ def pack_rqs(net, num_bins, d_t, col_map=None, k_in=None):
     return PackedConditioner(blob, vectors, st, hidden, k_in, n_final_tiles, num_bins)
 
 
+def pack_rqs(net, num_bins, d_t, col_map=None, k_in=None):
+    """`pack` for `fc_conditioner_rqs_apply` (linear tails: 3 K - 1 parameters per feature)."""
+    if num_bins not in RQS_PPAD:
+        raise ValueError("conditioner shape not supported by the fused kernel")
+    return pack(net, 3 * num_bins - 1, RQS_PPAD[num_bins], d_t, col_map=col_map, k_in=k_in, num_bins=num_bins)
+
+
+def pack_sos(net, n_sigmoids, d_t, col_map=None, k_in=None):
+    """`pack` for `fc_conditioner_sos_apply` (3 n + 1 parameters per feature)."""
+    if n_sigmoids not in SOS_SIGMOIDS:
+        raise ValueError("conditioner shape not supported by the fused kernel")
+    return pack(net, 3 * n_sigmoids + 1, SOS_PPAD, d_t, col_map=col_map, k_in=k_in)
+
+
 def rqs_apply(packed, a, x, y, logabsdet, accumulate, d_t, tcols, ccols, cfg, status=None):
     """Whole conditioner + rational-quadratic spline in one kernel (fc_conditioner_rqs_apply).  a: [B, k_in] matrix the
     initial layer multiplies; writes y[:, tcols] (and y[:, ccols] = x[:, ccols] unless y is x) and logabsdet."""
@@ -133,6 +163,27 @@ def rqs_apply(packed, a, x, y, logabsdet, accumulate, d_t, tcols, ccols, cfg, st
                                         _cabi.cols(ccols), ctypes.byref(cfg),
                                         status.data_ptr() if status is not None else None, _cabi.stream_ptr(x.device))
     _cabi.check(rc, "fc_conditioner_rqs_apply")
+    return y, logabsdet
+
+
+def sos_apply(packed, a, x, y, logabsdet, accumulate, d_t, n_sigmoids, offset):
+    """Whole conditioner + sum-of-sigmoids transform (forward) in one kernel (fc_conditioner_sos_apply).  a: [B, k_in]
+    matrix the initial layer multiplies (the context of a conditional layer, the inputs of a MADE)."""
+    _cabi.require_cuda_f32(a, "conditioner inputs")
+    _cabi.require_cuda_f32(x, "inputs")
+    L = _cabi.lib()
+    a, ap, lda = _cabi.rows(a)
+    if a.shape[1] != packed.k_in:
+        raise ValueError("conditioner inputs have {} columns, the packed net expects {}".format(a.shape[1], packed.k_in))
+    if a.shape[0] != x.shape[0]:
+        raise ValueError("conditioner inputs and inputs differ in rows")
+    assert x.stride(1) == 1 and y.stride(1) == 1 and logabsdet.is_contiguous()
+    with torch.cuda.device(x.device), _cabi.launch("fc_conditioner_sos_apply", x.device):
+        rc = L.fc_conditioner_sos_apply(ctypes.byref(packed.struct), ap, lda, a.shape[0], x.data_ptr(), x.stride(0),
+                                        y.data_ptr(), y.stride(0), logabsdet.data_ptr(), int(accumulate), d_t,
+                                        _cabi.cols(None), _cabi.cols(None), int(n_sigmoids), float(offset),
+                                        _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_conditioner_sos_apply")
     return y, logabsdet
 
 

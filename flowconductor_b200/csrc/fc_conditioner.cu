@@ -97,8 +97,31 @@ struct CondArgs {
   int n_copy;
   int D_t;
   RqsParams c;
+  float sos_offset;  // sum-of-sigmoids bijection: added to the outputs (autoregressive.py:309: -0.5; conditional.py: 0)
   int32_t* status;
   int32_t* error;  // device word: 0, or the code of the first wait that timed out
+};
+
+// The bijection a kernel instantiation evaluates from a register-resident parameter vector p[0 .. PPAD).
+template <int KC>
+struct CondRqs {  // rational-quadratic spline, KC bins, linear tails (rational_quadratic.py:13-181)
+  template <int PPAD>
+  static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
+                                              unsigned& status) {
+    rqs_eval<KC, true>(a.c, x, p, y, lad, status);
+  }
+};
+template <int NC>
+struct CondSos {  // sum of NC sigmoids + extended softplus (adaptive_sigmoids.py:111-142, nonlinearities.py:543-552), forward
+  template <int PPAD>
+  static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
+                                              unsigned&) {
+    static_assert(3 * NC + 1 <= PPAD, "parameters per feature");
+    float lj;
+    sos_eval_t<NC>(x, p, NC, y, lj);
+    y += a.sos_offset;
+    lad = lj;
+  }
 };
 
 __device__ int32_t g_cond_error;
@@ -257,8 +280,8 @@ struct CondSmem {
   static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + kVecBytes + BAR_BYTES + 1024;
 };
 
-// KC bins, PPAD accumulator columns per feature, NT = hidden width / 128
-template <int KC, int PPAD, int NT>
+// Bij the bijection, PPAD accumulator columns per feature, NT = hidden width / 128
+template <class Bij, int PPAD, int NT>
 __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(const CondArgs a) {
   constexpr int KCH = 2 * NT;         // 64-value chunks of a hidden-width reduction
   constexpr int FEATS = 96 / PPAD;    // features per final N tile
@@ -513,7 +536,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     auto spline = [&]() {
       if (pxc >= 0) {
         float yv, lv;
-        rqs_eval<KC, true>(a.c, pxv, pp, yv, lv, status);
+        Bij::eval(a, pxv, pp, yv, lv, status);
         if (pvalid) a.y[prow * a.ldy + pxc] = yv;
         lad_acc += lv;
       }
@@ -801,7 +824,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
 #pragma unroll
             for (int j = 0; j < PPAD; ++j) p[j] = pcol[(f * PPAD + j) * kCM];
             float yv, lv;
-            rqs_eval<KC, true>(a.c, xv[f], p, yv, lv, status);
+            Bij::eval(a, xv[f], p, yv, lv, status);
             if (xc[f] >= 0) {
               if (valid) a.y[row * a.ldy + xc[f]] = yv;
               lad_acc += lv;
@@ -908,9 +931,9 @@ __global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict_
   }
 }
 
-template <int KC, int PPAD, int NT>
+template <class Bij, int PPAD, int NT>
 static int launch_conditioner(const CondArgs& args, cudaStream_t stream) {
-  auto kern = conditioner_f16x3_kernel<KC, PPAD, NT>;
+  auto kern = conditioner_f16x3_kernel<Bij, PPAD, NT>;
   static_assert(CondSmem::TOTAL <= 232448, "shared memory per CTA");
   static std::atomic<uint64_t> configured{0};
   int dev_id = 0;
@@ -981,27 +1004,22 @@ extern "C" int fc_conditioner_error(int32_t* out) {
   return FC_OK;
 }
 
-extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
-                                        int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
-                                        int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
-                                        const fc_rqs_config* cfg, int32_t* status, void* stream) {
-  RqsParams c;
-  int rc = make_rqs_params(cfg, c);
-  if (rc != FC_OK) return rc;
+// Argument checks and the layer table shared by the fc_conditioner_*_apply entry points.  ppad: accumulator columns per
+// feature of the final layer's 96-column N tiles.
+static int cond_build_args(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                           int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                           int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int ppad, int32_t* status,
+                           CondArgs& args) {
   if (!net || !net->weights || net->n_layers < 2 || net->n_layers > kMaxCondLayers) return FC_ERR_INVALID_ARGUMENT;
   if (B < 0 || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
-  if (B == 0) return FC_OK;
-  if (!a || !x || !y || !logabsdet) return FC_ERR_INVALID_ARGUMENT;
+  if (B > 0 && (!a || !x || !y || !logabsdet)) return FC_ERR_INVALID_ARGUMENT;
   if (B >= ((int64_t)1 << 31)) return FC_ERR_UNSUPPORTED;
   if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
-  if (c.tails != FC_TAILS_LINEAR || (c.K != 8 && c.K != 16)) return FC_ERR_UNSUPPORTED;
   if (net->hidden != 128 && net->hidden != 256) return FC_ERR_UNSUPPORTED;
   if (net->k_in <= 0 || net->k_in > 256 || (net->k_in & 3) || (lda & 3) || lda < net->k_in ||
       (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(net->weights) & 15))
     return FC_ERR_UNSUPPORTED;
-  const int ppad = c.K == 8 ? 24 : 48;
   const int kch = net->hidden / 64;
-  CondArgs args{};
   args.weights = reinterpret_cast<const unsigned char*>(net->weights);
   args.a = a;
   args.lda = lda;
@@ -1046,16 +1064,49 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
   args.ccols = ccols.idx;
   args.n_copy = ccols.n;
   args.D_t = D_t;
-  args.c = c;
   args.status = status;
   void* err_ptr = nullptr;
   if (cudaGetSymbolAddress(&err_ptr, g_cond_error) != cudaSuccess) return FC_ERR_CUDA;
   args.error = reinterpret_cast<int32_t*>(err_ptr);
+  return FC_OK;
+}
+
+extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                                        int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                                        int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                                        const fc_rqs_config* cfg, int32_t* status, void* stream) {
+  RqsParams c;
+  int rc = make_rqs_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  if (c.tails != FC_TAILS_LINEAR || (c.K != 8 && c.K != 16)) return FC_ERR_UNSUPPORTED;
+  CondArgs args{};
+  rc = cond_build_args(net, a, lda, B, x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, D_t, tcols, ccols,
+                       c.K == 8 ? 24 : 48, status, args);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  args.c = c;
   cudaStream_t st = (cudaStream_t)stream;
   if (net->hidden == 256) {
-    if (c.K == 8) return launch_conditioner<8, 24, 2>(args, st);
-    return launch_conditioner<16, 48, 2>(args, st);
+    if (c.K == 8) return launch_conditioner<CondRqs<8>, 24, 2>(args, st);
+    return launch_conditioner<CondRqs<16>, 48, 2>(args, st);
   }
-  if (c.K == 8) return launch_conditioner<8, 24, 1>(args, st);
-  return launch_conditioner<16, 48, 1>(args, st);
+  if (c.K == 8) return launch_conditioner<CondRqs<8>, 24, 1>(args, st);
+  return launch_conditioner<CondRqs<16>, 48, 1>(args, st);
+}
+
+extern "C" int fc_conditioner_sos_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                                        int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                                        int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                                        int32_t n_sigmoids, float offset, void* stream) {
+  if (n_sigmoids < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (n_sigmoids != 10) return FC_ERR_UNSUPPORTED;  // the unrolled, MUFU-lean form (conditional.py:746 default)
+  CondArgs args{};
+  int rc = cond_build_args(net, a, lda, B, x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, D_t, tcols,
+                           ccols, 48, nullptr, args);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  args.sos_offset = offset;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (net->hidden == 256) return launch_conditioner<CondSos<10>, 48, 2>(args, st);
+  return launch_conditioner<CondSos<10>, 48, 1>(args, st);
 }

@@ -268,6 +268,36 @@ def cond_plan_for(net, col_map, k_in, num_bins, d_t):
     return packed
 
 
+def sos_cond_plan_for(net, k_in, n_sigmoids, d_t):
+    """PackedConditioner of `net` for the fused sum-of-sigmoids kernel, cached like the spline plans."""
+    key = (_param_key(net), "sos", n_sigmoids, k_in, d_t)
+    plan = getattr(net, "_fc_cond_plan", None)
+    if plan is not None and plan[0] == key:
+        return plan[1]
+    packed = fcond.pack_sos(net, n_sigmoids, d_t, k_in=k_in)
+    object.__setattr__(net, "_fc_cond_plan", (key, packed))
+    _generation[0] += 1
+    return packed
+
+
+def sos_fusable(net, k_in, n_sigmoids):
+    return FUSED_CONDITIONER and fcond.supported_sos_shape(net.initial_layer.weight.shape[0], k_in, len(net.blocks),
+                                                           n_sigmoids)
+
+
+def sos_layer(net, a, inputs, n_sigmoids, offset):
+    """Conditioner + sum-of-sigmoids transform (forward) as one kernel; returns (outputs, logabsdet).  `a` feeds the
+    conditioner (context / MADE inputs), `inputs` the bijection."""
+    packed = sos_cond_plan_for(net, a.shape[1], int(n_sigmoids), inputs.shape[1])
+    x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
+    y = torch.empty_like(x)
+    consume_consent()
+    mark_fresh(y)
+    lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
+    fcond.sos_apply(packed, a, x, y, lad, False, inputs.shape[1], n_sigmoids, offset)
+    return y, lad
+
+
 def conditioner_fusable(net, k_in, num_bins):
     return FUSED_CONDITIONER and fcond.supported_shape(net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins)
 

@@ -128,6 +128,13 @@ class MaskedSumOfSigmoidsTransform(AutoregressiveTransform):
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return ops.sos_layer(inputs, autoregressive_params, self.n_sigmoids, -0.5, True, 50, 120.0)
 
+    def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
+        net = self.autoregressive_net
+        if (not inverse and conditioner_inputs is inputs
+                and tensorcore.sos_fusable(net, inputs.shape[1], self.n_sigmoids)):
+            return tensorcore.sos_layer(net, inputs, inputs, self.n_sigmoids, -0.5)
+        return super()._tensorcore_layer(conditioner_inputs, inputs, inverse)
+
 
 class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTransform):
     """MAF-RQS layer.  Identity-init softplus (beta = ln2/(1-min_derivative)) is always on (autoregressive.py

@@ -29,6 +29,7 @@ class CompositeTransform(Transform):
 
     @staticmethod
     def _cascade(inputs, funcs, context):
+        from .. import _cabi
         from ..nn import tensorcore
 
         outputs = inputs
@@ -38,7 +39,13 @@ class CompositeTransform(Transform):
                 # the previous layer's output is referenced by this loop only: a layer may overwrite it in place
                 # (honoured by the tensor-core inference path when that layer allocated the tensor itself)
                 tensorcore.begin_layer(outputs if i > 0 else None)
-                outputs, logabsdet = func(outputs, context)
+                if _cabi.NVTX:
+                    owner = getattr(func, "__self__", func)
+                    name = "layer {}: {}.{}".format(i, type(owner).__name__, getattr(func, "__name__", "forward"))
+                    with _cabi.nvtx_range(name):
+                        outputs, logabsdet = func(outputs, context)
+                else:
+                    outputs, logabsdet = func(outputs, context)
                 total_logabsdet = total_logabsdet + logabsdet
         finally:
             tensorcore.end_cascade()

@@ -369,6 +369,16 @@ int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* a, int64_t 
                              int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
                              int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
                              const fc_rqs_config* cfg, int32_t* status, void* stream);
+/* Same kernel with the sum-of-sigmoids bijection (flowcon/transforms/adaptive_sigmoids.py:111-142 + ExtendedSoftplus,
+ * nonlinearities.py:543-552) in the forward direction: replaces ConditionalSumOfSigmoidsTransform.forward
+ * (flowcon/transforms/conditional.py:746-787: ResidualNet on the context, then SumOfSigmoids) and the forward of
+ * MaskedSumOfSigmoidsTransform (autoregressive.py:266-318, offset = -0.5); the [B, D_t * (3 n + 1)] parameter tensor is never
+ * materialised.  The final layer is packed with 48 accumulator columns per feature (row_map[j*P + i] = j*48 + i, two features
+ * per 96-column tile).  n_sigmoids = 10 only (FC_ERR_UNSUPPORTED otherwise: materialise the parameters, fc_sos_apply). */
+int fc_conditioner_sos_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                             int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                             int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t n_sigmoids,
+                             float offset, void* stream);
 /* Debugging aid: every barrier wait inside the kernel is bounded; if one ever times out the kernel ends early and leaves
  * a non-zero code (wait site + 100 * warp) here.  Synchronises the device.  Not part of the data path. */
 int fc_conditioner_error(int32_t* out);

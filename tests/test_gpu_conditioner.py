@@ -146,9 +146,13 @@ def test_conditioner_kernel(dev, kind, B, D, K, H, blocks, inverse, inplace):
 
 
 def test_conditioner_argument_errors(dev):
-    net = _random_net("resnet", 32, 64, 32 * 23, 2, dev, seed=0)  # hidden width 64: not covered
+    net = _random_net("resnet", 32, 320, 32 * 23, 2, dev, seed=0)  # hidden width above 256: not covered
     with pytest.raises(ValueError):
         fcond.pack_rqs(net, 8, 32)
+    net = _random_net("resnet", 32, 64, 32 * 23, 2, dev, seed=0)  # narrow nets are zero-padded to the kernel's 128
+    assert fcond.pack_rqs(net, 8, 32).hidden == 128
+    with pytest.raises(ValueError):
+        fcond.pack_rqs(net, 10, 32)  # 10 bins: not a fused shape
     net = _random_net("resnet", 32, 256, 32 * 23, 2, dev, seed=0)
     packed = fcond.pack_rqs(net, 8, 32, k_in=32)
     x = torch.randn(10, 32, device=dev)
@@ -227,6 +231,82 @@ def test_fused_and_perlayer_paths_agree_on_a_whole_flow(dev, monkeypatch):
     err = (xr - x).abs()
     assert err.median() < 1e-6 and torch.quantile(err.flatten()[: 1 << 20], 0.999) < 2e-4
     assert (lad + ladr).abs().median() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# sum-of-sigmoids bijection inside the fused conditioner (cfg 4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows", [777, 4096])
+def test_cfg4_layers_fused_sos_match_oracle(dev, rows):
+    """Every layer of the full-size conditional sum-of-sigmoids flow (D = 32, context 8, n = 10, H = 64 zero-padded to the
+    kernel's 128): ResidualNet on the context + SumOfSigmoids as ONE kernel, three-way against the fp32 / fp64 oracle."""
+    wl = workloads.get_workload("cfg4")
+    flow = workloads.build_flow(wl)
+    state = workloads.trained_like_({k: v.clone() for k, v in flow.state_dict().items()}, wl)
+    flow.load_state_dict(state)
+    specs = workloads.oracle_specs(wl)
+    state64 = {k: (v.double() if v.is_floating_point() else v) for k, v in state.items()}
+    flow = flow.to(dev).eval()
+    g = torch.Generator().manual_seed(17)
+    h = torch.randn(rows, wl["features"], generator=g)
+    ctx = torch.randn(rows, wl["context_features"], generator=g)
+    with torch.no_grad():
+        for li, (layer, spec) in enumerate(zip(flow._transform._transforms, specs)):
+            y64, l64 = restated.apply_layer(state64, spec, h.double(), ctx.double())
+            y32, l32 = restated.apply_layer(state, spec, h, ctx)
+            _cabi.STATS.reset()
+            y, lad = layer(h.to(dev), ctx.to(dev))
+            assert _cabi.STATS.counts.get("fc_conditioner_sos_apply", 0) == 1, _cabi.STATS.counts
+            assert set(_cabi.STATS.counts) <= {"fc_conditioner_sos_apply", "fc_conditioner_pack_layer"}, _cabi.STATS.counts
+            print("cfg4 layer %d fused sum-of-sigmoids: outputs %s | logabsdet %s" % (
+                li, parity_report(y, y32, y64, OUT_TOL, 1.0), parity_report(lad, l32, l64, OUT_TOL, 1.0)))
+            assert_parity(y, y32, y64, OUT_TOL, 1.0, "cfg4 layer %d outputs" % li)
+            assert_parity(lad, l32, l64, OUT_TOL, 1.0, "cfg4 layer %d logabsdet" % li)
+            h = y32
+        # whole flow: fused vs materialised parameters + element-wise kernel
+        x = torch.randn(rows, wl["features"], generator=g).to(dev)
+        c = ctx.to(dev)
+        a = flow.log_prob(x, context=c)
+        tensorcore.FUSED_CONDITIONER = False
+        try:
+            b = flow.log_prob(x, context=c)
+        finally:
+            tensorcore.FUSED_CONDITIONER = True
+    rel = (a - b).abs() / b.abs().clamp_min(1.0)
+    assert rel.median() < 2e-6 and rel.max() < 1e-3, (float(rel.median()), float(rel.max()))
+
+
+def test_masked_sum_of_sigmoids_forward_fused(dev, monkeypatch):
+    """MaskedSumOfSigmoidsTransform (autoregressive.py:266-318: MADE + SumOfSigmoids - 0.5), forward: fused vs unfused."""
+    torch.manual_seed(4)
+    layer = transforms.MaskedSumOfSigmoidsTransform(features=8, hidden_features=64, n_sigmoids=10).to(dev).eval()
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(torch.randn_like(p) * 0.2)
+        x = torch.randn(1500, 8, device=dev)
+        _cabi.STATS.reset()
+        y, lad = layer(x)
+        assert _cabi.STATS.counts.get("fc_conditioner_sos_apply", 0) == 1, _cabi.STATS.counts
+        monkeypatch.setattr(tensorcore, "ENABLED", False)
+        yu, ladu = layer(x)
+    assert ((y - yu).abs() / yu.abs().clamp_min(1.0)).max() < 1e-4
+    assert (lad - ladu).abs().max() < 1e-3
+
+
+def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypatch):
+    """H = 64 ResidualNet (cfg2_tc_small): zero-padded to 128 at pack time, one fused launch per layer, same numbers as the
+    per-layer kernels."""
+    wl = workloads.get_workload("cfg2_tc_small")
+    flow = workloads.build_flow(wl, seed=3).to(dev).eval()
+    x = torch.randn(1000, 64, device=dev)
+    with torch.no_grad():
+        _cabi.STATS.reset()
+        a = flow.log_prob(x)
+        assert _cabi.STATS.counts.get("fc_conditioner_rqs_apply", 0) == 3, _cabi.STATS.counts
+        monkeypatch.setattr(tensorcore, "FUSED_CONDITIONER", False)
+        b = flow.log_prob(x)
+    rel = (a - b).abs() / b.abs().clamp_min(1.0)
+    assert rel.max() < 1e-4, float(rel.max())
 
 
 # ------------------------------------------------------------------------------------------------
