@@ -69,7 +69,7 @@ class ConditionerLayer(ctypes.Structure):
 class Conditioner(ctypes.Structure):
     """struct fc_conditioner"""
     _fields_ = [("weights", ctypes.c_void_p), ("n_layers", ctypes.c_int32), ("hidden", ctypes.c_int32),
-                ("k_in", ctypes.c_int32), ("reserved", ctypes.c_int32), ("layers", ConditionerLayer * COND_MAX_LAYERS)]
+                ("k_in", ctypes.c_int32), ("hidden_k", ctypes.c_int32), ("layers", ConditionerLayer * COND_MAX_LAYERS)]
 
 
 class MadeProgramStruct(ctypes.Structure):

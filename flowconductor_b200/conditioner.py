@@ -87,7 +87,8 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
     L = _cabi.lib()
     init, fin = net.initial_layer, net.final_layer
     dev = init.weight.device
-    hidden = padded_hidden(init.weight.shape[0])
+    hidden_real = init.weight.shape[0]
+    hidden = padded_hidden(hidden_real)
     k_in = init.weight.shape[1] if k_in is None else k_in
     nb = len(net.blocks)
     if hidden is None or not (0 < k_in <= MAX_K_IN and k_in % 4 == 0 and 1 <= nb <= MAX_BLOCKS) or 96 % ppad or P > ppad:
@@ -96,18 +97,19 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
         raise ValueError("final layer has {} outputs, expected {} x {}".format(fin.weight.shape[0], d_t, P))
     feats = 96 // ppad
     n_final_tiles = (d_t + feats - 1) // feats
+    hk = _ceil_to(hidden_real, 64)  # k-values the layers after the first multiply (padding chunks are skipped)
     layers = [(init, _cabi.COND_INITIAL, 128, _ceil_to(k_in, 64), hidden)]
     for blk in net.blocks:
-        layers.append((blk.linear_layers[0], _cabi.COND_BLOCK_FIRST, 128, hidden, hidden))
-        layers.append((blk.linear_layers[1], _cabi.COND_BLOCK_SECOND, 128, hidden, hidden))
-    layers.append((fin, _cabi.COND_FINAL, 96, hidden, n_final_tiles * 96))
+        layers.append((blk.linear_layers[0], _cabi.COND_BLOCK_FIRST, 128, hk, hidden))
+        layers.append((blk.linear_layers[1], _cabi.COND_BLOCK_SECOND, 128, hk, hidden))
+    layers.append((fin, _cabi.COND_FINAL, 96, hk, n_final_tiles * 96))
     sizes = [int(L.fc_conditioner_layer_bytes(n_pad, k_pad, bn)) for (_, _, bn, k_pad, n_pad) in layers]
     assert all(s > 0 for s in sizes)
     blob = torch.empty((sum(sizes),), dtype=torch.uint8, device=dev)
     assert blob.data_ptr() % 16 == 0
     st = _cabi.Conditioner()
     st.weights = blob.data_ptr()
-    st.n_layers, st.hidden, st.k_in = len(layers), hidden, k_in
+    st.n_layers, st.hidden, st.k_in, st.hidden_k = len(layers), hidden, k_in, _ceil_to(hidden_real, 4)
     vectors = []
     offset = 0
     with torch.cuda.device(dev):

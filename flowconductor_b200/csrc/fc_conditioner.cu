@@ -710,6 +710,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           }
 #pragma unroll
           for (int c = 0; c < KCH; ++c) {
+            if (c >= L.k_chunks) break;  // a zero-padded narrow net has fewer real chunks than the kernel's width
             CPROF_T0(t_w);
             if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(7);
             CPROF_ADD(r_wait_f, t_w);
@@ -1020,6 +1021,8 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
       (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(net->weights) & 15))
     return FC_ERR_UNSUPPORTED;
   const int kch = net->hidden / 64;
+  const int hidden_k = net->hidden_k > 0 ? net->hidden_k : net->hidden;
+  if (hidden_k > net->hidden || (hidden_k & 3)) return FC_ERR_INVALID_ARGUMENT;
   args.weights = reinterpret_cast<const unsigned char*>(net->weights);
   args.a = a;
   args.lda = lda;
@@ -1037,12 +1040,14 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
     if ((reinterpret_cast<uintptr_t>(s.bias) & 3) || (reinterpret_cast<uintptr_t>(s.winv) & 3)) return FC_ERR_UNSUPPORTED;
     d.n_tiles = s.n_tiles;
     d.bn = last ? 96 : 128;
-    const int k = l == 0 ? net->k_in : net->hidden;
+    // reduction length: the input width, then the REAL hidden width (a narrower net zero-padded to 128 multiplies only its
+    // real k-values: the padding chunks are never staged, issued or drained)
+    const int k = l == 0 ? net->k_in : hidden_k;
     d.k_chunks = (k + 63) / 64;
     d.k_steps_last = ((k - (d.k_chunks - 1) * 64) + 15) / 16;
     if (!last && s.n_tiles != net->hidden / 128) return FC_ERR_INVALID_ARGUMENT;
     if (last && (int64_t)s.n_tiles * (96 / ppad) < D_t) return FC_ERR_INVALID_ARGUMENT;
-    if (l > 0 && d.k_chunks != kch) return FC_ERR_INVALID_ARGUMENT;
+    if (l > 0 && d.k_chunks > kch) return FC_ERR_INVALID_ARGUMENT;
     d.kind = s.kind;
     d.relu_next = s.relu_next;
     d.w_off16 = (unsigned)(s.w_offset >> 4);

@@ -353,7 +353,9 @@ typedef struct fc_conditioner_layer {
 } fc_conditioner_layer;
 typedef struct fc_conditioner {
   const void* weights; /* device, 16-byte aligned */
-  int32_t n_layers, hidden, k_in, reserved;
+  int32_t n_layers, hidden, k_in;
+  int32_t hidden_k; /* 0, or the real hidden width of a narrower net zero-padded to `hidden`: the layers after the first are
+                       then packed with k_pad = hidden_k rounded up to 64 and only those k-values are multiplied */
   fc_conditioner_layer layers[FC_COND_MAX_LAYERS];
 } fc_conditioner;
 
