@@ -165,12 +165,16 @@ def require_cuda_f32(t, name):
     return t
 
 
-def rows(t):
-    """(pointer, row stride in elements) of a 2-D tensor whose last dim is dense."""
+def rows(t, broadcast_ok=False):
+    """(pointer, row stride in elements) of a 2-D tensor whose last dim is dense.  broadcast_ok: a row shared by the whole
+    batch (an `expand`ed [1, n] tensor: row stride 0) is passed as it is — the kernels read `base + row * stride` — instead
+    of being materialised B times (the unconditional CDF layers' learnable parameters: ADVICE r1)."""
     if t.dim() != 2:
         raise ValueError("expected a 2-D tensor")
     if t.shape[1] > 1 and t.stride(1) != 1:
         t = t.contiguous()
+    if broadcast_ok and t.shape[0] > 1 and t.stride(0) == 0:
+        return t, t.data_ptr(), 0
     if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
         t = t.contiguous()
     return t, t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else t.shape[1])

@@ -32,7 +32,7 @@ def rqs_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: Optiona
     _cabi.require_cuda_f32(params, "transform params")
     L = _cabi.lib()
     x, xp, xs = _cabi.rows(x)
-    params, pp, ps = _cabi.rows(params)
+    params, pp, ps = _cabi.rows(params, broadcast_ok=True)
     B = x.shape[0]
     d_t = tcols.numel() if tcols is not None else x.shape[1]
     y = torch.empty((B, x.shape[1]), dtype=x.dtype, device=x.device)
@@ -144,7 +144,7 @@ def linspline_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: O
     _cabi.require_cuda_f32(params, "transform params")
     L = _cabi.lib()
     x, xp, xs = _cabi.rows(x)
-    params, pp, ps = _cabi.rows(params)
+    params, pp, ps = _cabi.rows(params, broadcast_ok=True)
     B = x.shape[0]
     d_t = tcols.numel() if tcols is not None else x.shape[1]
     if params.shape[1] != d_t * num_bins:
@@ -229,7 +229,7 @@ def quadspline_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: 
     _cabi.require_cuda_f32(params, "transform params")
     L = _cabi.lib()
     x, xp, xs = _cabi.rows(x)
-    params, pp, ps = _cabi.rows(params)
+    params, pp, ps = _cabi.rows(params, broadcast_ok=True)
     B = x.shape[0]
     d_t = tcols.numel() if tcols is not None else x.shape[1]
     p_per = 2 * num_bins - 1 if tails == _cabi.TAILS_LINEAR else 2 * num_bins + 1
@@ -318,7 +318,7 @@ def cubicspline_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols:
     _cabi.require_cuda_f32(params, "transform params")
     L = _cabi.lib()
     x, xp, xs = _cabi.rows(x)
-    params, pp, ps = _cabi.rows(params)
+    params, pp, ps = _cabi.rows(params, broadcast_ok=True)
     B = x.shape[0]
     d_t = tcols.numel() if tcols is not None else x.shape[1]
     p_per = 2 * num_bins + 2
@@ -406,7 +406,7 @@ def affine_layer(x: Tensor, params: Tensor, tcols: Optional[Tensor], ccols: Opti
     _cabi.require_cuda_f32(params, "transform params")
     L = _cabi.lib()
     x, xp, xs = _cabi.rows(x)
-    params, pp, ps = _cabi.rows(params)
+    params, pp, ps = _cabi.rows(params, broadcast_ok=True)
     B = x.shape[0]
     d_t = tcols.numel() if tcols is not None else x.shape[1]
     if params.shape[1] != 2 * d_t:
@@ -484,7 +484,7 @@ def sos_layer(x: Tensor, params: Tensor, n_sigmoids: int, offset: float, inverse
     _cabi.require_cuda_f32(params, "transform params")
     L = _cabi.lib()
     x, xp, xs = _cabi.rows(x)
-    params, pp, ps = _cabi.rows(params)
+    params, pp, ps = _cabi.rows(params, broadcast_ok=True)
     B, D = x.shape
     if params.shape[1] != D * (3 * n_sigmoids + 1):
         raise ValueError("sum-of-sigmoids params have {} columns, expected {}".format(

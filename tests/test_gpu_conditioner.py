@@ -309,6 +309,28 @@ def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypa
     assert rel.max() < 1e-4, float(rel.max())
 
 
+def test_shared_cdf_parameters_are_not_materialised(dev):
+    """the learnable parameters of an unconditional CDF layer are ONE row shared by the batch; the kernel reads
+    it with row stride 0 instead of a materialised [B, D * P] copy (3 GB at 1 M rows x 32 features x 23)."""
+    torch.manual_seed(0)
+    layer = transforms.PiecewiseRationalQuadraticCDF(shape=32, num_bins=8, tails="linear", tail_bound=3.0).to(dev)
+    rows = 1 << 18
+    x = torch.randn(rows, 32, device=dev)
+    with torch.no_grad():
+        p = layer._shared_params(rows)
+        assert p.stride(0) == 0
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats(dev)
+        before = torch.cuda.memory_allocated(dev)
+        y, lad = layer(x)
+        torch.cuda.synchronize()
+        extra = torch.cuda.max_memory_allocated(dev) - before
+        assert extra < 3 * x.numel() * 4, extra  # outputs + logabsdet, not rows x 32 x 23 floats
+        ym, ladm, _ = ops.rqs_layer(x, p.contiguous(), None, None, 8, _cabi.TAILS_LINEAR, False, False, -3.0, 3.0, -3.0, 3.0,
+                                    1e-3, 1e-3, 1e-3, 1.0)
+    assert torch.equal(y, ym) and torch.equal(lad, ladm)
+
+
 # ------------------------------------------------------------------------------------------------
 # host-side protocols around the kernels
 # ------------------------------------------------------------------------------------------------

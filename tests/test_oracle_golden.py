@@ -284,3 +284,20 @@ def test_restatement_matches_live_reference():
                                                                   tail_bound=tb, enable_identity_init=ident)
         _close(oy, ry, F32_TOL, "live rq y")
         _close(ol, rl, F32_TOL, "live rq lad")
+
+
+@pytest.mark.skipif(not locate.have_reference(), reason="reference tree not present")
+def test_standalone_sum_of_sigmoids_state_dict_matches_reference():
+    """the stand-alone SumOfSigmoids keeps the reference's state_dict keys (`extended_softplus.shift` as a
+    sub-module parameter, the frozen `log_scale_postact`), so a reference checkpoint loads with strict=True."""
+    locate.import_reference()
+    from flowcon.transforms.adaptive_sigmoids import SumOfSigmoids as RefSoS
+
+    from flowconductor_b200.transforms import SumOfSigmoids
+
+    torch.manual_seed(0)
+    ref = RefSoS(features=5, n_sigmoids=7)
+    ours = SumOfSigmoids(features=5, n_sigmoids=7)
+    assert set(ours.state_dict().keys()) == set(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    assert torch.equal(ours.get_raw_params(), ref.get_raw_params())
