@@ -27,6 +27,7 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_rqs_bins", "fc_linspline_apply
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
            "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_sos_apply", "fc_conditioner_error", "fc_conditioner_profile",
+           "fc_actnorm_apply", "fc_actnorm_workspace_floats", "fc_actnorm_backward",
            "fc_made_inverse_smem_bytes", "fc_made_inverse_profile", "fc_made_inverse_rqs", "fc_made_inverse_affine",
            "fc_version", "fc_built_for_sm"]
 COND_MAX_LAYERS = 10
@@ -136,6 +137,9 @@ def lib():
                                                Cols, Cols, i32, f32, vp]
         L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.fc_conditioner_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+        L.fc_actnorm_apply.argtypes = [vp, i64, vp, vp, vp, i64, vp, i32, i64, i32, i32, vp]
+        L.fc_actnorm_workspace_floats.argtypes = [i64, i32]
+        L.fc_actnorm_backward.argtypes = [vp, i64, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, i64, i32, i32, vp]
         L.fc_made_inverse_smem_bytes.argtypes = [i32, i32, i32, i32, i32]
         L.fc_made_inverse_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
         L.fc_made_inverse_rqs.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64,
@@ -147,6 +151,7 @@ def lib():
                 getattr(L, name).restype = ctypes.c_int
         L.fc_conditioner_layer_bytes.restype = ctypes.c_int64
         L.fc_made_inverse_smem_bytes.restype = ctypes.c_int64
+        L.fc_actnorm_workspace_floats.restype = ctypes.c_int64
         _lib = L
     return _lib
 

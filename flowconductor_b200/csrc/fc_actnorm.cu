@@ -1,0 +1,249 @@
+// fc_actnorm.cu — activation normalisation as a flow layer.
+//
+// Replaces ActNorm.forward / inverse (flowcon/transforms/normalization.py:144-218, 2-D inputs): per-feature
+//   forward  y = exp(log_scale) * x + shift,      logabsdet = +sum(log_scale)
+//   inverse  y = (x - shift) * exp(-log_scale),   logabsdet = -sum(log_scale)
+// and their gradients.  8 bytes per element forward: HBM-bound; one grid-stride pass with 128-bit accesses, the D scales /
+// shifts in shared memory.  The parameter gradients are reductions over the batch: every CTA reduces its row block per
+// column in a fixed order into a workspace, a second kernel sums the blocks in order (deterministic: replays of a
+// captured training step stay bitwise equal).
+#include "fc_common.cuh"
+
+namespace fc {
+
+constexpr int kActThreads = 256;
+
+struct ActArgs {
+  const float* x;
+  const float* log_scale;
+  const float* shift;
+  float* y;
+  float* lad;
+  int64_t xs, ys, B;
+  int D, inverse, accumulate;
+};
+
+__global__ void __launch_bounds__(kActThreads) actnorm_apply_kernel(const ActArgs a) {
+  extern __shared__ float sm[];  // [D] scale, [D] shift
+  float* sc = sm;
+  float* sh = sm + a.D;
+  __shared__ float total_s;
+  float part = 0.f;
+  for (int d = threadIdx.x; d < a.D; d += kActThreads) {
+    const float ls = __ldg(a.log_scale + d);
+    sc[d] = expf(a.inverse ? -ls : ls);
+    sh[d] = __ldg(a.shift + d);
+    part += ls;
+  }
+  // sum(log_scale) in a fixed order: per-thread partial sums, then thread 0 adds the 256 partials
+  __shared__ float parts[kActThreads];
+  parts[threadIdx.x] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kActThreads; ++i) t += parts[i];
+    total_s = a.inverse ? -t : t;
+  }
+  __syncthreads();
+  const float total = total_s;
+  const int D = a.D;
+  const bool vec = (D & 3) == 0 && (a.xs & 3) == 0 && (a.ys & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15) == 0;
+  const int64_t tid0 = (int64_t)blockIdx.x * kActThreads + threadIdx.x, nthr = (int64_t)gridDim.x * kActThreads;
+  if (vec) {
+    const int D4 = D >> 2;
+    const int64_t n4 = a.B * D4;
+    for (int64_t i = tid0; i < n4; i += nthr) {
+      const int64_t r = i / D4;
+      const int d = (int)(i - r * D4) << 2;
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(a.x + r * a.xs + d));
+      float4 o;
+      if (a.inverse) {
+        o.x = (v.x - sh[d]) * sc[d], o.y = (v.y - sh[d + 1]) * sc[d + 1];
+        o.z = (v.z - sh[d + 2]) * sc[d + 2], o.w = (v.w - sh[d + 3]) * sc[d + 3];
+      } else {
+        o.x = fmaf(sc[d], v.x, sh[d]), o.y = fmaf(sc[d + 1], v.y, sh[d + 1]);
+        o.z = fmaf(sc[d + 2], v.z, sh[d + 2]), o.w = fmaf(sc[d + 3], v.w, sh[d + 3]);
+      }
+      __stcs(reinterpret_cast<float4*>(a.y + r * a.ys + d), o);
+    }
+  } else {
+    const int64_t n = a.B * D;
+    for (int64_t i = tid0; i < n; i += nthr) {
+      const int64_t r = i / D;
+      const int d = (int)(i - r * D);
+      const float v = a.x[r * a.xs + d];
+      a.y[r * a.ys + d] = a.inverse ? (v - sh[d]) * sc[d] : fmaf(sc[d], v, sh[d]);
+    }
+  }
+  for (int64_t r = tid0; r < a.B; r += nthr) a.lad[r] = a.accumulate ? a.lad[r] + total : total;
+}
+
+struct ActBwdArgs {
+  const float* x;
+  const float* log_scale;
+  const float* shift;
+  const float* gy;
+  const float* gl;  // may be null
+  float* gx;
+  float* ws;  // [blocks][2][D] column sums, then [blocks] sums of gl
+  int64_t xs, gys, gxs, B;
+  int D, inverse, blocks;
+  int64_t rows_per_block;
+};
+
+// CTA g: rows [g R, (g + 1) R).  Threads (tx = column lane, ty = row lane); a thread owns columns tx, tx + CW, ... (<= 16)
+__global__ void __launch_bounds__(kActThreads) actnorm_backward_kernel(const ActBwdArgs a, int cw) {
+  extern __shared__ float sm[];  // [D] scale, [D] shift, then [ry][2][D] partial sums
+  const int D = a.D;
+  float* sc = sm;
+  float* sh = sm + D;
+  float* red = sm + 2 * D;
+  for (int d = threadIdx.x; d < D; d += kActThreads) {
+    const float ls = __ldg(a.log_scale + d);
+    sc[d] = expf(a.inverse ? -ls : ls);
+    sh[d] = __ldg(a.shift + d);
+  }
+  __syncthreads();
+  const int ry = kActThreads / cw, tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const int64_t r_lo = (int64_t)blockIdx.x * a.rows_per_block;
+  int64_t r_hi = r_lo + a.rows_per_block;
+  r_hi = r_hi < a.B ? r_hi : a.B;
+  constexpr int kMaxCols = 16;
+  float s_ls[kMaxCols], s_sh[kMaxCols];
+#pragma unroll
+  for (int c = 0; c < kMaxCols; ++c) s_ls[c] = s_sh[c] = 0.f;
+  for (int64_t r = r_lo + ty; r < r_hi; r += ry) {
+#pragma unroll
+    for (int c = 0; c < kMaxCols; ++c) {
+      const int d = tx + c * cw;
+      if (d < D) {
+        const float g = a.gy[r * a.gys + d], xv = a.x[r * a.xs + d], s = sc[d];
+        a.gx[r * a.gxs + d] = g * s;
+        if (a.inverse) {
+          s_ls[c] -= g * ((xv - sh[d]) * s);  // d y / d log_scale = -y
+          s_sh[c] -= g * s;
+        } else {
+          s_ls[c] += g * (xv * s);
+          s_sh[c] += g;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxCols; ++c) {
+    const int d = tx + c * cw;
+    if (d < D) {
+      red[(ty * 2 + 0) * D + d] = s_ls[c];
+      red[(ty * 2 + 1) * D + d] = s_sh[c];
+    }
+  }
+  __syncthreads();
+  float* out = a.ws + (size_t)blockIdx.x * 2 * D;
+  for (int d = threadIdx.x; d < D; d += kActThreads) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int y = 0; y < ry; ++y) {
+      t0 += red[(y * 2 + 0) * D + d];
+      t1 += red[(y * 2 + 1) * D + d];
+    }
+    out[d] = t0;
+    out[D + d] = t1;
+  }
+  // sum of grad_logabsdet over the CTA's rows (each log_scale[d] receives +-sum_b gl[b])
+  if (a.gl) {
+    __shared__ float gparts[kActThreads];
+    float t = 0.f;
+    for (int64_t r = r_lo + threadIdx.x; r < r_hi; r += kActThreads) t += a.gl[r];
+    gparts[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < kActThreads; ++i) s += gparts[i];
+      a.ws[(size_t)a.blocks * 2 * D + blockIdx.x] = s;
+    }
+  }
+}
+
+__global__ void actnorm_finish_kernel(const float* ws, int blocks, int D, int has_gl, int inverse, float* g_ls, float* g_sh) {
+  float gl_total = 0.f;
+  if (has_gl) {
+    for (int b = 0; b < blocks; ++b) gl_total += ws[(size_t)blocks * 2 * D + b];
+    if (inverse) gl_total = -gl_total;
+  }
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int b = 0; b < blocks; ++b) {
+      t0 += ws[(size_t)b * 2 * D + d];
+      t1 += ws[(size_t)b * 2 * D + D + d];
+    }
+    g_ls[d] = t0 + gl_total;
+    g_sh[d] = t1;
+  }
+}
+
+static int act_blocks(int64_t B) {
+  const int64_t want = (B + 255) / 256;  // at least 256 rows per CTA
+  const int cap = 2 * device_info().sm_count;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_actnorm_apply(const float* x, int64_t x_row_stride, const float* log_scale, const float* shift, float* y,
+                                int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B, int32_t D,
+                                int32_t inverse, void* stream) {
+  if (B < 0 || D < 1 || !log_scale || !shift) return FC_ERR_INVALID_ARGUMENT;
+  if (B == 0) return FC_OK;
+  if (!x || !y || !logabsdet || x_row_stride < D || y_row_stride < D) return FC_ERR_INVALID_ARGUMENT;
+  if (D > 8192) return FC_ERR_UNSUPPORTED;
+  ActArgs a;
+  a.x = x; a.log_scale = log_scale; a.shift = shift; a.y = y; a.lad = logabsdet;
+  a.xs = x_row_stride; a.ys = y_row_stride; a.B = B; a.D = D; a.inverse = inverse; a.accumulate = accumulate_logabsdet;
+  const int64_t work = (B * D + 4 * kActThreads - 1) / (4 * kActThreads);
+  const int cap = 8 * device_info().sm_count;
+  const int grid = (int)(work < 1 ? 1 : (work > cap ? cap : work));
+  actnorm_apply_kernel<<<grid, kActThreads, 2 * D * sizeof(float), (cudaStream_t)stream>>>(a);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}
+
+extern "C" int64_t fc_actnorm_workspace_floats(int64_t B, int32_t D) {
+  if (B < 0 || D < 1) return FC_ERR_INVALID_ARGUMENT;
+  const int blocks = act_blocks(B);
+  return (int64_t)blocks * 2 * D + blocks;
+}
+
+extern "C" int fc_actnorm_backward(const float* x, int64_t x_row_stride, const float* log_scale, const float* shift,
+                                   const float* grad_y, int64_t gy_row_stride, const float* grad_logabsdet, float* grad_x,
+                                   int64_t gx_row_stride, float* grad_log_scale, float* grad_shift, float* workspace,
+                                   int64_t B, int32_t D, int32_t inverse, void* stream) {
+  if (B < 0 || D < 1 || !log_scale || !shift || !grad_log_scale || !grad_shift) return FC_ERR_INVALID_ARGUMENT;
+  if (B > 0 && (!x || !grad_y || !grad_x || !workspace)) return FC_ERR_INVALID_ARGUMENT;
+  if (D > 4096) return FC_ERR_UNSUPPORTED;  // 16 columns per thread
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    if (cudaMemsetAsync(grad_log_scale, 0, sizeof(float) * D, st) != cudaSuccess) return FC_ERR_CUDA;
+    if (cudaMemsetAsync(grad_shift, 0, sizeof(float) * D, st) != cudaSuccess) return FC_ERR_CUDA;
+    return FC_OK;
+  }
+  ActBwdArgs a;
+  a.x = x; a.log_scale = log_scale; a.shift = shift; a.gy = grad_y; a.gl = grad_logabsdet; a.gx = grad_x; a.ws = workspace;
+  a.xs = x_row_stride; a.gys = gy_row_stride; a.gxs = gx_row_stride; a.B = B; a.D = D; a.inverse = inverse;
+  a.blocks = act_blocks(B);
+  a.rows_per_block = (B + a.blocks - 1) / a.blocks;
+  int cw = next_pow2(D);
+  cw = cw > kActThreads ? kActThreads : cw;
+  const int ry = kActThreads / cw;
+  const size_t smem = sizeof(float) * ((size_t)2 * D + (size_t)ry * 2 * D);
+  auto kern = actnorm_backward_kernel;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return FC_ERR_CUDA;
+  kern<<<a.blocks, kActThreads, smem, st>>>(a, cw);
+  actnorm_finish_kernel<<<(D + 255) / 256, 256, 0, st>>>(workspace, a.blocks, D, grad_logabsdet != nullptr, inverse,
+                                                         grad_log_scale, grad_shift);
+  FC_CHECK_LAUNCH();
+  return FC_OK;
+}

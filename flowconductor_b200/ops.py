@@ -475,6 +475,80 @@ affine_layer.register_autograd(_affine_backward, setup_context=_affine_setup)
 
 
 # ------------------------------------------------------------------------------------------------
+# activation normalisation (per-feature affine, parameters shared by the batch)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("flowcon_b200::actnorm_layer", mutates_args=())
+def actnorm_layer(x: Tensor, log_scale: Tensor, shift: Tensor, inverse: bool) -> Tuple[Tensor, Tensor]:
+    _cabi.require_cuda_f32(x, "inputs")
+    _cabi.require_cuda_f32(log_scale, "log_scale")
+    _cabi.require_cuda_f32(shift, "shift")
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    B, D = x.shape
+    if log_scale.numel() != D or shift.numel() != D:
+        raise ValueError("log_scale / shift must have {} entries".format(D))
+    log_scale, shift = log_scale.contiguous(), shift.contiguous()
+    y = torch.empty((B, D), dtype=x.dtype, device=x.device)
+    lad = torch.empty((B,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device), _cabi.launch("fc_actnorm_apply", x.device):
+        rc = L.fc_actnorm_apply(xp, xs, log_scale.data_ptr(), shift.data_ptr(), y.data_ptr(), D, lad.data_ptr(), 0, B, D,
+                                int(inverse), _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_actnorm_apply")
+    return y, lad
+
+
+@actnorm_layer.register_fake
+def _(x, log_scale, shift, inverse):
+    return torch.empty_like(x), x.new_empty((x.shape[0],))
+
+
+@torch.library.custom_op("flowcon_b200::actnorm_layer_backward", mutates_args=())
+def actnorm_layer_backward(x: Tensor, log_scale: Tensor, shift: Tensor, grad_y: Tensor, grad_lad: Optional[Tensor],
+                           inverse: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    L = _cabi.lib()
+    x, xp, xs = _cabi.rows(x)
+    grad_y, gyp, gys = _cabi.rows(_cabi.require_cuda_f32(grad_y, "grad outputs"))
+    B, D = x.shape
+    log_scale, shift = log_scale.contiguous(), shift.contiguous()
+    gx = torch.empty((B, D), dtype=x.dtype, device=x.device)
+    gls = torch.empty((D,), dtype=x.dtype, device=x.device)
+    gsh = torch.empty((D,), dtype=x.dtype, device=x.device)
+    ws = torch.empty((max(int(L.fc_actnorm_workspace_floats(B, D)), 1),), dtype=x.dtype, device=x.device)
+    glp = None
+    if grad_lad is not None:
+        grad_lad = grad_lad.contiguous()
+        glp = grad_lad.data_ptr()
+    with torch.cuda.device(x.device), _cabi.launch("fc_actnorm_backward", x.device):
+        rc = L.fc_actnorm_backward(xp, xs, log_scale.data_ptr(), shift.data_ptr(), gyp, gys, glp, gx.data_ptr(), D,
+                                   gls.data_ptr(), gsh.data_ptr(), ws.data_ptr(), B, D, int(inverse),
+                                   _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_actnorm_backward")
+    return gx, gls, gsh
+
+
+@actnorm_layer_backward.register_fake
+def _(x, log_scale, shift, grad_y, grad_lad, inverse):
+    return torch.empty_like(x), torch.empty_like(log_scale), torch.empty_like(shift)
+
+
+def _actnorm_setup(ctx, inputs, output):
+    x, log_scale, shift, inverse = inputs
+    ctx.save_for_backward(x, log_scale, shift)
+    ctx.inverse = inverse
+
+
+def _actnorm_backward(ctx, gy, gl):
+    x, log_scale, shift = ctx.saved_tensors
+    if gy is None:
+        gy = torch.zeros_like(x)
+    gx, gls, gsh = actnorm_layer_backward(x, log_scale, shift, gy, gl, ctx.inverse)
+    return gx, gls.reshape(log_scale.shape), gsh.reshape(shift.shape), None
+
+
+actnorm_layer.register_autograd(_actnorm_backward, setup_context=_actnorm_setup)
+
+
+# ------------------------------------------------------------------------------------------------
 # sum-of-sigmoids layer
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("flowcon_b200::sos_layer", mutates_args=())

@@ -77,6 +77,13 @@ WORKLOADS = {
                                              {"kind": "prq_coupling", "mask": "alternating_odd", "num_bins": 5,
                                               "tails": "linear", "tail_bound": 3.0, "hidden_features": 16,
                                               "num_blocks": 2, "unconditional": True}]},
+    # ActNorm (normalization.py:144-218) between masked autoregressive layers
+    "actnorm_maf_small": {"features": 6, "context_features": None, "batch": 96,
+                          "layers": [{"kind": "actnorm"},
+                                     {"kind": "maf_affine", "hidden_features": 16, "num_blocks": 2},
+                                     {"kind": "permutation", "mode": "reverse"},
+                                     {"kind": "actnorm"},
+                                     {"kind": "maf_affine", "hidden_features": 16, "num_blocks": 2}]},
     # the piecewise-linear family (coupling.py:299-352, autoregressive.py:321-372, nonlinearities.py:250-283)
     "plin_coupling_small": {"features": 6, "context_features": None, "batch": 64,
                             "layers": [{"kind": "plin_coupling", "mask": "alternating_even", "num_bins": 8,
@@ -179,6 +186,12 @@ def trained_like_(state, workload, seed=1, weight_gain=8.0):
         kind = layer["kind"]
         if kind == "permutation":
             continue
+        if kind == "actnorm":  # a trained ActNorm has non-trivial per-feature scales and shifts
+            for name, std in (("log_scale", 0.4), ("shift", 0.7)):
+                key = layer_prefix(i) + name
+                state[key] = state[key] + std * torch.randn(state[key].numel(), generator=g, dtype=torch.float32).to(
+                    state[key].dtype)
+            continue
         net = {"prq_coupling": "transform_net", "affine_coupling": "transform_net", "maf_affine": "autoregressive_net",
                "maf_prq": "autoregressive_net", "maf_sos": "autoregressive_net", "cond_sos": "conditional_net",
                "cond_prq": "conditional_net", "plin_coupling": "transform_net", "maf_plin": "autoregressive_net",
@@ -216,6 +229,8 @@ def build_flow(workload, seed=0):
         if kind == "permutation":
             cls = transforms.RandomPermutation if layer["mode"] == "random" else transforms.ReversePermutation
             layers.append(cls(features))
+        elif kind == "actnorm":
+            layers.append(transforms.ActNorm(features))
         elif kind == "prq_coupling":
             hidden, blocks = layer["hidden_features"], layer["num_blocks"]
             layers.append(transforms.PiecewiseRationalQuadraticCouplingTransform(

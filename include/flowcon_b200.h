@@ -452,6 +452,22 @@ int fc_made_inverse_affine(const fc_made_program* prog, const float* z, int64_t 
                            int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
                            int32_t activation, void* stream);
 
+/*
+ * Activation normalisation (csrc/fc_actnorm.cu): ActNorm.forward / inverse for 2-D inputs,
+ * flowcon/transforms/normalization.py:144-218 —  forward y = exp(log_scale) * x + shift, logabsdet = sum(log_scale);
+ * inverse y = (x - shift) / exp(log_scale), logabsdet = -sum(log_scale).  log_scale, shift: device [D].  y may alias x.
+ * The backward writes grad_x and the per-feature parameter gradients (reductions over the batch, summed in a fixed order:
+ * deterministic); grad_logabsdet may be null; workspace: fc_actnorm_workspace_floats(B, D) floats of device scratch.
+ */
+int fc_actnorm_apply(const float* x, int64_t x_row_stride, const float* log_scale, const float* shift, float* y,
+                     int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B, int32_t D,
+                     int32_t inverse, void* stream);
+int64_t fc_actnorm_workspace_floats(int64_t B, int32_t D);
+int fc_actnorm_backward(const float* x, int64_t x_row_stride, const float* log_scale, const float* shift, const float* grad_y,
+                        int64_t gy_row_stride, const float* grad_logabsdet, float* grad_x, int64_t gx_row_stride,
+                        float* grad_log_scale, float* grad_shift, float* workspace, int64_t B, int32_t D, int32_t inverse,
+                        void* stream);
+
 /* Library / build info (also used by the loader test). */
 const char* fc_version(void);
 int fc_built_for_sm(void); /* 100 */

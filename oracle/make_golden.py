@@ -286,6 +286,8 @@ def build_reference_flow(wl, seed=0):
         if kind == "permutation":
             layers.append(transforms.RandomPermutation(features) if layer["mode"] == "random"
                           else transforms.ReversePermutation(features))
+        elif kind == "actnorm":
+            layers.append(transforms.ActNorm(features))
         elif kind in ("prq_coupling", "affine_coupling"):
             h, b = layer["hidden_features"], layer["num_blocks"]
             create = lambda i, o, h=h, b=b: nets.ResidualNet(i, o, hidden_features=h, num_blocks=b)  # noqa: E731
@@ -381,6 +383,7 @@ def make_model(name, with_grad=False, x_scale=1.0, uniform01=False, batch=None):
         conv = np32 if tag == "32" else np64
         f = build_reference_flow(wl).to(dt)
         f.load_state_dict({k: (v.to(dt) if v.is_floating_point() else v) for k, v in state.items()})
+        f.eval()  # ActNorm would otherwise re-initialise itself from the first batch (normalization.py:177-178)
         xx = x.to(dt)
         cc = c.to(dt) if c is not None else None
         with torch.no_grad():
@@ -405,6 +408,9 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-uncond":  # add one fixture without rewriting the others
         make_model("prq_coupling_uncond_small", with_grad=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-actnorm":
+        make_model("actnorm_maf_small", with_grad=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--only-cubic-functions":
         make_cubic_functions()
@@ -437,3 +443,4 @@ if __name__ == "__main__":
     make_model("maf_sos_small")
     make_model("prq_coupling_notails_small", uniform01=True)
     make_model("prq_coupling_uncond_small", with_grad=True)
+    make_model("actnorm_maf_small", with_grad=True)

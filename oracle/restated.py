@@ -801,6 +801,12 @@ def apply_layer(state, spec, inputs, context=None, inverse=False):
         if inverse:
             perm = torch.argsort(perm)
         return torch.index_select(inputs, 1, perm), inputs.new_zeros(inputs.shape[0])
+    if kind == "actnorm":  # flowcon/transforms/normalization.py:173-201 (2-D inputs, eval mode)
+        log_scale, shift = state[p + "log_scale"], state[p + "shift"]
+        ones = inputs.new_ones(inputs.shape[0])
+        if inverse:
+            return (inputs - shift.view(1, -1)) / torch.exp(log_scale).view(1, -1), -torch.sum(log_scale) * ones
+        return torch.exp(log_scale).view(1, -1) * inputs + shift.view(1, -1), torch.sum(log_scale) * ones
     if kind in ("prq_coupling", "maf_prq", "cond_prq"):
         hidden = spec["hidden_features"]
         # 1/sqrt(H) scaling only where the conditioner exposes .hidden_features (coupling.py:554,

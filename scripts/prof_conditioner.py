@@ -22,3 +22,7 @@ with torch.no_grad():
 torch.cuda.synchronize()
 assert conditioner.kernel_error() == 0 and bool(torch.isfinite(lad).all())
 print("ok", float(lad.double().sum()))
+prof = conditioner.kernel_profile()
+if prof.get("mma total"):
+    import json
+    print(json.dumps(prof))

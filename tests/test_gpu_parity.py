@@ -239,7 +239,7 @@ def test_sum_of_sigmoids_large_inputs(dev):
 # ------------------------------------------------------------------------------------------------
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
           "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small", "plin_coupling_small",
-          "maf_plin_small", "pquad_coupling_small", "maf_pquad_small", "pcubic_coupling_small", "maf_pcubic_small"]
+          "maf_plin_small", "pquad_coupling_small", "maf_pquad_small", "pcubic_coupling_small", "maf_pcubic_small", "actnorm_maf_small"]
 
 
 def _load(name, dev):
@@ -274,7 +274,7 @@ def test_flow_matches_reference(dev, name):
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small",
-                                  "cond_prq_small"])
+                                  "cond_prq_small", "actnorm_maf_small"])
 def test_flow_parameter_gradients_match_reference(dev, name):
     """loss = -log_prob(x).mean(); backward through our kernels vs the reference's autograd."""
     gold, wl, flow = _load(name, dev)
@@ -288,6 +288,48 @@ def test_flow_parameter_gradients_match_reference(dev, name):
         g = p.grad if p.grad is not None else torch.zeros_like(p)
         scale = max(1e-6, r64.abs().max().item())
         assert_parity(g / scale, r32 / scale, r64 / scale, GRAD_TOL, 1.0, name + " grad " + pn)
+
+
+def test_actnorm_data_dependent_initialisation(dev):
+    """normalization.py:177-178,204-218: in training mode the first batch sets log_scale / shift so that the outputs have
+    zero mean and unit variance; later calls leave them alone.  Large ragged batch: the vector path and the tail."""
+    layer = transforms.ActNorm(12).to(dev)
+    x = torch.randn(4097, 12, device=dev) * 3.0 + 1.5
+    layer.train()
+    y, lad = layer(x)
+    assert bool(layer.initialized)
+    assert y.mean(0).abs().max() < 1e-4 and (y.std(0) - 1).abs().max() < 1e-4
+    ref_lad = layer.log_scale.sum()
+    assert (lad - ref_lad).abs().max() < 1e-5
+    ls = layer.log_scale.detach().clone()
+    layer(x * 2)
+    assert torch.equal(layer.log_scale.detach(), ls)
+    xi, ladi = layer.inverse(y)
+    assert (xi - x).abs().max() < 1e-4 and (lad + ladi).abs().max() < 1e-5
+    # gradients against torch autograd of the reference's formula, odd width (scalar path)
+    layer = transforms.ActNorm(7).to(dev).eval()
+    with torch.no_grad():
+        layer.log_scale.normal_(0, 0.3)
+        layer.shift.normal_(0, 0.5)
+    x = torch.randn(333, 7, device=dev, requires_grad=True)
+    w = torch.randn(333, 7, device=dev)
+    wl = torch.randn(333, device=dev)
+    for inverse in (False, True):
+        for p in (layer.log_scale, layer.shift, x):
+            p.grad = None
+        y, lad = layer.inverse(x) if inverse else layer(x)
+        ((y * w).sum() + (lad * wl).sum()).backward()
+        got = [x.grad.clone(), layer.log_scale.grad.clone(), layer.shift.grad.clone()]
+        xr = x.detach().double().requires_grad_(True)
+        lsr = layer.log_scale.detach().double().requires_grad_(True)
+        shr = layer.shift.detach().double().requires_grad_(True)
+        if inverse:
+            yr, ladr = (xr - shr) / torch.exp(lsr), -lsr.sum() * torch.ones(333, device=dev, dtype=torch.float64)
+        else:
+            yr, ladr = torch.exp(lsr) * xr + shr, lsr.sum() * torch.ones(333, device=dev, dtype=torch.float64)
+        ((yr * w.double()).sum() + (ladr * wl.double()).sum()).backward()
+        for g, r in zip(got, (xr.grad, lsr.grad, shr.grad)):
+            assert ((g.double() - r).abs() / r.abs().clamp_min(1.0)).max() < 1e-4
 
 
 def test_sample_and_log_prob_consistency(dev):

@@ -15,7 +15,7 @@ from tests.helpers import ROOT, golden_state, load_golden
 
 MODELS = ["cfg1", "cfg2_small", "cfg3_small", "cfg4_small", "affine_coupling_small", "cond_prq_small",
           "maf_sos_small", "prq_coupling_notails_small", "prq_coupling_uncond_small", "plin_coupling_small",
-          "maf_plin_small", "pquad_coupling_small", "maf_pquad_small", "pcubic_coupling_small", "maf_pcubic_small"]
+          "maf_plin_small", "pquad_coupling_small", "maf_pquad_small", "pcubic_coupling_small", "maf_pcubic_small", "actnorm_maf_small"]
 
 
 @pytest.mark.parametrize("name", MODELS)
