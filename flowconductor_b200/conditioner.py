@@ -199,7 +199,7 @@ def kernel_error():
 PROFILE_FIELDS = {0: "mma total", 1: "mma wait operand", 2: "mma wait accumulator", 3: "mma wait weights", 4: "mma slots",
                   8: "row total", 9: "row initial operand", 10: "row final hand-off", 11: "row hidden wait",
                   12: "row hidden drain", 13: "row hidden skip/relu", 14: "row hidden convert", 15: "row final wait",
-                  16: "row final drain", 18: "bij total", 19: "bij wait", 20: "bij work"}
+                  16: "row final drain", 17: "row spline", 18: "bij total", 19: "bij wait", 20: "bij work"}
 
 
 def kernel_profile():

@@ -39,6 +39,7 @@
 // the leader), 4-11 row threads (two per row), 12-15 bijection threads (one per row).  Every mbarrier wait is bounded
 // (kTimeoutCycles): a protocol error ends the kernel with a code in the error word instead of hanging the GPU.
 #include <atomic>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "fc_common.cuh"
@@ -97,6 +98,7 @@ struct CondArgs {
   int n_copy;
   int D_t;
   RqsParams c;
+  int hand_period;   // every hand_period-th final N tile a row thread hands ALL its features to the bijection warps (0: never)
   float sos_offset;  // sum-of-sigmoids bijection: added to the outputs (autoregressive.py:309: -0.5; conditional.py: 0)
   int32_t* status;
   int32_t* error;  // device word: 0, or the code of the first wait that timed out
@@ -286,9 +288,13 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   constexpr int KCH = 2 * NT;         // 64-value chunks of a hidden-width reduction
   constexpr int FEATS = 96 / PPAD;    // features per final N tile
   constexpr int NF = FEATS / 2;       // ... per row thread (two threads share a row)
-  constexpr int NF_OWN = (NF + 1) / 2;  // features of an N tile a row thread evaluates itself ...
-  constexpr int NF_BIJ = NF - NF_OWN;   // ... and hands to its row's bijection thread (8 bins: one each; 16 bins: 1 / 0)
-  static_assert(NF >= 1 && NF * 2 * PPAD == 96 && NF_OWN == 1, "final N tile: 96 columns");
+  // Of the NF features of an N tile whose parameters a row thread accumulates it evaluates its first one itself and hands
+  // the others to its row's bijection thread; on every hand_period-th tile it hands over ALL of them (measured: the row
+  // threads are the critical resource — drains, conversions and one spline per tile keep them ~80 % busy while the
+  // bijection warps wait 60 % of the time —, so part of the row threads' splines moves there).
+  constexpr int NF_OWN = 1;
+  static_assert(NF >= 1 && NF * 2 * PPAD == 96, "final N tile: 96 columns");
+  auto tile_own = [&](int nt) { return (a.hand_period > 0 && (nt + 1) % a.hand_period == 0) ? 0 : NF_OWN; };
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 1023u) & ~1023u;
@@ -502,7 +508,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     float pxv = 0.f, lad_acc = 0.f;
     int pxc = -1;
     long long prow = 0;
-    bool pvalid = false, pending = false;
+    bool pvalid = false, pending = false, tile_open = false;  // tile_open: the row tile's log-det share is not handed over yet
 #pragma unroll
     for (int j = 0; j < PPAD; ++j) pp[j] = 0.f;
     CPROF_DECL(r_spline);
@@ -577,10 +583,11 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         CPROF_ADD(r_l0, t_l0);
       }
       // ---- finish the previous row tile while the initial layer's MMAs run
-      if (pending) {
+      if (tile_open) {
         CPROF_T0(t_s);
-        spline();
+        if (pending) spline();
         finish_tile();
+        tile_open = false;
         CPROF_ADD(r_spline, t_s);
       }
       // ---- hidden layers
@@ -592,7 +599,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         uint32_t pw[64];
         float pre_inv = 0.f;
         const float winv_l = vwinv[l];
-        if (l == 0 && pt > 0 && NF_BIJ > 0) {
+        if (l == 0 && pt > 0) {
           // the residual stream's space still holds the previous row tile's last parameter tiles: wait until the bijection
           // warps have consumed both buffers (as if about to write each of them again)
           const uint32_t n0w = (pt + 1u) >> 1, n1w = pt >> 1;  // writes so far to buffer 0 / 1
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         const CondLayerDev& L = a.L[a.n_layers - 1];
         const float* sc_cur = scs + (lcount & 1u) * (4 * kCM);
         const float winv_f = vwinv[a.n_layers - 1];
-        for (int nt = 0; nt < L.n_tiles; ++nt, ++pt) {
+        for (int nt = 0; nt < L.n_tiles; ++nt) {
           float pv[NF * PPAD];
           const int fg = nt * FEATS + half * NF;  // this thread's own feature
           const bool live = fg < a.D_t;
@@ -732,30 +739,37 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
               CPROF_ADD(r_spline, t_s);
             }
           }
-          if constexpr (NF_BIJ > 0) {
+          const int nown = tile_own(nt), nhand = NF - nown;
+          if (nhand > 0) {
             CPROF_T0(t_h);
             const uint32_t b = pt & 1u, nw = pt >> 1;  // buffer, and how often it has been written before
             if (!cond_wait(pempty_bar(b), (nw & 1u) ^ 1u, abort_s)) COND_FAIL(10);
-            float* pcol = hs + (b * (2 * NF_BIJ * PPAD) + half * (NF_BIJ * PPAD)) * kCM + rl;
+            float* pcol = hs + (b * (2 * NF * PPAD) + half * (NF * PPAD)) * kCM + rl;
 #pragma unroll
-            for (int j = 0; j < NF_BIJ * PPAD; ++j) pcol[j * kCM] = pv[NF_OWN * PPAD + j];
+            for (int j = 0; j < NF * PPAD; ++j) {
+              if (j >= nown * PPAD) pcol[(j - nown * PPAD) * kCM] = pv[j];
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(pfull_bar(b));  // release: orders the warp's stores above
+            ++pt;
             CPROF_ADD(r_hand, t_h);
           }
+          if (nown > 0) {
 #pragma unroll
-          for (int j = 0; j < PPAD; ++j) pp[j] = pv[j];
-          pxv = xv;
-          pxc = xc;
-          prow = row;
-          pvalid = valid;
-          pending = true;
+            for (int j = 0; j < PPAD; ++j) pp[j] = pv[j];
+            pxv = xv;
+            pxc = xc;
+            prow = row;
+            pvalid = valid;
+            pending = true;
+          }
         }
         ++lcount;
+        tile_open = true;
       }
     }
-    if (pending) {
-      spline();
+    if (tile_open) {
+      if (pending) spline();
       finish_tile();
     }
     if (status != 0 && a.status) atomicOr(a.status, (int)status);
@@ -799,31 +813,35 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         }
       }
       float lad_acc = 0.f;
-      if constexpr (NF_BIJ > 0) {
-        for (int nt = 0; nt < n_final; ++nt, ++pt) {
-          // the features the two row threads of this row hand over: the last NF_BIJ of each half of the N tile
-          float xv[2 * NF_BIJ];
-          int xc[2 * NF_BIJ];
+      for (int nt = 0; nt < n_final; ++nt) {
+        const int nown = tile_own(nt), nhand = NF - nown;
+        if (nhand == 0) continue;
+        // the features the two row threads of this row hand over: the last nhand of each half of the N tile
+        float xv[2 * NF];
+        int xc[2 * NF];
 #pragma unroll
-          for (int f = 0; f < 2 * NF_BIJ; ++f) {  // inputs first: their latency hides behind the wait for the parameters
-            const int fg = nt * FEATS + (f / NF_BIJ) * NF + NF_OWN + (f % NF_BIJ);
-            const bool live = fg < a.D_t;
-            xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
-            xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
-          }
-          const uint32_t b = pt & 1u;
-          {
-            CPROF_T0(t_w);
-            if (!cond_wait(pfull_bar(b), (pt >> 1) & 1u, abort_s)) COND_FAIL(11);
-            CPROF_ADD(b_wait, t_w);
-          }
-          CPROF_T0(t_s);
-          const float* pcol = hs + (b * (2 * NF_BIJ * PPAD)) * kCM + r;
+        for (int f = 0; f < 2 * NF; ++f) {  // inputs first: their latency hides behind the wait for the parameters
+          const int h = f / NF, sl = f % NF;
+          const int fg = nt * FEATS + h * NF + nown + sl;
+          const bool live = sl < nhand && fg < a.D_t;
+          xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
+          xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
+        }
+        const uint32_t b = pt & 1u;
+        {
+          CPROF_T0(t_w);
+          if (!cond_wait(pfull_bar(b), (pt >> 1) & 1u, abort_s)) COND_FAIL(11);
+          CPROF_ADD(b_wait, t_w);
+        }
+        CPROF_T0(t_s);
+        const float* pcol = hs + (b * (2 * NF * PPAD)) * kCM + r;
 #pragma unroll
-          for (int f = 0; f < 2 * NF_BIJ; ++f) {
+        for (int f = 0; f < 2 * NF; ++f) {
+          const int h = f / NF, sl = f % NF;
+          if (sl < nhand) {
             float p[PPAD];
 #pragma unroll
-            for (int j = 0; j < PPAD; ++j) p[j] = pcol[(f * PPAD + j) * kCM];
+            for (int j = 0; j < PPAD; ++j) p[j] = pcol[((h * NF + sl) * PPAD + j) * kCM];
             float yv, lv;
             Bij::eval(a, xv[f], p, yv, lv, status);
             if (xc[f] >= 0) {
@@ -831,10 +849,11 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
               lad_acc += lv;
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pempty_bar(b));
-          CPROF_ADD(b_work, t_s);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pempty_bar(b));
+        ++pt;
+        CPROF_ADD(b_work, t_s);
       }
       // per-sample log|det J| (sum_except_batch, utils/torchutils.py:25-30): the row's three evaluating threads summed their
       // features in order; the partial sums are combined in a fixed order
@@ -1070,6 +1089,11 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
   args.n_copy = ccols.n;
   args.D_t = D_t;
   args.status = status;
+  static const int hand = [] {
+    const char* e = getenv("FC_COND_HAND");  // experiments: 0 = never hand everything over, n = every n-th final tile
+    return e && *e ? atoi(e) : 2;
+  }();
+  args.hand_period = hand < 0 ? 0 : hand;
   void* err_ptr = nullptr;
   if (cudaGetSymbolAddress(&err_ptr, g_cond_error) != cudaSuccess) return FC_ERR_CUDA;
   args.error = reinterpret_cast<int32_t*>(err_ptr);
