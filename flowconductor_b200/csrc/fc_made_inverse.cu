@@ -41,7 +41,8 @@ namespace fc {
 using namespace tc;
 
 constexpr int kMR = 32;                 // rows per CTA
-constexpr int kMW = FC_MADE_TASKS;      // compute warps = tasks per phase (8)
+constexpr int kMW = FC_MADE_TASKS;      // compute warps = tasks per phase (8; 16 measured: no faster — the wide phases are
+                                        // bound by shared-memory wavefronts, not by latency)
 constexpr int kMThreads = (kMW + 1) * 32;
 constexpr int kMJT = FC_MADE_MAX_NJ;    // outputs per task (24)
 constexpr int kMJL = kMJT / 4;          // ... per lane (6)
@@ -83,7 +84,7 @@ __device__ __forceinline__ long long made_clock_after(int dep) {
   return t;
 }
 #define MPROF_T(t, dep) const long long t = made_clock_after(dep)
-#define MPROF_ADD(i, t1, t0) prof[i] += (t1) - (t0)
+#define MPROF_ADD(i, t1, t0) prof[pb + (i)] += (t1) - (t0)
 #else
 #define MPROF_T(t, dep)
 #define MPROF_ADD(i, t1, t0)
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
   uint32_t ph = 0;
   unsigned status = 0;
 #if FC_MADE_PROFILE
-  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // [0..7] wide phases, [8..15] narrow phases
   const long long prof_begin = clock64();
 #endif
   const int D = a.D;
@@ -247,6 +248,9 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
       const int res_array = t2.x, b_off = t2.y;
       const int jl = (nj + 3) >> 2;  // outputs per lane
       const bool relu = (flags & FC_MADE_RELU_IN) != 0;
+#if FC_MADE_PROFILE
+      const int pb = rows > 40 ? 0 : 8;
+#endif
       MPROF_T(p_t1, rows + width + kn + b_off);
       MPROF_ADD(0, p_t1, p_t0);
       float2 acc[2 * kMJL];
@@ -334,7 +338,8 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
 #if FC_MADE_PROFILE
       {
         MPROF_T(p_t6, p);
-        prof[rows > 40 ? 6 : 7] += p_t6 - p_t0;
+        prof[pb + 6] += p_t6 - p_t0;
+        prof[pb + 7] += 1;
       }
 #endif
     }
@@ -350,12 +355,10 @@ __global__ void __launch_bounds__(kMThreads, 1) made_inverse_kernel(const MadeAr
   }
   if (warp == 0 && status != 0 && a.status) atomicOr(a.status, (int)status);
 #if FC_MADE_PROFILE
-  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {
-    unsigned long long* o = g_made_prof + (warp == 0 ? 0 : 8);
-    for (int i = 0; i < 6; ++i) o[i] = (unsigned long long)prof[i];
-    o[6] = (unsigned long long)(clock64() - prof_begin);
-    g_made_prof[16 + (warp == 0 ? 0 : 2)] = (unsigned long long)prof[6];
-    g_made_prof[17 + (warp == 0 ? 0 : 2)] = (unsigned long long)prof[7];
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5)) {  // (a light and a heavy warp of the wide phases)
+    unsigned long long* o = g_made_prof + (warp == 0 ? 0 : 16);
+    for (int i = 0; i < 16; ++i) o[i] = (unsigned long long)prof[i];
+    (void)prof_begin;
   }
 #endif
 }

@@ -183,13 +183,19 @@ def compile_made(net, params_per_feature):
             return [(li, j, min(MAX_NJ, j_hi - j), k0, kn, init_bias, final, j_base) for j in range(j_lo, j_hi, MAX_NJ)]
 
         def balance(tasks):
-            """Fewer than 8 tasks: halve the widest ones so that every warp has work."""
+            """Fewer tasks than warps: halve the most expensive ones (k-values x instructions per k-value) so that every
+            warp has work and the slowest task of the phase is as short as possible."""
             tasks = list(tasks)
+
+            def cost(t):
+                return (t[4] + 4) * (1 + 3 * ((t[2] + 3) // 4))
+
             while len(tasks) < TASKS:
-                i = max(range(len(tasks)), key=lambda t: tasks[t][2])
-                li, j, nj, k0, kn, ib, fn, jb = tasks[i]
-                if nj <= 4:
+                cand = [i for i in range(len(tasks)) if tasks[i][2] > 4]
+                if not cand:
                     break
+                i = max(cand, key=lambda t: cost(tasks[t]))
+                li, j, nj, k0, kn, ib, fn, jb = tasks[i]
                 half = 4 * (((nj + 3) // 4 + 1) // 2)
                 tasks[i:i + 1] = [(li, j, half, k0, kn, ib, fn, jb), (li, j + half, nj - half, k0, kn, ib, fn, jb)]
             return tasks
@@ -224,11 +230,8 @@ def compile_made(net, params_per_feature):
                     for li in range(1, fl):
                         wide += chunks(li, lo, hi, 0, lo, True, False, 0)
             if lo > 0 or not new:
-                # the feature's parameters from the units that were final before this pass (bias only when there are none),
-                # split evenly over the warps the layers above leave free
-                free = TASKS - len(wide) % TASKS
-                parts = max(free if free >= (P + MAX_NJ - 1) // MAX_NJ else TASKS, 1)
-                wide += [(fl, f * P + j, nj, 0, min(lo, hi), True, False, f * P) for j, nj in _split_even(P, parts)]
+                # the feature's parameters from the units that were final before this pass (bias only when there are none)
+                wide += chunks(fl, f * P, (f + 1) * P, 0, min(lo, hi), True, False, f * P)
             if not new:
                 # nothing new to compute: the wide phase completes the parameters
                 emit(balance(wide), f)
@@ -282,16 +285,20 @@ def apply_affine(prog, z, activation):
     return x, lad
 
 
-PROFILE_FIELDS = ("phase records", "wait weights", "multiply", "store units", "phase barrier", "invert feature", "total")
+PROFILE_FIELDS = ("phase record", "wait weights", "multiply", "store units", "phase barrier", "invert feature", "total",
+                  "phases")
 
 
 def kernel_profile():
-    """Cycle counters of the last launch (library built with FC_LINEAR_PROFILE_BUILD=1; zeros otherwise)."""
+    """Cycle counters of the last launch (library built with FC_LINEAR_PROFILE_BUILD=1; zeros otherwise): warps 0 and 5 of
+    CTA 0, wide phases (rows > 40) and narrow phases separately."""
     buf = (ctypes.c_uint64 * 32)()
     _cabi.check(_cabi.lib().fc_made_inverse_profile(buf), "fc_made_inverse_profile")
-    return {"warp0": {n: int(buf[i]) for i, n in enumerate(PROFILE_FIELDS)},
-            "warp5": {n: int(buf[8 + i]) for i, n in enumerate(PROFILE_FIELDS)},
-            "wide/narrow phases": [int(buf[16 + i]) for i in range(4)]}
+    out = {}
+    for w, base in (("warp0", 0), ("warp5", 16)):
+        for kind, off in (("wide", 0), ("narrow", 8)):
+            out[w + " " + kind] = {n: int(buf[base + off + i]) for i, n in enumerate(PROFILE_FIELDS)}
+    return out
 
 
 ENABLED = True  # False: every autoregressive inverse takes the D-pass path

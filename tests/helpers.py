@@ -119,7 +119,7 @@ def emulate_made_program(prog, z, invert_feature):
     for _, hdr, tasks in prog.tasks():
         rows, width, woff, feat = hdr["rows"], hdr["width"], hdr["w_off4"], hdr["feature"]
         assert width % 4 == 0 and 0 < width <= 2048 - 128 and len(tasks) >= 1
-        rec = prog.weights.detach().cpu()[woff * 4: woff * 4 + 100].view(torch.int32)
+        rec = prog.weights.detach().cpu()[woff * 4: woff * 4 + prog.phases_np.shape[1]].view(torch.int32)
         assert rec.tolist() == prog.phases_np[_].tolist()  # the record's copy in front of the matrix
         mat = w[woff * 4 + 128: woff * 4 + 128 + rows * width].reshape(rows, width)
         results = []
