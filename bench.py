@@ -503,11 +503,26 @@ def run_cfg2(args, wl):
                         "traffic": profile_json("traffic_rqs_apply.json").get("dram_bytes_per_launch"),
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_sample * B,
                         "kernel_ms_per_launch": (k_ms / n_k) if n_k else None, "launches_timed": n_k}
+        # (3) the sampling direction of the same flow (BASELINE configs[1]: "log_prob + sample"): noise -> 8 inverse layers,
+        # device-timed on this rank over the same number of rows; reported beside the headline, not part of `value`
+        with torch.no_grad():
+            flow._transform.inverse(x)
+            torch.cuda.synchronize()
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s3.record()
+            for _ in range(3):
+                flow._transform.inverse(x)
+            e3.record()
+            torch.cuda.synchronize()
+        ms_inv = s3.elapsed_time(e3) / 3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, wl, B, world),
+            "sample_direction": {"value": B / (ms_inv * 1e-3), "unit": "samples/s per GPU", "ms_per_pass": ms_inv,
+                                 "what": "CompositeTransform.inverse of the same flow over the same rows (Flow.sample minus "
+                                         "the base draw), rank 0"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "gpu_launches_by_entry_point": counts,

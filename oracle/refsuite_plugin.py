@@ -52,6 +52,14 @@ def pytest_configure(config):
     sys.stderr.write("refsuite: patched {} bindings of the reference with the CUDA kernels\n".format(len(undo.patched)))
 
 
+def pytest_runtest_setup(item):
+    # the reference's tests draw unseeded random inputs and weights (e.g. coupling_test.py:250: 3 * randn at eps 1e-3, where
+    # an input within rounding distance of a knot of a piecewise-LINEAR spline flips its bin between forward and inverse);
+    # a fixed seed per test makes a run reproducible, FC_REFSUITE_SEED selects another draw
+    seed = int(os.environ.get("FC_REFSUITE_SEED", "0"))
+    torch.manual_seed(seed * 100003 + len(item.nodeid))
+
+
 def pytest_unconfigure(config):
     sys.stderr.write("refsuite: {} calls went through the patched functions\n".format(CALLS["n"]))
     undo = getattr(config, "_fc_undo", None)
