@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libflowcon_b200.so")
+LIB_PATH = os.environ.get("FC_LIB") or os.path.join(_HERE, "lib", "libflowcon_b200.so")  # FC_LIB: A/B experiments only
 
 FC_OK = 0
 ERRORS = {-1: "invalid argument", -2: "unsupported configuration", -3: "CUDA launch error"}

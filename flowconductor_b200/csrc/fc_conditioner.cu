@@ -294,7 +294,15 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   // bijection warps wait 60 % of the time —, so part of the row threads' splines moves there).
   constexpr int NF_OWN = 1;
   static_assert(NF >= 1 && NF * 2 * PPAD == 96, "final N tile: 96 columns");
-  auto tile_own = [&](int nt) { return (a.hand_period > 0 && (nt + 1) % a.hand_period == 0) ? 0 : NF_OWN; };
+  // (compile-time "never" for tiles of several features per thread: measured to be best there, and the kernel keeps
+  // the leaner code — one own spline per row thread, NF - 1 per bijection thread and half)
+  auto tile_own = [&](int nt) -> int {
+    if constexpr (NF == 1) {
+      return (a.hand_period > 0 && (nt + 1) % a.hand_period == 0) ? 0 : NF_OWN;
+    } else {
+      return NF_OWN;
+    }
+  };
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_s = s32(smem_raw);
   const uint32_t base = (raw_s + 1023u) & ~1023u;
