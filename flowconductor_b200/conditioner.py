@@ -97,7 +97,8 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
         raise ValueError("final layer has {} outputs, expected {} x {}".format(fin.weight.shape[0], d_t, P))
     feats = 96 // ppad
     n_final_tiles = (d_t + feats - 1) // feats
-    hk = _ceil_to(hidden_real, 64)  # k-values the layers after the first multiply (padding chunks are skipped)
+    # k-values the layers after the first multiply: the 128-wide kernel skips a padding chunk (nets of <= 64 units)
+    hk = _ceil_to(hidden_real, 64) if hidden == 128 else hidden
     layers = [(init, _cabi.COND_INITIAL, 128, _ceil_to(k_in, 64), hidden)]
     for blk in net.blocks:
         layers.append((blk.linear_layers[0], _cabi.COND_BLOCK_FIRST, 128, hk, hidden))
@@ -109,7 +110,7 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
     assert blob.data_ptr() % 16 == 0
     st = _cabi.Conditioner()
     st.weights = blob.data_ptr()
-    st.n_layers, st.hidden, st.k_in, st.hidden_k = len(layers), hidden, k_in, _ceil_to(hidden_real, 4)
+    st.n_layers, st.hidden, st.k_in, st.hidden_k = len(layers), hidden, k_in, (_ceil_to(hidden_real, 4) if hidden == 128 else 0)
     vectors = []
     offset = 0
     with torch.cuda.device(dev):

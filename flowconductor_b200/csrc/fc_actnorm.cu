@@ -92,7 +92,10 @@ struct ActBwdArgs {
   int64_t rows_per_block;
 };
 
-// CTA g: rows [g R, (g + 1) R).  Threads (tx = column lane, ty = row lane); a thread owns columns tx, tx + CW, ... (<= 16)
+// CTA g: rows [g R, (g + 1) R).  Threads (tx = column lane, ty = row lane); a thread owns the V-wide column groups
+// tx, tx + CW, ... (V = 4: 128-bit accesses when D and the strides allow) and walks the CTA's rows two at a time, so that
+// four 16-byte loads are in flight per thread.
+template <int V>
 __global__ void __launch_bounds__(kActThreads) actnorm_backward_kernel(const ActBwdArgs a, int cw) {
   extern __shared__ float sm[];  // [D] scale, [D] shift, then [ry][2][D] partial sums
   const int D = a.D;
@@ -109,33 +112,70 @@ __global__ void __launch_bounds__(kActThreads) actnorm_backward_kernel(const Act
   const int64_t r_lo = (int64_t)blockIdx.x * a.rows_per_block;
   int64_t r_hi = r_lo + a.rows_per_block;
   r_hi = r_hi < a.B ? r_hi : a.B;
-  constexpr int kMaxCols = 16;
-  float s_ls[kMaxCols], s_sh[kMaxCols];
+  constexpr int kMaxGroups = 16 / V;  // column groups per thread (D <= 16 * 256 scalar, 4 * 4 * 256 vector)
+  float s_ls[kMaxGroups][V], s_sh[kMaxGroups][V];
 #pragma unroll
-  for (int c = 0; c < kMaxCols; ++c) s_ls[c] = s_sh[c] = 0.f;
-  for (int64_t r = r_lo + ty; r < r_hi; r += ry) {
+  for (int c = 0; c < kMaxGroups; ++c)
 #pragma unroll
-    for (int c = 0; c < kMaxCols; ++c) {
-      const int d = tx + c * cw;
+    for (int v = 0; v < V; ++v) s_ls[c][v] = s_sh[c][v] = 0.f;
+  auto one = [&](int c, int d, const float* g, const float* xv, float* gx) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float s = sc[d + v];
+      gx[v] = g[v] * s;
+      if (a.inverse) {
+        s_ls[c][v] -= g[v] * ((xv[v] - sh[d + v]) * s);  // d y / d log_scale = -y
+        s_sh[c][v] -= g[v] * s;
+      } else {
+        s_ls[c][v] += g[v] * (xv[v] * s);
+        s_sh[c][v] += g[v];
+      }
+    }
+  };
+  for (int64_t r = r_lo + ty; r < r_hi; r += 2 * ry) {
+    const bool two = r + ry < r_hi;
+#pragma unroll
+    for (int c = 0; c < kMaxGroups; ++c) {
+      const int d = (tx + c * cw) * V;
       if (d < D) {
-        const float g = a.gy[r * a.gys + d], xv = a.x[r * a.xs + d], s = sc[d];
-        a.gx[r * a.gxs + d] = g * s;
-        if (a.inverse) {
-          s_ls[c] -= g * ((xv - sh[d]) * s);  // d y / d log_scale = -y
-          s_sh[c] -= g * s;
+        float g0[V], x0[V], g1[V], x1[V], o0[V], o1[V];
+        if constexpr (V == 4) {
+          *reinterpret_cast<float4*>(g0) = __ldcs(reinterpret_cast<const float4*>(a.gy + r * a.gys + d));
+          *reinterpret_cast<float4*>(x0) = __ldcs(reinterpret_cast<const float4*>(a.x + r * a.xs + d));
+          if (two) {
+            *reinterpret_cast<float4*>(g1) = __ldcs(reinterpret_cast<const float4*>(a.gy + (r + ry) * a.gys + d));
+            *reinterpret_cast<float4*>(x1) = __ldcs(reinterpret_cast<const float4*>(a.x + (r + ry) * a.xs + d));
+          }
         } else {
-          s_ls[c] += g * (xv * s);
-          s_sh[c] += g;
+          g0[0] = a.gy[r * a.gys + d], x0[0] = a.x[r * a.xs + d];
+          if (two) g1[0] = a.gy[(r + ry) * a.gys + d], x1[0] = a.x[(r + ry) * a.xs + d];
+        }
+        one(c, d, g0, x0, o0);
+        if constexpr (V == 4) {
+          __stcs(reinterpret_cast<float4*>(a.gx + r * a.gxs + d), *reinterpret_cast<float4*>(o0));
+        } else {
+          a.gx[r * a.gxs + d] = o0[0];
+        }
+        if (two) {
+          one(c, d, g1, x1, o1);
+          if constexpr (V == 4) {
+            __stcs(reinterpret_cast<float4*>(a.gx + (r + ry) * a.gxs + d), *reinterpret_cast<float4*>(o1));
+          } else {
+            a.gx[(r + ry) * a.gxs + d] = o1[0];
+          }
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < kMaxCols; ++c) {
-    const int d = tx + c * cw;
+  for (int c = 0; c < kMaxGroups; ++c) {
+    const int d = (tx + c * cw) * V;
     if (d < D) {
-      red[(ty * 2 + 0) * D + d] = s_ls[c];
-      red[(ty * 2 + 1) * D + d] = s_sh[c];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        red[(ty * 2 + 0) * D + d + v] = s_ls[c][v];
+        red[(ty * 2 + 1) * D + d + v] = s_sh[c][v];
+      }
     }
   }
   __syncthreads();
@@ -182,8 +222,8 @@ __global__ void actnorm_finish_kernel(const float* ws, int blocks, int D, int ha
 }
 
 static int act_blocks(int64_t B) {
-  const int64_t want = (B + 255) / 256;  // at least 256 rows per CTA
-  const int cap = 2 * device_info().sm_count;
+  const int64_t want = (B + 127) / 128;  // at least 128 rows per CTA
+  const int cap = 8 * device_info().sm_count;
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -233,11 +273,13 @@ extern "C" int fc_actnorm_backward(const float* x, int64_t x_row_stride, const f
   a.xs = x_row_stride; a.gys = gy_row_stride; a.gxs = gx_row_stride; a.B = B; a.D = D; a.inverse = inverse;
   a.blocks = act_blocks(B);
   a.rows_per_block = (B + a.blocks - 1) / a.blocks;
-  int cw = next_pow2(D);
+  const bool vec = (D & 3) == 0 && (x_row_stride & 3) == 0 && (gy_row_stride & 3) == 0 && (gx_row_stride & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0;
+  int cw = next_pow2(vec ? D / 4 : D);
   cw = cw > kActThreads ? kActThreads : cw;
   const int ry = kActThreads / cw;
   const size_t smem = sizeof(float) * ((size_t)2 * D + (size_t)ry * 2 * D);
-  auto kern = actnorm_backward_kernel;
+  auto kern = vec ? actnorm_backward_kernel<4> : actnorm_backward_kernel<1>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return FC_ERR_CUDA;

@@ -283,7 +283,8 @@ struct CondSmem {
 };
 
 // Bij the bijection, PPAD accumulator columns per feature, NT = hidden width / 128
-template <class Bij, int PPAD, int NT>
+// HAND: every hand_period-th final tile is handed to the bijection warps entirely (instantiated where it pays)
+template <class Bij, int PPAD, int NT, bool HAND>
 __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(const CondArgs a) {
   constexpr int KCH = 2 * NT;         // 64-value chunks of a hidden-width reduction
   constexpr int FEATS = 96 / PPAD;    // features per final N tile
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   // (compile-time "never" for tiles of several features per thread: measured to be best there, and the kernel keeps
   // the leaner code — one own spline per row thread, NF - 1 per bijection thread and half)
   auto tile_own = [&](int nt) -> int {
-    if constexpr (NF == 1) {
+    if constexpr (HAND && NF == 1) {
       return (a.hand_period > 0 && (nt + 1) % a.hand_period == 0) ? 0 : NF_OWN;
     } else {
       return NF_OWN;
@@ -725,7 +726,9 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           }
 #pragma unroll
           for (int c = 0; c < KCH; ++c) {
-            if (c >= L.k_chunks) break;  // a zero-padded narrow net has fewer real chunks than the kernel's width
+            if constexpr (NT == 1) {
+              if (c >= L.k_chunks) break;  // a net of <= 64 units zero-padded to 128 has one real chunk, not two
+            }
             CPROF_T0(t_w);
             if (!cond_wait_cluster(tfull_bar(acc_i), aph, abort_s)) COND_FAIL(7);
             CPROF_ADD(r_wait_f, t_w);
@@ -959,9 +962,9 @@ __global__ void __launch_bounds__(128) cond_pack_kernel(const float* __restrict_
   }
 }
 
-template <class Bij, int PPAD, int NT>
+template <class Bij, int PPAD, int NT, bool HAND = false>
 static int launch_conditioner(const CondArgs& args, cudaStream_t stream) {
-  auto kern = conditioner_f16x3_kernel<Bij, PPAD, NT>;
+  auto kern = conditioner_f16x3_kernel<Bij, PPAD, NT, HAND>;
   static_assert(CondSmem::TOTAL <= 232448, "shared memory per CTA");
   static std::atomic<uint64_t> configured{0};
   int dev_id = 0;
@@ -1036,8 +1039,8 @@ extern "C" int fc_conditioner_error(int32_t* out) {
 // feature of the final layer's 96-column N tiles.
 static int cond_build_args(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
                            int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
-                           int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int ppad, int32_t* status,
-                           CondArgs& args) {
+                           int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int ppad, int hand_default,
+                           int32_t* status, CondArgs& args) {
   if (!net || !net->weights || net->n_layers < 2 || net->n_layers > kMaxCondLayers) return FC_ERR_INVALID_ARGUMENT;
   if (B < 0 || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (B > 0 && (!a || !x || !y || !logabsdet)) return FC_ERR_INVALID_ARGUMENT;
@@ -1048,7 +1051,7 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
       (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(net->weights) & 15))
     return FC_ERR_UNSUPPORTED;
   const int kch = net->hidden / 64;
-  const int hidden_k = net->hidden_k > 0 ? net->hidden_k : net->hidden;
+  const int hidden_k = (net->hidden_k > 0 && net->hidden == 128) ? net->hidden_k : net->hidden;
   if (hidden_k > net->hidden || (hidden_k & 3)) return FC_ERR_INVALID_ARGUMENT;
   args.weights = reinterpret_cast<const unsigned char*>(net->weights);
   args.a = a;
@@ -1074,7 +1077,8 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
     d.k_steps_last = ((k - (d.k_chunks - 1) * 64) + 15) / 16;
     if (!last && s.n_tiles != net->hidden / 128) return FC_ERR_INVALID_ARGUMENT;
     if (last && (int64_t)s.n_tiles * (96 / ppad) < D_t) return FC_ERR_INVALID_ARGUMENT;
-    if (l > 0 && d.k_chunks > kch) return FC_ERR_INVALID_ARGUMENT;
+    // (chunks are skipped only in the 128-wide kernel; the 256-wide one multiplies all four)
+    if (l > 0 && (d.k_chunks > kch || (net->hidden == 256 && d.k_chunks != kch))) return FC_ERR_INVALID_ARGUMENT;
     d.kind = s.kind;
     d.relu_next = s.relu_next;
     d.w_off16 = (unsigned)(s.w_offset >> 4);
@@ -1098,13 +1102,14 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
   args.D_t = D_t;
   args.status = status;
   // Measured (scripts/sweep_cond_hand.sh): with two features per row thread and tile (8 bins) handing more to the
-  // bijection warps does not pay (cfg 2: 24.4 ms never, 24.9 every 2nd, 26.4 always); with one feature per thread and
-  // tile (16 bins, sum of sigmoids: the bijection warps would otherwise idle) every 3rd tile is best (cfg 4: 2.00 -> 1.90 ms).
+  // bijection warps does not pay (cfg 2: 24.4 ms never, 24.9 every 2nd, 26.4 always), nor with 16-bin splines (cfg 3
+  // D-pass inverse 9.4 -> 10.8 ms at every 3rd tile); for the sum of sigmoids (one feature per thread and tile, the
+  // bijection warps would otherwise idle) every 3rd tile is best (cfg 4: 2.00 -> 1.90 ms).
   static const int hand = [] {
     const char* e = getenv("FC_COND_HAND");  // experiments: 0 = never hand everything over, n = every n-th final tile
     return e && *e ? atoi(e) : -1;
   }();
-  args.hand_period = hand >= 0 ? hand : (ppad == 48 ? 3 : 0);
+  args.hand_period = hand >= 0 ? hand : hand_default;
   void* err_ptr = nullptr;
   if (cudaGetSymbolAddress(&err_ptr, g_cond_error) != cudaSuccess) return FC_ERR_CUDA;
   args.error = reinterpret_cast<int32_t*>(err_ptr);
@@ -1121,7 +1126,7 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
   if (c.tails != FC_TAILS_LINEAR || (c.K != 8 && c.K != 16)) return FC_ERR_UNSUPPORTED;
   CondArgs args{};
   rc = cond_build_args(net, a, lda, B, x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, D_t, tcols, ccols,
-                       c.K == 8 ? 24 : 48, status, args);
+                       c.K == 8 ? 24 : 48, 0, status, args);
   if (rc != FC_OK) return rc;
   if (B == 0) return FC_OK;
   args.c = c;
@@ -1142,11 +1147,11 @@ extern "C" int fc_conditioner_sos_apply(const fc_conditioner* net, const float* 
   if (n_sigmoids != 10) return FC_ERR_UNSUPPORTED;  // the unrolled, MUFU-lean form (conditional.py:746 default)
   CondArgs args{};
   int rc = cond_build_args(net, a, lda, B, x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, D_t, tcols,
-                           ccols, 48, nullptr, args);
+                           ccols, 48, 3, nullptr, args);
   if (rc != FC_OK) return rc;
   if (B == 0) return FC_OK;
   args.sos_offset = offset;
   cudaStream_t st = (cudaStream_t)stream;
-  if (net->hidden == 256) return launch_conditioner<CondSos<10>, 48, 2>(args, st);
-  return launch_conditioner<CondSos<10>, 48, 1>(args, st);
+  if (net->hidden == 256) return launch_conditioner<CondSos<10>, 48, 2, true>(args, st);
+  return launch_conditioner<CondSos<10>, 48, 1, true>(args, st);
 }

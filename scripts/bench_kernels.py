@@ -161,6 +161,30 @@ def main():
         print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
                           "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                           "bytes": nbytes}), flush=True)
+    # cubic spline, same coupling shapes: K = 8 -> P = 2 K + 2 = 18, 4 (P + 2) B/element (was unmeasured)
+    pc = torch.randn(args.B, 32 * 18, generator=g, device=dev)
+    for name, fn, nbytes in (
+            ("cubicspline_fwd D=64 K=8 coupling", lambda: ops.cubicspline_layer(xl, pc, tca, cca, *quad),
+             args.B * (4 * 64 + 4 * 576 + 4 * 64 + 4)),
+            ("cubicspline_inv D=64 K=8 coupling (safeguarded Newton)",
+             lambda: ops.cubicspline_layer(xl, pc, tca, cca, 8, _cabi.TAILS_LINEAR, True, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3,
+                                           1.0 / 16.0), args.B * (4 * 64 + 4 * 576 + 4 * 64 + 4)),
+            ("cubicspline_bwd D=64 K=8 coupling", lambda: ops.cubicspline_layer_backward(xl, pc, gyl, gll, tca, cca, *quad),
+             args.B * (4 * 64 * 3 + 4 * 576 * 2 + 4))):
+        med, best = timeit(fn)
+        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
+                          "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
+                          "bytes": nbytes}), flush=True)
+    # ActNorm (8 B/element forward; backward reads x and grad_y, writes grad_x: 12 B/element)
+    ls, sh = torch.randn(64, device=dev) * 0.3, torch.randn(64, device=dev)
+    for name, fn, nbytes in (
+            ("actnorm_fwd D=64 (4M rows)", lambda: ops.actnorm_layer(xa, ls, sh, False), xa.shape[0] * (8 * 64 + 4)),
+            ("actnorm_bwd D=64 (4M rows)", lambda: ops.actnorm_layer_backward(xa, ls, sh, gya, gla, False),
+             xa.shape[0] * (12 * 64 + 4))):
+        med, best = timeit(fn)
+        print(json.dumps({"kernel": name, "variant": "direct", "ms_median": med, "ms_best": best,
+                          "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
+                          "bytes": nbytes}), flush=True)
     if args.sweep:
         a, nbytes = cases[args.sweep_case][1]
         best = None
