@@ -29,6 +29,7 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_rqs_bins", "fc_linspline_apply
            "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_sos_apply", "fc_conditioner_error", "fc_conditioner_profile",
            "fc_actnorm_apply", "fc_actnorm_workspace_floats", "fc_actnorm_backward",
            "fc_made_inverse_smem_bytes", "fc_made_inverse_profile", "fc_made_inverse_rqs", "fc_made_inverse_affine",
+           "fc_made_inverse_sos", "fc_made_inverse_linspline", "fc_made_inverse_quadspline", "fc_made_inverse_cubicspline",
            "fc_version", "fc_built_for_sm"]
 COND_MAX_LAYERS = 10
 COND_INITIAL, COND_BLOCK_FIRST, COND_BLOCK_SECOND, COND_FINAL = 0, 1, 2, 3
@@ -145,6 +146,13 @@ def lib():
         L.fc_made_inverse_rqs.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64,
                                           ctypes.POINTER(RqsConfig), vp, vp]
         L.fc_made_inverse_affine.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64, i32, vp]
+        L.fc_made_inverse_sos.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64, i32, f32, i32,
+                                          f32, vp]
+        L.fc_made_inverse_linspline.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64, i32, i32,
+                                                f32, f32, f32, f32, vp, vp]
+        L.fc_made_inverse_quadspline.argtypes = [ctypes.POINTER(MadeProgramStruct), vp, i64, vp, i64, vp, i32, i64,
+                                                 ctypes.POINTER(QuadSplineConfig), vp, vp]
+        L.fc_made_inverse_cubicspline.argtypes = L.fc_made_inverse_quadspline.argtypes
         L.fc_version.restype = ctypes.c_char_p
         for name in EXPORTS:
             if name not in ("fc_version",):

@@ -8,6 +8,7 @@
 // [K raw widths ; K raw heights ; raw left derivative ; raw right derivative]; configuration struct shared with the
 // quadratic layer (fc_quadspline_config).
 #include "fc_pipeline.cuh"
+#include "fc_made_inverse.cuh"
 
 namespace fc {
 
@@ -52,9 +53,43 @@ static int make_cubicspline_params(const fc_quadspline_config* cfg, CubicSplineP
   return FC_OK;
 }
 
+template <int KC>
+struct MadeCubicSplineOp {  // incremental autoregressive inverse (fc_made_inverse.cuh)
+  CubicSplineParams c;
+  __device__ __forceinline__ void eval(float z, const float* pc, float& x, float& lad, unsigned& status) const {
+    float p[2 * (KC ? KC : FC_MAX_BINS_GENERIC) + 2];
+    made_load_params(pc, 2 * c.K + 2, p);
+    cubicspline_eval<KC>(c, z, p, x, lad, status);
+  }
+};
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_made_inverse_cubicspline(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                                           int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                                           const fc_quadspline_config* cfg, int32_t* status, void* stream) {
+  CubicSplineParams c;
+  int rc = make_cubicspline_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  if (!c.inverse) return FC_ERR_INVALID_ARGUMENT;
+  MadeArgs a{};
+  rc = made_check(prog, z, z_row_stride, x, x_row_stride, logabsdet, B, 2 * c.K + 2, a);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  a.accumulate = accumulate_logabsdet;
+  a.status = status;
+#define CALL(KC)                                     \
+  {                                                  \
+    MadeCubicSplineOp<KC> op;                        \
+    op.c = c;                                        \
+    return launch_made(a, op, (cudaStream_t)stream); \
+  }
+  FC_DISPATCH_CUBIC_K(c.K, CALL)
+#undef CALL
+  return FC_OK;
+}
 
 extern "C" int fc_cubicspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
                                    float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,

@@ -7,6 +7,7 @@
 // (nonlinearities.py:250-283).  Same kernel skeletons as the rational-quadratic layer (fc_pipeline.cuh: per-warp TMA
 // ring; fc_staged.cuh: general strides); element math: fc_math.cuh.  HBM-bound: 4 (K + 2) bytes per transformed element.
 #include "fc_pipeline.cuh"
+#include "fc_made_inverse.cuh"
 
 namespace fc {
 
@@ -47,9 +48,43 @@ static int make_linspline_params(int32_t num_bins, int32_t tails, float left, fl
   return FC_OK;
 }
 
+template <int KC>
+struct MadeLinSplineOp {  // incremental autoregressive inverse (fc_made_inverse.cuh)
+  LinSplineParams c;
+  __device__ __forceinline__ void eval(float z, const float* pc, float& x, float& lad, unsigned& status) const {
+    float p[KC ? KC : FC_MAX_BINS_GENERIC];
+    made_load_params(pc, c.K, p);
+    linspline_eval<KC>(c, z, p, x, lad, status);
+  }
+};
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_made_inverse_linspline(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                                         int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                                         int32_t num_bins, int32_t tails, float left, float right, float bottom, float top,
+                                         int32_t* status, void* stream) {
+  LinSplineParams c;
+  int rc = make_linspline_params(num_bins, tails, left, right, bottom, top, 1, c);
+  if (rc != FC_OK) return rc;
+  MadeArgs a{};
+  rc = made_check(prog, z, z_row_stride, x, x_row_stride, logabsdet, B, c.K, a);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  a.accumulate = accumulate_logabsdet;
+  a.status = status;
+#define CALL(KC)                                     \
+  {                                                  \
+    MadeLinSplineOp<KC> op;                          \
+    op.c = c;                                        \
+    return launch_made(a, op, (cudaStream_t)stream); \
+  }
+  FC_DISPATCH_LIN_K(c.K, CALL)
+#undef CALL
+  return FC_OK;
+}
 
 extern "C" int fc_linspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
                                   float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,

@@ -7,6 +7,7 @@
 // (per-warp TMA ring) / fc_staged.cuh (general strides); element math: fc_math.cuh.  HBM-bound: 4 (P + 2) bytes per
 // transformed element, P = 2K+1 (no tails) or 2K-1 (linear tails).
 #include "fc_pipeline.cuh"
+#include "fc_made_inverse.cuh"
 
 namespace fc {
 
@@ -51,9 +52,46 @@ static int make_quadspline_params(const fc_quadspline_config* cfg, QuadSplinePar
   return FC_OK;
 }
 
+template <int KC>
+struct MadeQuadSplineOp {  // incremental autoregressive inverse (fc_made_inverse.cuh)
+  QuadSplineParams c;
+  int P;
+  __device__ __forceinline__ void eval(float z, const float* pc, float& x, float& lad, unsigned& status) const {
+    float p[2 * (KC ? KC : FC_MAX_BINS_GENERIC) + 1];
+    made_load_params(pc, P, p);
+    quadspline_eval<KC>(c, z, p, x, lad, status);
+  }
+};
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_made_inverse_quadspline(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                                          int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                                          const fc_quadspline_config* cfg, int32_t* status, void* stream) {
+  QuadSplineParams c;
+  int rc = make_quadspline_params(cfg, c);
+  if (rc != FC_OK) return rc;
+  if (!c.inverse) return FC_ERR_INVALID_ARGUMENT;
+  const int P = c.tails == FC_TAILS_LINEAR ? 2 * c.K - 1 : 2 * c.K + 1;
+  MadeArgs a{};
+  rc = made_check(prog, z, z_row_stride, x, x_row_stride, logabsdet, B, P, a);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  a.accumulate = accumulate_logabsdet;
+  a.status = status;
+#define CALL(KC)                                     \
+  {                                                  \
+    MadeQuadSplineOp<KC> op;                         \
+    op.c = c;                                        \
+    op.P = P;                                        \
+    return launch_made(a, op, (cudaStream_t)stream); \
+  }
+  FC_DISPATCH_QUAD_K(c.K, CALL)
+#undef CALL
+  return FC_OK;
+}
 
 extern "C" int fc_quadspline_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
                                    float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet,

@@ -7,6 +7,7 @@
 // full forward passes plus two autograd passes with host syncs (inverse).
 // Kernel skeleton: fc_staged.cuh; element math: fc_math.cuh.
 #include "fc_pipeline.cuh"
+#include "fc_made_inverse.cuh"
 
 namespace fc {
 
@@ -60,9 +61,44 @@ struct SosInverseOp {
   }
 };
 
+// incremental autoregressive inverse (fc_made_inverse.cuh): the numerical inverse of one feature
+template <int NC>
+struct MadeSosOp {
+  int n;
+  float offset;
+  int iters;
+  float lim;
+  __device__ __forceinline__ void eval(float z, const float* pc, float& x, float& lad, unsigned&) const {
+    float p[3 * (NC ? NC : FC_SOS_MAX_SIGMOIDS) + 1];
+    made_load_params(pc, 3 * n + 1, p);
+    float lj;
+    sos_invert_t<NC>(z - offset, p, n, iters, lim, x, lj);
+    lad = -lj;
+  }
+};
+
 }  // namespace fc
 
 using namespace fc;
+
+extern "C" int fc_made_inverse_sos(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                                   int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                                   int32_t n_sigmoids, float offset, int32_t bisection_iterations, float lim, void* stream) {
+  if (n_sigmoids < 1) return FC_ERR_INVALID_ARGUMENT;
+  if (n_sigmoids > FC_SOS_MAX_SIGMOIDS) return FC_ERR_UNSUPPORTED;
+  MadeArgs a{};
+  int rc = made_check(prog, z, z_row_stride, x, x_row_stride, logabsdet, B, 3 * n_sigmoids + 1, a);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  a.accumulate = accumulate_logabsdet;
+  a.status = nullptr;
+  if (n_sigmoids == 10) {
+    MadeSosOp<10> op{n_sigmoids, offset, bisection_iterations, lim};
+    return launch_made(a, op, (cudaStream_t)stream);
+  }
+  MadeSosOp<0> op{n_sigmoids, offset, bisection_iterations, lim};
+  return launch_made(a, op, (cudaStream_t)stream);
+}
 
 extern "C" int fc_sos_apply(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride,
                             float* y, int64_t y_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,

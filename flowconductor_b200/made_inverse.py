@@ -285,6 +285,39 @@ def apply_affine(prog, z, activation):
     return x, lad
 
 
+def _apply(entry, prog, z, *tail):
+    """Shared launch plumbing of the fc_made_inverse_* entry points: (x, logabsdet)."""
+    L = _cabi.lib()
+    z, zp, ldz, x, lad = _io(prog, z)
+    with torch.cuda.device(z.device), _cabi.launch(entry, z.device):
+        rc = getattr(L, entry)(ctypes.byref(prog.struct), zp, ldz, x.data_ptr(), x.stride(0), lad.data_ptr(), 0,
+                               z.shape[0], *tail, _cabi.stream_ptr(z.device))
+    _cabi.check(rc, entry)
+    return x, lad
+
+
+def _sptr(status):
+    return status.data_ptr() if status is not None else None
+
+
+def apply_sos(prog, z, n_sigmoids, offset, iterations, lim):
+    """Inverse of a MaskedSumOfSigmoidsTransform layer (numerical inverse per feature, as fc_sos_apply)."""
+    return _apply("fc_made_inverse_sos", prog, z, int(n_sigmoids), float(offset), int(iterations), float(lim))
+
+
+def apply_linspline(prog, z, num_bins, tails, lo, hi, status=None):
+    return _apply("fc_made_inverse_linspline", prog, z, int(num_bins), int(tails), float(lo), float(hi), float(lo), float(hi),
+                  _sptr(status))
+
+
+def apply_quadspline(prog, z, cfg, status=None):
+    return _apply("fc_made_inverse_quadspline", prog, z, ctypes.byref(cfg), _sptr(status))
+
+
+def apply_cubicspline(prog, z, cfg, status=None):
+    return _apply("fc_made_inverse_cubicspline", prog, z, ctypes.byref(cfg), _sptr(status))
+
+
 PROFILE_FIELDS = ("phase record", "wait weights", "multiply", "store units", "phase barrier", "invert feature", "total",
                   "phases")
 

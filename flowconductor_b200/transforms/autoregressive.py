@@ -128,6 +128,12 @@ class MaskedSumOfSigmoidsTransform(AutoregressiveTransform):
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return ops.sos_layer(inputs, autoregressive_params, self.n_sigmoids, -0.5, True, 50, 120.0)
 
+    def _incremental_inverse(self, inputs):
+        prog = made_inverse.program_for(self.autoregressive_net, self._output_dim_multiplier())
+        if prog is None:
+            return None
+        return made_inverse.apply_sos(prog, inputs, self.n_sigmoids, -0.5, 50, 120.0)
+
     def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
         net = self.autoregressive_net
         if (not inverse and conditioner_inputs is inputs
@@ -192,6 +198,13 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
                                     allow_inplace=not inverse)  # the inverse re-reads `inputs` D times
 
 
+def _status_for(inputs, tails):
+    """Device status word when the reference would check the domain on the host (no tails / STRICT)."""
+    if tails == _cabi.TAILS_NONE or splines.STRICT:
+        return torch.zeros((1,), dtype=torch.int32, device=inputs.device)
+    return None
+
+
 class MaskedPiecewiseLinearAutoregressiveTransform(AutoregressiveTransform):
     """autoregressive.py:321-372: always the constrained unit box (`linear_spline` without tails).  Note the
     reference's argument order: `num_bins` comes first."""
@@ -213,6 +226,17 @@ class MaskedPiecewiseLinearAutoregressiveTransform(AutoregressiveTransform):
 
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._spline.apply(inputs, autoregressive_params, None, None, True)
+
+    def _incremental_inverse(self, inputs):
+        prog = made_inverse.program_for(self.autoregressive_net, self._output_dim_multiplier())
+        if prog is None:
+            return None
+        tails, lo, hi = self._spline.domain()
+        status = _status_for(inputs, tails)
+        out = made_inverse.apply_linspline(prog, inputs, self.num_bins, tails, lo, hi, status)
+        if status is not None:
+            splines.check_status(status, tails)
+        return out
 
 
 class MaskedPiecewiseQuadraticAutoregressiveTransform(AutoregressiveTransform):
@@ -245,6 +269,17 @@ class MaskedPiecewiseQuadraticAutoregressiveTransform(AutoregressiveTransform):
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._spline.apply(inputs, autoregressive_params, None, None, True, None)
 
+    def _incremental_inverse(self, inputs):
+        prog = made_inverse.program_for(self.autoregressive_net, self._output_dim_multiplier())
+        if prog is None:
+            return None
+        cfg, tails = self._spline.config(True, None)
+        status = _status_for(inputs, tails)
+        out = made_inverse.apply_quadspline(prog, inputs, cfg, status)
+        if status is not None:
+            splines.check_status(status, tails)
+        return out
+
 
 class MaskedPiecewiseCubicAutoregressiveTransform(AutoregressiveTransform):
     """autoregressive.py:460-523: the constrained unit box (`cubic_spline` without tails); `num_bins` comes first as in
@@ -267,3 +302,14 @@ class MaskedPiecewiseCubicAutoregressiveTransform(AutoregressiveTransform):
 
     def _elementwise_inverse(self, inputs, autoregressive_params):
         return self._spline.apply(inputs, autoregressive_params, None, None, True, None)
+
+    def _incremental_inverse(self, inputs):
+        prog = made_inverse.program_for(self.autoregressive_net, self._output_dim_multiplier())
+        if prog is None:
+            return None
+        cfg, tails = self._spline.config(True, None)
+        status = _status_for(inputs, tails)
+        out = made_inverse.apply_cubicspline(prog, inputs, cfg, status)
+        if status is not None:
+            splines.check_status(status, tails)
+        return out

@@ -155,6 +155,12 @@ class LinearSplineSettings:
     def params_per_feature(self):
         return self.num_bins
 
+    def domain(self):
+        """(tails constant, lower, upper bound) of these settings."""
+        if self.tails == "linear":
+            return _cabi.TAILS_LINEAR, -float(self.tail_bound), float(self.tail_bound)
+        return _cabi.TAILS_NONE, 0.0, 1.0
+
     def apply(self, inputs, params, tcols, ccols, inverse):
         if self.tails == "linear":
             tails, lo, hi = _cabi.TAILS_LINEAR, -float(self.tail_bound), float(self.tail_bound)
@@ -189,6 +195,17 @@ def unconstrained_linear_spline(inputs, unnormalized_pdf, inverse=False, tail_bo
                                -tail_bound, tail_bound)
 
 
+def _quad_config(settings, inverse, hidden_for_scaling):
+    if settings.tails == "linear":
+        tails, lo, hi = _cabi.TAILS_LINEAR, -float(settings.tail_bound), float(settings.tail_bound)
+    else:
+        tails, lo, hi = _cabi.TAILS_NONE, 0.0, 1.0
+    wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
+    cfg = _cabi.QuadSplineConfig(int(settings.num_bins), tails, int(bool(inverse)), lo, hi, lo, hi,
+                                 float(settings.min_bin_width), float(settings.min_bin_height), float(wh_scale))
+    return cfg, tails
+
+
 # ------------------------------------------------------------------------------------------------
 # piecewise-quadratic spline (flowcon/transforms/splines/quadratic.py)
 # ------------------------------------------------------------------------------------------------
@@ -209,6 +226,10 @@ class QuadraticSplineSettings:
 
     def params_per_feature(self):
         return self.num_bins * 2 - 1 if self.tails == "linear" else self.num_bins * 2 + 1
+
+    def config(self, inverse, hidden_for_scaling):
+        """(struct fc_quadspline_config, tails constant) of these settings."""
+        return _quad_config(self, inverse, hidden_for_scaling)
 
     def apply(self, inputs, params, tcols, ccols, inverse, hidden_for_scaling):
         if self.tails == "linear":
@@ -277,6 +298,10 @@ class CubicSplineSettings:
 
     def params_per_feature(self):
         return self.num_bins * 2 + 2
+
+    def config(self, inverse, hidden_for_scaling):
+        """(struct fc_quadspline_config, tails constant) of these settings (the cubic family shares the struct)."""
+        return _quad_config(self, inverse, hidden_for_scaling)
 
     def apply(self, inputs, params, tcols, ccols, inverse, hidden_for_scaling):
         if self.tails == "linear":

@@ -447,6 +447,22 @@ int64_t fc_made_inverse_smem_bytes(int32_t features, int32_t params_per_feature,
 int fc_made_inverse_rqs(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x, int64_t x_row_stride,
                         float* logabsdet, int32_t accumulate_logabsdet, int64_t B, const fc_rqs_config* cfg,
                         int32_t* status, void* stream);
+/* The other autoregressive layers through the same kernel: MaskedSumOfSigmoidsTransform (autoregressive.py:266-318, offset
+ * -0.5: numerical inverse as fc_sos_apply), MaskedPiecewiseLinear / Quadratic / CubicAutoregressiveTransform
+ * (autoregressive.py:321-523; arguments as fc_linspline_apply / fc_quadspline_apply / fc_cubicspline_apply with inverse = 1). */
+int fc_made_inverse_sos(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x, int64_t x_row_stride,
+                        float* logabsdet, int32_t accumulate_logabsdet, int64_t B, int32_t n_sigmoids, float offset,
+                        int32_t bisection_iterations, float lim, void* stream);
+int fc_made_inverse_linspline(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                              int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                              int32_t num_bins, int32_t tails, float left, float right, float bottom, float top,
+                              int32_t* status, void* stream);
+int fc_made_inverse_quadspline(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                               int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                               const fc_quadspline_config* cfg, int32_t* status, void* stream);
+int fc_made_inverse_cubicspline(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
+                                int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
+                                const fc_quadspline_config* cfg, int32_t* status, void* stream);
 /* interleaved (raw scale, shift) parameters, autoregressive.py:97-129 */
 int fc_made_inverse_affine(const fc_made_program* prog, const float* z, int64_t z_row_stride, float* x,
                            int64_t x_row_stride, float* logabsdet, int32_t accumulate_logabsdet, int64_t B,
