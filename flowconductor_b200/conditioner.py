@@ -15,7 +15,8 @@ from . import _cabi
 HIDDEN_WIDTHS = (128, 256)  # what the kernel runs; narrower nets are zero-padded to 128 at pack time (exact: the padding
                             # units are relu(0) = 0 and multiply zero weights)
 MAX_K_IN = 256
-RQS_PPAD = {8: 24, 16: 48}
+RQS_PPAD = {8: 24, 16: 48}  # linear tails (kept for callers of the first fused shapes)
+RQS_BINS = (8, 10, 16)      # bin counts with a register-resident instantiation of the fused kernel
 SOS_PPAD = 48               # 3 n + 1 = 31 parameters per feature for n = 10, two features per 96-column tile
 SOS_SIGMOIDS = (10,)
 MAX_BLOCKS = (_cabi.COND_MAX_LAYERS - 2) // 2
@@ -69,9 +70,17 @@ def padded_hidden(hidden):
     return 128 if hidden <= 128 else (256 if hidden <= 256 else None)
 
 
-def supported_shape(hidden, k_in, num_blocks, num_bins):
+def rqs_ppad(num_bins, tails):
+    """Accumulator columns per feature of the final layer's tiles for a spline with these bins / tails, or None."""
+    P = 3 * num_bins - 1 if tails == "linear" else 3 * num_bins + 1
+    if num_bins not in RQS_BINS or P > 48:
+        return None
+    return 24 if P <= 24 else 48
+
+
+def supported_shape(hidden, k_in, num_blocks, num_bins, tails="linear"):
     return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
-            and 1 <= num_blocks <= MAX_BLOCKS and num_bins in RQS_PPAD)
+            and 1 <= num_blocks <= MAX_BLOCKS and rqs_ppad(num_bins, tails) is not None)
 
 
 def supported_sos_shape(hidden, k_in, num_blocks, n_sigmoids):
@@ -135,11 +144,13 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
     return PackedConditioner(blob, vectors, st, hidden, k_in, n_final_tiles, num_bins)
 
 
-def pack_rqs(net, num_bins, d_t, col_map=None, k_in=None):
-    """`pack` for `fc_conditioner_rqs_apply` (linear tails: 3 K - 1 parameters per feature)."""
-    if num_bins not in RQS_PPAD:
+def pack_rqs(net, num_bins, d_t, col_map=None, k_in=None, tails="linear"):
+    """`pack` for `fc_conditioner_rqs_apply` (3 K - 1 parameters per feature with linear tails, 3 K + 1 without)."""
+    ppad = rqs_ppad(num_bins, tails)
+    if ppad is None:
         raise ValueError("conditioner shape not supported by the fused kernel")
-    return pack(net, 3 * num_bins - 1, RQS_PPAD[num_bins], d_t, col_map=col_map, k_in=k_in, num_bins=num_bins)
+    P = 3 * num_bins - 1 if tails == "linear" else 3 * num_bins + 1
+    return pack(net, P, ppad, d_t, col_map=col_map, k_in=k_in, num_bins=num_bins)
 
 
 def pack_sos(net, n_sigmoids, d_t, col_map=None, k_in=None):

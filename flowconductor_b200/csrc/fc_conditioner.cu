@@ -110,7 +110,11 @@ struct CondRqs {  // rational-quadratic spline, KC bins, linear tails (rational_
   template <int PPAD>
   static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
                                               unsigned& status) {
-    rqs_eval<KC, true>(a.c, x, p, y, lad, status);
+    // raw derivative entries behind the 2 KC width / height parameters: KC - 1 with linear tails, KC + 1 without (an
+    // instantiation whose PPAD leaves room for KC - 1 only is launched for linear tails only)
+    constexpr int NPD = PPAD - 2 * KC >= KC + 1 ? KC + 1 : KC - 1;
+    static_assert(PPAD - 2 * KC >= KC - 1, "parameters per feature");
+    rqs_eval<KC, true, NPD>(a.c, x, p, y, lad, status);
   }
 };
 template <int NC>
@@ -1123,20 +1127,22 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
   RqsParams c;
   int rc = make_rqs_params(cfg, c);
   if (rc != FC_OK) return rc;
-  if (c.tails != FC_TAILS_LINEAR || (c.K != 8 && c.K != 16)) return FC_ERR_UNSUPPORTED;
+  // bins with a register-resident instantiation; P = 3K - 1 (linear tails) or 3K + 1 parameters in 24 or 48 columns
+  if ((c.K != 8 && c.K != 10 && c.K != 16) || c.P > 48) return FC_ERR_UNSUPPORTED;
+  const int ppad = c.P <= 24 ? 24 : 48;
   CondArgs args{};
   rc = cond_build_args(net, a, lda, B, x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, D_t, tcols, ccols,
-                       c.K == 8 ? 24 : 48, 0, status, args);
+                       ppad, 0, status, args);
   if (rc != FC_OK) return rc;
   if (B == 0) return FC_OK;
   args.c = c;
   cudaStream_t st = (cudaStream_t)stream;
-  if (net->hidden == 256) {
-    if (c.K == 8) return launch_conditioner<CondRqs<8>, 24, 2>(args, st);
-    return launch_conditioner<CondRqs<16>, 48, 2>(args, st);
-  }
-  if (c.K == 8) return launch_conditioner<CondRqs<8>, 24, 1>(args, st);
-  return launch_conditioner<CondRqs<16>, 48, 1>(args, st);
+  const bool wide = net->hidden == 256;
+#define FC_COND_LAUNCH(KC, PP) (wide ? launch_conditioner<CondRqs<KC>, PP, 2>(args, st) : launch_conditioner<CondRqs<KC>, PP, 1>(args, st))
+  if (c.K == 8) return ppad == 24 ? FC_COND_LAUNCH(8, 24) : FC_COND_LAUNCH(8, 48);
+  if (c.K == 10) return FC_COND_LAUNCH(10, 48);
+  return FC_COND_LAUNCH(16, 48);
+#undef FC_COND_LAUNCH
 }
 
 extern "C" int fc_conditioner_sos_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,

@@ -17,7 +17,7 @@ struct MadeRqsOp {
     } else {
       for (int i = 0; i < c.P; ++i) p[i] = pc[i * kMR];
     }
-    rqs_eval<KC, (KC != 0)>(c, z, p, x, lad, status);
+    rqs_eval<KC, (KC != 0), (KC > 1 ? KC + 1 : 1)>(c, z, p, x, lad, status);
   }
 };
 

@@ -203,16 +203,19 @@ FC_HD float knot_derivative(const RqsParams& c, int K, const float* pd, int j) {
   return padded ? c.pad_deriv : d;
 }
 
-// Register-resident variant for the fused GEMM epilogue (linear tails only): `pd` is a register array, so the
-// raw derivative is picked with a select chain over compile-time indices instead of a dynamic index (which would
-// push the array to local memory).  Same arithmetic as knot_derivative.
-template <int KC>
+// Register-resident variant for the fused kernels: `pd` is a register array, so the raw derivative is picked with a
+// select chain over compile-time indices instead of a dynamic index (which would push the array to local memory).  Same
+// arithmetic as knot_derivative: K - 1 raw derivatives with linear tails (padded boundary knots), K + 1 without.
+// NPD: entries of `pd` the caller's array really has (KC - 1: linear tails only; KC + 1: both).
+template <int KC, int NPD>
 FC_HD float knot_derivative_regs(const RqsParams& c, const float* pd, int j) {
-  const bool padded = (j == 0 || j == KC);
-  const int idx = padded ? 0 : j - 1;
+  static_assert(NPD >= KC - 1 && NPD <= KC + 1, "raw derivatives per feature");
+  const bool lin = NPD < KC + 1 || c.tails == FC_TAILS_LINEAR;
+  const bool padded = lin && (j == 0 || j == KC);
+  const int idx = padded ? 0 : (lin ? j - 1 : j);
   float raw = pd[0];
 #pragma unroll
-  for (int i = 1; i < KC - 1; ++i) raw = (i == idx) ? pd[i] : raw;
+  for (int i = 1; i < NPD; ++i) raw = (i == idx) ? pd[i] : raw;
   const float d = c.min_d + softplus_beta(raw, c.beta, c.inv_beta);
   return padded ? c.pad_deriv : d;
 }
@@ -299,7 +302,7 @@ struct RqsBin {
 
 // Shared front half of forward / inverse / backward: inside test, softmax, knots, bin, derivatives.
 // ew / eh receive the softmax numerators (needed again by the backward); inv_w / inv_h their 1/sum.
-template <int KC, bool kRegs = false>
+template <int KC, bool kRegs = false, int NPD = (KC > 1 ? KC - 1 : 1)>
 FC_HD void rqs_locate(const RqsParams& c, int K, float x, const float* p, RqsBin& bin, float* ew, float* eh,
                       float& inv_w, float& inv_h) {
   const float sum_w = softmax_numerators<KC>(p, K, c.wh_scale_l2e, ew);
@@ -325,8 +328,8 @@ FC_HD void rqs_locate(const RqsParams& c, int K, float x, const float* p, RqsBin
   bin.delta = bin.h * bin.inv_w;
   const float* pd = p + 2 * K;
   if (kRegs && KC > 1) {
-    bin.d0 = knot_derivative_regs<(KC > 1 ? KC : 2)>(c, pd, bin.k);
-    bin.d1 = knot_derivative_regs<(KC > 1 ? KC : 2)>(c, pd, bin.k + 1);
+    bin.d0 = knot_derivative_regs<(KC > 1 ? KC : 2), (KC > 1 ? NPD : 1)>(c, pd, bin.k);
+    bin.d1 = knot_derivative_regs<(KC > 1 ? KC : 2), (KC > 1 ? NPD : 1)>(c, pd, bin.k + 1);
   } else {
     bin.d0 = knot_derivative(c, K, pd, bin.k);
     bin.d1 = knot_derivative(c, K, pd, bin.k + 1);
@@ -394,7 +397,9 @@ FC_HD float rqs_logdet_at(const RqsBin& b, float theta, float& inv_den) {
 // One element, forward or inverse (c.inverse).  p -> this feature's P raw parameters.
 // Branch-free over the tails: outside elements evaluate the spline on a clamped input and are then replaced
 // by the identity (rational_quadratic.py:38-39), so a warp never diverges on the inside test.
-template <int KC, bool kRegs = false>
+// NPD (register-resident arrays only): raw derivative entries the array holds — KC - 1 restricts the instantiation to
+// linear tails, KC + 1 serves both.
+template <int KC, bool kRegs = false, int NPD = (KC > 1 ? KC - 1 : 1)>
 FC_HD void rqs_eval(const RqsParams& c, float x, const float* p, float& y, float& lad, unsigned& status) {
   const int K = KC ? KC : c.K;
   float xs;
@@ -402,7 +407,7 @@ FC_HD void rqs_eval(const RqsParams& c, float x, const float* p, float& y, float
   float ew[KC ? KC : FC_MAX_BINS_GENERIC], eh[KC ? KC : FC_MAX_BINS_GENERIC];
   float inv_w, inv_h;
   RqsBin b;
-  rqs_locate<KC, kRegs>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
+  rqs_locate<KC, kRegs, NPD>(c, K, xs, p, b, ew, eh, inv_w, inv_h);
   float inv_den, ys, ls;
   if (c.inverse) {
     const float root = rqs_inverse_root(b, xs, status);

@@ -248,21 +248,26 @@ def affine_layer(net, a, inputs, tcols, ccols, layout, activation, inverse, col_
     return y, lad
 
 
-def rqs_fusable(spline, final_out_features, d_t):
-    return (ENABLED and spline.tails == "linear" and spline.num_bins in fl.RQS_PPAD
-            and final_out_features == d_t * (3 * spline.num_bins - 1))
+def rqs_fusable(spline, final_out_features, d_t, net=None, k_in=None):
+    """Can the bijection run inside a tensor-core kernel?  Either in the final layer's epilogue (fc_linear_rqs_apply: linear
+    tails, 8 or 16 bins) or — `net` / `k_in` given — inside the fused conditioner (more bin counts, also without tails)."""
+    if not ENABLED or final_out_features != d_t * spline.params_per_feature():
+        return False
+    if spline.tails == "linear" and spline.num_bins in fl.RQS_PPAD:
+        return True
+    return net is not None and conditioner_fusable(net, k_in, spline)
 
 
 FUSED_CONDITIONER = True  # whole conditioner + spline as ONE persistent kernel (csrc/fc_conditioner.cu) where it applies
 
 
-def cond_plan_for(net, col_map, k_in, num_bins, d_t):
+def cond_plan_for(net, col_map, k_in, num_bins, d_t, tails="linear"):
     """PackedConditioner of `net`, cached on the module like the per-layer plans (same key rules)."""
-    key = (_param_key(net), num_bins, k_in, d_t)
+    key = (_param_key(net), num_bins, tails, k_in, d_t)
     plan = getattr(net, "_fc_cond_plan", None)
     if plan is not None and plan[0] == key:
         return plan[1]
-    packed = fcond.pack_rqs(net, num_bins, d_t, col_map=col_map, k_in=k_in)
+    packed = fcond.pack_rqs(net, num_bins, d_t, col_map=col_map, k_in=k_in, tails=tails)
     object.__setattr__(net, "_fc_cond_plan", (key, packed))
     _generation[0] += 1
     return packed
@@ -298,8 +303,11 @@ def sos_layer(net, a, inputs, n_sigmoids, offset):
     return y, lad
 
 
-def conditioner_fusable(net, k_in, num_bins):
-    return FUSED_CONDITIONER and fcond.supported_shape(net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins)
+def conditioner_fusable(net, k_in, spline):
+    """`spline`: RationalQuadraticSettings (or a bin count, meaning linear tails)."""
+    num_bins, tails = (spline, "linear") if isinstance(spline, int) else (int(spline.num_bins), spline.tails)
+    return FUSED_CONDITIONER and k_in is not None and fcond.supported_shape(
+        net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins, tails)
 
 
 def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None,
@@ -307,16 +315,20 @@ def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling,
     """Conditioner + spline for one layer; returns (outputs, logabsdet)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
     k_in = k_in if k_in is not None else a.shape[1]
-    tb = float(spline.tail_bound)
-    wh_scale = 1.0 / math.sqrt(hidden_for_scaling) if hidden_for_scaling else 1.0
-    cfg = _cabi.RqsConfig(int(spline.num_bins), _cabi.TAILS_LINEAR, int(bool(spline.identity_init)), int(bool(inverse)),
-                          -tb, tb, -tb, tb, float(spline.min_bin_width), float(spline.min_bin_height),
-                          float(spline.min_derivative), wh_scale)
-    if conditioner_fusable(net, k_in, int(spline.num_bins)):
-        packed = cond_plan_for(net, col_map, k_in, int(spline.num_bins), d_t)
+    cfg, tails = spline.config(inverse, hidden_for_scaling)
+    if conditioner_fusable(net, k_in, spline):
+        from ..transforms import splines as fsplines
+
+        packed = cond_plan_for(net, col_map, k_in, int(spline.num_bins), d_t, spline.tails)
         x, y = _output_buffer(inputs, allow_inplace)
         lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
-        fcond.rqs_apply(packed, a, x, y, lad, False, d_t, tcols, ccols, cfg, None)
+        # without tails the reference raises InputOutsideDomain after a host-side check (rational_quadratic.py:81-82): the
+        # kernel reports through the status word instead
+        status = torch.zeros((1,), dtype=torch.int32, device=x.device) if (tails == _cabi.TAILS_NONE or fsplines.STRICT) \
+            else None
+        fcond.rqs_apply(packed, a, x, y, lad, False, d_t, tcols, ccols, cfg, status)
+        if status is not None:
+            fsplines.check_status(status, tails)
         return y, lad
     plan = plan_for(net, col_map, k_in, ("rqs", spline.num_bins))
     h = hidden(net, plan, a)

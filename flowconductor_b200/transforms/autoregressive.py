@@ -191,7 +191,7 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
 
     def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
         net = self.autoregressive_net
-        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1]):
+        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1], net, inputs.shape[1]):
             return super()._tensorcore_layer(conditioner_inputs, inputs, inverse)
         return tensorcore.rqs_layer(net, conditioner_inputs, inputs, self._spline, None, None, inverse,
                                     getattr(net, "hidden_features", None),

@@ -100,7 +100,7 @@ class ConditionalPiecewiseRationalQuadraticTransform(ConditionalTransform):
 
     def _tensorcore_layer(self, inputs, context, inverse):
         net = self.conditional_net
-        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1]):
+        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], inputs.shape[1], net, context.shape[1]):
             return super()._tensorcore_layer(inputs, context, inverse)
         return tensorcore.rqs_layer(net, context, inputs, self._spline, None, None, inverse,
                                     getattr(net, "hidden_features", None))

@@ -198,7 +198,8 @@ class PiecewiseRationalQuadraticCouplingTransform(CouplingTransform):
 
     def _tensorcore_layer(self, inputs, inverse):
         net = self.transform_net
-        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], self.num_transform_features):
+        if not tensorcore.rqs_fusable(self._spline, net.final_layer.weight.shape[0], self.num_transform_features, net,
+                                      self.features):
             return super()._tensorcore_layer(inputs, inverse)
         # final layer + spline in one kernel: the [B, D_t*P] parameter tensor never reaches HBM
         return tensorcore.rqs_layer(net, inputs, inputs, self._spline, self._tcols, self._ccols, inverse,

@@ -335,7 +335,9 @@ int fc_linear_debug_profile(unsigned long long* out16);
  * ([n_pad] floats) and winv (2 floats: [0] = the exact power of two that undoes the layer's fp16 weight scaling, [1]
  * scratch).
  * Supported: hidden width 128 or 256, input width k_in <= 256 (a multiple of 4), at most FC_COND_MAX_LAYERS layers,
- * linear tails with 8 or 16 bins; everything else FC_ERR_UNSUPPORTED (run the per-layer fc_linear_* kernels).
+ * 8, 10 or 16 bins with at most 48 parameters per feature (linear tails: all three; no tails: 8 and 10 bins) — the final layer
+ * is packed with 24 accumulator columns per feature when P <= 24, else 48; everything else FC_ERR_UNSUPPORTED (run the
+ * per-layer fc_linear_* kernels).
  */
 #define FC_COND_MAX_LAYERS 10
 #define FC_COND_INITIAL 0      /* h = W a + b */

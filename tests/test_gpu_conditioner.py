@@ -152,12 +152,12 @@ def test_conditioner_argument_errors(dev):
     net = _random_net("resnet", 32, 64, 32 * 23, 2, dev, seed=0)  # narrow nets are zero-padded to the kernel's 128
     assert fcond.pack_rqs(net, 8, 32).hidden == 128
     with pytest.raises(ValueError):
-        fcond.pack_rqs(net, 10, 32)  # 10 bins: not a fused shape
+        fcond.pack_rqs(net, 5, 32)  # 5 bins: not a fused shape
     net = _random_net("resnet", 32, 256, 32 * 23, 2, dev, seed=0)
     packed = fcond.pack_rqs(net, 8, 32, k_in=32)
     x = torch.randn(10, 32, device=dev)
     cfg = _cabi.RqsConfig(8, _cabi.TAILS_NONE, 0, 0, 0.0, 1.0, 0.0, 1.0, 1e-3, 1e-3, 1e-3, 1.0)
-    with pytest.raises(RuntimeError, match="unsupported"):  # tails=None is not fused
+    with pytest.raises(RuntimeError, match="invalid argument"):  # packed for 23 parameters per feature, called with 25
         fcond.rqs_apply(packed, x, x, torch.empty_like(x), torch.empty(10, device=dev), False, 32, None, None, cfg)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         fcond.rqs_apply(packed, x.cpu(), x, torch.empty_like(x), torch.empty(10, device=dev), False, 32, None, None, cfg)
@@ -307,6 +307,39 @@ def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypa
         b = flow.log_prob(x)
     rel = (a - b).abs() / b.abs().clamp_min(1.0)
     assert rel.max() < 1e-4, float(rel.max())
+
+
+@pytest.mark.parametrize("bins,tails,hidden", [(10, "linear", 128), (8, None, 64), (10, None, 256), (16, "linear", 64)])
+def test_fused_conditioner_other_bin_counts_and_no_tails(dev, bins, tails, hidden, monkeypatch):
+    """The reference's default bin count (10) and splines without tails (domain [0, 1] for couplings, InputOutsideDomain
+    beyond it: coupling.py:566-567, rational_quadratic.py:81-82) inside the fused conditioner: against the unfused path
+    (torch conditioner + element-wise kernel) and, for the domain error, the reference's exception."""
+    from flowconductor_b200.transforms.base import InputOutsideDomain
+
+    torch.manual_seed(bins * 7 + hidden)
+    mask = workloads.make_mask(12, "alternating_even")
+    layer = transforms.PiecewiseRationalQuadraticCouplingTransform(
+        mask, lambda i, o: ResidualNet(i, o, hidden_features=hidden, num_blocks=2), num_bins=bins, tails=tails,
+        tail_bound=2.0).to(dev).eval()
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+        x = torch.randn(3000, 12, device=dev) if tails == "linear" else torch.rand(3000, 12, device=dev)
+        for inverse in (False, True):
+            fn = layer.inverse if inverse else layer
+            _cabi.STATS.reset()
+            y, lad = fn(x)
+            assert _cabi.STATS.counts.get("fc_conditioner_rqs_apply", 0) == 1, _cabi.STATS.counts
+            monkeypatch.setattr(tensorcore, "ENABLED", False)
+            yu, ladu = fn(x)
+            monkeypatch.setattr(tensorcore, "ENABLED", True)
+            assert ((y - yu).abs() / yu.abs().clamp_min(1.0)).max() < 2e-4, (bins, tails, inverse)
+            assert torch.quantile((lad - ladu).abs(), 0.99) < 2e-3 and (lad - ladu).abs().max() < 5e-2
+        if tails is None:
+            bad = x.clone()
+            bad[17, 0] = 1.5  # a transformed column outside the unit box
+            with pytest.raises(InputOutsideDomain):
+                layer(bad)
 
 
 def test_shared_cdf_parameters_are_not_materialised(dev):
