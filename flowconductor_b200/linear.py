@@ -92,7 +92,12 @@ class T128:
         if width % 16 != 0:
             raise ValueError("T128 needs a width that is a multiple of 16")
         self.rows, self.width = rows, width
+        # The staged kernels work on CTA PAIRS (cta_group::2): one unit = 256 rows = two tiles, and the pair stores (and
+        # loads) both tiles of its last unit even when the second one lies beyond `rows`.  The buffer therefore always holds
+        # an EVEN number of tiles; with ceil(rows / 128) tiles an odd tile count made the kernel write one tile past the
+        # end (found by scripts/fuzz_made_inverse.py: a neighbouring mask buffer was overwritten).
         tiles = (rows + self.TILE - 1) // self.TILE
+        tiles += tiles & 1
         self.buf = torch.empty((tiles * self.TILE * width,), dtype=torch.float32, device=device)
 
     @staticmethod

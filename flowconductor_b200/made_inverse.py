@@ -93,10 +93,15 @@ def supported_made(net):
 
 
 def _split_even(n, parts):
-    """n outputs -> at most `parts` consecutive slices whose widths are multiples of 4 (the last one may be ragged)."""
+    """n outputs -> consecutive slices whose widths are multiples of 4 (the last one may be ragged) and at most MAX_NJ: `parts`
+    of them when that is enough, more otherwise (the caller spreads more than TASKS slices over several phases)."""
     n4 = (n + 3) // 4
-    parts = max(1, min(parts, n4))
-    base, extra = divmod(n4, parts)
+    parts = max(1, min(parts, n4), (n + MAX_NJ - 1) // MAX_NJ)
+    while True:
+        base, extra = divmod(n4, parts)
+        if 4 * (base + (1 if extra else 0)) <= MAX_NJ:
+            break
+        parts += 1
     out, j = [], 0
     for i in range(parts):
         w = 4 * (base + (1 if i < extra else 0))

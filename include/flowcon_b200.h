@@ -236,8 +236,9 @@ int fc_linear_pack(const float* W, int64_t w_row_stride, const float* mask, int6
  * `layouts` (FC_LINEAR_A_T128 | FC_LINEAR_OUT_T128): activations between the conditioner's own layers are kept in the
  * "T128" layout instead of row-major: 128-row tiles, and inside a tile the 16-byte column groups are the slow index,
  *     element (r, c) of a [M, W] matrix  ->  float offset  (r/128)*128*W + ((c/4)*128 + r%128)*4 + c%4,
- * W a multiple of 16, buffer size ceil(M/128)*128*W floats (tail rows of the last tile are written, never read
- * back as results).  One epilogue thread owns one row, so with T128 the 32 threads of a warp store (and re-read as
+ * W a multiple of 16, buffer size T*128*W floats with T = ceil(M/128) ROUNDED UP TO AN EVEN NUMBER: the kernels work on
+ * CTA pairs (256 rows = two tiles) and a pair stores / loads both tiles of its last unit (tail rows and the tail tile are
+ * written, never read back as results).  One epilogue thread owns one row, so with T128 the 32 threads of a warp store (and re-read as
  * the skip connection) 512 contiguous bytes per instruction instead of 32 scattered 16-byte pieces, and the next
  * layer's TMA box of BK k-values is BK/4 contiguous 2 KB runs.  For a T128 operand its stride argument (lda / ldo /
  * ldr) is W.  The residual always has the layout of `out`.

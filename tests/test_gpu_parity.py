@@ -992,3 +992,35 @@ def test_quadratic_spline_wide_layer_round_trip(dev):
         ref_y, ref_lad = restated.quadratic_cdf(st, "", x.cpu().double(), 8, "linear", 3.0, False)
     assert (y.cpu().double() - ref_y).abs().max() < 2e-5 and (lad.cpu().double() - ref_lad).abs().max() < 5e-4
     assert (xi - x).abs().max() < 5e-4 and (lad + ladi).abs().max() < 5e-3
+
+
+def test_linear_kernels_stay_inside_their_buffers(dev):
+    """Guard bands around every output of fc_linear_apply (row-major and T128, ragged and odd tile counts): nothing outside
+    the buffer may change.  (Round 2: a T128 output with an odd number of 128-row tiles was written one tile past its end;
+    the T128 container now holds an even number of tiles.)"""
+    sent, guard = 12345.0, 1 << 16
+    torch.manual_seed(0)
+    for M in (1, 32, 129, 300, 641):
+        for K, N in ((256, 256), (256, 384), (64, 64)):
+            W = torch.randn(N, K, device=dev) * 0.1
+            b = torch.randn(N, device=dev)
+            packed = fl.pack(W, b)
+            a_rows = torch.randn(M, K, device=dev)
+            ref = a_rows @ W.t() + b
+            for a_t, o_t in ((False, False), (False, True), (True, True), (True, False)):
+                a = fl.T128.from_rows(a_rows) if a_t else a_rows
+                if o_t:
+                    out = fl.T128(M, N, dev)
+                    n = out.buf.numel()
+                    big = torch.full((n + 2 * guard,), sent, device=dev)
+                    out.buf = big[guard:guard + n]
+                else:
+                    n = M * N
+                    big = torch.full((n + 2 * guard,), sent, device=dev)
+                    out = big[guard:guard + n].view(M, N)
+                got = fl.linear(a, packed, out=out, out_t128=o_t, n_out=N)
+                torch.cuda.synchronize()
+                tag = "M=%d K=%d N=%d a_t128=%s out_t128=%s" % (M, K, N, a_t, o_t)
+                assert bool((big[:guard] == sent).all()) and bool((big[guard + n:] == sent).all()), "out-of-bounds write: " + tag
+                g = got.to_rows() if o_t else got
+                assert (g - ref).abs().max() < 1e-3, tag

@@ -53,6 +53,32 @@ def test_program_reproduces_d_pass_inverse(name):
         assert (lad - lad_ref).abs().max() < 1e-9
 
 
+@pytest.mark.parametrize("features,hidden,blocks", [(2, 256, 2), (1, 32, 1), (3, 100, 2), (5, 7, 1), (48, 64, 3), (7, 200, 1)])
+def test_program_shapes(features, hidden, blocks):
+    """Shapes with very large degree groups (2 features: every hidden unit has degree 1), a single feature, more features
+    than hidden units: the compiled program obeys the kernel's limits (checked by the emulator) and reproduces the oracle."""
+    torch.manual_seed(features * 1000 + hidden)
+    net = made_module.MADE(features=features, hidden_features=hidden, num_blocks=blocks, output_multiplier=2)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+    prog = made_inverse.compile_made(net, 2)
+    assert prog is not None
+    for _, hdr, tasks in prog.tasks():
+        assert 1 <= len(tasks) <= made_inverse.TASKS and all(1 <= t["nj"] <= made_inverse.MAX_NJ for t in tasks)
+    state = {"autoregressive_net." + k: v.double() for k, v in net.state_dict().items()}
+    spec = {"kind": "maf_affine", "prefix": "", "num_blocks": blocks, "hidden_features": hidden}
+    z = torch.randn(9, features, dtype=torch.float64)
+
+    def invert(zf, params):
+        y, lad = restated.affine_elementwise(zf[:, None], params, "interleaved", "softplus_eps", True)
+        return y[:, 0], lad
+
+    x, lad = emulate_made_program(prog, z, invert)
+    x_ref, lad_ref = restated.apply_layer(state, spec, z, inverse=True)
+    assert (x - x_ref).abs().max() < 1e-9 and (lad - lad_ref).abs().max() < 1e-9
+
+
 def test_program_structure_cfg3():
     """cfg 3 (D=16, H=256, 2 blocks, P=47): per pass one wide phase + 4 chain phases + the feature's chain phase."""
     wl = workloads.get_workload("cfg3")
