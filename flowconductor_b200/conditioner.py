@@ -78,14 +78,28 @@ def rqs_ppad(num_bins, tails):
     return 24 if P <= 24 else 48
 
 
-def supported_shape(hidden, k_in, num_blocks, num_bins, tails="linear"):
-    return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
-            and 1 <= num_blocks <= MAX_BLOCKS and rqs_ppad(num_bins, tails) is not None)
+VEC_BYTES = 20480  # kVecBytes of the kernel: the bias of every output column of every layer is staged in shared memory
 
 
-def supported_sos_shape(hidden, k_in, num_blocks, n_sigmoids):
+def _vectors_fit(hidden, num_blocks, ppad, d_t):
+    """The kernel keeps every layer's bias in shared memory: (1 + 2 blocks) hidden-wide layers + the final layer's tiles."""
+    if d_t is None:
+        return True
+    feats = 96 // ppad
+    total_cols = (1 + 2 * num_blocks) * padded_hidden(hidden) + (d_t + feats - 1) // feats * 96
+    return total_cols * 4 + 4 * _cabi.COND_MAX_LAYERS <= VEC_BYTES
+
+
+def supported_shape(hidden, k_in, num_blocks, num_bins, tails="linear", d_t=None):
+    ppad = rqs_ppad(num_bins, tails)
     return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
-            and 1 <= num_blocks <= MAX_BLOCKS and n_sigmoids in SOS_SIGMOIDS)
+            and 1 <= num_blocks <= MAX_BLOCKS and ppad is not None and _vectors_fit(hidden, num_blocks, ppad, d_t))
+
+
+def supported_sos_shape(hidden, k_in, num_blocks, n_sigmoids, d_t=None):
+    return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
+            and 1 <= num_blocks <= MAX_BLOCKS and n_sigmoids in SOS_SIGMOIDS
+            and _vectors_fit(hidden, num_blocks, SOS_PPAD, d_t))
 
 
 def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):

@@ -255,7 +255,7 @@ def rqs_fusable(spline, final_out_features, d_t, net=None, k_in=None):
         return False
     if spline.tails == "linear" and spline.num_bins in fl.RQS_PPAD:
         return True
-    return net is not None and conditioner_fusable(net, k_in, spline)
+    return net is not None and conditioner_fusable(net, k_in, spline, d_t)
 
 
 FUSED_CONDITIONER = True  # whole conditioner + spline as ONE persistent kernel (csrc/fc_conditioner.cu) where it applies
@@ -285,9 +285,9 @@ def sos_cond_plan_for(net, k_in, n_sigmoids, d_t):
     return packed
 
 
-def sos_fusable(net, k_in, n_sigmoids):
+def sos_fusable(net, k_in, n_sigmoids, d_t=None):
     return FUSED_CONDITIONER and fcond.supported_sos_shape(net.initial_layer.weight.shape[0], k_in, len(net.blocks),
-                                                           n_sigmoids)
+                                                           n_sigmoids, d_t)
 
 
 def sos_layer(net, a, inputs, n_sigmoids, offset):
@@ -303,11 +303,12 @@ def sos_layer(net, a, inputs, n_sigmoids, offset):
     return y, lad
 
 
-def conditioner_fusable(net, k_in, spline):
-    """`spline`: RationalQuadraticSettings (or a bin count, meaning linear tails)."""
+def conditioner_fusable(net, k_in, spline, d_t=None):
+    """`spline`: RationalQuadraticSettings (or a bin count, meaning linear tails); d_t: transformed features (the final
+    layer's bias vector must fit in the kernel's shared memory)."""
     num_bins, tails = (spline, "linear") if isinstance(spline, int) else (int(spline.num_bins), spline.tails)
     return FUSED_CONDITIONER and k_in is not None and fcond.supported_shape(
-        net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins, tails)
+        net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins, tails, d_t)
 
 
 def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None,
@@ -316,7 +317,7 @@ def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling,
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
     k_in = k_in if k_in is not None else a.shape[1]
     cfg, tails = spline.config(inverse, hidden_for_scaling)
-    if conditioner_fusable(net, k_in, spline):
+    if conditioner_fusable(net, k_in, spline, d_t):
         from ..transforms import splines as fsplines
 
         packed = cond_plan_for(net, col_map, k_in, int(spline.num_bins), d_t, spline.tails)

@@ -137,7 +137,7 @@ class MaskedSumOfSigmoidsTransform(AutoregressiveTransform):
     def _tensorcore_layer(self, conditioner_inputs, inputs, inverse):
         net = self.autoregressive_net
         if (not inverse and conditioner_inputs is inputs
-                and tensorcore.sos_fusable(net, inputs.shape[1], self.n_sigmoids)):
+                and tensorcore.sos_fusable(net, inputs.shape[1], self.n_sigmoids, inputs.shape[1])):
             return tensorcore.sos_layer(net, inputs, inputs, self.n_sigmoids, -0.5)
         return super()._tensorcore_layer(conditioner_inputs, inputs, inverse)
 

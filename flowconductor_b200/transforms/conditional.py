@@ -126,7 +126,7 @@ class ConditionalSumOfSigmoidsTransform(ConditionalTransform):
     def _tensorcore_layer(self, inputs, context, inverse):
         net = self.conditional_net
         if (not inverse and net.final_layer.weight.shape[0] == inputs.shape[1] * self._output_dim_multiplier()
-                and tensorcore.sos_fusable(net, context.shape[1], self.n_sigmoids)):
+                and tensorcore.sos_fusable(net, context.shape[1], self.n_sigmoids, inputs.shape[1])):
             # ResidualNet on the context + sum of sigmoids in one kernel: the [B, D * 31] parameters never exist
             return tensorcore.sos_layer(net, context, inputs, self.n_sigmoids, 0.0)
         return super()._tensorcore_layer(inputs, context, inverse)
