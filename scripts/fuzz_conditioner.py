@@ -21,7 +21,7 @@ def main():
     n_cases = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     worst, ran, skipped = 0.0, 0, 0
     for case in range(n_cases):
-        fam = random.choice(["coupling", "coupling", "maf", "cond_rqs", "cond_sos"])
+        fam = random.choice(["coupling", "coupling", "maf", "cond_rqs", "cond_sos", "lin", "quad", "cubic", "affine", "maf_affine"])
         D = random.choice([4, 8, 12, 16, 32, 64, 100])
         H = random.choice([64, 68, 100, 128, 132, 200, 256])
         blocks = random.choice([1, 2, 3, 4])
@@ -45,6 +45,22 @@ def main():
                                                                               tail_bound=3.0, num_blocks=blocks)
             ctx = torch.randn(rows, 8, device=dev)
             box = (-1.2, 1.2)
+        elif fam in ("lin", "quad", "cubic", "affine"):
+            # the other coupling families: per-layer tensor-core kernels (T128 activations), element-wise or fused-affine end
+            mask = workloads.make_mask(D, random.choice(["alternating_even", "mid_split"]))
+            create = lambda i, o: ResidualNet(i, o, hidden_features=H, num_blocks=blocks)  # noqa: E731
+            tails, box = "linear", None
+            if fam == "lin":
+                layer = transforms.PiecewiseLinearCouplingTransform(mask, create, num_bins=K, tails="linear", tail_bound=3.0)
+            elif fam == "quad":
+                layer = transforms.PiecewiseQuadraticCouplingTransform(mask, create, num_bins=K, tails="linear", tail_bound=3.0)
+            elif fam == "cubic":
+                layer = transforms.PiecewiseCubicCouplingTransform(mask, create, num_bins=K, tails="linear", tail_bound=3.0)
+            else:
+                layer = transforms.AffineCouplingTransform(mask, create)
+        elif fam == "maf_affine":
+            layer = transforms.MaskedAffineAutoregressiveTransform(D, H, num_blocks=blocks)
+            tails, box = "linear", None
         else:
             layer = transforms.ConditionalSumOfSigmoidsTransform(D, H, context_features=8, n_sigmoids=10, num_blocks=blocks)
             ctx = torch.randn(rows, 8, device=dev)
@@ -58,12 +74,14 @@ def main():
             else:
                 x = torch.randn(rows, D, device=dev)
             res = {}
-            for inverse in ((False,) if fam == "cond_sos" else (False, True)):
+            for inverse in ((False,) if fam in ("cond_sos", "maf_affine", "maf") else (False, True)):
                 fn = layer.inverse if inverse else layer
                 _cabi.STATS.reset()
                 try:
                     y, lad = fn(x, ctx)
                     fused = any(k.startswith("fc_conditioner_") and k.endswith("_apply") for k in _cabi.STATS.counts)
+                    path = "fused" if fused else ("per-layer" if any(k.startswith("fc_linear_") for k in _cabi.STATS.counts)
+                                                  else "unfused")
                     tensorcore.ENABLED = False
                     yu, ladu = fn(x, ctx)
                 except Exception as e:  # noqa: BLE001
@@ -73,7 +91,7 @@ def main():
                     continue
                 finally:
                     tensorcore.ENABLED = True
-                if not fused:
+                if path == "unfused":
                     skipped += 1
                     continue
                 ran += 1
@@ -83,10 +101,10 @@ def main():
                 worst = max(worst, q)
                 bad = (q > 1e-4 or float(torch.quantile(el, 0.99)) > 1e-3 or not bool(torch.isfinite(y).all())
                        or float(ey.max()) > 5e-2)
-                print("case %2d %-9s D=%3d H=%3d blocks=%d K=%2d tails=%-6s rows=%4d inverse=%d: outputs p99.9 %.1e max %.1e, logabsdet p99 %.1e%s" % (
-                    case, fam, D, H, blocks, K, tails, rows, inverse, q, float(ey.max()), float(torch.quantile(el, 0.99)),
+                print("case %2d %-9s %-9s D=%3d H=%3d blocks=%d K=%2d tails=%-6s rows=%4d inverse=%d: outputs p99.9 %.1e max %.1e, logabsdet p99 %.1e%s" % (
+                    case, fam, path, D, H, blocks, K, tails, rows, inverse, q, float(ey.max()), float(torch.quantile(el, 0.99)),
                     "   <<<<<< MISMATCH" if bad else ""))
-    print("ran %d fused calls (not fused: %d), worst p99.9 relative output difference %.2e" % (ran, skipped, worst))
+    print("ran %d tensor-core calls (torch conditioner only: %d), worst p99.9 relative output difference %.2e" % (ran, skipped, worst))
 
 
 if __name__ == "__main__":
