@@ -998,6 +998,8 @@ def test_linear_kernels_stay_inside_their_buffers(dev):
     """Guard bands around every output of fc_linear_apply (row-major and T128, ragged and odd tile counts): nothing outside
     the buffer may change.  (Round 2: a T128 output with an odd number of 128-row tiles was written one tile past its end;
     the T128 container now holds an even number of tiles.)"""
+    from flowconductor_b200 import linear as fl
+
     sent, guard = 12345.0, 1 << 16
     torch.manual_seed(0)
     for M in (1, 32, 129, 300, 641):
