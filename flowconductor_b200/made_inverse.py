@@ -257,7 +257,7 @@ def compile_made(net, params_per_feature):
     return MadeProgram(phases_np, weights.contiguous(), bias, D, P, n_arrays, H, dev)
 
 
-def _io(prog, z, inplace_ok=False):
+def _io(prog, z):
     _cabi.require_cuda_f32(z, "inputs")
     if z.dim() != 2 or z.shape[1] != prog.features:
         raise ValueError("expected inputs of shape [B, {}]".format(prog.features))
@@ -265,29 +265,6 @@ def _io(prog, z, inplace_ok=False):
     x = torch.empty((z.shape[0], prog.features), dtype=torch.float32, device=z.device)
     lad = torch.empty((z.shape[0],), dtype=torch.float32, device=z.device)
     return z, zp, ldz, x, lad
-
-
-def apply_rqs(prog, z, cfg, status=None):
-    """Inverse of a MAF layer with rational-quadratic splines: (x, logabsdet) = layer.inverse(z)."""
-    L = _cabi.lib()
-    z, zp, ldz, x, lad = _io(prog, z)
-    with torch.cuda.device(z.device), _cabi.launch("fc_made_inverse_rqs", z.device):
-        rc = L.fc_made_inverse_rqs(ctypes.byref(prog.struct), zp, ldz, x.data_ptr(), x.stride(0), lad.data_ptr(), 0,
-                                   z.shape[0], ctypes.byref(cfg), status.data_ptr() if status is not None else None,
-                                   _cabi.stream_ptr(z.device))
-    _cabi.check(rc, "fc_made_inverse_rqs")
-    return x, lad
-
-
-def apply_affine(prog, z, activation):
-    """Inverse of a MaskedAffineAutoregressiveTransform layer."""
-    L = _cabi.lib()
-    z, zp, ldz, x, lad = _io(prog, z)
-    with torch.cuda.device(z.device), _cabi.launch("fc_made_inverse_affine", z.device):
-        rc = L.fc_made_inverse_affine(ctypes.byref(prog.struct), zp, ldz, x.data_ptr(), x.stride(0), lad.data_ptr(), 0,
-                                      z.shape[0], int(activation), _cabi.stream_ptr(z.device))
-    _cabi.check(rc, "fc_made_inverse_affine")
-    return x, lad
 
 
 def _apply(entry, prog, z, *tail):
@@ -303,6 +280,16 @@ def _apply(entry, prog, z, *tail):
 
 def _sptr(status):
     return status.data_ptr() if status is not None else None
+
+
+def apply_rqs(prog, z, cfg, status=None):
+    """Inverse of a MAF layer with rational-quadratic splines: (x, logabsdet) = layer.inverse(z)."""
+    return _apply("fc_made_inverse_rqs", prog, z, ctypes.byref(cfg), _sptr(status))
+
+
+def apply_affine(prog, z, activation):
+    """Inverse of a MaskedAffineAutoregressiveTransform layer."""
+    return _apply("fc_made_inverse_affine", prog, z, int(activation))
 
 
 def apply_sos(prog, z, n_sigmoids, offset, iterations, lim):
