@@ -22,6 +22,9 @@ ROWS = 32        # rows per CTA of the kernel
 SMEM_LIMIT = 232448  # opt-in shared memory per CTA on sm_100
 SLOT_FLOATS = 2048   # ring slot of the kernel
 RELU_IN, INIT_BIAS = 1, 2
+# tasks per narrow (dependent-chain) phase.  Measured on cfg 3 at 32 768 rows: 8 tasks 7.45 ms, 2 tasks 7.51 ms, 1 task (as
+# few as the 24-output limit allows) 7.92 ms — the chain is latency-bound, so the outputs are spread over all warps.
+CHAIN_PARTS = int(__import__("os").environ.get("FC_MADE_CHAIN_PARTS", str(TASKS)))
 PHASE_INTS = 4 + 12 * TASKS
 RECORD_FLOATS = 128  # FC_MADE_RECORD_FLOATS: the phase record (padded) in front of the phase's matrix
 TASK_FIELDS = ("in_array", "out_array", "k0", "kn", "j0", "nj", "c0", "flags", "res_array", "b_off", "reserved0", "reserved1")
@@ -246,9 +249,10 @@ def compile_made(net, params_per_feature):
             # ---- the dependent chain: one narrow phase per layer over the new units of the layer below
             for li in range(1, fl):
                 need = int(counts[li][lo:hi].max())
-                tasks = [(li, lo + j, nj, lo, max(need - lo, 0), lo == 0, True, 0) for j, nj in _split_even(hi - lo, TASKS)]
+                tasks = [(li, lo + j, nj, lo, max(need - lo, 0), lo == 0, True, 0)
+                         for j, nj in _split_even(hi - lo, CHAIN_PARTS)]
                 emit(tasks)
-            tasks = [(fl, f * P + j, nj, lo, hi - lo, lo == 0, False, f * P) for j, nj in _split_even(P, TASKS)]
+            tasks = [(fl, f * P + j, nj, lo, hi - lo, lo == 0, False, f * P) for j, nj in _split_even(P, CHAIN_PARTS)]
             emit(tasks, f)
             ready = hi
         phases_np = np.asarray(phases, dtype=np.int32).reshape(-1, PHASE_INTS)
