@@ -38,7 +38,7 @@ CPU_SAMPLE_ROWS = 262144      # cpu_baseline leg of the default run (~10-30 s of
 # --impl reference: rows per step.  The reference's CPU path runs at ~1.5-3 k samples/s per 8 cores: the
 # 1M-row step of our arm would take 5-10 minutes EACH, so the step is a bounded sample of the same workload (the
 # per-sample rate is flat in the batch size: 33.0 k/s at 262144 rows vs 34.1 k/s at 65536).
-REF_STEP_ROWS = {"cfg2": 65536, "cfg5": 16384, "cfg3_train": 8192}
+REF_STEP_ROWS = {"cfg2": 65536, "cfg4": 16384, "cfg5": 16384, "cfg3_train": 8192}
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 FALLBACK_BF16_TFLOPS = 1400.0  # sustained dense bf16 (same guide)
 
@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=WORKLOAD, choices=["cfg2", "cfg5", "cfg3_train"])
+    ap.add_argument("--workload", default=WORKLOAD, choices=["cfg2", "cfg4", "cfg5", "cfg3_train"])
     ap.add_argument("--batch", type=int, default=None, help="cfg2: rows per GPU (default: the workload's batch)")
     ap.add_argument("--rows", type=int, default=None, help="cfg5 / cfg3_train: GLOBAL rows per step (default 100M / 262144)")
     ap.add_argument("--graph", action="store_true", help="cfg3_train: replay the whole step from one CUDA graph")
@@ -185,12 +185,14 @@ def cpu_log_prob_rate(wl, state, rows, repeats=1, warmup=0):
 
     torch.set_num_threads(os.cpu_count() or 1)
     x = torch.randn(rows, wl["features"], generator=torch.Generator().manual_seed(1234))
+    ctx = wl.get("context_features")
+    c = torch.randn(rows, ctx, generator=torch.Generator().manual_seed(4321)) if ctx else None
     ref = reference_flow(wl, state)
     if ref is not None:
         kind = "reference"
 
         def run():
-            ref.log_prob(x)
+            ref.log_prob(x, context=c)
     else:
         from oracle import restated
 
@@ -198,7 +200,7 @@ def cpu_log_prob_rate(wl, state, rows, repeats=1, warmup=0):
         specs = workloads.oracle_specs(wl)
 
         def run():
-            restated.flow_log_prob(state, specs, x)
+            restated.flow_log_prob(state, specs, x, c)
     times = []
     with torch.no_grad():
         for i in range(warmup + repeats):
@@ -281,7 +283,13 @@ def run_reference(args, wl):
 def config_dict(args, wl, rows_per_gpu, n_gpus):
     first = [l for l in wl["layers"] if l["kind"] != "permutation"][0]
     n_layers = len([l for l in wl["layers"] if l["kind"] != "permutation"])
-    if args.workload == "cfg3_train":
+    if args.workload == "cfg4":
+        what = ("{}: ConditionalSumOfSigmoidsTransform flow log_prob (hypernetwork ResidualNet on the context), D={}, "
+                "context={}, n_sigmoids={}, {} layers, H={}".format(wl["name"], wl["features"], wl["context_features"],
+                                                                     first.get("n_sigmoids"), n_layers,
+                                                                     first.get("hidden_features")))
+        l2 = "a step touches x + context + outputs only (42 MB at 262144 rows): L2 is flushed between timed steps"
+    elif args.workload == "cfg3_train":
         what = ("{}: MaskedPiecewiseRationalQuadraticAutoregressiveTransform (MAF-RQS) training step (zero_grad, "
                 "-log_prob.mean, backward, gradient all-reduce, Adam), D={}, K={}, {} layers, H={}".format(
                     wl["name"], wl["features"], first.get("num_bins"), n_layers, first.get("hidden_features")))
@@ -337,7 +345,7 @@ def conditioner_flops(wl):
     return alg, executed
 
 
-def gpu_eager_baseline(wl, state, x):
+def gpu_eager_baseline(wl, state, x, c=None):
     """The UNMODIFIED reference in eager mode on this GPU (fp32, TF32 off — torch's default), same weights, same rows."""
     ref = None
     try:
@@ -349,7 +357,7 @@ def gpu_eager_baseline(wl, state, x):
         with torch.no_grad():
             while True:
                 try:
-                    ref.log_prob(x[:rows])
+                    ref.log_prob(x[:rows], context=None if c is None else c[:rows])
                     break
                 except torch.cuda.OutOfMemoryError:
                     torch.cuda.empty_cache()
@@ -361,7 +369,7 @@ def gpu_eager_baseline(wl, state, x):
             s.record()
             reps = 3
             for _ in range(reps):
-                ref.log_prob(x[:rows])
+                ref.log_prob(x[:rows], context=None if c is None else c[:rows])
             e.record()
             torch.cuda.synchronize()
         ms = s.elapsed_time(e) / reps
@@ -538,6 +546,122 @@ def run_cfg2(args, wl):
                                     "sample": "{} rows of {} log_prob, one pass ({:.1f} s), {} on torch CPU fp32, all host "
                                               "threads".format(CPU_SAMPLE_ROWS, wl["name"], sec,
                                                                "the unmodified reference (oracle/_ref)"
+                                                               if kind == "reference" else "oracle/restated.py")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cfg4(args, wl):
+    """BASELINE configs[3]: conditional sum-of-sigmoids flow with a hypernetwork conditioner, D = 32, context 8, 262 144 rows
+    per GPU; one launch per flow layer (fc_conditioner_sos_apply).  Rows are sharded over the ranks (weak scaling)."""
+    import torch.distributed as dist
+
+    from flowconductor_b200 import _cabi
+    from flowconductor_b200 import distributed as fdist
+
+    world, rank, local_rank, dev = setup_dist(args)
+    _cabi.lib()
+    flow, state = build_state(wl)
+    flow = flow.to(dev).eval()
+    B = args.batch or wl["batch"]
+    D, C = wl["features"], wl["context_features"]
+    x = torch.randn(B, D, generator=torch.Generator(device=dev).manual_seed(1234 + rank), device=dev)
+    c = torch.randn(B, C, generator=torch.Generator(device=dev).manual_seed(4321 + rank), device=dev)
+    flush = torch.empty((1 << 26,), dtype=torch.float32, device=dev)  # 256 MB > the 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.no_grad():
+            lp = flow.log_prob(x, context=c)
+            total = lp.double().sum() if world == 1 else fdist.reduce_log_likelihood(lp)[0]
+        return lp, total
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _cabi.STATS.reset()
+    _cabi.STATS.timing = True
+    ms = 0.0
+    barrier()
+    for _ in range(args.steps):  # every step timed on its own, the L2 flushed in between (the working set fits in L2)
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        lp, total = step()
+        e.record()
+        torch.cuda.synchronize()
+        ms += s.elapsed_time(e)
+    barrier()
+    _cabi.STATS.timing = False
+    launches = _cabi.STATS.total()
+    counts = dict(_cabi.STATS.counts)
+    n_c, c_ms = _cabi.STATS.elapsed_ms("fc_conditioner_sos_apply")
+    clocks = sampler.stop() if rank == 0 else None
+    ll = float(total.item())
+    assert ll == ll, "log-likelihood is NaN"
+
+    x_host, c_host = x.cpu().pin_memory(), c.cpu().pin_memory()
+    out_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    for _ in range(min(2, args.warmup)):
+        fdist.host_log_prob(flow, x_host, out_host, context_host=c_host)
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(args.steps):
+        fdist.host_log_prob(flow, x_host, out_host, context_host=c_host)
+    e2.record()
+    barrier()
+    t = torch.tensor([ms, s2.elapsed_time(e2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        first = wl["layers"][0]
+        H, nb, n = first["hidden_features"], first["num_blocks"], first["n_sigmoids"]
+        P = 3 * n + 1
+        alg_row = 2.0 * (C * H + 2 * nb * H * H + H * D * P)
+        h_pad, k_real = (128 if H <= 128 else 256), (H + 63) // 64 * 64
+        exec_row = 3 * 2.0 * (64 * h_pad + 2 * nb * k_real * h_pad + k_real * ((D + 1) // 2 * 96))
+        tpeak, tpeak_src = measured_tensor_peak()
+        c_each = (c_ms / n_c) if n_c else None
+        roofline = {"bound": "tensor",
+                    "kernel": "conditioner_f16x3_kernel<CondSos<10>, 48, 1, true> (fc_conditioner_sos_apply: ResidualNet on the "
+                              "context + sum-of-sigmoids transform of one flow layer in one persistent tcgen05 kernel)",
+                    "achieved": (alg_row * B / (c_each * 1e-3) / 1e12) if c_each else None, "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": (alg_row * B / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None, "traffic": None,
+                    "peak_source": tpeak_src, "algorithmic_flops_per_launch": alg_row * B,
+                    "tensor_flops_executed_per_launch": exec_row * B,
+                    "tensor_pipe_frac": (exec_row * B / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
+                    "kernel_ms_per_launch": c_each, "kernel_share_of_step": (c_ms / ms) if n_c else None, "launches_timed": n_c,
+                    "note": "the only dense contraction of the step, hence the tensor roofline; the kernel itself is bound by the "
+                            "sum-of-sigmoids arithmetic of its row threads (~800 instructions per element, DESIGN 4.12), not "
+                            "by the tensor pipe"}
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, wl, B, world),
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * (D + C) * 4,
+                    "d2h_bytes_per_step": B * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "gpu_launches_by_entry_point": counts, "clocks": clocks, "roofline": roofline,
+            "log_likelihood_sum": ll,
+        }
+        if world == 1 and not args.no_eager_baseline:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(wl, state, x, c)
+        if world == 1 and not args.no_cpu_baseline:
+            rows = REF_STEP_ROWS["cfg4"] * 4
+            rate, sec, kind = cpu_log_prob_rate(wl, state, rows, repeats=1, warmup=0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                                    "sample": "{} rows of cfg4 log_prob, one pass ({:.1f} s), {} on torch CPU fp32, all host "
+                                              "threads".format(rows, sec, "the unmodified reference (oracle/_ref)"
                                                                if kind == "reference" else "oracle/restated.py")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -781,6 +905,8 @@ def main():
         run_cfg5(args, wl)
     elif args.workload == "cfg3_train":
         run_cfg3_train(args, wl)
+    elif args.workload == "cfg4":
+        run_cfg4(args, wl)
     else:
         run_cfg2(args, wl)
 
