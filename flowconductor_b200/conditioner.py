@@ -19,6 +19,8 @@ RQS_PPAD = {8: 24, 16: 48}  # linear tails (kept for callers of the first fused 
 RQS_BINS = (8, 10, 16)      # bin counts with a register-resident instantiation of the fused kernel
 SOS_PPAD = 48               # 3 n + 1 = 31 parameters per feature for n = 10, two features per 96-column tile
 SOS_SIGMOIDS = (10,)
+AFFINE_PPAD = 24            # a 24-column slot holds the (raw scale, shift) pairs of AFFINE_GROUP consecutive features
+AFFINE_GROUP = 12
 MAX_BLOCKS = (_cabi.COND_MAX_LAYERS - 2) // 2
 
 
@@ -81,11 +83,11 @@ def rqs_ppad(num_bins, tails):
 VEC_BYTES = 20480  # kVecBytes of the kernel: the bias of every output column of every layer is staged in shared memory
 
 
-def _vectors_fit(hidden, num_blocks, ppad, d_t):
+def _vectors_fit(hidden, num_blocks, ppad, d_t, group=1):
     """The kernel keeps every layer's bias in shared memory: (1 + 2 blocks) hidden-wide layers + the final layer's tiles."""
     if d_t is None:
         return True
-    feats = 96 // ppad
+    feats = 96 // ppad * group
     total_cols = (1 + 2 * num_blocks) * padded_hidden(hidden) + (d_t + feats - 1) // feats * 96
     return total_cols * 4 + 4 * _cabi.COND_MAX_LAYERS <= VEC_BYTES
 
@@ -102,9 +104,15 @@ def supported_sos_shape(hidden, k_in, num_blocks, n_sigmoids, d_t=None):
             and _vectors_fit(hidden, num_blocks, SOS_PPAD, d_t))
 
 
-def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
+def supported_affine_shape(hidden, k_in, num_blocks, d_t=None):
+    return (padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
+            and 1 <= num_blocks <= MAX_BLOCKS and _vectors_fit(hidden, num_blocks, AFFINE_PPAD, d_t, AFFINE_GROUP))
+
+
+def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None, final_row_map=None, group=1):
     """Pack `net` (initial_layer, blocks[*].linear_layers[0..1], final_layer; optional `.mask` per layer, made.py:72)
-    for the `fc_conditioner_*_apply` kernels: P parameters per feature in `ppad` accumulator columns.  col_map / k_in:
+    for the `fc_conditioner_*_apply` kernels: P parameters per feature in `ppad` accumulator columns (final_row_map /
+    group: explicit placement of the final layer's rows, `group` features per `ppad`-column slot).  col_map / k_in:
     scatter of the first layer's input columns (a coupling layer's conditioner reads the full-width inputs:
     coupling.py:82-86 folded into the weights)."""
     L = _cabi.lib()
@@ -118,7 +126,7 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
         raise ValueError("conditioner shape not supported by the fused kernel")
     if fin.weight.shape[0] != d_t * P:
         raise ValueError("final layer has {} outputs, expected {} x {}".format(fin.weight.shape[0], d_t, P))
-    feats = 96 // ppad
+    feats = 96 // ppad * group
     n_final_tiles = (d_t + feats - 1) // feats
     # k-values the layers after the first multiply: the 128-wide kernel skips a padding chunk (nets of <= 64 units)
     hk = _ceil_to(hidden_real, 64) if hidden == 128 else hidden
@@ -139,7 +147,9 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None):
     with torch.cuda.device(dev):
         for i, ((layer, kind, bn, k_pad, n_pad), size) in enumerate(zip(layers, sizes)):
             row_map = None
-            if kind == _cabi.COND_FINAL:
+            if kind == _cabi.COND_FINAL and final_row_map is not None:
+                row_map = final_row_map.to(device=dev, dtype=torch.int32)
+            elif kind == _cabi.COND_FINAL:
                 j = torch.arange(d_t, device=dev).repeat_interleave(P)
                 ii = torch.arange(P, device=dev).repeat(d_t)
                 row_map = (j * ppad + ii).to(torch.int32)
@@ -172,6 +182,14 @@ def pack_sos(net, n_sigmoids, d_t, col_map=None, k_in=None):
     if n_sigmoids not in SOS_SIGMOIDS:
         raise ValueError("conditioner shape not supported by the fused kernel")
     return pack(net, 3 * n_sigmoids + 1, SOS_PPAD, d_t, col_map=col_map, k_in=k_in)
+
+
+def pack_affine(net, d_t, layout, col_map=None, k_in=None):
+    """`pack` for `fc_conditioner_affine_apply`: feature j's (raw scale, shift) in final-layer rows (2 j, 2 j + 1)."""
+    from . import linear as fl
+
+    rm = fl.affine_row_map(d_t, layout, net.final_layer.weight.device)
+    return pack(net, 2, AFFINE_PPAD, d_t, col_map=col_map, k_in=k_in, final_row_map=rm, group=AFFINE_GROUP)
 
 
 def rqs_apply(packed, a, x, y, logabsdet, accumulate, d_t, tcols, ccols, cfg, status=None):
@@ -212,6 +230,26 @@ def sos_apply(packed, a, x, y, logabsdet, accumulate, d_t, n_sigmoids, offset):
                                         _cabi.cols(None), _cabi.cols(None), int(n_sigmoids), float(offset),
                                         _cabi.stream_ptr(x.device))
     _cabi.check(rc, "fc_conditioner_sos_apply")
+    return y, logabsdet
+
+
+def affine_apply(packed, a, x, y, logabsdet, accumulate, d_t, tcols, ccols, activation, inverse):
+    """Whole conditioner + affine transform in one kernel (fc_conditioner_affine_apply); arguments as `rqs_apply`."""
+    _cabi.require_cuda_f32(a, "conditioner inputs")
+    _cabi.require_cuda_f32(x, "inputs")
+    L = _cabi.lib()
+    a, ap, lda = _cabi.rows(a)
+    if a.shape[1] != packed.k_in:
+        raise ValueError("conditioner inputs have {} columns, the packed net expects {}".format(a.shape[1], packed.k_in))
+    if a.shape[0] != x.shape[0]:
+        raise ValueError("conditioner inputs and inputs differ in rows")
+    assert x.stride(1) == 1 and y.stride(1) == 1 and logabsdet.is_contiguous()
+    with torch.cuda.device(x.device), _cabi.launch("fc_conditioner_affine_apply", x.device):
+        rc = L.fc_conditioner_affine_apply(ctypes.byref(packed.struct), ap, lda, a.shape[0], x.data_ptr(), x.stride(0),
+                                           y.data_ptr(), y.stride(0), logabsdet.data_ptr(), int(accumulate), d_t,
+                                           _cabi.cols(tcols), _cabi.cols(ccols), int(activation), int(bool(inverse)),
+                                           _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "fc_conditioner_affine_apply")
     return y, logabsdet
 
 

@@ -100,13 +100,17 @@ struct CondArgs {
   RqsParams c;
   int hand_period;   // every hand_period-th final N tile a row thread hands ALL its features to the bijection warps (0: never)
   float sos_offset;  // sum-of-sigmoids bijection: added to the outputs (autoregressive.py:309: -0.5; conditional.py: 0)
+  int affine_activation, affine_inverse;  // affine bijection (FC_SCALE_*, direction)
   int32_t* status;
   int32_t* error;  // device word: 0, or the code of the first wait that timed out
 };
 
 // The bijection a kernel instantiation evaluates from a register-resident parameter vector p[0 .. PPAD).
+// G: features per accumulator slot of PPAD columns (1 for the splines / sum of sigmoids; the affine transform has two
+// parameters per feature, so a 24-column slot carries 12 features).
 template <int KC>
 struct CondRqs {  // rational-quadratic spline, KC bins, linear tails (rational_quadratic.py:13-181)
+  static constexpr int G = 1;
   template <int PPAD>
   static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
                                               unsigned& status) {
@@ -119,6 +123,7 @@ struct CondRqs {  // rational-quadratic spline, KC bins, linear tails (rational_
 };
 template <int NC>
 struct CondSos {  // sum of NC sigmoids + extended softplus (adaptive_sigmoids.py:111-142, nonlinearities.py:543-552), forward
+  static constexpr int G = 1;
   template <int PPAD>
   static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
                                               unsigned&) {
@@ -286,6 +291,15 @@ struct CondSmem {
   static constexpr int TOTAL = RING_BYTES + H_BYTES + SC_BYTES + LAD_BYTES + kVecBytes + BAR_BYTES + 1024;
 };
 
+struct CondAffine {  // y = x * scale(raw) + shift and its inverse (coupling.py:224-252, autoregressive.py:97-129): a slot of 24
+  static constexpr int G = 12;  // columns holds (raw scale, shift) of 12 consecutive features
+  // feature g of the slot
+  template <int PPAD>
+  static __device__ __forceinline__ void eval_g(const CondArgs& a, int g, float x, const float (&p)[PPAD], float& y, float& lad) {
+    affine_eval(x, p[2 * g], p[2 * g + 1], a.affine_activation, a.affine_inverse, y, lad);
+  }
+};
+
 // Bij the bijection, PPAD accumulator columns per feature, NT = hidden width / 128
 // HAND: every hand_period-th final tile is handed to the bijection warps entirely (instantiated where it pays)
 template <class Bij, int PPAD, int NT, bool HAND>
@@ -298,7 +312,9 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   // threads are the critical resource — drains, conversions and one spline per tile keep them ~80 % busy while the
   // bijection warps wait 60 % of the time —, so part of the row threads' splines moves there).
   constexpr int NF_OWN = 1;
+  constexpr int G = Bij::G;           // features per slot (see the bijection policies)
   static_assert(NF >= 1 && NF * 2 * PPAD == 96, "final N tile: 96 columns");
+  static_assert(G == 1 || 2 * G <= PPAD, "grouped features: two parameters each");
   // (compile-time "never" for tiles of several features per thread: measured to be best there, and the kernel keeps
   // the leaner code — one own spline per row thread, NF - 1 per bijection thread and half)
   auto tile_own = [&](int nt) -> int {
@@ -519,8 +535,11 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
     // pending bijection work: this thread's own feature of the last finished final-layer N tile
     float pp[PPAD];
     float pxv = 0.f, lad_acc = 0.f;
+    float pxg[G > 1 ? G : 1];  // grouped features (G > 1): the slot's inputs; their columns are re-derived from pxc = slot index
     int pxc = -1;
     long long prow = 0;
+#pragma unroll
+    for (int g = 0; g < (G > 1 ? G : 1); ++g) pxg[g] = 0.f;
     bool pvalid = false, pending = false, tile_open = false;  // tile_open: the row tile's log-det share is not handed over yet
 #pragma unroll
     for (int j = 0; j < PPAD; ++j) pp[j] = 0.f;
@@ -553,11 +572,26 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       if (lane == 0) mbar_arrive_remote_relaxed(opnd_bar(g), 0);
     };
     auto spline = [&]() {
-      if (pxc >= 0) {
-        float yv, lv;
-        Bij::eval(a, pxv, pp, yv, lv, status);
-        if (pvalid) a.y[prow * a.ldy + pxc] = yv;
-        lad_acc += lv;
+      if constexpr (G == 1) {
+        if (pxc >= 0) {
+          float yv, lv;
+          Bij::eval(a, pxv, pp, yv, lv, status);
+          if (pvalid) a.y[prow * a.ldy + pxc] = yv;
+          lad_acc += lv;
+        }
+      } else {
+        if (pxc >= 0) {  // pxc: the slot; its features pxc * G ..
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int f = pxc * G + g;
+            if (f < a.D_t) {
+              float yv, lv;
+              Bij::eval_g(a, g, pxg[g], pp, yv, lv);
+              if (pvalid) a.y[prow * a.ldy + (a.tcols ? __ldg(a.tcols + f) : f)] = yv;
+              lad_acc += lv;
+            }
+          }
+        }
       }
       pending = false;
     };
@@ -712,10 +746,22 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         const float winv_f = vwinv[a.n_layers - 1];
         for (int nt = 0; nt < L.n_tiles; ++nt) {
           float pv[NF * PPAD];
-          const int fg = nt * FEATS + half * NF;  // this thread's own feature
-          const bool live = fg < a.D_t;
-          const int xc = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
-          const float xv = (valid && live) ? __ldg(a.x + row * a.ldx + xc) : 0.f;
+          const int fg = nt * FEATS + half * NF;  // this thread's own feature (G > 1: slot of G features)
+          const bool live = fg * G < a.D_t;
+          int xc = -1;
+          float xv = 0.f;
+          float xg[G > 1 ? G : 1];
+          if constexpr (G == 1) {
+            xc = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
+            xv = (valid && live) ? __ldg(a.x + row * a.ldx + xc) : 0.f;
+          } else {
+            xc = live ? fg : -1;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int f = fg * G + g;
+              xg[g] = (valid && f < a.D_t) ? __ldg(a.x + row * a.ldx + (a.tcols ? __ldg(a.tcols + f) : f)) : 0.f;
+            }
+          }
           const int n0 = nt * 96 + half * (NF * PPAD);
           {
             const float4* b4 = reinterpret_cast<const float4*>(vbias + L.col0 + n0);
@@ -774,6 +820,10 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             for (int j = 0; j < PPAD; ++j) pp[j] = pv[j];
             pxv = xv;
             pxc = xc;
+            if constexpr (G > 1) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) pxg[g] = xg[g];
+            }
             prow = row;
             pvalid = valid;
             pending = true;
@@ -832,15 +882,24 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
         const int nown = tile_own(nt), nhand = NF - nown;
         if (nhand == 0) continue;
         // the features the two row threads of this row hand over: the last nhand of each half of the N tile
-        float xv[2 * NF];
-        int xc[2 * NF];
+        float xv[2 * NF * G];
+        int xc[2 * NF];  // G == 1: the column; G > 1: the slot
 #pragma unroll
         for (int f = 0; f < 2 * NF; ++f) {  // inputs first: their latency hides behind the wait for the parameters
           const int h = f / NF, sl = f % NF;
           const int fg = nt * FEATS + h * NF + nown + sl;
-          const bool live = sl < nhand && fg < a.D_t;
-          xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
-          xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
+          const bool live = sl < nhand && fg * G < a.D_t;
+          if constexpr (G == 1) {
+            xc[f] = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
+            xv[f] = (valid && live) ? __ldg(a.x + row * a.ldx + xc[f]) : 0.f;
+          } else {
+            xc[f] = live ? fg : -1;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int ff = fg * G + g;
+              xv[f * G + g] = (valid && live && ff < a.D_t) ? __ldg(a.x + row * a.ldx + (a.tcols ? __ldg(a.tcols + ff) : ff)) : 0.f;
+            }
+          }
         }
         const uint32_t b = pt & 1u;
         {
@@ -857,11 +916,26 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             float p[PPAD];
 #pragma unroll
             for (int j = 0; j < PPAD; ++j) p[j] = pcol[((h * NF + sl) * PPAD + j) * kCM];
-            float yv, lv;
-            Bij::eval(a, xv[f], p, yv, lv, status);
-            if (xc[f] >= 0) {
-              if (valid) a.y[row * a.ldy + xc[f]] = yv;
-              lad_acc += lv;
+            if constexpr (G == 1) {
+              float yv, lv;
+              Bij::eval(a, xv[f], p, yv, lv, status);
+              if (xc[f] >= 0) {
+                if (valid) a.y[row * a.ldy + xc[f]] = yv;
+                lad_acc += lv;
+              }
+            } else {
+              if (xc[f] >= 0) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                  const int ff = xc[f] * G + g;
+                  if (ff < a.D_t) {
+                    float yv, lv;
+                    Bij::eval_g(a, g, xv[f * G + g], p, yv, lv);
+                    if (valid) a.y[row * a.ldy + (a.tcols ? __ldg(a.tcols + ff) : ff)] = yv;
+                    lad_acc += lv;
+                  }
+                }
+              }
             }
           }
         }
@@ -1044,7 +1118,7 @@ extern "C" int fc_conditioner_error(int32_t* out) {
 static int cond_build_args(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
                            int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
                            int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int ppad, int hand_default,
-                           int32_t* status, CondArgs& args) {
+                           int32_t* status, CondArgs& args, int group = 1) {
   if (!net || !net->weights || net->n_layers < 2 || net->n_layers > kMaxCondLayers) return FC_ERR_INVALID_ARGUMENT;
   if (B < 0 || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (B > 0 && (!a || !x || !y || !logabsdet)) return FC_ERR_INVALID_ARGUMENT;
@@ -1080,7 +1154,7 @@ static int cond_build_args(const fc_conditioner* net, const float* a, int64_t ld
     d.k_chunks = (k + 63) / 64;
     d.k_steps_last = ((k - (d.k_chunks - 1) * 64) + 15) / 16;
     if (!last && s.n_tiles != net->hidden / 128) return FC_ERR_INVALID_ARGUMENT;
-    if (last && (int64_t)s.n_tiles * (96 / ppad) < D_t) return FC_ERR_INVALID_ARGUMENT;
+    if (last && (int64_t)s.n_tiles * (96 / ppad) * group < D_t) return FC_ERR_INVALID_ARGUMENT;
     // (chunks are skipped only in the 128-wide kernel; the 256-wide one multiplies all four)
     if (l > 0 && (d.k_chunks > kch || (net->hidden == 256 && d.k_chunks != kch))) return FC_ERR_INVALID_ARGUMENT;
     d.kind = s.kind;
@@ -1143,6 +1217,23 @@ extern "C" int fc_conditioner_rqs_apply(const fc_conditioner* net, const float* 
   if (c.K == 10) return FC_COND_LAUNCH(10, 48);
   return FC_COND_LAUNCH(16, 48);
 #undef FC_COND_LAUNCH
+}
+
+extern "C" int fc_conditioner_affine_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                                           int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                                           int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols,
+                                           int32_t activation, int32_t inverse, void* stream) {
+  if (activation < FC_SCALE_SIGMOID2 || activation > FC_SCALE_SOFTPLUS_EPS) return FC_ERR_INVALID_ARGUMENT;
+  CondArgs args{};
+  int rc = cond_build_args(net, a, lda, B, x, x_row_stride, y, y_row_stride, logabsdet, accumulate_logabsdet, D_t, tcols,
+                           ccols, 24, 0, nullptr, args, CondAffine::G);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  args.affine_activation = activation;
+  args.affine_inverse = inverse != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (net->hidden == 256) return launch_conditioner<CondAffine, 24, 2>(args, st);
+  return launch_conditioner<CondAffine, 24, 1>(args, st);
 }
 
 extern "C" int fc_conditioner_sos_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,

@@ -12,6 +12,7 @@ in-place version counter).  Training (autograd) keeps using the torch.nn modules
 `flowconductor_b200.ops`: this path has no backward.
 """
 import math
+import os
 import threading
 
 import torch
@@ -240,7 +241,14 @@ def affine_layer(net, a, inputs, tcols, ccols, layout, activation, inverse, col_
                  allow_inplace=True):
     """Conditioner + affine transform for one layer (final layer fused: fc_linear_affine_apply)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
-    plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("affine", layout))
+    k_in = k_in if k_in is not None else a.shape[1]
+    if affine_fusable(net, k_in, d_t):
+        packed = affine_cond_plan_for(net, col_map, k_in, d_t, layout)
+        x, y = _output_buffer(inputs, allow_inplace)
+        lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
+        fcond.affine_apply(packed, a, x, y, lad, False, d_t, tcols, ccols, activation, inverse)
+        return y, lad
+    plan = plan_for(net, col_map, k_in, ("affine", layout))
     h = hidden(net, plan, a)
     x, y = _output_buffer(inputs, allow_inplace)
     lad = torch.empty((x.shape[0],), dtype=x.dtype, device=x.device)
@@ -258,6 +266,7 @@ def rqs_fusable(spline, final_out_features, d_t, net=None, k_in=None):
     return net is not None and conditioner_fusable(net, k_in, spline, d_t)
 
 
+FUSED_AFFINE = os.environ.get("FC_FUSED_AFFINE", "1") != "0"  # A/B switch of the fused affine conditioner
 FUSED_CONDITIONER = True  # whole conditioner + spline as ONE persistent kernel (csrc/fc_conditioner.cu) where it applies
 
 
@@ -271,6 +280,23 @@ def cond_plan_for(net, col_map, k_in, num_bins, d_t, tails="linear"):
     object.__setattr__(net, "_fc_cond_plan", (key, packed))
     _generation[0] += 1
     return packed
+
+
+def affine_cond_plan_for(net, col_map, k_in, d_t, layout):
+    """PackedConditioner of `net` for the fused affine kernel, cached like the spline plans."""
+    key = (_param_key(net), "affine", layout, k_in, d_t)
+    plan = getattr(net, "_fc_cond_plan", None)
+    if plan is not None and plan[0] == key:
+        return plan[1]
+    packed = fcond.pack_affine(net, d_t, layout, col_map=col_map, k_in=k_in)
+    object.__setattr__(net, "_fc_cond_plan", (key, packed))
+    _generation[0] += 1
+    return packed
+
+
+def affine_fusable(net, k_in, d_t=None):
+    return FUSED_CONDITIONER and FUSED_AFFINE and k_in is not None and fcond.supported_affine_shape(
+        net.initial_layer.weight.shape[0], k_in, len(net.blocks), d_t)
 
 
 def sos_cond_plan_for(net, k_in, n_sigmoids, d_t):

@@ -384,6 +384,14 @@ int fc_conditioner_sos_apply(const fc_conditioner* net, const float* a, int64_t 
                              int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
                              int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t n_sigmoids,
                              float offset, void* stream);
+/* Same kernel with the affine bijection (AffineCouplingTransform, flowcon/transforms/coupling.py:212-252, and the forward of
+ * MaskedAffineAutoregressiveTransform, autoregressive.py:97-129): the final layer is packed so that feature j's (raw scale,
+ * shift) sit in rows (2j, 2j + 1) — row_map as for fc_linear_affine_apply, 48 features per 96-column tile.  `activation`
+ * FC_SCALE_*; inverse != 0: y = (x - shift) / scale. */
+int fc_conditioner_affine_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
+                                int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
+                                int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t activation,
+                                int32_t inverse, void* stream);
 /* Debugging aid: every barrier wait inside the kernel is bounded; if one ever times out the kernel ends early and leaves
  * a non-zero code (wait site + 100 * warp) here.  Synchronises the device.  Not part of the data path. */
 int fc_conditioner_error(int32_t* out);

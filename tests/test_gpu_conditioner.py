@@ -293,6 +293,45 @@ def test_masked_sum_of_sigmoids_forward_fused(dev, monkeypatch):
     assert (lad - ladu).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize("kind,features,hidden,rows", [("coupling", 32, 128, 3001), ("coupling", 132, 256, 2048),
+                                                       ("maf", 8, 64, 1500), ("maf", 64, 256, 4096), ("maf", 52, 128, 777)])
+def test_affine_layers_run_in_the_fused_conditioner(dev, kind, features, hidden, rows, monkeypatch):
+    """AffineCouplingTransform (coupling.py:212-252; [shift | raw scale] final layer, sigmoid(raw + 2) + 1e-3 scale) and
+    the forward of MaskedAffineAutoregressiveTransform (autoregressive.py:97-129; (raw scale, shift) pairs, softplus + 1e-3):
+    one fc_conditioner_affine_apply launch per call, against the unfused path; 12 features share a 24-column accumulator
+    slot, so feature counts that end inside a slot and inside a tile are covered."""
+    torch.manual_seed(features + hidden)
+    if kind == "coupling":
+        mask = workloads.make_mask(features, "alternating_even")
+        layer = transforms.AffineCouplingTransform(
+            mask, lambda i, o: ResidualNet(i, o, hidden_features=hidden, num_blocks=2))
+        directions = (False, True)
+    else:
+        layer = transforms.MaskedAffineAutoregressiveTransform(features=features, hidden_features=hidden, num_blocks=2)
+        directions = (False,)
+    layer = layer.to(dev).eval()
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+        x = torch.randn(rows, features, device=dev)
+        for inverse in directions:
+            fn = layer.inverse if inverse else layer
+            _cabi.STATS.reset()
+            y, lad = fn(x)
+            assert _cabi.STATS.counts.get("fc_conditioner_affine_apply", 0) == 1, _cabi.STATS.counts
+            monkeypatch.setattr(tensorcore, "ENABLED", False)
+            yu, ladu = fn(x)
+            monkeypatch.setattr(tensorcore, "ENABLED", True)
+            monkeypatch.setattr(tensorcore, "FUSED_AFFINE", False)
+            yp, ladp = fn(x)  # per-layer tensor-core kernels (fc_linear_affine_apply)
+            monkeypatch.setattr(tensorcore, "FUSED_AFFINE", True)
+            for (b, lb) in ((yu, ladu), (yp, ladp)):
+                # the inverse divides by a scale that can be ~1e-3 (sigmoid(raw + 2) + 1e-3): a few ill-conditioned entries
+                rel = ((y - b).abs() / b.abs().clamp_min(1.0)).flatten()
+                assert torch.quantile(rel, 0.999) < 1e-4 and rel.max() < 5e-2, (kind, inverse, float(rel.max()))
+                assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3 and (lad - lb).abs().max() < 5e-2
+
+
 def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypatch):
     """H = 64 ResidualNet (cfg2_tc_small): zero-padded to 128 at pack time, one fused launch per layer, same numbers as the
     per-layer kernels."""
