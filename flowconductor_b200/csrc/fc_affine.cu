@@ -38,6 +38,8 @@ __device__ __forceinline__ void affine_fetch(const AffineArgs& a, const float* p
 // Op for the per-warp TMA ring of fc_pipeline.cuh (contiguous rows whose column lists cover the row): parameters
 // per feature are (raw scale, shift) pairs (interleaved) or prow[0] = shift, prow[D_t] = raw scale (blocked).
 struct AffineOp {
+  static constexpr int kTileBwdWarps = 12;
+  static constexpr int kTileWarps = 12;  // little arithmetic per row: more consumer warps in flight (fc_pipeline.cuh)
   int D_t, layout, activation, inverse;
   __device__ __forceinline__ int P() const { return 2; }
   __device__ __forceinline__ int feature_stride() const { return layout == FC_AFFINE_BLOCKED ? 1 : 2; }

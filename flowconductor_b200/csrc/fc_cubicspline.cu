@@ -14,6 +14,7 @@ namespace fc {
 
 template <int KC>
 struct CubicSplineOp {
+  static constexpr int kTileWarps = 16, kTileCtas = 1;  // tile ring: ~90 registers, one large CTA per SM
   static constexpr int kMinBlocks = 1;  // arithmetic-heavy: the full 128 registers instead of spills (fc_pipeline.cuh)
   CubicSplineParams c;
   __device__ __forceinline__ int P() const { return 2 * c.K + 2; }

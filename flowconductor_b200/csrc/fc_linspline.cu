@@ -13,6 +13,7 @@ namespace fc {
 
 template <int KC>
 struct LinSplineOp {
+  static constexpr int kTileWarps = 12;  // little arithmetic per row: more consumer warps in flight (fc_pipeline.cuh)
   LinSplineParams c;
   __device__ __forceinline__ int P() const { return c.K; }
   __device__ __forceinline__ void eval(float x, const float* p, float& y, float& lad, unsigned& status) const {

@@ -756,7 +756,7 @@ FC_HD void linspline_eval(const LinSplineParams& c, float x, const float* u, flo
     // torchutils.py:147-149, before the slopes are taken, linear.py:60-71: the last bin's slope sees the bump)
     int idx = -1;
     float run = 0.f, c_lo = 0.f, c_hi = 0.f;
-#pragma unroll(KC ? KC : 4)
+#pragma unroll(KC ? KC + 1 : 4)  // K + 1 trips: a partial unroll would index p[] dynamically and push it to local memory
     for (int m = 0; m <= K; ++m) {
       const float knot = m == K ? 1.f + 1e-6f : run;
       if (yn >= knot) {

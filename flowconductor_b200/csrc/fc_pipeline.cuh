@@ -18,6 +18,10 @@
 // Requirements (checked by the host, else the staged kernel of fc_staged.cuh runs): contiguous params, x and
 // y rows (stride == width), 16-byte aligned bases, row sizes that are multiples of 16 bytes.
 #pragma once
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "fc_staged.cuh"
 
 namespace fc {
@@ -200,9 +204,273 @@ __global__ void __launch_bounds__(512, PipeMinBlocks<Op>::value) pipelined_apply
   if (status && a.status) atomicOr(a.status, (int)status);
 }
 
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// Tile ring: the same streaming scheme with the ring shared by the CTA.  One producer warp moves TILES of `tile_rows`
+// consecutive rows (parameters + inputs, two bulk loads; finished rows leave with ONE bulk store, the per-row
+// log|det J| with one coalesced store of the producer warp), `consumers` warps evaluate the rows of a tile side by side.
+// The per-slot bookkeeping of the per-warp ring above (barrier wait, re-arm, address arithmetic, output copy: ≈ 270 of
+// the ≈ 400 warp instructions per row of a K = 8 linear-spline row, where the ring is issue-bound at 54 % of the copy
+// peak) is paid once per tile by a warp that does nothing else, and once per tile — not per row — by a consumer.
+//   full[s]: armed by the producer's bulk loads (expect_tx);   done[s]: one arrival per consumer warp.
+// ------------------------------------------------------------------------------------------------------------
+struct TileArgs {
+  LayerArgs a;
+  int D;            // full row width of x / y
+  int tile_rows;    // rows per tile (multiple of 4)
+  int stages;       // tiles in flight per CTA
+  int consumers;    // consumer warps per CTA (the producer is warp `consumers`)
+  int64_t num_tiles;
+};
+
+__device__ __forceinline__ void ring_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int kTileMaxWarps = 17;
+
+// Consumer warps per CTA and CTAs per SM of the tile ring: 8 x 2 unless the Op says otherwise (kTileWarps / kTileCtas) —
+// rows with little arithmetic (affine, linear spline) want more consumers in flight, the register-heavy cubic spline one
+// larger CTA (scripts/bench_tile_ring.py --sweep).
+template <class Op, class = void>
+struct TileWarps {
+  static constexpr int value = 8;
+};
+template <class Op>
+struct TileWarps<Op, decltype((void)Op::kTileWarps)> {
+  static constexpr int value = Op::kTileWarps;
+};
+template <class Op, class = void>
+struct TileBwdWarps {  // the adjoints hold 80-100 registers: one CTA of 16 consumer warps per SM (0.98-1.00 of the copy peak on
+  static constexpr int value = 16;  // the rational-quadratic rows) unless the Op says otherwise (kTileBwdWarps)
+};
+template <class Op>
+struct TileBwdWarps<Op, decltype((void)Op::kTileBwdWarps)> {
+  static constexpr int value = Op::kTileBwdWarps;
+};
+template <class Op, class = void>
+struct TileCtas {
+  static constexpr int value = 2;
+};
+template <class Op>
+struct TileCtas<Op, decltype((void)Op::kTileCtas)> {
+  static constexpr int value = Op::kTileCtas;
+};
+
+template <class Op, bool kSimple>
+__global__ void __launch_bounds__(kTileMaxWarps * 32, PipeMinBlocks<Op>::value) tiled_apply_kernel(const TileArgs ta, const Op op) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const LayerArgs& a = ta.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NW = ta.consumers, S = ta.stages, TR = ta.tile_rows;
+  const int P = op.P();
+  const int D = ta.D, D_t = kSimple ? 32 : a.D_t;
+  const int row_floats = D_t * P;
+  const int tile_floats = TR * (row_floats + D + 1);  // parameters, inputs, one log|det J| per row
+  float* const tiles = reinterpret_cast<float*>(smem_raw);
+  const uint32_t tiles_s = smem_u32(tiles);
+  const uint32_t full_s = tiles_s + (uint32_t)S * tile_floats * 4u, done_s = full_s + (uint32_t)S * 8u;
+  const int64_t B = a.B, nt = ta.num_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_s + (uint32_t)s * 8u, 1);
+      mbar_init(done_s + (uint32_t)s * 8u, (uint32_t)NW);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  if (warp == NW) {  // ---- producer warp
+    int64_t t_fetch = blockIdx.x;
+    auto issue = [&](int slot) {  // lane 0 only
+      const int64_t row0 = t_fetch * TR;
+      const int rows = (int)min((int64_t)TR, B - row0);
+      const uint32_t dst = tiles_s + (uint32_t)slot * tile_floats * 4u;
+      const uint32_t bar = full_s + (uint32_t)slot * 8u;
+      const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
+      mbar_expect_tx(bar, pbytes + xbytes);
+      bulk_g2s(dst, a.params + row0 * row_floats, pbytes, bar);
+      bulk_g2s(dst + (uint32_t)TR * row_floats * 4u, a.x + row0 * D, xbytes, bar);
+      t_fetch += gridDim.x;
+    };
+    if (lane == 0)
+      for (int s = 0; s < S; ++s)
+        if (t_fetch < nt) issue(s);
+    __syncwarp();
+    int slot = 0;
+    uint32_t parity = 0;
+    const int accumulate = a.accumulate;
+    for (int64_t t = blockIdx.x; t < nt; t += gridDim.x) {
+      mbar_wait(done_s + (uint32_t)slot * 8u, parity);
+      const int64_t row0 = t * TR;
+      const int rows = (int)min((int64_t)TR, B - row0);
+      const float* slad = tiles + slot * tile_floats + TR * (row_floats + D);
+      for (int r = lane; r < rows; r += 32) {
+        float* g = a.lad + row0 + r;
+        *g = accumulate ? *g + slad[r] : slad[r];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(a.y + row0 * D, tiles_s + (uint32_t)(slot * tile_floats + TR * row_floats) * 4u, (uint32_t)(rows * D) * 4u);
+        bulk_commit();
+        if (t_fetch < nt) {
+          bulk_wait_read0();  // the store has read the tile: it may be refilled
+          issue(slot);
+        }
+      }
+      __syncwarp();
+      if (++slot == S) {
+        slot = 0;
+        parity ^= 1u;
+      }
+    }
+    if (lane == 0) bulk_wait_all0();  // global writes complete before the kernel ends
+    return;
+  }
+
+  // ---- consumer warps
+  const int seg = kSimple ? 32 : a.seg, rpw = 32 / seg;
+  const int sub = lane / seg, j0 = lane % seg;
+  const int32_t* __restrict__ tcols = a.tcols;
+  const int col0 = (j0 < D_t) ? (tcols ? __ldg(tcols + j0) : j0) : 0;  // this lane's first column
+  const int fstride = feature_stride(op, 0);
+  const int jstep = seg * fstride;
+  const int rstep = NW * rpw;
+  unsigned status = 0;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int64_t t = blockIdx.x; t < nt; t += gridDim.x) {
+    mbar_wait(full_s + (uint32_t)slot * 8u, parity);
+    const int rows = (int)min((int64_t)TR, B - t * TR);
+    float* const sp = tiles + slot * tile_floats;
+    float* const sx = sp + TR * row_floats;
+    float* const slad = sx + TR * D;
+    for (int rb = warp * rpw; rb < rows; rb += rstep) {  // uniform trip count within the warp
+      const int r = rb + sub;
+      const bool row_ok = r < rows;
+      float* xrow = sx + r * D;
+      const float* prow = sp + r * row_floats + j0 * fstride;
+      float lad_acc = 0.f;
+      if (kSimple) {
+        float yv;
+        op.eval(xrow[col0], prow, yv, lad_acc, status);
+        xrow[col0] = yv;
+      } else if (row_ok) {
+        const float* pj = prow;
+        for (int j = j0; j < D_t; j += seg, pj += jstep) {
+          const int col = (j == j0) ? col0 : (tcols ? __ldg(tcols + j) : j);
+          float yv, lv;
+          op.eval(xrow[col], pj, yv, lv, status);
+          xrow[col] = yv;  // compose the output row in place; identity columns are already there
+          lad_acc += lv;
+        }
+      }
+      lad_acc = seg_reduce_sum(lad_acc, seg);
+      if (row_ok && j0 == 0) slad[r] = lad_acc;
+    }
+    fence_proxy_async();  // the bulk store / the refill touch the tile through the async proxy
+    __syncwarp();
+    if (lane == 0) ring_arrive(done_s + (uint32_t)slot * 8u);
+    if (++slot == S) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+  if (status && a.status) atomicOr(a.status, (int)status);
+}
+
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
+}
+
+// CTAs of `kern` that fit one SM with this block size / dynamic shared memory (registers included); cached per
+// (kernel, threads, smem) — the query costs microseconds and the launchers below run once per layer call.
+template <class Kern>
+inline int resident_ctas(Kern kern, int threads, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t>, int> cache;
+  const auto key = std::make_tuple(reinterpret_cast<const void*>(kern), threads, smem);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) nb = 0;
+  cache.emplace(key, nb);
+  return nb;
+}
+
+// Launch the tile ring if the shape fits; 1 launched, 0 not applicable, <0 error.  Same preconditions as the per-warp ring
+// (checked by the caller).
+template <class Op>
+inline int try_launch_tiled(const LayerArgs& a, const Op& op, int P, int D, cudaStream_t st) {
+  if (env_int("FC_TILE", 1) == 0) return 0;
+  const DeviceInfo& dev = device_info();
+  const LaneMap lm = lane_map(a.D_t);
+  const int64_t row_bytes = ((int64_t)a.D_t * P + D + 1) * 4;
+  int consumers = env_int("FC_TILE_WARPS", TileWarps<Op>::value);
+  if (consumers < 1) consumers = 1;
+  if (consumers > kTileMaxWarps - 1) consumers = kTileMaxWarps - 1;
+  // two CTAs per SM, two tiles in flight each, tiles as large as the shared memory allows (≈ 50 KB): measured best on the
+  // rational-quadratic (0.98 of the copy peak), affine (0.97) and linear-spline rows (scripts/bench_tile_ring.py --sweep)
+  int ctas_per_sm = env_int("FC_TILE_CTAS", TileCtas<Op>::value);
+  int stages = env_int("FC_TILE_STAGES", 2);
+  int passes = env_int("FC_TILE_PASSES", 32);  // rows (groups of rows_per_warp) a consumer warp evaluates per tile
+  const int64_t sm_budget = 224 * 1024;
+  const int passes_max = passes;
+  auto tile_rows = [&](int ps) { return (consumers * lm.rows_per_warp * ps + 3) / 4 * 4; };
+  auto smem_need = [&](int ps, int s) { return (int64_t)s * (tile_rows(ps) * row_bytes + 16) + 128; };
+  auto resident = [&](size_t smem) {  // CTAs per SM the registers of this instantiation allow
+    return a.D_t == 32 ? resident_ctas(tiled_apply_kernel<Op, true>, (consumers + 1) * 32, smem)
+                       : resident_ctas(tiled_apply_kernel<Op, false>, (consumers + 1) * 32, smem);
+  };
+  for (;;) {
+    passes = passes_max;
+    while ((int64_t)ctas_per_sm * (smem_need(passes, stages) + 1024) > sm_budget) {
+      if (passes > 1) --passes;
+      else if (stages > 2) --stages;
+      else if (ctas_per_sm > 1) --ctas_per_sm;
+      else return 0;
+    }
+    if (a.D_t == 32 ? prepare_kernel(tiled_apply_kernel<Op, true>, (size_t)smem_need(passes, stages)) != FC_OK
+                    : prepare_kernel(tiled_apply_kernel<Op, false>, (size_t)smem_need(passes, stages)) != FC_OK)
+      return FC_ERR_CUDA;
+    const int nb = resident((size_t)smem_need(passes, stages));
+    if (nb <= 0) return 0;
+    if (nb >= ctas_per_sm) break;
+    ctas_per_sm = nb;  // fewer, larger CTAs
+  }
+  // a short batch: smaller tiles so that every SM gets one
+  while (passes > 1 && (a.B + tile_rows(passes) - 1) / tile_rows(passes) < (int64_t)dev.sm_count * ctas_per_sm) --passes;
+  TileArgs ta;
+  ta.a = a;
+  ta.a.seg = lm.seg;
+  ta.D = D;
+  ta.tile_rows = tile_rows(passes);
+  ta.stages = stages;
+  ta.consumers = consumers;
+  ta.num_tiles = (a.B + ta.tile_rows - 1) / ta.tile_rows;
+  const size_t smem = (size_t)smem_need(passes, stages);
+  int64_t grid = (int64_t)dev.sm_count * ctas_per_sm;
+  if (grid > ta.num_tiles) grid = ta.num_tiles;
+  if (grid < 1) grid = 1;
+  if (a.D_t == 32) {
+    if (prepare_kernel(tiled_apply_kernel<Op, true>, smem) != FC_OK) return FC_ERR_CUDA;
+    tiled_apply_kernel<Op, true><<<(int)grid, (consumers + 1) * 32, smem, st>>>(ta, op);
+  } else {
+    if (prepare_kernel(tiled_apply_kernel<Op, false>, smem) != FC_OK) return FC_ERR_CUDA;
+    tiled_apply_kernel<Op, false><<<(int)grid, (consumers + 1) * 32, smem, st>>>(ta, op);
+  }
+  if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  return 1;
 }
 
 // Try the pipelined kernel; returns 1 if it was launched, 0 if the call does not qualify, <0 on error.
@@ -215,6 +483,10 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
   if (!aligned || a.p_stride != row_floats || a.x_stride != D || a.y_stride != D) return 0;
   if (a.D_t + a.n_copy != D) return 0;  // whole rows are streamed: the column lists must cover the row
   if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
+  {
+    const int tiled = try_launch_tiled(a, op, P, D, st);
+    if (tiled != 0) return tiled;
+  }
   const DeviceInfo& dev = device_info();
   const LaneMap lm = lane_map(a.D_t);
   const int64_t row_bytes = (row_floats + D) * 4;
@@ -276,12 +548,6 @@ struct PipeBwdArgs {
   int slot_rows, stages, warps;
 };
 
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <class Op>
 __global__ void __launch_bounds__(512) pipelined_backward_kernel(const PipeBwdArgs pa, const Op op) {
@@ -379,6 +645,183 @@ __global__ void __launch_bounds__(512) pipelined_backward_kernel(const PipeBwdAr
   if (lane == 0) bulk_wait_all0();  // global writes complete before the kernel ends
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Backward on the tile ring: a tile holds the parameters, the inputs, the upstream gradients and the grad_logabsdet
+// scalars of `tile_rows` rows (four bulk loads by the producer warp); the consumers write the parameter gradients over
+// the parameters and the input gradients over the inputs; the producer sends the two finished blocks off with two bulk
+// stores.  Same traffic as the per-warp backward ring, a fraction of its bookkeeping instructions.
+// ------------------------------------------------------------------------------------------------------------
+struct TileBwdArgs {
+  LayerBwdArgs a;
+  int D;
+  int tile_rows, stages, consumers;
+  int gl_bulk;  // grad_logabsdet rows travel with the tile (base 16-byte aligned); the ragged last tile reads them directly
+  int64_t num_tiles;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kTileMaxWarps * 32) tiled_backward_kernel(const TileBwdArgs ta, const Op op) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const LayerBwdArgs& a = ta.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NW = ta.consumers, S = ta.stages, TR = ta.tile_rows;
+  const int P = op.P();
+  const int D = ta.D, D_t = a.D_t;
+  const int row_floats = D_t * P;
+  const int tile_floats = TR * (row_floats + 2 * D + 1);  // parameters, inputs, upstream gradients, grad_logabsdet
+  float* const tiles = reinterpret_cast<float*>(smem_raw);
+  const uint32_t tiles_s = smem_u32(tiles);
+  const uint32_t full_s = tiles_s + (uint32_t)S * tile_floats * 4u, done_s = full_s + (uint32_t)S * 8u;
+  const int64_t B = a.B, nt = ta.num_tiles;
+  const uint32_t xoff = (uint32_t)TR * row_floats * 4u, goff = xoff + (uint32_t)TR * D * 4u, loff = goff + (uint32_t)TR * D * 4u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_s + (uint32_t)s * 8u, 1);
+      mbar_init(done_s + (uint32_t)s * 8u, (uint32_t)NW);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  if (warp == NW) {  // ---- producer (one lane)
+    if (lane != 0) return;
+    int64_t t_fetch = blockIdx.x;
+    auto issue = [&](int slot) {
+      const int64_t row0 = t_fetch * TR;
+      const int rows = (int)min((int64_t)TR, B - row0);
+      const uint32_t dst = tiles_s + (uint32_t)slot * tile_floats * 4u;
+      const uint32_t bar = full_s + (uint32_t)slot * 8u;
+      const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
+      const uint32_t lbytes = (ta.gl_bulk && rows == TR) ? (uint32_t)TR * 4u : 0u;
+      mbar_expect_tx(bar, pbytes + 2 * xbytes + lbytes);
+      bulk_g2s(dst, a.params + row0 * row_floats, pbytes, bar);
+      bulk_g2s(dst + xoff, a.x + row0 * D, xbytes, bar);
+      bulk_g2s(dst + goff, a.gy + row0 * D, xbytes, bar);
+      if (lbytes) bulk_g2s(dst + loff, a.gl + row0, lbytes, bar);
+      t_fetch += gridDim.x;
+    };
+    for (int s = 0; s < S; ++s)
+      if (t_fetch < nt) issue(s);
+    int slot = 0;
+    uint32_t parity = 0;
+    for (int64_t t = blockIdx.x; t < nt; t += gridDim.x) {
+      mbar_wait(done_s + (uint32_t)slot * 8u, parity);
+      const int64_t row0 = t * TR;
+      const int rows = (int)min((int64_t)TR, B - row0);
+      const uint32_t src = tiles_s + (uint32_t)slot * tile_floats * 4u;
+      bulk_s2g(a.gp + row0 * row_floats, src, (uint32_t)(rows * row_floats) * 4u);
+      bulk_s2g(a.gx + row0 * D, src + xoff, (uint32_t)(rows * D) * 4u);
+      bulk_commit();
+      if (t_fetch < nt) {
+        bulk_wait_read0();  // the stores have read the tile: it may be refilled
+        issue(slot);
+      }
+      if (++slot == S) {
+        slot = 0;
+        parity ^= 1u;
+      }
+    }
+    bulk_wait_all0();  // global writes complete before the kernel ends
+    return;
+  }
+
+  // ---- consumer warps
+  const int seg = a.seg, rpw = 32 / seg;
+  const int sub = lane / seg, j0 = lane % seg;
+  const int32_t* __restrict__ tcols = a.tcols;
+  const int32_t* __restrict__ ccols = a.ccols;
+  const int fstride = feature_stride(op, 0);
+  const int rstep = NW * rpw;
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int64_t t = blockIdx.x; t < nt; t += gridDim.x) {
+    mbar_wait(full_s + (uint32_t)slot * 8u, parity);
+    const int64_t row0 = t * TR;
+    const int rows = (int)min((int64_t)TR, B - row0);
+    float* const sp = tiles + slot * tile_floats;
+    float* const sx = sp + TR * row_floats;
+    const float* const sg = sx + TR * D;
+    const float* const sl = sg + TR * D;
+    const bool gl_tile = ta.gl_bulk && rows == TR;
+    for (int r = warp * rpw + sub; r < rows; r += rstep) {
+      float* xrow = sx + r * D;
+      const float* grow = sg + r * D;
+      const float gl = a.gl ? (gl_tile ? sl[r] : __ldg(a.gl + row0 + r)) : 0.f;
+      for (int j = j0; j < D_t; j += seg) {
+        const int col = tcols ? __ldg(tcols + j) : j;
+        float* pj = sp + r * row_floats + j * fstride;
+        float gxv;
+        op.backward(xrow[col], pj, grow[col], gl, gxv, pj);  // parameter gradients overwrite the parameters
+        xrow[col] = gxv;                                      // input gradient overwrites the input
+      }
+      for (int i = j0; i < a.n_copy; i += seg) {  // identity columns: grad_x = grad_y
+        const int col = __ldg(ccols + i);
+        xrow[col] = grow[col];
+      }
+    }
+    fence_proxy_async();  // the bulk stores / the refill touch the tile through the async proxy
+    __syncwarp();
+    if (lane == 0) ring_arrive(done_s + (uint32_t)slot * 8u);
+    if (++slot == S) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+}
+
+template <class Op>
+inline int try_launch_tiled_backward(const LayerBwdArgs& a, const Op& op, int P, int D, cudaStream_t st) {
+  if (env_int("FC_TILE", 1) == 0 || env_int("FC_TILE_BWD", 1) == 0) return 0;
+  const DeviceInfo& dev = device_info();
+  const LaneMap lm = lane_map(a.D_t);
+  const int64_t row_bytes = ((int64_t)a.D_t * P + 2 * D + 1) * 4;
+  int consumers = env_int("FC_TILE_BWD_WARPS", TileBwdWarps<Op>::value);
+  if (consumers < 1) consumers = 1;
+  if (consumers > kTileMaxWarps - 1) consumers = kTileMaxWarps - 1;
+  int ctas_per_sm = env_int("FC_TILE_BWD_CTAS", TileCtas<Op>::value);
+  int stages = env_int("FC_TILE_BWD_STAGES", 2);
+  int passes = env_int("FC_TILE_BWD_PASSES", 32);
+  const int64_t sm_budget = 224 * 1024;
+  const int passes_max = passes;
+  auto tile_rows = [&](int ps) { return (consumers * lm.rows_per_warp * ps + 3) / 4 * 4; };
+  auto smem_need = [&](int ps, int s) { return (int64_t)s * (tile_rows(ps) * row_bytes + 16) + 128; };
+  for (;;) {
+    passes = passes_max;
+    while ((int64_t)ctas_per_sm * (smem_need(passes, stages) + 1024) > sm_budget) {
+      if (passes > 1) --passes;
+      else if (stages > 2) --stages;
+      else if (ctas_per_sm > 1) --ctas_per_sm;
+      else return 0;
+    }
+    const size_t smem = (size_t)smem_need(passes, stages);
+    if (prepare_kernel(tiled_backward_kernel<Op>, smem) != FC_OK) return FC_ERR_CUDA;
+    const int nb = resident_ctas(tiled_backward_kernel<Op>, (consumers + 1) * 32, smem);  // registers included
+    if (nb <= 0) return 0;
+    if (nb >= ctas_per_sm) break;
+    ctas_per_sm = nb;  // fewer, larger CTAs
+  }
+  while (passes > 1 && (a.B + tile_rows(passes) - 1) / tile_rows(passes) < (int64_t)dev.sm_count * ctas_per_sm) --passes;
+  TileBwdArgs ta;
+  ta.a = a;
+  ta.a.seg = lm.seg;
+  ta.D = D;
+  ta.tile_rows = tile_rows(passes);
+  ta.stages = stages;
+  ta.consumers = consumers;
+  ta.gl_bulk = a.gl != nullptr && (reinterpret_cast<uintptr_t>(a.gl) & 15) == 0;
+  ta.num_tiles = (a.B + ta.tile_rows - 1) / ta.tile_rows;
+  const size_t smem = (size_t)smem_need(passes, stages);
+  int64_t grid = (int64_t)dev.sm_count * ctas_per_sm;
+  if (grid > ta.num_tiles) grid = ta.num_tiles;
+  if (grid < 1) grid = 1;
+  if (prepare_kernel(tiled_backward_kernel<Op>, smem) != FC_OK) return FC_ERR_CUDA;
+  tiled_backward_kernel<Op><<<(int)grid, (consumers + 1) * 32, smem, st>>>(ta, op);
+  if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  return 1;
+}
+
 // Try the pipelined backward kernel; returns 1 if it was launched, 0 if the call does not qualify, <0 on error.
 template <class Op>
 inline int try_launch_pipelined_backward(const LayerBwdArgs& a, const Op& op, int P, int D, cudaStream_t st) {
@@ -392,6 +835,10 @@ inline int try_launch_pipelined_backward(const LayerBwdArgs& a, const Op& op, in
     return 0;
   if (a.D_t + a.n_copy != D) return 0;  // whole rows are streamed: the column lists must cover the row
   if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
+  {
+    const int tiled = try_launch_tiled_backward(a, op, P, D, st);
+    if (tiled != 0) return tiled;
+  }
   const DeviceInfo& dev = device_info();
   const LaneMap lm = lane_map(a.D_t);
   const int64_t row_bytes = (row_floats + 2 * D) * 4;

@@ -13,6 +13,7 @@ namespace fc {
 
 template <int KC>
 struct QuadSplineOp {
+  static constexpr int kTileWarps = 12;  // tile ring: 12 consumer warps x 2 CTAs (68 registers)
   static constexpr int kMinBlocks = 1;  // arithmetic-heavy: the full 128 registers instead of spills (fc_pipeline.cuh)
   QuadSplineParams c;
   __device__ __forceinline__ int P() const { return c.tails == FC_TAILS_LINEAR ? 2 * c.K - 1 : 2 * c.K + 1; }
