@@ -242,6 +242,7 @@ extern "C" int fc_affine_apply(const float* x, int64_t x_row_stride, const float
   // interleaved (raw, shift) pairs are read as float2: the parameter rows must keep 8-byte alignment
   const bool pairs_ok = layout == FC_AFFINE_BLOCKED ||
                         ((reinterpret_cast<uintptr_t>(params) & 7) == 0 && (params_row_stride & 1) == 0);
+  last_path() = kPathStaged;
   if (pairs_ok) {
     affine_forward_kernel<<<affine_grid((B + kAffineUnroll - 1) / kAffineUnroll, a.seg), kThreads, 0, (cudaStream_t)stream>>>(a);
   } else {
@@ -280,6 +281,7 @@ extern "C" int fc_affine_backward(const float* x, int64_t x_row_stride, const fl
     const int piped = try_launch_pipelined_backward(lb, op, 2, (int)x_row_stride, (cudaStream_t)stream);
     if (piped != 0) return piped < 0 ? piped : FC_OK;
   }
+  last_path() = kPathStaged;
   affine_kernel<true><<<affine_grid(B, a.seg), kThreads, 0, (cudaStream_t)stream>>>(a);
   FC_CHECK_LAUNCH();
   return FC_OK;

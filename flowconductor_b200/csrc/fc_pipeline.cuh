@@ -16,7 +16,8 @@
 // DRAM pages.  HBM traffic = algorithmic bytes: params + x read once, y + logabsdet written once.
 //
 // Requirements (checked by the host, else the staged kernel of fc_staged.cuh runs): contiguous params, x and
-// y rows (stride == width), 16-byte aligned bases, row sizes that are multiples of 16 bytes.
+// y rows (stride == width), 16-byte aligned bases; the per-warp ring also needs row sizes that are multiples of 16
+// bytes, the tile ring further down (the default) takes any row length.
 #pragma once
 #include <map>
 #include <mutex>
@@ -290,21 +291,35 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32, PipeMinBlocks<Op>::value) 
 
   if (warp == NW) {  // ---- producer warp
     int64_t t_fetch = blockIdx.x;
-    auto issue = [&](int slot) {  // lane 0 only
+    // Rows need not be multiples of 16 bytes: a tile starts at a multiple of 4 rows, so a FULL tile is an aligned block of
+    // a 16-byte-multiple size whatever the row length.  Only a ragged last tile of such rows is moved with plain loads /
+    // stores of the producer's lanes (released to the consumers by an ordinary arrival on the same barrier).
+    auto bulk_ok = [&](int rows) { return ((rows * row_floats) & 3) == 0 && ((rows * D) & 3) == 0; };
+    auto issue = [&](int slot) {  // whole warp
       const int64_t row0 = t_fetch * TR;
       const int rows = (int)min((int64_t)TR, B - row0);
-      const uint32_t dst = tiles_s + (uint32_t)slot * tile_floats * 4u;
       const uint32_t bar = full_s + (uint32_t)slot * 8u;
-      const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
-      mbar_expect_tx(bar, pbytes + xbytes);
-      bulk_g2s(dst, a.params + row0 * row_floats, pbytes, bar);
-      bulk_g2s(dst + (uint32_t)TR * row_floats * 4u, a.x + row0 * D, xbytes, bar);
+      if (bulk_ok(rows)) {
+        if (lane == 0) {
+          const uint32_t dst = tiles_s + (uint32_t)slot * tile_floats * 4u;
+          const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
+          mbar_expect_tx(bar, pbytes + xbytes);
+          bulk_g2s(dst, a.params + row0 * row_floats, pbytes, bar);
+          bulk_g2s(dst + (uint32_t)TR * row_floats * 4u, a.x + row0 * D, xbytes, bar);
+        }
+      } else {
+        float* d = tiles + slot * tile_floats;
+        const float* gp = a.params + row0 * row_floats;
+        const float* gx = a.x + row0 * D;
+        for (int i = lane; i < rows * row_floats; i += 32) d[i] = __ldg(gp + i);
+        for (int i = lane; i < rows * D; i += 32) d[TR * row_floats + i] = __ldg(gx + i);
+        __syncwarp();
+        if (lane == 0) ring_arrive(bar);
+      }
       t_fetch += gridDim.x;
     };
-    if (lane == 0)
-      for (int s = 0; s < S; ++s)
-        if (t_fetch < nt) issue(s);
-    __syncwarp();
+    for (int s = 0; s < S; ++s)
+      if (t_fetch < nt) issue(s);
     int slot = 0;
     uint32_t parity = 0;
     const int accumulate = a.accumulate;
@@ -312,21 +327,25 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32, PipeMinBlocks<Op>::value) 
       mbar_wait(done_s + (uint32_t)slot * 8u, parity);
       const int64_t row0 = t * TR;
       const int rows = (int)min((int64_t)TR, B - row0);
-      const float* slad = tiles + slot * tile_floats + TR * (row_floats + D);
+      const float* sx = tiles + slot * tile_floats + TR * row_floats;
+      const float* slad = sx + TR * D;
       for (int r = lane; r < rows; r += 32) {
         float* g = a.lad + row0 + r;
         *g = accumulate ? *g + slad[r] : slad[r];
       }
-      __syncwarp();
-      if (lane == 0) {
-        bulk_s2g(a.y + row0 * D, tiles_s + (uint32_t)(slot * tile_floats + TR * row_floats) * 4u, (uint32_t)(rows * D) * 4u);
-        bulk_commit();
-        if (t_fetch < nt) {
-          bulk_wait_read0();  // the store has read the tile: it may be refilled
-          issue(slot);
+      if (bulk_ok(rows)) {
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(a.y + row0 * D, tiles_s + (uint32_t)(slot * tile_floats + TR * row_floats) * 4u, (uint32_t)(rows * D) * 4u);
+          bulk_commit();
+          if (t_fetch < nt) bulk_wait_read0();  // the store has read the tile: it may be refilled
         }
+      } else {
+        float* gy = a.y + row0 * D;
+        for (int i = lane; i < rows * D; i += 32) gy[i] = sx[i];
       }
       __syncwarp();
+      if (t_fetch < nt) issue(slot);
       if (++slot == S) {
         slot = 0;
         parity ^= 1u;
@@ -470,6 +489,7 @@ inline int try_launch_tiled(const LayerArgs& a, const Op& op, int P, int D, cuda
     tiled_apply_kernel<Op, false><<<(int)grid, (consumers + 1) * 32, smem, st>>>(ta, op);
   }
   if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  last_path() = kPathTileRing;
   return 1;
 }
 
@@ -482,11 +502,11 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
                          reinterpret_cast<uintptr_t>(a.y)) & 15) == 0;
   if (!aligned || a.p_stride != row_floats || a.x_stride != D || a.y_stride != D) return 0;
   if (a.D_t + a.n_copy != D) return 0;  // whole rows are streamed: the column lists must cover the row
-  if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
   {
-    const int tiled = try_launch_tiled(a, op, P, D, st);
+    const int tiled = try_launch_tiled(a, op, P, D, st);  // any row length
     if (tiled != 0) return tiled;
   }
+  if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
   const DeviceInfo& dev = device_info();
   const LaneMap lm = lane_map(a.D_t);
   const int64_t row_bytes = (row_floats + D) * 4;
@@ -532,6 +552,7 @@ inline int try_launch_pipelined(const LayerArgs& a, const Op& op, int P, int D, 
     pipelined_apply_kernel<Op, false><<<(int)grid, warps * 32, smem, st>>>(pa, op);
   }
   if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  last_path() = kPathWarpRing;
   return 1;
 }
 
@@ -685,21 +706,37 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32) tiled_backward_kernel(cons
   }
   __syncthreads();
 
-  if (warp == NW) {  // ---- producer (one lane)
-    if (lane != 0) return;
+  if (warp == NW) {  // ---- producer warp (lane 0 moves the tiles; the other lanes only help with a ragged last tile)
     int64_t t_fetch = blockIdx.x;
-    auto issue = [&](int slot) {
+    auto bulk_ok = [&](int rows) { return ((rows * row_floats) & 3) == 0 && ((rows * D) & 3) == 0; };  // see the forward ring
+    auto issue = [&](int slot) {  // whole warp
       const int64_t row0 = t_fetch * TR;
       const int rows = (int)min((int64_t)TR, B - row0);
-      const uint32_t dst = tiles_s + (uint32_t)slot * tile_floats * 4u;
       const uint32_t bar = full_s + (uint32_t)slot * 8u;
-      const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
-      const uint32_t lbytes = (ta.gl_bulk && rows == TR) ? (uint32_t)TR * 4u : 0u;
-      mbar_expect_tx(bar, pbytes + 2 * xbytes + lbytes);
-      bulk_g2s(dst, a.params + row0 * row_floats, pbytes, bar);
-      bulk_g2s(dst + xoff, a.x + row0 * D, xbytes, bar);
-      bulk_g2s(dst + goff, a.gy + row0 * D, xbytes, bar);
-      if (lbytes) bulk_g2s(dst + loff, a.gl + row0, lbytes, bar);
+      if (bulk_ok(rows)) {
+        if (lane == 0) {
+          const uint32_t dst = tiles_s + (uint32_t)slot * tile_floats * 4u;
+          const uint32_t pbytes = (uint32_t)(rows * row_floats) * 4u, xbytes = (uint32_t)(rows * D) * 4u;
+          const uint32_t lbytes = (ta.gl_bulk && rows == TR) ? (uint32_t)TR * 4u : 0u;
+          mbar_expect_tx(bar, pbytes + 2 * xbytes + lbytes);
+          bulk_g2s(dst, a.params + row0 * row_floats, pbytes, bar);
+          bulk_g2s(dst + xoff, a.x + row0 * D, xbytes, bar);
+          bulk_g2s(dst + goff, a.gy + row0 * D, xbytes, bar);
+          if (lbytes) bulk_g2s(dst + loff, a.gl + row0, lbytes, bar);
+        }
+      } else {
+        float* d = tiles + slot * tile_floats;
+        const float* gp = a.params + row0 * row_floats;
+        const float* gx = a.x + row0 * D;
+        const float* gg = a.gy + row0 * D;
+        for (int i = lane; i < rows * row_floats; i += 32) d[i] = __ldg(gp + i);
+        for (int i = lane; i < rows * D; i += 32) {
+          d[TR * row_floats + i] = __ldg(gx + i);
+          d[TR * (row_floats + D) + i] = __ldg(gg + i);
+        }
+        __syncwarp();
+        if (lane == 0) ring_arrive(bar);
+      }
       t_fetch += gridDim.x;
     };
     for (int s = 0; s < S; ++s)
@@ -710,20 +747,29 @@ __global__ void __launch_bounds__(kTileMaxWarps * 32) tiled_backward_kernel(cons
       mbar_wait(done_s + (uint32_t)slot * 8u, parity);
       const int64_t row0 = t * TR;
       const int rows = (int)min((int64_t)TR, B - row0);
-      const uint32_t src = tiles_s + (uint32_t)slot * tile_floats * 4u;
-      bulk_s2g(a.gp + row0 * row_floats, src, (uint32_t)(rows * row_floats) * 4u);
-      bulk_s2g(a.gx + row0 * D, src + xoff, (uint32_t)(rows * D) * 4u);
-      bulk_commit();
-      if (t_fetch < nt) {
-        bulk_wait_read0();  // the stores have read the tile: it may be refilled
-        issue(slot);
+      if (bulk_ok(rows)) {
+        if (lane == 0) {
+          const uint32_t src = tiles_s + (uint32_t)slot * tile_floats * 4u;
+          bulk_s2g(a.gp + row0 * row_floats, src, (uint32_t)(rows * row_floats) * 4u);
+          bulk_s2g(a.gx + row0 * D, src + xoff, (uint32_t)(rows * D) * 4u);
+          bulk_commit();
+          if (t_fetch < nt) bulk_wait_read0();  // the stores have read the tile: it may be refilled
+        }
+      } else {
+        const float* d = tiles + slot * tile_floats;
+        float* ogp = a.gp + row0 * row_floats;
+        float* ogx = a.gx + row0 * D;
+        for (int i = lane; i < rows * row_floats; i += 32) ogp[i] = d[i];
+        for (int i = lane; i < rows * D; i += 32) ogx[i] = d[TR * row_floats + i];
       }
+      __syncwarp();
+      if (t_fetch < nt) issue(slot);
       if (++slot == S) {
         slot = 0;
         parity ^= 1u;
       }
     }
-    bulk_wait_all0();  // global writes complete before the kernel ends
+    if (lane == 0) bulk_wait_all0();  // global writes complete before the kernel ends
     return;
   }
 
@@ -819,6 +865,7 @@ inline int try_launch_tiled_backward(const LayerBwdArgs& a, const Op& op, int P,
   if (prepare_kernel(tiled_backward_kernel<Op>, smem) != FC_OK) return FC_ERR_CUDA;
   tiled_backward_kernel<Op><<<(int)grid, (consumers + 1) * 32, smem, st>>>(ta, op);
   if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  last_path() = kPathTileRing;
   return 1;
 }
 
@@ -834,11 +881,11 @@ inline int try_launch_pipelined_backward(const LayerBwdArgs& a, const Op& op, in
       a.gx_stride != D)
     return 0;
   if (a.D_t + a.n_copy != D) return 0;  // whole rows are streamed: the column lists must cover the row
-  if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
   {
-    const int tiled = try_launch_tiled_backward(a, op, P, D, st);
+    const int tiled = try_launch_tiled_backward(a, op, P, D, st);  // any row length
     if (tiled != 0) return tiled;
   }
+  if ((row_floats * 4) % 16 != 0 || (D * 4) % 16 != 0) return 0;
   const DeviceInfo& dev = device_info();
   const LaneMap lm = lane_map(a.D_t);
   const int64_t row_bytes = (row_floats + 2 * D) * 4;
@@ -875,6 +922,7 @@ inline int try_launch_pipelined_backward(const LayerBwdArgs& a, const Op& op, in
   if (prepare_kernel(pipelined_backward_kernel<Op>, smem) != FC_OK) return FC_ERR_CUDA;
   pipelined_backward_kernel<Op><<<(int)grid, warps * 32, smem, st>>>(pa, op);
   if (cudaGetLastError() != cudaSuccess) return FC_ERR_CUDA;
+  last_path() = kPathWarpRing;
   return 1;
 }
 

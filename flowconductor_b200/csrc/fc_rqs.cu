@@ -67,6 +67,8 @@ __global__ void rqs_bins_kernel(const float* __restrict__ x, int64_t x_stride, c
 
 using namespace fc;
 
+extern "C" int fc_elementwise_last_path(void) { return last_path(); }
+
 extern "C" int fc_rqs_bins(const float* x, int64_t x_row_stride, const float* params, int64_t params_row_stride, int64_t B,
                            int32_t D_t, fc_cols tcols, const fc_rqs_config* cfg, int32_t* bins, float* knot_dist,
                            void* stream) {

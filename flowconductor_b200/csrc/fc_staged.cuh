@@ -195,8 +195,16 @@ inline size_t plan_tiles(Args& a, int P) {
   return stage ? (size_t)a.tile_rows * row_floats * 4 : 0;
 }
 
+// Which skeleton the last element-wise layer call of this thread launched (fc_elementwise_last_path: tests, profiles)
+enum { kPathStaged = 0, kPathWarpRing = 1, kPathTileRing = 2 };
+inline int& last_path() {
+  static thread_local int p = -1;
+  return p;
+}
+
 template <class Op>
 inline int launch_apply(const LayerArgs& a, const Op& op, size_t smem, cudaStream_t st) {
+  last_path() = kPathStaged;
   const int grid = grid_for(a.num_tiles, smem);
   if (smem) {
     if (prepare_kernel(staged_apply_kernel<Op, true>, smem) != FC_OK) return FC_ERR_CUDA;
@@ -210,6 +218,7 @@ inline int launch_apply(const LayerArgs& a, const Op& op, size_t smem, cudaStrea
 
 template <class Op>
 inline int launch_backward(const LayerBwdArgs& a, const Op& op, size_t smem, cudaStream_t st) {
+  last_path() = kPathStaged;
   const int grid = grid_for(a.num_tiles, smem);
   if (smem) {
     if (prepare_kernel(staged_backward_kernel<Op, true>, smem) != FC_OK) return FC_ERR_CUDA;

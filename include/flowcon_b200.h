@@ -74,6 +74,10 @@ int fc_rqs_apply(const float* x, int64_t x_row_stride, const float* params, int6
                  int64_t B, int32_t D_t, fc_cols tcols, fc_cols ccols, const fc_rqs_config* cfg,
                  int32_t* status, void* stream);
 
+/* Debugging / test aid: which kernel skeleton the calling thread's last element-wise layer call (fc_*_apply,
+ * fc_*_backward) launched: 0 general strides (staged), 1 per-warp TMA ring, 2 CTA-level tile ring; -1 none yet. */
+int fc_elementwise_last_path(void);
+
 /*
  * Parity aid (not on the data path): the bin index the kernels' own arithmetic selects for every transformed element
  * — what searchsorted (utils/torchutils.py:147-149) returns inside rational_quadratic_spline (:115-118) — and
