@@ -51,7 +51,7 @@ def rqs_case(B, D, K, coupling=True, inverse=False):
 
 def set_env(**kw):
     for k in list(os.environ):
-        if k.startswith("FC_PIPE"):
+        if k.startswith("FC_PIPE") or k.startswith("FC_TILE"):
             del os.environ[k]
     for k, v in kw.items():
         os.environ[k] = str(v)
@@ -69,7 +69,7 @@ def main():
              ("rqs_fwd cfg5 D=256 K=8 coupling", rqs_case(args.B // 4, 256, 8)),
              ("rqs_fwd cfg3 D=16 K=16 autoregressive", rqs_case(args.B, 16, 16, coupling=False))]
     for name, (a, nbytes) in cases:
-        for label, env in (("staged", {"FC_PIPE": 0}), ("pipelined", {})):
+        for label, env in (("staged", {"FC_PIPE": 0, "FC_TILE": 0}), ("tile ring", {})):
             set_env(**env)
             med, best = timeit(lambda: ops.rqs_layer(*a))
             gbs = nbytes / med / 1e6
@@ -78,7 +78,7 @@ def main():
             out.append(rec)
             print(json.dumps(rec), flush=True)
         # the two variants must agree bit for bit (same element arithmetic)
-        set_env(FC_PIPE=0)
+        set_env(FC_PIPE=0, FC_TILE=0)
         y0, l0, _ = ops.rqs_layer(*a)
         set_env()
         y1, l1, _ = ops.rqs_layer(*a)
@@ -91,7 +91,7 @@ def main():
         gl = torch.randn(x.shape[0], device=x.device)
         nbytes = x.shape[0] * (2 * 4 * p.shape[1] + 3 * 4 * x.shape[1] + 4)
         res = {}
-        for label, env in (("staged", {"FC_PIPE_BWD": 0}), ("pipelined", {})):
+        for label, env in (("staged", {"FC_PIPE_BWD": 0, "FC_TILE_BWD": 0}), ("tile ring", {})):
             set_env(**env)
             os.environ.pop("FC_PIPE_BWD", None)
             for k, v in env.items():
@@ -103,7 +103,7 @@ def main():
                    "GB/s": gbs, "frac_of_measured_peak": gbs / PEAK, "bytes": nbytes}
             print(json.dumps(rec), flush=True)
         os.environ.pop("FC_PIPE_BWD", None)
-        print("  bit-identical:", all(bool(torch.equal(u, v)) for u, v in zip(res["staged"], res["pipelined"])), flush=True)
+        print("  bit-identical:", all(bool(torch.equal(u, v)) for u, v in zip(res["staged"], res["tile ring"])), flush=True)
     # sum-of-sigmoids (cfg 4 shapes: D = 32, n = 10, P = 31) forward / inverse / backward, affine coupling (16 B/element)
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(1)
@@ -118,7 +118,7 @@ def main():
             ("sos_bwd cfg4 D=32 n=10", lambda: ops.sos_layer_backward(xs, ps, gys, gls, ns), Bs * (8 * ps.shape[1] + 12 * Ds + 4))):
         med, best = timeit(fn)
         gbs = nbytes / med / 1e6
-        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best, "GB/s": gbs,
+        print(json.dumps({"kernel": name, "variant": "tile ring", "ms_median": med, "ms_best": best, "GB/s": gbs,
                           "frac_of_measured_peak": gbs / PEAK, "bytes": nbytes}), flush=True)
     xa = torch.randn(args.B * 4, 64, generator=g, device=dev)
     pa = torch.randn(args.B * 4, 64, generator=g, device=dev)
@@ -126,13 +126,13 @@ def main():
     cca = torch.arange(1, 64, 2, dtype=torch.int32, device=dev)
     med, best = timeit(lambda: ops.affine_layer(xa, pa, tca, cca, _cabi.AFFINE_BLOCKED, _cabi.SCALE_SIGMOID2, False))
     nbytes = xa.shape[0] * (4 * 64 + 4 * 64 + 4 * 64 + 4)
-    print(json.dumps({"kernel": "affine_fwd coupling D=64 (4M rows)", "variant": "pipelined", "ms_median": med, "ms_best": best,
+    print(json.dumps({"kernel": "affine_fwd coupling D=64 (4M rows)", "variant": "tile ring", "ms_median": med, "ms_best": best,
                       "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK, "bytes": nbytes}), flush=True)
     gya, gla = torch.randn_like(xa), torch.randn(xa.shape[0], device=dev)
     med, best = timeit(lambda: ops.affine_layer_backward(xa, pa, gya, gla, tca, cca, _cabi.AFFINE_BLOCKED,
                                                          _cabi.SCALE_SIGMOID2, False))
     nbytes = xa.shape[0] * (4 * 64 * 5 + 4)
-    print(json.dumps({"kernel": "affine_bwd coupling D=64 (4M rows)", "variant": "pipelined", "ms_median": med,
+    print(json.dumps({"kernel": "affine_bwd coupling D=64 (4M rows)", "variant": "tile ring", "ms_median": med,
                       "ms_best": best, "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                       "bytes": nbytes}), flush=True)
     # piecewise-linear spline, coupling shapes of cfg 2 (D = 64, 32 transformed + 32 copied, K = 8): 4 (K + 2) B/element
@@ -146,7 +146,7 @@ def main():
             ("linspline_bwd D=64 K=8 coupling", lambda: ops.linspline_layer_backward(xl, pl, gyl, gll, tca, cca, *lin),
              args.B * (4 * 64 * 3 + 4 * 256 * 2 + 4))):
         med, best = timeit(fn)
-        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
+        print(json.dumps({"kernel": name, "variant": "tile ring", "ms_median": med, "ms_best": best,
                           "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                           "bytes": nbytes}), flush=True)
     # piecewise-quadratic spline, same coupling shapes: K = 8 with linear tails -> P = 15, 4 (P + 2) B/element
@@ -158,7 +158,7 @@ def main():
             ("quadspline_bwd D=64 K=8 coupling", lambda: ops.quadspline_layer_backward(xl, pq, gyl, gll, tca, cca, *quad),
              args.B * (4 * 64 * 3 + 4 * 480 * 2 + 4))):
         med, best = timeit(fn)
-        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
+        print(json.dumps({"kernel": name, "variant": "tile ring", "ms_median": med, "ms_best": best,
                           "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                           "bytes": nbytes}), flush=True)
     # cubic spline, same coupling shapes: K = 8 -> P = 2 K + 2 = 18, 4 (P + 2) B/element (was unmeasured)
@@ -172,7 +172,7 @@ def main():
             ("cubicspline_bwd D=64 K=8 coupling", lambda: ops.cubicspline_layer_backward(xl, pc, gyl, gll, tca, cca, *quad),
              args.B * (4 * 64 * 3 + 4 * 576 * 2 + 4))):
         med, best = timeit(fn)
-        print(json.dumps({"kernel": name, "variant": "pipelined", "ms_median": med, "ms_best": best,
+        print(json.dumps({"kernel": name, "variant": "tile ring", "ms_median": med, "ms_best": best,
                           "GB/s": nbytes / med / 1e6, "frac_of_measured_peak": nbytes / med / 1e6 / PEAK,
                           "bytes": nbytes}), flush=True)
     # ActNorm (8 B/element forward; backward reads x and grad_y, writes grad_x: 12 B/element)

@@ -158,3 +158,28 @@ def test_conditional_sum_of_sigmoids_and_actnorm_and_training(dev, rows):
         (-(lad.mean()) + (y ** 2).mean()).backward()
     g.check("training step rows=%d" % rows)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("rows", [1, 37, 1500, 4099])
+@pytest.mark.parametrize("D,coupling", [(21, False), (6, True), (64, True)])
+def test_element_wise_tile_ring_stays_inside_its_buffers(dev, rows, D, coupling):
+    """The tile ring's bulk stores (whole tiles of rows that need not be 16-byte multiples) and the plain stores of a ragged
+    last tile: forward, inverse and backward of the spline layer, outputs allocated inside guard bands."""
+    from flowconductor_b200 import _cabi, ops
+
+    g0 = torch.Generator(device=dev).manual_seed(rows + D)
+    tc = torch.arange(0, D, 2, dtype=torch.int32, device=dev) if coupling else None
+    cc = torch.arange(1, D, 2, dtype=torch.int32, device=dev) if coupling else None
+    d_t = tc.numel() if coupling else D
+    x = torch.randn(rows, D, generator=g0, device=dev)
+    p = torch.randn(rows, d_t * 23, generator=g0, device=dev)
+    gy, gl = torch.randn(rows, D, generator=g0, device=dev), torch.randn(rows, generator=g0, device=dev)
+    rest = (8, _cabi.TAILS_LINEAR, False, False, -3.0, 3.0, -3.0, 3.0, 1e-3, 1e-3, 1e-3, 0.25)
+    with torch.no_grad(), GuardedAllocations() as g:
+        y, lad, _ = ops.rqs_layer(x, p, tc, cc, *rest)
+        assert _cabi.lib().fc_elementwise_last_path() == 2
+        xi, _, _ = ops.rqs_layer(y, p, tc, cc, 8, _cabi.TAILS_LINEAR, True, *rest[3:])
+        gx, gp = ops.rqs_layer_backward(x, p, gy, gl, tc, cc, *rest)
+        assert _cabi.lib().fc_elementwise_last_path() == 2
+    g.check("element-wise tile ring rows=%d D=%d" % (rows, D))
+    assert (xi - x).abs().max() < 1e-3 and torch.isfinite(gx).all() and torch.isfinite(gp).all()
