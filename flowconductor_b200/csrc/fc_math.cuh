@@ -1530,34 +1530,28 @@ FC_HD void quad_prepare(const QuadSplineParams& c, const float* u, QuadKnots<KC>
 template <int KC>
 FC_HD void quad_locate(int K, const QuadKnots<KC>& q, float pos, bool by_cdf, int& idx, float& loc, float& bw,
                        float& lcdf, float& hl, float& hr) {
+  // One pass, "last true wins": bin m is taken when pos >= its left knot (bin 0 always).  The knots are running sums of
+  // positive terms, hence monotone, so this is the count of knots <= pos that searchsorted returns; a position beyond the
+  // bumped last knot (1 + 1e-6) lands in bin K - 1 either way.  The selects depend on a comparison of values, not of the
+  // loop index, so the knot arrays stay in registers.
   idx = 0;
-  float rl = 0.f, rc = 0.f;
-#pragma unroll(KC ? 2 * KC + 2 : 4)
-  for (int m = 1; m <= K; ++m) {
-    rl += q.w[m - 1];
-    rc = fmaf(0.5f * (q.H[m - 1] + q.H[m]), q.w[m - 1], rc);
-    const float knot = m == K ? 1.f + 1e-6f : (by_cdf ? rc : rl);
-    idx += pos >= knot ? 1 : 0;
-  }
-  idx = idx > K - 1 ? K - 1 : idx;
   loc = 0.f;
   lcdf = 0.f;
-  bw = 0.f;
-  hl = 0.f;
-  hr = 0.f;
-  rl = 0.f;
-  rc = 0.f;
+  bw = q.w[0];
+  hl = q.H[0];
+  hr = q.H[1];
+  float rl = 0.f, rc = 0.f;
 #pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int m = 0; m < K; ++m) {
-    // masked accumulation (exactly one m matches; sel is 0 or 1, so the FMAs are exact): a chain of conditional
-    // assignments is turned into q.w[idx]-style indexed loads by the compiler, which forces the knot arrays into
-    // local memory
-    const float sel = m == idx ? 1.f : 0.f;
-    loc = fmaf(sel, rl, loc);
-    lcdf = fmaf(sel, rc, lcdf);
-    bw = fmaf(sel, q.w[m], bw);
-    hl = fmaf(sel, q.H[m], hl);
-    hr = fmaf(sel, q.H[m + 1], hr);
+    if (m > 0) {
+      const bool ge = pos >= (by_cdf ? rc : rl);
+      idx = ge ? m : idx;
+      loc = ge ? rl : loc;
+      lcdf = ge ? rc : lcdf;
+      bw = ge ? q.w[m] : bw;
+      hl = ge ? q.H[m] : hl;
+      hr = ge ? q.H[m + 1] : hr;
+    }
     rl += q.w[m];
     rc = fmaf(0.5f * (q.H[m] + q.H[m + 1]), q.w[m], rc);
   }
@@ -1801,28 +1795,27 @@ FC_HD void cubic_prepare(const CubicSplineParams& c, const float* u, CubicKnots<
 template <int KC>
 FC_HD void cubic_locate(int K, const CubicKnots<KC>& q, float pos, bool by_height, int& idx, float& x_lo, float& y_lo,
                         float& w, float& s, float& d0, float& d1) {
+  // one pass, "last true wins" (see quad_locate)
   idx = 0;
+  x_lo = 0.f;
+  y_lo = 0.f;
+  w = q.w[0];
+  s = q.s[0];
+  d0 = q.dv[0];
+  d1 = q.dv[1];
   float rw = 0.f, rh = 0.f;
 #pragma unroll(KC ? 2 * KC + 2 : 4)
-  for (int m = 1; m <= K; ++m) {
-    rw += q.w[m - 1];
-    rh += q.h[m - 1];
-    const float knot = m == K ? 1.f + 1e-6f : (by_height ? rh : rw);
-    idx += pos >= knot ? 1 : 0;
-  }
-  idx = idx > K - 1 ? K - 1 : idx;
-  x_lo = y_lo = w = s = d0 = d1 = 0.f;
-  rw = 0.f;
-  rh = 0.f;
-#pragma unroll(KC ? 2 * KC + 2 : 4)
   for (int m = 0; m < K; ++m) {
-    const float sel = m == idx ? 1.f : 0.f;
-    x_lo = fmaf(sel, rw, x_lo);
-    y_lo = fmaf(sel, rh, y_lo);
-    w = fmaf(sel, q.w[m], w);
-    s = fmaf(sel, q.s[m], s);
-    d0 = fmaf(sel, q.dv[m], d0);
-    d1 = fmaf(sel, q.dv[m + 1], d1);
+    if (m > 0) {
+      const bool ge = pos >= (by_height ? rh : rw);
+      idx = ge ? m : idx;
+      x_lo = ge ? rw : x_lo;
+      y_lo = ge ? rh : y_lo;
+      w = ge ? q.w[m] : w;
+      s = ge ? q.s[m] : s;
+      d0 = ge ? q.dv[m] : d0;
+      d1 = ge ? q.dv[m + 1] : d1;
+    }
     rw += q.w[m];
     rh += q.h[m];
   }
