@@ -117,10 +117,34 @@ def usable(net, a, context, *other_inputs):
     """Should this conditioner call take the tensor-core path?  `a` is the matrix the first layer multiplies."""
     if not supported_net(net, context) or wants_grad(net, a, *other_inputs):
         return False
-    if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0):
-        return False
-    # TMA operand constraints: 16-byte aligned base and row pitch
-    return a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0
+    # (the TMA operand constraints — 16-byte aligned base and row pitch — are met by `aligned_inputs` below)
+    return a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0
+
+
+def aligned_inputs(a, col_map, k_in):
+    """(a, col_map, k_in) with a 16-byte aligned base and row pitch for the TMA loads of the first layer.  A feature count that
+    is not a multiple of 4 (the tabular data sets of the reference's experiments: 6, 21, 43, 63 columns) gets a zero-padded
+    copy of the inputs — B x D floats, noise next to the conditioner — and the first layer's packed weights the matching
+    zero columns (col_map scatters the real ones)."""
+    k = a.shape[1] if k_in is None else k_in
+    if a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0 and k % 4 == 0:
+        return a, col_map, k_in
+    k4 = (a.shape[1] + 3) // 4 * 4
+    padded = a.new_zeros((a.shape[0], k4))
+    padded[:, :a.shape[1]] = a
+    if col_map is None:
+        col_map = _identity_cols(a.shape[1], a.device)
+    return padded, col_map, k4
+
+
+_identity_cache = {}
+
+
+def _identity_cols(n, device):
+    key = (n, str(device))
+    if key not in _identity_cache:
+        _identity_cache[key] = torch.arange(n, dtype=torch.int32, device=device)
+    return _identity_cache[key]
 
 
 def _param_key(net):
@@ -220,6 +244,7 @@ def hidden(net, plan, a):
 
 def params(net, a, col_map=None, k_in=None):
     """Full conditioner output [B, out_features] (final layer materialised)."""
+    a, col_map, k_in = aligned_inputs(a, col_map, k_in)
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("store",))
     n = plan.final.n_out
     n4 = (n + 3) // 4 * 4  # the store epilogue writes 16-byte vectors: round up into the zero-weight padding
@@ -241,6 +266,7 @@ def affine_layer(net, a, inputs, tcols, ccols, layout, activation, inverse, col_
                  allow_inplace=True):
     """Conditioner + affine transform for one layer (final layer fused: fc_linear_affine_apply)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
+    a, col_map, k_in = aligned_inputs(a, col_map, k_in)
     k_in = k_in if k_in is not None else a.shape[1]
     if affine_fusable(net, k_in, d_t):
         packed = affine_cond_plan_for(net, col_map, k_in, d_t, layout)
@@ -294,32 +320,38 @@ def affine_cond_plan_for(net, col_map, k_in, d_t, layout):
     return packed
 
 
+def _pad4(k_in):
+    """Input width the kernels see: `aligned_inputs` pads to a multiple of 4 columns."""
+    return None if k_in is None else (k_in + 3) // 4 * 4
+
+
 def affine_fusable(net, k_in, d_t=None):
     return FUSED_CONDITIONER and FUSED_AFFINE and k_in is not None and fcond.supported_affine_shape(
-        net.initial_layer.weight.shape[0], k_in, len(net.blocks), d_t)
+        net.initial_layer.weight.shape[0], _pad4(k_in), len(net.blocks), d_t)
 
 
-def sos_cond_plan_for(net, k_in, n_sigmoids, d_t):
+def sos_cond_plan_for(net, k_in, n_sigmoids, d_t, col_map=None):
     """PackedConditioner of `net` for the fused sum-of-sigmoids kernel, cached like the spline plans."""
     key = (_param_key(net), "sos", n_sigmoids, k_in, d_t)
     plan = getattr(net, "_fc_cond_plan", None)
     if plan is not None and plan[0] == key:
         return plan[1]
-    packed = fcond.pack_sos(net, n_sigmoids, d_t, k_in=k_in)
+    packed = fcond.pack_sos(net, n_sigmoids, d_t, col_map=col_map, k_in=k_in)
     object.__setattr__(net, "_fc_cond_plan", (key, packed))
     _generation[0] += 1
     return packed
 
 
 def sos_fusable(net, k_in, n_sigmoids, d_t=None):
-    return FUSED_CONDITIONER and fcond.supported_sos_shape(net.initial_layer.weight.shape[0], k_in, len(net.blocks),
+    return FUSED_CONDITIONER and fcond.supported_sos_shape(net.initial_layer.weight.shape[0], _pad4(k_in), len(net.blocks),
                                                            n_sigmoids, d_t)
 
 
 def sos_layer(net, a, inputs, n_sigmoids, offset):
     """Conditioner + sum-of-sigmoids transform (forward) as one kernel; returns (outputs, logabsdet).  `a` feeds the
     conditioner (context / MADE inputs), `inputs` the bijection."""
-    packed = sos_cond_plan_for(net, a.shape[1], int(n_sigmoids), inputs.shape[1])
+    a, col_map, k_in = aligned_inputs(a, None, None)
+    packed = sos_cond_plan_for(net, a.shape[1], int(n_sigmoids), inputs.shape[1], col_map)
     x = inputs if inputs.stride(1) == 1 else inputs.contiguous()
     y = torch.empty_like(x)
     consume_consent()
@@ -334,13 +366,14 @@ def conditioner_fusable(net, k_in, spline, d_t=None):
     layer's bias vector must fit in the kernel's shared memory)."""
     num_bins, tails = (spline, "linear") if isinstance(spline, int) else (int(spline.num_bins), spline.tails)
     return FUSED_CONDITIONER and k_in is not None and fcond.supported_shape(
-        net.initial_layer.weight.shape[0], k_in, len(net.blocks), num_bins, tails, d_t)
+        net.initial_layer.weight.shape[0], _pad4(k_in), len(net.blocks), num_bins, tails, d_t)
 
 
 def rqs_layer(net, a, inputs, spline, tcols, ccols, inverse, hidden_for_scaling, col_map=None, k_in=None,
               allow_inplace=True):
     """Conditioner + spline for one layer; returns (outputs, logabsdet)."""
     d_t = tcols.numel() if tcols is not None else inputs.shape[1]
+    a, col_map, k_in = aligned_inputs(a, col_map, k_in)
     k_in = k_in if k_in is not None else a.shape[1]
     cfg, tails = spline.config(inverse, hidden_for_scaling)
     if conditioner_fusable(net, k_in, spline, d_t):

@@ -22,7 +22,7 @@ def main():
     worst, ran, skipped = 0.0, 0, 0
     for case in range(n_cases):
         fam = random.choice(["coupling", "coupling", "maf", "cond_rqs", "cond_sos", "lin", "quad", "cubic", "affine", "maf_affine"])
-        D = random.choice([4, 8, 12, 16, 32, 64, 100])
+        D = random.choice([4, 6, 8, 12, 16, 21, 32, 43, 63, 64, 100])
         H = random.choice([64, 68, 100, 128, 132, 200, 256])
         blocks = random.choice([1, 2, 3, 4])
         K = random.choice([8, 10, 16])

@@ -332,6 +332,51 @@ def test_affine_layers_run_in_the_fused_conditioner(dev, kind, features, hidden,
                 assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3 and (lad - lb).abs().max() < 5e-2
 
 
+@pytest.mark.parametrize("features", [6, 21, 43, 63])
+@pytest.mark.parametrize("kind", ["coupling_rqs", "maf_rqs", "coupling_affine", "cond_sos", "coupling_quadratic"])
+def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kind, features, monkeypatch):
+    """The tabular data sets of the reference's experiments have 6, 8, 21, 43 and 63 columns: the conditioner inputs are
+    zero-padded to a 16-byte row pitch (tensorcore.aligned_inputs) instead of falling back to the torch conditioner."""
+    torch.manual_seed(features)
+    net = lambda i, o: ResidualNet(i, o, hidden_features=128, num_blocks=2)  # noqa: E731
+    mask = workloads.make_mask(features, "alternating_even")
+    ctx, want = None, None
+    if kind == "coupling_rqs":
+        layer = transforms.PiecewiseRationalQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
+        want = "fc_conditioner_rqs_apply"
+    elif kind == "maf_rqs":
+        layer = transforms.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features, 128, num_bins=8, tails="linear",
+                                                                                   tail_bound=3.0)
+        want = "fc_conditioner_rqs_apply"
+    elif kind == "coupling_affine":
+        layer = transforms.AffineCouplingTransform(mask, net)
+        want = "fc_conditioner_affine_apply"
+    elif kind == "cond_sos":
+        layer = transforms.ConditionalSumOfSigmoidsTransform(features, 128, context_features=5, n_sigmoids=10, num_blocks=2)
+        ctx = torch.randn(1234, 5, device=dev)
+        want = "fc_conditioner_sos_apply"
+    else:
+        layer = transforms.PiecewiseQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
+        want = "fc_linear_apply"
+    layer = layer.to(dev).eval()
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+        x = torch.randn(1234, features, device=dev)
+        _cabi.STATS.reset()
+        y, lad = layer(x, ctx)
+        assert _cabi.STATS.counts.get(want, 0) >= 1, _cabi.STATS.counts
+        monkeypatch.setattr(tensorcore, "ENABLED", False)
+        yu, ladu = layer(x, ctx)
+        monkeypatch.setattr(tensorcore, "ENABLED", True)
+        rel = ((y - yu).abs() / yu.abs().clamp_min(1.0)).flatten()
+        assert torch.quantile(rel, 0.999) < 1e-4 and rel.max() < 5e-2, (kind, features, float(rel.max()))
+        assert torch.quantile((lad - ladu).abs(), 0.99) < 2e-3
+        if kind != "cond_sos":
+            xi, ladi = layer.inverse(y, ctx)
+            assert (xi - x).abs().max() < 5e-3 and torch.quantile((ladi + lad).abs(), 0.99) < 5e-3
+
+
 def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypatch):
     """H = 64 ResidualNet (cfg2_tc_small): zero-padded to 128 at pack time, one fused launch per layer, same numbers as the
     per-layer kernels."""
