@@ -471,7 +471,7 @@ def run_cfg2(args, wl):
         alg_flops, exec_flops = alg_row * B, exec_row * B
         c_each = (c_ms / n_c) if n_c else None
         roofline = {"bound": "tensor",
-                    "kernel": "conditioner_f16x3_kernel<8, 24, 2> (fc_conditioner_rqs_apply: initial layer, 2 residual "
+                    "kernel": "conditioner_f16x3_kernel<CondRqs<8>, 24, 2, false> (fc_conditioner_rqs_apply: initial layer, 2 residual "
                               "blocks, final layer and RQ spline of one flow layer in one persistent tcgen05 kernel)",
                     "achieved": (alg_flops / (c_each * 1e-3) / 1e12) if c_each else None, "peak": tpeak,
                     "unit": "TFLOP/s", "frac": (alg_flops / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
@@ -770,7 +770,7 @@ def run_cfg5(args, wl):
                     "h2d_bytes_per_step": passes * host_rows * D * 4, "d2h_bytes_per_step": passes * host_rows * 4,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conditioner_f16x3_kernel<8, 24, 2> (fc_conditioner_rqs_apply)",
+            "roofline": {"bound": "tensor", "kernel": "conditioner_f16x3_kernel<CondRqs<8>, 24, 2, false> (fc_conditioner_rqs_apply)",
                          "achieved": (alg_row * rows_per_launch / (c_each * 1e-3) / 1e12) if c_each else None,
                          "peak": tpeak, "unit": "TFLOP/s",
                          "frac": (alg_row * rows_per_launch / (c_each * 1e-3) / 1e12 / tpeak) if c_each else None,
