@@ -117,3 +117,40 @@ def test_per_warp_ring_is_still_selectable(dev):
     finally:
         _env()
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("B,D", [(4099, 64), (1000, 21)])
+def test_c_abi_accumulate_in_place_and_status(dev, B, D):
+    """Straight through the C ABI (fc_rqs_apply): accumulate_logabsdet = 1 adds to the caller's vector (the producer warp's
+    read-modify-write), y == x works in place (the tile is complete in shared memory before its rows are stored), and a
+    spline without tails reports inputs outside the domain through the status word — tile ring and general kernel alike."""
+    import ctypes
+
+    from flowconductor_b200 import ops as _ops
+
+    lib = _cabi.lib()
+    g = torch.Generator(device=dev).manual_seed(B + D)
+    x = torch.rand(B, D, generator=g, device=dev) * 0.98 + 0.01
+    x[B // 2, D // 3] = 1.7  # outside [0, 1]
+    p = torch.randn(B, D * 25, generator=g, device=dev)
+    cfg = _ops._cfg(8, _cabi.TAILS_NONE, False, False, 0.0, 1.0, 0.0, 1.0, 1e-3, 1e-3, 1e-3, 1.0)
+    res = {}
+    try:
+        for name, env in (("tile", {}), ("staged", {"FC_TILE": 0, "FC_PIPE": 0})):
+            _env(**env)
+            y = x.clone()
+            lad = torch.full((B,), 3.0, device=dev)
+            status = torch.zeros((1,), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.fc_rqs_apply(y.data_ptr(), D, p.data_ptr(), p.shape[1], y.data_ptr(), D, lad.data_ptr(), 1, B, D,
+                                      _cabi.cols(None), _cabi.cols(None), ctypes.byref(cfg), status.data_ptr(),
+                                      _cabi.stream_ptr(dev))
+            assert rc == 0
+            assert lib.fc_elementwise_last_path() == (TILE_RING if name == "tile" else STAGED)
+            res[name] = (y, lad, int(status.item()))
+    finally:
+        _env()
+    fresh = ops.rqs_layer(x, p, None, None, 8, _cabi.TAILS_NONE, False, False, 0.0, 1.0, 0.0, 1.0, 1e-3, 1e-3, 1e-3, 1.0)
+    assert torch.equal(res["tile"][0], res["staged"][0]) and torch.equal(res["tile"][1], res["staged"][1])
+    assert torch.equal(res["tile"][0], fresh[0]) and torch.allclose(res["tile"][1], fresh[1] + 3.0, rtol=0, atol=1e-5)
+    assert res["tile"][2] == res["staged"][2] != 0
