@@ -457,6 +457,7 @@ inline int try_launch_tiled(const LayerArgs& a, const Op& op, int P, int D, cuda
       if (passes > 1) --passes;
       else if (stages > 2) --stages;
       else if (ctas_per_sm > 1) --ctas_per_sm;
+      else if (consumers > 1) consumers = (consumers + 1) / 2;  // very long rows: fewer rows per tile
       else return 0;
     }
     if (a.D_t == 32 ? prepare_kernel(tiled_apply_kernel<Op, true>, (size_t)smem_need(passes, stages)) != FC_OK
@@ -839,6 +840,7 @@ inline int try_launch_tiled_backward(const LayerBwdArgs& a, const Op& op, int P,
       if (passes > 1) --passes;
       else if (stages > 2) --stages;
       else if (ctas_per_sm > 1) --ctas_per_sm;
+      else if (consumers > 1) consumers = (consumers + 1) / 2;  // very long rows: fewer rows per tile
       else return 0;
     }
     const size_t smem = (size_t)smem_need(passes, stages);

@@ -154,3 +154,25 @@ def test_c_abi_accumulate_in_place_and_status(dev, B, D):
     assert torch.equal(res["tile"][0], res["staged"][0]) and torch.equal(res["tile"][1], res["staged"][1])
     assert torch.equal(res["tile"][0], fresh[0]) and torch.allclose(res["tile"][1], fresh[1] + 3.0, rtol=0, atol=1e-5)
     assert res["tile"][2] == res["staged"][2] != 0
+
+
+def test_very_long_rows_shrink_the_tile_instead_of_leaving_the_ring(dev):
+    """256 transformed features x 23 parameters = 23.5 KB per row: a tile of 8 rows no longer fits twice in shared memory, so
+    the launcher halves the consumer warps (rows per tile) rather than falling back."""
+    lib = _cabi.lib()
+    g = torch.Generator(device=dev).manual_seed(9)
+    B, D = 300, 256
+    P, fwd, bwd = _family("rqs", D, None, None)
+    x = torch.randn(B, D, generator=g, device=dev)
+    p = torch.randn(B, D * P, generator=g, device=dev)
+    gy, gl = torch.randn(B, D, generator=g, device=dev), torch.randn(B, generator=g, device=dev)
+    try:
+        _env()
+        got = fwd(x, p, False) + bwd(x, p, gy, gl)
+        assert lib.fc_elementwise_last_path() == TILE_RING
+        _env(FC_TILE=0, FC_PIPE=0)
+        want = fwd(x, p, False) + bwd(x, p, gy, gl)
+    finally:
+        _env()
+    for u, v in zip(got, want):
+        assert torch.equal(u, v)
