@@ -26,7 +26,7 @@ EXPORTS = ["fc_rqs_apply", "fc_rqs_backward", "fc_rqs_bins", "fc_linspline_apply
            "fc_sos_backward", "fc_stdnormal_log_prob", "fc_linear_pack", "fc_linear_apply", "fc_linear_rqs_apply",
            "fc_linear_affine_apply", "fc_linear_splitk_apply", "fc_linear_splitk_t_apply", "fc_linear_transpose",
            "fc_linear_pack_transposed", "fc_linear_debug_profile",
-           "fc_elementwise_last_path", "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_sos_apply", "fc_conditioner_affine_apply", "fc_conditioner_error", "fc_conditioner_profile",
+           "fc_elementwise_last_path", "fc_conditioner_layer_bytes", "fc_conditioner_pack_layer", "fc_conditioner_rqs_apply", "fc_conditioner_sos_apply", "fc_conditioner_affine_apply", "fc_conditioner_store_apply", "fc_conditioner_error", "fc_conditioner_profile",
            "fc_actnorm_apply", "fc_actnorm_workspace_floats", "fc_actnorm_backward",
            "fc_made_inverse_smem_bytes", "fc_made_inverse_profile", "fc_made_inverse_rqs", "fc_made_inverse_affine",
            "fc_made_inverse_sos", "fc_made_inverse_linspline", "fc_made_inverse_quadspline", "fc_made_inverse_cubicspline",
@@ -138,6 +138,7 @@ def lib():
                                                Cols, Cols, i32, f32, vp]
         L.fc_conditioner_affine_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, vp, i64, vp, i32,
                                                   i32, Cols, Cols, i32, i32, vp]
+        L.fc_conditioner_store_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, i32, i32, vp]
         L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.fc_conditioner_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
         L.fc_actnorm_apply.argtypes = [vp, i64, vp, vp, vp, i64, vp, i32, i64, i32, i32, vp]

@@ -101,6 +101,9 @@ struct CondArgs {
   int hand_period;   // every hand_period-th final N tile a row thread hands ALL its features to the bijection warps (0: never)
   float sos_offset;  // sum-of-sigmoids bijection: added to the outputs (autoregressive.py:309: -0.5; conditional.py: 0)
   int affine_activation, affine_inverse;  // affine bijection (FC_SCALE_*, direction)
+  float* params_out;      // CondStore: the final layer's outputs [M][D_t * store_P] instead of a bijection
+  long long ldp;
+  int store_P;
   int32_t* status;
   int32_t* error;  // device word: 0, or the code of the first wait that timed out
 };
@@ -111,6 +114,7 @@ struct CondArgs {
 template <int KC>
 struct CondRqs {  // rational-quadratic spline, KC bins, linear tails (rational_quadratic.py:13-181)
   static constexpr int G = 1;
+  static constexpr bool kStore = false;
   template <int PPAD>
   static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
                                               unsigned& status) {
@@ -124,6 +128,7 @@ struct CondRqs {  // rational-quadratic spline, KC bins, linear tails (rational_
 template <int NC>
 struct CondSos {  // sum of NC sigmoids + extended softplus (adaptive_sigmoids.py:111-142, nonlinearities.py:543-552), forward
   static constexpr int G = 1;
+  static constexpr bool kStore = false;
   template <int PPAD>
   static __device__ __forceinline__ void eval(const CondArgs& a, float x, const float (&p)[PPAD], float& y, float& lad,
                                               unsigned&) {
@@ -293,10 +298,27 @@ struct CondSmem {
 
 struct CondAffine {  // y = x * scale(raw) + shift and its inverse (coupling.py:224-252, autoregressive.py:97-129): a slot of 24
   static constexpr int G = 12;  // columns holds (raw scale, shift) of 12 consecutive features
+  static constexpr bool kStore = false;
   // feature g of the slot
   template <int PPAD>
   static __device__ __forceinline__ void eval_g(const CondArgs& a, int g, float x, const float (&p)[PPAD], float& y, float& lad) {
     affine_eval(x, p[2 * g], p[2 * g + 1], a.affine_activation, a.affine_inverse, y, lad);
+  }
+};
+
+// No bijection: the conditioner's outputs are written out, store_P per 48-column accumulator slot (ResidualNet.forward /
+// MADE.forward as ONE launch, for the bijections that run as element-wise kernels afterwards).  A row thread owns (row, 48
+// columns): stored from there, 32 lanes would write 4 bytes each a row pitch apart (measured: 2.5x slower than the per-layer
+// kernels).  Instead EVERY final tile goes through the shared-memory parameter tile (HAND, period 1; its column stride is
+// padded to 129 words here so that both the row threads' column-wise writes and the row-wise reads below are free of bank
+// conflicts) and the four bijection warps copy it out row by row, 32 lanes on 32 consecutive outputs of one row.
+struct CondStore {
+  static constexpr int G = 1;
+  static constexpr bool kStore = true;
+  template <int PPAD>
+  static __device__ __forceinline__ void eval(const CondArgs&, float, const float (&)[PPAD], float& y, float& lad, unsigned&) {
+    y = 0.f;
+    lad = 0.f;
   }
 };
 
@@ -313,6 +335,8 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
   // bijection warps wait 60 % of the time —, so part of the row threads' splines moves there).
   constexpr int NF_OWN = 1;
   constexpr int G = Bij::G;           // features per slot (see the bijection policies)
+  constexpr int kPS = Bij::kStore ? kCM + 1 : kCM;  // column stride (words) of the handed-over parameter tile
+  static_assert(!Bij::kStore || (HAND && NF == 1), "the store variant hands every tile over");
   static_assert(NF >= 1 && NF * 2 * PPAD == 96, "final N tile: 96 columns");
   static_assert(G == 1 || 2 * G <= PPAD, "grouped features: two parameters each");
   // (compile-time "never" for tiles of several features per thread: measured to be best there, and the kernel keeps
@@ -751,7 +775,9 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           int xc = -1;
           float xv = 0.f;
           float xg[G > 1 ? G : 1];
-          if constexpr (G == 1) {
+          if constexpr (Bij::kStore) {
+            xc = live ? fg : -1;  // nothing to read
+          } else if constexpr (G == 1) {
             xc = live ? (a.tcols ? __ldg(a.tcols + fg) : fg) : -1;
             xv = (valid && live) ? __ldg(a.x + row * a.ldx + xc) : 0.f;
           } else {
@@ -805,10 +831,10 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
             CPROF_T0(t_h);
             const uint32_t b = pt & 1u, nw = pt >> 1;  // buffer, and how often it has been written before
             if (!cond_wait(pempty_bar(b), (nw & 1u) ^ 1u, abort_s)) COND_FAIL(10);
-            float* pcol = hs + (b * (2 * NF * PPAD) + half * (NF * PPAD)) * kCM + rl;
+            float* pcol = hs + (b * (2 * NF * PPAD) + half * (NF * PPAD)) * kPS + rl;
 #pragma unroll
             for (int j = 0; j < NF * PPAD; ++j) {
-              if (j >= nown * PPAD) pcol[(j - nown * PPAD) * kCM] = pv[j];
+              if (j >= nown * PPAD) pcol[(j - nown * PPAD) * kPS] = pv[j];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pfull_bar(b));  // release: orders the warp's stores above
@@ -881,6 +907,48 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       for (int nt = 0; nt < n_final; ++nt) {
         const int nown = tile_own(nt), nhand = NF - nown;
         if (nhand == 0) continue;
+        if constexpr (Bij::kStore) {
+          // the whole 96-column tile of this warp's 32 rows, row by row: lanes on consecutive outputs
+          const uint32_t b = pt & 1u;
+          {
+            CPROF_T0(t_w);
+            if (!cond_wait(pfull_bar(b), (pt >> 1) & 1u, abort_s)) COND_FAIL(11);
+            CPROF_ADD(b_wait, t_w);
+          }
+          CPROF_T0(t_s);
+          const int rl0 = r & ~31;
+          const long long grow0 = row - (r & 31);
+          const int nrows = (int)min((long long)32, a.M - grow0);  // rows of this warp inside the batch (<= 0: none)
+          const float* tile_s = hs + (b * (2 * NF * PPAD)) * kPS + rl0;
+          const int P = a.store_P;
+#pragma unroll
+          for (int cc = 0; cc < 2 * NF * PPAD; cc += 32) {
+            const int c = cc + lane;
+            const int slot = c / PPAD, j = c - slot * PPAD;
+            const int feature = nt * FEATS + slot;
+            const bool live = j < P && feature < a.D_t;
+            float* out = a.params_out + grow0 * a.ldp + (long long)feature * P + j;
+            const float* src = tile_s + c * kPS;
+            // eight shared-memory loads in flight, then eight predicated stores (a loop of guarded load-store pairs compiles to
+            // one branch region per element with the load latency exposed every time: 120 cycles per element)
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = src[r0 + u];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (live && r0 + u < nrows) out[0] = v[u];
+                out += a.ldp;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pempty_bar(b));
+          ++pt;
+          CPROF_ADD(b_work, t_s);
+          continue;
+        }
         // the features the two row threads of this row hand over: the last nhand of each half of the N tile
         float xv[2 * NF * G];
         int xc[2 * NF];  // G == 1: the column; G > 1: the slot
@@ -950,7 +1018,9 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
       {
         const float* lx = ladx + (tcount & 1u) * (2 * kCM);
         const float tot = (lx[r] + lx[kCM + r]) + lad_acc;
-        if (valid) a.lad[row] = a.accumulate ? a.lad[row] + tot : tot;
+        if constexpr (!Bij::kStore) {
+          if (valid) a.lad[row] = a.accumulate ? a.lad[row] + tot : tot;
+        }
       }
       ++tcount;
     }
@@ -1118,10 +1188,10 @@ extern "C" int fc_conditioner_error(int32_t* out) {
 static int cond_build_args(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,
                            int64_t x_row_stride, float* y, int64_t y_row_stride, float* logabsdet,
                            int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int ppad, int hand_default,
-                           int32_t* status, CondArgs& args, int group = 1) {
+                           int32_t* status, CondArgs& args, int group = 1, bool store = false) {
   if (!net || !net->weights || net->n_layers < 2 || net->n_layers > kMaxCondLayers) return FC_ERR_INVALID_ARGUMENT;
   if (B < 0 || D_t <= 0) return FC_ERR_INVALID_ARGUMENT;
-  if (B > 0 && (!a || !x || !y || !logabsdet)) return FC_ERR_INVALID_ARGUMENT;
+  if (B > 0 && (!a || (!store && (!x || !y || !logabsdet)))) return FC_ERR_INVALID_ARGUMENT;
   if (B >= ((int64_t)1 << 31)) return FC_ERR_UNSUPPORTED;
   if (tcols.idx && tcols.n != D_t) return FC_ERR_INVALID_ARGUMENT;
   if (net->hidden != 128 && net->hidden != 256) return FC_ERR_UNSUPPORTED;
@@ -1234,6 +1304,25 @@ extern "C" int fc_conditioner_affine_apply(const fc_conditioner* net, const floa
   cudaStream_t st = (cudaStream_t)stream;
   if (net->hidden == 256) return launch_conditioner<CondAffine, 24, 2>(args, st);
   return launch_conditioner<CondAffine, 24, 1>(args, st);
+}
+
+extern "C" int fc_conditioner_store_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, float* params,
+                                          int64_t params_row_stride, int32_t D_t, int32_t params_per_feature, void* stream) {
+  if (params_per_feature <= 0 || params_per_feature > 48) return FC_ERR_UNSUPPORTED;
+  if (B > 0 && !params) return FC_ERR_INVALID_ARGUMENT;
+  if (D_t > 0 && params_row_stride < (int64_t)D_t * params_per_feature) return FC_ERR_INVALID_ARGUMENT;
+  CondArgs args{};
+  fc_cols none{nullptr, 0};
+  int rc = cond_build_args(net, a, lda, B, nullptr, 0, nullptr, 0, nullptr, 0, D_t, none, none, 48, 1, nullptr, args, 1, true);
+  if (rc != FC_OK) return rc;
+  if (B == 0) return FC_OK;
+  args.hand_period = 1;  // every tile leaves through the shared-memory parameter tile
+  args.params_out = params;
+  args.ldp = params_row_stride;
+  args.store_P = params_per_feature;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (net->hidden == 256) return launch_conditioner<CondStore, 48, 2, true>(args, st);
+  return launch_conditioner<CondStore, 48, 1, true>(args, st);
 }
 
 extern "C" int fc_conditioner_sos_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, const float* x,

@@ -245,6 +245,16 @@ def hidden(net, plan, a):
 def params(net, a, col_map=None, k_in=None):
     """Full conditioner output [B, out_features] (final layer materialised)."""
     a, col_map, k_in = aligned_inputs(a, col_map, k_in)
+    k = k_in if k_in is not None else a.shape[1]
+    if store_fusable(net, k):  # the whole conditioner as one launch
+        key = (_param_key(net), "store", k)
+        plan = getattr(net, "_fc_cond_plan", None)
+        if plan is None or plan[0] != key:
+            plan = (key, fcond.pack_store(net, col_map=col_map, k_in=k))
+            object.__setattr__(net, "_fc_cond_plan", plan)
+            _generation[0] += 1
+        out = torch.empty((a.shape[0], net.final_layer.weight.shape[0]), dtype=a.dtype, device=a.device)
+        return fcond.store_apply(plan[1], a, out)
     plan = plan_for(net, col_map, k_in if k_in is not None else a.shape[1], ("store",))
     n = plan.final.n_out
     n4 = (n + 3) // 4 * 4  # the store epilogue writes 16-byte vectors: round up into the zero-weight padding
@@ -320,6 +330,15 @@ def affine_cond_plan_for(net, col_map, k_in, d_t, layout):
     return packed
 
 
+FUSED_STORE = os.environ.get("FC_FUSED_STORE", "1") != "0"  # A/B switch: fc_conditioner_store_apply behind `params`
+FUSED_SOS = os.environ.get("FC_FUSED_SOS", "1") != "0"      # A/B: sum of sigmoids inside the conditioner kernel, or store + layer kernel
+
+
+def store_fusable(net, k_in):
+    return FUSED_CONDITIONER and FUSED_STORE and fcond.supported_store_shape(
+        net.initial_layer.weight.shape[0], _pad4(k_in), len(net.blocks), net.final_layer.weight.shape[0])
+
+
 def _pad4(k_in):
     """Input width the kernels see: `aligned_inputs` pads to a multiple of 4 columns."""
     return None if k_in is None else (k_in + 3) // 4 * 4
@@ -343,7 +362,7 @@ def sos_cond_plan_for(net, k_in, n_sigmoids, d_t, col_map=None):
 
 
 def sos_fusable(net, k_in, n_sigmoids, d_t=None):
-    return FUSED_CONDITIONER and fcond.supported_sos_shape(net.initial_layer.weight.shape[0], _pad4(k_in), len(net.blocks),
+    return FUSED_CONDITIONER and FUSED_SOS and fcond.supported_sos_shape(net.initial_layer.weight.shape[0], _pad4(k_in), len(net.blocks),
                                                            n_sigmoids, d_t)
 
 

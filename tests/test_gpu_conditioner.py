@@ -332,6 +332,11 @@ def test_affine_layers_run_in_the_fused_conditioner(dev, kind, features, hidden,
                 assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3 and (lad - lb).abs().max() < 5e-2
 
 
+def fcond_store_ok(net):
+    from flowconductor_b200 import conditioner as fcond
+    return fcond.store_layout(net.final_layer.weight.shape[0]) is not None
+
+
 @pytest.mark.parametrize("features", [6, 21, 43, 63])
 @pytest.mark.parametrize("kind", ["coupling_rqs", "maf_rqs", "coupling_affine", "cond_sos", "coupling_quadratic"])
 def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kind, features, monkeypatch):
@@ -357,7 +362,7 @@ def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kin
         want = "fc_conditioner_sos_apply"
     else:
         layer = transforms.PiecewiseQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
-        want = "fc_linear_apply"
+        want = "fc_conditioner_store_apply" if fcond_store_ok(layer.transform_net) else "fc_linear_apply"
     layer = layer.to(dev).eval()
     with torch.no_grad():
         for p in layer.parameters():
@@ -375,6 +380,64 @@ def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kin
         if kind != "cond_sos":
             xi, ladi = layer.inverse(y, ctx)
             assert (xi - x).abs().max() < 5e-3 and torch.quantile((ladi + lad).abs(), 0.99) < 5e-3
+
+
+@pytest.mark.parametrize("kind,features,hidden,blocks,rows", [
+    ("coupling_quadratic", 64, 256, 2, 3001), ("coupling_linear", 30, 128, 1, 777), ("coupling_cubic", 12, 64, 3, 256),
+    ("maf_quadratic", 16, 256, 2, 4096), ("cond_sos_inverse", 32, 64, 2, 1500), ("maf_linear", 21, 100, 2, 1)])
+def test_whole_conditioner_store_kernel(dev, kind, features, hidden, blocks, rows, monkeypatch):
+    """`tensorcore.params` as ONE launch (fc_conditioner_store_apply: ResidualNet.forward resnet.py:92-100 / MADE.forward
+    made.py:274-283 with the outputs written out) for the bijections that run as element-wise kernels: against the per-layer
+    tensor-core kernels and the torch conditioner."""
+    torch.manual_seed(features * 3 + hidden)
+    net = lambda i, o: ResidualNet(i, o, hidden_features=hidden, num_blocks=blocks)  # noqa: E731
+    mask = workloads.make_mask(features, "alternating_even")
+    ctx = None
+    if kind == "coupling_quadratic":
+        layer = transforms.PiecewiseQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
+    elif kind == "coupling_linear":
+        layer = transforms.PiecewiseLinearCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
+    elif kind == "coupling_cubic":
+        layer = transforms.PiecewiseCubicCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
+    elif kind == "maf_quadratic":
+        layer = transforms.MaskedPiecewiseQuadraticAutoregressiveTransform(features, hidden, num_bins=8, tails="linear",
+                                                                           tail_bound=3.0, num_blocks=blocks)
+    elif kind == "maf_linear":
+        layer = transforms.MaskedPiecewiseLinearAutoregressiveTransform(8, features, hidden, num_blocks=blocks)
+    else:
+        layer = transforms.ConditionalSumOfSigmoidsTransform(features, hidden, context_features=8, n_sigmoids=10,
+                                                             num_blocks=blocks)
+        ctx = torch.randn(rows, 8, device=dev)
+    layer = layer.to(dev).eval()
+    inverse = kind == "cond_sos_inverse"
+    fn = layer.inverse if inverse else layer
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+        x = torch.rand(rows, features, device=dev) if kind == "maf_linear" else torch.randn(rows, features, device=dev)
+        _cabi.STATS.reset()
+        y, lad = fn(x, ctx)
+        assert _cabi.STATS.counts.get("fc_conditioner_store_apply", 0) == 1, _cabi.STATS.counts
+        assert not any(k.startswith("fc_linear_") for k in _cabi.STATS.counts), _cabi.STATS.counts
+        monkeypatch.setattr(tensorcore, "FUSED_STORE", False)
+        yp, ladp = fn(x, ctx)
+        monkeypatch.setattr(tensorcore, "ENABLED", False)
+        yu, ladu = fn(x, ctx)
+    for (b, lb) in ((yp, ladp), (yu, ladu)):
+        rel = ((y - b).abs() / b.abs().clamp_min(1.0)).flatten()
+        assert torch.quantile(rel, 0.999) < 1e-4 and rel.max() < 5e-2, (kind, float(rel.max()))
+        assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3
+
+
+def test_store_layout_wastes_few_accumulator_columns():
+    from flowconductor_b200 import conditioner as fcond
+    assert fcond.store_layout(992) == (32, 31) and fcond.store_layout(480) == (48, 10)
+    assert fcond.store_layout(97) is None  # prime: one output per 48-column slot -> the per-layer kernels
+    for n in range(1, 3000):
+        lay = fcond.store_layout(n)
+        if lay is not None:
+            P, d_t = lay
+            assert P * d_t == n and 24 <= P <= 48
 
 
 def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypatch):
