@@ -138,7 +138,7 @@ def lib():
                                                Cols, Cols, i32, f32, vp]
         L.fc_conditioner_affine_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, vp, i64, vp, i32,
                                                   i32, Cols, Cols, i32, i32, vp]
-        L.fc_conditioner_store_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, i32, i32, vp]
+        L.fc_conditioner_store_apply.argtypes = [ctypes.POINTER(Conditioner), vp, i64, i64, vp, i64, i32, vp]
         L.fc_conditioner_error.argtypes = [ctypes.POINTER(ctypes.c_int32)]
         L.fc_conditioner_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
         L.fc_actnorm_apply.argtypes = [vp, i64, vp, vp, vp, i64, vp, i32, i64, i32, i32, vp]

@@ -112,20 +112,10 @@ def supported_affine_shape(hidden, k_in, num_blocks, d_t=None):
 STORE_PPAD = 48
 
 
-def store_layout(n_out):
-    """How `fc_conditioner_store_apply` walks a final layer of n_out outputs: (P, d_t) with n_out = d_t * P and P <= 48
-    outputs per 48-column accumulator slot — the largest such divisor wastes the fewest padding columns; None if more than
-    half would be padding (the per-layer kernels take those)."""
-    for P in range(STORE_PPAD, 0, -1):
-        if n_out % P == 0:
-            return (P, n_out // P) if 2 * P >= STORE_PPAD else None
-    return None
-
-
 def supported_store_shape(hidden, k_in, num_blocks, n_out):
-    lay = store_layout(n_out)
-    return (lay is not None and padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
-            and 1 <= num_blocks <= MAX_BLOCKS and _vectors_fit(hidden, num_blocks, STORE_PPAD, lay[1]))
+    """`fc_conditioner_store_apply`: any final width (padded to whole 96-column tiles)."""
+    return (n_out > 0 and padded_hidden(hidden) is not None and 0 < k_in <= MAX_K_IN and k_in % 4 == 0
+            and 1 <= num_blocks <= MAX_BLOCKS and _vectors_fit(hidden, num_blocks, STORE_PPAD, (n_out + 47) // 48))
 
 
 def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None, final_row_map=None, group=1):
@@ -143,7 +133,7 @@ def pack(net, P, ppad, d_t, col_map=None, k_in=None, num_bins=None, final_row_ma
     nb = len(net.blocks)
     if hidden is None or not (0 < k_in <= MAX_K_IN and k_in % 4 == 0 and 1 <= nb <= MAX_BLOCKS) or 96 % ppad or P > ppad:
         raise ValueError("conditioner shape not supported by the fused kernel")
-    if fin.weight.shape[0] != d_t * P:
+    if final_row_map is None and fin.weight.shape[0] != d_t * P:
         raise ValueError("final layer has {} outputs, expected {} x {}".format(fin.weight.shape[0], d_t, P))
     feats = 96 // ppad * group
     n_final_tiles = (d_t + feats - 1) // feats
@@ -273,13 +263,11 @@ def affine_apply(packed, a, x, y, logabsdet, accumulate, d_t, tcols, ccols, acti
 
 
 def pack_store(net, col_map=None, k_in=None):
-    """`pack` for `fc_conditioner_store_apply` (the conditioner's outputs, no bijection)."""
-    lay = store_layout(net.final_layer.weight.shape[0])
-    if lay is None:
-        raise ValueError("conditioner shape not supported by the fused kernel")
-    P, d_t = lay
-    packed = pack(net, P, STORE_PPAD, d_t, col_map=col_map, k_in=k_in)
-    packed.store = (d_t, P)
+    """`pack` for `fc_conditioner_store_apply` (the conditioner's outputs, no bijection): final-layer rows in their own order."""
+    n_out = net.final_layer.weight.shape[0]
+    rm = torch.arange(n_out, dtype=torch.int32, device=net.final_layer.weight.device)
+    packed = pack(net, STORE_PPAD, STORE_PPAD, (n_out + 47) // 48, col_map=col_map, k_in=k_in, final_row_map=rm)
+    packed.n_out = n_out
     return packed
 
 
@@ -288,13 +276,12 @@ def store_apply(packed, a, out):
     _cabi.require_cuda_f32(a, "conditioner inputs")
     L = _cabi.lib()
     a, ap, lda = _cabi.rows(a)
-    d_t, P = packed.store
     if a.shape[1] != packed.k_in:
         raise ValueError("conditioner inputs have {} columns, the packed net expects {}".format(a.shape[1], packed.k_in))
-    assert out.shape == (a.shape[0], d_t * P) and out.stride(1) == 1 and out.is_cuda and out.dtype == torch.float32
+    assert out.shape == (a.shape[0], packed.n_out) and out.stride(1) == 1 and out.is_cuda and out.dtype == torch.float32
     with torch.cuda.device(a.device), _cabi.launch("fc_conditioner_store_apply", a.device):
         rc = L.fc_conditioner_store_apply(ctypes.byref(packed.struct), ap, lda, a.shape[0], out.data_ptr(), out.stride(0),
-                                          d_t, P, _cabi.stream_ptr(a.device))
+                                          packed.n_out, _cabi.stream_ptr(a.device))
     _cabi.check(rc, "fc_conditioner_store_apply")
     return out
 

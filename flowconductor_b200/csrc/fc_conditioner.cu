@@ -101,9 +101,9 @@ struct CondArgs {
   int hand_period;   // every hand_period-th final N tile a row thread hands ALL its features to the bijection warps (0: never)
   float sos_offset;  // sum-of-sigmoids bijection: added to the outputs (autoregressive.py:309: -0.5; conditional.py: 0)
   int affine_activation, affine_inverse;  // affine bijection (FC_SCALE_*, direction)
-  float* params_out;      // CondStore: the final layer's outputs [M][D_t * store_P] instead of a bijection
+  float* params_out;      // CondStore: the final layer's outputs [M][store_n] instead of a bijection
   long long ldp;
-  int store_P;
+  int store_n;
   int32_t* status;
   int32_t* error;  // device word: 0, or the code of the first wait that timed out
 };
@@ -306,8 +306,8 @@ struct CondAffine {  // y = x * scale(raw) + shift and its inverse (coupling.py:
   }
 };
 
-// No bijection: the conditioner's outputs are written out, store_P per 48-column accumulator slot (ResidualNet.forward /
-// MADE.forward as ONE launch, for the bijections that run as element-wise kernels afterwards).  A row thread owns (row, 48
+// No bijection: the conditioner's outputs are written out, output column 96 t + c from column c of final tile t
+// (ResidualNet.forward / MADE.forward as ONE launch, for the bijections that run as element-wise kernels afterwards).  A row thread owns (row, 48
 // columns): stored from there, 32 lanes would write 4 bytes each a row pitch apart (measured: 2.5x slower than the per-layer
 // kernels).  Instead EVERY final tile goes through the shared-memory parameter tile (HAND, period 1; its column stride is
 // padded to 129 words here so that both the row threads' column-wise writes and the row-wise reads below are free of bank
@@ -920,14 +920,12 @@ __global__ void __launch_bounds__(kCondThreads, 1) conditioner_f16x3_kernel(cons
           const long long grow0 = row - (r & 31);
           const int nrows = (int)min((long long)32, a.M - grow0);  // rows of this warp inside the batch (<= 0: none)
           const float* tile_s = hs + (b * (2 * NF * PPAD)) * kPS + rl0;
-          const int P = a.store_P;
 #pragma unroll
           for (int cc = 0; cc < 2 * NF * PPAD; cc += 32) {
             const int c = cc + lane;
-            const int slot = c / PPAD, j = c - slot * PPAD;
-            const int feature = nt * FEATS + slot;
-            const bool live = j < P && feature < a.D_t;
-            float* out = a.params_out + grow0 * a.ldp + (long long)feature * P + j;
+            const int col = nt * (2 * NF * PPAD) + c;
+            const bool live = col < a.store_n;
+            float* out = a.params_out + grow0 * a.ldp + col;
             const float* src = tile_s + c * kPS;
             // eight shared-memory loads in flight, then eight predicated stores (a loop of guarded load-store pairs compiles to
             // one branch region per element with the load latency exposed every time: 120 cycles per element)
@@ -1307,19 +1305,20 @@ extern "C" int fc_conditioner_affine_apply(const fc_conditioner* net, const floa
 }
 
 extern "C" int fc_conditioner_store_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, float* params,
-                                          int64_t params_row_stride, int32_t D_t, int32_t params_per_feature, void* stream) {
-  if (params_per_feature <= 0 || params_per_feature > 48) return FC_ERR_UNSUPPORTED;
+                                          int64_t params_row_stride, int32_t n_out, void* stream) {
+  if (n_out <= 0) return FC_ERR_INVALID_ARGUMENT;
   if (B > 0 && !params) return FC_ERR_INVALID_ARGUMENT;
-  if (D_t > 0 && params_row_stride < (int64_t)D_t * params_per_feature) return FC_ERR_INVALID_ARGUMENT;
+  if (params_row_stride < n_out) return FC_ERR_INVALID_ARGUMENT;
   CondArgs args{};
   fc_cols none{nullptr, 0};
-  int rc = cond_build_args(net, a, lda, B, nullptr, 0, nullptr, 0, nullptr, 0, D_t, none, none, 48, 1, nullptr, args, 1, true);
+  int rc = cond_build_args(net, a, lda, B, nullptr, 0, nullptr, 0, nullptr, 0, (n_out + 47) / 48, none, none, 48, 1, nullptr, args,
+                           1, true);
   if (rc != FC_OK) return rc;
   if (B == 0) return FC_OK;
   args.hand_period = 1;  // every tile leaves through the shared-memory parameter tile
   args.params_out = params;
   args.ldp = params_row_stride;
-  args.store_P = params_per_feature;
+  args.store_n = n_out;
   cudaStream_t st = (cudaStream_t)stream;
   if (net->hidden == 256) return launch_conditioner<CondStore, 48, 2, true>(args, st);
   return launch_conditioner<CondStore, 48, 1, true>(args, st);

@@ -397,13 +397,12 @@ int fc_conditioner_affine_apply(const fc_conditioner* net, const float* a, int64
                                 int32_t accumulate_logabsdet, int32_t D_t, fc_cols tcols, fc_cols ccols, int32_t activation,
                                 int32_t inverse, void* stream);
 /* Same kernel without a bijection: the conditioner's outputs (ResidualNet.forward, flowcon/nn/nets/resnet.py:92-100 /
- * MADE.forward, flowcon/transforms/made.py:274-283) are written to params[B][D_t * params_per_feature] (row stride in floats)
- * in ONE launch, for the bijections that run as element-wise kernels afterwards (fc_linspline_apply, fc_quadspline_apply,
- * fc_cubicspline_apply, fc_sos_apply ...).  Any factorisation D_t * params_per_feature of the final layer's width serves
- * (params_per_feature <= 48); the final layer is packed with 48 accumulator columns per "feature" (packed row j * 48 + i <-
- * output j * params_per_feature + i). */
+ * MADE.forward, flowcon/transforms/made.py:274-283) are written to params[B][n_out] (row stride in floats) in ONE launch, for
+ * the bijections that run as element-wise kernels afterwards (fc_linspline_apply, fc_quadspline_apply, fc_cubicspline_apply,
+ * fc_sos_apply ...).  The final layer is packed without a row map (packed row j <- output j), n_out padded to a multiple of
+ * 96 columns. */
 int fc_conditioner_store_apply(const fc_conditioner* net, const float* a, int64_t lda, int64_t B, float* params,
-                               int64_t params_row_stride, int32_t D_t, int32_t params_per_feature, void* stream);
+                               int64_t params_row_stride, int32_t n_out, void* stream);
 /* Debugging aid: every barrier wait inside the kernel is bounded; if one ever times out the kernel ends early and leaves
  * a non-zero code (wait site + 100 * warp) here.  Synchronises the device.  Not part of the data path. */
 int fc_conditioner_error(int32_t* out);

@@ -332,11 +332,6 @@ def test_affine_layers_run_in_the_fused_conditioner(dev, kind, features, hidden,
                 assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3 and (lad - lb).abs().max() < 5e-2
 
 
-def fcond_store_ok(net):
-    from flowconductor_b200 import conditioner as fcond
-    return fcond.store_layout(net.final_layer.weight.shape[0]) is not None
-
-
 @pytest.mark.parametrize("features", [6, 21, 43, 63])
 @pytest.mark.parametrize("kind", ["coupling_rqs", "maf_rqs", "coupling_affine", "cond_sos", "coupling_quadratic"])
 def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kind, features, monkeypatch):
@@ -362,7 +357,7 @@ def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kin
         want = "fc_conditioner_sos_apply"
     else:
         layer = transforms.PiecewiseQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)
-        want = "fc_conditioner_store_apply" if fcond_store_ok(layer.transform_net) else "fc_linear_apply"
+        want = "fc_conditioner_store_apply"
     layer = layer.to(dev).eval()
     with torch.no_grad():
         for p in layer.parameters():
@@ -384,7 +379,8 @@ def test_feature_counts_that_are_not_multiples_of_four_take_the_kernels(dev, kin
 
 @pytest.mark.parametrize("kind,features,hidden,blocks,rows", [
     ("coupling_quadratic", 64, 256, 2, 3001), ("coupling_linear", 30, 128, 1, 777), ("coupling_cubic", 12, 64, 3, 256),
-    ("maf_quadratic", 16, 256, 2, 4096), ("cond_sos_inverse", 32, 64, 2, 1500), ("maf_linear", 21, 100, 2, 1)])
+    ("maf_quadratic", 16, 256, 2, 4096), ("cond_sos_inverse", 32, 64, 2, 1500), ("maf_linear", 21, 100, 2, 1),
+    ("coupling_quadratic", 26, 128, 2, 500)])  # 13 x 15 = 195 outputs: three tiles, the last one ragged
 def test_whole_conditioner_store_kernel(dev, kind, features, hidden, blocks, rows, monkeypatch):
     """`tensorcore.params` as ONE launch (fc_conditioner_store_apply: ResidualNet.forward resnet.py:92-100 / MADE.forward
     made.py:274-283 with the outputs written out) for the bijections that run as element-wise kernels: against the per-layer
@@ -427,17 +423,6 @@ def test_whole_conditioner_store_kernel(dev, kind, features, hidden, blocks, row
         rel = ((y - b).abs() / b.abs().clamp_min(1.0)).flatten()
         assert torch.quantile(rel, 0.999) < 1e-4 and rel.max() < 5e-2, (kind, float(rel.max()))
         assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3
-
-
-def test_store_layout_wastes_few_accumulator_columns():
-    from flowconductor_b200 import conditioner as fcond
-    assert fcond.store_layout(992) == (32, 31) and fcond.store_layout(480) == (48, 10)
-    assert fcond.store_layout(97) is None  # prime: one output per 48-column slot -> the per-layer kernels
-    for n in range(1, 3000):
-        lay = fcond.store_layout(n)
-        if lay is not None:
-            P, d_t = lay
-            assert P * d_t == n and 24 <= P <= 48
 
 
 def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypatch):
