@@ -255,6 +255,17 @@ template <class Op>
 struct TileBwdWarps<Op, decltype((void)Op::kTileBwdWarps)> {
   static constexpr int value = Op::kTileBwdWarps;
 };
+// Block-size bound of the backward kernel in warps.  ptxas rounds the bound up to a multiple of 128 threads when it sizes the
+// register budget: 17 warps (16 consumers) -> 640 threads -> 96 registers, 16 warps -> 512 threads -> 128 registers.  The
+// sum-of-sigmoids adjoint spills at 96 (0.68 of the copy peak, 0.91 with 128); the spline adjoints prefer the 16th consumer.
+template <class Op, class = void>
+struct TileBwdMaxWarps {
+  static constexpr int value = kTileMaxWarps;
+};
+template <class Op>
+struct TileBwdMaxWarps<Op, decltype((void)Op::kTileBwdMaxWarps)> {
+  static constexpr int value = Op::kTileBwdMaxWarps;
+};
 template <class Op, class = void>
 struct TileCtas {
   static constexpr int value = 2;
@@ -682,7 +693,7 @@ struct TileBwdArgs {
 };
 
 template <class Op>
-__global__ void __launch_bounds__(kTileMaxWarps * 32) tiled_backward_kernel(const TileBwdArgs ta, const Op op) {
+__global__ void __launch_bounds__(TileBwdMaxWarps<Op>::value * 32) tiled_backward_kernel(const TileBwdArgs ta, const Op op) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const LayerBwdArgs& a = ta.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -826,7 +837,7 @@ inline int try_launch_tiled_backward(const LayerBwdArgs& a, const Op& op, int P,
   const int64_t row_bytes = ((int64_t)a.D_t * P + 2 * D + 1) * 4;
   int consumers = env_int("FC_TILE_BWD_WARPS", TileBwdWarps<Op>::value);
   if (consumers < 1) consumers = 1;
-  if (consumers > kTileMaxWarps - 1) consumers = kTileMaxWarps - 1;
+  if (consumers > TileBwdMaxWarps<Op>::value - 1) consumers = TileBwdMaxWarps<Op>::value - 1;
   int ctas_per_sm = env_int("FC_TILE_BWD_CTAS", TileCtas<Op>::value);
   int stages = env_int("FC_TILE_BWD_STAGES", 2);
   int passes = env_int("FC_TILE_BWD_PASSES", 32);

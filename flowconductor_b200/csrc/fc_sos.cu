@@ -13,7 +13,7 @@ namespace fc {
 
 template <int kMB>
 struct SosOpT {
-  static constexpr int kTileBwdWarps = 8;  // the adjoint fits two CTAs of 8 consumer warps (0.71-0.74 of the copy peak; 16 x 1: 0.66)
+  static constexpr int kTileBwdWarps = 8, kTileBwdMaxWarps = 16;  // the adjoint wants 128 registers (fc_pipeline.cuh)
   static constexpr int kMinBlocks = kMB;
   int n;
   float offset;
