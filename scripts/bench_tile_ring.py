@@ -121,7 +121,7 @@ def main():
         for name, fn, nbytes in cs:
             if pat not in name:
                 continue
-            for warps, ctas, stages, passes in itertools.product((8, 12, 16), (1, 2, 3), (2, 3), (2, 8, 32)):
+            for warps, ctas, stages, passes in itertools.product((8, 10, 12, 15, 16), (1, 2), (2, 3), (8, 32)):
                 set_env(**{pre + "WARPS": warps, pre + "CTAS": ctas, pre + "STAGES": stages, pre + "PASSES": passes})
                 med, _ = timeit(fn, warm=2, reps=7)
                 gbs = nbytes / med / 1e6
