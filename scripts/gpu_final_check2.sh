@@ -10,3 +10,6 @@ for f in ("bench_final","bench_cfg4","bench_cfg5","bench_cfg3_train"):
         d=json.loads(open("gpurun_out/%s.json"%f).readline()); print(f, round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), (d.get('roofline') or {}).get('frac'), d['clocks']['sm_mhz'], d['clocks']['reasons'])
     except Exception as e: print(f, "ERR", e)
 PY
+timeout 600 python scripts/bench_kernels.py > gpurun_out/kernel_microbench.jsonl 2> gpurun_out/kernel_microbench.err; echo "microbench rc=$?"
+timeout 600 python bench.py --workload cfg3_train --graph > gpurun_out/bench_cfg3_train_graph.json 2> gpurun_out/bench_cfg3_train_graph.err; echo "cfg3 graph rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_cfg3_train_graph.json').readline()); print('graph', d['value'], d['ms_per_step'])"
