@@ -654,6 +654,20 @@ def run_cfg4(args, wl):
             "gpu_launches": launches, "gpu_launches_by_entry_point": counts, "clocks": clocks, "roofline": roofline,
             "log_likelihood_sum": ll,
         }
+        # the sampling direction (numerical inverse, transforms/no_analytic_inv/base.py:23-83): conditioner outputs from one
+        # fc_conditioner_store_apply per layer, then the safeguarded-Newton inverse kernel; outside the timed region above
+        with torch.no_grad():
+            flow._transform.inverse(x, context=c)
+            torch.cuda.synchronize()
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s3.record()
+            for _ in range(3):
+                flow._transform.inverse(x, context=c)
+            e3.record()
+            torch.cuda.synchronize()
+        ms_inv = s3.elapsed_time(e3) / 3
+        line["sample_direction"] = {"value": B / (ms_inv * 1e-3), "unit": "samples/s per GPU", "ms_per_pass": ms_inv,
+                                    "what": "CompositeTransform.inverse of the same flow over the same rows and contexts, rank 0"}
         if world == 1 and not args.no_eager_baseline:
             line["gpu_eager_baseline"] = gpu_eager_baseline(wl, state, x, c)
         if world == 1 and not args.no_cpu_baseline:
