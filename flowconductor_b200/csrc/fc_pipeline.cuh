@@ -1,6 +1,11 @@
-// fc_pipeline.cuh — TMA-pipelined persistent forward/inverse layer kernel (the fast path of fc_*_apply).
+// fc_pipeline.cuh — TMA-pipelined persistent element-wise layer kernels (the fast paths of fc_*_apply / fc_*_backward).
 //
-// Every warp runs its OWN software pipeline, so there is no CTA-wide synchronisation at all:
+// Two skeletons share the bijections' Op::eval / Op::backward:
+//   * the TILE RING (tiled_apply_kernel / tiled_backward_kernel, further down; round 2, the default): one producer warp per
+//     CTA moves ~50 KB tiles of rows with bulk loads and stores, 8-16 consumer warps evaluate them;
+//   * the PER-WARP RING described next (round 1; FC_TILE=0, or rows too long for a CTA-level tile).
+//
+// Per-warp ring: every warp runs its OWN software pipeline, so there is no CTA-wide synchronisation at all:
 //   * a warp owns a ring of S slots in shared memory; a slot holds `slot_rows` consecutive rows:
 //     their parameters (slot_rows * D_t * P floats, one contiguous block of global memory) and their inputs
 //     (slot_rows * D floats, contiguous too);
