@@ -425,6 +425,35 @@ def test_whole_conditioner_store_kernel(dev, kind, features, hidden, blocks, row
         assert torch.quantile((lad - lb).abs(), 0.99) < 2e-3
 
 
+def test_padded_input_and_store_paths_replay_from_a_cuda_graph(dev):
+    """A 21-feature flow (padded conditioner inputs) of a fused-spline layer, a fused-affine layer and a quadratic-spline layer
+    (store conditioner + element-wise tile ring): `graphs.capture(flow.log_prob)` replays bit for bit what the eager call
+    returns, also on fresh inputs."""
+    from flowconductor_b200 import flows, distributions, graphs
+
+    torch.manual_seed(21)
+    D = 21
+    net = lambda i, o: ResidualNet(i, o, hidden_features=128, num_blocks=2)  # noqa: E731
+    mask = workloads.make_mask(D, "alternating_even")
+    tr = transforms.CompositeTransform([
+        transforms.PiecewiseRationalQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0),
+        transforms.ReversePermutation(D),
+        transforms.AffineCouplingTransform(mask, net),
+        transforms.PiecewiseQuadraticCouplingTransform(mask, net, num_bins=8, tails="linear", tail_bound=3.0)])
+    flow = flows.Flow(tr, distributions.StandardNormal([D])).to(dev).eval()
+    x = torch.randn(2000, D, device=dev)
+    with torch.no_grad():
+        _cabi.STATS.reset()
+        eager = flow.log_prob(x)
+        c = _cabi.STATS.counts
+        assert c.get("fc_conditioner_rqs_apply") == 1 and c.get("fc_conditioner_affine_apply") == 1 \
+            and c.get("fc_conditioner_store_apply") == 1, c
+        lp = graphs.capture(flow.log_prob, x)
+        assert torch.equal(lp(x), eager)
+        x2 = torch.randn(2000, D, device=dev)
+        assert torch.equal(lp(x2), flow.log_prob(x2))
+
+
 def test_narrow_coupling_conditioner_is_padded_to_the_kernel_width(dev, monkeypatch):
     """H = 64 ResidualNet (cfg2_tc_small): zero-padded to 128 at pack time, one fused launch per layer, same numbers as the
     per-layer kernels."""
